@@ -1,0 +1,324 @@
+/*
+ * cerberus_b200.h -- C ABI of the B200-native sliding-window VILO backend.
+ *
+ * This is the drop-in boundary for ONE path of ShuoYangRobotics/Cerberus: the body of
+ * Estimator::optimization() between vector2double() and double2vector()
+ * (reference src/estimator/estimator.cpp:1057-1241), i.e. "build the Ceres problem over the
+ * 11-frame window and run <= NUM_ITERATIONS DENSE_SCHUR/DOGLEG iterations", plus the factor
+ * families it evaluates (the files of src/factor) and the leg-contact preintegration that feeds it
+ * (src/factor/imu_leg_integration_base.cpp, src/legKinematics/A1Kinematics.cpp).
+ *
+ * The reference has no FFI for this path (everything is one C++ process linking Ceres), so the
+ * seam is cut here.  Every struct mirrors, field by field, the data the reference holds at that
+ * seam; the citation next to each field is the reference member it binds to.  Plain pointers and
+ * sizes only; no C++ / torch types.  All floating point is fp64 like the reference.
+ *
+ * Conventions fixed by the reference (kept bit-for-bit in layout):
+ *   pose block        = [px,py,pz,qx,qy,qz,qw]                 estimator.cpp:852-859
+ *   speed-bias block  = [v(3), ba(3), bg(3)]                   estimator.cpp:863-873
+ *   leg-bias block    = [rho1..rho4]                           estimator.cpp:877-880
+ *   feature           = inverse depth of the anchor observation feature_manager.cpp:189
+ *   Eigen dense matrices handed over as-is are COLUMN-major (Eigen default).
+ *   Jacobians returned by the cerb_eval_* entry points are ROW-major rows x global_size with the
+ *   7th column of every pose block zero, exactly like ceres::CostFunction::Evaluate.
+ *
+ * Error model: every entry point returns an int status (CERB_OK == 0); nothing throws across the
+ * ABI.  cerb_last_error() returns a thread-local human readable string for the last failure.
+ * Threading: one CerbHandle per calling thread (the reference calls optimization() from a single
+ * thread, processThread, under mProcess: estimator.cpp:497-498).
+ */
+#ifndef CERBERUS_B200_H
+#define CERBERUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- compile-time sizes (reference src/utils/parameters.h:22-24,93-102) ------------------- */
+#define CERB_WINDOW_SIZE 10        /* WINDOW_SIZE */
+#define CERB_NUM_FRAMES 11         /* WINDOW_SIZE + 1 states */
+#define CERB_NUM_OF_F 1000         /* NUM_OF_F: para_Feature capacity of the reference */
+#define CERB_SIZE_POSE 7
+#define CERB_SIZE_SPEEDBIAS 9
+#define CERB_SIZE_LEG_BIAS 4
+#define CERB_NUM_LEG 4
+#define CERB_NUM_DOF 12
+#define CERB_IL_RES 31             /* RESIDUAL_STATE_SIZE */
+#define CERB_IL_NOISE 46           /* NOISE_SIZE */
+#define CERB_MAX_PRIOR_BLOCKS 16   /* pose0..9, speedbias0, legbias0, ex0, ex1, td = 15 */
+#define CERB_MAX_PRIOR_DIM 96      /* n <= 60+9+4+12+1 = 86 */
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+    CERB_OK = 0,
+    CERB_ERR_BAD_ARGUMENT = 1,   /* null pointer, size over capacity, malformed descriptor */
+    CERB_ERR_NO_DEVICE = 2,      /* CUDA device / driver missing: the product has NO CPU fallback */
+    CERB_ERR_CUDA = 3,           /* a CUDA runtime call failed */
+    CERB_ERR_NON_FINITE = 4      /* a window produced a non-finite cost (reported per window too) */
+};
+
+/* CerbSolveReport.termination: what ceres::Solver::Summary::termination_type would say. */
+enum {
+    CERB_TERM_CONVERGENCE = 0,   /* gradient / parameter / function tolerance reached */
+    CERB_TERM_NO_CONVERGENCE = 1,/* max_num_iterations reached */
+    CERB_TERM_FAILURE = 2        /* too many consecutive invalid steps / non-finite */
+};
+
+/* Kinds of parameter block a marginalization prior can keep (estimator.cpp:1253-1348). */
+enum {
+    CERB_BLOCK_POSE = 0,        /* para_Pose[index]       size 7 (local 6) */
+    CERB_BLOCK_SPEEDBIAS = 1,   /* para_SpeedBias[index]  size 9 */
+    CERB_BLOCK_LEGBIAS = 2,     /* para_LegBias[index]    size 4 */
+    CERB_BLOCK_EX_POSE = 3,     /* para_Ex_Pose[index]    size 7 (local 6) */
+    CERB_BLOCK_TD = 4           /* para_Td[0]             size 1 */
+};
+
+/* Projection factor families (src/factor/projection*Factor.h). */
+enum {
+    CERB_PROJ_TWO_FRAME_ONE_CAM = 0, /* ProjectionTwoFrameOneCamFactor <2,7,7,7,1,1>   */
+    CERB_PROJ_TWO_FRAME_TWO_CAM = 1, /* ProjectionTwoFrameTwoCamFactor <2,7,7,7,7,1,1> */
+    CERB_PROJ_ONE_FRAME_TWO_CAM = 2  /* ProjectionOneFrameTwoCamFactor <2,7,7,1,1>     */
+};
+
+/* ---- solver configuration ------------------------------------------------------------------
+ * Globals of the reference that parameterise optimization() (src/utils/parameters.h:27-89,
+ * values from config/a1_config/hardware_a1_vilo_config.yaml) + the Ceres 1.14 options the
+ * reference leaves at their defaults (estimator.cpp:1221-1236). */
+typedef struct CerbSolverConfig {
+    int32_t device;               /* CUDA device ordinal */
+    int32_t max_batch;            /* capacity: windows per batch call */
+    int32_t max_features;         /* capacity: features per window (<= CERB_NUM_OF_F) */
+    int32_t max_obs;              /* capacity: observations per window (sum of track lengths) */
+    int32_t max_num_iterations;   /* NUM_ITERATIONS (yaml max_num_iterations, 12) */
+    int32_t optimize_leg_bias;    /* OPTIMIZE_LEG_BIAS; 0 => para_LegBias constant (estimator.cpp:1074) */
+    double g[3];                  /* G = (0,0,g_norm)  parameters.cpp:21,130 */
+    double visual_sqrt_info;      /* FOCAL_LENGTH/1.5 = 460/1.5, sqrt_info = this * I2 (estimator.cpp:124) */
+    double huber_delta;           /* ceres::HuberLoss(1.0) (estimator.cpp:1062) */
+    /* ceres::Solver::Options defaults of Ceres 1.14.0 (not overridden by the reference) */
+    double initial_trust_region_radius; /* 1e4  */
+    double max_trust_region_radius;     /* 1e16 */
+    double min_trust_region_radius;     /* 1e-32 */
+    double min_relative_decrease;       /* 1e-3 */
+    double function_tolerance;          /* 1e-6 */
+    double gradient_tolerance;          /* 1e-10 */
+    double parameter_tolerance;         /* 1e-8 */
+} CerbSolverConfig;
+
+/* ---- leg-contact preintegration result: IMULegIntegrationBase public members
+ * (src/factor/imu_leg_integration_base.h:73-85) consumed by IMULegFactor::Evaluate. */
+typedef struct CerbIMULegPreint {
+    double sum_dt;                 /* sum_dt; factor skipped if > 10.0 (estimator.cpp:1119) */
+    double delta_p[3];             /* delta_p  (alpha) */
+    double delta_q[4];             /* delta_q  (gamma), Eigen coeffs order x,y,z,w */
+    double delta_v[3];             /* delta_v  (beta)  */
+    double delta_epsilon[12];      /* delta_epsilon[leg][3] */
+    double linearized_ba[3];
+    double linearized_bg[3];
+    double linearized_rho[4];
+    double jacobian[CERB_IL_RES * CERB_IL_RES];   /* jacobian,   31x31 column-major */
+    double covariance[CERB_IL_RES * CERB_IL_RES]; /* covariance, 31x31 column-major (symmetric) */
+} CerbIMULegPreint;
+
+/* ---- one observation of a feature: FeaturePerFrame (src/featureTracker/feature_manager.h:28-59) */
+typedef struct CerbObservation {
+    double point[2];        /* point.x, point.y      (z == 1) */
+    double velocity[2];     /* velocity              */
+    double pointRight[2];   /* pointRight.x, .y      (valid iff is_stereo) */
+    double velocityRight[2];
+    double cur_td;          /* cur_td */
+    int32_t is_stereo;      /* is_stereo */
+    int32_t reserved;
+} CerbObservation;
+
+/* ---- one tracked feature: FeaturePerId (feature_manager.h:61-81), only those with
+ * used_num >= 4 are passed (estimator.cpp:1178); index in the array == feature_index. */
+typedef struct CerbFeature {
+    int32_t start_frame;    /* start_frame = anchor frame imu_i */
+    int32_t n_obs;          /* feature_per_frame.size(); frames start_frame .. start_frame+n_obs-1 */
+    int32_t obs_offset;     /* first CerbObservation of this feature in CerbWindowDesc.obs */
+    int32_t reserved;
+} CerbFeature;
+
+/* ---- marginalization prior: MarginalizationInfo members read by MarginalizationFactor::Evaluate
+ * (src/factor/marginalization_factor.cpp:347-395) + last_marginalization_parameter_blocks. */
+typedef struct CerbPrior {
+    int32_t valid;                                /* last_marginalization_info && ->valid */
+    int32_t n;                                    /* MarginalizationInfo::n */
+    int32_t num_blocks;                           /* keep_block_size.size() */
+    int32_t reserved;
+    int32_t block_kind[CERB_MAX_PRIOR_BLOCKS];    /* which para_* array the kept block address maps to */
+    int32_t block_index[CERB_MAX_PRIOR_BLOCKS];   /* index into that array */
+    int32_t block_col[CERB_MAX_PRIOR_BLOCKS];     /* keep_block_idx[i] - m */
+    double block_x0[CERB_MAX_PRIOR_BLOCKS][7];    /* keep_block_data[i] (global size, unused tail 0) */
+    const double *linearized_jacobians;           /* n x n, column-major (Eigen::MatrixXd) */
+    const double *linearized_residuals;           /* n */
+} CerbPrior;
+
+/* ---- everything optimization() reads besides the para_* arrays */
+typedef struct CerbWindowDesc {
+    int32_t n_features;
+    int32_t n_obs;
+    const CerbFeature *features;          /* [n_features] */
+    const CerbObservation *obs;           /* [n_obs] */
+    const CerbIMULegPreint *preint;       /* [CERB_WINDOW_SIZE]; preint[i] = il_pre_integrations[i+1] (frames i -> i+1) */
+    CerbPrior prior;
+    int32_t extrinsic_open;               /* 1 => para_Ex_Pose free (openExEstimation latch, estimator.cpp:1091-1100) */
+    int32_t td_open;                      /* 1 => para_Td free (ESTIMATE_TD && |Vs[0]| >= 0.2, estimator.cpp:1104) */
+} CerbWindowDesc;
+
+/* ---- the para_* arrays exactly as laid out in estimator.h:189-196; in/out */
+typedef struct CerbWindowState {
+    double para_Pose[CERB_NUM_FRAMES][CERB_SIZE_POSE];
+    double para_SpeedBias[CERB_NUM_FRAMES][CERB_SIZE_SPEEDBIAS];
+    double para_LegBias[CERB_NUM_FRAMES][CERB_SIZE_LEG_BIAS];
+    double para_Ex_Pose[2][CERB_SIZE_POSE];
+    double para_Td[1];
+    double reserved;
+    double *para_Feature;                 /* [n_features] */
+} CerbWindowState;
+
+/* ---- what ceres::Solver::Summary would have said (ignored by the reference, estimator.cpp:1235) */
+typedef struct CerbSolveReport {
+    int32_t iterations;            /* trust-region iterations performed (successful + unsuccessful) */
+    int32_t num_successful_steps;
+    int32_t termination;           /* CERB_TERM_* */
+    int32_t status;                /* CERB_OK or CERB_ERR_NON_FINITE for this window */
+    double initial_cost;
+    double final_cost;
+} CerbSolveReport;
+
+/* ---- raw IMU + leg sample stream of one inter-frame interval, as pushed through
+ * IMULegIntegrationBase::push_back (imu_leg_integration_base.cpp:49-59). */
+typedef struct CerbIMULegSample {
+    double dt;
+    double acc[3];
+    double gyr[3];
+    double phi[CERB_NUM_DOF];    /* joint angles */
+    double dphi[CERB_NUM_DOF];   /* joint velocities */
+    double c[CERB_NUM_LEG];      /* contact flags (sensor type 0/1) or foot force (type 2) */
+} CerbIMULegSample;
+
+/* Noise / kinematics globals read by IMULegIntegrationBase (parameters.h:59-75, estimator.cpp:140-171). */
+typedef struct CerbPreintConfig {
+    double acc_n, acc_n_z, gyr_n, acc_w, gyr_w;      /* ACC_N, ACC_N_Z, GYR_N, ACC_W, GYR_W */
+    double phi_n, dphi_n;                            /* PHI_N (joint_angle_n), DPHI_N */
+    double rho_c_n, rho_nc_n;                        /* RHO_C_N, RHO_NC_N */
+    double v_n_min_xy, v_n_min_z, v_n_min, v_n_max;  /* V_N_* */
+    double v_n_force_thres_ratio, v_n_term1_steep, v_n_term2_var_rescale, v_n_term3_distance_rescale;
+    int32_t contact_sensor_type;                     /* CONTACT_SENSOR_TYPE */
+    int32_t reserved;
+    double rho_fix[CERB_NUM_LEG][4];                 /* rho_fix_list[leg] = [ox, oy, d, lt] */
+    double p_br[3];                                  /* p_br */
+    double R_br[9];                                  /* R_br, row-major 3x3 */
+} CerbPreintConfig;
+
+/* One interval to preintegrate: constructor arguments (imu_leg_integration_base.cpp:7-47) + samples. */
+typedef struct CerbPreintJob {
+    double acc_0[3], gyr_0[3];
+    double phi_0[CERB_NUM_DOF], dphi_0[CERB_NUM_DOF], c_0[CERB_NUM_LEG];
+    double linearized_ba[3], linearized_bg[3], linearized_rho[4];
+    int32_t n_samples;
+    int32_t reserved;
+    const CerbIMULegSample *samples;   /* [n_samples] */
+} CerbPreintJob;
+
+typedef struct CerbHandle CerbHandle;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+void cerb_default_config(CerbSolverConfig *cfg);            /* A1 yaml + Ceres 1.14 defaults */
+void cerb_default_preint_config(CerbPreintConfig *cfg);     /* A1 yaml + A1 geometry */
+int cerb_create(const CerbSolverConfig *cfg, CerbHandle **out);
+void cerb_destroy(CerbHandle *h);
+const char *cerb_last_error(void);
+const char *cerb_version(void);
+
+/* ---- the hot path: replaces estimator.cpp:1059-1236 ------------------------------------------
+ * Host buffers in, host buffers out (the call a drop-in Estimator::optimization() makes).
+ * H2D pack, solve, D2H happen inside; blocking. */
+int cerb_solve_window(CerbHandle *h, const CerbWindowDesc *desc, CerbWindowState *state,
+                      CerbSolveReport *report);
+int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs,
+                     CerbWindowState *states, CerbSolveReport *reports);
+
+/* Device-resident variant used for batched replay / benchmarking: upload once, solve many times.
+ * cerb_batch_upload packs and copies descriptors + initial states to HBM and keeps a pristine
+ * device copy of the initial states; cerb_batch_solve_resident restores the states from that copy
+ * and launches the solve on the handle's stream (asynchronous; *kernel_ms, if non-null, receives
+ * the CUDA-event time of the previous completed resident solve); cerb_batch_download syncs and
+ * copies states/reports back. */
+int cerb_batch_upload(CerbHandle *h, int32_t n, const CerbWindowDesc *descs,
+                      const CerbWindowState *states);
+int cerb_batch_solve_resident(CerbHandle *h);
+int cerb_batch_download(CerbHandle *h, CerbWindowState *states, CerbSolveReport *reports);
+int cerb_sync(CerbHandle *h);
+/* CUDA-event milliseconds of the last completed solve launch sequence on the handle's stream and
+ * the number of kernels it launched. */
+int cerb_last_solve_stats(CerbHandle *h, double *kernel_ms, int32_t *kernel_launches);
+/* Debug/parity probe: linearisation of window `w` of the resident batch at its CURRENT state,
+ * exactly what the first solver iteration sees: cost, gradient (tangent space, order
+ * [pose0..10 (66) | ex0, ex1 (12) | speedbias0..10 (99) | legbias0..10 (44) | features]),
+ * the Schur-reduced 221x221 system is not exposed, only the gradient and diag(J^T J). */
+int cerb_debug_linearize(CerbHandle *h, int32_t w, double *cost, double *gradient, double *jtj_diag,
+                         int32_t n_alloc);
+
+/* ---- one kernel per factor family: batched Evaluate (replaces the virtual
+ * ceres::CostFunction::Evaluate calls; also what marginalization / outlier rejection need).
+ * All arrays are host pointers, n factors, tightly packed. Outputs may be NULL to skip. ------- */
+
+/* Projection factors (projectionTwoFrameOneCamFactor.cpp:43-150, ...TwoCam...:43-166,
+ * projectionOneFrameTwoCamFactor.cpp:42-134).
+ *   kind        CERB_PROJ_*
+ *   pose_i/j    [n][7] (ignored for ONE_FRAME_TWO_CAM), ex0/ex1 [n][7] (ex1 ignored for ONE_CAM)
+ *   inv_dep, td [n]
+ *   pts_i,pts_j [n][3]; vel_i, vel_j [n][2]; td_i, td_j [n]
+ *   residuals   [n][2]
+ *   jacobians   [n][J] row-major blocks concatenated in the reference's parameter-block order:
+ *               ONE_CAM: 2x7,2x7,2x7,2x1,2x1 (J=46); TWO_CAM: 2x7 x4,2x1,2x1 (J=60);
+ *               ONE_FRAME: 2x7,2x7,2x1,2x1 (J=32). */
+int cerb_eval_projection(CerbHandle *h, int32_t kind, int32_t n, const double *pose_i,
+                         const double *pose_j, const double *ex0, const double *ex1,
+                         const double *inv_dep, const double *td, const double *pts_i,
+                         const double *pts_j, const double *vel_i, const double *vel_j,
+                         const double *td_i, const double *td_j, double *residuals,
+                         double *jacobians);
+
+/* IMULegFactor::Evaluate (imu_leg_factor.cpp:173-386), <31,7,9,4,7,9,4>.
+ *   params [n][40] = pose_i(7) speedbias_i(9) legbias_i(4) pose_j(7) speedbias_j(9) legbias_j(4)
+ *   residuals [n][31]; jacobians [n][31*40] row-major blocks 31x7,31x9,31x4,31x7,31x9,31x4;
+ *   sqrt_info [n][31*31] row-major (the upper-triangular LLT(cov^-1).matrixL().transpose()). */
+int cerb_eval_imu_leg(CerbHandle *h, int32_t n, const CerbIMULegPreint *preint,
+                      const double *params, double *residuals, double *jacobians,
+                      double *sqrt_info);
+
+/* MarginalizationFactor::Evaluate (marginalization_factor.cpp:347-395) for one prior at one state:
+ * residuals [n]; jacobians: for each kept block b, n x global_size(b) row-major, concatenated. */
+int cerb_eval_prior(CerbHandle *h, const CerbPrior *prior, const CerbWindowState *state,
+                    double *residuals, double *jacobians);
+
+/* ---- leg-contact preintegration on device (IMULegIntegrationBase::push_back loop,
+ * imu_leg_integration_base.cpp:49-59,88-470): n independent intervals. */
+int cerb_preintegrate_batch(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n,
+                            const CerbPreintJob *jobs, CerbIMULegPreint *out);
+
+/* A1 leg kinematics (src/legKinematics/A1Kinematics.cpp:7-40), n legs:
+ *   q [n][3], rho_opt [n] (lc), rho_fix [n][4];
+ *   fk [n][3]; jac [n][9] column-major; dfk_drho [n][3]; dJ_dq [n][27] col-major 9x3; dJ_drho [n][9].
+ * Any output may be NULL. */
+int cerb_a1_kinematics(CerbHandle *h, int32_t n, const double *q, const double *rho_opt,
+                       const double *rho_fix, double *fk, double *jac, double *dfk_drho,
+                       double *dJ_dq, double *dJ_drho);
+
+/* ---- host-side helpers that stay on the CPU in the reference too ---------------------------- */
+/* Gauge re-anchoring of Estimator::double2vector (estimator.cpp:903-957): rotates the solved
+ * window by the yaw difference of frame 0 and re-anchors its position.  before/after are the
+ * para_* arrays at vector2double() time and after the solve; writes Ps[11][3], Rs[11][9]
+ * (row-major), Vs[11][3]. */
+void cerb_double2vector(const CerbWindowState *before, const CerbWindowState *after, double *Ps,
+                        double *Rs, double *Vs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CERBERUS_B200_H */

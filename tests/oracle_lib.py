@@ -1,0 +1,112 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE (the CPU restatement of the reference).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+from cerberus_b200 import abi
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "oracle")])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_ROOT, "oracle", "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        sizes = (C.c_int * 16)()
+        k = _LIB.oracle_abi_sizes(sizes, 16)
+        got = [sizes[i] for i in range(k)]
+        want = [C.sizeof(s) for s in abi.ABI_STRUCTS]
+        assert got == want, f"ABI struct size mismatch oracle={got} python={want}"
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(abi.c_dp)
+
+
+class OracleBackend:
+    """Implements the synth `backend` protocol and the solve/eval entry points with the CPU oracle."""
+
+    def __init__(self, cfg=None):
+        self.cfg = cfg or abi.default_config()
+        self.lib = lib()
+
+    def preintegrate(self, pcfg, jobs, n):
+        out = np.zeros(n, dtype=abi.preint_dtype)
+        rc = self.lib.oracle_preintegrate(C.byref(pcfg), n, jobs, out.ctypes.data_as(C.POINTER(abi.IMULegPreint)))
+        assert rc == 0
+        return out
+
+    def marginalize(self, cfg, src, dst, margin_old=True):
+        for w in range(src.n):
+            pr = dst.descs[w].prior
+            J, r = dst.prior_J[w], dst.prior_r[w]
+            rc = self.lib.oracle_marginalize(C.byref(cfg), C.byref(src.descs[w]), C.byref(src.states[w]), 1 if margin_old else 0,
+                                             C.byref(pr), _p(J), _p(r))
+            assert rc == 0
+
+    def solve_batch(self, batch, nthreads=1, cfg=None):
+        cfg = cfg or self.cfg
+        rc = self.lib.oracle_solve_batch(C.byref(cfg), batch.n, batch.descs, batch.states, batch.reports, nthreads)
+        assert rc == 0
+        return batch.report_array().copy()
+
+    def solve_window(self, batch, w, want_probe=False, cfg=None):
+        cfg = cfg or self.cfg
+        nf = batch.descs[w].n_features
+        g = np.zeros(abi.NUM_REDUCED + nf)
+        d = np.zeros(abi.NUM_REDUCED + nf)
+        rc = self.lib.oracle_solve_window(C.byref(cfg), C.byref(batch.descs[w]), C.byref(batch.states[w]), C.byref(batch.reports[w]),
+                                          _p(g) if want_probe else None, _p(d) if want_probe else None, g.size)
+        assert rc == 0
+        return (g, d) if want_probe else None
+
+    def eval_projection(self, kind, pose_i, pose_j, ex0, ex1, inv_dep, td, pts_i, pts_j, vel_i, vel_j, td_i, td_j, sqrt_info=460.0 / 1.5, want_jac=True):
+        n = inv_dep.shape[0]
+        res = np.zeros((n, 2))
+        jac = np.zeros((n, abi.PROJ_JAC_SIZE[kind])) if want_jac else None
+        self.lib.oracle_eval_projection.argtypes = [C.c_int, C.c_int, C.c_double] + [abi.c_dp] * 14
+        rc = self.lib.oracle_eval_projection(kind, n, sqrt_info, _p(pose_i), _p(pose_j), _p(ex0), _p(ex1), _p(inv_dep), _p(td), _p(pts_i), _p(pts_j),
+                                             _p(vel_i), _p(vel_j), _p(td_i), _p(td_j), _p(res), _p(jac))
+        assert rc == 0
+        return res, jac
+
+    def eval_imu_leg(self, preint, params, g=(0.0, 0.0, 9.805), want_jac=True):
+        n = params.shape[0]
+        res = np.zeros((n, 31))
+        jac = np.zeros((n, 31 * 40)) if want_jac else None
+        si = np.zeros((n, 961))
+        garr = np.array(g, dtype=np.float64)
+        rc = self.lib.oracle_eval_imu_leg(n, _p(garr), preint.ctypes.data_as(C.POINTER(abi.IMULegPreint)), _p(params), _p(res), _p(jac), _p(si))
+        assert rc == 0
+        return res, jac, si
+
+    def eval_prior(self, prior, state, n_cols):
+        res = np.zeros(prior.n)
+        jac = np.zeros(prior.n * n_cols)
+        rc = self.lib.oracle_eval_prior(C.byref(prior), C.byref(state), _p(res), _p(jac))
+        assert rc == 0
+        return res, jac
+
+    def a1_kinematics(self, q, rho_opt, rho_fix):
+        n = q.shape[0]
+        fk, jac, dfk, djq, djr = np.zeros((n, 3)), np.zeros((n, 9)), np.zeros((n, 3)), np.zeros((n, 27)), np.zeros((n, 9))
+        rc = self.lib.oracle_a1_kinematics(n, _p(q), _p(rho_opt), _p(rho_fix), _p(fk), _p(jac), _p(dfk), _p(djq), _p(djr))
+        assert rc == 0
+        return fk, jac, dfk, djq, djr
+
+    def double2vector(self, before_state, after_state):
+        Ps, Rs, Vs = np.zeros((11, 3)), np.zeros((11, 3, 3)), np.zeros((11, 3))
+        self.lib.oracle_double2vector(C.byref(before_state), C.byref(after_state), _p(Ps), _p(Rs), _p(Vs))
+        return Ps, Rs, Vs
