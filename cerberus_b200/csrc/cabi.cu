@@ -1,0 +1,547 @@
+// cabi.cu -- implementation of the C ABI of include/cerberus_b200.h on top of the sm_100a kernels.
+// Host side only packs the reference-shaped descriptors (AoS, Eigen column-major) into the device
+// layout (planar observations, compact preintegration records), moves them through pinned staging
+// buffers on the handle's stream and launches kernels.  There is no CPU compute path: if no CUDA
+// device is present cerb_create fails with CERB_ERR_NO_DEVICE.
+#include "../../include/cerberus_b200.h"
+#include "solve_kernel.cuh"
+#include "preint_kernel.cuh"
+#include <string>
+#include <vector>
+#include <thread>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+
+using namespace cerb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t e_ = (expr);                                                                               \
+        if (e_ != cudaSuccess) return fail(CERB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T> static cudaError_t dmalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
+template <typename T> static cudaError_t hmalloc(T **p, size_t n) { return cudaMallocHost((void **)p, n * sizeof(T)); }
+
+struct CerbHandle {
+    CerbSolverConfig cfg;
+    int sm_count = 0, grid = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_pending = false;
+    double last_ms = 0; int last_launches = 0;
+    int B = 0, F = 0, O = 0;          // capacities
+    int n = 0;                        // windows currently resident
+    // device buffers
+    int *d_nfeat = nullptr, *d_fstart = nullptr, *d_fnobs = nullptr, *d_foff = nullptr, *d_flags = nullptr, *d_stereo = nullptr, *d_pmeta = nullptr, *d_repi = nullptr;
+    double *d_obs = nullptr, *d_pre = nullptr, *d_sinfo = nullptr, *d_pJ = nullptr, *d_pr = nullptr, *d_px0 = nullptr, *d_pHp = nullptr;
+    double *d_state = nullptr, *d_state0 = nullptr, *d_lam = nullptr, *d_lam0 = nullptr, *d_repd = nullptr, *d_ws = nullptr, *d_dbg = nullptr, *d_G = nullptr;
+    // pinned staging
+    int *h_nfeat = nullptr, *h_fstart = nullptr, *h_fnobs = nullptr, *h_foff = nullptr, *h_flags = nullptr, *h_stereo = nullptr, *h_pmeta = nullptr, *h_repi = nullptr;
+    double *h_obs = nullptr, *h_pre = nullptr, *h_pJ = nullptr, *h_pr = nullptr, *h_px0 = nullptr, *h_state = nullptr, *h_lam = nullptr, *h_repd = nullptr, *h_dbg = nullptr;
+    long ws_stride = 0;
+    size_t smem_bytes = 0;
+};
+
+extern "C" {
+
+const char *cerb_last_error(void) { return g_err.c_str(); }
+const char *cerb_version(void) {
+#if defined(CERB_CUSIM)
+    return "cerberus_b200 0.1 (cusim test build)";
+#else
+    return "cerberus_b200 0.1 (sm_100a)";
+#endif
+}
+
+void cerb_default_config(CerbSolverConfig *c) {
+    std::memset(c, 0, sizeof(*c));
+    c->device = 0; c->max_batch = 1024; c->max_features = 160; c->max_obs = 160 * CERB_NUM_FRAMES;
+    c->max_num_iterations = 12; c->optimize_leg_bias = 1;
+    c->g[0] = 0; c->g[1] = 0; c->g[2] = 9.805;
+    c->visual_sqrt_info = 460.0 / 1.5; c->huber_delta = 1.0;
+    c->initial_trust_region_radius = 1e4; c->max_trust_region_radius = 1e16; c->min_trust_region_radius = 1e-32;
+    c->min_relative_decrease = 1e-3; c->function_tolerance = 1e-6; c->gradient_tolerance = 1e-10; c->parameter_tolerance = 1e-8;
+}
+
+void cerb_default_preint_config(CerbPreintConfig *p) {
+    std::memset(p, 0, sizeof(*p));
+    p->acc_n = 0.9; p->acc_n_z = 2.5; p->gyr_n = 0.05; p->acc_w = 0.0004; p->gyr_w = 0.0002;
+    p->phi_n = 1e-5; p->dphi_n = 1e-5; p->rho_c_n = 1e-8; p->rho_nc_n = 1e-11;
+    p->v_n_min_xy = 1e-3; p->v_n_min_z = 5e-3; p->v_n_min = 5e-3; p->v_n_max = 900.0;
+    p->v_n_force_thres_ratio = 0.8; p->v_n_term1_steep = 10; p->v_n_term2_var_rescale = 1e-6; p->v_n_term3_distance_rescale = 1e-3;
+    p->contact_sensor_type = 0;
+    const double ox[4] = {0.1805, 0.1805, -0.1805, -0.1805}, oy[4] = {0.047, -0.047, 0.047, -0.047}, d[4] = {0.0838, -0.0838, 0.0838, -0.0838};
+    for (int l = 0; l < 4; l++) { p->rho_fix[l][0] = ox[l]; p->rho_fix[l][1] = oy[l]; p->rho_fix[l][2] = d[l]; p->rho_fix[l][3] = 0.21; }
+    p->R_br[0] = p->R_br[4] = p->R_br[8] = 1.0;
+}
+
+
+int cerb_create(const CerbSolverConfig *cfg, CerbHandle **out) {
+    if (!cfg || !out) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_create: null argument");
+    if (cfg->max_batch < 1 || cfg->max_features < 1 || cfg->max_features > CERB_NUM_OF_F || cfg->max_obs < 1)
+        return fail(CERB_ERR_BAD_ARGUMENT, "cerb_create: bad capacities");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device)
+        return fail(CERB_ERR_NO_DEVICE, "cerb_create: no CUDA device (this library has no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    CerbHandle *h = new CerbHandle();
+    h->cfg = *cfg; h->sm_count = prop.multiProcessorCount;
+    h->B = cfg->max_batch; h->F = cfg->max_features; h->O = cfg->max_obs;
+    h->grid = std::min(h->B, h->sm_count);
+    h->smem_bytes = (size_t)SMEM_DOUBLES * sizeof(double);
+    if (h->smem_bytes > prop.sharedMemPerBlockOptin) { delete h; return fail(CERB_ERR_CUDA, "solve kernel needs more shared memory than the device offers"); }
+    CUDA_TRY(cudaFuncSetAttribute(vilo_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    CUDA_TRY(cudaStreamCreate(&h->stream));
+    CUDA_TRY(cudaEventCreate(&h->ev0)); CUDA_TRY(cudaEventCreate(&h->ev1));
+    const size_t B = h->B, F = h->F, O = h->O;
+    h->ws_stride = ws_size(h->F);
+    CUDA_TRY(dmalloc(&h->d_nfeat, B)); CUDA_TRY(dmalloc(&h->d_fstart, B * F)); CUDA_TRY(dmalloc(&h->d_fnobs, B * F)); CUDA_TRY(dmalloc(&h->d_foff, B * F));
+    CUDA_TRY(dmalloc(&h->d_flags, B)); CUDA_TRY(dmalloc(&h->d_stereo, B * O)); CUDA_TRY(dmalloc(&h->d_pmeta, B * PRIOR_META_STRIDE)); CUDA_TRY(dmalloc(&h->d_repi, B * 4));
+    CUDA_TRY(dmalloc(&h->d_obs, B * NOBS_PLANES * O)); CUDA_TRY(dmalloc(&h->d_pre, B * 10 * PRE_STRIDE)); CUDA_TRY(dmalloc(&h->d_sinfo, B * 10 * 961));
+    CUDA_TRY(dmalloc(&h->d_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(dmalloc(&h->d_pr, B * PRIOR_LD)); CUDA_TRY(dmalloc(&h->d_px0, B * 16 * 7)); CUDA_TRY(dmalloc(&h->d_pHp, B * PRIOR_LD * PRIOR_LD));
+    CUDA_TRY(dmalloc(&h->d_state, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_state0, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_lam, B * F)); CUDA_TRY(dmalloc(&h->d_lam0, B * F));
+    CUDA_TRY(dmalloc(&h->d_repd, B * 2)); CUDA_TRY(dmalloc(&h->d_ws, (size_t)h->grid * h->ws_stride)); CUDA_TRY(dmalloc(&h->d_dbg, 2 * (NR + F) + 8)); CUDA_TRY(dmalloc(&h->d_G, 4));
+    CUDA_TRY(hmalloc(&h->h_nfeat, B)); CUDA_TRY(hmalloc(&h->h_fstart, B * F)); CUDA_TRY(hmalloc(&h->h_fnobs, B * F)); CUDA_TRY(hmalloc(&h->h_foff, B * F));
+    CUDA_TRY(hmalloc(&h->h_flags, B)); CUDA_TRY(hmalloc(&h->h_stereo, B * O)); CUDA_TRY(hmalloc(&h->h_pmeta, B * PRIOR_META_STRIDE)); CUDA_TRY(hmalloc(&h->h_repi, B * 4));
+    CUDA_TRY(hmalloc(&h->h_obs, B * NOBS_PLANES * O)); CUDA_TRY(hmalloc(&h->h_pre, B * 10 * PRE_STRIDE));
+    CUDA_TRY(hmalloc(&h->h_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_pr, B * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_px0, B * 16 * 7));
+    CUDA_TRY(hmalloc(&h->h_state, B * ST_STRIDE)); CUDA_TRY(hmalloc(&h->h_lam, B * F)); CUDA_TRY(hmalloc(&h->h_repd, B * 2)); CUDA_TRY(hmalloc(&h->h_dbg, 2 * (NR + F) + 8));
+    CUDA_TRY(cudaMemcpy(h->d_G, cfg->g, 3 * sizeof(double), cudaMemcpyHostToDevice));
+    *out = h;
+    return CERB_OK;
+}
+
+void cerb_destroy(CerbHandle *h) {
+    if (!h) return;
+    cudaStreamSynchronize(h->stream);
+    void *dev[] = {h->d_nfeat, h->d_fstart, h->d_fnobs, h->d_foff, h->d_flags, h->d_stereo, h->d_pmeta, h->d_repi, h->d_obs, h->d_pre, h->d_sinfo, h->d_pJ, h->d_pr,
+                   h->d_px0, h->d_pHp, h->d_state, h->d_state0, h->d_lam, h->d_lam0, h->d_repd, h->d_ws, h->d_dbg, h->d_G};
+    for (void *p : dev) if (p) cudaFree(p);
+    void *hst[] = {h->h_nfeat, h->h_fstart, h->h_fnobs, h->h_foff, h->h_flags, h->h_stereo, h->h_pmeta, h->h_repi, h->h_obs, h->h_pre, h->h_pJ, h->h_pr, h->h_px0,
+                   h->h_state, h->h_lam, h->h_repd, h->h_dbg};
+    for (void *p : hst) if (p) cudaFreeHost(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+}  // extern "C"
+
+// ---- host packing ---------------------------------------------------------------------------------------------
+static void pack_preint(const CerbIMULegPreint &p, double *o) {
+    o[PRE_SUM_DT] = p.sum_dt;
+    for (int k = 0; k < 3; k++) { o[PRE_DP + k] = p.delta_p[k]; o[PRE_DV + k] = p.delta_v[k]; o[PRE_BA + k] = p.linearized_ba[k]; o[PRE_BG + k] = p.linearized_bg[k]; }
+    for (int k = 0; k < 4; k++) { o[PRE_DQ + k] = p.delta_q[k]; o[PRE_RHO + k] = p.linearized_rho[k]; }
+    for (int k = 0; k < 12; k++) o[PRE_DEPS + k] = p.delta_epsilon[k];
+    auto J = [&](int r, int c) { return p.jacobian[c * 31 + r]; };   // column-major source
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+        o[PRE_DP_DBA + 3 * a + b] = J(ILO_P + a, ILO_BA + b); o[PRE_DP_DBG + 3 * a + b] = J(ILO_P + a, ILO_BG + b);
+        o[PRE_DQ_DBG + 3 * a + b] = J(ILO_R + a, ILO_BG + b);
+        o[PRE_DV_DBA + 3 * a + b] = J(ILO_V + a, ILO_BA + b); o[PRE_DV_DBG + 3 * a + b] = J(ILO_V + a, ILO_BG + b);
+        for (int k = 0; k < 4; k++) o[PRE_DEP_DBG + 9 * k + 3 * a + b] = J(ILO_EPS1 + 3 * k + a, ILO_BG + b);
+    }
+    for (int k = 0; k < 4; k++) for (int a = 0; a < 3; a++) o[PRE_DEP_DRHO + 3 * k + a] = J(ILO_EPS1 + 3 * k + a, ILO_RHO1 + k);
+    for (int r = 0; r < 31; r++) for (int c = 0; c < 31; c++) o[PRE_INFO + r * 31 + c] = p.covariance[c * 31 + r];
+}
+
+static int pack_prior(const CerbPrior &pr, int *meta, double *J, double *r, double *x0) {
+    std::memset(meta, 0, PRIOR_META_STRIDE * sizeof(int));
+    if (!pr.valid) return CERB_OK;
+    if (pr.n < 1 || pr.n > CERB_MAX_PRIOR_DIM || pr.num_blocks < 1 || pr.num_blocks > CERB_MAX_PRIOR_BLOCKS || !pr.linearized_jacobians || !pr.linearized_residuals)
+        return fail(CERB_ERR_BAD_ARGUMENT, "prior: bad n / num_blocks / null matrices");
+    meta[0] = 1; meta[1] = pr.n; meta[2] = pr.num_blocks;
+    for (int b = 0; b < pr.num_blocks; b++) {
+        const int kind = pr.block_kind[b], index = pr.block_index[b];
+        if (kind < 0 || kind > 4 || index < 0 || index > 10 || ((kind == CERB_BLOCK_EX_POSE) && index > 1)) return fail(CERB_ERR_BAD_ARGUMENT, "prior: bad block");
+        // the solver keeps Hyy block tridiagonal: a prior may only keep the speed/leg bias of frame 0 (what
+        // MARGIN_OLD / MARGIN_SECOND_NEW produce, estimator.cpp:1253-1401)
+        if ((kind == CERB_BLOCK_SPEEDBIAS || kind == CERB_BLOCK_LEGBIAS) && index != 0) return fail(CERB_ERR_BAD_ARGUMENT, "prior keeps a speed/leg bias block of a frame other than 0");
+        meta[4 + 3 * b] = kind; meta[5 + 3 * b] = index; meta[6 + 3 * b] = pr.block_col[b];
+        const int size = prior_block_size(kind), local = size == 7 ? 6 : size;
+        if (pr.block_col[b] < 0 || pr.block_col[b] + local > pr.n) return fail(CERB_ERR_BAD_ARGUMENT, "prior: block column out of range");
+        for (int k = 0; k < 7; k++) x0[7 * b + k] = pr.block_x0[b][k];
+    }
+    std::memcpy(J, pr.linearized_jacobians, sizeof(double) * pr.n * pr.n);
+    std::memcpy(r, pr.linearized_residuals, sizeof(double) * pr.n);
+    return CERB_OK;
+}
+
+static int pack_window(CerbHandle *h, int w, const CerbWindowDesc &d, const CerbWindowState &st) {
+    const int F = h->F, O = h->O;
+    if (d.n_features < 0 || d.n_features > F) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_features over capacity");
+    if (d.n_obs < 0 || d.n_obs > O) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_obs over capacity");
+    if (d.td_open) return fail(CERB_ERR_BAD_ARGUMENT, "td estimation (td_open) is not supported by this build; keep para_Td constant");
+    if ((d.n_features && (!d.features || !d.obs || !st.para_Feature)) || !d.preint) return fail(CERB_ERR_BAD_ARGUMENT, "window: null pointer");
+    h->h_nfeat[w] = d.n_features;
+    h->h_flags[w] = (d.extrinsic_open ? 1 : 0) | (d.td_open ? 2 : 0);
+    for (int f = 0; f < d.n_features; f++) {
+        const CerbFeature &ft = d.features[f];
+        if (ft.start_frame < 0 || ft.n_obs < 1 || ft.start_frame + ft.n_obs > CERB_NUM_FRAMES || ft.obs_offset < 0 || ft.obs_offset + ft.n_obs > d.n_obs)
+            return fail(CERB_ERR_BAD_ARGUMENT, "window: malformed feature track");
+        h->h_fstart[(size_t)w * F + f] = ft.start_frame; h->h_fnobs[(size_t)w * F + f] = ft.n_obs; h->h_foff[(size_t)w * F + f] = ft.obs_offset;
+        h->h_lam[(size_t)w * F + f] = st.para_Feature[f];
+    }
+    double *ob = h->h_obs + (size_t)w * NOBS_PLANES * O;
+    int *sto = h->h_stereo + (size_t)w * O;
+    for (int o = 0; o < d.n_obs; o++) {
+        const CerbObservation &q = d.obs[o];
+        ob[0 * O + o] = q.point[0]; ob[1 * O + o] = q.point[1]; ob[2 * O + o] = q.velocity[0]; ob[3 * O + o] = q.velocity[1];
+        ob[4 * O + o] = q.pointRight[0]; ob[5 * O + o] = q.pointRight[1]; ob[6 * O + o] = q.velocityRight[0]; ob[7 * O + o] = q.velocityRight[1];
+        ob[8 * O + o] = q.cur_td; sto[o] = q.is_stereo;
+    }
+    for (int i = 0; i < CERB_WINDOW_SIZE; i++) pack_preint(d.preint[i], h->h_pre + ((size_t)w * 10 + i) * PRE_STRIDE);
+    int rc = pack_prior(d.prior, h->h_pmeta + (size_t)w * PRIOR_META_STRIDE, h->h_pJ + (size_t)w * PRIOR_LD * PRIOR_LD, h->h_pr + (size_t)w * PRIOR_LD, h->h_px0 + (size_t)w * 16 * 7);
+    if (rc) return rc;
+    double *s = h->h_state + (size_t)w * ST_STRIDE;
+    std::memcpy(s + ST_POSE, st.para_Pose, sizeof(st.para_Pose));
+    std::memcpy(s + ST_SB, st.para_SpeedBias, sizeof(st.para_SpeedBias));
+    std::memcpy(s + ST_LB, st.para_LegBias, sizeof(st.para_LegBias));
+    std::memcpy(s + ST_EX, st.para_Ex_Pose, sizeof(st.para_Ex_Pose));
+    s[ST_TD] = st.para_Td[0];
+    return CERB_OK;
+}
+
+static int pack_all(CerbHandle *h, int n, const CerbWindowDesc *descs, const CerbWindowState *states) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nth = (int)std::min<unsigned>(hw ? hw : 1, 16u);
+    if (n < 8) nth = 1;
+    std::vector<int> rcs(nth, 0); std::vector<std::string> errs(nth);
+    auto work = [&](int t) {
+        for (int w = t; w < n; w += nth) { int rc = pack_window(h, w, descs[w], states[w]); if (rc) { rcs[t] = rc; errs[t] = g_err; return; } }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nth; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int t = 0; t < nth; t++) if (rcs[t]) return fail(rcs[t], errs[t]);
+    return CERB_OK;
+}
+
+static int upload(CerbHandle *h, int n) {
+    const size_t F = h->F, O = h->O;
+    cudaStream_t s = h->stream;
+#define H2D(dst, src, count) CUDA_TRY(cudaMemcpyAsync(dst, src, (count) * sizeof(*(src)), cudaMemcpyHostToDevice, s))
+    H2D(h->d_nfeat, h->h_nfeat, (size_t)n); H2D(h->d_fstart, h->h_fstart, n * F); H2D(h->d_fnobs, h->h_fnobs, n * F); H2D(h->d_foff, h->h_foff, n * F);
+    H2D(h->d_flags, h->h_flags, (size_t)n); H2D(h->d_stereo, h->h_stereo, n * O); H2D(h->d_pmeta, h->h_pmeta, (size_t)n * PRIOR_META_STRIDE);
+    H2D(h->d_obs, h->h_obs, n * NOBS_PLANES * O); H2D(h->d_pre, h->h_pre, (size_t)n * 10 * PRE_STRIDE);
+    H2D(h->d_pJ, h->h_pJ, (size_t)n * PRIOR_LD * PRIOR_LD); H2D(h->d_pr, h->h_pr, (size_t)n * PRIOR_LD); H2D(h->d_px0, h->h_px0, (size_t)n * 16 * 7);
+    H2D(h->d_state0, h->h_state, (size_t)n * ST_STRIDE); H2D(h->d_lam0, h->h_lam, n * F);
+#undef H2D
+    h->n = n;
+    return CERB_OK;
+}
+
+static SolveParams make_params(CerbHandle *h, int max_iters, double *dbg, int dbg_window) {
+    SolveParams P;
+    std::memset(&P, 0, sizeof(P));
+    const CerbSolverConfig &c = h->cfg;
+    P.n_windows = h->n; P.maxF = h->F; P.maxObs = h->O; P.max_iters = max_iters; P.optimize_leg_bias = c.optimize_leg_bias;
+    for (int k = 0; k < 3; k++) P.G[k] = c.g[k];
+    P.sqrt_info = c.visual_sqrt_info; P.huber = c.huber_delta;
+    P.radius0 = c.initial_trust_region_radius; P.max_radius = c.max_trust_region_radius; P.min_radius = c.min_trust_region_radius;
+    P.min_rel_dec = c.min_relative_decrease; P.ftol = c.function_tolerance; P.gtol = c.gradient_tolerance; P.ptol = c.parameter_tolerance;
+    P.n_features = h->d_nfeat; P.feat_start = h->d_fstart; P.feat_nobs = h->d_fnobs; P.feat_off = h->d_foff; P.flags = h->d_flags;
+    P.obs = h->d_obs; P.obs_stereo = h->d_stereo; P.pre = h->d_pre; P.sinfo = h->d_sinfo;
+    P.prior_J = h->d_pJ; P.prior_r = h->d_pr; P.prior_x0 = h->d_px0; P.prior_Hp = h->d_pHp; P.prior_meta = h->d_pmeta;
+    P.state = h->d_state; P.lam = h->d_lam; P.rep_i = h->d_repi; P.rep_d = h->d_repd; P.ws = h->d_ws; P.ws_stride = h->ws_stride;
+    P.dbg = dbg; P.dbg_window = dbg_window;
+    return P;
+}
+
+// restore the initial states, prepare (sqrt_info, prior Gram matrix) and solve; all asynchronous on the stream
+static int launch_solve(CerbHandle *h, int max_iters, double *dbg, int dbg_window, bool timed) {
+    const int n = h->n;
+    if (n < 1) return fail(CERB_ERR_BAD_ARGUMENT, "no resident batch");
+    cudaStream_t s = h->stream;
+    if (timed) CUDA_TRY(cudaEventRecord(h->ev0, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_state, h->d_state0, (size_t)n * ST_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_lam, h->d_lam0, (size_t)n * h->F * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    const int nfac = n * 10;
+    CERB_LAUNCH(imu_leg_prepare_kernel, (nfac + 1) / 2, 64, 0, s, nfac, (const double *)h->d_pre, h->d_sinfo);
+    CERB_LAUNCH(prior_prepare_kernel, n, 256, 0, s, (const double *)h->d_pJ, (const int *)h->d_pmeta, h->d_pHp);
+    SolveParams P = make_params(h, max_iters, dbg, dbg_window);
+    CERB_LAUNCH(vilo_solve_kernel, std::min(n, h->grid), SOLVE_THREADS, h->smem_bytes, s, P);
+    CUDA_TRY(cudaGetLastError());
+    if (timed) { CUDA_TRY(cudaEventRecord(h->ev1, s)); h->ev_pending = true; h->last_launches = 3; }
+    return CERB_OK;
+}
+
+static int collect_time(CerbHandle *h) {
+    if (h->ev_pending) {
+        CUDA_TRY(cudaEventSynchronize(h->ev1));
+        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->last_ms = ms; h->ev_pending = false;
+    }
+    return CERB_OK;
+}
+
+static int download(CerbHandle *h, CerbWindowState *states, CerbSolveReport *reports) {
+    const int n = h->n; const size_t F = h->F;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->h_state, h->d_state, (size_t)n * ST_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_lam, h->d_lam, n * F * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_repi, h->d_repi, (size_t)n * 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_repd, h->d_repd, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    int rc = collect_time(h); if (rc) return rc;
+    int status = CERB_OK;
+    for (int w = 0; w < n; w++) {
+        if (states) {
+            CerbWindowState &st = states[w];
+            const double *q = h->h_state + (size_t)w * ST_STRIDE;
+            std::memcpy(st.para_Pose, q + ST_POSE, sizeof(st.para_Pose));
+            std::memcpy(st.para_SpeedBias, q + ST_SB, sizeof(st.para_SpeedBias));
+            std::memcpy(st.para_LegBias, q + ST_LB, sizeof(st.para_LegBias));
+            std::memcpy(st.para_Ex_Pose, q + ST_EX, sizeof(st.para_Ex_Pose));
+            st.para_Td[0] = q[ST_TD];
+            const int nf = h->h_nfeat[w];
+            if (st.para_Feature) for (int f = 0; f < nf; f++) st.para_Feature[f] = h->h_lam[(size_t)w * F + f];
+        }
+        if (reports) {
+            CerbSolveReport &r = reports[w];
+            r.iterations = h->h_repi[4 * w]; r.num_successful_steps = h->h_repi[4 * w + 1]; r.termination = h->h_repi[4 * w + 2]; r.status = h->h_repi[4 * w + 3];
+            r.initial_cost = h->h_repd[2 * w]; r.final_cost = h->h_repd[2 * w + 1];
+        }
+        if (h->h_repi[4 * w + 3] != 0) status = CERB_ERR_NON_FINITE;
+    }
+    if (status) return fail(status, "at least one window produced a non-finite cost (see reports[].status)");
+    return CERB_OK;
+}
+
+extern "C" {
+
+int cerb_batch_upload(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, const CerbWindowState *states) {
+    if (!h || !descs || !states) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    if (n < 1 || n > h->B) return fail(CERB_ERR_BAD_ARGUMENT, "batch size over capacity");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));          // staging buffers may still be in flight
+    int rc = pack_all(h, n, descs, states); if (rc) return rc;
+    return upload(h, n);
+}
+int cerb_batch_solve_resident(CerbHandle *h) {
+    if (!h) return fail(CERB_ERR_BAD_ARGUMENT, "null handle");
+    int rc = collect_time(h); if (rc) return rc;
+    return launch_solve(h, h->cfg.max_num_iterations, nullptr, -1, true);
+}
+int cerb_batch_download(CerbHandle *h, CerbWindowState *states, CerbSolveReport *reports) {
+    if (!h) return fail(CERB_ERR_BAD_ARGUMENT, "null handle");
+    return download(h, states, reports);
+}
+int cerb_sync(CerbHandle *h) {
+    if (!h) return fail(CERB_ERR_BAD_ARGUMENT, "null handle");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return collect_time(h);
+}
+int cerb_last_solve_stats(CerbHandle *h, double *kernel_ms, int32_t *kernel_launches) {
+    if (!h) return fail(CERB_ERR_BAD_ARGUMENT, "null handle");
+    int rc = collect_time(h); if (rc) return rc;
+    if (kernel_ms) *kernel_ms = h->last_ms;
+    if (kernel_launches) *kernel_launches = h->last_launches;
+    return CERB_OK;
+}
+int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, CerbWindowState *states, CerbSolveReport *reports) {
+    int rc = cerb_batch_upload(h, n, descs, states); if (rc) return rc;
+    rc = launch_solve(h, h->cfg.max_num_iterations, nullptr, -1, true); if (rc) return rc;
+    return download(h, states, reports);
+}
+int cerb_solve_window(CerbHandle *h, const CerbWindowDesc *desc, CerbWindowState *state, CerbSolveReport *report) {
+    return cerb_solve_batch(h, 1, desc, state, report);
+}
+
+int cerb_debug_linearize(CerbHandle *h, int32_t w, double *cost, double *gradient, double *jtj_diag, int32_t n_alloc) {
+    if (!h || w < 0 || w >= h->n) return fail(CERB_ERR_BAD_ARGUMENT, "bad window index");
+    const int nf = h->h_nfeat[w], F = h->F;
+    if (n_alloc < NR + nf) return fail(CERB_ERR_BAD_ARGUMENT, "n_alloc too small");
+    const size_t cnt = 2 * (size_t)(NR + F) + 8;
+    CUDA_TRY(cudaMemsetAsync(h->d_dbg, 0, cnt * sizeof(double), h->stream));
+    int rc = launch_solve(h, 0, h->d_dbg, w, false); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->h_dbg, h->d_dbg, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (cost) *cost = h->h_dbg[0];
+    for (int k = 0; k < NR + nf; k++) {
+        const int src = k < NR ? k : NR + (k - NR);
+        if (gradient) gradient[k] = h->h_dbg[1 + src];
+        if (jtj_diag) jtj_diag[k] = h->h_dbg[1 + NR + F + src];
+    }
+    return CERB_OK;
+}
+
+// ---- factor-family evaluators ----------------------------------------------------------------------------------
+struct DevBuf {   // RAII scratch
+    std::vector<void *> ptrs;
+    ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
+    double *up(const double *src, size_t n, cudaStream_t s) {
+        double *d = nullptr; if (cudaMalloc((void **)&d, std::max<size_t>(n, 1) * sizeof(double)) != cudaSuccess) return nullptr;
+        ptrs.push_back(d);
+        if (src) cudaMemcpyAsync(d, src, n * sizeof(double), cudaMemcpyHostToDevice, s);
+        return d;
+    }
+};
+
+int cerb_eval_projection(CerbHandle *h, int32_t kind, int32_t n, const double *pose_i, const double *pose_j, const double *ex0, const double *ex1,
+                         const double *inv_dep, const double *td, const double *pts_i, const double *pts_j, const double *vel_i, const double *vel_j,
+                         const double *td_i, const double *td_j, double *residuals, double *jacobians) {
+    if (!h || n < 1 || kind < 0 || kind > 2 || !ex0 || !inv_dep || !td || !pts_i || !pts_j || !vel_i || !vel_j || !td_i || !td_j) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_projection: bad argument");
+    if (kind != CERB_PROJ_ONE_FRAME_TWO_CAM && (!pose_i || !pose_j)) return fail(CERB_ERR_BAD_ARGUMENT, "poses required");
+    if (kind != CERB_PROJ_TWO_FRAME_ONE_CAM && !ex1) return fail(CERB_ERR_BAD_ARGUMENT, "ex1 required");
+    cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
+    const int JS = kind == 0 ? 46 : (kind == 1 ? 60 : 32);
+    double *dpi = pose_i ? B.up(pose_i, 7 * N, s) : nullptr, *dpj = pose_j ? B.up(pose_j, 7 * N, s) : nullptr;
+    double *de0 = B.up(ex0, 7 * N, s), *de1 = ex1 ? B.up(ex1, 7 * N, s) : nullptr;
+    double *dl = B.up(inv_dep, N, s), *dtd = B.up(td, N, s), *dpti = B.up(pts_i, 3 * N, s), *dptj = B.up(pts_j, 3 * N, s);
+    double *dvi = B.up(vel_i, 2 * N, s), *dvj = B.up(vel_j, 2 * N, s), *dti = B.up(td_i, N, s), *dtj = B.up(td_j, N, s);
+    double *dr = B.up(nullptr, 2 * N, s), *dJ = jacobians ? B.up(nullptr, JS * N, s) : nullptr;
+    if (!dr || !dtj) return fail(CERB_ERR_CUDA, "device allocation failed");
+    CERB_LAUNCH(projection_eval_kernel, (n + 127) / 128, 128, 0, s, (int)kind, (int)n, (const double *)dpi, (const double *)dpj, (const double *)de0, (const double *)de1,
+                (const double *)dl, (const double *)dtd, (const double *)dpti, (const double *)dptj, (const double *)dvi, (const double *)dvj, (const double *)dti,
+                (const double *)dtj, h->cfg.visual_sqrt_info, dr, dJ);
+    CUDA_TRY(cudaGetLastError());
+    if (residuals) CUDA_TRY(cudaMemcpyAsync(residuals, dr, 2 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (jacobians) CUDA_TRY(cudaMemcpyAsync(jacobians, dJ, JS * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return CERB_OK;
+}
+
+int cerb_eval_imu_leg(CerbHandle *h, int32_t n, const CerbIMULegPreint *preint, const double *params, double *residuals, double *jacobians, double *sqrt_info) {
+    if (!h || n < 1 || !preint || !params) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_imu_leg: bad argument");
+    cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
+    std::vector<double> packed(N * PRE_STRIDE, 0.0);
+    for (int k = 0; k < n; k++) pack_preint(preint[k], packed.data() + (size_t)k * PRE_STRIDE);
+    double *dpre = B.up(packed.data(), N * PRE_STRIDE, s), *dsi = B.up(nullptr, N * 961, s), *dpar = B.up(params, 40 * N, s);
+    double *dr = B.up(nullptr, 31 * N, s), *dJ = jacobians ? B.up(nullptr, 31 * 40 * N, s) : nullptr;
+    if (!dpre || !dsi || !dpar || !dr) return fail(CERB_ERR_CUDA, "device allocation failed");
+    CERB_LAUNCH(imu_leg_prepare_kernel, (n + 1) / 2, 64, 0, s, (int)n, (const double *)dpre, dsi);
+    CERB_LAUNCH(imu_leg_eval_kernel, n, 128, 0, s, (int)n, (const double *)dpre, (const double *)dsi, (const double *)dpar, (const double *)h->d_G, dr, dJ);
+    CUDA_TRY(cudaGetLastError());
+    if (residuals) CUDA_TRY(cudaMemcpyAsync(residuals, dr, 31 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (jacobians) CUDA_TRY(cudaMemcpyAsync(jacobians, dJ, 31 * 40 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (sqrt_info) CUDA_TRY(cudaMemcpyAsync(sqrt_info, dsi, 961 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return CERB_OK;
+}
+
+int cerb_eval_prior(CerbHandle *h, const CerbPrior *prior, const CerbWindowState *state, double *residuals, double *jacobians) {
+    if (!h || !prior || !state || !prior->valid || !residuals) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_prior: bad argument");
+    std::vector<int> meta(PRIOR_META_STRIDE); std::vector<double> J(PRIOR_LD * PRIOR_LD, 0.0), r(PRIOR_LD, 0.0), x0(16 * 7, 0.0), st(ST_STRIDE, 0.0);
+    int rc = pack_prior(*prior, meta.data(), J.data(), r.data(), x0.data()); if (rc) return rc;
+    std::memcpy(st.data() + ST_POSE, state->para_Pose, sizeof(state->para_Pose)); std::memcpy(st.data() + ST_SB, state->para_SpeedBias, sizeof(state->para_SpeedBias));
+    std::memcpy(st.data() + ST_LB, state->para_LegBias, sizeof(state->para_LegBias)); std::memcpy(st.data() + ST_EX, state->para_Ex_Pose, sizeof(state->para_Ex_Pose));
+    st[ST_TD] = state->para_Td[0];
+    size_t jtot = 0; for (int b = 0; b < prior->num_blocks; b++) jtot += (size_t)prior->n * prior_block_size(prior->block_kind[b]);
+    cudaStream_t s = h->stream; DevBuf B;
+    double *dJ = B.up(J.data(), J.size(), s), *dr0 = B.up(r.data(), r.size(), s), *dx0 = B.up(x0.data(), x0.size(), s), *dst = B.up(st.data(), st.size(), s);
+    double *dres = B.up(nullptr, PRIOR_LD, s), *djac = jacobians ? B.up(nullptr, jtot, s) : nullptr;
+    int *dmeta = nullptr; CUDA_TRY(cudaMalloc((void **)&dmeta, PRIOR_META_STRIDE * sizeof(int))); B.ptrs.push_back(dmeta);
+    CUDA_TRY(cudaMemcpyAsync(dmeta, meta.data(), PRIOR_META_STRIDE * sizeof(int), cudaMemcpyHostToDevice, s));
+    CERB_LAUNCH(prior_eval_kernel, 1, 128, 0, s, (const double *)dJ, (const double *)dr0, (const int *)dmeta, (const double *)dx0, (const double *)dst, dres, djac);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(residuals, dres, prior->n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (jacobians) CUDA_TRY(cudaMemcpyAsync(jacobians, djac, jtot * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return CERB_OK;
+}
+
+int cerb_a1_kinematics(CerbHandle *h, int32_t n, const double *q, const double *rho_opt, const double *rho_fix, double *fk, double *jac, double *dfk_drho,
+                       double *dJ_dq, double *dJ_drho) {
+    if (!h || n < 1 || !q || !rho_opt || !rho_fix) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_a1_kinematics: bad argument");
+    cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
+    double *dq = B.up(q, 3 * N, s), *dro = B.up(rho_opt, N, s), *drf = B.up(rho_fix, 4 * N, s);
+    double *dfk = fk ? B.up(nullptr, 3 * N, s) : nullptr, *dj = jac ? B.up(nullptr, 9 * N, s) : nullptr, *ddf = dfk_drho ? B.up(nullptr, 3 * N, s) : nullptr;
+    double *djq = dJ_dq ? B.up(nullptr, 27 * N, s) : nullptr, *djr = dJ_drho ? B.up(nullptr, 9 * N, s) : nullptr;
+    CERB_LAUNCH(a1_kinematics_kernel, (n + 127) / 128, 128, 0, s, (int)n, (const double *)dq, (const double *)dro, (const double *)drf, dfk, dj, ddf, djq, djr);
+    CUDA_TRY(cudaGetLastError());
+    if (fk) CUDA_TRY(cudaMemcpyAsync(fk, dfk, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (jac) CUDA_TRY(cudaMemcpyAsync(jac, dj, 9 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dfk_drho) CUDA_TRY(cudaMemcpyAsync(dfk_drho, ddf, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dJ_dq) CUDA_TRY(cudaMemcpyAsync(dJ_dq, djq, 27 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dJ_drho) CUDA_TRY(cudaMemcpyAsync(dJ_drho, djr, 9 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return CERB_OK;
+}
+
+// ---- leg-contact preintegration ------------------------------------------------------------------------------------
+int cerb_preintegrate_batch(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n, const CerbPreintJob *jobs, CerbIMULegPreint *out) {
+    if (!h || !cfg || n < 1 || !jobs || !out) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_preintegrate_batch: bad argument");
+    PreintParams P;
+    P.acc_n = cfg->acc_n; P.acc_n_z = cfg->acc_n_z; P.gyr_n = cfg->gyr_n; P.acc_w = cfg->acc_w; P.gyr_w = cfg->gyr_w; P.phi_n = cfg->phi_n; P.dphi_n = cfg->dphi_n;
+    P.rho_c_n = cfg->rho_c_n; P.rho_nc_n = cfg->rho_nc_n; P.v_n_min_xy = cfg->v_n_min_xy; P.v_n_min_z = cfg->v_n_min_z; P.v_n_min = cfg->v_n_min; P.v_n_max = cfg->v_n_max;
+    P.v_n_force_thres_ratio = cfg->v_n_force_thres_ratio; P.v_n_term1_steep = cfg->v_n_term1_steep; P.v_n_term2_var_rescale = cfg->v_n_term2_var_rescale;
+    P.v_n_term3_distance_rescale = cfg->v_n_term3_distance_rescale; P.contact_sensor_type = cfg->contact_sensor_type;
+    for (int l = 0; l < 4; l++) for (int k = 0; k < 4; k++) P.rho_fix[4 * l + k] = cfg->rho_fix[l][k];
+    for (int k = 0; k < 3; k++) P.p_br[k] = cfg->p_br[k];
+    for (int k = 0; k < 9; k++) P.R_br[k] = cfg->R_br[k];
+    size_t total = 0;
+    for (int j = 0; j < n; j++) { if (jobs[j].n_samples < 0 || (jobs[j].n_samples && !jobs[j].samples)) return fail(CERB_ERR_BAD_ARGUMENT, "bad job"); total += jobs[j].n_samples; }
+    std::vector<double> hj((size_t)n * PJ_STRIDE), hs(std::max<size_t>(total, 1) * SAMPLE_STRIDE);
+    std::vector<int> hi((size_t)n * 2);
+    size_t off = 0;
+    for (int j = 0; j < n; j++) {
+        const CerbPreintJob &q = jobs[j];
+        double *o = hj.data() + (size_t)j * PJ_STRIDE;
+        std::memcpy(o, q.acc_0, 24); std::memcpy(o + 3, q.gyr_0, 24); std::memcpy(o + 6, q.phi_0, 96); std::memcpy(o + 18, q.dphi_0, 96); std::memcpy(o + 30, q.c_0, 32);
+        std::memcpy(o + 34, q.linearized_ba, 24); std::memcpy(o + 37, q.linearized_bg, 24); std::memcpy(o + 40, q.linearized_rho, 32);
+        hi[2 * j] = q.n_samples; hi[2 * j + 1] = (int)off;
+        for (int k = 0; k < q.n_samples; k++) {
+            const CerbIMULegSample &m = q.samples[k];
+            double *so = hs.data() + (off + k) * SAMPLE_STRIDE;
+            so[0] = m.dt; std::memcpy(so + 1, m.acc, 24); std::memcpy(so + 4, m.gyr, 24); std::memcpy(so + 7, m.phi, 96); std::memcpy(so + 19, m.dphi, 96); std::memcpy(so + 31, m.c, 32);
+        }
+        off += q.n_samples;
+    }
+    cudaStream_t s = h->stream; DevBuf B;
+    double *dj = B.up(hj.data(), hj.size(), s), *ds = B.up(hs.data(), hs.size(), s), *dout = B.up(nullptr, (size_t)n * PRE_STRIDE, s), *dfull = B.up(nullptr, (size_t)n * 1922, s);
+    int *di = nullptr; CUDA_TRY(cudaMalloc((void **)&di, hi.size() * sizeof(int))); B.ptrs.push_back(di);
+    if (!dj || !ds || !dout || !dfull) return fail(CERB_ERR_CUDA, "device allocation failed");
+    CUDA_TRY(cudaMemcpyAsync(di, hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CERB_LAUNCH(preintegrate_kernel, n, 128, 0, s, P, (int)n, (const double *)dj, (const int *)di, (const double *)ds, dout, dfull);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> ho((size_t)n * PRE_STRIDE), hf((size_t)n * 1922);
+    CUDA_TRY(cudaMemcpyAsync(ho.data(), dout, ho.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hf.data(), dfull, hf.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int j = 0; j < n; j++) {
+        const double *o = ho.data() + (size_t)j * PRE_STRIDE, *f = hf.data() + (size_t)j * 1922;
+        CerbIMULegPreint &r = out[j];
+        r.sum_dt = o[PRE_SUM_DT];
+        for (int k = 0; k < 3; k++) { r.delta_p[k] = o[PRE_DP + k]; r.delta_v[k] = o[PRE_DV + k]; r.linearized_ba[k] = o[PRE_BA + k]; r.linearized_bg[k] = o[PRE_BG + k]; }
+        for (int k = 0; k < 4; k++) { r.delta_q[k] = o[PRE_DQ + k]; r.linearized_rho[k] = o[PRE_RHO + k]; }
+        for (int k = 0; k < 12; k++) r.delta_epsilon[k] = o[PRE_DEPS + k];
+        for (int a = 0; a < 31; a++) for (int b = 0; b < 31; b++) { r.jacobian[b * 31 + a] = f[a * 31 + b]; r.covariance[b * 31 + a] = f[961 + a * 31 + b]; }
+    }
+    return CERB_OK;
+}
+
+// ---- host-side gauge re-anchoring: Estimator::double2vector (estimator.cpp:903-957) ----------------------------------
+static void r2ypr(const m33 &R, double ypr[3]) {   // Utility::R2ypr, degrees
+    const double nx = R.m[0], ny = R.m[3], nz = R.m[6], ox = R.m[1], oy = R.m[4], ax = R.m[2], ay = R.m[5];
+    const double y = atan2(ny, nx);
+    const double p = atan2(-nz, nx * cos(y) + ny * sin(y));
+    const double r = atan2(ax * sin(y) - ay * cos(y), -ox * sin(y) + oy * cos(y));
+    ypr[0] = y / M_PI * 180.0; ypr[1] = p / M_PI * 180.0; ypr[2] = r / M_PI * 180.0;
+}
+void cerb_double2vector(const CerbWindowState *before, const CerbWindowState *after, double *Ps, double *Rs, double *Vs) {
+    const m33 Rs0 = qtoR(ldq(before->para_Pose[0] + 3));
+    const m33 R00 = qtoR(ldq(after->para_Pose[0] + 3));
+    double o0[3], o00[3];
+    r2ypr(Rs0, o0); r2ypr(R00, o00);
+    const double yd = (o0[0] - o00[0]) / 180.0 * M_PI;
+    m33 rot = ident33();
+    rot.m[0] = cos(yd); rot.m[1] = -sin(yd); rot.m[3] = sin(yd); rot.m[4] = cos(yd);
+    if (fabs(fabs(o0[1]) - 90) < 1.0 || fabs(fabs(o00[1]) - 90) < 1.0) rot = mul33(Rs0, tr33(R00));
+    const d3 P0 = ld3(after->para_Pose[0]), origin = ld3(before->para_Pose[0]);
+    for (int i = 0; i < CERB_NUM_FRAMES; i++) {
+        const m33 R = mul33(rot, qtoR(qnormalized(ldq(after->para_Pose[i] + 3))));
+        const d3 P = mv33(rot, ld3(after->para_Pose[i]) - P0) + origin;
+        const d3 V = mv33(rot, ld3(after->para_SpeedBias[i]));
+        st3(Ps + 3 * i, P); st3(Vs + 3 * i, V);
+        for (int k = 0; k < 9; k++) Rs[9 * i + k] = R.m[k];
+    }
+}
+
+}  // extern "C"

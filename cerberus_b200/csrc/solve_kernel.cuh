@@ -1,0 +1,845 @@
+// solve_kernel.cuh -- the fused sliding-window solve: everything Estimator::optimization() does between
+// vector2double() and double2vector() (reference src/estimator/estimator.cpp:1059-1236), one window per
+// CTA, the whole trust-region loop device resident.
+//
+// Unknowns of a window (tangent space): x = [pose0..10 (66) | ex0, ex1 (12)] = 78 "camera" dims,
+// y_f = [speedbias_f (9) | legbias_f (4)] = 13 dims per frame (143), lambda = one inverse depth per
+// feature.  Structure exploited:
+//   * visual factors touch only x and lambda  -> lambda is Schur-eliminated with rank-1 updates
+//     S = Hxx - W diag(1/h) W^T   (W = 78 x F, the per-landmark 1x1 blocks)
+//   * IMU-leg factors couple (pose_f, y_f, pose_f+1, y_f+1) only -> Hyy is block tridiagonal (13x13
+//     blocks) and is eliminated by a block-bidiagonal Cholesky:  S' = S - (L^-1 Hyx)^T (L^-1 Hyx)
+//   * the 78 x 78 remainder is factored densely in shared memory.
+// The solver semantics restated on top of that are those of Ceres 1.14: TRUST_REGION + TRADITIONAL
+// DOGLEG (mu-regularised Gauss-Newton, Cauchy point), Jacobi scaling from iteration 0, HuberLoss
+// corrector, the accept / reject / tolerance logic of TrustRegionMinimizer.  Constant parameter blocks
+// are masked (scale 0).  td is kept constant (td_open is rejected by the host layer this round).
+#pragma once
+#include "eval_kernels.cuh"
+
+namespace cerb {
+
+enum { CERB_WINDOW = 10, NX = 78, NYB = 13, NFR = 11, NY = 143, NR = 221, NRP = 224, SOLVE_THREADS = 256, FT = 64, TILE_LD = 25, NOBS_PLANES = 9 };
+
+struct SolveParams {
+    int n_windows, maxF, maxObs, max_iters, optimize_leg_bias;
+    double G[3], sqrt_info, huber;
+    double radius0, max_radius, min_radius, min_rel_dec, ftol, gtol, ptol;
+    // batch (device pointers)
+    const int *n_features, *feat_start, *feat_nobs, *feat_off, *flags;      // flags bit0 ex_open, bit1 td_open
+    const double *obs; const int *obs_stereo;                               // obs [B][9][maxObs] planar
+    const double *pre;                                                      // [B][10][PRE_STRIDE] compact preintegration results
+    const double *sinfo;                                                    // [B][10][961] sqrt_info (imu_leg_prepare_kernel)
+    const double *prior_J, *prior_r, *prior_x0, *prior_Hp; const int *prior_meta;
+    double *state, *lam;                                                    // [B][ST_STRIDE], [B][maxF]  in/out
+    int *rep_i; double *rep_d;                                              // [B][4], [B][2]
+    double *ws;                                                             // [grid][ws_stride] per-CTA workspace
+    long ws_stride;
+    double *dbg; int dbg_window;                                            // optional probe (cost, gradient, diag)
+};
+
+// per-CTA global workspace layout (doubles); F = maxF
+CERB_HD long ws_W(int) { return 0; }                                        // [NX][F]
+CERB_HD long ws_vecs(int F) { return (long)NX * F; }                        // 8 vectors of F: hh, gl, sl, Dl, ghl, gnl, stl, lamc
+CERB_HD long ws_backup(int F) { return (long)NX * F + 8L * F; }             // Hxx 6084 | Hxy 11154 | Ad 1859 | Bo 1690
+CERB_HD long ws_size(int F) { return ws_backup(F) + 6084 + 11154 + 1859 + 1690 + 64; }
+
+struct Smem {
+    double *Hxx, *Hxy, *Ad, *Bo;            // 78x78, 78x143, 11x13x13, 10x13x13
+    double *g, *sc, *D, *gh, *gn, *stp, *yv; // NRP each: gradient, jacobi scale, dogleg diag, g/D, GN step (z space), step (scaled), work
+    double *xs, *xc;                        // current / candidate state (ST_STRIDE)
+    double *Rw, *Rex;                       // rotation matrices: 11x9, 2x9 (of the state being evaluated)
+    double *Ju;                             // 31 x 39
+    double *lin;                            // 10 x 96 (IMULegLin)
+    double *pdx, *pr;                       // prior dx, residual (96 each)
+    double *red;                            // 8 x 256 reduction scratch
+    double *wj;                             // 128 x 8 per-thread exchange
+    double *sca;                            // 64 scalars
+    int *ti;                                // 128 ints: anchor per tile factor ; + misc ints
+    double *tile;                           // alias of Hxy: 256 x 25
+};
+enum { SMEM_DOUBLES = 6084 + 11154 + 1859 + 1690 + 7 * NRP + 2 * ST_STRIDE + 99 + 18 + 3 + 31 * 39 + 960 + 192 + 8 * 256 + 128 * 8 + 64 + 80 };
+
+CERB_D void smem_carve(double *base, Smem &s) {
+    double *p = base;
+    s.Hxx = p; p += 6084; s.Hxy = p; p += 11154; s.Ad = p; p += 1859; s.Bo = p; p += 1690;
+    s.g = p; p += NRP; s.sc = p; p += NRP; s.D = p; p += NRP; s.gh = p; p += NRP; s.gn = p; p += NRP; s.stp = p; p += NRP; s.yv = p; p += NRP;
+    s.xs = p; p += ST_STRIDE; s.xc = p; p += ST_STRIDE;
+    s.Rw = p; p += 99; s.Rex = p; p += 18; p += 3;
+    s.Ju = p; p += 31 * 39; s.lin = p; p += 960; s.pdx = p; p += 96; s.pr = p; p += 96;
+    s.red = p; p += 8 * 256; s.wj = p; p += 128 * 8; s.sca = p; p += 64;
+    s.ti = reinterpret_cast<int *>(p); p += 80;
+    s.tile = s.Hxy;
+}
+
+// deterministic block-wide sums of up to 8 values per thread; result broadcast in out[0..nv)
+template <int NV>
+CERB_D void block_sum(const double *v, double *red, double *out, int tid) {
+    for (int k = 0; k < NV; k++) red[k * 256 + tid] = v[k];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) for (int k = 0; k < NV; k++) red[k * 256 + tid] += red[k * 256 + tid + s];
+        __syncthreads();
+    }
+    for (int k = 0; k < NV; k++) out[k] = red[k * 256];
+    __syncthreads();
+}
+
+CERB_D void load_geometry(const double *x, Smem &s, int tid) {
+    if (tid < 11) { const m33 R = qtoR(ldq(x + ST_POSE + 7 * tid + 3)); for (int k = 0; k < 9; k++) s.Rw[9 * tid + k] = R.m[k]; }
+    else if (tid < 13) { const int e = tid - 11; const m33 R = qtoR(ldq(x + ST_EX + 7 * e + 3)); for (int k = 0; k < 9; k++) s.Rex[9 * e + k] = R.m[k]; }
+    __syncthreads();
+}
+
+// Evaluate the (up to) two factors of observation (f, frame j) seen by thread `cam`; returns false if none.
+struct ObsCtx { int start, nobs, off; double lam, pix, piy, vix, viy, tdi; };
+CERB_D bool eval_obs(const SolveParams &P, const Smem &s, const double *x, const double *obs, const int *stereo, const ObsCtx &c, int j, int cam,
+                     double r[2], ProjJac *J) {
+    if (j < c.start || j >= c.start + c.nobs) return false;
+    const int o = c.off + (j - c.start);
+    const int mo = P.maxObs;
+    int kind;
+    if (j == c.start) { if (cam == 0 || !stereo[o]) return false; kind = PROJ_K3; }
+    else if (cam == 0) kind = PROJ_K1;
+    else { if (!stereo[o]) return false; kind = PROJ_K2; }
+    const double pjx = obs[(cam ? 4 : 0) * mo + o], pjy = obs[(cam ? 5 : 1) * mo + o];
+    const double vjx = obs[(cam ? 6 : 2) * mo + o], vjy = obs[(cam ? 7 : 3) * mo + o];
+    const double tdj = obs[8 * mo + o];
+    const int i = c.start;
+    proj_eval(kind, ldm33(s.Rw + 9 * i), ld3(x + ST_POSE + 7 * i), ldm33(s.Rw + 9 * j), ld3(x + ST_POSE + 7 * j),
+              ldm33(s.Rex), ld3(x + ST_EX), ldm33(s.Rex + 9), ld3(x + ST_EX + 7), c.lam, x[ST_TD], c.pix, c.piy, pjx, pjy,
+              c.vix, c.viy, vjx, vjy, c.tdi, tdj, P.sqrt_info, r, J);
+    return true;
+}
+
+// ---- visual part: cost only (candidate evaluation) -------------------------------------------------------
+CERB_D double vision_cost(const SolveParams &P, const Smem &s, int w, const double *x, const double *lam, int tid) {
+    const int nF = P.n_features[w];
+    const double *obs = P.obs + (size_t)w * NOBS_PLANES * P.maxObs;
+    const int *stereo = P.obs_stereo + (size_t)w * P.maxObs;
+    double cost = 0.0;
+    for (int idx = tid; idx < 2 * nF; idx += SOLVE_THREADS) {
+        const int f = idx >> 1, cam = idx & 1;
+        ObsCtx c;
+        c.start = P.feat_start[(size_t)w * P.maxF + f]; c.nobs = P.feat_nobs[(size_t)w * P.maxF + f]; c.off = P.feat_off[(size_t)w * P.maxF + f];
+        c.lam = lam[f];
+        c.pix = obs[0 * P.maxObs + c.off]; c.piy = obs[1 * P.maxObs + c.off]; c.vix = obs[2 * P.maxObs + c.off]; c.viy = obs[3 * P.maxObs + c.off];
+        c.tdi = obs[8 * P.maxObs + c.off];
+        for (int j = c.start; j < c.start + c.nobs; j++) {
+            double r[2];
+            if (!eval_obs(P, s, x, obs, stereo, c, j, cam, r, nullptr)) continue;
+            double cf; huber_weight(P.huber, r[0] * r[0] + r[1] * r[1], &cf);
+            cost += cf;
+        }
+    }
+    return cost;
+}
+
+// ---- visual part: linearisation.  Accumulates the upper triangle of Hxx, g_x, writes W, hh, gl (global) ----
+CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const double *x, const double *lam, double *W, double *hh, double *gl, int tid) {
+    const int nF = P.n_features[w], F = P.maxF;
+    const double *obs = P.obs + (size_t)w * NOBS_PLANES * P.maxObs;
+    const int *stereo = P.obs_stereo + (size_t)w * P.maxObs;
+    double cost = 0.0;
+    for (int i = tid; i < NX * nF; i += SOLVE_THREADS) W[(i / nF) * F + (i % nF)] = 0.0;
+    for (int c0 = 0; c0 < nF; c0 += FT) {
+        const int fl = tid & (FT - 1), cam = (tid >> 6) & 1;
+        const int f = c0 + fl;
+        const bool ev = (tid < 2 * FT) && (f < nF);
+        ObsCtx c; c.start = 0; c.nobs = 0; c.off = 0; c.lam = 1.0; c.pix = c.piy = c.vix = c.viy = c.tdi = 0.0;
+        if (ev) {
+            c.start = P.feat_start[(size_t)w * F + f]; c.nobs = P.feat_nobs[(size_t)w * F + f]; c.off = P.feat_off[(size_t)w * F + f];
+            c.lam = lam[f];
+            c.pix = obs[0 * P.maxObs + c.off]; c.piy = obs[1 * P.maxObs + c.off]; c.vix = obs[2 * P.maxObs + c.off]; c.viy = obs[3 * P.maxObs + c.off];
+            c.tdi = obs[8 * P.maxObs + c.off];
+        }
+        if (tid < 2 * FT) s.ti[tid] = ev ? c.start : 127;
+        __syncthreads();
+        if (tid == 0) {   // anchor range of the chunk
+            int lo = 127, hi = -1;
+            for (int k = 0; k < FT; k++) { const int a = s.ti[k]; if (a != 127) { lo = a < lo ? a : lo; hi = a > hi ? a : hi; } }
+            s.ti[128] = lo; s.ti[129] = hi;
+        }
+        double h = 0.0, gq = 0.0, wI[6], wE0[6], wE1[6];
+        for (int k = 0; k < 6; k++) { wI[k] = 0.0; wE0[k] = 0.0; wE1[k] = 0.0; }
+        __syncthreads();
+        const int amin = s.ti[128], amax = s.ti[129];
+        for (int j = 0; j < NFR; j++) {
+            // --- evaluate the factors of frame j into the tile -------------------------------------------------
+            if (tid < 2 * FT) {
+                double *row0 = s.tile + (2 * tid) * TILE_LD, *row1 = row0 + TILE_LD;
+                double r[2]; ProjJac J;
+                double wjv[6] = {0, 0, 0, 0, 0, 0};
+                if (ev && eval_obs(P, s, x, obs, stereo, c, j, cam, r, &J)) {
+                    double cf; const double hw = huber_weight(P.huber, r[0] * r[0] + r[1] * r[1], &cf);
+                    cost += cf;
+                    for (int k = 0; k < 6; k++) {
+                        row0[k] = hw * J.Ji[k]; row1[k] = hw * J.Ji[6 + k];
+                        row0[6 + k] = hw * J.Jj[k]; row1[6 + k] = hw * J.Jj[6 + k];
+                        row0[12 + k] = hw * J.Je0[k]; row1[12 + k] = hw * J.Je0[6 + k];
+                        row0[18 + k] = hw * J.Je1[k]; row1[18 + k] = hw * J.Je1[6 + k];
+                    }
+                    row0[24] = hw * r[0]; row1[24] = hw * r[1];
+                    const double l0 = hw * J.Jl[0], l1 = hw * J.Jl[1];
+                    h += l0 * l0 + l1 * l1; gq += l0 * row0[24] + l1 * row1[24];
+                    for (int k = 0; k < 6; k++) {
+                        wI[k] += row0[k] * l0 + row1[k] * l1;
+                        wjv[k] = row0[6 + k] * l0 + row1[6 + k] * l1;
+                        wE0[k] += row0[12 + k] * l0 + row1[12 + k] * l1;
+                        wE1[k] += row0[18 + k] * l0 + row1[18 + k] * l1;
+                    }
+                } else {
+                    for (int k = 0; k < TILE_LD; k++) { row0[k] = 0.0; row1[k] = 0.0; }
+                }
+                for (int k = 0; k < 6; k++) s.wj[tid * 8 + k] = wjv[k];
+            }
+            __syncthreads();
+            // --- W rows of frame j: sum of the two cameras -----------------------------------------------------
+            if (tid < FT && ev && j != c.start && j >= c.start && j < c.start + c.nobs)
+                for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] = s.wj[tid * 8 + k] + s.wj[(tid + FT) * 8 + k];
+            // --- J^T J of the tile, one pass per anchor frame present -------------------------------------------
+            for (int a = amin; a <= amax && a <= j; a++) {
+                for (int e = tid; e < 325; e += SOLVE_THREADS) {
+                    // unpack e -> (la <= lb) of the 25 x 25 local matrix [I 6 | J 6 | E0 6 | E1 6 | r]
+                    int la = 0, rem = e;
+                    while (rem >= 25 - la) { rem -= 25 - la; la++; }
+                    const int lb = la + rem;
+                    if (a == j && la < 12) continue;                  // anchor-frame rows (K3) have no pose columns
+                    if (la == 24) continue;                           // r^T r
+                    double acc = 0.0;
+                    for (int t = 0; t < 2 * FT; t++) {
+                        if (s.ti[t] != a) continue;
+                        const double *q0 = s.tile + (2 * t) * TILE_LD;
+                        acc += q0[la] * q0[lb] + q0[TILE_LD + la] * q0[TILE_LD + lb];
+                    }
+                    const int ga = la < 6 ? 6 * a + la : (la < 12 ? 6 * j + la - 6 : 66 + la - 12);
+                    if (lb == 24) s.g[ga] += acc;
+                    else {
+                        const int gb = lb < 6 ? 6 * a + lb : (lb < 12 ? 6 * j + lb - 6 : 66 + lb - 12);
+                        s.Hxx[ga * NX + gb] += acc;
+                    }
+                }
+                __syncthreads();
+            }
+            __syncthreads();
+        }
+        // --- per-feature lambda blocks: h, g_lambda, W rows of the anchor pose and the extrinsics --------------
+        if (tid >= FT && tid < 2 * FT) {
+            double *q = s.tile + (tid - FT) * 20;
+            q[0] = h; q[1] = gq;
+            for (int k = 0; k < 6; k++) { q[2 + k] = wI[k]; q[8 + k] = wE0[k]; q[14 + k] = wE1[k]; }
+        }
+        __syncthreads();
+        if (tid < FT && ev) {
+            const double *q = s.tile + tid * 20;
+            hh[f] = h + q[0]; gl[f] = gq + q[1];
+            for (int k = 0; k < 6; k++) {
+                W[(size_t)(6 * c.start + k) * F + f] = wI[k] + q[2 + k];
+                W[(size_t)(66 + k) * F + f] = wE0[k] + q[8 + k];
+                W[(size_t)(72 + k) * F + f] = wE1[k] + q[14 + k];
+            }
+        }
+        __syncthreads();
+    }
+    return cost;
+}
+
+// ---- inertial part (IMU-leg factors + prior) ------------------------------------------------------------------
+CERB_D void imu_lin_all(const SolveParams &P, Smem &s, int w, const double *x, bool want_jac, int tid) {
+    if (tid < CERB_WINDOW) {
+        const double *pre = P.pre + ((size_t)w * CERB_WINDOW + tid) * PRE_STRIDE;
+        IMULegLin *L = reinterpret_cast<IMULegLin *>(s.lin + 96 * tid);
+        imu_leg_linearize(pre, x + ST_POSE + 7 * tid, x + ST_SB + 9 * tid, x + ST_LB + 4 * tid, x + ST_POSE + 7 * (tid + 1),
+                          x + ST_SB + 9 * (tid + 1), x + ST_LB + 4 * (tid + 1), P.G, want_jac, L);
+    }
+    __syncthreads();
+}
+
+// cost only: 0.5 * sum || S r ||^2 over the valid factors + prior
+CERB_D double inertial_cost(const SolveParams &P, Smem &s, int w, const double *x, int tid) {
+    imu_lin_all(P, s, w, x, false, tid);
+    double cost = 0.0;
+    for (int idx = tid; idx < CERB_WINDOW * 31; idx += SOLVE_THREADS) {
+        const int i = idx / 31, r = idx % 31;
+        const double *pre = P.pre + ((size_t)w * CERB_WINDOW + i) * PRE_STRIDE;
+        if (pre[PRE_SUM_DT] > 10.0) continue;
+        const double *ru = s.lin + 96 * i, *S = P.sinfo + ((size_t)w * CERB_WINDOW + i) * 961;
+        double t = 0.0;
+        for (int q = r; q < 31; q++) t += S[r * 31 + q] * ru[q];
+        cost += 0.5 * t * t;
+    }
+    return cost;
+}
+
+// prior residual r = r0 + J0 dx into s.pr; returns this thread's share of 0.5 ||r||^2
+CERB_D double prior_residual(const SolveParams &P, Smem &s, int w, const double *x, int tid) {
+    const int *meta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
+    if (!meta[0]) return 0.0;
+    const int n = meta[1], nb = meta[2];
+    const double *J = P.prior_J + (size_t)w * PRIOR_LD * PRIOR_LD, *r0 = P.prior_r + (size_t)w * PRIOR_LD, *x0 = P.prior_x0 + (size_t)w * 16 * 7;
+    if (tid < nb) {
+        const int kind = meta[4 + 3 * tid], index = meta[5 + 3 * tid], col = meta[6 + 3 * tid];
+        prior_block_dx(kind, x + prior_block_state_offset(kind, index), x0 + 7 * tid, s.pdx + col);
+    }
+    __syncthreads();
+    double cost = 0.0;
+    for (int i = tid; i < n; i += SOLVE_THREADS) {
+        double t = r0[i];
+        for (int k = 0; k < n; k++) t += J[(size_t)k * n + i] * s.pdx[k];
+        s.pr[i] = t; cost += 0.5 * t * t;
+    }
+    __syncthreads();
+    return cost;
+}
+
+// destination of a local IMU-leg tangent column c (0..37) of factor i: x index (>=0) or -(1 + y index)
+CERB_D int imu_col_dest(int i, int c) {
+    if (c < 6) return 6 * i + c;
+    if (c < 19) return -(1 + NYB * i + (c - 6));
+    if (c < 25) return 6 * (i + 1) + (c - 19);
+    return -(1 + NYB * (i + 1) + (c - 25));
+}
+// add v to H at (a, b) given destinations in the x / y numbering (a, b come from upper-triangular local order)
+CERB_D void scatter_H(Smem &s, int da, int db, double v) {
+    if (da >= 0 && db >= 0) { if (da <= db) s.Hxx[da * NX + db] += v; else s.Hxx[db * NX + da] += v; return; }
+    if (da >= 0) { s.Hxy[da * NY + (-db - 1)] += v; return; }
+    if (db >= 0) { s.Hxy[db * NY + (-da - 1)] += v; return; }
+    const int ya = -da - 1, yb = -db - 1;
+    const int fa = ya / NYB, fb = yb / NYB, ka = ya % NYB, kb = yb % NYB;
+    if (fa == fb) { s.Ad[fa * 169 + ka * NYB + kb] += v; if (ka != kb) s.Ad[fa * 169 + kb * NYB + ka] += v; }
+    else if (fb == fa + 1) s.Bo[fa * 169 + ka * NYB + kb] += v;
+    else s.Bo[fb * 169 + kb * NYB + ka] += v;
+}
+
+CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const double *x, int tid) {
+    double cost = 0.0;
+    imu_lin_all(P, s, w, x, true, tid);
+    for (int i = 0; i < CERB_WINDOW; i++) {
+        const double *pre = P.pre + ((size_t)w * CERB_WINDOW + i) * PRE_STRIDE;
+        if (pre[PRE_SUM_DT] > 10.0) continue;                      // estimator.cpp:1119 (uniform across the CTA)
+        for (int k = tid; k < 31 * 39; k += SOLVE_THREADS) s.Ju[k] = 0.0;
+        __syncthreads();
+        if (tid == 0) {
+            const IMULegLin *L = reinterpret_cast<const IMULegLin *>(s.lin + 96 * i);
+            imu_leg_fill_ju(*L, pre, s.Ju, 39);
+            for (int r = 0; r < 31; r++) s.Ju[r * 39 + 38] = L->ru[r];
+        }
+        __syncthreads();
+        if (tid < 39) {                                           // whiten in place, top row first: Jw = S Ju
+            const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + i) * 961;
+            for (int r = 0; r < 31; r++) {
+                double t = 0.0;
+                for (int q = r; q < 31; q++) t += S[r * 31 + q] * s.Ju[q * 39 + tid];
+                s.Ju[r * 39 + tid] = t;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < 780; e += SOLVE_THREADS) {          // upper triangle of the 39 x 39 Gram matrix
+            int la = 0, rem = e;
+            while (rem >= 39 - la) { rem -= 39 - la; la++; }
+            const int lb = la + rem;
+            double acc = 0.0;
+            for (int r = 0; r < 31; r++) acc += s.Ju[r * 39 + la] * s.Ju[r * 39 + lb];
+            if (la == 38) { cost += 0.5 * acc; continue; }
+            const int da = imu_col_dest(i, la);
+            if (lb == 38) { if (da >= 0) s.g[da] += acc; else s.g[NX + (-da - 1)] += acc; continue; }
+            scatter_H(s, da, imu_col_dest(i, lb), acc);
+        }
+        __syncthreads();
+    }
+    // ---- prior: r = r0 + J0 dx, g += J0^T r, H += J0^T J0 (precomputed once per solve) -------------------
+    const int *meta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
+    if (meta[0]) {
+        cost += prior_residual(P, s, w, x, tid);
+        const int n = meta[1], nb = meta[2];
+        const double *J = P.prior_J + (size_t)w * PRIOR_LD * PRIOR_LD, *Hp = P.prior_Hp + (size_t)w * PRIOR_LD * PRIOR_LD;
+        // column -> destination map in s.ti[0..n)
+        if (tid < nb) {
+            const int kind = meta[4 + 3 * tid], index = meta[5 + 3 * tid], col = meta[6 + 3 * tid];
+            const int local = (kind == 0 || kind == 3) ? 6 : prior_block_size(kind);
+            for (int k = 0; k < local; k++) {
+                int d;
+                if (kind == 0) d = 6 * index + k;
+                else if (kind == 3) d = 66 + 6 * index + k;
+                else if (kind == 1) d = -(1 + NYB * index + k);
+                else if (kind == 2) d = -(1 + NYB * index + 9 + k);
+                else d = 1 << 20;                                      // td: constant this round
+                s.ti[col + k] = d;
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < n; c += SOLVE_THREADS) {
+            const int d = s.ti[c];
+            if (d == (1 << 20)) continue;
+            double t = 0.0;
+            for (int k = 0; k < n; k++) t += J[(size_t)c * n + k] * s.pr[k];
+            if (d >= 0) s.g[d] += t; else s.g[NX + (-d - 1)] += t;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n * n; idx += SOLVE_THREADS) {
+            const int a = idx / n, b = idx % n;
+            if (b < a) continue;
+            const int da = s.ti[a], db = s.ti[b];
+            if (da == (1 << 20) || db == (1 << 20)) continue;
+            scatter_H(s, da, db, Hp[a * PRIOR_LD + b]);
+        }
+        __syncthreads();
+    }
+    return cost;
+}
+
+// x [+] delta -> xc ; lam + dlam -> lamc
+CERB_D void apply_plus(const Smem &s, const double *delta, const double *lam, const double *dlam, double *lamc, int nF, int tid) {
+    if (tid < 11) pose_plus(s.xs + ST_POSE + 7 * tid, delta + 6 * tid, s.xc + ST_POSE + 7 * tid);
+    else if (tid < 13) pose_plus(s.xs + ST_EX + 7 * (tid - 11), delta + 66 + 6 * (tid - 11), s.xc + ST_EX + 7 * (tid - 11));
+    for (int k = tid; k < 99; k += SOLVE_THREADS) { const int f = k / 9, c = k % 9; s.xc[ST_SB + k] = s.xs[ST_SB + k] + delta[NX + NYB * f + c]; }
+    for (int k = tid; k < 44; k += SOLVE_THREADS) { const int f = k / 4, c = k % 4; s.xc[ST_LB + k] = s.xs[ST_LB + k] + delta[NX + NYB * f + 9 + c]; }
+    if (tid == 0) s.xc[ST_TD] = s.xs[ST_TD];
+    for (int f = tid; f < nF; f += SOLVE_THREADS) lamc[f] = lam[f] + dlam[f];
+    __syncthreads();
+}
+
+// ambient squared norm of the active parameter blocks of `a` (or of a - b if b != null)
+CERB_D double ambient_sq(const SolveParams &P, const double *a, const double *b, const double *la, const double *lb, int nF, bool ex_open, int tid) {
+    double t = 0.0;
+    for (int k = tid; k < ST_SIZE; k += SOLVE_THREADS) {
+        if (k >= ST_LB && k < ST_EX && !P.optimize_leg_bias) continue;
+        if (k >= ST_EX && k < ST_TD && !ex_open) continue;
+        if (k == ST_TD) continue;
+        const double v = b ? a[k] - b[k] : a[k];
+        t += v * v;
+    }
+    for (int f = tid; f < nF; f += SOLVE_THREADS) { const double v = lb ? la[f] - lb[f] : la[f]; t += v * v; }
+    return t;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------
+CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolveParams P) {
+    CERB_DYN_SMEM(double, smem_base);
+    Smem s; smem_carve(smem_base, s);
+    const int tid = threadIdx.x;
+    const int F = P.maxF;
+    double *ws = P.ws + (size_t)blockIdx.x * P.ws_stride;
+    double *W = ws + ws_W(F);
+    double *hh = ws + ws_vecs(F), *gl = hh + F, *sl = gl + F, *Dl = sl + F, *ghl = Dl + F, *gnl = ghl + F, *stl = gnl + F, *lamc = stl + F;
+    double *bk = ws + ws_backup(F);
+    double *sca = s.sca;
+    // scalar slots
+    enum { S_RADIUS = 0, S_MU, S_REUSE, S_XCOST, S_CCOST, S_ALPHA, S_GNORM2, S_GNNORM2, S_GDOTGN, S_MODEL, S_STEPNORM, S_XNORM, S_DLNORM,
+           S_OK, S_DONE, S_TERM, S_ITER, S_NSUCC, S_INVALID, S_GMAX, S_INIT_COST, S_P, S_Q };
+
+    for (int w = blockIdx.x; w < P.n_windows; w += gridDim.x) {
+        const int nF = P.n_features[w];
+        const bool ex_open = (P.flags[w] & 1) != 0;
+        double *lam = P.lam + (size_t)w * F;
+        for (int k = tid; k < ST_STRIDE; k += SOLVE_THREADS) s.xs[k] = (k < ST_SIZE) ? P.state[(size_t)w * ST_STRIDE + k] : 0.0;
+        if (tid == 0) {
+            sca[S_RADIUS] = P.radius0; sca[S_MU] = 1e-8; sca[S_REUSE] = 0; sca[S_DONE] = 0; sca[S_TERM] = 1; sca[S_ITER] = 0; sca[S_NSUCC] = 0;
+            sca[S_INVALID] = 0; sca[S_DLNORM] = 0;
+        }
+        __syncthreads();
+        bool need_linearize = true;
+        int iteration = 0;
+
+        while (true) {
+            // =============================== linearise at xs ===========================================
+            if (need_linearize) {
+                for (int k = tid; k < 6084; k += SOLVE_THREADS) s.Hxx[k] = 0.0;
+                for (int k = tid; k < NRP; k += SOLVE_THREADS) s.g[k] = 0.0;
+                load_geometry(s.xs, s, tid);
+                double part[2];
+                part[0] = vision_linearize(P, s, w, s.xs, lam, W, hh, gl, tid);
+                for (int k = tid; k < 11154; k += SOLVE_THREADS) s.Hxy[k] = 0.0;     // the tile aliased Hxy
+                for (int k = tid; k < 1859; k += SOLVE_THREADS) s.Ad[k] = 0.0;
+                for (int k = tid; k < 1690; k += SOLVE_THREADS) s.Bo[k] = 0.0;
+                __syncthreads();
+                part[0] += inertial_linearize(P, s, w, s.xs, tid);
+                part[1] = ambient_sq(P, s.xs, nullptr, lam, nullptr, nF, ex_open, tid);
+                double tot[2];
+                block_sum<2>(part, s.red, tot, tid);
+                if (tid == 0) { sca[S_XCOST] = tot[0]; sca[S_XNORM] = sqrt(tot[1]); if (iteration == 0) sca[S_INIT_COST] = tot[0]; }
+                // symmetrise Hxx (upper -> lower)
+                for (int k = tid; k < NX * NX; k += SOLVE_THREADS) { const int a = k / NX, b = k % NX; if (a > b) s.Hxx[k] = s.Hxx[b * NX + a]; }
+                __syncthreads();
+                // gradient max norm over active dims (unscaled), Jacobi scale at iteration 0
+                if (iteration == 0) {
+                    for (int k = tid; k < NR; k += SOLVE_THREADS) {
+                        double d;
+                        bool active = true;
+                        if (k < NX) { d = s.Hxx[k * NX + k]; if (k >= 66 && !ex_open) active = false; }
+                        else { const int yk = k - NX, f = yk / NYB, c = yk % NYB; d = s.Ad[f * 169 + c * NYB + c]; if (c >= 9 && !P.optimize_leg_bias) active = false; }
+                        s.sc[k] = active ? 1.0 / (1.0 + sqrt(d)) : 0.0;
+                    }
+                    for (int f = tid; f < nF; f += SOLVE_THREADS) sl[f] = 1.0 / (1.0 + sqrt(hh[f]));
+                }
+                __syncthreads();
+                if (P.dbg && w == P.dbg_window && iteration == 0) {      // parity probe, ABI order
+                    for (int k = tid; k < NR; k += SOLVE_THREADS) {
+                        int dst; double d;
+                        if (k < NX) { dst = k; d = s.Hxx[k * NX + k]; }
+                        else { const int yk = k - NX, f = yk / NYB, c = yk % NYB; dst = c < 9 ? 78 + 9 * f + c : 177 + 4 * f + (c - 9); d = s.Ad[f * 169 + c * NYB + c]; }
+                        const bool act = s.sc[k] != 0.0;
+                        P.dbg[1 + dst] = act ? s.g[k] : 0.0; P.dbg[1 + NR + F + dst] = act ? d : 0.0;
+                    }
+                    for (int f = tid; f < nF; f += SOLVE_THREADS) { P.dbg[1 + NR + f] = gl[f]; P.dbg[1 + NR + F + NR + f] = hh[f]; }
+                    if (tid == 0) P.dbg[0] = sca[S_XCOST];
+                }
+                double gm = 0.0;
+                for (int k = tid; k < NR; k += SOLVE_THREADS) if (s.sc[k] != 0.0) gm = fmax(gm, fabs(s.g[k]));
+                for (int f = tid; f < nF; f += SOLVE_THREADS) gm = fmax(gm, fabs(gl[f]));
+                s.red[tid] = gm;
+                __syncthreads();
+                for (int st = 128; st > 0; st >>= 1) { if (tid < st) s.red[tid] = fmax(s.red[tid], s.red[tid + st]); __syncthreads(); }
+                if (tid == 0) sca[S_GMAX] = s.red[0];
+                __syncthreads();
+                // apply the Jacobi scaling: H~ = S H S, g~ = S g, w~_f = s_f S_x w_f, h~ = s_f^2 h, gl~ = s_f gl
+                for (int k = tid; k < NX * NX; k += SOLVE_THREADS) s.Hxx[k] *= s.sc[k / NX] * s.sc[k % NX];
+                for (int k = tid; k < NX * NY; k += SOLVE_THREADS) s.Hxy[k] *= s.sc[k / NY] * s.sc[NX + k % NY];
+                for (int k = tid; k < 1859; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; s.Ad[k] *= s.sc[NX + NYB * f + a] * s.sc[NX + NYB * f + b]; }
+                for (int k = tid; k < 1690; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; s.Bo[k] *= s.sc[NX + NYB * f + a] * s.sc[NX + NYB * (f + 1) + b]; }
+                for (int k = tid; k < NR; k += SOLVE_THREADS) s.g[k] *= s.sc[k];
+                for (int k = tid; k < NX * nF; k += SOLVE_THREADS) { const int a = k / nF, f = k % nF; W[(size_t)a * F + f] *= s.sc[a] * sl[f]; }
+                for (int f = tid; f < nF; f += SOLVE_THREADS) { hh[f] *= sl[f] * sl[f]; gl[f] *= sl[f]; }
+                __syncthreads();
+                // pristine copy for the mu-retry path
+                for (int k = tid; k < 6084; k += SOLVE_THREADS) bk[k] = s.Hxx[k];
+                for (int k = tid; k < 11154; k += SOLVE_THREADS) bk[6084 + k] = s.Hxy[k];
+                for (int k = tid; k < 1859; k += SOLVE_THREADS) bk[6084 + 11154 + k] = s.Ad[k];
+                for (int k = tid; k < 1690; k += SOLVE_THREADS) bk[6084 + 11154 + 1859 + k] = s.Bo[k];
+                __syncthreads();
+                need_linearize = false;
+            }
+            // =============================== FinalizeIterationAndCheckIfMinimizerCanContinue =============
+            if (tid == 0) {
+                if (iteration >= P.max_iters) { sca[S_DONE] = 1; sca[S_TERM] = 1; }
+                else if (sca[S_GMAX] <= P.gtol) { sca[S_DONE] = 1; sca[S_TERM] = 0; }
+                else if (sca[S_RADIUS] <= P.min_radius) { sca[S_DONE] = 1; sca[S_TERM] = 0; }
+                else if (!(sca[S_XCOST] == sca[S_XCOST]) || fabs(sca[S_XCOST]) > 1e300) { sca[S_DONE] = 1; sca[S_TERM] = 2; }
+            }
+            __syncthreads();
+            if (sca[S_DONE] != 0.0) break;
+            iteration++;
+
+            // =============================== DoglegStrategy::ComputeStep ===================================
+            if (sca[S_REUSE] == 0.0) {
+                // diagonal, gradient / D, Cauchy point
+                for (int k = tid; k < NR; k += SOLVE_THREADS) {
+                    const double d = (k < NX) ? s.Hxx[k * NX + k] : s.Ad[((k - NX) / NYB) * 169 + ((k - NX) % NYB) * (NYB + 1)];
+                    const double D = sqrt(fmin(fmax(d, 1e-6), 1e32));
+                    s.D[k] = D; s.gh[k] = s.g[k] / D; s.yv[k] = s.gh[k] / D;      // yv = v = scaled gradient
+                }
+                for (int f = tid; f < nF; f += SOLVE_THREADS) { const double D = sqrt(fmin(fmax(hh[f], 1e-6), 1e32)); Dl[f] = D; ghl[f] = gl[f] / D; stl[f] = ghl[f] / D; }
+                __syncthreads();
+                double part[2] = {0.0, 0.0};     // [0] v^T H v  [1] ||gh||^2
+                for (int k = tid; k < NX * NX; k += SOLVE_THREADS) part[0] += s.yv[k / NX] * s.Hxx[k] * s.yv[k % NX];
+                for (int k = tid; k < NX * NY; k += SOLVE_THREADS) part[0] += 2.0 * s.yv[k / NY] * s.Hxy[k] * s.yv[NX + k % NY];
+                for (int k = tid; k < 1859; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; part[0] += s.yv[NX + NYB * f + a] * s.Ad[k] * s.yv[NX + NYB * f + b]; }
+                for (int k = tid; k < 1690; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; part[0] += 2.0 * s.yv[NX + NYB * f + a] * s.Bo[k] * s.yv[NX + NYB * (f + 1) + b]; }
+                for (int f = tid; f < nF; f += SOLVE_THREADS) {
+                    double wv = 0.0;
+                    for (int a = 0; a < NX; a++) wv += W[(size_t)a * F + f] * s.yv[a];
+                    part[0] += 2.0 * stl[f] * wv + hh[f] * stl[f] * stl[f];
+                    part[1] += ghl[f] * ghl[f];
+                }
+                for (int k = tid; k < NR; k += SOLVE_THREADS) part[1] += s.gh[k] * s.gh[k];
+                double tot[2];
+                block_sum<2>(part, s.red, tot, tid);
+                if (tid == 0) { sca[S_GNORM2] = tot[1]; sca[S_ALPHA] = tot[1] / tot[0]; }
+                __syncthreads();
+
+                // ---- Gauss-Newton step: (H~ + mu D^2) y = g~, retry with mu *= 10 on failure ----------------
+                bool first_attempt = true;
+                while (true) {
+                    const double mu = sca[S_MU];
+                    if (!(mu < 1.0)) { if (tid == 0) sca[S_OK] = 0; __syncthreads(); break; }
+                    if (!first_attempt) {
+                        for (int k = tid; k < 6084; k += SOLVE_THREADS) s.Hxx[k] = bk[k];
+                        for (int k = tid; k < 11154; k += SOLVE_THREADS) s.Hxy[k] = bk[6084 + k];
+                        for (int k = tid; k < 1859; k += SOLVE_THREADS) s.Ad[k] = bk[6084 + 11154 + k];
+                        for (int k = tid; k < 1690; k += SOLVE_THREADS) s.Bo[k] = bk[6084 + 11154 + 1859 + k];
+                    }
+                    first_attempt = false;
+                    if (tid == 0) sca[S_OK] = 1;
+                    __syncthreads();
+                    // rhs: yv[0..NR) = g~ ; regularise the diagonals
+                    for (int k = tid; k < NR; k += SOLVE_THREADS) {
+                        s.yv[k] = s.g[k];
+                        if (k < NX) s.Hxx[k * NX + k] += mu * s.D[k] * s.D[k];
+                        else s.Ad[((k - NX) / NYB) * 169 + ((k - NX) % NYB) * (NYB + 1)] += mu * s.D[k] * s.D[k];
+                    }
+                    __syncthreads();
+                    if (tid < 32) {
+                        // ---- warp 0: block-bidiagonal Cholesky of Hyy: Ad[f] <- L_f (lower), Bo[f] <- M_f = B_f^T L_f^-T ----
+                        const int lane = tid;
+                        for (int f = 0; f < NFR; f++) {
+                            double *A = s.Ad + f * 169;
+                            if (f > 0) {
+                                const double *M = s.Bo + (f - 1) * 169;        // M[r][c], r: y_f index, c: y_{f-1} index
+                                for (int e = lane; e < 169; e += 32) { const int r = e / NYB, c = e % NYB; if (c > r) continue; double t = 0.0; for (int q = 0; q < NYB; q++) t += M[r * NYB + q] * M[c * NYB + q]; A[e] -= t; }
+                                __syncwarp();
+                            }
+                            for (int j = 0; j < NYB; j++) {
+                                if (lane == 0) { double t = A[j * NYB + j]; for (int q = 0; q < j; q++) t -= A[j * NYB + q] * A[j * NYB + q]; if (!(t > 0.0)) { sca[S_OK] = 0; t = 1.0; } A[j * NYB + j] = sqrt(t); }
+                                __syncwarp();
+                                if (lane > j && lane < NYB) { double t = A[lane * NYB + j]; for (int q = 0; q < j; q++) t -= A[lane * NYB + q] * A[j * NYB + q]; A[lane * NYB + j] = t / A[j * NYB + j]; }
+                                __syncwarp();
+                            }
+                            if (f < NFR - 1) {
+                                double *B = s.Bo + f * 169;                     // in: B[k1][k2] = H(y_f[k1], y_{f+1}[k2]); out: M[r][c]
+                                double row[NYB];
+                                if (lane < NYB) {
+                                    const int r = lane;
+                                    for (int c = 0; c < NYB; c++) { double t = B[c * NYB + r]; for (int q = 0; q < c; q++) t -= row[q] * A[c * NYB + q]; row[c] = t / A[c * NYB + c]; }
+                                }
+                                __syncwarp();
+                                if (lane < NYB) for (int c = 0; c < NYB; c++) B[lane * NYB + c] = row[c];
+                                __syncwarp();
+                            }
+                        }
+                    } else {
+                        // ---- other warps: eliminate the inverse depths  S = Hxx - W diag(1/(h + mu D^2)) W^T ----------
+                        const int t2 = tid - 32, n2 = SOLVE_THREADS - 32;
+                        for (int e = t2; e < NX * (NX + 1) / 2 + NX; e += n2) {
+                            if (e >= NX * (NX + 1) / 2) {           // rhs_x
+                                const int a = e - NX * (NX + 1) / 2;
+                                double t = 0.0;
+                                for (int f = 0; f < nF; f++) t += W[(size_t)a * F + f] * gl[f] / (hh[f] + mu * Dl[f] * Dl[f]);
+                                s.yv[a] -= t;
+                                continue;
+                            }
+                            int a = 0, rem = e;
+                            while (rem >= NX - a) { rem -= NX - a; a++; }
+                            const int b = a + rem;
+                            double t = 0.0;
+                            for (int f = 0; f < nF; f++) t += W[(size_t)a * F + f] * W[(size_t)b * F + f] / (hh[f] + mu * Dl[f] * Dl[f]);
+                            s.Hxx[b * NX + a] -= t;                   // lower triangle is the one factored below
+                            if (a != b) s.Hxx[a * NX + b] -= t;
+                        }
+                    }
+                    __syncthreads();
+                    // ---- T = L^-1 Hyx (row a of Hxy in place), and the same for the y part of the rhs (row 78) ----
+                    if (tid <= NX) {
+                        double *row = (tid < NX) ? s.Hxy + tid * NY : s.yv + NX;
+                        for (int f = 0; f < NFR; f++) {
+                            const double *L = s.Ad + f * 169;
+                            double *t = row + NYB * f;
+                            if (f > 0) {
+                                const double *M = s.Bo + (f - 1) * 169; const double *tp = row + NYB * (f - 1);
+                                for (int r = 0; r < NYB; r++) { double acc = 0.0; for (int q = 0; q < NYB; q++) acc += M[r * NYB + q] * tp[q]; t[r] -= acc; }
+                            }
+                            for (int r = 0; r < NYB; r++) { double acc = t[r]; for (int q = 0; q < r; q++) acc -= L[r * NYB + q] * t[q]; t[r] = acc / L[r * NYB + r]; }
+                        }
+                    }
+                    __syncthreads();
+                    // ---- S' = S - T T^T (lower), rhs'_x = rhs_x - T gy' -------------------------------------------
+                    for (int e = tid; e < NX * (NX + 1) / 2 + NX; e += SOLVE_THREADS) {
+                        if (e >= NX * (NX + 1) / 2) {
+                            const int a = e - NX * (NX + 1) / 2;
+                            double t = 0.0;
+                            for (int q = 0; q < NY; q++) t += s.Hxy[a * NY + q] * s.yv[NX + q];
+                            s.yv[a] -= t;
+                            continue;
+                        }
+                        int a = 0, rem = e;
+                        while (rem >= NX - a) { rem -= NX - a; a++; }
+                        const int b = a + rem;
+                        double t = 0.0;
+                        for (int q = 0; q < NY; q++) t += s.Hxy[a * NY + q] * s.Hxy[b * NY + q];
+                        s.Hxx[b * NX + a] -= t;
+                    }
+                    __syncthreads();
+                    // ---- dense Cholesky of the 78 x 78 lower triangle, rhs carried as an extra row (z = L^-1 rhs) ----
+                    for (int k = 0; k < NX; k++) {
+                        if (tid == 0) { double d = s.Hxx[k * NX + k]; if (!(d > 0.0)) { sca[S_OK] = 0; d = 1.0; } s.Hxx[k * NX + k] = sqrt(d); }
+                        __syncthreads();
+                        const double piv = s.Hxx[k * NX + k];
+                        for (int i = k + 1 + tid; i <= NX; i += SOLVE_THREADS) { if (i < NX) s.Hxx[i * NX + k] /= piv; else s.yv[k] /= piv; }
+                        __syncthreads();
+                        const int m = NX - 1 - k;                        // trailing size
+                        for (int e = tid; e < m * (m + 1) / 2 + m; e += SOLVE_THREADS) {
+                            if (e >= m * (m + 1) / 2) { const int i = k + 1 + (e - m * (m + 1) / 2); s.yv[i] -= s.Hxx[i * NX + k] * s.yv[k]; continue; }
+                            int a = 0, rem = e;
+                            while (rem >= m - a) { rem -= m - a; a++; }
+                            const int j = k + 1 + a, i = j + rem;       // i >= j > k
+                            s.Hxx[i * NX + j] -= s.Hxx[i * NX + k] * s.Hxx[j * NX + k];
+                        }
+                        __syncthreads();
+                    }
+                    // ---- back substitution L^T y_x = z by warp 0 (column oriented) -------------------------------------
+                    if (tid < 32) {
+                        for (int k = NX - 1; k >= 0; k--) {
+                            if (tid == 0) s.yv[k] /= s.Hxx[k * NX + k];
+                            __syncwarp();
+                            const double yk = s.yv[k];
+                            for (int i = tid; i < k; i += 32) s.yv[i] -= s.Hxx[k * NX + i] * yk;
+                            __syncwarp();
+                        }
+                    }
+                    __syncthreads();
+                    // ---- y part: u = gy' - T^T y_x, then L^T y_y = u blockwise (warp 0) ------------------------------------
+                    for (int q = tid; q < NY; q += SOLVE_THREADS) { double t = 0.0; for (int a = 0; a < NX; a++) t += s.Hxy[a * NY + q] * s.yv[a]; s.yv[NX + q] -= t; }
+                    __syncthreads();
+                    if (tid < 32) {
+                        for (int f = NFR - 1; f >= 0; f--) {
+                            double *u = s.yv + NX + NYB * f;
+                            const double *L = s.Ad + f * 169;
+                            if (f < NFR - 1) {
+                                const double *M = s.Bo + f * 169; const double *yn = s.yv + NX + NYB * (f + 1);
+                                if (tid < NYB) { double t = 0.0; for (int r = 0; r < NYB; r++) t += M[r * NYB + tid] * yn[r]; u[tid] -= t; }
+                                __syncwarp();
+                            }
+                            for (int k = NYB - 1; k >= 0; k--) {
+                                if (tid == 0) u[k] /= L[k * NYB + k];
+                                __syncwarp();
+                                if (tid < k) u[tid] -= L[k * NYB + tid] * u[k];
+                                __syncwarp();
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    // ---- inverse depths: y_l = (gl - w^T y_x) / (h + mu D^2) ; validity ---------------------------------------
+                    double bad = 0.0;
+                    for (int f = tid; f < nF; f += SOLVE_THREADS) {
+                        double t = gl[f];
+                        for (int a = 0; a < NX; a++) t -= W[(size_t)a * F + f] * s.yv[a];
+                        const double y = t / (hh[f] + mu * Dl[f] * Dl[f]);
+                        gnl[f] = y;
+                        if (!(fabs(y) < 1e300)) bad = 1.0;
+                    }
+                    for (int k = tid; k < NR; k += SOLVE_THREADS) if (!(fabs(s.yv[k]) < 1e300)) bad = 1.0;
+                    if (bad != 0.0) sca[S_OK] = 0;          // benign race: every writer stores 0
+                    __syncthreads();
+                    if (sca[S_OK] != 0.0) break;
+                    if (tid == 0) sca[S_MU] = mu * 10.0;
+                    __syncthreads();
+                }
+                if (sca[S_OK] != 0.0) {
+                    // gauss_newton_step = -D * y ; norms for the dogleg
+                    double part3[2] = {0.0, 0.0};    // ||gn||^2, gh . gn
+                    for (int k = tid; k < NR; k += SOLVE_THREADS) { const double v = -s.D[k] * s.yv[k]; s.gn[k] = v; part3[0] += v * v; part3[1] += s.gh[k] * v; }
+                    for (int f = tid; f < nF; f += SOLVE_THREADS) { const double v = -Dl[f] * gnl[f]; gnl[f] = v; part3[0] += v * v; part3[1] += ghl[f] * v; }
+                    double tot3[2];
+                    block_sum<2>(part3, s.red, tot3, tid);
+                    if (tid == 0) { sca[S_GNNORM2] = tot3[0]; sca[S_GDOTGN] = tot3[1]; }
+                    __syncthreads();
+                }
+                if (tid == 0) sca[S_REUSE] = 1;
+                __syncthreads();
+            }
+            // =============================== step validity =================================================
+            if (sca[S_OK] == 0.0) {       // LINEAR_SOLVER_FAILURE -> HandleInvalidStep
+                if (tid == 0) {
+                    sca[S_INVALID] += 1;
+                    if (sca[S_INVALID] >= 5) { sca[S_DONE] = 1; sca[S_TERM] = 2; }
+                    sca[S_MU] *= 10.0; sca[S_REUSE] = 0;      // StepIsInvalid
+                    if (sca[S_MU] >= 1.0) sca[S_MU] = 1.0 - 1e-12;   // keep retrying like Ceres does at max_mu
+                }
+                __syncthreads();
+                if (sca[S_DONE] != 0.0) break;
+                need_linearize = true;     // the failed factorisation overwrote H; rebuild it at the same point
+                continue;
+            }
+            // =============================== ComputeTraditionalDoglegStep ====================================
+            if (tid == 0) {
+                const double radius = sca[S_RADIUS], alpha = sca[S_ALPHA];
+                const double gradient_norm = sqrt(sca[S_GNORM2]), gauss_newton_norm = sqrt(sca[S_GNNORM2]);
+                double p, q, nrm;
+                if (gauss_newton_norm <= radius) { p = 0.0; q = 1.0; nrm = gauss_newton_norm; }
+                else if (gradient_norm * alpha >= radius) { p = -(radius / gradient_norm); q = 0.0; nrm = radius; }
+                else {
+                    const double b_dot_a = -alpha * sca[S_GDOTGN];
+                    const double a_squared_norm = (alpha * gradient_norm) * (alpha * gradient_norm);
+                    const double b_minus_a_squared_norm = a_squared_norm - 2 * b_dot_a + gauss_newton_norm * gauss_newton_norm;
+                    const double c = b_dot_a - a_squared_norm;
+                    const double d = sqrt(c * c + b_minus_a_squared_norm * (radius * radius - a_squared_norm));
+                    const double beta = (c <= 0) ? (d - c) / b_minus_a_squared_norm : (radius * radius - a_squared_norm) / (d + c);
+                    p = -alpha * (1.0 - beta); q = beta;
+                    nrm = sqrt(p * p * sca[S_GNORM2] + 2 * p * q * sca[S_GDOTGN] + q * q * sca[S_GNNORM2]);
+                }
+                sca[S_P] = p; sca[S_Q] = q; sca[S_DLNORM] = nrm;
+                // model_cost_change = -(step^T g~ + 0.5 step^T H~ step) with step = (p gh + q gn) / D, using
+                // H~ (gn/D) = -(g~ + mu D gn)  (the Gauss-Newton equations):
+                const double mu = sca[S_MU], g2 = sca[S_GNORM2], gg = sca[S_GDOTGN], n2 = sca[S_GNNORM2];
+                const double sTg = p * g2 + q * gg;
+                const double sHs = p * p * (g2 / alpha) - 2.0 * p * q * (g2 + mu * gg) + q * q * (-gg - mu * n2);
+                sca[S_MODEL] = -(sTg + 0.5 * sHs);
+            }
+            __syncthreads();
+            if (!(sca[S_MODEL] > 0.0)) {   // invalid step
+                if (tid == 0) {
+                    sca[S_INVALID] += 1;
+                    if (sca[S_INVALID] >= 5) { sca[S_DONE] = 1; sca[S_TERM] = 2; }
+                    sca[S_MU] *= 10.0; sca[S_REUSE] = 0;
+                    if (sca[S_MU] >= 1.0) sca[S_MU] = 1.0 - 1e-12;
+                }
+                __syncthreads();
+                if (sca[S_DONE] != 0.0) break;
+                need_linearize = true;     // the factorisation overwrote H; rebuild it at the same point
+                continue;
+            }
+            if (tid == 0) sca[S_INVALID] = 0;
+            // delta = ((p gh + q gn) / D) * jacobi_scale
+            {
+                const double p = sca[S_P], q = sca[S_Q];
+                for (int k = tid; k < NR; k += SOLVE_THREADS) s.stp[k] = (p * s.gh[k] + q * s.gn[k]) / s.D[k] * s.sc[k];
+                for (int f = tid; f < nF; f += SOLVE_THREADS) stl[f] = (p * ghl[f] + q * gnl[f]) / Dl[f] * sl[f];
+            }
+            __syncthreads();
+            // =============================== candidate point and its cost ===================================
+            apply_plus(s, s.stp, lam, stl, lamc, nF, tid);
+            load_geometry(s.xc, s, tid);
+            {
+                double part[2];
+                part[0] = vision_cost(P, s, w, s.xc, lamc, tid) + inertial_cost(P, s, w, s.xc, tid) + prior_residual(P, s, w, s.xc, tid);
+                part[1] = ambient_sq(P, s.xs, s.xc, lam, lamc, nF, ex_open, tid);
+                double tot[2];
+                block_sum<2>(part, s.red, tot, tid);
+                if (tid == 0) {
+                    double cc = tot[0];
+                    if (!(cc == cc) || fabs(cc) > 1e300) cc = 1.7976931348623157e308;
+                    sca[S_CCOST] = cc; sca[S_STEPNORM] = sqrt(tot[1]);
+                }
+            }
+            __syncthreads();
+            // =============================== tolerances, accept / reject =====================================
+            bool accepted = false;
+            if (tid == 0) {
+                const double x_cost = sca[S_XCOST], cand = sca[S_CCOST];
+                if (sca[S_STEPNORM] <= P.ptol * (sca[S_XNORM] + P.ptol)) { sca[S_DONE] = 1; sca[S_TERM] = 0; }
+                else if (fabs(x_cost - cand) <= P.ftol * x_cost) { sca[S_DONE] = 1; sca[S_TERM] = 0; }
+                else {
+                    const double rel = (x_cost - cand) / sca[S_MODEL];
+                    if (rel > P.min_rel_dec) {            // StepAccepted
+                        if (rel < 0.25) sca[S_RADIUS] *= 0.5;
+                        if (rel > 0.75) sca[S_RADIUS] = fmax(sca[S_RADIUS], 3.0 * sca[S_DLNORM]);
+                        sca[S_MU] = fmax(1e-8, 2.0 * sca[S_MU] / 10.0);
+                        sca[S_REUSE] = 0; sca[S_NSUCC] += 1; sca[S_OK] = 2;     // 2 == accepted marker
+                    } else {                              // StepRejected
+                        sca[S_RADIUS] *= 0.5; sca[S_REUSE] = 1; sca[S_OK] = 1;
+                    }
+                }
+            }
+            __syncthreads();
+            if (sca[S_DONE] != 0.0) break;
+            accepted = (sca[S_OK] == 2.0);
+            __syncthreads();
+            if (accepted) {
+                for (int k = tid; k < ST_STRIDE; k += SOLVE_THREADS) s.xs[k] = s.xc[k];
+                for (int f = tid; f < nF; f += SOLVE_THREADS) lam[f] = lamc[f];
+                if (tid == 0) sca[S_OK] = 1;
+                __syncthreads();
+                need_linearize = true;
+            }
+        }
+        // ---- write back ---------------------------------------------------------------------------------
+        for (int k = tid; k < ST_SIZE; k += SOLVE_THREADS) P.state[(size_t)w * ST_STRIDE + k] = s.xs[k];
+        if (tid == 0) {
+            P.rep_i[4 * w + 0] = iteration; P.rep_i[4 * w + 1] = (int)sca[S_NSUCC]; P.rep_i[4 * w + 2] = (int)sca[S_TERM];
+            P.rep_i[4 * w + 3] = (sca[S_XCOST] == sca[S_XCOST] && fabs(sca[S_XCOST]) < 1e300) ? 0 : 4;
+            P.rep_d[2 * w + 0] = sca[S_INIT_COST]; P.rep_d[2 * w + 1] = sca[S_XCOST];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace cerb

@@ -1,0 +1,159 @@
+"""ctypes binding of libcerberus_b200.so (the C ABI of include/cerberus_b200.h).
+
+The product library is the nvcc-built sm_100a one next to this file; it has no CPU fallback and
+`Backend()` raises if it (or a CUDA device) is missing.  Tests that run without a GPU pass the path of
+the CPU kernel *simulator* build (tests/cusim) explicitly -- that is test infrastructure, never a default.
+"""
+import ctypes as C
+import os
+import numpy as np
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(_HERE, "libcerberus_b200.so")
+
+
+class CerbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cerberus_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(abi.c_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Backend:
+    """One CerbHandle.  Implements the hot-path calls, the factor-family evaluators, device preintegration and
+    the `backend` protocol of cerberus_b200.synth (preintegrate / marginalize)."""
+
+    def __init__(self, cfg=None, lib_path=None):
+        path = lib_path or PRODUCT_LIB
+        if not os.path.exists(path):
+            raise CerbError(abi.ERR_NO_DEVICE, f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.cerb_last_error.restype = C.c_char_p
+        L.cerb_version.restype = C.c_char_p
+        L.cerb_create.argtypes = [C.POINTER(abi.SolverConfig), C.POINTER(C.c_void_p)]
+        L.cerb_destroy.argtypes = [C.c_void_p]
+        L.cerb_solve_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.WindowDesc), C.POINTER(abi.WindowState), C.POINTER(abi.SolveReport)]
+        L.cerb_solve_window.argtypes = [C.c_void_p, C.POINTER(abi.WindowDesc), C.POINTER(abi.WindowState), C.POINTER(abi.SolveReport)]
+        L.cerb_batch_upload.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.WindowDesc), C.POINTER(abi.WindowState)]
+        L.cerb_batch_solve_resident.argtypes = [C.c_void_p]
+        L.cerb_batch_download.argtypes = [C.c_void_p, C.POINTER(abi.WindowState), C.POINTER(abi.SolveReport)]
+        L.cerb_sync.argtypes = [C.c_void_p]
+        L.cerb_last_solve_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+        L.cerb_debug_linearize.argtypes = [C.c_void_p, C.c_int32, abi.c_dp, abi.c_dp, abi.c_dp, C.c_int32]
+        L.cerb_eval_projection.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [abi.c_dp] * 14
+        L.cerb_eval_imu_leg.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.IMULegPreint), abi.c_dp, abi.c_dp, abi.c_dp, abi.c_dp]
+        L.cerb_eval_prior.argtypes = [C.c_void_p, C.POINTER(abi.Prior), C.POINTER(abi.WindowState), abi.c_dp, abi.c_dp]
+        L.cerb_preintegrate_batch.argtypes = [C.c_void_p, C.POINTER(abi.PreintConfig), C.c_int32, C.POINTER(abi.PreintJob), C.POINTER(abi.IMULegPreint)]
+        L.cerb_a1_kinematics.argtypes = [C.c_void_p, C.c_int32] + [abi.c_dp] * 8
+        L.cerb_double2vector.argtypes = [C.POINTER(abi.WindowState), C.POINTER(abi.WindowState), abi.c_dp, abi.c_dp, abi.c_dp]
+        L.cerb_double2vector.restype = None
+        self.cfg = cfg or abi.default_config()
+        self.h = C.c_void_p()
+        self._check(L.cerb_create(C.byref(self.cfg), C.byref(self.h)))
+
+    def _check(self, rc, allow=()):
+        if rc != 0 and rc not in allow:
+            raise CerbError(rc, self.lib.cerb_last_error().decode())
+        return rc
+
+    def close(self):
+        if self.h:
+            self.lib.cerb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def version(self):
+        return self.lib.cerb_version().decode()
+
+    # ---- the hot path ------------------------------------------------------------------------------
+    def solve_batch(self, batch):
+        """Host buffers in / out (the drop-in call): pack + H2D + solve + D2H.  Returns the report array."""
+        self._check(self.lib.cerb_solve_batch(self.h, batch.n, batch.descs, batch.states, batch.reports), allow=(abi.ERR_NON_FINITE,))
+        return batch.report_array().copy()
+
+    def solve_window(self, batch, w):
+        self._check(self.lib.cerb_solve_window(self.h, C.byref(batch.descs[w]), C.byref(batch.states[w]), C.byref(batch.reports[w])), allow=(abi.ERR_NON_FINITE,))
+
+    def upload(self, batch):
+        self._check(self.lib.cerb_batch_upload(self.h, batch.n, batch.descs, batch.states))
+
+    def solve_resident(self):
+        self._check(self.lib.cerb_batch_solve_resident(self.h))
+
+    def download(self, batch):
+        self._check(self.lib.cerb_batch_download(self.h, batch.states, batch.reports), allow=(abi.ERR_NON_FINITE,))
+        return batch.report_array().copy()
+
+    def sync(self):
+        self._check(self.lib.cerb_sync(self.h))
+
+    def last_solve_stats(self):
+        ms, nl = C.c_double(), C.c_int32()
+        self._check(self.lib.cerb_last_solve_stats(self.h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def debug_linearize(self, batch, w):
+        """cost, gradient, diag(J^T J) of resident window w at its initial state (ABI tangent order)."""
+        nf = batch.descs[w].n_features
+        g, d = np.zeros(abi.NUM_REDUCED + nf), np.zeros(abi.NUM_REDUCED + nf)
+        cost = C.c_double()
+        self._check(self.lib.cerb_debug_linearize(self.h, w, C.cast(C.byref(cost), abi.c_dp), _p(g), _p(d), g.size))
+        return cost.value, g, d
+
+    # ---- factor families -----------------------------------------------------------------------------
+    def eval_projection(self, kind, pose_i, pose_j, ex0, ex1, inv_dep, td, pts_i, pts_j, vel_i, vel_j, td_i, td_j, want_jac=True):
+        n = inv_dep.shape[0]
+        args = [None if a is None else _f64(a) for a in (pose_i, pose_j, ex0, ex1, inv_dep, td, pts_i, pts_j, vel_i, vel_j, td_i, td_j)]
+        res = np.zeros((n, 2))
+        jac = np.zeros((n, abi.PROJ_JAC_SIZE[kind])) if want_jac else None
+        self._check(self.lib.cerb_eval_projection(self.h, kind, n, *[_p(a) for a in args], _p(res), _p(jac)))
+        return res, jac
+
+    def eval_imu_leg(self, preint, params, want_jac=True):
+        n = params.shape[0]
+        params = _f64(params)
+        res, si = np.zeros((n, 31)), np.zeros((n, 961))
+        jac = np.zeros((n, 31 * 40)) if want_jac else None
+        self._check(self.lib.cerb_eval_imu_leg(self.h, n, preint.ctypes.data_as(C.POINTER(abi.IMULegPreint)), _p(params), _p(res), _p(jac), _p(si)))
+        return res, jac, si
+
+    def eval_prior(self, prior, state, n_cols):
+        res, jac = np.zeros(prior.n), np.zeros(prior.n * n_cols)
+        self._check(self.lib.cerb_eval_prior(self.h, C.byref(prior), C.byref(state), _p(res), _p(jac)))
+        return res, jac
+
+    def a1_kinematics(self, q, rho_opt, rho_fix):
+        q, rho_opt, rho_fix = _f64(q), _f64(rho_opt), _f64(rho_fix)
+        n = q.shape[0]
+        fk, jac, dfk, djq, djr = np.zeros((n, 3)), np.zeros((n, 9)), np.zeros((n, 3)), np.zeros((n, 27)), np.zeros((n, 9))
+        self._check(self.lib.cerb_a1_kinematics(self.h, n, _p(q), _p(rho_opt), _p(rho_fix), _p(fk), _p(jac), _p(dfk), _p(djq), _p(djr)))
+        return fk, jac, dfk, djq, djr
+
+    def double2vector(self, before_state, after_state):
+        Ps, Rs, Vs = np.zeros((11, 3)), np.zeros((11, 3, 3)), np.zeros((11, 3))
+        self.lib.cerb_double2vector(C.byref(before_state), C.byref(after_state), _p(Ps), _p(Rs), _p(Vs))
+        return Ps, Rs, Vs
+
+    # ---- synth backend protocol -----------------------------------------------------------------------------
+    def preintegrate(self, pcfg, jobs, n):
+        out = np.zeros(n, dtype=abi.preint_dtype)
+        self._check(self.lib.cerb_preintegrate_batch(self.h, C.byref(pcfg), n, jobs, out.ctypes.data_as(C.POINTER(abi.IMULegPreint))))
+        return out
+
+    def marginalize(self, cfg, src, dst, margin_old=True):
+        from . import marginalization
+        marginalization.marginalize_batch(self, cfg, src, dst, margin_old)

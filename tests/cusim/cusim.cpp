@@ -1,0 +1,30 @@
+// tests/cusim/cusim.cpp -- TEST INFRASTRUCTURE: block launcher of the CUDA-on-CPU shim (see cusim.h).
+#include "cusim.h"
+thread_local cusim_dim3 threadIdx;
+thread_local cusim_dim3 blockIdx;
+cusim_dim3 blockDim, gridDim;
+namespace cusim {
+unsigned char *dyn_smem_ptr = nullptr;
+pthread_barrier_t block_barrier;
+pthread_barrier_t *warp_barriers = nullptr;
+void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body) {
+    blockDim.x = block; gridDim.x = grid;
+    std::vector<unsigned char> sm(smem + 64);
+    dyn_smem_ptr = sm.data();
+    unsigned nwarps = (block + 31) / 32;
+    std::vector<pthread_barrier_t> wb(nwarps);
+    for (unsigned w = 0; w < nwarps; w++) { unsigned cnt = std::min(32u, block - 32 * w); pthread_barrier_init(&wb[w], nullptr, cnt); }
+    warp_barriers = wb.data();
+    pthread_barrier_init(&block_barrier, nullptr, block);
+    // blocks run one after another (shared / static storage is per block), threads of a block concurrently
+    for (unsigned b = 0; b < grid; b++) {
+        std::vector<std::thread> th;
+        th.reserve(block);
+        for (unsigned t = 0; t < block; t++)
+            th.emplace_back([&, b, t]() { threadIdx.x = t; blockIdx.x = b; body(); });
+        for (auto &x : th) x.join();
+    }
+    pthread_barrier_destroy(&block_barrier);
+    for (auto &x : wb) pthread_barrier_destroy(&x);
+}
+}  // namespace cusim

@@ -1,0 +1,74 @@
+// tests/cusim/cusim.h -- TEST INFRASTRUCTURE: a tiny CUDA-on-CPU shim.
+//
+// Lets the non-GPU test tier run the *actual* kernel sources of cerberus_b200/csrc on host threads
+// (one std::thread per CUDA thread of a block, pthread barriers for __syncthreads / __syncwarp),
+// so indexing / math / control-flow bugs are caught without a GPU.  It models exactly the CUDA subset
+// those kernels use.  Nothing here is shipped or used by the product library.
+#pragma once
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include <thread>
+#include <vector>
+#include <functional>
+#include <pthread.h>
+#include <chrono>
+
+struct cusim_dim3 { unsigned x = 1, y = 1, z = 1; };
+extern thread_local cusim_dim3 threadIdx;
+extern thread_local cusim_dim3 blockIdx;
+extern cusim_dim3 blockDim, gridDim;
+namespace cusim {
+extern unsigned char *dyn_smem_ptr;
+extern pthread_barrier_t block_barrier;
+extern pthread_barrier_t *warp_barriers;
+void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body);
+}  // namespace cusim
+
+#define CERB_HD inline
+#define CERB_D inline
+#define CERB_GLOBAL static
+#define __shared__ static
+#define __restrict__ __restrict
+#define __launch_bounds__(...)
+#define CERB_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(cusim::dyn_smem_ptr)
+#define CERB_LAUNCH(kernel, grid, block, smem, stream, ...) cusim::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+inline void __syncthreads() { pthread_barrier_wait(&cusim::block_barrier); }
+inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cusim::warp_barriers[threadIdx.x / 32]); }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+template <typename T> inline T __ldg(const T *p) { return *p; }
+inline void __threadfence() {}
+
+// ---- the slice of the CUDA runtime API the C-ABI layer uses ------------------------------------
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+struct cusim_event { std::chrono::steady_clock::time_point t; };
+typedef cusim_event *cudaEvent_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+inline cudaError_t cudaMalloc(void **p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? 0 : 2; }
+inline cudaError_t cudaFree(void *p) { std::free(p); return 0; }
+inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? 0 : 2; }
+inline cudaError_t cudaFreeHost(void *p) { std::free(p); return 0; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
+inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaDeviceSynchronize() { return 0; }
+inline cudaError_t cudaSetDevice(int) { return 0; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
+inline cudaError_t cudaGetLastError() { return 0; }
+inline cudaError_t cudaPeekAtLastError() { return 0; }
+inline const char *cudaGetErrorString(cudaError_t) { return "cusim"; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new cusim_event(); return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return 0; }
+struct cudaDeviceProp { int multiProcessorCount; size_t sharedMemPerBlockOptin; char name[64]; int major, minor; };
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { p->multiProcessorCount = 4; p->sharedMemPerBlockOptin = 227 * 1024; std::strcpy(p->name, "cusim"); p->major = 10; p->minor = 0; return 0; }
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
