@@ -16,4 +16,10 @@
     extern __shared__ __align__(16) unsigned char name##_raw[]; \
     T *name = reinterpret_cast<T *>(name##_raw)
 #define CERB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// named barrier among a subset of warps (bar.sync id, nthreads)
+#define CERB_BAR_SYNC(id, nthreads) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory")
+// fp64 tensor-core MMA, D(8x8) = A(8x4, row) * B(4x8, col) + C.  Fragment layout (PTX ISA, m8n8k4 .f64):
+//   a = A[lane / 4][lane % 4], b = B[lane % 4][lane / 4], c/d{0,1} = C[lane / 4][2 * (lane % 4) + {0,1}]
+#define CERB_DMMA(d0, d1, a, b, c0, c1) \
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};" : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1))
 #endif

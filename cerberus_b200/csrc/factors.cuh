@@ -184,11 +184,14 @@ CERB_HD void imu_leg_linearize(const double *pre, const double *pose_i, const do
 }
 
 // Expand the unwhitened Jacobian into a dense [31][ld] tangent matrix with columns
-// [pose_i 6 | sb_i 9 | lb_i 4 | pose_j 6 | sb_j 9 | lb_j 4] (38).  Ju must be zero on entry.
-CERB_HD void imu_leg_fill_ju(const IMULegLin &L, const double *pre, double *Ju, int ld) {
+// [pose_i 6 | sb_i 9 | lb_i 4 | pose_j 6 | sb_j 9 | lb_j 4] (38).  Ju must be zero on entry.  The work is cut
+// into 11 independent parts (part 0..8: one (a, b) entry of every 3x3 block, 9: the +-identity entries,
+// 10: the leg-length columns) so that 11 threads can fill one factor concurrently.
+CERB_HD void imu_leg_fill_ju_part(const IMULegLin &L, const double *pre, double *Ju, int ld, int part) {
 #define JU(rr, cc) Ju[(rr) * ld + (cc)]
-    const double dt = pre[PRE_SUM_DT];
-    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+    if (part < 9) {
+        const int a = part / 3, b = part % 3;
+        const double dt = pre[PRE_SUM_DT];
         const double rit = L.RiT.m[3 * a + b];
         // pose_i (cols 0..5)
         JU(ILO_P + a, b) = -rit;               JU(ILO_P + a, 3 + b) = L.skP.m[3 * a + b];
@@ -213,17 +216,22 @@ CERB_HD void imu_leg_fill_ju(const IMULegLin &L, const double *pre, double *Ju, 
             JU(ILO_EPS1 + 3 * k + a, 12 + b) = -pre[PRE_DEP_DBG + 9 * k + 3 * a + b];
             JU(ILO_EPS1 + 3 * k + a, 19 + b) = rit;
         }
-    }
-    for (int a = 0; a < 3; a++) {
-        JU(ILO_BA + a, 9 + a) = -1.0;  JU(ILO_BG + a, 12 + a) = -1.0;
-        JU(ILO_BA + a, 28 + a) = 1.0;  JU(ILO_BG + a, 31 + a) = 1.0;
-    }
-    for (int k = 0; k < 4; k++) {
-        for (int a = 0; a < 3; a++) JU(ILO_EPS1 + 3 * k + a, 15 + k) = -pre[PRE_DEP_DRHO + 3 * k + a];
-        JU(ILO_RHO1 + k, 15 + k) = -1.0;
-        JU(ILO_RHO1 + k, 34 + k) = 1.0;
+    } else if (part == 9) {
+        for (int a = 0; a < 3; a++) {
+            JU(ILO_BA + a, 9 + a) = -1.0;  JU(ILO_BG + a, 12 + a) = -1.0;
+            JU(ILO_BA + a, 28 + a) = 1.0;  JU(ILO_BG + a, 31 + a) = 1.0;
+        }
+    } else {
+        for (int k = 0; k < 4; k++) {
+            for (int a = 0; a < 3; a++) JU(ILO_EPS1 + 3 * k + a, 15 + k) = -pre[PRE_DEP_DRHO + 3 * k + a];
+            JU(ILO_RHO1 + k, 15 + k) = -1.0;
+            JU(ILO_RHO1 + k, 34 + k) = 1.0;
+        }
     }
 #undef JU
+}
+CERB_HD void imu_leg_fill_ju(const IMULegLin &L, const double *pre, double *Ju, int ld) {
+    for (int part = 0; part < 11; part++) imu_leg_fill_ju_part(L, pre, Ju, ld, part);
 }
 
 // ---- A1 leg kinematics (closed forms, A1Kinematics.cpp:43-220) -------------------------------------

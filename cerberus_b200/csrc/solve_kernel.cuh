@@ -19,7 +19,7 @@
 
 namespace cerb {
 
-enum { CERB_WINDOW = 10, NX = 78, NYB = 13, NFR = 11, NY = 143, NR = 221, NRP = 224, SOLVE_THREADS = 256, FT = 64, TILE_LD = 25, NOBS_PLANES = 9 };
+enum { CERB_WINDOW = 10, NX = 78, NYB = 13, NFR = 11, NY = 143, NR = 221, NRP = 224, SOLVE_THREADS = 256, FT = 64, TILE_LD = 36, NOBS_PLANES = 9 };
 
 struct SolveParams {
     int n_windows, maxF, maxObs, max_iters, optimize_leg_bias;
@@ -56,7 +56,7 @@ struct Smem {
     double *wj;                             // 128 x 8 per-thread exchange
     double *sca;                            // 64 scalars
     int *ti;                                // 128 ints: anchor per tile factor ; + misc ints
-    double *tile;                           // alias of Hxy: 256 x 25
+    double *tile;                           // alias of Hxy (+ Ad, Bo): 256 x TILE_LD tile + 8 x 640 partial Gram tiles
 };
 enum { SMEM_DOUBLES = 6084 + 11154 + 1859 + 1690 + 7 * NRP + 2 * ST_STRIDE + 99 + 18 + 3 + 31 * 39 + 960 + 192 + 8 * 256 + 128 * 8 + 64 + 80 };
 
@@ -180,6 +180,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
                         row0[18 + k] = hw * J.Je1[k]; row1[18 + k] = hw * J.Je1[6 + k];
                     }
                     row0[24] = hw * r[0]; row1[24] = hw * r[1];
+                    for (int k = 25; k < 32; k++) { row0[k] = 0.0; row1[k] = 0.0; }
                     const double l0 = hw * J.Jl[0], l1 = hw * J.Jl[1];
                     h += l0 * l0 + l1 * l1; gq += l0 * row0[24] + l1 * row1[24];
                     for (int k = 0; k < 6; k++) {
@@ -189,7 +190,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
                         wE1[k] += row0[18 + k] * l0 + row1[18 + k] * l1;
                     }
                 } else {
-                    for (int k = 0; k < TILE_LD; k++) { row0[k] = 0.0; row1[k] = 0.0; }
+                    for (int k = 0; k < 32; k++) { row0[k] = 0.0; row1[k] = 0.0; }
                 }
                 for (int k = 0; k < 6; k++) s.wj[tid * 8 + k] = wjv[k];
             }
@@ -197,29 +198,55 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
             // --- W rows of frame j: sum of the two cameras -----------------------------------------------------
             if (tid < FT && ev && j != c.start && j >= c.start && j < c.start + c.nobs)
                 for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] = s.wj[tid * 8 + k] + s.wj[(tid + FT) * 8 + k];
-            // --- J^T J of the tile, one pass per anchor frame present -------------------------------------------
-            for (int a = amin; a <= amax && a <= j; a++) {
-                for (int e = tid; e < 325; e += SOLVE_THREADS) {
-                    // unpack e -> (la <= lb) of the 25 x 25 local matrix [I 6 | J 6 | E0 6 | E1 6 | r]
-                    int la = 0, rem = e;
-                    while (rem >= 25 - la) { rem -= 25 - la; la++; }
-                    const int lb = la + rem;
-                    if (a == j && la < 12) continue;                  // anchor-frame rows (K3) have no pose columns
-                    if (la == 24) continue;                           // r^T r
-                    double acc = 0.0;
-                    for (int t = 0; t < 2 * FT; t++) {
-                        if (s.ti[t] != a) continue;
-                        const double *q0 = s.tile + (2 * t) * TILE_LD;
-                        acc += q0[la] * q0[lb] + q0[TILE_LD + la] * q0[TILE_LD + lb];
+            // --- J^T J of the tile on the fp64 tensor cores (mma.sync m8n8k4), one pass per anchor frame present.
+            // The tile is a (256 rows) x (32 cols: I 6 | J 6 | E0 6 | E1 6 | r | 0-pad) matrix T; the Gram matrix
+            // T^T T is cut into 8x8 blocks (10 upper ones); warp wid contracts rows [32 wid, 32 wid + 32), the eight
+            // partial results are summed through shared memory and scattered into Hxx / g.
+            {
+                const int wid = tid >> 5, lane = tid & 31;
+                double *part = s.tile + 256 * TILE_LD;
+                for (int a = amin; a <= amax && a <= j; a++) {
+                    double acc[10][2];
+                    for (int k = 0; k < 10; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
+                    for (int ks = 0; ks < 8; ks++) {
+                        const int row = 32 * wid + 4 * ks + (lane & 3);
+                        const bool on = (s.ti[row >> 1] == a);
+                        const double *q = s.tile + row * TILE_LD + (lane >> 2);
+                        const double v0 = on ? q[0] : 0.0, v1 = on ? q[8] : 0.0, v2 = on ? q[16] : 0.0, v3 = on ? q[24] : 0.0;
+                        CERB_DMMA(acc[0][0], acc[0][1], v0, v0, acc[0][0], acc[0][1]);
+                        CERB_DMMA(acc[1][0], acc[1][1], v0, v1, acc[1][0], acc[1][1]);
+                        CERB_DMMA(acc[2][0], acc[2][1], v0, v2, acc[2][0], acc[2][1]);
+                        CERB_DMMA(acc[3][0], acc[3][1], v0, v3, acc[3][0], acc[3][1]);
+                        CERB_DMMA(acc[4][0], acc[4][1], v1, v1, acc[4][0], acc[4][1]);
+                        CERB_DMMA(acc[5][0], acc[5][1], v1, v2, acc[5][0], acc[5][1]);
+                        CERB_DMMA(acc[6][0], acc[6][1], v1, v3, acc[6][0], acc[6][1]);
+                        CERB_DMMA(acc[7][0], acc[7][1], v2, v2, acc[7][0], acc[7][1]);
+                        CERB_DMMA(acc[8][0], acc[8][1], v2, v3, acc[8][0], acc[8][1]);
+                        CERB_DMMA(acc[9][0], acc[9][1], v3, v3, acc[9][0], acc[9][1]);
                     }
-                    const int ga = la < 6 ? 6 * a + la : (la < 12 ? 6 * j + la - 6 : 66 + la - 12);
-                    if (lb == 24) s.g[ga] += acc;
-                    else {
-                        const int gb = lb < 6 ? 6 * a + lb : (lb < 12 ? 6 * j + lb - 6 : 66 + lb - 12);
-                        s.Hxx[ga * NX + gb] += acc;
+                    for (int k = 0; k < 10; k++) {
+                        double *o = part + wid * 640 + k * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
+                        o[0] = acc[k][0]; o[1] = acc[k][1];
                     }
+                    __syncthreads();
+                    for (int e = tid; e < 640; e += SOLVE_THREADS) {
+                        const int k = e >> 6, r = (e >> 3) & 7, c = e & 7;
+                        const int mi = k < 4 ? 0 : (k < 7 ? 1 : (k < 9 ? 2 : 3));
+                        const int ni = k < 4 ? k : (k < 7 ? k - 3 : (k < 9 ? k - 5 : 3));
+                        const int la = 8 * mi + r, lb = 8 * ni + c;
+                        if (la > lb || lb > 24 || la == 24) continue;
+                        if (a == j && la < 12) continue;                  // anchor-frame rows (K3) have no pose columns
+                        double accv = 0.0;
+                        for (int wq = 0; wq < 8; wq++) accv += part[wq * 640 + e];
+                        const int ga = la < 6 ? 6 * a + la : (la < 12 ? 6 * j + la - 6 : 66 + la - 12);
+                        if (lb == 24) s.g[ga] += accv;
+                        else {
+                            const int gb = lb < 6 ? 6 * a + lb : (lb < 12 ? 6 * j + lb - 6 : 66 + lb - 12);
+                            s.Hxx[ga * NX + gb] += accv;
+                        }
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             __syncthreads();
         }
@@ -319,18 +346,17 @@ CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const dou
         if (pre[PRE_SUM_DT] > 10.0) continue;                      // estimator.cpp:1119 (uniform across the CTA)
         for (int k = tid; k < 31 * 39; k += SOLVE_THREADS) s.Ju[k] = 0.0;
         __syncthreads();
-        if (tid == 0) {
-            const IMULegLin *L = reinterpret_cast<const IMULegLin *>(s.lin + 96 * i);
-            imu_leg_fill_ju(*L, pre, s.Ju, 39);
-            for (int r = 0; r < 31; r++) s.Ju[r * 39 + 38] = L->ru[r];
-        }
+        if (tid < 11) imu_leg_fill_ju_part(*reinterpret_cast<const IMULegLin *>(s.lin + 96 * i), pre, s.Ju, 39, tid);
+        else if (tid >= 32 && tid < 63) s.Ju[(tid - 32) * 39 + 38] = s.lin[96 * i + (tid - 32)];       // residual column
         __syncthreads();
-        if (tid < 39) {                                           // whiten in place, top row first: Jw = S Ju
+        double *Jw = s.red;                                         // whitened copy Jw = S Ju (S upper triangular)
+        {
             const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + i) * 961;
-            for (int r = 0; r < 31; r++) {
+            for (int idx = tid; idx < 31 * 39; idx += SOLVE_THREADS) {
+                const int r = idx / 39, c = idx % 39;
                 double t = 0.0;
-                for (int q = r; q < 31; q++) t += S[r * 31 + q] * s.Ju[q * 39 + tid];
-                s.Ju[r * 39 + tid] = t;
+                for (int q = r; q < 31; q++) t += S[r * 31 + q] * s.Ju[q * 39 + c];
+                Jw[idx] = t;
             }
         }
         __syncthreads();
@@ -339,7 +365,7 @@ CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const dou
             while (rem >= 39 - la) { rem -= 39 - la; la++; }
             const int lb = la + rem;
             double acc = 0.0;
-            for (int r = 0; r < 31; r++) acc += s.Ju[r * 39 + la] * s.Ju[r * 39 + lb];
+            for (int r = 0; r < 31; r++) acc += Jw[r * 39 + la] * Jw[r * 39 + lb];
             if (la == 38) { cost += 0.5 * acc; continue; }
             const int da = imu_col_dest(i, la);
             if (lb == 38) { if (da >= 0) s.g[da] += acc; else s.g[NX + (-da - 1)] += acc; continue; }
@@ -598,23 +624,43 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                         }
                     } else {
                         // ---- other warps: eliminate the inverse depths  S = Hxx - W diag(1/(h + mu D^2)) W^T ----------
+                        // W is staged through shared memory in tiles of 32 features (raw and scaled by 1/(h + mu D^2));
+                        // each of the 224 threads owns the entries (a, b >= a) with a = ta + 14 i, b = tb + 16 j.
                         const int t2 = tid - 32, n2 = SOLVE_THREADS - 32;
-                        for (int e = t2; e < NX * (NX + 1) / 2 + NX; e += n2) {
-                            if (e >= NX * (NX + 1) / 2) {           // rhs_x
-                                const int a = e - NX * (NX + 1) / 2;
-                                double t = 0.0;
-                                for (int f = 0; f < nF; f++) t += W[(size_t)a * F + f] * gl[f] / (hh[f] + mu * Dl[f] * Dl[f]);
-                                s.yv[a] -= t;
-                                continue;
+                        const int ta = t2 >> 4, tb = t2 & 15;
+                        double acc[36];
+                        for (int k = 0; k < 36; k++) acc[k] = 0.0;
+                        double racc = 0.0;                        // rhs_x entry a = t2 (t2 < NX)
+                        double *tw = s.Ju, *tws = s.Ju + NX * 32; // two tiles of 78 x 32 (aliases Ju .. wj, unused during the solve)
+                        for (int f0 = 0; f0 < nF; f0 += 32) {
+                            const int nf = (nF - f0) < 32 ? (nF - f0) : 32;
+                            for (int e = t2; e < NX * 32; e += n2) {
+                                const int a = e >> 5, f = e & 31;
+                                double wv = 0.0, iv = 0.0;
+                                if (f < nf) { wv = W[(size_t)a * F + f0 + f]; iv = 1.0 / (hh[f0 + f] + mu * Dl[f0 + f] * Dl[f0 + f]); }
+                                tw[e] = wv; tws[e] = wv * iv;
                             }
-                            int a = 0, rem = e;
-                            while (rem >= NX - a) { rem -= NX - a; a++; }
-                            const int b = a + rem;
-                            double t = 0.0;
-                            for (int f = 0; f < nF; f++) t += W[(size_t)a * F + f] * W[(size_t)b * F + f] / (hh[f] + mu * Dl[f] * Dl[f]);
-                            s.Hxx[b * NX + a] -= t;                   // lower triangle is the one factored below
-                            if (a != b) s.Hxx[a * NX + b] -= t;
+                            // named barrier among the 224 threads of warps 1..7 (warp 0 is busy with the chain)
+                            CERB_BAR_SYNC(1, n2);
+                            int q = 0;
+                            for (int a = ta; a < NX; a += 14)
+                                for (int b = tb; b < NX; b += 16, q++) {
+                                    if (b < a) continue;
+                                    double t = 0.0;
+                                    for (int f = 0; f < 32; f++) t += tw[a * 32 + f] * tws[b * 32 + f];
+                                    acc[q] += t;
+                                }
+                            if (t2 < NX) { double t = 0.0; for (int f = 0; f < nf; f++) t += tws[t2 * 32 + f] * gl[f0 + f]; racc += t; }
+                            CERB_BAR_SYNC(1, n2);
                         }
+                        int q = 0;
+                        for (int a = ta; a < NX; a += 14)
+                            for (int b = tb; b < NX; b += 16, q++) {
+                                if (b < a) continue;
+                                s.Hxx[b * NX + a] -= acc[q];              // lower triangle is the one factored below
+                                if (a != b) s.Hxx[a * NX + b] -= acc[q];
+                            }
+                        if (t2 < NX) s.yv[t2] -= racc;
                     }
                     __syncthreads();
                     // ---- T = L^-1 Hyx (row a of Hxy in place), and the same for the y part of the rhs (row 78) ----
@@ -632,36 +678,40 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                     }
                     __syncthreads();
                     // ---- S' = S - T T^T (lower), rhs'_x = rhs_x - T gy' -------------------------------------------
-                    for (int e = tid; e < NX * (NX + 1) / 2 + NX; e += SOLVE_THREADS) {
-                        if (e >= NX * (NX + 1) / 2) {
-                            const int a = e - NX * (NX + 1) / 2;
-                            double t = 0.0;
-                            for (int q = 0; q < NY; q++) t += s.Hxy[a * NY + q] * s.yv[NX + q];
-                            s.yv[a] -= t;
-                            continue;
-                        }
-                        int a = 0, rem = e;
-                        while (rem >= NX - a) { rem -= NX - a; a++; }
-                        const int b = a + rem;
-                        double t = 0.0;
-                        for (int q = 0; q < NY; q++) t += s.Hxy[a * NY + q] * s.Hxy[b * NY + q];
-                        s.Hxx[b * NX + a] -= t;
+                    {
+                        const int ta = tid >> 4, tb = tid & 15;
+                        for (int a = ta; a < NX; a += 16)
+                            for (int b = tb; b < NX; b += 16) {
+                                if (b < a) continue;
+                                double t = 0.0;
+                                for (int q = 0; q < NY; q++) t += s.Hxy[a * NY + q] * s.Hxy[b * NY + q];
+                                s.Hxx[b * NX + a] -= t;
+                            }
+                        if (tid < NX) { double t = 0.0; for (int q = 0; q < NY; q++) t += s.Hxy[tid * NY + q] * s.yv[NX + q]; s.yv[tid] -= t; }
                     }
                     __syncthreads();
                     // ---- dense Cholesky of the 78 x 78 lower triangle, rhs carried as an extra row (z = L^-1 rhs) ----
-                    for (int k = 0; k < NX; k++) {
-                        if (tid == 0) { double d = s.Hxx[k * NX + k]; if (!(d > 0.0)) { sca[S_OK] = 0; d = 1.0; } s.Hxx[k * NX + k] = sqrt(d); }
-                        __syncthreads();
-                        const double piv = s.Hxx[k * NX + k];
-                        for (int i = k + 1 + tid; i <= NX; i += SOLVE_THREADS) { if (i < NX) s.Hxx[i * NX + k] /= piv; else s.yv[k] /= piv; }
-                        __syncthreads();
-                        const int m = NX - 1 - k;                        // trailing size
-                        for (int e = tid; e < m * (m + 1) / 2 + m; e += SOLVE_THREADS) {
-                            if (e >= m * (m + 1) / 2) { const int i = k + 1 + (e - m * (m + 1) / 2); s.yv[i] -= s.Hxx[i * NX + k] * s.yv[k]; continue; }
-                            int a = 0, rem = e;
-                            while (rem >= m - a) { rem -= m - a; a++; }
-                            const int j = k + 1 + a, i = j + rem;       // i >= j > k
-                            s.Hxx[i * NX + j] -= s.Hxx[i * NX + k] * s.Hxx[j * NX + k];
+                    // Right-looking, one barrier per column: the trailing update of column k uses the raw column
+                    // (A[i][k] A[j][k] / d_k); column k is normalised by 1/sqrt(d_k) one step later, when nobody reads it.
+                    {
+                        const int ti = tid >> 4, tj = tid & 15;
+                        double dprev = 1.0;
+                        for (int k = 0; k <= NX; k++) {
+                            if (k > 0) {            // normalise column k-1 (and z[k-1])
+                                const double isq = 1.0 / sqrt(dprev);
+                                for (int i = k - 1 + tid; i <= NX; i += SOLVE_THREADS) { if (i < NX) s.Hxx[i * NX + (k - 1)] *= isq; else s.yv[k - 1] *= isq; }
+                            }
+                            if (k == NX) break;
+                            double d = s.Hxx[k * NX + k];
+                            if (!(d > 0.0)) { if (tid == 0) sca[S_OK] = 0; d = 1.0; }
+                            const double inv_d = 1.0 / d;
+                            for (int i = k + 1 + ti; i <= NX; i += 16) {
+                                const double lik = (i < NX ? s.Hxx[i * NX + k] : s.yv[k]) * inv_d;
+                                if (i < NX) { for (int j = k + 1 + tj; j <= i; j += 16) s.Hxx[i * NX + j] -= lik * s.Hxx[j * NX + k]; }
+                                else { for (int j = k + 1 + tj; j < NX; j += 16) s.yv[j] -= lik * s.Hxx[j * NX + k]; }
+                            }
+                            dprev = d;
+                            __syncthreads();
                         }
                         __syncthreads();
                     }

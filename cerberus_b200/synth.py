@@ -346,3 +346,23 @@ def generate_batch(n, n_features, backend, cfg=None, pcfg=None, window0=0, reali
         return batch, tr_out
     batch._keepalive = (samples, jobs)
     return batch
+
+
+def tile_batch(batch, n):
+    """Replicate the windows of `batch` cyclically into a new WindowBatch of n windows (distinct storage)."""
+    big = abi.WindowBatch(n, batch.max_features, batch.max_obs)
+    src_n = batch.n
+    reps = n // src_n + 1
+    for arr in ("features", "obs", "preint", "prior_J", "prior_r", "para_Feature"):
+        a = getattr(batch, arr)
+        getattr(big, arr)[:] = np.tile(a, (reps,) + (1,) * (a.ndim - 1))[:n]
+    for w in range(n):
+        s = w % src_n
+        C.memmove(C.byref(big.states[w]), C.byref(batch.states[s]), C.sizeof(abi.WindowState))
+        big.states[w].para_Feature = big.para_Feature[w].ctypes.data_as(abi.c_dp)
+        d, sd = big.descs[w], batch.descs[s]
+        d.n_features, d.n_obs, d.extrinsic_open, d.td_open = sd.n_features, sd.n_obs, sd.extrinsic_open, sd.td_open
+        C.memmove(C.byref(d.prior), C.byref(sd.prior), C.sizeof(abi.Prior))
+        d.prior.linearized_jacobians = big.prior_J[w].ctypes.data_as(abi.c_dp)
+        d.prior.linearized_residuals = big.prior_r[w].ctypes.data_as(abi.c_dp)
+    return big

@@ -7,6 +7,8 @@ namespace cusim {
 unsigned char *dyn_smem_ptr = nullptr;
 pthread_barrier_t block_barrier;
 pthread_barrier_t *warp_barriers = nullptr;
+pthread_barrier_t named_barrier;
+double *warp_scratch = nullptr;
 void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body) {
     blockDim.x = block; gridDim.x = grid;
     std::vector<unsigned char> sm(smem + 64);
@@ -15,7 +17,10 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
     std::vector<pthread_barrier_t> wb(nwarps);
     for (unsigned w = 0; w < nwarps; w++) { unsigned cnt = std::min(32u, block - 32 * w); pthread_barrier_init(&wb[w], nullptr, cnt); }
     warp_barriers = wb.data();
+    std::vector<double> wsc(nwarps * 64);
+    warp_scratch = wsc.data();
     pthread_barrier_init(&block_barrier, nullptr, block);
+    pthread_barrier_init(&named_barrier, nullptr, block > 32 ? block - 32 : 1);
     // blocks run one after another (shared / static storage is per block), threads of a block concurrently
     for (unsigned b = 0; b < grid; b++) {
         std::vector<std::thread> th;
@@ -25,6 +30,7 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
         for (auto &x : th) x.join();
     }
     pthread_barrier_destroy(&block_barrier);
+    pthread_barrier_destroy(&named_barrier);
     for (auto &x : wb) pthread_barrier_destroy(&x);
 }
 }  // namespace cusim

@@ -36,6 +36,23 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
 #define CERB_LAUNCH(kernel, grid, block, smem, stream, ...) cusim::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
 inline void __syncthreads() { pthread_barrier_wait(&cusim::block_barrier); }
 inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cusim::warp_barriers[threadIdx.x / 32]); }
+// named barrier used by warps 1..7 of the solve kernel (224 threads)
+namespace cusim { extern pthread_barrier_t named_barrier; }
+#define CERB_BAR_SYNC(id, nthreads) pthread_barrier_wait(&cusim::named_barrier)
+// emulation of mma.sync.m8n8k4.f64 across the 32 threads of a (simulated) warp
+namespace cusim { extern double *warp_scratch; }
+inline void cusim_dmma(double &d0, double &d1, double a, double b, double c0, double c1) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sa = cusim::warp_scratch + warp * 64, *sb = sa + 32;
+    sa[lane] = a; sb[lane] = b;
+    __syncwarp();
+    const unsigned r = lane / 4, c = 2 * (lane % 4);
+    double x0 = c0, x1 = c1;
+    for (unsigned k = 0; k < 4; k++) { x0 += sa[4 * r + k] * sb[4 * c + k]; x1 += sa[4 * r + k] * sb[4 * (c + 1) + k]; }
+    __syncwarp();
+    d0 = x0; d1 = x1;
+}
+#define CERB_DMMA(d0, d1, a, b, c0, c1) cusim_dmma(d0, d1, a, b, c0, c1)
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline void __threadfence() {}
