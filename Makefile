@@ -4,6 +4,7 @@ CXX ?= g++
 CSRC = cerberus_b200/csrc
 HDRS = $(wildcard $(CSRC)/*.cuh) $(CSRC)/compat.h include/cerberus_b200.h
 
+.PHONY: all lib oracle sim clean
 all: lib oracle sim
 
 lib: cerberus_b200/libcerberus_b200.so

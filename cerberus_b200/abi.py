@@ -57,7 +57,7 @@ class Prior(C.Structure):
     _fields_ = [
         ("valid", C.c_int32), ("n", C.c_int32), ("num_blocks", C.c_int32), ("reserved", C.c_int32),
         ("block_kind", C.c_int32 * MAX_PRIOR_BLOCKS), ("block_index", C.c_int32 * MAX_PRIOR_BLOCKS),
-        ("block_col", C.c_int32 * MAX_PRIOR_BLOCKS), ("block_x0", (C.c_double * 7) * MAX_PRIOR_BLOCKS),
+        ("block_col", C.c_int32 * MAX_PRIOR_BLOCKS), ("block_x0", (C.c_double * 9) * MAX_PRIOR_BLOCKS),
         ("linearized_jacobians", c_dp), ("linearized_residuals", c_dp),
     ]
 

@@ -104,13 +104,13 @@ int cerb_create(const CerbSolverConfig *cfg, CerbHandle **out) {
     CUDA_TRY(dmalloc(&h->d_nfeat, B)); CUDA_TRY(dmalloc(&h->d_fstart, B * F)); CUDA_TRY(dmalloc(&h->d_fnobs, B * F)); CUDA_TRY(dmalloc(&h->d_foff, B * F));
     CUDA_TRY(dmalloc(&h->d_flags, B)); CUDA_TRY(dmalloc(&h->d_stereo, B * O)); CUDA_TRY(dmalloc(&h->d_pmeta, B * PRIOR_META_STRIDE)); CUDA_TRY(dmalloc(&h->d_repi, B * 4));
     CUDA_TRY(dmalloc(&h->d_obs, B * NOBS_PLANES * O)); CUDA_TRY(dmalloc(&h->d_pre, B * 10 * PRE_STRIDE)); CUDA_TRY(dmalloc(&h->d_sinfo, B * 10 * 961));
-    CUDA_TRY(dmalloc(&h->d_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(dmalloc(&h->d_pr, B * PRIOR_LD)); CUDA_TRY(dmalloc(&h->d_px0, B * 16 * 7)); CUDA_TRY(dmalloc(&h->d_pHp, B * PRIOR_LD * PRIOR_LD));
+    CUDA_TRY(dmalloc(&h->d_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(dmalloc(&h->d_pr, B * PRIOR_LD)); CUDA_TRY(dmalloc(&h->d_px0, B * 16 * 9)); CUDA_TRY(dmalloc(&h->d_pHp, B * PRIOR_LD * PRIOR_LD));
     CUDA_TRY(dmalloc(&h->d_state, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_state0, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_lam, B * F)); CUDA_TRY(dmalloc(&h->d_lam0, B * F));
     CUDA_TRY(dmalloc(&h->d_repd, B * 2)); CUDA_TRY(dmalloc(&h->d_ws, (size_t)h->grid * h->ws_stride)); CUDA_TRY(dmalloc(&h->d_dbg, 2 * (NR + F) + 8)); CUDA_TRY(dmalloc(&h->d_G, 4));
     CUDA_TRY(hmalloc(&h->h_nfeat, B)); CUDA_TRY(hmalloc(&h->h_fstart, B * F)); CUDA_TRY(hmalloc(&h->h_fnobs, B * F)); CUDA_TRY(hmalloc(&h->h_foff, B * F));
     CUDA_TRY(hmalloc(&h->h_flags, B)); CUDA_TRY(hmalloc(&h->h_stereo, B * O)); CUDA_TRY(hmalloc(&h->h_pmeta, B * PRIOR_META_STRIDE)); CUDA_TRY(hmalloc(&h->h_repi, B * 4));
     CUDA_TRY(hmalloc(&h->h_obs, B * NOBS_PLANES * O)); CUDA_TRY(hmalloc(&h->h_pre, B * 10 * PRE_STRIDE));
-    CUDA_TRY(hmalloc(&h->h_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_pr, B * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_px0, B * 16 * 7));
+    CUDA_TRY(hmalloc(&h->h_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_pr, B * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_px0, B * 16 * 9));
     CUDA_TRY(hmalloc(&h->h_state, B * ST_STRIDE)); CUDA_TRY(hmalloc(&h->h_lam, B * F)); CUDA_TRY(hmalloc(&h->h_repd, B * 2)); CUDA_TRY(hmalloc(&h->h_dbg, 2 * (NR + F) + 8));
     CUDA_TRY(cudaMemcpy(h->d_G, cfg->g, 3 * sizeof(double), cudaMemcpyHostToDevice));
     *out = h;
@@ -166,7 +166,7 @@ static int pack_prior(const CerbPrior &pr, int *meta, double *J, double *r, doub
         meta[4 + 3 * b] = kind; meta[5 + 3 * b] = index; meta[6 + 3 * b] = pr.block_col[b];
         const int size = prior_block_size(kind), local = size == 7 ? 6 : size;
         if (pr.block_col[b] < 0 || pr.block_col[b] + local > pr.n) return fail(CERB_ERR_BAD_ARGUMENT, "prior: block column out of range");
-        for (int k = 0; k < 7; k++) x0[7 * b + k] = pr.block_x0[b][k];
+        for (int k = 0; k < 9; k++) x0[9 * b + k] = pr.block_x0[b][k];
     }
     std::memcpy(J, pr.linearized_jacobians, sizeof(double) * pr.n * pr.n);
     std::memcpy(r, pr.linearized_residuals, sizeof(double) * pr.n);
@@ -197,7 +197,7 @@ static int pack_window(CerbHandle *h, int w, const CerbWindowDesc &d, const Cerb
         ob[8 * O + o] = q.cur_td; sto[o] = q.is_stereo;
     }
     for (int i = 0; i < CERB_WINDOW_SIZE; i++) pack_preint(d.preint[i], h->h_pre + ((size_t)w * 10 + i) * PRE_STRIDE);
-    int rc = pack_prior(d.prior, h->h_pmeta + (size_t)w * PRIOR_META_STRIDE, h->h_pJ + (size_t)w * PRIOR_LD * PRIOR_LD, h->h_pr + (size_t)w * PRIOR_LD, h->h_px0 + (size_t)w * 16 * 7);
+    int rc = pack_prior(d.prior, h->h_pmeta + (size_t)w * PRIOR_META_STRIDE, h->h_pJ + (size_t)w * PRIOR_LD * PRIOR_LD, h->h_pr + (size_t)w * PRIOR_LD, h->h_px0 + (size_t)w * 16 * 9);
     if (rc) return rc;
     double *s = h->h_state + (size_t)w * ST_STRIDE;
     std::memcpy(s + ST_POSE, st.para_Pose, sizeof(st.para_Pose));
@@ -231,7 +231,7 @@ static int upload(CerbHandle *h, int n) {
     H2D(h->d_nfeat, h->h_nfeat, (size_t)n); H2D(h->d_fstart, h->h_fstart, n * F); H2D(h->d_fnobs, h->h_fnobs, n * F); H2D(h->d_foff, h->h_foff, n * F);
     H2D(h->d_flags, h->h_flags, (size_t)n); H2D(h->d_stereo, h->h_stereo, n * O); H2D(h->d_pmeta, h->h_pmeta, (size_t)n * PRIOR_META_STRIDE);
     H2D(h->d_obs, h->h_obs, n * NOBS_PLANES * O); H2D(h->d_pre, h->h_pre, (size_t)n * 10 * PRE_STRIDE);
-    H2D(h->d_pJ, h->h_pJ, (size_t)n * PRIOR_LD * PRIOR_LD); H2D(h->d_pr, h->h_pr, (size_t)n * PRIOR_LD); H2D(h->d_px0, h->h_px0, (size_t)n * 16 * 7);
+    H2D(h->d_pJ, h->h_pJ, (size_t)n * PRIOR_LD * PRIOR_LD); H2D(h->d_pr, h->h_pr, (size_t)n * PRIOR_LD); H2D(h->d_px0, h->h_px0, (size_t)n * 16 * 9);
     H2D(h->d_state0, h->h_state, (size_t)n * ST_STRIDE); H2D(h->d_lam0, h->h_lam, n * F);
 #undef H2D
     h->n = n;
@@ -428,7 +428,7 @@ int cerb_eval_imu_leg(CerbHandle *h, int32_t n, const CerbIMULegPreint *preint, 
 
 int cerb_eval_prior(CerbHandle *h, const CerbPrior *prior, const CerbWindowState *state, double *residuals, double *jacobians) {
     if (!h || !prior || !state || !prior->valid || !residuals) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_prior: bad argument");
-    std::vector<int> meta(PRIOR_META_STRIDE); std::vector<double> J(PRIOR_LD * PRIOR_LD, 0.0), r(PRIOR_LD, 0.0), x0(16 * 7, 0.0), st(ST_STRIDE, 0.0);
+    std::vector<int> meta(PRIOR_META_STRIDE); std::vector<double> J(PRIOR_LD * PRIOR_LD, 0.0), r(PRIOR_LD, 0.0), x0(16 * 9, 0.0), st(ST_STRIDE, 0.0);
     int rc = pack_prior(*prior, meta.data(), J.data(), r.data(), x0.data()); if (rc) return rc;
     std::memcpy(st.data() + ST_POSE, state->para_Pose, sizeof(state->para_Pose)); std::memcpy(st.data() + ST_SB, state->para_SpeedBias, sizeof(state->para_SpeedBias));
     std::memcpy(st.data() + ST_LB, state->para_LegBias, sizeof(state->para_LegBias)); std::memcpy(st.data() + ST_EX, state->para_Ex_Pose, sizeof(state->para_Ex_Pose));

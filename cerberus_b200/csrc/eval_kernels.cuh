@@ -209,7 +209,7 @@ CERB_GLOBAL void prior_eval_kernel(const double *J, const double *r0, const int 
     __syncthreads();
     if (tid < nb) {
         const int kind = meta[4 + 3 * tid], index = meta[5 + 3 * tid], col = meta[6 + 3 * tid];
-        prior_block_dx(kind, state + prior_block_state_offset(kind, index), x0 + 7 * tid, dx + col);
+        prior_block_dx(kind, state + prior_block_state_offset(kind, index), x0 + 9 * tid, dx + col);
     }
     __syncthreads();
     for (int i = tid; i < n; i += nt) { double s = r0[i]; for (int k = 0; k < n; k++) s += J[(size_t)k * n + i] * dx[k]; residuals[i] = s; }

@@ -303,10 +303,10 @@ CERB_D double prior_residual(const SolveParams &P, Smem &s, int w, const double 
     const int *meta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
     if (!meta[0]) return 0.0;
     const int n = meta[1], nb = meta[2];
-    const double *J = P.prior_J + (size_t)w * PRIOR_LD * PRIOR_LD, *r0 = P.prior_r + (size_t)w * PRIOR_LD, *x0 = P.prior_x0 + (size_t)w * 16 * 7;
+    const double *J = P.prior_J + (size_t)w * PRIOR_LD * PRIOR_LD, *r0 = P.prior_r + (size_t)w * PRIOR_LD, *x0 = P.prior_x0 + (size_t)w * 16 * 9;
     if (tid < nb) {
         const int kind = meta[4 + 3 * tid], index = meta[5 + 3 * tid], col = meta[6 + 3 * tid];
-        prior_block_dx(kind, x + prior_block_state_offset(kind, index), x0 + 7 * tid, s.pdx + col);
+        prior_block_dx(kind, x + prior_block_state_offset(kind, index), x0 + 9 * tid, s.pdx + col);
     }
     __syncthreads();
     double cost = 0.0;
@@ -415,9 +415,13 @@ CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const dou
 }
 
 // x [+] delta -> xc ; lam + dlam -> lamc
-CERB_D void apply_plus(const Smem &s, const double *delta, const double *lam, const double *dlam, double *lamc, int nF, int tid) {
+CERB_D void apply_plus(const Smem &s, const double *delta, const double *lam, const double *dlam, double *lamc, int nF, bool ex_open, int tid) {
     if (tid < 11) pose_plus(s.xs + ST_POSE + 7 * tid, delta + 6 * tid, s.xc + ST_POSE + 7 * tid);
-    else if (tid < 13) pose_plus(s.xs + ST_EX + 7 * (tid - 11), delta + 66 + 6 * (tid - 11), s.xc + ST_EX + 7 * (tid - 11));
+    else if (tid < 13) {
+        const int e = tid - 11;
+        if (ex_open) pose_plus(s.xs + ST_EX + 7 * e, delta + 66 + 6 * e, s.xc + ST_EX + 7 * e);
+        else for (int k = 0; k < 7; k++) s.xc[ST_EX + 7 * e + k] = s.xs[ST_EX + 7 * e + k];     // constant block: bit-exact copy
+    }
     for (int k = tid; k < 99; k += SOLVE_THREADS) { const int f = k / 9, c = k % 9; s.xc[ST_SB + k] = s.xs[ST_SB + k] + delta[NX + NYB * f + c]; }
     for (int k = tid; k < 44; k += SOLVE_THREADS) { const int f = k / 4, c = k % 4; s.xc[ST_LB + k] = s.xs[ST_LB + k] + delta[NX + NYB * f + 9 + c]; }
     if (tid == 0) s.xc[ST_TD] = s.xs[ST_TD];
@@ -836,7 +840,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
             }
             __syncthreads();
             // =============================== candidate point and its cost ===================================
-            apply_plus(s, s.stp, lam, stl, lamc, nF, tid);
+            apply_plus(s, s.stp, lam, stl, lamc, nF, ex_open, tid);
             load_geometry(s.xc, s, tid);
             {
                 double part[2];

@@ -151,7 +151,7 @@ typedef struct CerbPrior {
     int32_t block_kind[CERB_MAX_PRIOR_BLOCKS];    /* which para_* array the kept block address maps to */
     int32_t block_index[CERB_MAX_PRIOR_BLOCKS];   /* index into that array */
     int32_t block_col[CERB_MAX_PRIOR_BLOCKS];     /* keep_block_idx[i] - m */
-    double block_x0[CERB_MAX_PRIOR_BLOCKS][7];    /* keep_block_data[i] (global size, unused tail 0) */
+    double block_x0[CERB_MAX_PRIOR_BLOCKS][9];    /* keep_block_data[i] (global size <= 9, unused tail 0) */
     const double *linearized_jacobians;           /* n x n, column-major (Eigen::MatrixXd) */
     const double *linearized_residuals;           /* n */
 } CerbPrior;

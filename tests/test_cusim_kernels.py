@@ -1,0 +1,103 @@
+"""The sm_100a kernel sources, run on CPU threads by tests/cusim, against the CPU oracle (non-GPU tier).
+The same comparisons run on the real device in test_gpu_parity.py."""
+import numpy as np
+import pytest
+from cerberus_b200 import abi, synth
+from oracle_lib import OracleBackend
+from helpers import sim_backend, small_cfg, state_diffs, prior_canonical
+from test_oracle_jacobians import proj_inputs, imu_leg_setup
+
+ob = OracleBackend()
+
+
+@pytest.fixture(scope="module")
+def sb():
+    return sim_backend(small_cfg())
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_projection_kernel(sb, kind):
+    args = proj_inputs(np.random.default_rng(kind), 40)
+    r0, j0 = ob.eval_projection(kind, *args)
+    r1, j1 = sb.eval_projection(kind, *args)
+    assert np.abs(r0 - r1).max() < 1e-9 * max(1.0, np.abs(r0).max())
+    assert np.abs(j0 - j1).max() < 1e-10 * np.abs(j0).max()
+
+
+def test_imu_leg_kernel(sb):
+    pre, params = imu_leg_setup(3)
+    r0, j0, s0 = ob.eval_imu_leg(pre, params)
+    r1, j1, s1 = sb.eval_imu_leg(pre, params)
+    assert np.abs(s0 - s1).max() < 1e-10 * np.abs(s0).max()
+    assert np.abs(r0 - r1).max() < 1e-9 * np.abs(r0).max()
+    assert np.abs(j0 - j1).max() < 1e-9 * np.abs(j0).max()
+
+
+def test_prior_kernel(sb):
+    batch = synth.generate_batch(1, 8, ob, prior_features=6)
+    st = batch.state_array()
+    st["para_Pose"][0, :, :3] += 0.01; st["para_Pose"][0, :, 3:7] += 0.002
+    st["para_Pose"][0, :, 3:7] /= np.linalg.norm(st["para_Pose"][0, :, 3:7], axis=-1, keepdims=True)
+    st["para_SpeedBias"][0, 0] += 0.01
+    pr = batch.descs[0].prior
+    ncols = 7 * 12 + 9 + 4 + 1
+    r0, j0 = ob.eval_prior(pr, batch.states[0], ncols)
+    r1, j1 = sb.eval_prior(pr, batch.states[0], ncols)
+    assert np.abs(r0 - r1).max() < 1e-9 * np.abs(r0).max() and np.abs(j0 - j1).max() == 0.0
+
+
+@pytest.mark.parametrize("realistic,iters", [(False, 3), (True, 4)])
+def test_fused_solve_matches_oracle(realistic, iters):
+    cfg = small_cfg(iters=iters)
+    o, s = OracleBackend(cfg), sim_backend(cfg)
+    batch = synth.generate_batch(2, 10, o, realistic=realistic, window0=11, prior_features=6)
+    st = batch.state_array(); saved = batch.copy_states()
+    # linearisation probe: cost, gradient and diag(J^T J) at the initial point
+    s.upload(batch)
+    cost, g, d = s.debug_linearize(batch, 1)
+    g0, d0 = o.solve_window(batch, 1, want_probe=True)
+    assert abs(cost - batch.reports[1].initial_cost) < 1e-9 * cost
+    assert np.abs(g - g0).max() < 1e-9 * np.abs(g0).max()
+    assert (np.abs(d - d0) / np.maximum(np.abs(d0), 1e-300)).max() < 1e-8
+    batch.restore_states(saved)
+    rep_o = o.solve_batch(batch); ref = st.copy(); lam = batch.para_Feature.copy()
+    batch.restore_states(saved)
+    rep_s = s.solve_batch(batch)
+    assert (rep_o["iterations"] == rep_s["iterations"]).all() and (rep_o["num_successful_steps"] == rep_s["num_successful_steps"]).all()
+    assert np.abs(rep_o["final_cost"] - rep_s["final_cost"]).max() < 1e-7 * rep_o["final_cost"].max()
+    diffs = state_diffs(batch.state_array(), ref)
+    assert diffs["para_Pose"] < 1e-7 and diffs["para_SpeedBias"] < 1e-6 and diffs["para_Ex_Pose"] < 1e-7, diffs
+    assert np.abs(batch.para_Feature - lam).max() < 1e-7
+
+
+def test_masked_blocks_and_missing_prior():
+    """ex / leg bias constant, no prior: the masked dimensions must not move and the rest must match the oracle."""
+    cfg = small_cfg(iters=3); cfg.optimize_leg_bias = 0
+    o, s = OracleBackend(cfg), sim_backend(cfg)
+    batch = synth.generate_batch(1, 10, o, with_prior=False, window0=3)
+    batch.descs[0].extrinsic_open = 0
+    st = batch.state_array(); saved = batch.copy_states()
+    ex0, lb0 = st["para_Ex_Pose"].copy(), st["para_LegBias"].copy()
+    o.solve_batch(batch); ref = st.copy()
+    batch.restore_states(saved)
+    s.solve_batch(batch)
+    st = batch.state_array()
+    assert (st["para_Ex_Pose"] == ex0).all() and (st["para_LegBias"] == lb0).all()
+    assert state_diffs(st, ref)["para_Pose"] < 1e-7
+
+
+def test_marginalization_glue_matches_oracle(sb):
+    """MARGIN_OLD through the device evaluators + numpy glue vs the oracle's restatement: same information matrix."""
+    cfg = small_cfg()
+    for realistic in (False, True):
+        src = synth.generate_batch(2, 10, ob, realistic=realistic, with_prior=False, window0=21)
+        if realistic:
+            src.features[:, :4]["start_frame"] = 0       # make sure some features are anchored at frame 0
+            src.features[:, :4]["n_obs"] = np.minimum(src.features[:, :4]["n_obs"], 11)
+        a, b = synth.generate_batch(2, 10, ob, with_prior=False, window0=21), synth.generate_batch(2, 10, ob, with_prior=False, window0=21)
+        ob.marginalize(cfg, src, a); sb.marginalize(cfg, src, b)
+        for w in range(2):
+            A0, b0, x0 = prior_canonical(a, w); A1, b1, x1 = prior_canonical(b, w)
+            assert A0.shape == A1.shape
+            assert np.abs(A0 - A1).max() < 1e-5 * np.abs(A0).max() and np.abs(b0 - b1).max() < 1e-4 * np.abs(b0).max()
+            assert all(np.abs(x0[k] - x1[k]).max() == 0 for k in x0)
