@@ -19,7 +19,7 @@
 
 namespace cerb {
 
-enum { CERB_WINDOW = 10, NX = 78, NYB = 13, NFR = 11, NY = 143, NR = 221, NRP = 224, SOLVE_THREADS = 256, FT = 64, TILE_LD = 36, NOBS_PLANES = 9 };
+enum { CERB_WINDOW = 10, NX = 78, NYB = 13, NFR = 11, NY = 143, NR = 221, NRP = 224, SOLVE_THREADS = 256, FT = 64, TILE_LD = 33, NOBS_PLANES = 9 };
 
 struct SolveParams {
     int n_windows, maxF, maxObs, max_iters, optimize_leg_bias;
@@ -167,7 +167,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
         for (int j = 0; j < NFR; j++) {
             // --- evaluate the factors of frame j into the tile -------------------------------------------------
             if (tid < 2 * FT) {
-                double *row0 = s.tile + (2 * tid) * TILE_LD, *row1 = row0 + TILE_LD;
+                double *row0 = s.tile + tid * TILE_LD, *row1 = row0 + 128 * TILE_LD;      // factor tid owns rows tid and tid + 128
                 double r[2]; ProjJac J;
                 double wjv[6] = {0, 0, 0, 0, 0, 0};
                 if (ev && eval_obs(P, s, x, obs, stereo, c, j, cam, r, &J)) {
@@ -210,7 +210,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
                     for (int k = 0; k < 10; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
                     for (int ks = 0; ks < 8; ks++) {
                         const int row = 32 * wid + 4 * ks + (lane & 3);
-                        const bool on = (s.ti[row >> 1] == a);
+                        const bool on = (s.ti[row & 127] == a);
                         const double *q = s.tile + row * TILE_LD + (lane >> 2);
                         const double v0 = on ? q[0] : 0.0, v1 = on ? q[8] : 0.0, v2 = on ? q[16] : 0.0, v3 = on ? q[24] : 0.0;
                         CERB_DMMA(acc[0][0], acc[0][1], v0, v0, acc[0][0], acc[0][1]);
@@ -531,12 +531,6 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 for (int k = tid; k < NX * nF; k += SOLVE_THREADS) { const int a = k / nF, f = k % nF; W[(size_t)a * F + f] *= s.sc[a] * sl[f]; }
                 for (int f = tid; f < nF; f += SOLVE_THREADS) { hh[f] *= sl[f] * sl[f]; gl[f] *= sl[f]; }
                 __syncthreads();
-                // pristine copy for the mu-retry path
-                for (int k = tid; k < 6084; k += SOLVE_THREADS) bk[k] = s.Hxx[k];
-                for (int k = tid; k < 11154; k += SOLVE_THREADS) bk[6084 + k] = s.Hxy[k];
-                for (int k = tid; k < 1859; k += SOLVE_THREADS) bk[6084 + 11154 + k] = s.Ad[k];
-                for (int k = tid; k < 1690; k += SOLVE_THREADS) bk[6084 + 11154 + 1859 + k] = s.Bo[k];
-                __syncthreads();
                 need_linearize = false;
             }
             // =============================== FinalizeIterationAndCheckIfMinimizerCanContinue =============
@@ -578,18 +572,9 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 __syncthreads();
 
                 // ---- Gauss-Newton step: (H~ + mu D^2) y = g~, retry with mu *= 10 on failure ----------------
-                bool first_attempt = true;
-                while (true) {
+                {
                     const double mu = sca[S_MU];
-                    if (!(mu < 1.0)) { if (tid == 0) sca[S_OK] = 0; __syncthreads(); break; }
-                    if (!first_attempt) {
-                        for (int k = tid; k < 6084; k += SOLVE_THREADS) s.Hxx[k] = bk[k];
-                        for (int k = tid; k < 11154; k += SOLVE_THREADS) s.Hxy[k] = bk[6084 + k];
-                        for (int k = tid; k < 1859; k += SOLVE_THREADS) s.Ad[k] = bk[6084 + 11154 + k];
-                        for (int k = tid; k < 1690; k += SOLVE_THREADS) s.Bo[k] = bk[6084 + 11154 + 1859 + k];
-                    }
-                    first_attempt = false;
-                    if (tid == 0) sca[S_OK] = 1;
+                    if (tid == 0) sca[S_OK] = 1;        // a failure below is handled as an invalid step: mu *= 10, re-linearise
                     __syncthreads();
                     // rhs: yv[0..NR) = g~ ; regularise the diagonals
                     for (int k = tid; k < NR; k += SOLVE_THREADS) {
@@ -627,44 +612,57 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                             }
                         }
                     } else {
-                        // ---- other warps: eliminate the inverse depths  S = Hxx - W diag(1/(h + mu D^2)) W^T ----------
-                        // W is staged through shared memory in tiles of 32 features (raw and scaled by 1/(h + mu D^2));
-                        // each of the 224 threads owns the entries (a, b >= a) with a = ta + 14 i, b = tb + 16 j.
+                        // ---- warps 1..7: eliminate the inverse depths on the fp64 tensor cores ---------------------------
+                        //   S = Hxx - W' W'^T,  rhs_x -= W' (w g_l),  W'[a][f] = W[a][f] / sqrt(h_f + mu D_f^2)
+                        // W' is staged through shared memory 32 features at a time as an 80-row tile whose row 78 carries
+                        // g_l / sqrt(h + mu D^2) (so that column 78 of the Gram matrix is the rhs update) and row 79 is zero.
+                        // The 55 upper 8x8 blocks of the 80x80 Gram matrix are dealt round-robin to the 7 warps.
                         const int t2 = tid - 32, n2 = SOLVE_THREADS - 32;
-                        const int ta = t2 >> 4, tb = t2 & 15;
-                        double acc[36];
-                        for (int k = 0; k < 36; k++) acc[k] = 0.0;
-                        double racc = 0.0;                        // rhs_x entry a = t2 (t2 < NX)
-                        double *tw = s.Ju, *tws = s.Ju + NX * 32; // two tiles of 78 x 32 (aliases Ju .. wj, unused during the solve)
+                        const int wq = (tid >> 5) - 1, lane = tid & 31;
+                        const int LDW = 36;
+                        double *tw = s.Ju;                         // 80 x 36 tile (aliases Ju .. red, unused during the solve)
+                        double *sinv = s.wj;                       // <= CERB features: 1 / sqrt(h + mu D^2)   (wj: 1024 doubles)
+                        for (int f = t2; f < nF; f += n2) sinv[f] = 1.0 / sqrt(hh[f] + mu * Dl[f] * Dl[f]);
+                        double acc[8][2];
+                        for (int k = 0; k < 8; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
+                        int tmi[8], tni[8];
+                        for (int k = 0; k < 8; k++) {
+                            int idx = wq + 7 * k, mi = 0;
+                            if (idx >= 55) { tmi[k] = -1; tni[k] = 0; continue; }
+                            while (idx >= 10 - mi) { idx -= 10 - mi; mi++; }
+                            tmi[k] = mi; tni[k] = mi + idx;
+                        }
+                        CERB_BAR_SYNC(1, n2);
                         for (int f0 = 0; f0 < nF; f0 += 32) {
                             const int nf = (nF - f0) < 32 ? (nF - f0) : 32;
-                            for (int e = t2; e < NX * 32; e += n2) {
+                            for (int e = t2; e < 80 * 32; e += n2) {
                                 const int a = e >> 5, f = e & 31;
-                                double wv = 0.0, iv = 0.0;
-                                if (f < nf) { wv = W[(size_t)a * F + f0 + f]; iv = 1.0 / (hh[f0 + f] + mu * Dl[f0 + f] * Dl[f0 + f]); }
-                                tw[e] = wv; tws[e] = wv * iv;
+                                double v = 0.0;
+                                if (f < nf) { if (a < NX) v = W[(size_t)a * F + f0 + f] * sinv[f0 + f]; else if (a == NX) v = gl[f0 + f] * sinv[f0 + f]; }
+                                tw[a * LDW + f] = v;
                             }
-                            // named barrier among the 224 threads of warps 1..7 (warp 0 is busy with the chain)
                             CERB_BAR_SYNC(1, n2);
-                            int q = 0;
-                            for (int a = ta; a < NX; a += 14)
-                                for (int b = tb; b < NX; b += 16, q++) {
-                                    if (b < a) continue;
-                                    double t = 0.0;
-                                    for (int f = 0; f < 32; f++) t += tw[a * 32 + f] * tws[b * 32 + f];
-                                    acc[q] += t;
+                            for (int ks = 0; ks < 8; ks++) {
+                                const int col = 4 * ks + (lane & 3);
+                                for (int k = 0; k < 8; k++) {
+                                    if (tmi[k] < 0) continue;              // warp-uniform
+                                    const double av = tw[(8 * tmi[k] + (lane >> 2)) * LDW + col];
+                                    const double bv = tw[(8 * tni[k] + (lane >> 2)) * LDW + col];
+                                    CERB_DMMA(acc[k][0], acc[k][1], av, bv, acc[k][0], acc[k][1]);
                                 }
-                            if (t2 < NX) { double t = 0.0; for (int f = 0; f < nf; f++) t += tws[t2 * 32 + f] * gl[f0 + f]; racc += t; }
+                            }
                             CERB_BAR_SYNC(1, n2);
                         }
-                        int q = 0;
-                        for (int a = ta; a < NX; a += 14)
-                            for (int b = tb; b < NX; b += 16, q++) {
-                                if (b < a) continue;
-                                s.Hxx[b * NX + a] -= acc[q];              // lower triangle is the one factored below
-                                if (a != b) s.Hxx[a * NX + b] -= acc[q];
+                        for (int k = 0; k < 8; k++) {
+                            if (tmi[k] < 0) continue;
+                            const int a = 8 * tmi[k] + (lane >> 2);
+                            for (int e = 0; e < 2; e++) {
+                                const int b = 8 * tni[k] + 2 * (lane & 3) + e;
+                                if (a > b || a >= NX || b > NX) continue;
+                                if (b == NX) s.yv[a] -= acc[k][e];            // rhs_x
+                                else { s.Hxx[b * NX + a] -= acc[k][e]; if (a != b) s.Hxx[a * NX + b] -= acc[k][e]; }
                             }
-                        if (t2 < NX) s.yv[t2] -= racc;
+                        }
                     }
                     __syncthreads();
                     // ---- T = L^-1 Hyx (row a of Hxy in place), and the same for the y part of the rhs (row 78) ----
@@ -681,17 +679,39 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                         }
                     }
                     __syncthreads();
-                    // ---- S' = S - T T^T (lower), rhs'_x = rhs_x - T gy' -------------------------------------------
+                    // ---- S' = S - T T^T (lower), rhs'_x = rhs_x - T gy' : Gram matrix of the 79 x 143 matrix [T; gy'^T] on the
+                    // fp64 tensor cores, 55 upper 8x8 blocks dealt round-robin to the 8 warps, K = 143 padded to 144 ----------
                     {
-                        const int ta = tid >> 4, tb = tid & 15;
-                        for (int a = ta; a < NX; a += 16)
-                            for (int b = tb; b < NX; b += 16) {
-                                if (b < a) continue;
-                                double t = 0.0;
-                                for (int q = 0; q < NY; q++) t += s.Hxy[a * NY + q] * s.Hxy[b * NY + q];
-                                s.Hxx[b * NX + a] -= t;
+                        const int wq = tid >> 5, lane = tid & 31;
+                        double acc[7][2];
+                        int tmi[7], tni[7];
+                        for (int k = 0; k < 7; k++) {
+                            acc[k][0] = 0.0; acc[k][1] = 0.0;
+                            int idx = wq + 8 * k, mi = 0;
+                            if (idx >= 55) { tmi[k] = -1; tni[k] = 0; continue; }
+                            while (idx >= 10 - mi) { idx -= 10 - mi; mi++; }
+                            tmi[k] = mi; tni[k] = mi + idx;
+                        }
+                        for (int q0 = 0; q0 < NY; q0 += 4) {
+                            const int q = q0 + (lane & 3);
+                            for (int k = 0; k < 7; k++) {
+                                if (tmi[k] < 0) continue;
+                                const int ra = 8 * tmi[k] + (lane >> 2), rb = 8 * tni[k] + (lane >> 2);
+                                const double av = (q < NY) ? (ra < NX ? s.Hxy[ra * NY + q] : (ra == NX ? s.yv[NX + q] : 0.0)) : 0.0;
+                                const double bv = (q < NY) ? (rb < NX ? s.Hxy[rb * NY + q] : (rb == NX ? s.yv[NX + q] : 0.0)) : 0.0;
+                                CERB_DMMA(acc[k][0], acc[k][1], av, bv, acc[k][0], acc[k][1]);
                             }
-                        if (tid < NX) { double t = 0.0; for (int q = 0; q < NY; q++) t += s.Hxy[tid * NY + q] * s.yv[NX + q]; s.yv[tid] -= t; }
+                        }
+                        for (int k = 0; k < 7; k++) {
+                            if (tmi[k] < 0) continue;
+                            const int a = 8 * tmi[k] + (lane >> 2);
+                            for (int e = 0; e < 2; e++) {
+                                const int b = 8 * tni[k] + 2 * (lane & 3) + e;
+                                if (a > b || a >= NX || b > NX) continue;
+                                if (b == NX) s.yv[a] -= acc[k][e];
+                                else s.Hxx[b * NX + a] -= acc[k][e];
+                            }
+                        }
                     }
                     __syncthreads();
                     // ---- dense Cholesky of the 78 x 78 lower triangle, rhs carried as an extra row (z = L^-1 rhs) ----
@@ -762,9 +782,6 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                     }
                     for (int k = tid; k < NR; k += SOLVE_THREADS) if (!(fabs(s.yv[k]) < 1e300)) bad = 1.0;
                     if (bad != 0.0) sca[S_OK] = 0;          // benign race: every writer stores 0
-                    __syncthreads();
-                    if (sca[S_OK] != 0.0) break;
-                    if (tid == 0) sca[S_MU] = mu * 10.0;
                     __syncthreads();
                 }
                 if (sca[S_OK] != 0.0) {
