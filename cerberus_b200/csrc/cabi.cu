@@ -29,7 +29,8 @@ template <typename T> static cudaError_t hmalloc(T **p, size_t n) { return cudaM
 struct CerbHandle {
     CerbSolverConfig cfg;
     int sm_count = 0, grid = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_pending = false;
     double last_ms = 0; int last_launches = 0;
@@ -98,6 +99,8 @@ int cerb_create(const CerbSolverConfig *cfg, CerbHandle **out) {
     if (h->smem_bytes > prop.sharedMemPerBlockOptin) { delete h; return fail(CERB_ERR_CUDA, "solve kernel needs more shared memory than the device offers"); }
     CUDA_TRY(cudaFuncSetAttribute(vilo_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     CUDA_TRY(cudaStreamCreate(&h->stream));
+    CUDA_TRY(cudaStreamCreate(&h->copy_stream));
+    for (int k = 0; k < 8; k++) CUDA_TRY(cudaEventCreate(&h->ev_copy[k]));
     CUDA_TRY(cudaEventCreate(&h->ev0)); CUDA_TRY(cudaEventCreate(&h->ev1));
     const size_t B = h->B, F = h->F, O = h->O;
     h->ws_stride = ws_size(h->F);
@@ -128,6 +131,8 @@ void cerb_destroy(CerbHandle *h) {
     for (void *p : hst) if (p) cudaFreeHost(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int k = 0; k < 8; k++) if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -208,13 +213,13 @@ static int pack_window(CerbHandle *h, int w, const CerbWindowDesc &d, const Cerb
     return CERB_OK;
 }
 
-static int pack_all(CerbHandle *h, int n, const CerbWindowDesc *descs, const CerbWindowState *states) {
+static int pack_range(CerbHandle *h, int w0, int n, const CerbWindowDesc *descs, const CerbWindowState *states) {
     unsigned hw = std::thread::hardware_concurrency();
     int nth = (int)std::min<unsigned>(hw ? hw : 1, 16u);
     if (n < 8) nth = 1;
     std::vector<int> rcs(nth, 0); std::vector<std::string> errs(nth);
     auto work = [&](int t) {
-        for (int w = t; w < n; w += nth) { int rc = pack_window(h, w, descs[w], states[w]); if (rc) { rcs[t] = rc; errs[t] = g_err; return; } }
+        for (int w = w0 + t; w < w0 + n; w += nth) { int rc = pack_window(h, w, descs[w], states[w]); if (rc) { rcs[t] = rc; errs[t] = g_err; return; } }
     };
     std::vector<std::thread> th;
     for (int t = 1; t < nth; t++) th.emplace_back(work, t);
@@ -224,52 +229,61 @@ static int pack_all(CerbHandle *h, int n, const CerbWindowDesc *descs, const Cer
     return CERB_OK;
 }
 
-static int upload(CerbHandle *h, int n) {
-    const size_t F = h->F, O = h->O;
-    cudaStream_t s = h->stream;
-#define H2D(dst, src, count) CUDA_TRY(cudaMemcpyAsync(dst, src, (count) * sizeof(*(src)), cudaMemcpyHostToDevice, s))
-    H2D(h->d_nfeat, h->h_nfeat, (size_t)n); H2D(h->d_fstart, h->h_fstart, n * F); H2D(h->d_fnobs, h->h_fnobs, n * F); H2D(h->d_foff, h->h_foff, n * F);
-    H2D(h->d_flags, h->h_flags, (size_t)n); H2D(h->d_stereo, h->h_stereo, n * O); H2D(h->d_pmeta, h->h_pmeta, (size_t)n * PRIOR_META_STRIDE);
-    H2D(h->d_obs, h->h_obs, n * NOBS_PLANES * O); H2D(h->d_pre, h->h_pre, (size_t)n * 10 * PRE_STRIDE);
-    H2D(h->d_pJ, h->h_pJ, (size_t)n * PRIOR_LD * PRIOR_LD); H2D(h->d_pr, h->h_pr, (size_t)n * PRIOR_LD); H2D(h->d_px0, h->h_px0, (size_t)n * 16 * 9);
-    H2D(h->d_state0, h->h_state, (size_t)n * ST_STRIDE); H2D(h->d_lam0, h->h_lam, n * F);
+static int pack_all(CerbHandle *h, int n, const CerbWindowDesc *descs, const CerbWindowState *states) { return pack_range(h, 0, n, descs, states); }
+
+// H2D of windows [w0, w0 + n) from the pinned staging buffers on stream s
+static int upload_range(CerbHandle *h, int w0, int n, cudaStream_t s) {
+    const size_t F = h->F, O = h->O, W0 = (size_t)w0;
+#define H2D(dst, src, per) CUDA_TRY(cudaMemcpyAsync((dst) + W0 * (per), (src) + W0 * (per), (size_t)n * (per) * sizeof(*(src)), cudaMemcpyHostToDevice, s))
+    H2D(h->d_nfeat, h->h_nfeat, 1); H2D(h->d_fstart, h->h_fstart, F); H2D(h->d_fnobs, h->h_fnobs, F); H2D(h->d_foff, h->h_foff, F);
+    H2D(h->d_flags, h->h_flags, 1); H2D(h->d_stereo, h->h_stereo, O); H2D(h->d_pmeta, h->h_pmeta, (size_t)PRIOR_META_STRIDE);
+    H2D(h->d_obs, h->h_obs, NOBS_PLANES * O); H2D(h->d_pre, h->h_pre, (size_t)10 * PRE_STRIDE);
+    H2D(h->d_pJ, h->h_pJ, (size_t)PRIOR_LD * PRIOR_LD); H2D(h->d_pr, h->h_pr, (size_t)PRIOR_LD); H2D(h->d_px0, h->h_px0, (size_t)16 * 9);
+    H2D(h->d_state0, h->h_state, (size_t)ST_STRIDE); H2D(h->d_lam0, h->h_lam, F);
 #undef H2D
-    h->n = n;
     return CERB_OK;
 }
+static int upload(CerbHandle *h, int n) { int rc = upload_range(h, 0, n, h->stream); h->n = n; return rc; }
 
-static SolveParams make_params(CerbHandle *h, int max_iters, double *dbg, int dbg_window) {
+static SolveParams make_params(CerbHandle *h, int w0, int n, int max_iters, double *dbg, int dbg_window) {
     SolveParams P;
     std::memset(&P, 0, sizeof(P));
     const CerbSolverConfig &c = h->cfg;
-    P.n_windows = h->n; P.maxF = h->F; P.maxObs = h->O; P.max_iters = max_iters; P.optimize_leg_bias = c.optimize_leg_bias;
+    P.n_windows = n; P.maxF = h->F; P.maxObs = h->O; P.max_iters = max_iters; P.optimize_leg_bias = c.optimize_leg_bias;
     for (int k = 0; k < 3; k++) P.G[k] = c.g[k];
     P.sqrt_info = c.visual_sqrt_info; P.huber = c.huber_delta;
     P.radius0 = c.initial_trust_region_radius; P.max_radius = c.max_trust_region_radius; P.min_radius = c.min_trust_region_radius;
     P.min_rel_dec = c.min_relative_decrease; P.ftol = c.function_tolerance; P.gtol = c.gradient_tolerance; P.ptol = c.parameter_tolerance;
-    P.n_features = h->d_nfeat; P.feat_start = h->d_fstart; P.feat_nobs = h->d_fnobs; P.feat_off = h->d_foff; P.flags = h->d_flags;
-    P.obs = h->d_obs; P.obs_stereo = h->d_stereo; P.pre = h->d_pre; P.sinfo = h->d_sinfo;
-    P.prior_J = h->d_pJ; P.prior_r = h->d_pr; P.prior_x0 = h->d_px0; P.prior_Hp = h->d_pHp; P.prior_meta = h->d_pmeta;
-    P.state = h->d_state; P.lam = h->d_lam; P.rep_i = h->d_repi; P.rep_d = h->d_repd; P.ws = h->d_ws; P.ws_stride = h->ws_stride;
+    const size_t W0 = (size_t)w0, F = h->F, O = h->O;
+    P.n_features = h->d_nfeat + W0; P.feat_start = h->d_fstart + W0 * F; P.feat_nobs = h->d_fnobs + W0 * F; P.feat_off = h->d_foff + W0 * F; P.flags = h->d_flags + W0;
+    P.obs = h->d_obs + W0 * NOBS_PLANES * O; P.obs_stereo = h->d_stereo + W0 * O; P.pre = h->d_pre + W0 * 10 * PRE_STRIDE; P.sinfo = h->d_sinfo + W0 * 10 * 961;
+    P.prior_J = h->d_pJ + W0 * PRIOR_LD * PRIOR_LD; P.prior_r = h->d_pr + W0 * PRIOR_LD; P.prior_x0 = h->d_px0 + W0 * 16 * 9; P.prior_Hp = h->d_pHp + W0 * PRIOR_LD * PRIOR_LD;
+    P.prior_meta = h->d_pmeta + W0 * PRIOR_META_STRIDE;
+    P.state = h->d_state + W0 * ST_STRIDE; P.lam = h->d_lam + W0 * F; P.rep_i = h->d_repi + W0 * 4; P.rep_d = h->d_repd + W0 * 2; P.ws = h->d_ws; P.ws_stride = h->ws_stride;
     P.dbg = dbg; P.dbg_window = dbg_window;
     return P;
 }
 
-// restore the initial states, prepare (sqrt_info, prior Gram matrix) and solve; all asynchronous on the stream
+// restore the initial states of windows [w0, w0 + n), prepare (sqrt_info, prior Gram matrix) and solve; asynchronous on the stream
+static int enqueue_solve(CerbHandle *h, int w0, int n, int max_iters, double *dbg, int dbg_window) {
+    cudaStream_t s = h->stream;
+    const size_t W0 = (size_t)w0;
+    CUDA_TRY(cudaMemcpyAsync(h->d_state + W0 * ST_STRIDE, h->d_state0 + W0 * ST_STRIDE, (size_t)n * ST_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_lam + W0 * h->F, h->d_lam0 + W0 * h->F, (size_t)n * h->F * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    const int nfac = n * 10;
+    CERB_LAUNCH(imu_leg_prepare_kernel, (nfac + 1) / 2, 64, 0, s, nfac, (const double *)(h->d_pre + W0 * 10 * PRE_STRIDE), h->d_sinfo + W0 * 10 * 961);
+    CERB_LAUNCH(prior_prepare_kernel, n, 256, 0, s, (const double *)(h->d_pJ + W0 * PRIOR_LD * PRIOR_LD), (const int *)(h->d_pmeta + W0 * PRIOR_META_STRIDE), h->d_pHp + W0 * PRIOR_LD * PRIOR_LD);
+    SolveParams P = make_params(h, w0, n, max_iters, dbg, dbg_window);
+    CERB_LAUNCH(vilo_solve_kernel, std::min(n, h->grid), SOLVE_THREADS, h->smem_bytes, s, P);
+    CUDA_TRY(cudaGetLastError());
+    return CERB_OK;
+}
 static int launch_solve(CerbHandle *h, int max_iters, double *dbg, int dbg_window, bool timed) {
     const int n = h->n;
     if (n < 1) return fail(CERB_ERR_BAD_ARGUMENT, "no resident batch");
-    cudaStream_t s = h->stream;
-    if (timed) CUDA_TRY(cudaEventRecord(h->ev0, s));
-    CUDA_TRY(cudaMemcpyAsync(h->d_state, h->d_state0, (size_t)n * ST_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->d_lam, h->d_lam0, (size_t)n * h->F * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    const int nfac = n * 10;
-    CERB_LAUNCH(imu_leg_prepare_kernel, (nfac + 1) / 2, 64, 0, s, nfac, (const double *)h->d_pre, h->d_sinfo);
-    CERB_LAUNCH(prior_prepare_kernel, n, 256, 0, s, (const double *)h->d_pJ, (const int *)h->d_pmeta, h->d_pHp);
-    SolveParams P = make_params(h, max_iters, dbg, dbg_window);
-    CERB_LAUNCH(vilo_solve_kernel, std::min(n, h->grid), SOLVE_THREADS, h->smem_bytes, s, P);
-    CUDA_TRY(cudaGetLastError());
-    if (timed) { CUDA_TRY(cudaEventRecord(h->ev1, s)); h->ev_pending = true; h->last_launches = 3; }
+    if (timed) CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    int rc = enqueue_solve(h, 0, n, max_iters, dbg, dbg_window); if (rc) return rc;
+    if (timed) { CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->ev_pending = true; h->last_launches = 3; }
     return CERB_OK;
 }
 
@@ -346,8 +360,32 @@ int cerb_last_solve_stats(CerbHandle *h, double *kernel_ms, int32_t *kernel_laun
     return CERB_OK;
 }
 int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, CerbWindowState *states, CerbSolveReport *reports) {
-    int rc = cerb_batch_upload(h, n, descs, states); if (rc) return rc;
-    rc = launch_solve(h, h->cfg.max_num_iterations, nullptr, -1, true); if (rc) return rc;
+    if (!h || !descs || !states) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    if (n < 1 || n > h->B) return fail(CERB_ERR_BAD_ARGUMENT, "batch size over capacity");
+    CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+    int rc = collect_time(h); if (rc) return rc;
+    // Pipeline in chunks that are whole waves of the persistent grid (first chunk one wave so the GPU starts early): the
+    // host packs chunk c + 1 and the copy stream moves it while the compute stream solves chunk c.
+    const int wave = h->grid;
+    int bounds[9], nch = 0; bounds[0] = 0;
+    if (n <= 2 * wave) { bounds[1] = n; nch = 1; }
+    else {
+        int pos = wave; bounds[++nch] = pos;
+        const int rest = n - pos, per = ((rest + 5) / 6 + wave - 1) / wave * wave;      // <= 6 more chunks, whole waves each
+        while (pos < n && nch < 7) { pos = std::min(n, pos + per); bounds[++nch] = pos; }
+        bounds[nch] = n;
+    }
+    h->n = n;
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    for (int c = 0; c < nch; c++) {
+        const int w0 = bounds[c], cn = bounds[c + 1] - bounds[c];
+        rc = pack_range(h, w0, cn, descs, states); if (rc) return rc;
+        rc = upload_range(h, w0, cn, h->copy_stream); if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_copy[c], h->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy[c], 0));
+        rc = enqueue_solve(h, w0, cn, h->cfg.max_num_iterations, nullptr, -1); if (rc) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->ev_pending = true; h->last_launches = 3 * nch;
     return download(h, states, reports);
 }
 int cerb_solve_window(CerbHandle *h, const CerbWindowDesc *desc, CerbWindowState *state, CerbSolveReport *report) {

@@ -55,10 +55,11 @@ struct Smem {
     double *red;                            // 8 x 256 reduction scratch
     double *wj;                             // 128 x 8 per-thread exchange
     double *sca;                            // 64 scalars
+    double *idg;                            // 143 (+pad): 1 / diag(L) of the block-bidiagonal factor of Hyy
     int *ti;                                // 128 ints: anchor per tile factor ; + misc ints
     double *tile;                           // alias of Hxy (+ Ad, Bo): 256 x TILE_LD tile + 8 x 640 partial Gram tiles
 };
-enum { SMEM_DOUBLES = 6084 + 11154 + 1859 + 1690 + 7 * NRP + 2 * ST_STRIDE + 99 + 18 + 3 + 31 * 39 + 960 + 192 + 8 * 256 + 128 * 8 + 64 + 80 };
+enum { SMEM_DOUBLES = 6084 + 11154 + 1859 + 1690 + 7 * NRP + 2 * ST_STRIDE + 99 + 18 + 3 + 31 * 39 + 960 + 192 + 8 * 256 + 128 * 8 + 64 + 80 + 160 };
 
 CERB_D void smem_carve(double *base, Smem &s) {
     double *p = base;
@@ -69,6 +70,7 @@ CERB_D void smem_carve(double *base, Smem &s) {
     s.Ju = p; p += 31 * 39; s.lin = p; p += 960; s.pdx = p; p += 96; s.pr = p; p += 96;
     s.red = p; p += 8 * 256; s.wj = p; p += 128 * 8; s.sca = p; p += 64;
     s.ti = reinterpret_cast<int *>(p); p += 80;
+    s.idg = p; p += 160;
     s.tile = s.Hxy;
 }
 
@@ -136,7 +138,10 @@ CERB_D double vision_cost(const SolveParams &P, const Smem &s, int w, const doub
 }
 
 // ---- visual part: linearisation.  Accumulates the upper triangle of Hxx, g_x, writes W, hh, gl (global) ----
-CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const double *x, const double *lam, double *W, double *hh, double *gl, int tid) {
+// prescale: write W, hh, gl already multiplied by the Jacobi scales (s.sc for x, sl for the inverse depths), which are
+// fixed after iteration 0 -- saves a read-modify-write pass over W per linearisation.
+CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const double *x, const double *lam, double *W, double *hh, double *gl,
+                               const double *sl, bool prescale, int tid) {
     const int nF = P.n_features[w], F = P.maxF;
     const double *obs = P.obs + (size_t)w * NOBS_PLANES * P.maxObs;
     const int *stereo = P.obs_stereo + (size_t)w * P.maxObs;
@@ -147,6 +152,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
         const int f = c0 + fl;
         const bool ev = (tid < 2 * FT) && (f < nF);
         ObsCtx c; c.start = 0; c.nobs = 0; c.off = 0; c.lam = 1.0; c.pix = c.piy = c.vix = c.viy = c.tdi = 0.0;
+        const double slf = (prescale && ev) ? sl[f] : 1.0;
         if (ev) {
             c.start = P.feat_start[(size_t)w * F + f]; c.nobs = P.feat_nobs[(size_t)w * F + f]; c.off = P.feat_off[(size_t)w * F + f];
             c.lam = lam[f];
@@ -197,7 +203,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
             __syncthreads();
             // --- W rows of frame j: sum of the two cameras -----------------------------------------------------
             if (tid < FT && ev && j != c.start && j >= c.start && j < c.start + c.nobs)
-                for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] = s.wj[tid * 8 + k] + s.wj[(tid + FT) * 8 + k];
+                for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] = (s.wj[tid * 8 + k] + s.wj[(tid + FT) * 8 + k]) * (prescale ? s.sc[6 * j + k] * slf : 1.0);
             // --- J^T J of the tile on the fp64 tensor cores (mma.sync m8n8k4), one pass per anchor frame present.
             // The tile is a (256 rows) x (32 cols: I 6 | J 6 | E0 6 | E1 6 | r | 0-pad) matrix T; the Gram matrix
             // T^T T is cut into 8x8 blocks (10 upper ones); warp wid contracts rows [32 wid, 32 wid + 32), the eight
@@ -259,11 +265,11 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
         __syncthreads();
         if (tid < FT && ev) {
             const double *q = s.tile + tid * 20;
-            hh[f] = h + q[0]; gl[f] = gq + q[1];
+            hh[f] = (h + q[0]) * slf * slf; gl[f] = (gq + q[1]) * slf;
             for (int k = 0; k < 6; k++) {
-                W[(size_t)(6 * c.start + k) * F + f] = wI[k] + q[2 + k];
-                W[(size_t)(66 + k) * F + f] = wE0[k] + q[8 + k];
-                W[(size_t)(72 + k) * F + f] = wE1[k] + q[14 + k];
+                W[(size_t)(6 * c.start + k) * F + f] = (wI[k] + q[2 + k]) * (prescale ? s.sc[6 * c.start + k] * slf : 1.0);
+                W[(size_t)(66 + k) * F + f] = (wE0[k] + q[8 + k]) * (prescale ? s.sc[66 + k] * slf : 1.0);
+                W[(size_t)(72 + k) * F + f] = (wE1[k] + q[14 + k]) * (prescale ? s.sc[72 + k] * slf : 1.0);
             }
         }
         __syncthreads();
@@ -346,16 +352,17 @@ CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const dou
         if (pre[PRE_SUM_DT] > 10.0) continue;                      // estimator.cpp:1119 (uniform across the CTA)
         for (int k = tid; k < 31 * 39; k += SOLVE_THREADS) s.Ju[k] = 0.0;
         __syncthreads();
+        double *Ssm = s.wj;                                         // sqrt_info of this factor (961 doubles; wj holds 1024)
+        { const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + i) * 961; for (int k = tid; k < 961; k += SOLVE_THREADS) Ssm[k] = S[k]; }
         if (tid < 11) imu_leg_fill_ju_part(*reinterpret_cast<const IMULegLin *>(s.lin + 96 * i), pre, s.Ju, 39, tid);
         else if (tid >= 32 && tid < 63) s.Ju[(tid - 32) * 39 + 38] = s.lin[96 * i + (tid - 32)];       // residual column
         __syncthreads();
         double *Jw = s.red;                                         // whitened copy Jw = S Ju (S upper triangular)
         {
-            const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + i) * 961;
             for (int idx = tid; idx < 31 * 39; idx += SOLVE_THREADS) {
                 const int r = idx / 39, c = idx % 39;
                 double t = 0.0;
-                for (int q = r; q < 31; q++) t += S[r * 31 + q] * s.Ju[q * 39 + c];
+                for (int q = r; q < 31; q++) t += Ssm[r * 31 + q] * s.Ju[q * 39 + c];
                 Jw[idx] = t;
             }
         }
@@ -478,7 +485,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 for (int k = tid; k < NRP; k += SOLVE_THREADS) s.g[k] = 0.0;
                 load_geometry(s.xs, s, tid);
                 double part[2];
-                part[0] = vision_linearize(P, s, w, s.xs, lam, W, hh, gl, tid);
+                part[0] = vision_linearize(P, s, w, s.xs, lam, W, hh, gl, sl, iteration > 0, tid);
                 for (int k = tid; k < 11154; k += SOLVE_THREADS) s.Hxy[k] = 0.0;     // the tile aliased Hxy
                 for (int k = tid; k < 1859; k += SOLVE_THREADS) s.Ad[k] = 0.0;
                 for (int k = tid; k < 1690; k += SOLVE_THREADS) s.Bo[k] = 0.0;
@@ -516,7 +523,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 }
                 double gm = 0.0;
                 for (int k = tid; k < NR; k += SOLVE_THREADS) if (s.sc[k] != 0.0) gm = fmax(gm, fabs(s.g[k]));
-                for (int f = tid; f < nF; f += SOLVE_THREADS) gm = fmax(gm, fabs(gl[f]));
+                for (int f = tid; f < nF; f += SOLVE_THREADS) gm = fmax(gm, fabs(iteration > 0 ? gl[f] / sl[f] : gl[f]));   // unscaled gradient
                 s.red[tid] = gm;
                 __syncthreads();
                 for (int st = 128; st > 0; st >>= 1) { if (tid < st) s.red[tid] = fmax(s.red[tid], s.red[tid + st]); __syncthreads(); }
@@ -528,8 +535,10 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 for (int k = tid; k < 1859; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; s.Ad[k] *= s.sc[NX + NYB * f + a] * s.sc[NX + NYB * f + b]; }
                 for (int k = tid; k < 1690; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; s.Bo[k] *= s.sc[NX + NYB * f + a] * s.sc[NX + NYB * (f + 1) + b]; }
                 for (int k = tid; k < NR; k += SOLVE_THREADS) s.g[k] *= s.sc[k];
-                for (int k = tid; k < NX * nF; k += SOLVE_THREADS) { const int a = k / nF, f = k % nF; W[(size_t)a * F + f] *= s.sc[a] * sl[f]; }
-                for (int f = tid; f < nF; f += SOLVE_THREADS) { hh[f] *= sl[f] * sl[f]; gl[f] *= sl[f]; }
+                if (iteration == 0) {      // later linearisations write W, hh, gl pre-scaled
+                    for (int k = tid; k < NX * nF; k += SOLVE_THREADS) { const int a = k / nF, f = k % nF; W[(size_t)a * F + f] *= s.sc[a] * sl[f]; }
+                    for (int f = tid; f < nF; f += SOLVE_THREADS) { hh[f] *= sl[f] * sl[f]; gl[f] *= sl[f]; }
+                }
                 __syncthreads();
                 need_linearize = false;
             }
@@ -593,10 +602,19 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                                 for (int e = lane; e < 169; e += 32) { const int r = e / NYB, c = e % NYB; if (c > r) continue; double t = 0.0; for (int q = 0; q < NYB; q++) t += M[r * NYB + q] * M[c * NYB + q]; A[e] -= t; }
                                 __syncwarp();
                             }
-                            for (int j = 0; j < NYB; j++) {
-                                if (lane == 0) { double t = A[j * NYB + j]; for (int q = 0; q < j; q++) t -= A[j * NYB + q] * A[j * NYB + q]; if (!(t > 0.0)) { sca[S_OK] = 0; t = 1.0; } A[j * NYB + j] = sqrt(t); }
+                            double *idg = s.idg + NYB * f;
+                            for (int j = 0; j < NYB; j++) {                     // right-looking: short dependency chains
+                                double d = A[j * NYB + j];
+                                if (!(d > 0.0)) { if (lane == 0) sca[S_OK] = 0; d = 1.0; }
+                                const double ljj = sqrt(d), inv = 1.0 / ljj;
                                 __syncwarp();
-                                if (lane > j && lane < NYB) { double t = A[lane * NYB + j]; for (int q = 0; q < j; q++) t -= A[lane * NYB + q] * A[j * NYB + q]; A[lane * NYB + j] = t / A[j * NYB + j]; }
+                                if (lane > j && lane < NYB) A[lane * NYB + j] *= inv;
+                                if (lane == j) { A[j * NYB + j] = ljj; idg[j] = inv; }
+                                __syncwarp();
+                                for (int e = lane; e < 169; e += 32) {
+                                    const int i = e / NYB, k = e % NYB;
+                                    if (k > j && k <= i) A[e] -= A[i * NYB + j] * A[k * NYB + j];
+                                }
                                 __syncwarp();
                             }
                             if (f < NFR - 1) {
@@ -604,7 +622,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                                 double row[NYB];
                                 if (lane < NYB) {
                                     const int r = lane;
-                                    for (int c = 0; c < NYB; c++) { double t = B[c * NYB + r]; for (int q = 0; q < c; q++) t -= row[q] * A[c * NYB + q]; row[c] = t / A[c * NYB + c]; }
+                                    for (int c = 0; c < NYB; c++) { double t = B[c * NYB + r]; for (int q = 0; q < c; q++) t -= row[q] * A[c * NYB + q]; row[c] = t * idg[c]; }
                                 }
                                 __syncwarp();
                                 if (lane < NYB) for (int c = 0; c < NYB; c++) B[lane * NYB + c] = row[c];
@@ -668,14 +686,18 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                     // ---- T = L^-1 Hyx (row a of Hxy in place), and the same for the y part of the rhs (row 78) ----
                     if (tid <= NX) {
                         double *row = (tid < NX) ? s.Hxy + tid * NY : s.yv + NX;
+                        double tp[NYB];
                         for (int f = 0; f < NFR; f++) {
-                            const double *L = s.Ad + f * 169;
+                            const double *L = s.Ad + f * 169, *idg = s.idg + NYB * f;
                             double *t = row + NYB * f;
+                            double tc[NYB];
+                            for (int r = 0; r < NYB; r++) tc[r] = t[r];
                             if (f > 0) {
-                                const double *M = s.Bo + (f - 1) * 169; const double *tp = row + NYB * (f - 1);
-                                for (int r = 0; r < NYB; r++) { double acc = 0.0; for (int q = 0; q < NYB; q++) acc += M[r * NYB + q] * tp[q]; t[r] -= acc; }
+                                const double *M = s.Bo + (f - 1) * 169;
+                                for (int r = 0; r < NYB; r++) { double acc = 0.0; for (int q = 0; q < NYB; q++) acc += M[r * NYB + q] * tp[q]; tc[r] -= acc; }
                             }
-                            for (int r = 0; r < NYB; r++) { double acc = t[r]; for (int q = 0; q < r; q++) acc -= L[r * NYB + q] * t[q]; t[r] = acc / L[r * NYB + r]; }
+                            for (int r = 0; r < NYB; r++) { double acc = tc[r]; for (int q = 0; q < r; q++) acc -= L[r * NYB + q] * tc[q]; tc[r] = acc * idg[r]; }
+                            for (int r = 0; r < NYB; r++) { t[r] = tc[r]; tp[r] = tc[r]; }
                         }
                     }
                     __syncthreads();
@@ -763,7 +785,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                                 __syncwarp();
                             }
                             for (int k = NYB - 1; k >= 0; k--) {
-                                if (tid == 0) u[k] /= L[k * NYB + k];
+                                if (tid == 0) u[k] *= s.idg[NYB * f + k];
                                 __syncwarp();
                                 if (tid < k) u[tid] -= L[k * NYB + tid] * u[k];
                                 __syncwarp();
