@@ -1,0 +1,196 @@
+// oracle/ref_glue.cpp -- TEST INFRASTRUCTURE.
+//
+// Thin extern "C" surface over the reference's OWN factor classes, compiled from the sources where they lie under
+// /root/reference/src (see oracle/Makefile target `ref`) against the header shims of oracle/shim (Eigen / Ceres
+// interfaces / ROS macros are not in this image).  It defines the configuration globals that parameters.cpp would
+// load from the yaml (parameters.cpp needs OpenCV's FileStorage and is not compiled) and forwards to
+//   Projection{TwoFrameOneCam,TwoFrameTwoCam,OneFrameTwoCam}Factor::Evaluate, IMULegFactor::Evaluate,
+//   IMULegIntegrationBase::{push_back,...}, A1Kinematics::*, PoseLocalParameterization::Plus,
+//   MarginalizationFactor::Evaluate.
+// No reference source is copied into this repository; the output (oracle/_ref/libcerberus_ref.so) is git-ignored.
+#include "../include/cerberus_b200.h"
+#include "factor/projectionTwoFrameOneCamFactor.h"
+#include "factor/projectionTwoFrameTwoCamFactor.h"
+#include "factor/projectionOneFrameTwoCamFactor.h"
+#include "factor/imu_leg_factor.h"
+#include "factor/imu_leg_integration_base.h"
+#include "factor/marginalization_factor.h"
+#include "factor/pose_local_parameterization.h"
+#include "legKinematics/A1Kinematics.h"
+#include <cstring>
+
+// ---- globals of src/utils/parameters.cpp that the compiled objects reference --------------------------------
+double ACC_N, ACC_N_Z, ACC_W, GYR_N, GYR_W;
+Eigen::Vector3d G{0.0, 0.0, 9.805};
+int CONTACT_SENSOR_TYPE;
+double PHI_N, DPHI_N, RHO_C_N, RHO_NC_N;
+double V_N_MIN_XY, V_N_MIN_Z, V_N_MIN, V_N_MAX, V_N_FORCE_THRES_RATIO, V_N_TERM1_STEEP, V_N_TERM2_VAR_RESCALE, V_N_TERM3_DISTANCE_RESCALE;
+
+namespace {
+Eigen::Vector3d v3(const double *p) { return Eigen::Vector3d(p[0], p[1], p[2]); }
+struct LegCfg { std::vector<Eigen::VectorXd> rho_fix_list; Eigen::Vector3d p_br; Eigen::Matrix3d R_br; };
+LegCfg g_leg;
+
+IMULegIntegrationBase *make_integrator(const double *acc0, const double *gyr0, const double *phi0, const double *dphi0, const double *c0,
+                                       const double *ba, const double *bg, const double *rho) {
+    Vector_dof phi, dphi; Vector_leg c; Vector_rho r;
+    for (int k = 0; k < 12; k++) { phi(k) = phi0[k]; dphi(k) = dphi0[k]; }
+    for (int k = 0; k < 4; k++) { c(k) = c0[k]; r(k) = rho[k]; }
+    return new IMULegIntegrationBase(v3(acc0), v3(gyr0), phi, dphi, c, v3(ba), v3(bg), r, g_leg.rho_fix_list, g_leg.p_br, g_leg.R_br);
+}
+void load_preint(IMULegIntegrationBase &p, const CerbIMULegPreint &q) {
+    p.sum_dt = q.sum_dt; p.delta_p = v3(q.delta_p); p.delta_v = v3(q.delta_v);
+    p.delta_q = Eigen::Quaterniond(q.delta_q[3], q.delta_q[0], q.delta_q[1], q.delta_q[2]);
+    for (int k = 0; k < 4; k++) { p.delta_epsilon[k] = v3(q.delta_epsilon + 3 * k); p.linearized_rho(k) = q.linearized_rho[k]; }
+    p.linearized_ba = v3(q.linearized_ba); p.linearized_bg = v3(q.linearized_bg);
+    std::memcpy(p.jacobian.data(), q.jacobian, sizeof(q.jacobian));        // both column-major 31x31
+    std::memcpy(p.covariance.data(), q.covariance, sizeof(q.covariance));
+}
+void store_preint(const IMULegIntegrationBase &p, CerbIMULegPreint &q) {
+    q.sum_dt = p.sum_dt;
+    for (int k = 0; k < 3; k++) { q.delta_p[k] = p.delta_p(k); q.delta_v[k] = p.delta_v(k); q.linearized_ba[k] = p.linearized_ba(k); q.linearized_bg[k] = p.linearized_bg(k); }
+    q.delta_q[0] = p.delta_q.x(); q.delta_q[1] = p.delta_q.y(); q.delta_q[2] = p.delta_q.z(); q.delta_q[3] = p.delta_q.w();
+    for (int j = 0; j < 4; j++) { for (int k = 0; k < 3; k++) q.delta_epsilon[3 * j + k] = p.delta_epsilon[j](k); q.linearized_rho[j] = p.linearized_rho(j); }
+    std::memcpy(q.jacobian, p.jacobian.data(), sizeof(q.jacobian));
+    std::memcpy(q.covariance, p.covariance.data(), sizeof(q.covariance));
+}
+const double kZero12[12] = {0}, kZero4[4] = {0}, kZero3[3] = {0};
+}  // namespace
+
+extern "C" {
+
+void ref_set_globals(const CerbPreintConfig *c, const double *g, double visual_sqrt_info) {
+    ACC_N = c->acc_n; ACC_N_Z = c->acc_n_z; GYR_N = c->gyr_n; ACC_W = c->acc_w; GYR_W = c->gyr_w; PHI_N = c->phi_n; DPHI_N = c->dphi_n;
+    RHO_C_N = c->rho_c_n; RHO_NC_N = c->rho_nc_n; V_N_MIN_XY = c->v_n_min_xy; V_N_MIN_Z = c->v_n_min_z; V_N_MIN = c->v_n_min; V_N_MAX = c->v_n_max;
+    V_N_FORCE_THRES_RATIO = c->v_n_force_thres_ratio; V_N_TERM1_STEEP = c->v_n_term1_steep; V_N_TERM2_VAR_RESCALE = c->v_n_term2_var_rescale;
+    V_N_TERM3_DISTANCE_RESCALE = c->v_n_term3_distance_rescale; CONTACT_SENSOR_TYPE = c->contact_sensor_type;
+    G = v3(g);
+    // estimator.cpp:124-126
+    ProjectionTwoFrameOneCamFactor::sqrt_info = visual_sqrt_info * Eigen::Matrix2d::Identity();
+    ProjectionTwoFrameTwoCamFactor::sqrt_info = visual_sqrt_info * Eigen::Matrix2d::Identity();
+    ProjectionOneFrameTwoCamFactor::sqrt_info = visual_sqrt_info * Eigen::Matrix2d::Identity();
+    g_leg.rho_fix_list.clear();
+    for (int l = 0; l < 4; l++) { Eigen::VectorXd f(RHO_FIX_SIZE); f << c->rho_fix[l][0], c->rho_fix[l][1], c->rho_fix[l][2], c->rho_fix[l][3]; g_leg.rho_fix_list.push_back(f); }
+    g_leg.p_br = v3(c->p_br);
+    for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) g_leg.R_br(r, k) = c->R_br[3 * r + k];
+}
+
+int ref_eval_projection(int kind, int n, const double *pose_i, const double *pose_j, const double *ex0, const double *ex1, const double *inv_dep,
+                        const double *td, const double *pts_i, const double *pts_j, const double *vel_i, const double *vel_j, const double *td_i,
+                        const double *td_j, double *residuals, double *jacobians) {
+    for (int k = 0; k < n; k++) {
+        Eigen::Vector3d pi = v3(pts_i + 3 * k), pj = v3(pts_j + 3 * k);
+        Eigen::Vector2d vi(vel_i[2 * k], vel_i[2 * k + 1]), vj(vel_j[2 * k], vel_j[2 * k + 1]);
+        double r[2]; double *J[6]; const double *p[6];
+        if (kind == CERB_PROJ_TWO_FRAME_ONE_CAM) {
+            ProjectionTwoFrameOneCamFactor f(pi, pj, vi, vj, td_i[k], td_j[k]);
+            double *b = jacobians ? jacobians + (size_t)k * 46 : nullptr;
+            p[0] = pose_i + 7 * k; p[1] = pose_j + 7 * k; p[2] = ex0 + 7 * k; p[3] = inv_dep + k; p[4] = td + k;
+            if (b) { J[0] = b; J[1] = b + 14; J[2] = b + 28; J[3] = b + 42; J[4] = b + 44; }
+            f.Evaluate(p, r, b ? J : nullptr);
+        } else if (kind == CERB_PROJ_TWO_FRAME_TWO_CAM) {
+            ProjectionTwoFrameTwoCamFactor f(pi, pj, vi, vj, td_i[k], td_j[k]);
+            double *b = jacobians ? jacobians + (size_t)k * 60 : nullptr;
+            p[0] = pose_i + 7 * k; p[1] = pose_j + 7 * k; p[2] = ex0 + 7 * k; p[3] = ex1 + 7 * k; p[4] = inv_dep + k; p[5] = td + k;
+            if (b) { J[0] = b; J[1] = b + 14; J[2] = b + 28; J[3] = b + 42; J[4] = b + 56; J[5] = b + 58; }
+            f.Evaluate(p, r, b ? J : nullptr);
+        } else {
+            ProjectionOneFrameTwoCamFactor f(pi, pj, vi, vj, td_i[k], td_j[k]);
+            double *b = jacobians ? jacobians + (size_t)k * 32 : nullptr;
+            p[0] = ex0 + 7 * k; p[1] = ex1 + 7 * k; p[2] = inv_dep + k; p[3] = td + k;
+            if (b) { J[0] = b; J[1] = b + 14; J[2] = b + 28; J[3] = b + 30; }
+            f.Evaluate(p, r, b ? J : nullptr);
+        }
+        if (residuals) { residuals[2 * k] = r[0]; residuals[2 * k + 1] = r[1]; }
+    }
+    return 0;
+}
+
+int ref_eval_imu_leg(int n, const CerbIMULegPreint *preint, const double *params, double *residuals, double *jacobians, double *sqrt_info) {
+    for (int k = 0; k < n; k++) {
+        IMULegIntegrationBase *pre = make_integrator(kZero3, kZero3, kZero12, kZero12, kZero4, preint[k].linearized_ba, preint[k].linearized_bg, preint[k].linearized_rho);
+        load_preint(*pre, preint[k]);
+        IMULegFactor f(pre);
+        const double *q = params + (size_t)k * 40;
+        const double *p[6] = {q, q + 7, q + 16, q + 20, q + 27, q + 36};
+        double r[31]; double *J[6];
+        double *b = jacobians ? jacobians + (size_t)k * 31 * 40 : nullptr;
+        if (b) { J[0] = b; J[1] = b + 31 * 7; J[2] = b + 31 * 16; J[3] = b + 31 * 20; J[4] = b + 31 * 27; J[5] = b + 31 * 36; }
+        f.Evaluate(p, r, b ? J : nullptr);
+        if (residuals) for (int i = 0; i < 31; i++) residuals[(size_t)k * 31 + i] = r[i];
+        if (sqrt_info) {   // the statement of imu_leg_factor.cpp:197-198 on the reference's own covariance member
+            Eigen::Matrix<double, 31, 31> si = Eigen::LLT<Eigen::Matrix<double, 31, 31>>(pre->covariance.inverse()).matrixL().transpose();
+            for (int i = 0; i < 31; i++) for (int j = 0; j < 31; j++) sqrt_info[(size_t)k * 961 + i * 31 + j] = si(i, j);
+        }
+        delete pre;
+    }
+    return 0;
+}
+
+int ref_preintegrate(int n, const CerbPreintJob *jobs, CerbIMULegPreint *out) {
+    for (int k = 0; k < n; k++) {
+        const CerbPreintJob &j = jobs[k];
+        IMULegIntegrationBase *pre = make_integrator(j.acc_0, j.gyr_0, j.phi_0, j.dphi_0, j.c_0, j.linearized_ba, j.linearized_bg, j.linearized_rho);
+        for (int s = 0; s < j.n_samples; s++) {
+            const CerbIMULegSample &m = j.samples[s];
+            Vector_dof phi, dphi; Vector_leg c;
+            for (int t = 0; t < 12; t++) { phi(t) = m.phi[t]; dphi(t) = m.dphi[t]; }
+            for (int t = 0; t < 4; t++) c(t) = m.c[t];
+            pre->push_back(m.dt, v3(m.acc), v3(m.gyr), phi, dphi, c);
+        }
+        store_preint(*pre, out[k]);
+        delete pre;
+    }
+    return 0;
+}
+
+int ref_a1_kinematics(int n, const double *q, const double *rho_opt, const double *rho_fix, double *fk, double *jac, double *dfk_drho, double *dJ_dq, double *dJ_drho) {
+    A1Kinematics kin;
+    for (int k = 0; k < n; k++) {
+        Eigen::Vector3d qq = v3(q + 3 * k);
+        Eigen::VectorXd ro(1), rf(4); ro << rho_opt[k]; rf << rho_fix[4 * k], rho_fix[4 * k + 1], rho_fix[4 * k + 2], rho_fix[4 * k + 3];
+        if (fk) { Eigen::Vector3d o = kin.fk(qq, ro, rf); for (int t = 0; t < 3; t++) fk[3 * k + t] = o(t); }
+        if (jac) { Eigen::Matrix3d o = kin.jac(qq, ro, rf); std::memcpy(jac + 9 * k, o.data(), 72); }
+        if (dfk_drho) { Eigen::Matrix<double, 3, RHO_OPT_SIZE> o = kin.dfk_drho(qq, ro, rf); std::memcpy(dfk_drho + 3 * k, o.data(), 24); }
+        if (dJ_dq) { Eigen::Matrix<double, 9, 3> o = kin.dJ_dq(qq, ro, rf); std::memcpy(dJ_dq + 27 * k, o.data(), 216); }
+        if (dJ_drho) { Eigen::Matrix<double, 9, RHO_OPT_SIZE> o = kin.dJ_drho(qq, ro, rf); std::memcpy(dJ_drho + 9 * k, o.data(), 72); }
+    }
+    return 0;
+}
+
+int ref_pose_plus(const double *x, const double *delta, double *out) {
+    PoseLocalParameterization p;
+    static_cast<const ceres::LocalParameterization &>(p).Plus(x, delta, out);   // Plus is private in the subclass, public in the interface
+    return 0;
+}
+
+// MarginalizationFactor::Evaluate of the reference on a prior given in the ABI shape
+int ref_eval_prior(const CerbPrior *prior, const CerbWindowState *state, double *residuals, double *jacobians) {
+    MarginalizationInfo *mi = new MarginalizationInfo();
+    mi->n = prior->n; mi->m = 0;
+    mi->linearized_jacobians = Eigen::MatrixXd(prior->n, prior->n);
+    std::memcpy(mi->linearized_jacobians.data(), prior->linearized_jacobians, sizeof(double) * prior->n * prior->n);
+    mi->linearized_residuals = Eigen::VectorXd(prior->n);
+    for (int i = 0; i < prior->n; i++) mi->linearized_residuals(i) = prior->linearized_residuals[i];
+    std::vector<const double *> params; std::vector<double *> J; size_t off = 0;
+    CerbWindowState st = *state;
+    for (int b = 0; b < prior->num_blocks; b++) {
+        const int kind = prior->block_kind[b], idx = prior->block_index[b];
+        const int size = (kind == CERB_BLOCK_POSE || kind == CERB_BLOCK_EX_POSE) ? 7 : (kind == CERB_BLOCK_SPEEDBIAS ? 9 : (kind == CERB_BLOCK_LEGBIAS ? 4 : 1));
+        mi->keep_block_size.push_back(size); mi->keep_block_idx.push_back(prior->block_col[b]);
+        mi->keep_block_data.push_back(const_cast<double *>(prior->block_x0[b]));
+        const double *p = kind == CERB_BLOCK_POSE ? st.para_Pose[idx] : kind == CERB_BLOCK_SPEEDBIAS ? st.para_SpeedBias[idx] : kind == CERB_BLOCK_LEGBIAS ? st.para_LegBias[idx]
+                        : kind == CERB_BLOCK_EX_POSE ? st.para_Ex_Pose[idx] : st.para_Td;
+        params.push_back(p);
+        J.push_back(jacobians ? jacobians + off : nullptr); off += (size_t)prior->n * size;
+    }
+    {
+        MarginalizationFactor f(mi);
+        f.Evaluate(params.data(), residuals, jacobians ? J.data() : nullptr);
+    }
+    mi->keep_block_data.clear();     // borrowed pointers
+    delete mi;
+    return 0;
+}
+
+}  // extern "C"

@@ -110,3 +110,73 @@ class OracleBackend:
         Ps, Rs, Vs = np.zeros((11, 3)), np.zeros((11, 3, 3)), np.zeros((11, 3))
         self.lib.oracle_double2vector(C.byref(before_state), C.byref(after_state), _p(Ps), _p(Rs), _p(Vs))
         return Ps, Rs, Vs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's OWN factor sources compiled against the header shims (oracle/shim), `make -C oracle ref`
+_REF = None
+
+
+def ref_lib():
+    global _REF
+    if _REF is None:
+        path = os.path.join(_ROOT, "oracle", "_ref", "libcerberus_ref.so")
+        if not os.path.exists(path):
+            if os.path.isdir("/root/reference/src"):
+                subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "oracle"), "ref"])
+            else:
+                return None
+        _REF = C.CDLL(path)
+    return _REF
+
+
+class RefBackend:
+    """Factor evaluators / preintegration / kinematics of the compiled reference sources (no solver: Ceres is absent)."""
+
+    def __init__(self, pcfg=None, g=(0.0, 0.0, 9.805), visual_sqrt_info=460.0 / 1.5):
+        self.lib = ref_lib()
+        if self.lib is None:
+            raise RuntimeError("oracle/_ref/libcerberus_ref.so is not built and /root/reference is absent")
+        self.set_globals(pcfg or abi.default_preint_config(), g, visual_sqrt_info)
+
+    def set_globals(self, pcfg, g=(0.0, 0.0, 9.805), visual_sqrt_info=460.0 / 1.5):
+        garr = (C.c_double * 3)(*g)
+        self.lib.ref_set_globals.argtypes = [C.POINTER(abi.PreintConfig), C.POINTER(C.c_double), C.c_double]
+        self.lib.ref_set_globals(C.byref(pcfg), garr, visual_sqrt_info)
+
+    def eval_projection(self, kind, pose_i, pose_j, ex0, ex1, inv_dep, td, pts_i, pts_j, vel_i, vel_j, td_i, td_j, want_jac=True):
+        n = inv_dep.shape[0]
+        res = np.zeros((n, 2))
+        jac = np.zeros((n, abi.PROJ_JAC_SIZE[kind])) if want_jac else None
+        self.lib.ref_eval_projection(kind, n, _p(pose_i), _p(pose_j), _p(ex0), _p(ex1), _p(inv_dep), _p(td), _p(pts_i), _p(pts_j), _p(vel_i), _p(vel_j),
+                                     _p(td_i), _p(td_j), _p(res), _p(jac))
+        return res, jac
+
+    def eval_imu_leg(self, preint, params, want_jac=True):
+        n = params.shape[0]
+        res, si = np.zeros((n, 31)), np.zeros((n, 961))
+        jac = np.zeros((n, 31 * 40)) if want_jac else None
+        self.lib.ref_eval_imu_leg(n, preint.ctypes.data_as(C.POINTER(abi.IMULegPreint)), _p(params), _p(res), _p(jac), _p(si))
+        return res, jac, si
+
+    def preintegrate(self, pcfg, jobs, n):
+        self.set_globals(pcfg)
+        out = np.zeros(n, dtype=abi.preint_dtype)
+        self.lib.ref_preintegrate(n, jobs, out.ctypes.data_as(C.POINTER(abi.IMULegPreint)))
+        return out
+
+    def a1_kinematics(self, q, rho_opt, rho_fix):
+        n = q.shape[0]
+        fk, jac, dfk, djq, djr = np.zeros((n, 3)), np.zeros((n, 9)), np.zeros((n, 3)), np.zeros((n, 27)), np.zeros((n, 9))
+        self.lib.ref_a1_kinematics(n, _p(q), _p(rho_opt), _p(rho_fix), _p(fk), _p(jac), _p(dfk), _p(djq), _p(djr))
+        return fk, jac, dfk, djq, djr
+
+    def pose_plus(self, x, delta):
+        out = np.zeros(7)
+        self.lib.ref_pose_plus(_p(np.ascontiguousarray(x)), _p(np.ascontiguousarray(delta)), _p(out))
+        return out
+
+    def eval_prior(self, prior, state, n_cols):
+        res, jac = np.zeros(prior.n), np.zeros(prior.n * n_cols)
+        self.lib.ref_eval_prior(C.byref(prior), C.byref(state), _p(res), _p(jac))
+        return res, jac
