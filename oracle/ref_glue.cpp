@@ -193,4 +193,131 @@ int ref_eval_prior(const CerbPrior *prior, const CerbWindowState *state, double 
     return 0;
 }
 
+// Marginalization half of Estimator::optimization() with the reference's OWN classes (ResidualBlockInfo,
+// MarginalizationInfo::{addResidualBlockInfo, preMarginalize, marginalize, getParameterBlocks}, the factor classes,
+// ceres::HuberLoss of the shim): the statements of estimator.cpp:1248-1376 (MARGIN_OLD) / :1377-1455 (SECOND_NEW)
+// re-issued on the ABI structs.  Same output convention as oracle_marginalize (block order = the reference's
+// unordered_map order, i.e. arbitrary).
+int ref_marginalize(const CerbWindowDesc *desc, const CerbWindowState *state_in, int margin_old, CerbPrior *out, double *J_out, double *r_out) {
+    static double para_Pose[CERB_NUM_FRAMES][7], para_SpeedBias[CERB_NUM_FRAMES][9], para_LegBias[CERB_NUM_FRAMES][4], para_Ex_Pose[2][7], para_Td[1][1];
+    static double para_Feature[CERB_NUM_OF_F][1];
+    std::memcpy(para_Pose, state_in->para_Pose, sizeof(para_Pose)); std::memcpy(para_SpeedBias, state_in->para_SpeedBias, sizeof(para_SpeedBias));
+    std::memcpy(para_LegBias, state_in->para_LegBias, sizeof(para_LegBias)); std::memcpy(para_Ex_Pose, state_in->para_Ex_Pose, sizeof(para_Ex_Pose));
+    para_Td[0][0] = state_in->para_Td[0];
+    for (int f = 0; f < desc->n_features; f++) para_Feature[f][0] = state_in->para_Feature[f];
+    auto block_ptr = [&](int kind, int idx) -> double * {
+        return kind == CERB_BLOCK_POSE ? para_Pose[idx] : kind == CERB_BLOCK_SPEEDBIAS ? para_SpeedBias[idx] : kind == CERB_BLOCK_LEGBIAS ? para_LegBias[idx]
+             : kind == CERB_BLOCK_EX_POSE ? para_Ex_Pose[idx] : para_Td[0]; };
+    std::memset(out, 0, sizeof(*out));
+    ceres::LossFunction *loss_function = new ceres::HuberLoss(1.0);
+    MarginalizationInfo *last = nullptr; std::vector<double *> last_blocks;
+    if (desc->prior.valid) {
+        const CerbPrior &pr = desc->prior;
+        last = new MarginalizationInfo(); last->n = pr.n; last->m = 0;
+        last->linearized_jacobians = Eigen::MatrixXd(pr.n, pr.n);
+        std::memcpy(last->linearized_jacobians.data(), pr.linearized_jacobians, sizeof(double) * pr.n * pr.n);
+        last->linearized_residuals = Eigen::VectorXd(pr.n);
+        for (int i = 0; i < pr.n; i++) last->linearized_residuals(i) = pr.linearized_residuals[i];
+        for (int b = 0; b < pr.num_blocks; b++) {
+            const int kind = pr.block_kind[b];
+            const int size = (kind == CERB_BLOCK_POSE || kind == CERB_BLOCK_EX_POSE) ? 7 : (kind == CERB_BLOCK_SPEEDBIAS ? 9 : (kind == CERB_BLOCK_LEGBIAS ? 4 : 1));
+            last->keep_block_size.push_back(size); last->keep_block_idx.push_back(pr.block_col[b]);
+            double *copy = new double[size]; std::memcpy(copy, pr.block_x0[b], sizeof(double) * size);
+            last->keep_block_data.push_back(copy);
+            last_blocks.push_back(block_ptr(kind, pr.block_index[b]));
+        }
+    }
+    MarginalizationInfo *mi = new MarginalizationInfo();
+    std::vector<IMULegIntegrationBase *> keep_pre;
+    if (margin_old) {
+        if (last) {
+            std::vector<int> drop_set;
+            for (int i = 0; i < (int)last_blocks.size(); i++)
+                if (last_blocks[i] == para_Pose[0] || last_blocks[i] == para_SpeedBias[0] || last_blocks[i] == para_LegBias[0]) drop_set.push_back(i);
+            mi->addResidualBlockInfo(new ResidualBlockInfo(new MarginalizationFactor(last), NULL, last_blocks, drop_set));
+        }
+        if (desc->preint[0].sum_dt < 10.0) {
+            IMULegIntegrationBase *pre = make_integrator(kZero3, kZero3, kZero12, kZero12, kZero4, desc->preint[0].linearized_ba, desc->preint[0].linearized_bg, desc->preint[0].linearized_rho);
+            load_preint(*pre, desc->preint[0]); keep_pre.push_back(pre);
+            mi->addResidualBlockInfo(new ResidualBlockInfo(new IMULegFactor(pre), NULL,
+                std::vector<double *>{para_Pose[0], para_SpeedBias[0], para_LegBias[0], para_Pose[1], para_SpeedBias[1], para_LegBias[1]}, std::vector<int>{0, 1, 2}));
+        }
+        for (int fi = 0; fi < desc->n_features; fi++) {
+            const CerbFeature &ft = desc->features[fi];
+            if (ft.start_frame != 0) continue;
+            const CerbObservation &o0 = desc->obs[ft.obs_offset];
+            Eigen::Vector3d pts_i(o0.point[0], o0.point[1], 1.0); Eigen::Vector2d vel_i(o0.velocity[0], o0.velocity[1]);
+            for (int k = 0; k < ft.n_obs; k++) {
+                const CerbObservation &o = desc->obs[ft.obs_offset + k];
+                const int imu_i = 0, imu_j = k;
+                if (imu_i != imu_j) {
+                    Eigen::Vector3d pts_j(o.point[0], o.point[1], 1.0);
+                    auto *f_td = new ProjectionTwoFrameOneCamFactor(pts_i, pts_j, vel_i, Eigen::Vector2d(o.velocity[0], o.velocity[1]), o0.cur_td, o.cur_td);
+                    mi->addResidualBlockInfo(new ResidualBlockInfo(f_td, loss_function,
+                        std::vector<double *>{para_Pose[imu_i], para_Pose[imu_j], para_Ex_Pose[0], para_Feature[fi], para_Td[0]}, std::vector<int>{0, 3}));
+                }
+                if (o.is_stereo) {
+                    Eigen::Vector3d pts_j_right(o.pointRight[0], o.pointRight[1], 1.0); Eigen::Vector2d vr(o.velocityRight[0], o.velocityRight[1]);
+                    if (imu_i != imu_j) {
+                        auto *f = new ProjectionTwoFrameTwoCamFactor(pts_i, pts_j_right, vel_i, vr, o0.cur_td, o.cur_td);
+                        mi->addResidualBlockInfo(new ResidualBlockInfo(f, loss_function,
+                            std::vector<double *>{para_Pose[imu_i], para_Pose[imu_j], para_Ex_Pose[0], para_Ex_Pose[1], para_Feature[fi], para_Td[0]}, std::vector<int>{0, 4}));
+                    } else {
+                        auto *f = new ProjectionOneFrameTwoCamFactor(pts_i, pts_j_right, vel_i, vr, o0.cur_td, o.cur_td);
+                        mi->addResidualBlockInfo(new ResidualBlockInfo(f, loss_function,
+                            std::vector<double *>{para_Ex_Pose[0], para_Ex_Pose[1], para_Feature[fi], para_Td[0]}, std::vector<int>{2}));
+                    }
+                }
+            }
+        }
+    } else {
+        bool has = false;
+        for (double *p : last_blocks) if (p == para_Pose[CERB_WINDOW_SIZE - 1]) has = true;
+        if (!has) { *out = desc->prior; return 0; }
+        std::vector<int> drop_set;
+        for (int i = 0; i < (int)last_blocks.size(); i++) if (last_blocks[i] == para_Pose[CERB_WINDOW_SIZE - 1]) drop_set.push_back(i);
+        mi->addResidualBlockInfo(new ResidualBlockInfo(new MarginalizationFactor(last), NULL, last_blocks, drop_set));
+    }
+    mi->preMarginalize();
+    mi->marginalize();
+    if (!mi->valid) { out->valid = 0; return 0; }
+    std::unordered_map<long, double *> addr_shift;
+    if (margin_old) {
+        for (int i = 1; i <= CERB_WINDOW_SIZE; i++) {
+            addr_shift[reinterpret_cast<long>(para_Pose[i])] = para_Pose[i - 1];
+            addr_shift[reinterpret_cast<long>(para_SpeedBias[i])] = para_SpeedBias[i - 1];
+            addr_shift[reinterpret_cast<long>(para_LegBias[i])] = para_LegBias[i - 1];
+        }
+    } else {
+        for (int i = 0; i <= CERB_WINDOW_SIZE; i++) {
+            if (i == CERB_WINDOW_SIZE - 1) continue;
+            const int t = (i == CERB_WINDOW_SIZE) ? i - 1 : i;
+            addr_shift[reinterpret_cast<long>(para_Pose[i])] = para_Pose[t];
+            addr_shift[reinterpret_cast<long>(para_SpeedBias[i])] = para_SpeedBias[t];
+            addr_shift[reinterpret_cast<long>(para_LegBias[i])] = para_LegBias[t];
+        }
+    }
+    for (int i = 0; i < 2; i++) addr_shift[reinterpret_cast<long>(para_Ex_Pose[i])] = para_Ex_Pose[i];
+    addr_shift[reinterpret_cast<long>(para_Td[0])] = para_Td[0];
+    std::vector<double *> parameter_blocks = mi->getParameterBlocks(addr_shift);
+    out->valid = 1; out->n = mi->n; out->num_blocks = (int)parameter_blocks.size();
+    for (int b = 0; b < out->num_blocks; b++) {
+        double *p = parameter_blocks[b]; int kind = -1, index = 0;
+        for (int i = 0; i < CERB_NUM_FRAMES; i++) {
+            if (p == para_Pose[i]) { kind = CERB_BLOCK_POSE; index = i; }
+            if (p == para_SpeedBias[i]) { kind = CERB_BLOCK_SPEEDBIAS; index = i; }
+            if (p == para_LegBias[i]) { kind = CERB_BLOCK_LEGBIAS; index = i; }
+        }
+        for (int i = 0; i < 2; i++) if (p == para_Ex_Pose[i]) { kind = CERB_BLOCK_EX_POSE; index = i; }
+        if (p == para_Td[0]) { kind = CERB_BLOCK_TD; index = 0; }
+        out->block_kind[b] = kind; out->block_index[b] = index; out->block_col[b] = mi->keep_block_idx[b] - mi->m;
+        for (int k = 0; k < mi->keep_block_size[b]; k++) out->block_x0[b][k] = mi->keep_block_data[b][k];
+    }
+    std::memcpy(J_out, mi->linearized_jacobians.data(), sizeof(double) * mi->n * mi->n);
+    for (int i = 0; i < mi->n; i++) r_out[i] = mi->linearized_residuals(i);
+    out->linearized_jacobians = J_out; out->linearized_residuals = r_out;
+    // (objects are leaked on purpose: MarginalizationInfo's destructor owns the factors and `last`'s data; test helper only)
+    return 0;
+}
+
 }  // extern "C"

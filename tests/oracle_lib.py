@@ -180,3 +180,14 @@ class RefBackend:
         res, jac = np.zeros(prior.n), np.zeros(prior.n * n_cols)
         self.lib.ref_eval_prior(C.byref(prior), C.byref(state), _p(res), _p(jac))
         return res, jac
+
+
+def _ref_marginalize(self, cfg, src, dst, margin_old=True):
+    """RefBackend.marginalize: the reference's own MarginalizationInfo / ResidualBlockInfo classes."""
+    for w in range(src.n):
+        pr = dst.descs[w].prior
+        rc = self.lib.ref_marginalize(C.byref(src.descs[w]), C.byref(src.states[w]), 1 if margin_old else 0, C.byref(pr), _p(dst.prior_J[w]), _p(dst.prior_r[w]))
+        assert rc == 0
+
+
+RefBackend.marginalize = _ref_marginalize

@@ -95,3 +95,24 @@ def test_gpu_kernels_vs_reference_sources(ref):
     a = ref.preintegrate(pcfg, jobs, 6); b = gpu.preintegrate(pcfg, jobs, 6)
     for name in a.dtype.names:
         assert np.abs(a[name] - b[name]).max() <= 1e-11 * max(1e-30, np.abs(a[name]).max()), name
+
+
+@pytest.mark.parametrize("realistic", [False, True])
+def test_marginalization_vs_reference(ref, realistic):
+    """MARGIN_OLD with the reference's own MarginalizationInfo::{preMarginalize, marginalize} and ResidualBlockInfo::Evaluate
+    (marginalization_factor.cpp:12-333) vs the oracle restatement and vs the product's numpy glue over the kernel evaluators."""
+    from helpers import prior_canonical, sim_backend, small_cfg
+    cfg = small_cfg()
+    mk = lambda: synth.generate_batch(2, 10, ob, realistic=realistic, with_prior=False, window0=31)
+    src = mk()
+    if realistic:
+        src.features[:, :4]["start_frame"] = 0
+    a, b, c = mk(), mk(), mk()
+    ref.marginalize(cfg, src, a); ob.marginalize(cfg, src, b); sim_backend(cfg).marginalize(cfg, src, c)
+    for w in range(2):
+        A0, b0, x0 = prior_canonical(a, w)
+        for other in (b, c):
+            A1, b1, x1 = prior_canonical(other, w)
+            assert A0.shape == A1.shape and set(x0) == set(x1)
+            assert np.abs(A0 - A1).max() < 1e-5 * np.abs(A0).max() and np.abs(b0 - b1).max() < 1e-4 * np.abs(b0).max()
+            assert all(np.abs(x0[k][:7] - x1[k][:7]).max() == 0 for k in x0)
