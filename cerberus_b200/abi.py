@@ -42,6 +42,13 @@ class IMULegPreint(C.Structure):
     ]
 
 
+class IMUPreint(C.Structure):
+    _fields_ = [
+        ("sum_dt", C.c_double), ("delta_p", C.c_double * 3), ("delta_q", C.c_double * 4), ("delta_v", C.c_double * 3),
+        ("linearized_ba", C.c_double * 3), ("linearized_bg", C.c_double * 3), ("jacobian", C.c_double * 225), ("covariance", C.c_double * 225),
+    ]
+
+
 class Observation(C.Structure):
     _fields_ = [
         ("point", C.c_double * 2), ("velocity", C.c_double * 2), ("pointRight", C.c_double * 2),
@@ -65,7 +72,7 @@ class Prior(C.Structure):
 class WindowDesc(C.Structure):
     _fields_ = [
         ("n_features", C.c_int32), ("n_obs", C.c_int32),
-        ("features", C.POINTER(Feature)), ("obs", C.POINTER(Observation)), ("preint", C.POINTER(IMULegPreint)),
+        ("features", C.POINTER(Feature)), ("obs", C.POINTER(Observation)), ("preint", C.POINTER(IMULegPreint)), ("imu_preint", C.POINTER(IMUPreint)),
         ("prior", Prior), ("extrinsic_open", C.c_int32), ("td_open", C.c_int32),
     ]
 
@@ -111,11 +118,12 @@ class PreintJob(C.Structure):
 
 
 ABI_STRUCTS = [SolverConfig, IMULegPreint, Observation, Feature, Prior, WindowDesc, WindowState, SolveReport,
-               IMULegSample, PreintConfig, PreintJob]
+               IMULegSample, PreintConfig, PreintJob, IMUPreint]
 
 feature_dtype = np.dtype(Feature)
 obs_dtype = np.dtype(Observation)
 preint_dtype = np.dtype(IMULegPreint)
+imu_preint_dtype = np.dtype(IMUPreint)
 sample_dtype = np.dtype(IMULegSample)
 report_dtype = np.dtype(SolveReport)
 
@@ -181,6 +189,7 @@ class WindowBatch:
         self.features = np.zeros((n, self.max_features), dtype=feature_dtype)
         self.obs = np.zeros((n, self.max_obs), dtype=obs_dtype)
         self.preint = np.zeros((n, WINDOW_SIZE), dtype=preint_dtype)
+        self.imu_preint = None                      # allocated by use_imu_only()
         self.prior_J = np.zeros((n, MAX_PRIOR_DIM * MAX_PRIOR_DIM))
         self.prior_r = np.zeros((n, MAX_PRIOR_DIM))
         self.para_Feature = np.zeros((n, self.max_features))
@@ -195,6 +204,13 @@ class WindowBatch:
             d.prior.linearized_jacobians = self.prior_J[w].ctypes.data_as(c_dp)
             d.prior.linearized_residuals = self.prior_r[w].ctypes.data_as(c_dp)
             self.states[w].para_Feature = self.para_Feature[w].ctypes.data_as(c_dp)
+
+    def use_imu_only(self):
+        """Switch the batch to USE_LEG == 0: descriptors carry IMUFactor preintegrations instead of IMU-leg ones."""
+        self.imu_preint = np.zeros((self.n, WINDOW_SIZE), dtype=imu_preint_dtype)
+        for w in range(self.n):
+            self.descs[w].preint = None
+            self.descs[w].imu_preint = self.imu_preint[w].ctypes.data_as(C.POINTER(IMUPreint))
 
     # numpy views of the state arrays (no copy): shape [n, ...]
     def state_array(self):

@@ -141,7 +141,7 @@ void cerb_destroy(CerbHandle *h) {
 
 // ---- host packing ---------------------------------------------------------------------------------------------
 static void pack_preint(const CerbIMULegPreint &p, double *o) {
-    o[PRE_SUM_DT] = p.sum_dt;
+    o[PRE_SUM_DT] = p.sum_dt; o[PRE_IMU_ONLY] = 0.0;
     for (int k = 0; k < 3; k++) { o[PRE_DP + k] = p.delta_p[k]; o[PRE_DV + k] = p.delta_v[k]; o[PRE_BA + k] = p.linearized_ba[k]; o[PRE_BG + k] = p.linearized_bg[k]; }
     for (int k = 0; k < 4; k++) { o[PRE_DQ + k] = p.delta_q[k]; o[PRE_RHO + k] = p.linearized_rho[k]; }
     for (int k = 0; k < 12; k++) o[PRE_DEPS + k] = p.delta_epsilon[k];
@@ -154,6 +154,25 @@ static void pack_preint(const CerbIMULegPreint &p, double *o) {
     }
     for (int k = 0; k < 4; k++) for (int a = 0; a < 3; a++) o[PRE_DEP_DRHO + 3 * k + a] = J(ILO_EPS1 + 3 * k + a, ILO_RHO1 + k);
     for (int r = 0; r < 31; r++) for (int c = 0; c < 31; c++) o[PRE_INFO + r * 31 + c] = p.covariance[c * 31 + r];
+}
+
+// IntegrationBase result (USE_LEG == 0) embedded in the 31-row IMU-leg layout: rows / columns P, R, V, BA, BG map to their
+// ILStateOrder slots, the EPS / RHO diagonal of the covariance is the identity (block diagonal => sqrt_info restricted to
+// the 15 kept rows equals LLT(cov15^-1).matrixL()^T) and PRE_IMU_ONLY makes the device drop the EPS / RHO residual rows.
+static const int kImuTo31[15] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 21, 22, 23, 24, 25, 26};
+static void pack_imu_preint(const CerbIMUPreint &p, double *o) {
+    for (int k = 0; k < PRE_STRIDE; k++) o[k] = 0.0;
+    o[PRE_SUM_DT] = p.sum_dt; o[PRE_IMU_ONLY] = 1.0;
+    for (int k = 0; k < 3; k++) { o[PRE_DP + k] = p.delta_p[k]; o[PRE_DV + k] = p.delta_v[k]; o[PRE_BA + k] = p.linearized_ba[k]; o[PRE_BG + k] = p.linearized_bg[k]; }
+    for (int k = 0; k < 4; k++) o[PRE_DQ + k] = p.delta_q[k];
+    auto J = [&](int r, int c) { return p.jacobian[c * 15 + r]; };
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+        o[PRE_DP_DBA + 3 * a + b] = J(0 + a, 9 + b); o[PRE_DP_DBG + 3 * a + b] = J(0 + a, 12 + b);
+        o[PRE_DQ_DBG + 3 * a + b] = J(3 + a, 12 + b);
+        o[PRE_DV_DBA + 3 * a + b] = J(6 + a, 9 + b); o[PRE_DV_DBG + 3 * a + b] = J(6 + a, 12 + b);
+    }
+    for (int r = 0; r < 31; r++) o[PRE_INFO + r * 31 + r] = 1.0;
+    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) o[PRE_INFO + kImuTo31[r] * 31 + kImuTo31[c]] = p.covariance[c * 15 + r];
 }
 
 static int pack_prior(const CerbPrior &pr, int *meta, double *J, double *r, double *x0) {
@@ -183,9 +202,9 @@ static int pack_window(CerbHandle *h, int w, const CerbWindowDesc &d, const Cerb
     if (d.n_features < 0 || d.n_features > F) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_features over capacity");
     if (d.n_obs < 0 || d.n_obs > O) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_obs over capacity");
     if (d.td_open) return fail(CERB_ERR_BAD_ARGUMENT, "td estimation (td_open) is not supported by this build; keep para_Td constant");
-    if ((d.n_features && (!d.features || !d.obs || !st.para_Feature)) || !d.preint) return fail(CERB_ERR_BAD_ARGUMENT, "window: null pointer");
+    if ((d.n_features && (!d.features || !d.obs || !st.para_Feature)) || (!d.preint && !d.imu_preint)) return fail(CERB_ERR_BAD_ARGUMENT, "window: null pointer");
     h->h_nfeat[w] = d.n_features;
-    h->h_flags[w] = (d.extrinsic_open ? 1 : 0) | (d.td_open ? 2 : 0);
+    h->h_flags[w] = (d.extrinsic_open ? 1 : 0) | (d.td_open ? 2 : 0) | (d.preint ? 0 : 4);      // bit2: USE_LEG == 0, no leg-bias blocks
     for (int f = 0; f < d.n_features; f++) {
         const CerbFeature &ft = d.features[f];
         if (ft.start_frame < 0 || ft.n_obs < 1 || ft.start_frame + ft.n_obs > CERB_NUM_FRAMES || ft.obs_offset < 0 || ft.obs_offset + ft.n_obs > d.n_obs)
@@ -201,7 +220,10 @@ static int pack_window(CerbHandle *h, int w, const CerbWindowDesc &d, const Cerb
         ob[4 * O + o] = q.pointRight[0]; ob[5 * O + o] = q.pointRight[1]; ob[6 * O + o] = q.velocityRight[0]; ob[7 * O + o] = q.velocityRight[1];
         ob[8 * O + o] = q.cur_td; sto[o] = q.is_stereo;
     }
-    for (int i = 0; i < CERB_WINDOW_SIZE; i++) pack_preint(d.preint[i], h->h_pre + ((size_t)w * 10 + i) * PRE_STRIDE);
+    for (int i = 0; i < CERB_WINDOW_SIZE; i++) {
+        if (d.preint) pack_preint(d.preint[i], h->h_pre + ((size_t)w * 10 + i) * PRE_STRIDE);
+        else pack_imu_preint(d.imu_preint[i], h->h_pre + ((size_t)w * 10 + i) * PRE_STRIDE);
+    }
     int rc = pack_prior(d.prior, h->h_pmeta + (size_t)w * PRIOR_META_STRIDE, h->h_pJ + (size_t)w * PRIOR_LD * PRIOR_LD, h->h_pr + (size_t)w * PRIOR_LD, h->h_px0 + (size_t)w * 16 * 9);
     if (rc) return rc;
     double *s = h->h_state + (size_t)w * ST_STRIDE;
@@ -464,6 +486,40 @@ int cerb_eval_imu_leg(CerbHandle *h, int32_t n, const CerbIMULegPreint *preint, 
     return CERB_OK;
 }
 
+int cerb_eval_imu(CerbHandle *h, int32_t n, const CerbIMUPreint *preint, const double *params, double *residuals, double *jacobians, double *sqrt_info) {
+    if (!h || n < 1 || !preint || !params) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_imu: bad argument");
+    cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
+    std::vector<double> packed(N * PRE_STRIDE), p40(N * 40, 0.0);
+    for (int k = 0; k < n; k++) {
+        pack_imu_preint(preint[k], packed.data() + (size_t)k * PRE_STRIDE);
+        const double *q = params + (size_t)k * 32; double *o = p40.data() + (size_t)k * 40;
+        std::memcpy(o, q, 16 * sizeof(double)); std::memcpy(o + 20, q + 16, 16 * sizeof(double));     // leg-bias slots stay 0
+    }
+    double *dpre = B.up(packed.data(), N * PRE_STRIDE, s), *dsi = B.up(nullptr, N * 961, s), *dpar = B.up(p40.data(), 40 * N, s);
+    double *dr = B.up(nullptr, 31 * N, s), *dJ = jacobians ? B.up(nullptr, 31 * 40 * N, s) : nullptr;
+    if (!dpre || !dsi || !dpar || !dr) return fail(CERB_ERR_CUDA, "device allocation failed");
+    CERB_LAUNCH(imu_leg_prepare_kernel, (n + 1) / 2, 64, 0, s, (int)n, (const double *)dpre, dsi);
+    CERB_LAUNCH(imu_leg_eval_kernel, n, 128, 0, s, (int)n, (const double *)dpre, (const double *)dsi, (const double *)dpar, (const double *)h->d_G, dr, dJ);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> hr(31 * N), hj(jacobians ? 31 * 40 * N : 0), hs(961 * N);
+    CUDA_TRY(cudaMemcpyAsync(hr.data(), dr, hr.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (jacobians) CUDA_TRY(cudaMemcpyAsync(hj.data(), dJ, hj.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hs.data(), dsi, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    // gather the 15 rows P, R, V, BA, BG and the blocks pose_i, speedbias_i, pose_j, speedbias_j
+    const int boff31[4] = {0, 7, 20, 27}, bsz[4] = {7, 9, 7, 9}, boff15[4] = {0, 7, 16, 23};
+    for (int k = 0; k < n; k++) {
+        for (int r = 0; r < 15; r++) {
+            const int R = kImuTo31[r];
+            if (residuals) residuals[(size_t)k * 15 + r] = hr[(size_t)k * 31 + R];
+            if (sqrt_info) for (int c = 0; c < 15; c++) sqrt_info[(size_t)k * 225 + r * 15 + c] = hs[(size_t)k * 961 + R * 31 + kImuTo31[c]];
+            if (jacobians) for (int b = 0; b < 4; b++) for (int c = 0; c < bsz[b]; c++)
+                jacobians[(size_t)k * 15 * 32 + 15 * boff15[b] + r * bsz[b] + c] = hj[(size_t)k * 31 * 40 + 31 * boff31[b] + R * bsz[b] + c];
+        }
+    }
+    return CERB_OK;
+}
+
 int cerb_eval_prior(CerbHandle *h, const CerbPrior *prior, const CerbWindowState *state, double *residuals, double *jacobians) {
     if (!h || !prior || !state || !prior->valid || !residuals) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_prior: bad argument");
     std::vector<int> meta(PRIOR_META_STRIDE); std::vector<double> J(PRIOR_LD * PRIOR_LD, 0.0), r(PRIOR_LD, 0.0), x0(16 * 9, 0.0), st(ST_STRIDE, 0.0);
@@ -504,9 +560,10 @@ int cerb_a1_kinematics(CerbHandle *h, int32_t n, const double *q, const double *
 }
 
 // ---- leg-contact preintegration ------------------------------------------------------------------------------------
-int cerb_preintegrate_batch(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n, const CerbPreintJob *jobs, CerbIMULegPreint *out) {
-    if (!h || !cfg || n < 1 || !jobs || !out) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_preintegrate_batch: bad argument");
+static int preintegrate_impl(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n, const CerbPreintJob *jobs, CerbIMULegPreint *out, CerbIMUPreint *out_imu) {
+    if (!h || !cfg || n < 1 || !jobs || (!out && !out_imu)) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_preintegrate: bad argument");
     PreintParams P;
+    P.imu_only = out_imu ? 1 : 0;
     P.acc_n = cfg->acc_n; P.acc_n_z = cfg->acc_n_z; P.gyr_n = cfg->gyr_n; P.acc_w = cfg->acc_w; P.gyr_w = cfg->gyr_w; P.phi_n = cfg->phi_n; P.dphi_n = cfg->dphi_n;
     P.rho_c_n = cfg->rho_c_n; P.rho_nc_n = cfg->rho_nc_n; P.v_n_min_xy = cfg->v_n_min_xy; P.v_n_min_z = cfg->v_n_min_z; P.v_n_min = cfg->v_n_min; P.v_n_max = cfg->v_n_max;
     P.v_n_force_thres_ratio = cfg->v_n_force_thres_ratio; P.v_n_term1_steep = cfg->v_n_term1_steep; P.v_n_term2_var_rescale = cfg->v_n_term2_var_rescale;
@@ -545,6 +602,14 @@ int cerb_preintegrate_batch(CerbHandle *h, const CerbPreintConfig *cfg, int32_t 
     CUDA_TRY(cudaStreamSynchronize(s));
     for (int j = 0; j < n; j++) {
         const double *o = ho.data() + (size_t)j * PRE_STRIDE, *f = hf.data() + (size_t)j * 1922;
+        if (out_imu) {
+            CerbIMUPreint &r = out_imu[j];
+            r.sum_dt = o[PRE_SUM_DT];
+            for (int k = 0; k < 3; k++) { r.delta_p[k] = o[PRE_DP + k]; r.delta_v[k] = o[PRE_DV + k]; r.linearized_ba[k] = o[PRE_BA + k]; r.linearized_bg[k] = o[PRE_BG + k]; }
+            for (int k = 0; k < 4; k++) r.delta_q[k] = o[PRE_DQ + k];
+            for (int a = 0; a < 15; a++) for (int b = 0; b < 15; b++) { r.jacobian[b * 15 + a] = f[kImuTo31[a] * 31 + kImuTo31[b]]; r.covariance[b * 15 + a] = f[961 + kImuTo31[a] * 31 + kImuTo31[b]]; }
+            continue;
+        }
         CerbIMULegPreint &r = out[j];
         r.sum_dt = o[PRE_SUM_DT];
         for (int k = 0; k < 3; k++) { r.delta_p[k] = o[PRE_DP + k]; r.delta_v[k] = o[PRE_DV + k]; r.linearized_ba[k] = o[PRE_BA + k]; r.linearized_bg[k] = o[PRE_BG + k]; }
@@ -553,6 +618,13 @@ int cerb_preintegrate_batch(CerbHandle *h, const CerbPreintConfig *cfg, int32_t 
         for (int a = 0; a < 31; a++) for (int b = 0; b < 31; b++) { r.jacobian[b * 31 + a] = f[a * 31 + b]; r.covariance[b * 31 + a] = f[961 + a * 31 + b]; }
     }
     return CERB_OK;
+}
+
+int cerb_preintegrate_batch(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n, const CerbPreintJob *jobs, CerbIMULegPreint *out) {
+    return preintegrate_impl(h, cfg, n, jobs, out, nullptr);
+}
+int cerb_preintegrate_imu_batch(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n, const CerbPreintJob *jobs, CerbIMUPreint *out) {
+    return preintegrate_impl(h, cfg, n, jobs, nullptr, out);
 }
 
 // ---- host-side gauge re-anchoring: Estimator::double2vector (estimator.cpp:903-957) ----------------------------------

@@ -18,6 +18,7 @@ enum { PROJ_K1 = 0, PROJ_K2 = 1, PROJ_K3 = 2 };
 enum {
     PRE_SUM_DT = 0, PRE_DP = 1, PRE_DQ = 4, PRE_DV = 8, PRE_DEPS = 11, PRE_BA = 23, PRE_BG = 26, PRE_RHO = 29,
     PRE_DP_DBA = 33, PRE_DP_DBG = 42, PRE_DQ_DBG = 51, PRE_DV_DBA = 60, PRE_DV_DBG = 69, PRE_DEP_DBG = 78, PRE_DEP_DRHO = 114,
+    PRE_IMU_ONLY = 126,          // != 0: plain IMUFactor (imu_factor.h) embedded in the 31-row layout: EPS / RHO rows are absent
     PRE_INFO = 128,              // 31x31 row-major covariance (sqrt_info goes to a separate [961] array per factor)
     PRE_STRIDE = 128 + 961 + 7   // 1096 doubles
 };
@@ -173,6 +174,10 @@ CERB_HD void imu_leg_linearize(const double *pre, const double *pose_i, const do
     }
     st3(r + ILO_BA, Baj - Bai);
     st3(r + ILO_BG, Bgj - Bgi);
+    if (pre[PRE_IMU_ONLY] != 0.0) {      // IMUFactor: 15 rows P, R, V, BA, BG only
+        for (int k = ILO_EPS1; k < ILO_BA; k++) r[k] = 0.0;
+        for (int k = ILO_RHO1; k < IL_RES; k++) r[k] = 0.0;
+    }
     if (!want_jac) return;
     out->RiT = qtoR(Qi_inv);
     out->skP = skew33(aP);
@@ -189,6 +194,7 @@ CERB_HD void imu_leg_linearize(const double *pre, const double *pose_i, const do
 // 10: the leg-length columns) so that 11 threads can fill one factor concurrently.
 CERB_HD void imu_leg_fill_ju_part(const IMULegLin &L, const double *pre, double *Ju, int ld, int part) {
 #define JU(rr, cc) Ju[(rr) * ld + (cc)]
+    const bool imu_only = pre[PRE_IMU_ONLY] != 0.0;
     if (part < 9) {
         const int a = part / 3, b = part % 3;
         const double dt = pre[PRE_SUM_DT];
@@ -210,7 +216,7 @@ CERB_HD void imu_leg_fill_ju_part(const IMULegLin &L, const double *pre, double 
         JU(ILO_R + a, 22 + b) = L.M3.m[3 * a + b];
         // sb_j (cols 25..33)
         JU(ILO_V + a, 25 + b) = rit;
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 4 && !imu_only; k++) {
             JU(ILO_EPS1 + 3 * k + a, b) = -rit;
             JU(ILO_EPS1 + 3 * k + a, 3 + b) = L.skE.m[3 * a + b];
             JU(ILO_EPS1 + 3 * k + a, 12 + b) = -pre[PRE_DEP_DBG + 9 * k + 3 * a + b];
@@ -221,7 +227,7 @@ CERB_HD void imu_leg_fill_ju_part(const IMULegLin &L, const double *pre, double 
             JU(ILO_BA + a, 9 + a) = -1.0;  JU(ILO_BG + a, 12 + a) = -1.0;
             JU(ILO_BA + a, 28 + a) = 1.0;  JU(ILO_BG + a, 31 + a) = 1.0;
         }
-    } else {
+    } else if (!imu_only) {
         for (int k = 0; k < 4; k++) {
             for (int a = 0; a < 3; a++) JU(ILO_EPS1 + 3 * k + a, 15 + k) = -pre[PRE_DEP_DRHO + 3 * k + a];
             JU(ILO_RHO1 + k, 15 + k) = -1.0;

@@ -15,6 +15,7 @@ struct PreintParams {   // mirror of CerbPreintConfig (plain doubles so it can b
     double acc_n, acc_n_z, gyr_n, acc_w, gyr_w, phi_n, dphi_n, rho_c_n, rho_nc_n;
     double v_n_min_xy, v_n_min_z, v_n_min, v_n_max, v_n_force_thres_ratio, v_n_term1_steep, v_n_term2_var_rescale, v_n_term3_distance_rescale;
     int contact_sensor_type;
+    int imu_only;             // 1: plain IntegrationBase (integration_base.h): no legs, acc_n on all three axes
     double rho_fix[16], p_br[3], R_br[9];
 };
 
@@ -104,7 +105,12 @@ CERB_GLOBAL void preintegrate_kernel(PreintParams P, int n_jobs, const double *j
         }
         __syncthreads();
         // ---- 1b: per-leg kinematics and velocity (:232-286); one thread per leg ---------------------
-        if (tid < 4) {
+        if (tid < 4 && P.imu_only) {
+            LegStep &L = legs[tid];
+            L.fi = L.fi1 = L.vi = L.vi1 = L.gi = L.gi1 = mk3(0, 0, 0);
+            for (int k = 0; k < 9; k++) { L.Ji.m[k] = 0; L.Ji1.m[k] = 0; L.hi.m[k] = 0; L.hi1.m[k] = 0; }
+        }
+        if (tid < 4 && !P.imu_only) {
             const int j = tid;
             const double lc = nom[29 + j];
             const double *fix = P.rho_fix + 4 * j;
@@ -180,7 +186,7 @@ CERB_GLOBAL void preintegrate_kernel(PreintParams P, int n_jobs, const double *j
             set_block(V, LDV, ILO_BG, NO_BG, scale33(I3, -dt));
             for (int j = 0; j < 4; j++) V[(ILO_RHO1 + j) * LDV + NO_NRHO1 + j] = -dt;
             // noise (:360-374)
-            const double an = P.acc_n * P.acc_n, anz = P.acc_n_z * P.acc_n_z, gn = P.gyr_n * P.gyr_n;
+            const double an = P.acc_n * P.acc_n, anz = P.imu_only ? P.acc_n * P.acc_n : P.acc_n_z * P.acc_n_z, gn = P.gyr_n * P.gyr_n;
             const double aw = P.acc_w * P.acc_w, gw = P.gyr_w * P.gyr_w, pn = P.phi_n * P.phi_n, dn = P.dphi_n * P.dphi_n;
             Nn[0] = an; Nn[1] = an; Nn[2] = anz; Nn[6] = an; Nn[7] = an; Nn[8] = anz;
             for (int k = 0; k < 3; k++) { Nn[3 + k] = gn; Nn[9 + k] = gn; Nn[12 + k] = aw; Nn[15 + k] = gw; }
@@ -208,6 +214,8 @@ CERB_GLOBAL void preintegrate_kernel(PreintParams P, int n_jobs, const double *j
         }
         if (tid >= 32 && tid < 36) {   // per-leg rows of F and V (:405-413, :452-460), one thread per leg, another warp
             const int j = tid - 32, e = ILO_EPS1 + 3 * j;
+            if (P.imu_only) { set_block(F, LD, e, e, ident33()); }
+            else {
             const LegStep &L = legs[j];
             const m33 R0 = ldm33(stp + 10), R1 = ldm33(stp + 19), I3 = ident33(), R_br = ldm33(P.R_br);
             const d3 p_br = ld3(P.p_br), bg = ld3(nom + 26);
@@ -226,6 +234,7 @@ CERB_GLOBAL void preintegrate_kernel(PreintParams P, int n_jobs, const double *j
             set_block(V, LDV, e, NO_DPHIi, scale33(mul33(mul33(R0, R_br), L.Ji), -0.5 * dt));
             set_block(V, LDV, e, NO_DPHIi1, scale33(mul33(mul33(R1, R_br), L.Ji1), -0.5 * dt));
             set_block(V, LDV, e, NO_V1 + 3 * j, scale33(I3, -dt));
+            }
         }
         __syncthreads();
         // ---- 3: jacobian = F jacobian ; covariance = F cov F^T + V N V^T (:467-468) ----------------------

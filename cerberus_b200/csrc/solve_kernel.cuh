@@ -26,7 +26,7 @@ struct SolveParams {
     double G[3], sqrt_info, huber;
     double radius0, max_radius, min_radius, min_rel_dec, ftol, gtol, ptol;
     // batch (device pointers)
-    const int *n_features, *feat_start, *feat_nobs, *feat_off, *flags;      // flags bit0 ex_open, bit1 td_open
+    const int *n_features, *feat_start, *feat_nobs, *feat_off, *flags;      // flags bit0 ex_open, bit1 td_open, bit2 no leg-bias blocks (USE_LEG == 0)
     const double *obs; const int *obs_stereo;                               // obs [B][9][maxObs] planar
     const double *pre;                                                      // [B][10][PRE_STRIDE] compact preintegration results
     const double *sinfo;                                                    // [B][10][961] sqrt_info (imu_leg_prepare_kernel)
@@ -437,10 +437,10 @@ CERB_D void apply_plus(const Smem &s, const double *delta, const double *lam, co
 }
 
 // ambient squared norm of the active parameter blocks of `a` (or of a - b if b != null)
-CERB_D double ambient_sq(const SolveParams &P, const double *a, const double *b, const double *la, const double *lb, int nF, bool ex_open, int tid) {
+CERB_D double ambient_sq(const double *a, const double *b, const double *la, const double *lb, int nF, bool ex_open, bool lb_open, int tid) {
     double t = 0.0;
     for (int k = tid; k < ST_SIZE; k += SOLVE_THREADS) {
-        if (k >= ST_LB && k < ST_EX && !P.optimize_leg_bias) continue;
+        if (k >= ST_LB && k < ST_EX && !lb_open) continue;
         if (k >= ST_EX && k < ST_TD && !ex_open) continue;
         if (k == ST_TD) continue;
         const double v = b ? a[k] - b[k] : a[k];
@@ -468,6 +468,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
     for (int w = blockIdx.x; w < P.n_windows; w += gridDim.x) {
         const int nF = P.n_features[w];
         const bool ex_open = (P.flags[w] & 1) != 0;
+        const bool lb_open = P.optimize_leg_bias && (P.flags[w] & 4) == 0;
         double *lam = P.lam + (size_t)w * F;
         for (int k = tid; k < ST_STRIDE; k += SOLVE_THREADS) s.xs[k] = (k < ST_SIZE) ? P.state[(size_t)w * ST_STRIDE + k] : 0.0;
         if (tid == 0) {
@@ -491,7 +492,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 for (int k = tid; k < 1690; k += SOLVE_THREADS) s.Bo[k] = 0.0;
                 __syncthreads();
                 part[0] += inertial_linearize(P, s, w, s.xs, tid);
-                part[1] = ambient_sq(P, s.xs, nullptr, lam, nullptr, nF, ex_open, tid);
+                part[1] = ambient_sq(s.xs, nullptr, lam, nullptr, nF, ex_open, lb_open, tid);
                 double tot[2];
                 block_sum<2>(part, s.red, tot, tid);
                 if (tid == 0) { sca[S_XCOST] = tot[0]; sca[S_XNORM] = sqrt(tot[1]); if (iteration == 0) sca[S_INIT_COST] = tot[0]; }
@@ -504,7 +505,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                         double d;
                         bool active = true;
                         if (k < NX) { d = s.Hxx[k * NX + k]; if (k >= 66 && !ex_open) active = false; }
-                        else { const int yk = k - NX, f = yk / NYB, c = yk % NYB; d = s.Ad[f * 169 + c * NYB + c]; if (c >= 9 && !P.optimize_leg_bias) active = false; }
+                        else { const int yk = k - NX, f = yk / NYB, c = yk % NYB; d = s.Ad[f * 169 + c * NYB + c]; if (c >= 9 && !lb_open) active = false; }
                         s.sc[k] = active ? 1.0 / (1.0 + sqrt(d)) : 0.0;
                     }
                     for (int f = tid; f < nF; f += SOLVE_THREADS) sl[f] = 1.0 / (1.0 + sqrt(hh[f]));
@@ -884,7 +885,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
             {
                 double part[2];
                 part[0] = vision_cost(P, s, w, s.xc, lamc, tid) + inertial_cost(P, s, w, s.xc, tid) + prior_residual(P, s, w, s.xc, tid);
-                part[1] = ambient_sq(P, s.xs, s.xc, lam, lamc, nF, ex_open, tid);
+                part[1] = ambient_sq(s.xs, s.xc, lam, lamc, nF, ex_open, lb_open, tid);
                 double tot[2];
                 block_sum<2>(part, s.red, tot, tid);
                 if (tid == 0) {

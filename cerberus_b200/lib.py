@@ -51,6 +51,8 @@ class Backend:
         L.cerb_debug_linearize.argtypes = [C.c_void_p, C.c_int32, abi.c_dp, abi.c_dp, abi.c_dp, C.c_int32]
         L.cerb_eval_projection.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [abi.c_dp] * 14
         L.cerb_eval_imu_leg.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.IMULegPreint), abi.c_dp, abi.c_dp, abi.c_dp, abi.c_dp]
+        L.cerb_eval_imu.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.IMUPreint), abi.c_dp, abi.c_dp, abi.c_dp, abi.c_dp]
+        L.cerb_preintegrate_imu_batch.argtypes = [C.c_void_p, C.POINTER(abi.PreintConfig), C.c_int32, C.POINTER(abi.PreintJob), C.POINTER(abi.IMUPreint)]
         L.cerb_eval_prior.argtypes = [C.c_void_p, C.POINTER(abi.Prior), C.POINTER(abi.WindowState), abi.c_dp, abi.c_dp]
         L.cerb_preintegrate_batch.argtypes = [C.c_void_p, C.POINTER(abi.PreintConfig), C.c_int32, C.POINTER(abi.PreintJob), C.POINTER(abi.IMULegPreint)]
         L.cerb_a1_kinematics.argtypes = [C.c_void_p, C.c_int32] + [abi.c_dp] * 8
@@ -130,6 +132,20 @@ class Backend:
         jac = np.zeros((n, 31 * 40)) if want_jac else None
         self._check(self.lib.cerb_eval_imu_leg(self.h, n, preint.ctypes.data_as(C.POINTER(abi.IMULegPreint)), _p(params), _p(res), _p(jac), _p(si)))
         return res, jac, si
+
+    def eval_imu(self, preint, params, want_jac=True):
+        """IMUFactor::Evaluate (USE_LEG == 0): params [n, 32] = pose_i, speedbias_i, pose_j, speedbias_j."""
+        n = params.shape[0]
+        params = _f64(params)
+        res, si = np.zeros((n, 15)), np.zeros((n, 225))
+        jac = np.zeros((n, 15 * 32)) if want_jac else None
+        self._check(self.lib.cerb_eval_imu(self.h, n, preint.ctypes.data_as(C.POINTER(abi.IMUPreint)), _p(params), _p(res), _p(jac), _p(si)))
+        return res, jac, si
+
+    def preintegrate_imu(self, pcfg, jobs, n):
+        out = np.zeros(n, dtype=abi.imu_preint_dtype)
+        self._check(self.lib.cerb_preintegrate_imu_batch(self.h, C.byref(pcfg), n, jobs, out.ctypes.data_as(C.POINTER(abi.IMUPreint))))
+        return out
 
     def eval_prior(self, prior, state, n_cols):
         res, jac = np.zeros(prior.n), np.zeros(prior.n * n_cols)

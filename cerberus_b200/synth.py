@@ -160,8 +160,9 @@ def _trajectory(par, t):
 
 
 def generate_batch(n, n_features, backend, cfg=None, pcfg=None, window0=0, realistic=False, prior_features=None,
-                   with_prior=True, outlier_fraction=0.0, return_truth=False):
-    """Generate windows window0 .. window0+n-1.  Returns an abi.WindowBatch (and SynthTruth if asked)."""
+                   with_prior=True, outlier_fraction=0.0, return_truth=False, use_leg=True):
+    """Generate windows window0 .. window0+n-1.  Returns an abi.WindowBatch (and SynthTruth if asked).
+    use_leg=False produces USE_LEG == 0 windows (IMUFactor instead of IMULegFactor, no leg bias, no prior)."""
     cfg = cfg or abi.default_config()
     pcfg = pcfg or abi.default_preint_config()
     B, F = n, n_features
@@ -279,7 +280,11 @@ def generate_batch(n, n_features, backend, cfg=None, pcfg=None, window0=0, reali
         st["para_Td"][:] = 0.0
         nf = feats["lam"].shape[1]
         batch.para_Feature[:, :nf] = feats["lam"]
-        batch.preint[:] = pre
+        if use_leg:
+            batch.preint[:] = pre
+        else:
+            batch.use_imu_only()
+            batch.imu_preint[:] = pre
         for w in range(B):
             off = 0
             fw, ow = batch.features[w], batch.obs[w]
@@ -323,7 +328,11 @@ def generate_batch(n, n_features, backend, cfg=None, pcfg=None, window0=0, reali
             j.linearized_rho[:] = (LC_NOMINAL,) * 4
             j.n_samples = S
             j.samples = samples[w, i].ctypes.data_as(C.POINTER(abi.IMULegSample))
-    pre_all = backend.preintegrate(pcfg, jobs, B * (NF - 1)).reshape(B, NF - 1)
+    if use_leg:
+        pre_all = backend.preintegrate(pcfg, jobs, B * (NF - 1)).reshape(B, NF - 1)
+    else:
+        pre_all = backend.preintegrate_imu(pcfg, jobs, B * (NF - 1)).reshape(B, NF - 1)
+        with_prior = False
 
     # ---- the window itself: frames 0..10 (index 1..11) ------------------------------------------------------
     batch = abi.WindowBatch(B, max(F, 1))

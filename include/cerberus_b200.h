@@ -121,6 +121,20 @@ typedef struct CerbIMULegPreint {
     double covariance[CERB_IL_RES * CERB_IL_RES]; /* covariance, 31x31 column-major (symmetric) */
 } CerbIMULegPreint;
 
+/* ---- plain IMU preintegration result: IntegrationBase public members (src/factor/integration_base.h:200-213)
+ * consumed by IMUFactor::Evaluate (src/factor/imu_factor.h:28-188); used when USE_LEG == 0 (estimator.cpp:1160-1171).
+ * Error-state order O_P 0, O_R 3, O_V 6, O_BA 9, O_BG 12 (parameters.h:119-126). */
+typedef struct CerbIMUPreint {
+    double sum_dt;
+    double delta_p[3];
+    double delta_q[4];             /* x,y,z,w */
+    double delta_v[3];
+    double linearized_ba[3];
+    double linearized_bg[3];
+    double jacobian[15 * 15];      /* column-major */
+    double covariance[15 * 15];    /* column-major (symmetric) */
+} CerbIMUPreint;
+
 /* ---- one observation of a feature: FeaturePerFrame (src/featureTracker/feature_manager.h:28-59) */
 typedef struct CerbObservation {
     double point[2];        /* point.x, point.y      (z == 1) */
@@ -162,7 +176,9 @@ typedef struct CerbWindowDesc {
     int32_t n_obs;
     const CerbFeature *features;          /* [n_features] */
     const CerbObservation *obs;           /* [n_obs] */
-    const CerbIMULegPreint *preint;       /* [CERB_WINDOW_SIZE]; preint[i] = il_pre_integrations[i+1] (frames i -> i+1) */
+    const CerbIMULegPreint *preint;       /* [CERB_WINDOW_SIZE]; preint[i] = il_pre_integrations[i+1] (frames i -> i+1); USE_LEG == 1 */
+    const CerbIMUPreint *imu_preint;      /* [CERB_WINDOW_SIZE]; pre_integrations[i+1]; used iff preint == NULL (USE_LEG == 0:
+                                             IMUFactor instead of IMULegFactor, no leg-bias blocks, estimator.cpp:1160-1171) */
     CerbPrior prior;
     int32_t extrinsic_open;               /* 1 => para_Ex_Pose free (openExEstimation latch, estimator.cpp:1091-1100) */
     int32_t td_open;                      /* 1 => para_Td free (ESTIMATE_TD && |Vs[0]| >= 0.2, estimator.cpp:1104) */
@@ -292,6 +308,12 @@ int cerb_eval_imu_leg(CerbHandle *h, int32_t n, const CerbIMULegPreint *preint,
                       const double *params, double *residuals, double *jacobians,
                       double *sqrt_info);
 
+/* IMUFactor::Evaluate (imu_factor.h:28-188), <15,7,9,7,9>.
+ *   params [n][32] = pose_i(7) speedbias_i(9) pose_j(7) speedbias_j(9); residuals [n][15];
+ *   jacobians [n][15*32] row-major blocks 15x7,15x9,15x7,15x9; sqrt_info [n][15*15] row-major. */
+int cerb_eval_imu(CerbHandle *h, int32_t n, const CerbIMUPreint *preint, const double *params, double *residuals,
+                  double *jacobians, double *sqrt_info);
+
 /* MarginalizationFactor::Evaluate (marginalization_factor.cpp:347-395) for one prior at one state:
  * residuals [n]; jacobians: for each kept block b, n x global_size(b) row-major, concatenated. */
 int cerb_eval_prior(CerbHandle *h, const CerbPrior *prior, const CerbWindowState *state,
@@ -301,6 +323,11 @@ int cerb_eval_prior(CerbHandle *h, const CerbPrior *prior, const CerbWindowState
  * imu_leg_integration_base.cpp:49-59,88-470): n independent intervals. */
 int cerb_preintegrate_batch(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n,
                             const CerbPreintJob *jobs, CerbIMULegPreint *out);
+
+/* Plain IMU preintegration on device (IntegrationBase::push_back loop, integration_base.h:40-170): the jobs use the
+ * acc/gyr fields of the samples only; noise = acc_n on all three axes (integration_base.h:31-37). */
+int cerb_preintegrate_imu_batch(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n, const CerbPreintJob *jobs,
+                                CerbIMUPreint *out);
 
 /* A1 leg kinematics (src/legKinematics/A1Kinematics.cpp:7-40), n legs:
  *   q [n][3], rho_opt [n] (lc), rho_fix [n][4];

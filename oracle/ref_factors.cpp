@@ -319,6 +319,74 @@ bool IMULegFactor::Evaluate(double const *const *p, double *residuals, double **
     return true;
 }
 
+// ---- IntegrationBase::evaluate (integration_base.h:172-198) and IMUFactor::Evaluate (imu_factor.h:28-188) -------
+enum { O_P = 0, O_R = 3, O_V = 6, O_BA = 9, O_BG = 12 };
+void imu_residual(const ImuPreintState &s, const FactorGlobals &g, V3 Pi, Quat Qi, V3 Vi, V3 Bai, V3 Bgi, V3 Pj, Quat Qj, V3 Vj, V3 Baj, V3 Bgj, double *res) {
+    M3 dp_dba = s.jacobian.block3(O_P, O_BA), dp_dbg = s.jacobian.block3(O_P, O_BG), dq_dbg = s.jacobian.block3(O_R, O_BG);
+    M3 dv_dba = s.jacobian.block3(O_V, O_BA), dv_dbg = s.jacobian.block3(O_V, O_BG);
+    V3 dba = Bai - s.linearized_ba, dbg = Bgi - s.linearized_bg;
+    Quat corrected_delta_q = s.delta_q * deltaQ(dq_dbg * dbg);
+    V3 corrected_delta_v = s.delta_v + dv_dba * dba + dv_dbg * dbg;
+    V3 corrected_delta_p = s.delta_p + dp_dba * dba + dp_dbg * dbg;
+    const double sum_dt = s.sum_dt;
+    V3 rp = inverse(Qi) * (0.5 * g.G * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt) - corrected_delta_p;
+    V3 rq = 2.0 * (inverse(corrected_delta_q) * (inverse(Qi) * Qj)).vec();
+    V3 rv = inverse(Qi) * (g.G * sum_dt + Vj - Vi) - corrected_delta_v;
+    V3 rba = Baj - Bai, rbg = Bgj - Bgi;
+    for (int k = 0; k < 3; k++) { res[O_P + k] = rp[k]; res[O_R + k] = rq[k]; res[O_V + k] = rv[k]; res[O_BA + k] = rba[k]; res[O_BG + k] = rbg[k]; }
+}
+
+bool IMUFactor::Evaluate(double const *const *p, double *residuals, double **jacobians) const {
+    const ImuPreintState &s = *pre;
+    V3 Pi(p[0]); Quat Qi(p[0][6], p[0][3], p[0][4], p[0][5]);
+    V3 Vi(p[1]), Bai(p[1] + 3), Bgi(p[1] + 6);
+    V3 Pj(p[2]); Quat Qj(p[2][6], p[2][3], p[2][4], p[2][5]);
+    V3 Vj(p[3]), Baj(p[3] + 3), Bgj(p[3] + 6);
+    double raw[15];
+    imu_residual(s, g, Pi, Qi, Vi, Bai, Bgi, Pj, Qj, Vj, Baj, Bgj, raw);
+    Mat sqrt_info;
+    if (!imu_leg_sqrt_info(s.covariance, sqrt_info)) return false;          // imu_factor.h:73, every call
+    for (int i = 0; i < 15; i++) { double t = 0; for (int k = i; k < 15; k++) t += sqrt_info(i, k) * raw[k]; residuals[i] = t; }
+    if (jacobians) {
+        const double sum_dt = s.sum_dt;
+        M3 dp_dba = s.jacobian.block3(O_P, O_BA), dp_dbg = s.jacobian.block3(O_P, O_BG), dq_dbg = s.jacobian.block3(O_R, O_BG);
+        M3 dv_dba = s.jacobian.block3(O_V, O_BA), dv_dbg = s.jacobian.block3(O_V, O_BG);
+        M3 RiT = toR(inverse(Qi));
+        auto whiten_and_store = [&](const Mat &Jm, double *out) {
+            for (int i = 0; i < 15; i++) for (int cc = 0; cc < Jm.c; cc++) { double t = 0; for (int k = i; k < 15; k++) t += sqrt_info(i, k) * Jm(k, cc); out[i * Jm.c + cc] = t; }
+        };
+        Quat corrected_delta_q = s.delta_q * deltaQ(dq_dbg * (Bgi - s.linearized_bg));
+        if (jacobians[0]) {   // imu_factor.h:95-123
+            Mat J(15, 7);
+            J.setBlock(O_P, O_P, -RiT);
+            J.setBlock(O_P, O_R, skew(inverse(Qi) * (0.5 * g.G * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt)));
+            J.setBlock(O_R, O_R, -QleftQrightBR(inverse(Qj) * Qi, corrected_delta_q));
+            J.setBlock(O_V, O_R, skew(inverse(Qi) * (g.G * sum_dt + Vj - Vi)));
+            whiten_and_store(J, jacobians[0]);
+        }
+        if (jacobians[1]) {   // :124-152
+            Mat J(15, 9);
+            J.setBlock(O_P, 0, -1.0 * RiT * sum_dt); J.setBlock(O_P, 3, -dp_dba); J.setBlock(O_P, 6, -dp_dbg);
+            J.setBlock(O_R, 6, -(QleftBR(inverse(Qj) * Qi * s.delta_q) * dq_dbg));
+            J.setBlock(O_V, 0, -RiT); J.setBlock(O_V, 3, -dv_dba); J.setBlock(O_V, 6, -dv_dbg);
+            J.setBlock(O_BA, 3, -M3::identity()); J.setBlock(O_BG, 6, -M3::identity());
+            whiten_and_store(J, jacobians[1]);
+        }
+        if (jacobians[2]) {   // :153-171
+            Mat J(15, 7);
+            J.setBlock(O_P, O_P, RiT);
+            J.setBlock(O_R, O_R, QleftBR(inverse(corrected_delta_q) * inverse(Qi) * Qj));
+            whiten_and_store(J, jacobians[2]);
+        }
+        if (jacobians[3]) {   // :172-184
+            Mat J(15, 9);
+            J.setBlock(O_V, 0, RiT); J.setBlock(O_BA, 3, M3::identity()); J.setBlock(O_BG, 6, M3::identity());
+            whiten_and_store(J, jacobians[3]);
+        }
+    }
+    return true;
+}
+
 // ---- MarginalizationFactor::Evaluate, marginalization_factor.cpp:347-395 -----------------------
 bool MarginalizationFactor::Evaluate(double const *const *p, double *residuals, double **jacobians) const {
     int n = info->n, m = info->m;

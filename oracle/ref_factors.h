@@ -71,6 +71,23 @@ struct IMULegFactor : CostFunction {
     bool Evaluate(double const *const *p, double *r, double **J) const override;
 };
 
+// Public state of IntegrationBase that IMUFactor reads (integration_base.h:200-213); 15-dim error state
+// O_P 0, O_R 3, O_V 6, O_BA 9, O_BG 12 (parameters.h:119-126).
+struct ImuPreintState {
+    Mat jacobian{15, 15}, covariance{15, 15};
+    double sum_dt = 0;
+    V3 delta_p; Quat delta_q; V3 delta_v;
+    V3 linearized_ba, linearized_bg;
+};
+// IntegrationBase::evaluate, integration_base.h:172-198
+void imu_residual(const ImuPreintState &s, const FactorGlobals &g, V3 Pi, Quat Qi, V3 Vi, V3 Bai, V3 Bgi, V3 Pj, Quat Qj, V3 Vj, V3 Baj, V3 Bgj, double *residuals15);
+// imu_factor.h:28-188   SizedCostFunction<15,7,9,7,9>
+struct IMUFactor : CostFunction {
+    const ImuPreintState *pre; FactorGlobals g;
+    IMUFactor(const ImuPreintState *p, const FactorGlobals &g_) : pre(p), g(g_) { num_residuals = 15; block_sizes = {7, 9, 7, 9}; }
+    bool Evaluate(double const *const *p, double *r, double **J) const override;
+};
+
 // State of MarginalizationInfo read by MarginalizationFactor (marginalization_factor.h:76-84)
 struct MargInfoLite {
     int n = 0, m = 0;

@@ -14,6 +14,8 @@
 #include "factor/projectionOneFrameTwoCamFactor.h"
 #include "factor/imu_leg_factor.h"
 #include "factor/imu_leg_integration_base.h"
+#include "factor/integration_base.h"
+#include "factor/imu_factor.h"
 #include "factor/marginalization_factor.h"
 #include "factor/pose_local_parameterization.h"
 #include "legKinematics/A1Kinematics.h"
@@ -317,6 +319,43 @@ int ref_marginalize(const CerbWindowDesc *desc, const CerbWindowState *state_in,
     for (int i = 0; i < mi->n; i++) r_out[i] = mi->linearized_residuals(i);
     out->linearized_jacobians = J_out; out->linearized_residuals = r_out;
     // (objects are leaked on purpose: MarginalizationInfo's destructor owns the factors and `last`'s data; test helper only)
+    return 0;
+}
+
+// IMUFactor::Evaluate / IntegrationBase (imu_factor.h, integration_base.h) -- the USE_LEG == 0 path
+int ref_eval_imu(int n, const CerbIMUPreint *preint, const double *params, double *residuals, double *jacobians, double *sqrt_info) {
+    for (int k = 0; k < n; k++) {
+        const CerbIMUPreint &q = preint[k];
+        IntegrationBase pre(v3(kZero3), v3(kZero3), v3(q.linearized_ba), v3(q.linearized_bg));
+        pre.sum_dt = q.sum_dt; pre.delta_p = v3(q.delta_p); pre.delta_v = v3(q.delta_v);
+        pre.delta_q = Eigen::Quaterniond(q.delta_q[3], q.delta_q[0], q.delta_q[1], q.delta_q[2]);
+        std::memcpy(pre.jacobian.data(), q.jacobian, sizeof(q.jacobian)); std::memcpy(pre.covariance.data(), q.covariance, sizeof(q.covariance));
+        IMUFactor f(&pre);
+        const double *x = params + (size_t)k * 32;
+        const double *p[4] = {x, x + 7, x + 16, x + 23};
+        double r[15]; double *J[4];
+        double *b = jacobians ? jacobians + (size_t)k * 15 * 32 : nullptr;
+        if (b) { J[0] = b; J[1] = b + 15 * 7; J[2] = b + 15 * 16; J[3] = b + 15 * 23; }
+        f.Evaluate(p, r, b ? J : nullptr);
+        if (residuals) for (int i = 0; i < 15; i++) residuals[(size_t)k * 15 + i] = r[i];
+        if (sqrt_info) {
+            Eigen::Matrix<double, 15, 15> si = Eigen::LLT<Eigen::Matrix<double, 15, 15>>(pre.covariance.inverse()).matrixL().transpose();
+            for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) sqrt_info[(size_t)k * 225 + i * 15 + j] = si(i, j);
+        }
+    }
+    return 0;
+}
+int ref_preintegrate_imu(int n, const CerbPreintJob *jobs, CerbIMUPreint *out) {
+    for (int k = 0; k < n; k++) {
+        const CerbPreintJob &j = jobs[k];
+        IntegrationBase pre(v3(j.acc_0), v3(j.gyr_0), v3(j.linearized_ba), v3(j.linearized_bg));
+        for (int s = 0; s < j.n_samples; s++) pre.push_back(j.samples[s].dt, v3(j.samples[s].acc), v3(j.samples[s].gyr));
+        CerbIMUPreint &q = out[k];
+        q.sum_dt = pre.sum_dt;
+        for (int t = 0; t < 3; t++) { q.delta_p[t] = pre.delta_p(t); q.delta_v[t] = pre.delta_v(t); q.linearized_ba[t] = pre.linearized_ba(t); q.linearized_bg[t] = pre.linearized_bg(t); }
+        q.delta_q[0] = pre.delta_q.x(); q.delta_q[1] = pre.delta_q.y(); q.delta_q[2] = pre.delta_q.z(); q.delta_q[3] = pre.delta_q.w();
+        std::memcpy(q.jacobian, pre.jacobian.data(), sizeof(q.jacobian)); std::memcpy(q.covariance, pre.covariance.data(), sizeof(q.covariance));
+    }
     return 0;
 }
 

@@ -284,4 +284,53 @@ void LegPreintegrator::propagate(double _dt, V3 _acc_1, V3 _gyr_1, const double 
     for (int i = 0; i < 4; i++) c_0_[i] = _c_1[i];
 }
 
+// ---- IntegrationBase::{push_back, propagate, midPointIntegration}, integration_base.h:40-170 --------------------
+ImuPreintegrator::ImuPreintegrator(const PreintGlobals &gl, V3 acc_0, V3 gyr_0, V3 lin_ba, V3 lin_bg) : gl_(gl), acc_0_(acc_0), gyr_0_(gyr_0) {
+    linearized_ba = lin_ba; linearized_bg = lin_bg; sum_dt = 0; delta_q = Quat();
+    jacobian = Mat::identity(15); covariance = Mat(15, 15);
+}
+void ImuPreintegrator::push_back(double _dt, V3 _acc_1, V3 _gyr_1) {
+    const V3 _acc_0 = acc_0_, _gyr_0 = gyr_0_;
+    V3 un_acc_0 = delta_q * (_acc_0 - linearized_ba);
+    V3 un_gyr = 0.5 * (_gyr_0 + _gyr_1) - linearized_bg;
+    Quat result_delta_q = delta_q * Quat(1, un_gyr.x * _dt / 2, un_gyr.y * _dt / 2, un_gyr.z * _dt / 2);
+    V3 un_acc_1 = result_delta_q * (_acc_1 - linearized_ba);
+    V3 un_acc = 0.5 * (un_acc_0 + un_acc_1);
+    V3 result_delta_p = delta_p + delta_v * _dt + 0.5 * un_acc * _dt * _dt;
+    V3 result_delta_v = delta_v + un_acc * _dt;
+    M3 R_w_x = skew(un_gyr), R_a_0_x = skew(_acc_0 - linearized_ba), R_a_1_x = skew(_acc_1 - linearized_ba);
+    M3 R0 = toR(delta_q), R1 = toR(result_delta_q), I3 = M3::identity();
+    Mat F(15, 15), V(15, 18);
+    F.setBlock(0, 0, I3);
+    F.setBlock(0, 3, -0.25 * R0 * R_a_0_x * _dt * _dt + -0.25 * R1 * R_a_1_x * (I3 - R_w_x * _dt) * _dt * _dt);
+    F.setBlock(0, 6, I3 * _dt);
+    F.setBlock(0, 9, -0.25 * (R0 + R1) * _dt * _dt);
+    F.setBlock(0, 12, -0.25 * R1 * R_a_1_x * _dt * _dt * -_dt);
+    F.setBlock(3, 3, I3 - R_w_x * _dt);
+    F.setBlock(3, 12, -1.0 * I3 * _dt);
+    F.setBlock(6, 3, -0.5 * R0 * R_a_0_x * _dt + -0.5 * R1 * R_a_1_x * (I3 - R_w_x * _dt) * _dt);
+    F.setBlock(6, 6, I3);
+    F.setBlock(6, 9, -0.5 * (R0 + R1) * _dt);
+    F.setBlock(6, 12, -0.5 * R1 * R_a_1_x * _dt * -_dt);
+    F.setBlock(9, 9, I3); F.setBlock(12, 12, I3);
+    V.setBlock(0, 0, 0.25 * R0 * _dt * _dt);
+    M3 v03 = 0.25 * (-R1) * R_a_1_x * _dt * _dt * 0.5 * _dt;
+    V.setBlock(0, 3, v03); V.setBlock(0, 6, 0.25 * R1 * _dt * _dt); V.setBlock(0, 9, v03);
+    V.setBlock(3, 3, 0.5 * I3 * _dt); V.setBlock(3, 9, 0.5 * I3 * _dt);
+    V.setBlock(6, 0, 0.5 * R0 * _dt);
+    M3 v63 = 0.5 * (-R1) * R_a_1_x * _dt * 0.5 * _dt;
+    V.setBlock(6, 3, v63); V.setBlock(6, 6, 0.5 * R1 * _dt); V.setBlock(6, 9, v63);
+    V.setBlock(9, 12, I3 * _dt); V.setBlock(12, 15, I3 * _dt);
+    double N[18];
+    for (int k = 0; k < 3; k++) { N[k] = N[6 + k] = gl_.ACC_N * gl_.ACC_N; N[3 + k] = N[9 + k] = gl_.GYR_N * gl_.GYR_N; N[12 + k] = gl_.ACC_W * gl_.ACC_W; N[15 + k] = gl_.GYR_W * gl_.GYR_W; }
+    jacobian = matmul(F, jacobian);
+    Mat cov = matmul(matmul(F, covariance), transpose(F));
+    Mat VN = V; for (int i = 0; i < 15; i++) for (int k = 0; k < 18; k++) VN(i, k) *= N[k];
+    Mat vnv = matmul(VN, transpose(V));
+    for (int i = 0; i < 15; i++) for (int k = 0; k < 15; k++) cov(i, k) += vnv(i, k);
+    covariance = cov;
+    delta_p = result_delta_p; delta_q = normalized(result_delta_q); delta_v = result_delta_v;
+    sum_dt += _dt; acc_0_ = _acc_1; gyr_0_ = _gyr_1;
+}
+
 }  // namespace oracle

@@ -49,4 +49,13 @@ private:
     std::vector<Sample> buf_;
 };
 
+// IntegrationBase (integration_base.h:22-170): plain IMU midpoint preintegration, 15 x 15 F, 15 x 18 V
+class ImuPreintegrator : public ImuPreintState {
+public:
+    ImuPreintegrator(const PreintGlobals &gl, V3 acc_0, V3 gyr_0, V3 lin_ba, V3 lin_bg);
+    void push_back(double dt, V3 acc, V3 gyr);
+private:
+    PreintGlobals gl_; V3 acc_0_, gyr_0_;
+};
+
 }  // namespace oracle

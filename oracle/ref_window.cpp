@@ -32,6 +32,21 @@ void from_state(const LegPreintState &s, CerbIMULegPreint &p) {
     for (int r = 0; r < 31; r++) for (int c = 0; c < 31; c++) { p.jacobian[c * 31 + r] = s.jacobian(r, c); p.covariance[c * 31 + r] = s.covariance(r, c); }
 }
 
+ImuPreintState to_imu_state(const CerbIMUPreint &p) {
+    ImuPreintState s;
+    s.sum_dt = p.sum_dt; s.delta_p = V3(p.delta_p); s.delta_v = V3(p.delta_v);
+    s.delta_q = Quat(p.delta_q[3], p.delta_q[0], p.delta_q[1], p.delta_q[2]);
+    s.linearized_ba = V3(p.linearized_ba); s.linearized_bg = V3(p.linearized_bg);
+    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) { s.jacobian(r, c) = p.jacobian[c * 15 + r]; s.covariance(r, c) = p.covariance[c * 15 + r]; }
+    return s;
+}
+void from_imu_state(const ImuPreintState &s, CerbIMUPreint &p) {
+    p.sum_dt = s.sum_dt;
+    for (int k = 0; k < 3; k++) { p.delta_p[k] = s.delta_p[k]; p.delta_v[k] = s.delta_v[k]; p.linearized_ba[k] = s.linearized_ba[k]; p.linearized_bg[k] = s.linearized_bg[k]; }
+    p.delta_q[0] = s.delta_q.x; p.delta_q[1] = s.delta_q.y; p.delta_q[2] = s.delta_q.z; p.delta_q[3] = s.delta_q.w;
+    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) { p.jacobian[c * 15 + r] = s.jacobian(r, c); p.covariance[c * 15 + r] = s.covariance(r, c); }
+}
+
 double *block_ptr(CerbWindowState &st, int kind, int index) {
     switch (kind) {
         case CERB_BLOCK_POSE: return st.para_Pose[index];
@@ -65,6 +80,7 @@ ProjConst make_proj_const(const CerbObservation &o0, const double *ptj, const do
 struct WindowProblem {
     Problem problem;
     std::vector<LegPreintState> pre;
+    std::vector<ImuPreintState> imu_pre;
     MargInfoLite prior_info;
     FactorGlobals fg;
 };
@@ -73,9 +89,11 @@ struct WindowProblem {
 void build_problem(const CerbSolverConfig &cfg, const CerbWindowDesc &d, CerbWindowState &st, WindowProblem &wp) {
     Problem &problem = wp.problem;
     wp.fg.G = V3(cfg.g); wp.fg.visual_sqrt_info = cfg.visual_sqrt_info;
+    const bool use_leg = d.preint != nullptr;
     for (int i = 0; i < CERB_NUM_FRAMES; i++) {                       // :1065-1083
         problem.AddParameterBlock(st.para_Pose[i], 7, true, 1);
         problem.AddParameterBlock(st.para_SpeedBias[i], 9, false, 1);
+        if (!use_leg) continue;                                        // USE_LEG == 0: no leg-bias blocks at all (:1071)
         problem.AddParameterBlock(st.para_LegBias[i], 4, false, 1);
         if (!cfg.optimize_leg_bias) problem.SetParameterBlockConstant(st.para_LegBias[i]);
     }
@@ -93,8 +111,14 @@ void build_problem(const CerbSolverConfig &cfg, const CerbWindowDesc &d, CerbWin
         for (int b = 0; b < d.prior.num_blocks; b++) blocks.push_back(block_ptr(st, d.prior.block_kind[b], d.prior.block_index[b]));
         problem.AddResidualBlock(std::make_shared<MarginalizationFactor>(&wp.prior_info), false, blocks);
     }
-    wp.pre.reserve(CERB_WINDOW_SIZE);
-    for (int i = 0; i < CERB_WINDOW_SIZE; i++) {                       // :1114-1159
+    wp.pre.reserve(CERB_WINDOW_SIZE); wp.imu_pre.reserve(CERB_WINDOW_SIZE);
+    for (int i = 0; i < CERB_WINDOW_SIZE && !use_leg; i++) {           // :1160-1171  (USE_IMU only)
+        wp.imu_pre.push_back(to_imu_state(d.imu_preint[i]));
+        if (wp.imu_pre.back().sum_dt > 10.0) continue;
+        int j = i + 1;
+        problem.AddResidualBlock(std::make_shared<IMUFactor>(&wp.imu_pre[i], wp.fg), false, {st.para_Pose[i], st.para_SpeedBias[i], st.para_Pose[j], st.para_SpeedBias[j]});
+    }
+    for (int i = 0; i < CERB_WINDOW_SIZE && use_leg; i++) {            // :1114-1159
         wp.pre.push_back(to_state(d.preint[i]));
         if (wp.pre.back().sum_dt > 10.0) continue;
         int j = i + 1;
@@ -258,6 +282,7 @@ int oracle_solve_window(const CerbSolverConfig *cfg, const CerbWindowDesc *desc,
         if (n_alloc < total) return CERB_ERR_BAD_ARGUMENT;
         for (int k = 0; k < total; k++) { if (gradient0) gradient0[k] = 0; if (jtj_diag0) jtj_diag0[k] = 0; }
         auto put = [&](double *ptr, int off) {
+            if (!wp.problem.index.count(ptr)) return;
             const Problem::PB &b = wp.problem.pbs[wp.problem.index.at(ptr)];
             if (b.constant || s.gradient0.empty()) return;
             for (int k = 0; k < b.local; k++) { if (gradient0) gradient0[off + k] = s.gradient0[b.col + k]; if (jtj_diag0) jtj_diag0[off + k] = s.jtj_diag0[b.col + k]; }
@@ -331,6 +356,23 @@ int oracle_eval_imu_leg(int n, const double g[3], const CerbIMULegPreint *preint
     return CERB_OK;
 }
 
+int oracle_eval_imu(int n, const double g[3], const CerbIMUPreint *preint, const double *params, double *residuals, double *jacobians, double *sqrt_info) {
+    FactorGlobals fg; fg.G = V3(g);
+    for (int k = 0; k < n; k++) {
+        ImuPreintState s = to_imu_state(preint[k]);
+        IMUFactor f(&s, fg);
+        const double *q = params + (size_t)k * 32;
+        const double *p[4] = {q, q + 7, q + 16, q + 23};
+        double r[15]; double *J[4];
+        double *base = jacobians ? jacobians + (size_t)k * 15 * 32 : nullptr;
+        if (base) { J[0] = base; J[1] = base + 15 * 7; J[2] = base + 15 * 16; J[3] = base + 15 * 23; }
+        if (!f.Evaluate(p, r, base ? J : nullptr)) return CERB_ERR_NON_FINITE;
+        if (residuals) for (int i = 0; i < 15; i++) residuals[(size_t)k * 15 + i] = r[i];
+        if (sqrt_info) { Mat si; imu_leg_sqrt_info(s.covariance, si); for (int i = 0; i < 225; i++) sqrt_info[(size_t)k * 225 + i] = si.d[i]; }
+    }
+    return CERB_OK;
+}
+
 int oracle_eval_prior(const CerbPrior *prior, const CerbWindowState *state, double *residuals, double *jacobians) {
     MargInfoLite info; prior_to_info(*prior, info);
     MarginalizationFactor f(&info);
@@ -369,6 +411,17 @@ int oracle_preintegrate(const CerbPreintConfig *cfg, int n, const CerbPreintJob 
         LegPreintegrator pi(g, V3(j.acc_0), V3(j.gyr_0), j.phi_0, j.dphi_0, j.c_0, V3(j.linearized_ba), V3(j.linearized_bg), j.linearized_rho);
         for (int s = 0; s < j.n_samples; s++) { const CerbIMULegSample &m = j.samples[s]; pi.push_back(m.dt, V3(m.acc), V3(m.gyr), m.phi, m.dphi, m.c); }
         from_state(pi, out[k]);
+    }
+    return CERB_OK;
+}
+
+int oracle_preintegrate_imu(const CerbPreintConfig *cfg, int n, const CerbPreintJob *jobs, CerbIMUPreint *out) {
+    PreintGlobals g = to_globals(*cfg);
+    for (int k = 0; k < n; k++) {
+        const CerbPreintJob &j = jobs[k];
+        ImuPreintegrator pi(g, V3(j.acc_0), V3(j.gyr_0), V3(j.linearized_ba), V3(j.linearized_bg));
+        for (int s = 0; s < j.n_samples; s++) pi.push_back(j.samples[s].dt, V3(j.samples[s].acc), V3(j.samples[s].gyr));
+        from_imu_state(pi, out[k]);
     }
     return CERB_OK;
 }
@@ -502,7 +555,7 @@ void oracle_double2vector(const CerbWindowState *before, const CerbWindowState *
 
 int oracle_abi_sizes(int *out, int n) {   // struct-size handshake for the ctypes mirror
     int v[] = {(int)sizeof(CerbSolverConfig), (int)sizeof(CerbIMULegPreint), (int)sizeof(CerbObservation), (int)sizeof(CerbFeature), (int)sizeof(CerbPrior),
-               (int)sizeof(CerbWindowDesc), (int)sizeof(CerbWindowState), (int)sizeof(CerbSolveReport), (int)sizeof(CerbIMULegSample), (int)sizeof(CerbPreintConfig), (int)sizeof(CerbPreintJob)};
+               (int)sizeof(CerbWindowDesc), (int)sizeof(CerbWindowState), (int)sizeof(CerbSolveReport), (int)sizeof(CerbIMULegSample), (int)sizeof(CerbPreintConfig), (int)sizeof(CerbPreintJob), (int)sizeof(CerbIMUPreint)};
     int k = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < k && i < n; i++) out[i] = v[i];
     return k;

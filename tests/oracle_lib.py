@@ -92,6 +92,21 @@ class OracleBackend:
         assert rc == 0
         return res, jac, si
 
+    def eval_imu(self, preint, params, g=(0.0, 0.0, 9.805), want_jac=True):
+        n = params.shape[0]
+        res, si = np.zeros((n, 15)), np.zeros((n, 225))
+        jac = np.zeros((n, 15 * 32)) if want_jac else None
+        garr = np.array(g, dtype=np.float64)
+        rc = self.lib.oracle_eval_imu(n, _p(garr), preint.ctypes.data_as(C.POINTER(abi.IMUPreint)), _p(np.ascontiguousarray(params)), _p(res), _p(jac), _p(si))
+        assert rc == 0
+        return res, jac, si
+
+    def preintegrate_imu(self, pcfg, jobs, n):
+        out = np.zeros(n, dtype=abi.imu_preint_dtype)
+        rc = self.lib.oracle_preintegrate_imu(C.byref(pcfg), n, jobs, out.ctypes.data_as(C.POINTER(abi.IMUPreint)))
+        assert rc == 0
+        return out
+
     def eval_prior(self, prior, state, n_cols):
         res = np.zeros(prior.n)
         jac = np.zeros(prior.n * n_cols)
@@ -191,3 +206,22 @@ def _ref_marginalize(self, cfg, src, dst, margin_old=True):
 
 
 RefBackend.marginalize = _ref_marginalize
+
+
+def _ref_eval_imu(self, preint, params, want_jac=True):
+    n = params.shape[0]
+    res, si = np.zeros((n, 15)), np.zeros((n, 225))
+    jac = np.zeros((n, 15 * 32)) if want_jac else None
+    self.lib.ref_eval_imu(n, preint.ctypes.data_as(C.POINTER(abi.IMUPreint)), _p(np.ascontiguousarray(params)), _p(res), _p(jac), _p(si))
+    return res, jac, si
+
+
+def _ref_preintegrate_imu(self, pcfg, jobs, n):
+    self.set_globals(pcfg)
+    out = np.zeros(n, dtype=abi.imu_preint_dtype)
+    self.lib.ref_preintegrate_imu(n, jobs, out.ctypes.data_as(C.POINTER(abi.IMUPreint)))
+    return out
+
+
+RefBackend.eval_imu = _ref_eval_imu
+RefBackend.preintegrate_imu = _ref_preintegrate_imu

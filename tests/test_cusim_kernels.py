@@ -101,3 +101,19 @@ def test_marginalization_glue_matches_oracle(sb):
             assert A0.shape == A1.shape
             assert np.abs(A0 - A1).max() < 1e-5 * np.abs(A0).max() and np.abs(b0 - b1).max() < 1e-4 * np.abs(b0).max()
             assert all(np.abs(x0[k] - x1[k]).max() == 0 for k in x0)
+
+
+def test_imu_only_window_solve():
+    """USE_LEG == 0 (estimator.cpp:1160-1171): IMUFactor windows, no leg-bias blocks, no prior."""
+    cfg = small_cfg(iters=3)
+    o, s = OracleBackend(cfg), sim_backend(cfg)
+    batch = synth.generate_batch(1, 10, o, use_leg=False, window0=55)
+    st = batch.state_array(); saved = batch.copy_states(); lb0 = st["para_LegBias"].copy()
+    rep_o = o.solve_batch(batch); ref = st.copy()
+    batch.restore_states(saved)
+    rep_s = s.solve_batch(batch)
+    st = batch.state_array()
+    assert (rep_o["iterations"] == rep_s["iterations"]).all() and (st["para_LegBias"] == lb0).all()
+    assert abs(rep_o["final_cost"][0] - rep_s["final_cost"][0]) < 1e-7 * rep_o["final_cost"][0]
+    d = state_diffs(st, ref)
+    assert d["para_Pose"] < 1e-7 and d["para_SpeedBias"] < 1e-6, d

@@ -137,3 +137,13 @@ def test_full_size_properties(gpu):
     assert (a2 == b2).all() and (lam_a == big.para_Feature).all() and (rep_a["final_cost"] == rep_b["final_cost"]).all()
     ms, launches = gpu.last_solve_stats()
     assert launches == 3 and ms > 0
+
+
+def test_imu_only_windows(gpu, oracle):
+    """USE_LEG == 0: IMUFactor (imu_factor.h) windows through the same kernels (EPS / RHO rows dropped, no leg bias)."""
+    batch = synth.generate_batch(8, 80, gpu, use_leg=False, window0=300)
+    st = batch.state_array(); lb0 = st["para_LegBias"].copy()
+    rep_o, rep_g, ref, lam, st = solve_both(gpu, oracle, batch)
+    assert (rep_o["iterations"] == rep_g["iterations"]).all() and (st["para_LegBias"] == lb0).all()
+    d = state_diffs(st, ref)
+    assert d["para_Pose"] < POS_TOL and d["para_SpeedBias"] < 1e-5, d

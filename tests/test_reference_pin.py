@@ -116,3 +116,42 @@ def test_marginalization_vs_reference(ref, realistic):
             assert A0.shape == A1.shape and set(x0) == set(x1)
             assert np.abs(A0 - A1).max() < 1e-5 * np.abs(A0).max() and np.abs(b0 - b1).max() < 1e-4 * np.abs(b0).max()
             assert all(np.abs(x0[k][:7] - x1[k][:7]).max() == 0 for k in x0)
+
+
+def imu_setup(n=4, backend=None):
+    """IMU-only (USE_LEG == 0) factors of a synthetic window: IntegrationBase results + the 32 parameters."""
+    backend = backend or ob
+    batch = synth.generate_batch(1, 4, backend, use_leg=False)
+    st = batch.state_array()
+    pre = batch.imu_preint[0][:n].copy()
+    params = np.zeros((n, 32))
+    for k in range(n):
+        params[k, 0:7] = st["para_Pose"][0, k]; params[k, 7:16] = st["para_SpeedBias"][0, k]
+        params[k, 16:23] = st["para_Pose"][0, k + 1]; params[k, 23:32] = st["para_SpeedBias"][0, k + 1]
+    params[:, 10:16] += np.random.default_rng(4).normal(0, 1e-3, (n, 6))
+    return pre, params
+
+
+def test_imu_factor_and_preintegration_vs_reference(ref):
+    """IMUFactor::Evaluate (imu_factor.h:28-188) and IntegrationBase (integration_base.h:40-198)."""
+    jobs, _, _ = make_jobs(5, seed=29)
+    pcfg = abi.default_preint_config()
+    a = ref.preintegrate_imu(pcfg, jobs, 5); b = ob.preintegrate_imu(pcfg, jobs, 5)
+    for name in a.dtype.names:
+        assert np.abs(a[name] - b[name]).max() <= 1e-12 * max(1e-30, np.abs(a[name]).max()), name
+    pre, params = imu_setup(4)
+    r0, j0, s0 = ref.eval_imu(pre, params); r1, j1, s1 = ob.eval_imu(pre, params)
+    assert np.abs(s0 - s1).max() < 1e-9 * np.abs(s0).max() and np.abs(r0 - r1).max() < 1e-9 * np.abs(r0).max() and np.abs(j0 - j1).max() < 1e-9 * np.abs(j0).max()
+
+
+def test_imu_only_kernels_vs_reference_in_simulator(ref):
+    from helpers import sim_backend, small_cfg
+    sb = sim_backend(small_cfg())
+    jobs, _, _ = make_jobs(3, seed=29)
+    pcfg = abi.default_preint_config()
+    a = ref.preintegrate_imu(pcfg, jobs, 3); b = sb.preintegrate_imu(pcfg, jobs, 3)
+    for name in a.dtype.names:
+        assert np.abs(a[name] - b[name]).max() <= 1e-11 * max(1e-30, np.abs(a[name]).max()), name
+    pre, params = imu_setup(3)
+    r0, j0, s0 = ref.eval_imu(pre, params); r1, j1, s1 = sb.eval_imu(pre, params)
+    assert np.abs(s0 - s1).max() < 1e-9 * np.abs(s0).max() and np.abs(r0 - r1).max() < 1e-9 * np.abs(r0).max() and np.abs(j0 - j1).max() < 1e-9 * np.abs(j0).max()
