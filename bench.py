@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 WINDOWS_PER_GPU = 1024
 FEATURES = 150
 PRIOR_FEATURES = 24
-CPU_SAMPLE = 96
+CPU_SAMPLE = 256
 
 
 def b_alg(F):
@@ -76,6 +76,19 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def usable_cpus():
+    """CPUs this process may actually burn: the affinity mask clipped by the cgroup CPU quota (the GPU boxes expose
+    128 hardware threads but cap the container at 16 CPUs; oversubscribing past ~2x the quota only adds throttling)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, 2 * int(-(-int(quota) // int(period)))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of Estimator::optimization() on all host cores, bounded sample per step."""
     if rank != 0:
@@ -85,7 +98,7 @@ def run_reference(args, rank, world):
     from oracle_lib import OracleBackend
     cfg = abi.default_config()
     ob = OracleBackend(cfg)
-    cores = os.cpu_count() or 1
+    cores = usable_cpus()
     batch = synth.generate_batch(CPU_SAMPLE, FEATURES, ob, prior_features=PRIOR_FEATURES)
     saved = batch.copy_states()
     nthreads = min(cores, CPU_SAMPLE)
@@ -227,7 +240,7 @@ def main():
                 sys.path.insert(0, os.path.join(ROOT, "tests"))
                 from oracle_lib import OracleBackend
                 ob = OracleBackend(cfg)
-                cores = os.cpu_count() or 1
+                cores = usable_cpus()
                 ns = min(CPU_SAMPLE, NW)
                 sub = synth.tile_batch(batch, ns) if ns != NW else batch
                 if sub is batch:

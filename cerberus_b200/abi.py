@@ -12,7 +12,7 @@ NUM_FRAMES = 11
 IL_RES = 31
 MAX_PRIOR_BLOCKS = 16
 MAX_PRIOR_DIM = 96
-NUM_REDUCED = 221  # 66 pose + 12 extrinsic + 99 speed-bias + 44 leg-bias tangent dims
+NUM_REDUCED = 222  # 66 pose + 12 extrinsic + 99 speed-bias + 44 leg-bias + 1 td tangent dims
 
 OK, ERR_BAD_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_NON_FINITE = 0, 1, 2, 3, 4
 TERM_CONVERGENCE, TERM_NO_CONVERGENCE, TERM_FAILURE = 0, 1, 2

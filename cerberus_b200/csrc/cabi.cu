@@ -201,7 +201,6 @@ static int pack_window(CerbHandle *h, int w, const CerbWindowDesc &d, const Cerb
     const int F = h->F, O = h->O;
     if (d.n_features < 0 || d.n_features > F) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_features over capacity");
     if (d.n_obs < 0 || d.n_obs > O) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_obs over capacity");
-    if (d.td_open) return fail(CERB_ERR_BAD_ARGUMENT, "td estimation (td_open) is not supported by this build; keep para_Td constant");
     if ((d.n_features && (!d.features || !d.obs || !st.para_Feature)) || (!d.preint && !d.imu_preint)) return fail(CERB_ERR_BAD_ARGUMENT, "window: null pointer");
     h->h_nfeat[w] = d.n_features;
     h->h_flags[w] = (d.extrinsic_open ? 1 : 0) | (d.td_open ? 2 : 0) | (d.preint ? 0 : 4);      // bit2: USE_LEG == 0, no leg-bias blocks

@@ -2,7 +2,7 @@
 // vector2double() and double2vector() (reference src/estimator/estimator.cpp:1059-1236), one window per
 // CTA, the whole trust-region loop device resident.
 //
-// Unknowns of a window (tangent space): x = [pose0..10 (66) | ex0, ex1 (12)] = 78 "camera" dims,
+// Unknowns of a window (tangent space): x = [pose0..10 (66) | ex0, ex1 (12) | td (1)] = 79 "camera" dims,
 // y_f = [speedbias_f (9) | legbias_f (4)] = 13 dims per frame (143), lambda = one inverse depth per
 // feature.  Structure exploited:
 //   * visual factors touch only x and lambda  -> lambda is Schur-eliminated with rank-1 updates
@@ -13,13 +13,13 @@
 // The solver semantics restated on top of that are those of Ceres 1.14: TRUST_REGION + TRADITIONAL
 // DOGLEG (mu-regularised Gauss-Newton, Cauchy point), Jacobi scaling from iteration 0, HuberLoss
 // corrector, the accept / reject / tolerance logic of TrustRegionMinimizer.  Constant parameter blocks
-// are masked (scale 0).  td is kept constant (td_open is rejected by the host layer this round).
+// are masked (scale 0): leg bias if !optimize_leg_bias, extrinsics until extrinsic_open, td unless td_open.
 #pragma once
 #include "eval_kernels.cuh"
 
 namespace cerb {
 
-enum { CERB_WINDOW = 10, NX = 78, NYB = 13, NFR = 11, NY = 143, NR = 221, NRP = 224, SOLVE_THREADS = 256, FT = 64, TILE_LD = 33, NOBS_PLANES = 9 };
+enum { CERB_WINDOW = 10, NX = 79, NYB = 13, NFR = 11, NY = 143, NR = 222, NRP = 224, HXX_SZ = 79 * 79, HXY_SZ = 79 * 143, X_TD = 78, SOLVE_THREADS = 256, FT = 64, TILE_LD = 33, NOBS_PLANES = 9 };
 
 struct SolveParams {
     int n_windows, maxF, maxObs, max_iters, optimize_leg_bias;
@@ -42,7 +42,7 @@ struct SolveParams {
 CERB_HD long ws_W(int) { return 0; }                                        // [NX][F]
 CERB_HD long ws_vecs(int F) { return (long)NX * F; }                        // 8 vectors of F: hh, gl, sl, Dl, ghl, gnl, stl, lamc
 CERB_HD long ws_backup(int F) { return (long)NX * F + 8L * F; }             // Hxx 6084 | Hxy 11154 | Ad 1859 | Bo 1690
-CERB_HD long ws_size(int F) { return ws_backup(F) + 6084 + 11154 + 1859 + 1690 + 64; }
+CERB_HD long ws_size(int F) { return ws_backup(F) + HXX_SZ + HXY_SZ + 1859 + 1690 + 64; }
 
 struct Smem {
     double *Hxx, *Hxy, *Ad, *Bo;            // 78x78, 78x143, 11x13x13, 10x13x13
@@ -59,11 +59,11 @@ struct Smem {
     int *ti;                                // 128 ints: anchor per tile factor ; + misc ints
     double *tile;                           // alias of Hxy (+ Ad, Bo): 256 x TILE_LD tile + 8 x 640 partial Gram tiles
 };
-enum { SMEM_DOUBLES = 6084 + 11154 + 1859 + 1690 + 7 * NRP + 2 * ST_STRIDE + 99 + 18 + 3 + 31 * 39 + 960 + 192 + 8 * 256 + 128 * 8 + 64 + 80 + 160 };
+enum { SMEM_DOUBLES = HXX_SZ + HXY_SZ + 1859 + 1690 + 7 * NRP + 2 * ST_STRIDE + 99 + 18 + 3 + 31 * 39 + 960 + 192 + 8 * 256 + 128 * 8 + 64 + 80 + 160 };
 
 CERB_D void smem_carve(double *base, Smem &s) {
     double *p = base;
-    s.Hxx = p; p += 6084; s.Hxy = p; p += 11154; s.Ad = p; p += 1859; s.Bo = p; p += 1690;
+    s.Hxx = p; p += HXX_SZ; s.Hxy = p; p += HXY_SZ; s.Ad = p; p += 1859; s.Bo = p; p += 1690;
     s.g = p; p += NRP; s.sc = p; p += NRP; s.D = p; p += NRP; s.gh = p; p += NRP; s.gn = p; p += NRP; s.stp = p; p += NRP; s.yv = p; p += NRP;
     s.xs = p; p += ST_STRIDE; s.xc = p; p += ST_STRIDE;
     s.Rw = p; p += 99; s.Rex = p; p += 18; p += 3;
@@ -166,7 +166,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
             for (int k = 0; k < FT; k++) { const int a = s.ti[k]; if (a != 127) { lo = a < lo ? a : lo; hi = a > hi ? a : hi; } }
             s.ti[128] = lo; s.ti[129] = hi;
         }
-        double h = 0.0, gq = 0.0, wI[6], wE0[6], wE1[6];
+        double h = 0.0, gq = 0.0, wT = 0.0, wI[6], wE0[6], wE1[6];
         for (int k = 0; k < 6; k++) { wI[k] = 0.0; wE0[k] = 0.0; wE1[k] = 0.0; }
         __syncthreads();
         const int amin = s.ti[128], amax = s.ti[129];
@@ -185,10 +185,12 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
                         row0[12 + k] = hw * J.Je0[k]; row1[12 + k] = hw * J.Je0[6 + k];
                         row0[18 + k] = hw * J.Je1[k]; row1[18 + k] = hw * J.Je1[6 + k];
                     }
-                    row0[24] = hw * r[0]; row1[24] = hw * r[1];
-                    for (int k = 25; k < 32; k++) { row0[k] = 0.0; row1[k] = 0.0; }
+                    row0[24] = hw * J.Jtd[0]; row1[24] = hw * J.Jtd[1];          // d r / d td
+                    row0[25] = hw * r[0]; row1[25] = hw * r[1];
+                    for (int k = 26; k < 32; k++) { row0[k] = 0.0; row1[k] = 0.0; }
                     const double l0 = hw * J.Jl[0], l1 = hw * J.Jl[1];
-                    h += l0 * l0 + l1 * l1; gq += l0 * row0[24] + l1 * row1[24];
+                    h += l0 * l0 + l1 * l1; gq += l0 * row0[25] + l1 * row1[25];
+                    wT += row0[24] * l0 + row1[24] * l1;
                     for (int k = 0; k < 6; k++) {
                         wI[k] += row0[k] * l0 + row1[k] * l1;
                         wjv[k] = row0[6 + k] * l0 + row1[6 + k] * l1;
@@ -240,14 +242,15 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
                         const int mi = k < 4 ? 0 : (k < 7 ? 1 : (k < 9 ? 2 : 3));
                         const int ni = k < 4 ? k : (k < 7 ? k - 3 : (k < 9 ? k - 5 : 3));
                         const int la = 8 * mi + r, lb = 8 * ni + c;
-                        if (la > lb || lb > 24 || la == 24) continue;
+                        if (la > lb || lb > 25 || la == 25) continue;
                         if (a == j && la < 12) continue;                  // anchor-frame rows (K3) have no pose columns
                         double accv = 0.0;
                         for (int wq = 0; wq < 8; wq++) accv += part[wq * 640 + e];
-                        const int ga = la < 6 ? 6 * a + la : (la < 12 ? 6 * j + la - 6 : 66 + la - 12);
-                        if (lb == 24) s.g[ga] += accv;
+                        // local column -> x index: I 0..5 | J 6..11 | E0, E1 12..23 | td 24 ; column 25 is the residual
+                        const int ga = la < 6 ? 6 * a + la : (la < 12 ? 6 * j + la - 6 : (la < 24 ? 66 + la - 12 : X_TD));
+                        if (lb == 25) s.g[ga] += accv;
                         else {
-                            const int gb = lb < 6 ? 6 * a + lb : (lb < 12 ? 6 * j + lb - 6 : 66 + lb - 12);
+                            const int gb = lb < 6 ? 6 * a + lb : (lb < 12 ? 6 * j + lb - 6 : (lb < 24 ? 66 + lb - 12 : X_TD));
                             s.Hxx[ga * NX + gb] += accv;
                         }
                     }
@@ -258,14 +261,15 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
         }
         // --- per-feature lambda blocks: h, g_lambda, W rows of the anchor pose and the extrinsics --------------
         if (tid >= FT && tid < 2 * FT) {
-            double *q = s.tile + (tid - FT) * 20;
-            q[0] = h; q[1] = gq;
+            double *q = s.tile + (tid - FT) * 24;
+            q[0] = h; q[1] = gq; q[20] = wT;
             for (int k = 0; k < 6; k++) { q[2 + k] = wI[k]; q[8 + k] = wE0[k]; q[14 + k] = wE1[k]; }
         }
         __syncthreads();
         if (tid < FT && ev) {
-            const double *q = s.tile + tid * 20;
+            const double *q = s.tile + tid * 24;
             hh[f] = (h + q[0]) * slf * slf; gl[f] = (gq + q[1]) * slf;
+            W[(size_t)X_TD * F + f] = (wT + q[20]) * (prescale ? s.sc[X_TD] * slf : 1.0);
             for (int k = 0; k < 6; k++) {
                 W[(size_t)(6 * c.start + k) * F + f] = (wI[k] + q[2 + k]) * (prescale ? s.sc[6 * c.start + k] * slf : 1.0);
                 W[(size_t)(66 + k) * F + f] = (wE0[k] + q[8 + k]) * (prescale ? s.sc[66 + k] * slf : 1.0);
@@ -396,7 +400,7 @@ CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const dou
                 else if (kind == 3) d = 66 + 6 * index + k;
                 else if (kind == 1) d = -(1 + NYB * index + k);
                 else if (kind == 2) d = -(1 + NYB * index + 9 + k);
-                else d = 1 << 20;                                      // td: constant this round
+                else d = X_TD;
                 s.ti[col + k] = d;
             }
         }
@@ -422,7 +426,7 @@ CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const dou
 }
 
 // x [+] delta -> xc ; lam + dlam -> lamc
-CERB_D void apply_plus(const Smem &s, const double *delta, const double *lam, const double *dlam, double *lamc, int nF, bool ex_open, int tid) {
+CERB_D void apply_plus(const Smem &s, const double *delta, const double *lam, const double *dlam, double *lamc, int nF, bool ex_open, bool td_open, int tid) {
     if (tid < 11) pose_plus(s.xs + ST_POSE + 7 * tid, delta + 6 * tid, s.xc + ST_POSE + 7 * tid);
     else if (tid < 13) {
         const int e = tid - 11;
@@ -431,18 +435,18 @@ CERB_D void apply_plus(const Smem &s, const double *delta, const double *lam, co
     }
     for (int k = tid; k < 99; k += SOLVE_THREADS) { const int f = k / 9, c = k % 9; s.xc[ST_SB + k] = s.xs[ST_SB + k] + delta[NX + NYB * f + c]; }
     for (int k = tid; k < 44; k += SOLVE_THREADS) { const int f = k / 4, c = k % 4; s.xc[ST_LB + k] = s.xs[ST_LB + k] + delta[NX + NYB * f + 9 + c]; }
-    if (tid == 0) s.xc[ST_TD] = s.xs[ST_TD];
+    if (tid == 0) s.xc[ST_TD] = td_open ? s.xs[ST_TD] + delta[X_TD] : s.xs[ST_TD];
     for (int f = tid; f < nF; f += SOLVE_THREADS) lamc[f] = lam[f] + dlam[f];
     __syncthreads();
 }
 
 // ambient squared norm of the active parameter blocks of `a` (or of a - b if b != null)
-CERB_D double ambient_sq(const double *a, const double *b, const double *la, const double *lb, int nF, bool ex_open, bool lb_open, int tid) {
+CERB_D double ambient_sq(const double *a, const double *b, const double *la, const double *lb, int nF, bool ex_open, bool lb_open, bool td_open, int tid) {
     double t = 0.0;
     for (int k = tid; k < ST_SIZE; k += SOLVE_THREADS) {
         if (k >= ST_LB && k < ST_EX && !lb_open) continue;
         if (k >= ST_EX && k < ST_TD && !ex_open) continue;
-        if (k == ST_TD) continue;
+        if (k == ST_TD && !td_open) continue;
         const double v = b ? a[k] - b[k] : a[k];
         t += v * v;
     }
@@ -469,6 +473,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
         const int nF = P.n_features[w];
         const bool ex_open = (P.flags[w] & 1) != 0;
         const bool lb_open = P.optimize_leg_bias && (P.flags[w] & 4) == 0;
+        const bool td_open = (P.flags[w] & 2) != 0;
         double *lam = P.lam + (size_t)w * F;
         for (int k = tid; k < ST_STRIDE; k += SOLVE_THREADS) s.xs[k] = (k < ST_SIZE) ? P.state[(size_t)w * ST_STRIDE + k] : 0.0;
         if (tid == 0) {
@@ -482,17 +487,17 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
         while (true) {
             // =============================== linearise at xs ===========================================
             if (need_linearize) {
-                for (int k = tid; k < 6084; k += SOLVE_THREADS) s.Hxx[k] = 0.0;
+                for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = 0.0;
                 for (int k = tid; k < NRP; k += SOLVE_THREADS) s.g[k] = 0.0;
                 load_geometry(s.xs, s, tid);
                 double part[2];
                 part[0] = vision_linearize(P, s, w, s.xs, lam, W, hh, gl, sl, iteration > 0, tid);
-                for (int k = tid; k < 11154; k += SOLVE_THREADS) s.Hxy[k] = 0.0;     // the tile aliased Hxy
+                for (int k = tid; k < HXY_SZ; k += SOLVE_THREADS) s.Hxy[k] = 0.0;     // the tile aliased Hxy
                 for (int k = tid; k < 1859; k += SOLVE_THREADS) s.Ad[k] = 0.0;
                 for (int k = tid; k < 1690; k += SOLVE_THREADS) s.Bo[k] = 0.0;
                 __syncthreads();
                 part[0] += inertial_linearize(P, s, w, s.xs, tid);
-                part[1] = ambient_sq(s.xs, nullptr, lam, nullptr, nF, ex_open, lb_open, tid);
+                part[1] = ambient_sq(s.xs, nullptr, lam, nullptr, nF, ex_open, lb_open, td_open, tid);
                 double tot[2];
                 block_sum<2>(part, s.red, tot, tid);
                 if (tid == 0) { sca[S_XCOST] = tot[0]; sca[S_XNORM] = sqrt(tot[1]); if (iteration == 0) sca[S_INIT_COST] = tot[0]; }
@@ -504,7 +509,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                     for (int k = tid; k < NR; k += SOLVE_THREADS) {
                         double d;
                         bool active = true;
-                        if (k < NX) { d = s.Hxx[k * NX + k]; if (k >= 66 && !ex_open) active = false; }
+                        if (k < NX) { d = s.Hxx[k * NX + k]; if (k >= 66 && k < X_TD && !ex_open) active = false; if (k == X_TD && !td_open) active = false; }
                         else { const int yk = k - NX, f = yk / NYB, c = yk % NYB; d = s.Ad[f * 169 + c * NYB + c]; if (c >= 9 && !lb_open) active = false; }
                         s.sc[k] = active ? 1.0 / (1.0 + sqrt(d)) : 0.0;
                     }
@@ -514,7 +519,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 if (P.dbg && w == P.dbg_window && iteration == 0) {      // parity probe, ABI order
                     for (int k = tid; k < NR; k += SOLVE_THREADS) {
                         int dst; double d;
-                        if (k < NX) { dst = k; d = s.Hxx[k * NX + k]; }
+                        if (k < NX) { dst = k < X_TD ? k : 221; d = s.Hxx[k * NX + k]; }      // ABI order: td after the leg biases
                         else { const int yk = k - NX, f = yk / NYB, c = yk % NYB; dst = c < 9 ? 78 + 9 * f + c : 177 + 4 * f + (c - 9); d = s.Ad[f * 169 + c * NYB + c]; }
                         const bool act = s.sc[k] != 0.0;
                         P.dbg[1 + dst] = act ? s.g[k] : 0.0; P.dbg[1 + NR + F + dst] = act ? d : 0.0;
@@ -880,12 +885,12 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
             }
             __syncthreads();
             // =============================== candidate point and its cost ===================================
-            apply_plus(s, s.stp, lam, stl, lamc, nF, ex_open, tid);
+            apply_plus(s, s.stp, lam, stl, lamc, nF, ex_open, td_open, tid);
             load_geometry(s.xc, s, tid);
             {
                 double part[2];
                 part[0] = vision_cost(P, s, w, s.xc, lamc, tid) + inertial_cost(P, s, w, s.xc, tid) + prior_residual(P, s, w, s.xc, tid);
-                part[1] = ambient_sq(s.xs, s.xc, lam, lamc, nF, ex_open, lb_open, tid);
+                part[1] = ambient_sq(s.xs, s.xc, lam, lamc, nF, ex_open, lb_open, td_open, tid);
                 double tot[2];
                 block_sum<2>(part, s.red, tot, tid);
                 if (tid == 0) {

@@ -274,7 +274,7 @@ int cerb_sync(CerbHandle *h);
 int cerb_last_solve_stats(CerbHandle *h, double *kernel_ms, int32_t *kernel_launches);
 /* Debug/parity probe: linearisation of window `w` of the resident batch at its CURRENT state,
  * exactly what the first solver iteration sees: cost, gradient (tangent space, order
- * [pose0..10 (66) | ex0, ex1 (12) | speedbias0..10 (99) | legbias0..10 (44) | features]),
+ * [pose0..10 (66) | ex0, ex1 (12) | speedbias0..10 (99) | legbias0..10 (44) | td (1) | features]),
  * the Schur-reduced 221x221 system is not exposed, only the gradient and diag(J^T J). */
 int cerb_debug_linearize(CerbHandle *h, int32_t w, double *cost, double *gradient, double *jtj_diag,
                          int32_t n_alloc);

@@ -277,8 +277,8 @@ int oracle_solve_window(const CerbSolverConfig *cfg, const CerbWindowDesc *desc,
     if (report) { report->iterations = s.iterations; report->num_successful_steps = s.num_successful_steps; report->termination = s.termination;
                   report->status = std::isfinite(s.final_cost) ? CERB_OK : CERB_ERR_NON_FINITE; report->initial_cost = s.initial_cost; report->final_cost = s.final_cost; }
     if (gradient0 || jtj_diag0) {
-        // ABI order: [pose0..10 (66) | ex0, ex1 (12) | speedbias0..10 (99) | legbias0..10 (44) | features]; constant blocks -> 0
-        int total = 221 + desc->n_features;
+        // ABI order: [pose0..10 (66) | ex0, ex1 (12) | speedbias0..10 (99) | legbias0..10 (44) | td | features]; constant blocks -> 0
+        int total = 222 + desc->n_features;
         if (n_alloc < total) return CERB_ERR_BAD_ARGUMENT;
         for (int k = 0; k < total; k++) { if (gradient0) gradient0[k] = 0; if (jtj_diag0) jtj_diag0[k] = 0; }
         auto put = [&](double *ptr, int off) {
@@ -288,8 +288,8 @@ int oracle_solve_window(const CerbSolverConfig *cfg, const CerbWindowDesc *desc,
             for (int k = 0; k < b.local; k++) { if (gradient0) gradient0[off + k] = s.gradient0[b.col + k]; if (jtj_diag0) jtj_diag0[off + k] = s.jtj_diag0[b.col + k]; }
         };
         for (int i = 0; i < 11; i++) { put(state->para_Pose[i], 6 * i); put(state->para_SpeedBias[i], 78 + 9 * i); put(state->para_LegBias[i], 177 + 4 * i); }
-        put(state->para_Ex_Pose[0], 66); put(state->para_Ex_Pose[1], 72);
-        for (int f = 0; f < desc->n_features; f++) put(&state->para_Feature[f], 221 + f);
+        put(state->para_Ex_Pose[0], 66); put(state->para_Ex_Pose[1], 72); put(state->para_Td, 221);
+        for (int f = 0; f < desc->n_features; f++) put(&state->para_Feature[f], 222 + f);
     }
     return CERB_OK;
 }

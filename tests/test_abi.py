@@ -70,14 +70,10 @@ def test_bad_descriptors_are_rejected():
     cfg = small_cfg()
     sb = sim_backend(cfg)
     batch = synth.generate_batch(1, 6, OracleBackend(cfg), with_prior=False)
-    batch.descs[0].td_open = 1
+    batch.descs[0].n_features = cfg.max_features + 1
     with pytest.raises(lib.CerbError) as e:
         sb.solve_batch(batch)
-    assert e.value.code == abi.ERR_BAD_ARGUMENT and "td" in str(e.value)
-    batch.descs[0].td_open = 0
-    batch.descs[0].n_features = cfg.max_features + 1
-    with pytest.raises(lib.CerbError):
-        sb.solve_batch(batch)
+    assert e.value.code == abi.ERR_BAD_ARGUMENT
     batch.descs[0].n_features = 6
     batch.features[0][2]["n_obs"] = 40
     with pytest.raises(lib.CerbError):

@@ -117,3 +117,38 @@ def test_imu_only_window_solve():
     assert abs(rep_o["final_cost"][0] - rep_s["final_cost"][0]) < 1e-7 * rep_o["final_cost"][0]
     d = state_diffs(st, ref)
     assert d["para_Pose"] < 1e-7 and d["para_SpeedBias"] < 1e-6, d
+
+
+def test_td_open_window_solve():
+    """ESTIMATE_TD (estimator.cpp:1114-1123 adds para_Td unless it is held constant): td is the 79th camera-side
+    unknown; gradient/diagonal probe, iteration counts, the td estimate and the poses must match the oracle."""
+    cfg = small_cfg(iters=4)
+    o, s = OracleBackend(cfg), sim_backend(cfg)
+    batch = synth.generate_batch(2, 12, o, window0=77, prior_features=6)
+    st = batch.state_array()
+    for w in range(2):
+        batch.descs[w].td_open = 1
+    st["para_Td"][:, 0] = [0.004, -0.003]
+    saved = batch.copy_states()
+    s.upload(batch)
+    cost, g, d = s.debug_linearize(batch, 0)
+    g0, d0 = o.solve_window(batch, 0, want_probe=True)
+    assert g0[221] != 0.0 and d0[221] > 0.0
+    assert np.abs(g - g0).max() < 1e-9 * np.abs(g0).max()
+    assert (np.abs(d - d0) / np.maximum(np.abs(d0), 1e-300)).max() < 1e-8
+    batch.restore_states(saved)
+    rep_o = o.solve_batch(batch); ref = st.copy(); lam = batch.para_Feature.copy()
+    batch.restore_states(saved)
+    rep_s = s.solve_batch(batch)
+    st = batch.state_array()
+    assert (rep_o["iterations"] == rep_s["iterations"]).all() and (rep_o["num_successful_steps"] == rep_s["num_successful_steps"]).all()
+    assert np.abs(rep_o["final_cost"] - rep_s["final_cost"]).max() < 1e-7 * rep_o["final_cost"].max()
+    assert (st["para_Td"] != saved_td(saved)).all()
+    assert np.abs(st["para_Td"] - ref["para_Td"]).max() < 1e-8
+    diffs = state_diffs(st, ref)
+    assert diffs["para_Pose"] < 1e-7 and diffs["para_SpeedBias"] < 1e-6 and diffs["para_Ex_Pose"] < 1e-7, diffs
+    assert np.abs(batch.para_Feature - lam).max() < 1e-7
+
+
+def saved_td(saved):
+    return np.array([[0.004], [-0.003]])

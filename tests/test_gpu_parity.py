@@ -147,3 +147,19 @@ def test_imu_only_windows(gpu, oracle):
     assert (rep_o["iterations"] == rep_g["iterations"]).all() and (st["para_LegBias"] == lb0).all()
     d = state_diffs(st, ref)
     assert d["para_Pose"] < POS_TOL and d["para_SpeedBias"] < 1e-5, d
+
+
+def test_td_open_windows(gpu, oracle):
+    """ESTIMATE_TD: para_Td is the 79th camera-side unknown; it must move towards the truth (0) and match the oracle."""
+    batch = synth.generate_batch(8, 100, gpu, window0=400, prior_features=16)
+    st = batch.state_array()
+    for w in range(8):
+        batch.descs[w].td_open = 1
+    td0 = np.linspace(-0.004, 0.004, 8).reshape(8, 1); td0[np.abs(td0) < 1e-4] = 0.002
+    st["para_Td"][:] = td0
+    rep_o, rep_g, ref, lam, st = solve_both(gpu, oracle, batch)
+    assert (rep_o["iterations"] == rep_g["iterations"]).all()
+    assert np.abs(st["para_Td"] - ref["para_Td"]).max() < 1e-7
+    assert (np.abs(st["para_Td"]) < np.abs(td0)).all()
+    d = state_diffs(st, ref)
+    assert d["para_Pose"] < POS_TOL and d["para_SpeedBias"] < 1e-5 and d["para_Ex_Pose"] < POS_TOL, d
