@@ -431,6 +431,16 @@ int cerb_debug_linearize(CerbHandle *h, int32_t w, double *cost, double *gradien
     return CERB_OK;
 }
 
+#if defined(CERB_PHASE_TIMING) && !defined(CERB_CUSIM)
+// tools/phase_profile.py only (separate library build): read and reset the per-phase cycle counters of the solve kernel
+extern "C" int cerb_prof_phase_cycles(unsigned long long *out48) {
+    unsigned long long z[48] = {0};
+    if (cudaMemcpyFromSymbol(out48, g_phase_cycles, sizeof(z)) != cudaSuccess) return CERB_ERR_CUDA;
+    if (cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)) != cudaSuccess) return CERB_ERR_CUDA;
+    return CERB_OK;
+}
+#endif
+
 // ---- factor-family evaluators ----------------------------------------------------------------------------------
 struct DevBuf {   // RAII scratch
     std::vector<void *> ptrs;

@@ -19,6 +19,19 @@
 
 namespace cerb {
 
+// Optional per-phase cycle counters (tools/phase_profile.py builds a separate library with -DCERB_PHASE_TIMING; the
+// product build compiles these macros to nothing).
+#if defined(CERB_PHASE_TIMING) && !defined(CERB_CUSIM)
+__device__ unsigned long long g_phase_cycles[48];
+#define PH_DECL() long long ph_t = clock64()
+#define PH_MARK_T(id, t) do { if ((threadIdx.x & 31) == 0) { const long long ph_n = clock64(); if (threadIdx.x == (t)) atomicAdd(&g_phase_cycles[id], (unsigned long long)(ph_n - ph_t)); ph_t = ph_n; } } while (0)
+#define PH_MARK(id) PH_MARK_T(id, 0)
+#else
+#define PH_DECL()
+#define PH_MARK_T(id, t)
+#define PH_MARK(id)
+#endif
+
 enum { CERB_WINDOW = 10, NX = 79, NYB = 13, NFR = 11, NY = 143, NR = 222, NRP = 224, HXX_SZ = 79 * 79, HXY_SZ = 79 * 143, X_TD = 78, SOLVE_THREADS = 256, FT = 64, TILE_LD = 33, NOBS_PLANES = 9 };
 
 struct SolveParams {
@@ -56,10 +69,11 @@ struct Smem {
     double *wj;                             // 128 x 8 per-thread exchange
     double *sca;                            // 64 scalars
     double *idg;                            // 143 (+pad): 1 / diag(L) of the block-bidiagonal factor of Hyy
+    double *idx;                            // 79 (+pad): 1 / diag(L) of the dense factor of the reduced camera system
     int *ti;                                // 128 ints: anchor per tile factor ; + misc ints
     double *tile;                           // alias of Hxy (+ Ad, Bo): 256 x TILE_LD tile + 8 x 640 partial Gram tiles
 };
-enum { SMEM_DOUBLES = HXX_SZ + HXY_SZ + 1859 + 1690 + 7 * NRP + 2 * ST_STRIDE + 99 + 18 + 3 + 31 * 39 + 960 + 192 + 8 * 256 + 128 * 8 + 64 + 80 + 160 };
+enum { SMEM_DOUBLES = HXX_SZ + HXY_SZ + 1859 + 1690 + 7 * NRP + 2 * ST_STRIDE + 99 + 18 + 3 + 31 * 39 + 960 + 192 + 8 * 256 + 128 * 8 + 64 + 66 + 144 + 80 };
 
 CERB_D void smem_carve(double *base, Smem &s) {
     double *p = base;
@@ -67,10 +81,11 @@ CERB_D void smem_carve(double *base, Smem &s) {
     s.g = p; p += NRP; s.sc = p; p += NRP; s.D = p; p += NRP; s.gh = p; p += NRP; s.gn = p; p += NRP; s.stp = p; p += NRP; s.yv = p; p += NRP;
     s.xs = p; p += ST_STRIDE; s.xc = p; p += ST_STRIDE;
     s.Rw = p; p += 99; s.Rex = p; p += 18; p += 3;
-    s.Ju = p; p += 31 * 39; s.lin = p; p += 960; s.pdx = p; p += 96; s.pr = p; p += 96;
-    s.red = p; p += 8 * 256; s.wj = p; p += 128 * 8; s.sca = p; p += 64;
-    s.ti = reinterpret_cast<int *>(p); p += 80;
-    s.idg = p; p += 160;
+    s.Ju = p; p += 31 * 39; s.red = p; p += 8 * 256; s.wj = p; p += 128 * 8;      // contiguous scratch (4281 doubles): IMU_SCRATCH, Schur tile
+    s.lin = p; p += 960; s.pdx = p; p += 96; s.pr = p; p += 96; s.sca = p; p += 64;
+    s.ti = reinterpret_cast<int *>(p); p += 66;       // 132 ints
+    s.idg = p; p += 144;
+    s.idx = p; p += 80;
     s.tile = s.Hxy;
 }
 
@@ -146,6 +161,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
     const double *obs = P.obs + (size_t)w * NOBS_PLANES * P.maxObs;
     const int *stereo = P.obs_stereo + (size_t)w * P.maxObs;
     double cost = 0.0;
+    PH_DECL();
     for (int i = tid; i < NX * nF; i += SOLVE_THREADS) W[(i / nF) * F + (i % nF)] = 0.0;
     for (int c0 = 0; c0 < nF; c0 += FT) {
         const int fl = tid & (FT - 1), cam = (tid >> 6) & 1;
@@ -170,6 +186,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
         for (int k = 0; k < 6; k++) { wI[k] = 0.0; wE0[k] = 0.0; wE1[k] = 0.0; }
         __syncthreads();
         const int amin = s.ti[128], amax = s.ti[129];
+        PH_MARK(20);
         for (int j = 0; j < NFR; j++) {
             // --- evaluate the factors of frame j into the tile -------------------------------------------------
             if (tid < 2 * FT) {
@@ -203,6 +220,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
                 for (int k = 0; k < 6; k++) s.wj[tid * 8 + k] = wjv[k];
             }
             __syncthreads();
+            PH_MARK(21);
             // --- W rows of frame j: sum of the two cameras -----------------------------------------------------
             if (tid < FT && ev && j != c.start && j >= c.start && j < c.start + c.nobs)
                 for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] = (s.wj[tid * 8 + k] + s.wj[(tid + FT) * 8 + k]) * (prescale ? s.sc[6 * j + k] * slf : 1.0);
@@ -237,6 +255,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
                         o[0] = acc[k][0]; o[1] = acc[k][1];
                     }
                     __syncthreads();
+                    PH_MARK(22);
                     for (int e = tid; e < 640; e += SOLVE_THREADS) {
                         const int k = e >> 6, r = (e >> 3) & 7, c = e & 7;
                         const int mi = k < 4 ? 0 : (k < 7 ? 1 : (k < 9 ? 2 : 3));
@@ -255,6 +274,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
                         }
                     }
                     __syncthreads();
+                    PH_MARK(23);
                 }
             }
             __syncthreads();
@@ -277,6 +297,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
             }
         }
         __syncthreads();
+        PH_MARK(24);
     }
     return cost;
 }
@@ -348,42 +369,82 @@ CERB_D void scatter_H(Smem &s, int da, int db, double v) {
     else s.Bo[fb * 169 + kb * NYB + ka] += v;
 }
 
+// IMU-leg factors.  Per factor: Ju (unwhitened 31 x 38 tangent Jacobian + residual column, expanded from IMULegLin) is
+// whitened, Jw = S Ju, and the Gram matrix Jw^T Jw (39 x 39: Hessian blocks, gradient column, cost corner) is scattered
+// into Hxx / Hxy / Hyy / g.  Both products are dense contractions (32 x 32 x 40 and 40 x 32 x 40 after padding) and run on
+// the fp64 tensor cores; S of the next factor is prefetched into registers while the current one is processed.
+// Scratch (s.Ju .. s.wj, 4281 doubles): SP [32][36] sqrt_info (zero padded) | JuP [32][44] | JwP [32][44].
+enum { IMU_LDS = 36, IMU_LDJ = 44, IMU_SP = 0, IMU_JU = 32 * 36, IMU_JW = 32 * 36 + 32 * 44 };
 CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const double *x, int tid) {
     double cost = 0.0;
+    PH_DECL();
     imu_lin_all(P, s, w, x, true, tid);
+    PH_MARK(25);
+    double *SP = s.Ju + IMU_SP, *JuP = s.Ju + IMU_JU, *JwP = s.Ju + IMU_JW;
+    const int wid = tid >> 5, lane = tid & 31;
+    for (int k = tid; k < IMU_JW; k += SOLVE_THREADS) s.Ju[k] = 0.0;        // SP padding and JuP
+    double sreg[4];
+    {   // prefetch sqrt_info of factor 0 (upper triangular; the lower part is masked when staged)
+        const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + 0) * 961;
+        for (int q = 0; q < 4; q++) { const int k = tid + SOLVE_THREADS * q; sreg[q] = (k < 961) ? S[k] : 0.0; }
+    }
+    __syncthreads();
     for (int i = 0; i < CERB_WINDOW; i++) {
         const double *pre = P.pre + ((size_t)w * CERB_WINDOW + i) * PRE_STRIDE;
-        if (pre[PRE_SUM_DT] > 10.0) continue;                      // estimator.cpp:1119 (uniform across the CTA)
-        for (int k = tid; k < 31 * 39; k += SOLVE_THREADS) s.Ju[k] = 0.0;
+        const bool skip = pre[PRE_SUM_DT] > 10.0;                          // estimator.cpp:1119 (uniform across the CTA)
+        // ---- stage S (padded, lower part masked) and expand Ju ----------------------------------------------------------
+        if (!skip) {
+            for (int q = 0; q < 4; q++) { const int k = tid + SOLVE_THREADS * q; if (k < 961) { const int r = k / 31, c = k % 31; SP[r * IMU_LDS + c] = (c >= r) ? sreg[q] : 0.0; } }
+            if (tid < 11) imu_leg_fill_ju_part(*reinterpret_cast<const IMULegLin *>(s.lin + 96 * i), pre, JuP, IMU_LDJ, tid);
+            else if (tid >= 32 && tid < 63) JuP[(tid - 32) * IMU_LDJ + 38] = s.lin[96 * i + (tid - 32)];       // residual column
+        }
+        if (i + 1 < CERB_WINDOW) {
+            const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + i + 1) * 961;
+            for (int q = 0; q < 4; q++) { const int k = tid + SOLVE_THREADS * q; sreg[q] = (k < 961) ? S[k] : 0.0; }
+        }
+        if (skip) continue;
         __syncthreads();
-        double *Ssm = s.wj;                                         // sqrt_info of this factor (961 doubles; wj holds 1024)
-        { const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + i) * 961; for (int k = tid; k < 961; k += SOLVE_THREADS) Ssm[k] = S[k]; }
-        if (tid < 11) imu_leg_fill_ju_part(*reinterpret_cast<const IMULegLin *>(s.lin + 96 * i), pre, s.Ju, 39, tid);
-        else if (tid >= 32 && tid < 63) s.Ju[(tid - 32) * 39 + 38] = s.lin[96 * i + (tid - 32)];       // residual column
+        // ---- Jw = S Ju: 4 x 5 output blocks of 8 x 8; S is upper triangular, so block row mi needs k >= 8 mi only ------------
+        for (int t = 0; t < 3; t++) {
+            int mi, ni;
+            if (t == 0) { mi = wid & 3; ni = wid >> 2; }
+            else if (t == 1) { mi = 3 - (wid & 3); ni = 2 + (wid >> 2); }
+            else { if (wid >= 4) break; mi = wid; ni = 4; }
+            double a0 = 0.0, a1 = 0.0;
+            for (int ks = 2 * mi; ks < 8; ks++) {
+                const double av = SP[(8 * mi + (lane >> 2)) * IMU_LDS + 4 * ks + (lane & 3)];
+                const double bv = JuP[(4 * ks + (lane & 3)) * IMU_LDJ + 8 * ni + (lane >> 2)];
+                CERB_DMMA(a0, a1, av, bv, a0, a1);
+            }
+            double *o = JwP + (8 * mi + (lane >> 2)) * IMU_LDJ + 8 * ni + 2 * (lane & 3);
+            o[0] = a0; o[1] = a1;
+        }
         __syncthreads();
-        double *Jw = s.red;                                         // whitened copy Jw = S Ju (S upper triangular)
-        {
-            for (int idx = tid; idx < 31 * 39; idx += SOLVE_THREADS) {
-                const int r = idx / 39, c = idx % 39;
-                double t = 0.0;
-                for (int q = r; q < 31; q++) t += Ssm[r * 31 + q] * s.Ju[q * 39 + c];
-                Jw[idx] = t;
+        // ---- Gram matrix of Jw (40 x 40, 15 upper blocks, K = 32) and scatter ---------------------------------------------------
+        for (int b = wid; b < 15; b += 8) {
+            int mi = 0, idx = b;
+            while (idx >= 5 - mi) { idx -= 5 - mi; mi++; }
+            const int ni = mi + idx;
+            double a0 = 0.0, a1 = 0.0;
+            for (int ks = 0; ks < 8; ks++) {
+                const double av = JwP[(4 * ks + (lane & 3)) * IMU_LDJ + 8 * mi + (lane >> 2)];
+                const double bv = JwP[(4 * ks + (lane & 3)) * IMU_LDJ + 8 * ni + (lane >> 2)];
+                CERB_DMMA(a0, a1, av, bv, a0, a1);
+            }
+            const int la = 8 * mi + (lane >> 2);
+            for (int e = 0; e < 2; e++) {
+                const int lb = 8 * ni + 2 * (lane & 3) + e;
+                const double acc = e ? a1 : a0;
+                if (la > lb || lb > 38) continue;
+                if (la == 38) { cost += 0.5 * acc; continue; }
+                const int da = imu_col_dest(i, la);
+                if (lb == 38) { if (da >= 0) s.g[da] += acc; else s.g[NX + (-da - 1)] += acc; continue; }
+                scatter_H(s, da, imu_col_dest(i, lb), acc);
             }
         }
         __syncthreads();
-        for (int e = tid; e < 780; e += SOLVE_THREADS) {          // upper triangle of the 39 x 39 Gram matrix
-            int la = 0, rem = e;
-            while (rem >= 39 - la) { rem -= 39 - la; la++; }
-            const int lb = la + rem;
-            double acc = 0.0;
-            for (int r = 0; r < 31; r++) acc += Jw[r * 39 + la] * Jw[r * 39 + lb];
-            if (la == 38) { cost += 0.5 * acc; continue; }
-            const int da = imu_col_dest(i, la);
-            if (lb == 38) { if (da >= 0) s.g[da] += acc; else s.g[NX + (-da - 1)] += acc; continue; }
-            scatter_H(s, da, imu_col_dest(i, lb), acc);
-        }
-        __syncthreads();
     }
+    PH_MARK(26);
     // ---- prior: r = r0 + J0 dx, g += J0^T r, H += J0^T J0 (precomputed once per solve) -------------------
     const int *meta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
     if (meta[0]) {
@@ -422,6 +483,7 @@ CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const dou
         }
         __syncthreads();
     }
+    PH_MARK(27);
     return cost;
 }
 
@@ -469,6 +531,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
     enum { S_RADIUS = 0, S_MU, S_REUSE, S_XCOST, S_CCOST, S_ALPHA, S_GNORM2, S_GNNORM2, S_GDOTGN, S_MODEL, S_STEPNORM, S_XNORM, S_DLNORM,
            S_OK, S_DONE, S_TERM, S_ITER, S_NSUCC, S_INVALID, S_GMAX, S_INIT_COST, S_P, S_Q };
 
+    PH_DECL();
     for (int w = blockIdx.x; w < P.n_windows; w += gridDim.x) {
         const int nF = P.n_features[w];
         const bool ex_open = (P.flags[w] & 1) != 0;
@@ -491,12 +554,15 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 for (int k = tid; k < NRP; k += SOLVE_THREADS) s.g[k] = 0.0;
                 load_geometry(s.xs, s, tid);
                 double part[2];
+                PH_MARK(0);
                 part[0] = vision_linearize(P, s, w, s.xs, lam, W, hh, gl, sl, iteration > 0, tid);
                 for (int k = tid; k < HXY_SZ; k += SOLVE_THREADS) s.Hxy[k] = 0.0;     // the tile aliased Hxy
                 for (int k = tid; k < 1859; k += SOLVE_THREADS) s.Ad[k] = 0.0;
                 for (int k = tid; k < 1690; k += SOLVE_THREADS) s.Bo[k] = 0.0;
                 __syncthreads();
+                PH_MARK(1);
                 part[0] += inertial_linearize(P, s, w, s.xs, tid);
+                PH_MARK(2);
                 part[1] = ambient_sq(s.xs, nullptr, lam, nullptr, nF, ex_open, lb_open, td_open, tid);
                 double tot[2];
                 block_sum<2>(part, s.red, tot, tid);
@@ -547,6 +613,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 }
                 __syncthreads();
                 need_linearize = false;
+                PH_MARK(3);
             }
             // =============================== FinalizeIterationAndCheckIfMinimizerCanContinue =============
             if (tid == 0) {
@@ -585,6 +652,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 block_sum<2>(part, s.red, tot, tid);
                 if (tid == 0) { sca[S_GNORM2] = tot[1]; sca[S_ALPHA] = tot[1] / tot[0]; }
                 __syncthreads();
+                PH_MARK(4);
 
                 // ---- Gauss-Newton step: (H~ + mu D^2) y = g~, retry with mu *= 10 on failure ----------------
                 {
@@ -600,41 +668,45 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                     __syncthreads();
                     if (tid < 32) {
                         // ---- warp 0: block-bidiagonal Cholesky of Hyy: Ad[f] <- L_f (lower), Bo[f] <- M_f = B_f^T L_f^-T ----
+                        // Lane r owns row r of the 13 x 13 block in registers; the column sweep exchanges pivots and column
+                        // entries with shuffles (no shared-memory round trips on the dependency chain).
                         const int lane = tid;
+                        const bool act = lane < NYB;
+                        const int r = act ? lane : 0;              // idle lanes shadow row 0 and never store
+                        double m[NYB];                             // row r of M_{f-1}
                         for (int f = 0; f < NFR; f++) {
                             double *A = s.Ad + f * 169;
+                            double a[NYB], invd[NYB];
+                            for (int c = 0; c < NYB; c++) a[c] = A[r * NYB + c];
                             if (f > 0) {
-                                const double *M = s.Bo + (f - 1) * 169;        // M[r][c], r: y_f index, c: y_{f-1} index
-                                for (int e = lane; e < 169; e += 32) { const int r = e / NYB, c = e % NYB; if (c > r) continue; double t = 0.0; for (int q = 0; q < NYB; q++) t += M[r * NYB + q] * M[c * NYB + q]; A[e] -= t; }
-                                __syncwarp();
+                                const double *Mp = s.Bo + (f - 1) * 169;        // M[r][c], r: y_f index, c: y_{f-1} index
+                                for (int c = 0; c < NYB; c++) { double t = 0.0; for (int q = 0; q < NYB; q++) t += m[q] * Mp[c * NYB + q]; a[c] -= t; }
                             }
-                            double *idg = s.idg + NYB * f;
-                            for (int j = 0; j < NYB; j++) {                     // right-looking: short dependency chains
-                                double d = A[j * NYB + j];
+                            for (int j = 0; j < NYB; j++) {                     // right-looking column sweep
+                                double d = __shfl_sync(0xffffffffu, a[j], j);
                                 if (!(d > 0.0)) { if (lane == 0) sca[S_OK] = 0; d = 1.0; }
-                                const double ljj = sqrt(d), inv = 1.0 / ljj;
-                                __syncwarp();
-                                if (lane > j && lane < NYB) A[lane * NYB + j] *= inv;
-                                if (lane == j) { A[j * NYB + j] = ljj; idg[j] = inv; }
-                                __syncwarp();
-                                for (int e = lane; e < 169; e += 32) {
-                                    const int i = e / NYB, k = e % NYB;
-                                    if (k > j && k <= i) A[e] -= A[i * NYB + j] * A[k * NYB + j];
-                                }
-                                __syncwarp();
+                                const double inv = rsqrt(d);
+                                invd[j] = inv;
+                                const double l = (lane == j) ? d * inv : a[j] * inv;
+                                a[j] = l;
+                                for (int k = j + 1; k < NYB; k++) { const double lk = __shfl_sync(0xffffffffu, l, k); a[k] -= l * lk; }
                             }
+                            if (act) { for (int c = 0; c < NYB; c++) if (c <= r) A[r * NYB + c] = a[c]; s.idg[NYB * f + r] = invd[r]; }
+                            __syncwarp();
                             if (f < NFR - 1) {
                                 double *B = s.Bo + f * 169;                     // in: B[k1][k2] = H(y_f[k1], y_{f+1}[k2]); out: M[r][c]
-                                double row[NYB];
-                                if (lane < NYB) {
-                                    const int r = lane;
-                                    for (int c = 0; c < NYB; c++) { double t = B[c * NYB + r]; for (int q = 0; q < c; q++) t -= row[q] * A[c * NYB + q]; row[c] = t * idg[c]; }
+                                double t[NYB];
+                                for (int c = 0; c < NYB; c++) t[c] = B[c * NYB + r];
+                                for (int c = 0; c < NYB; c++) {
+                                    m[c] = t[c] * invd[c];
+                                    for (int c2 = c + 1; c2 < NYB; c2++) t[c2] -= m[c] * A[c2 * NYB + c];
                                 }
                                 __syncwarp();
-                                if (lane < NYB) for (int c = 0; c < NYB; c++) B[lane * NYB + c] = row[c];
+                                if (act) for (int c = 0; c < NYB; c++) B[r * NYB + c] = m[c];
                                 __syncwarp();
                             }
                         }
+                        PH_MARK(6);
                     } else {
                         // ---- warps 1..7: eliminate the inverse depths on the fp64 tensor cores ---------------------------
                         //   S = Hxx - W' W'^T,  rhs_x -= W' (w g_l),  W'[a][f] = W[a][f] / sqrt(h_f + mu D_f^2)
@@ -687,8 +759,10 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                                 else { s.Hxx[b * NX + a] -= acc[k][e]; if (a != b) s.Hxx[a * NX + b] -= acc[k][e]; }
                             }
                         }
+                        PH_MARK_T(7, 32);
                     }
                     __syncthreads();
+                    PH_MARK(5);
                     // ---- T = L^-1 Hyx (row a of Hxy in place), and the same for the y part of the rhs (row 78) ----
                     if (tid <= NX) {
                         double *row = (tid < NX) ? s.Hxy + tid * NY : s.yv + NX;
@@ -707,6 +781,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                         }
                     }
                     __syncthreads();
+                    PH_MARK(8);
                     // ---- S' = S - T T^T (lower), rhs'_x = rhs_x - T gy' : Gram matrix of the 79 x 143 matrix [T; gy'^T] on the
                     // fp64 tensor cores, 55 upper 8x8 blocks dealt round-robin to the 8 warps, K = 143 padded to 144 ----------
                     {
@@ -742,42 +817,106 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                         }
                     }
                     __syncthreads();
-                    // ---- dense Cholesky of the 78 x 78 lower triangle, rhs carried as an extra row (z = L^-1 rhs) ----
-                    // Right-looking, one barrier per column: the trailing update of column k uses the raw column
-                    // (A[i][k] A[j][k] / d_k); column k is normalised by 1/sqrt(d_k) one step later, when nobody reads it.
+                    PH_MARK(9);
+                    // ---- dense Cholesky of the 79 x 79 lower triangle, rhs carried as row 79 (z = L^-1 rhs), blocked by panels of 8:
+                    // (a) warp 0 factors the diagonal block in registers (pivots / column entries exchanged by shuffles),
+                    // (b) one thread per row below solves its 8 panel entries against L_kk, (c) the trailing lower triangle
+                    // is updated block by block on the fp64 tensor cores (A_ij -= L_ik L_jk^T, K = 8).
                     {
-                        const int ti = tid >> 4, tj = tid & 15;
-                        double dprev = 1.0;
-                        for (int k = 0; k <= NX; k++) {
-                            if (k > 0) {            // normalise column k-1 (and z[k-1])
-                                const double isq = 1.0 / sqrt(dprev);
-                                for (int i = k - 1 + tid; i <= NX; i += SOLVE_THREADS) { if (i < NX) s.Hxx[i * NX + (k - 1)] *= isq; else s.yv[k - 1] *= isq; }
+                        const int wq = tid >> 5, lane = tid & 31;
+                        double *Lkk = s.red;                           // 8 x 8 factored diagonal block (+ its inverse diagonal at [64..72))
+                        for (int c0 = 0; c0 < NX; c0 += 8) {
+                            const int nb = (NX - c0) < 8 ? (NX - c0) : 8, c1 = c0 + nb;
+                            if (wq == 0) {
+                                const bool act = lane < nb;
+                                const int r = act ? lane : 0;
+                                double a[8];
+                                for (int c = 0; c < 8; c++) a[c] = (c < nb && c <= r) ? s.Hxx[(c0 + r) * NX + c0 + c] : 0.0;
+                                double myinv = 1.0;
+                                for (int j = 0; j < 8; j++) {
+                                    double d = __shfl_sync(0xffffffffu, a[j], j);
+                                    if (j < nb && !(d > 0.0)) { if (lane == 0) sca[S_OK] = 0; }
+                                    if (!(d > 0.0)) d = 1.0;
+                                    const double inv = rsqrt(d);
+                                    if (lane == j) myinv = inv;
+                                    const double l = (lane == j) ? d * inv : a[j] * inv;
+                                    a[j] = l;
+                                    for (int k = j + 1; k < 8; k++) { const double lk = __shfl_sync(0xffffffffu, l, k); a[k] -= l * lk; }
+                                }
+                                if (act) {
+                                    for (int c = 0; c < 8; c++) if (c <= r) { s.Hxx[(c0 + r) * NX + c0 + c] = a[c]; Lkk[r * 8 + c] = a[c]; }
+                                    Lkk[64 + r] = myinv; s.idx[c0 + r] = myinv;
+                                }
                             }
-                            if (k == NX) break;
-                            double d = s.Hxx[k * NX + k];
-                            if (!(d > 0.0)) { if (tid == 0) sca[S_OK] = 0; d = 1.0; }
-                            const double inv_d = 1.0 / d;
-                            for (int i = k + 1 + ti; i <= NX; i += 16) {
-                                const double lik = (i < NX ? s.Hxx[i * NX + k] : s.yv[k]) * inv_d;
-                                if (i < NX) { for (int j = k + 1 + tj; j <= i; j += 16) s.Hxx[i * NX + j] -= lik * s.Hxx[j * NX + k]; }
-                                else { for (int j = k + 1 + tj; j < NX; j += 16) s.yv[j] -= lik * s.Hxx[j * NX + k]; }
+                            __syncthreads();
+                            // (b) rows c1 .. NX (row NX = rhs, kept in yv)
+                            if (tid <= NX - c1) {
+                                const int i = c1 + tid;
+                                double *row = (i < NX) ? s.Hxx + i * NX + c0 : s.yv + c0;
+                                double t[8];
+                                for (int c = 0; c < 8; c++) t[c] = (c < nb) ? row[c] : 0.0;
+                                for (int c = 0; c < 8; c++) {
+                                    if (c >= nb) break;
+                                    t[c] *= Lkk[64 + c];
+                                    for (int c2 = c + 1; c2 < 8; c2++) if (c2 < nb) t[c2] -= t[c] * Lkk[c2 * 8 + c];
+                                }
+                                for (int c = 0; c < 8; c++) if (c < nb) row[c] = t[c];
                             }
-                            dprev = d;
+                            __syncthreads();
+                            if (c1 >= NX) break;
+                            // (c) trailing update; 8 x 8 blocks (bi >= bj) of rows / columns c1 .. NX, row NX = rhs
+                            {
+                                const int b0 = c1 >> 3, nbt = 10 - b0;               // block rows b0 .. 9
+                                const int nblk = nbt * (nbt + 1) / 2;
+                                for (int b = wq; b < nblk; b += 8) {
+                                    int bi = 0, idx = b;
+                                    while (idx > bi) { idx -= bi + 1; bi++; }          // b -> (bi, bj) with bj <= bi (relative)
+                                    const int ri = 8 * (b0 + bi) + (lane >> 2), rj = 8 * (b0 + idx) + (lane >> 2);
+                                    double a0 = 0.0, a1 = 0.0;
+                                    for (int ks = 0; ks < 2; ks++) {
+                                        const int cc = c0 + 4 * ks + (lane & 3);
+                                        const double av = (ri < NX) ? s.Hxx[ri * NX + cc] : (ri == NX ? s.yv[cc] : 0.0);
+                                        const double bv = (rj < NX) ? s.Hxx[rj * NX + cc] : 0.0;
+                                        CERB_DMMA(a0, a1, av, bv, a0, a1);
+                                    }
+                                    const int cj = 8 * (b0 + idx) + 2 * (lane & 3);
+                                    if (ri < NX) {
+                                        if (cj <= ri && cj < NX) s.Hxx[ri * NX + cj] -= a0;
+                                        if (cj + 1 <= ri && cj + 1 < NX) s.Hxx[ri * NX + cj + 1] -= a1;
+                                    } else if (ri == NX) {
+                                        if (cj < NX) s.yv[cj] -= a0;
+                                        if (cj + 1 < NX) s.yv[cj + 1] -= a1;
+                                    }
+                                }
+                            }
                             __syncthreads();
                         }
-                        __syncthreads();
                     }
-                    // ---- back substitution L^T y_x = z by warp 0 (column oriented) -------------------------------------
+                    PH_MARK(10);
+                    // ---- back substitution L^T y_x = z by warp 0: lane holds y[lane], y[lane + 32], y[lane + 64] in registers --------------
                     if (tid < 32) {
-                        for (int k = NX - 1; k >= 0; k--) {
-                            if (tid == 0) s.yv[k] /= s.Hxx[k * NX + k];
-                            __syncwarp();
-                            const double yk = s.yv[k];
-                            for (int i = tid; i < k; i += 32) s.yv[i] -= s.Hxx[k * NX + i] * yk;
-                            __syncwarp();
+                        double y0 = s.yv[tid], y1 = s.yv[32 + tid], y2 = (64 + tid < NX) ? s.yv[64 + tid] : 0.0;
+                        for (int k = NX - 1; k >= 64; k--) {
+                            const double yk = __shfl_sync(0xffffffffu, y2, k - 64) * s.idx[k];
+                            const double *Lk = s.Hxx + k * NX;
+                            if (tid == k - 64) y2 = yk; else if (64 + tid < k) y2 -= Lk[64 + tid] * yk;
+                            y1 -= Lk[32 + tid] * yk; y0 -= Lk[tid] * yk;
                         }
+                        for (int k = 63; k >= 32; k--) {
+                            const double yk = __shfl_sync(0xffffffffu, y1, k - 32) * s.idx[k];
+                            const double *Lk = s.Hxx + k * NX;
+                            if (tid == k - 32) y1 = yk; else if (32 + tid < k) y1 -= Lk[32 + tid] * yk;
+                            y0 -= Lk[tid] * yk;
+                        }
+                        for (int k = 31; k >= 0; k--) {
+                            const double yk = __shfl_sync(0xffffffffu, y0, k) * s.idx[k];
+                            const double *Lk = s.Hxx + k * NX;
+                            if (tid == k) y0 = yk; else if (tid < k) y0 -= Lk[tid] * yk;
+                        }
+                        s.yv[tid] = y0; s.yv[32 + tid] = y1; if (64 + tid < NX) s.yv[64 + tid] = y2;
                     }
                     __syncthreads();
+                    PH_MARK(11);
                     // ---- y part: u = gy' - T^T y_x, then L^T y_y = u blockwise (warp 0) ------------------------------------
                     for (int q = tid; q < NY; q += SOLVE_THREADS) { double t = 0.0; for (int a = 0; a < NX; a++) t += s.Hxy[a * NY + q] * s.yv[a]; s.yv[NX + q] -= t; }
                     __syncthreads();
@@ -799,6 +938,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                         }
                     }
                     __syncthreads();
+                    PH_MARK(12);
                     // ---- inverse depths: y_l = (gl - w^T y_x) / (h + mu D^2) ; validity ---------------------------------------
                     double bad = 0.0;
                     for (int f = tid; f < nF; f += SOLVE_THREADS) {
@@ -811,6 +951,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                     for (int k = tid; k < NR; k += SOLVE_THREADS) if (!(fabs(s.yv[k]) < 1e300)) bad = 1.0;
                     if (bad != 0.0) sca[S_OK] = 0;          // benign race: every writer stores 0
                     __syncthreads();
+                    PH_MARK(13);
                 }
                 if (sca[S_OK] != 0.0) {
                     // gauss_newton_step = -D * y ; norms for the dogleg
@@ -885,11 +1026,16 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
             }
             __syncthreads();
             // =============================== candidate point and its cost ===================================
+            PH_MARK(14);
             apply_plus(s, s.stp, lam, stl, lamc, nF, ex_open, td_open, tid);
             load_geometry(s.xc, s, tid);
             {
                 double part[2];
-                part[0] = vision_cost(P, s, w, s.xc, lamc, tid) + inertial_cost(P, s, w, s.xc, tid) + prior_residual(P, s, w, s.xc, tid);
+                PH_MARK(15);
+                part[0] = vision_cost(P, s, w, s.xc, lamc, tid);
+                PH_MARK(16);
+                part[0] += inertial_cost(P, s, w, s.xc, tid) + prior_residual(P, s, w, s.xc, tid);
+                PH_MARK(17);
                 part[1] = ambient_sq(s.xs, s.xc, lam, lamc, nF, ex_open, lb_open, td_open, tid);
                 double tot[2];
                 block_sum<2>(part, s.red, tot, tid);
@@ -929,6 +1075,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 __syncthreads();
                 need_linearize = true;
             }
+            PH_MARK(18);
         }
         // ---- write back ---------------------------------------------------------------------------------
         for (int k = tid; k < ST_SIZE; k += SOLVE_THREADS) P.state[(size_t)w * ST_STRIDE + k] = s.xs[k];

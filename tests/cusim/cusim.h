@@ -53,6 +53,16 @@ inline void cusim_dmma(double &d0, double &d1, double a, double b, double c0, do
     d0 = x0; d1 = x1;
 }
 #define CERB_DMMA(d0, d1, a, b, c0, c1) cusim_dmma(d0, d1, a, b, c0, c1)
+// warp shuffle (all 32 threads of the simulated warp must call it, like the full-mask CUDA form)
+inline double __shfl_sync(unsigned, double v, int src) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sc = cusim::warp_scratch + warp * 64;
+    sc[lane] = v;
+    __syncwarp();
+    const double r = sc[src & 31];
+    __syncwarp();
+    return r;
+}
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline void __threadfence() {}
