@@ -43,6 +43,7 @@ struct CerbHandle {
     // pinned staging
     int *h_nfeat = nullptr, *h_fstart = nullptr, *h_fnobs = nullptr, *h_foff = nullptr, *h_flags = nullptr, *h_stereo = nullptr, *h_pmeta = nullptr, *h_repi = nullptr;
     double *h_obs = nullptr, *h_pre = nullptr, *h_pJ = nullptr, *h_pr = nullptr, *h_px0 = nullptr, *h_state = nullptr, *h_lam = nullptr, *h_repd = nullptr, *h_dbg = nullptr;
+    std::vector<int> h_perm;          // [B][F] device feature slot -> index in the caller's feature array (tracks are sorted by anchor frame on the device)
     long ws_stride = 0;
     size_t smem_bytes = 0;
 };
@@ -114,6 +115,7 @@ int cerb_create(const CerbSolverConfig *cfg, CerbHandle **out) {
     CUDA_TRY(hmalloc(&h->h_flags, B)); CUDA_TRY(hmalloc(&h->h_stereo, B * O)); CUDA_TRY(hmalloc(&h->h_pmeta, B * PRIOR_META_STRIDE)); CUDA_TRY(hmalloc(&h->h_repi, B * 4));
     CUDA_TRY(hmalloc(&h->h_obs, B * NOBS_PLANES * O)); CUDA_TRY(hmalloc(&h->h_pre, B * 10 * PRE_STRIDE));
     CUDA_TRY(hmalloc(&h->h_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_pr, B * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_px0, B * 16 * 9));
+    h->h_perm.assign(B * F, 0);
     CUDA_TRY(hmalloc(&h->h_state, B * ST_STRIDE)); CUDA_TRY(hmalloc(&h->h_lam, B * F)); CUDA_TRY(hmalloc(&h->h_repd, B * 2)); CUDA_TRY(hmalloc(&h->h_dbg, 2 * (NR + F) + 8));
     CUDA_TRY(cudaMemcpy(h->d_G, cfg->g, 3 * sizeof(double), cudaMemcpyHostToDevice));
     *out = h;
@@ -204,12 +206,22 @@ static int pack_window(CerbHandle *h, int w, const CerbWindowDesc &d, const Cerb
     if ((d.n_features && (!d.features || !d.obs || !st.para_Feature)) || (!d.preint && !d.imu_preint)) return fail(CERB_ERR_BAD_ARGUMENT, "window: null pointer");
     h->h_nfeat[w] = d.n_features;
     h->h_flags[w] = (d.extrinsic_open ? 1 : 0) | (d.td_open ? 2 : 0) | (d.preint ? 0 : 4);      // bit2: USE_LEG == 0, no leg-bias blocks
+    // Device order: tracks sorted by anchor frame (stable counting sort), so that the solver's feature chunks share one anchor.
+    // The reference's f_manager.feature list is already in first-seen order (feature_manager.cpp:60-92); arbitrary orders are accepted.
+    int cnt[CERB_NUM_FRAMES + 1] = {0};
     for (int f = 0; f < d.n_features; f++) {
         const CerbFeature &ft = d.features[f];
         if (ft.start_frame < 0 || ft.n_obs < 1 || ft.start_frame + ft.n_obs > CERB_NUM_FRAMES || ft.obs_offset < 0 || ft.obs_offset + ft.n_obs > d.n_obs)
             return fail(CERB_ERR_BAD_ARGUMENT, "window: malformed feature track");
-        h->h_fstart[(size_t)w * F + f] = ft.start_frame; h->h_fnobs[(size_t)w * F + f] = ft.n_obs; h->h_foff[(size_t)w * F + f] = ft.obs_offset;
-        h->h_lam[(size_t)w * F + f] = st.para_Feature[f];
+        cnt[ft.start_frame + 1]++;
+    }
+    for (int a = 0; a < CERB_NUM_FRAMES; a++) cnt[a + 1] += cnt[a];
+    int *perm = h->h_perm.data() + (size_t)w * F;
+    for (int f = 0; f < d.n_features; f++) perm[cnt[d.features[f].start_frame]++] = f;
+    for (int k = 0; k < d.n_features; k++) {
+        const CerbFeature &ft = d.features[perm[k]];
+        h->h_fstart[(size_t)w * F + k] = ft.start_frame; h->h_fnobs[(size_t)w * F + k] = ft.n_obs; h->h_foff[(size_t)w * F + k] = ft.obs_offset;
+        h->h_lam[(size_t)w * F + k] = st.para_Feature[perm[k]];
     }
     double *ob = h->h_obs + (size_t)w * NOBS_PLANES * O;
     int *sto = h->h_stereo + (size_t)w * O;
@@ -337,7 +349,7 @@ static int download(CerbHandle *h, CerbWindowState *states, CerbSolveReport *rep
             std::memcpy(st.para_Ex_Pose, q + ST_EX, sizeof(st.para_Ex_Pose));
             st.para_Td[0] = q[ST_TD];
             const int nf = h->h_nfeat[w];
-            if (st.para_Feature) for (int f = 0; f < nf; f++) st.para_Feature[f] = h->h_lam[(size_t)w * F + f];
+            if (st.para_Feature) { const int *perm = h->h_perm.data() + (size_t)w * F; for (int k = 0; k < nf; k++) st.para_Feature[perm[k]] = h->h_lam[(size_t)w * F + k]; }
         }
         if (reports) {
             CerbSolveReport &r = reports[w];
@@ -423,10 +435,11 @@ int cerb_debug_linearize(CerbHandle *h, int32_t w, double *cost, double *gradien
     CUDA_TRY(cudaMemcpyAsync(h->h_dbg, h->d_dbg, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (cost) *cost = h->h_dbg[0];
+    const int *perm = h->h_perm.data() + (size_t)w * F;
     for (int k = 0; k < NR + nf; k++) {
-        const int src = k < NR ? k : NR + (k - NR);
-        if (gradient) gradient[k] = h->h_dbg[1 + src];
-        if (jtj_diag) jtj_diag[k] = h->h_dbg[1 + NR + F + src];
+        const int dst = k < NR ? k : NR + perm[k - NR];          // device feature slot -> caller's feature index
+        if (gradient) gradient[dst] = h->h_dbg[1 + k];
+        if (jtj_diag) jtj_diag[dst] = h->h_dbg[1 + NR + F + k];
     }
     return CERB_OK;
 }

@@ -153,147 +153,205 @@ CERB_D double vision_cost(const SolveParams &P, const Smem &s, int w, const doub
 }
 
 // ---- visual part: linearisation.  Accumulates the upper triangle of Hxx, g_x, writes W, hh, gl (global) ----
+// Features are processed in chunks of <= 64 consecutive tracks that share one anchor frame a (the host sorts the tracks by
+// anchor; `chunks` = [n, c0_0, c0_1, ..., nF] is built once per window).  A pass covers two frames: thread (jj, cam, fl)
+// evaluates the factor of feature c0 + fl in frame j0 + jj seen by camera `cam` (K1 / K2, or K3 for the anchor frame) and
+// writes its two Huber-corrected Jacobian rows into a column-major tile T[26][VT_LD]:
+//     physical columns  0..5 pose_a | 6 td | 7 residual | 8..13 pose_j | 14..19 ex0 | 20..25 ex1
+// The Gram matrix of the tile is a dense contraction and runs on the fp64 tensor cores: warp (jj, cam, feature half) contracts
+// its 64 rows over the four 8-wide column groups g0 = [pose_a, td, r], g1 = [pose_j, 0, 0], g2 = [ex0, 0, 0], g3 = [ex1, 0, 0].
+// Blocks that do not involve g1 have a destination that is independent of the frame and are accumulated per warp in shared
+// memory over all passes of the chunk; the four g1 blocks are reduced over the warps of a frame and scattered after every
+// pass.  Blocks that are structurally zero are skipped: g3 for camera 0 (K1 has no ex1 columns), g1 for the anchor frame (K3).
 // prescale: write W, hh, gl already multiplied by the Jacobi scales (s.sc for x, sl for the inverse depths), which are
 // fixed after iteration 0 -- saves a read-modify-write pass over W per linearisation.
+enum { VT_LD = 516, VT_COLS = 26, VT_SZ = VT_COLS * VT_LD, VP_SZ = 6 * 64, VJ_SZ = 4 * 64 };
+struct ObsVals { double px, py, vx, vy, td; int stereo; };
+CERB_D void obs_fetch(const double *obs, const int *stereo, int mo, int o, int cam, ObsVals &v) {
+    v.px = obs[(cam ? 4 : 0) * mo + o]; v.py = obs[(cam ? 5 : 1) * mo + o]; v.vx = obs[(cam ? 6 : 2) * mo + o]; v.vy = obs[(cam ? 7 : 3) * mo + o];
+    v.td = obs[8 * mo + o]; v.stereo = stereo[o];
+}
+// destination of local column c (0..7) of group g in the x numbering; -1: padding, -2: the residual column (gradient)
+CERB_D int vis_col_dest(int g, int c, int a, int j) {
+    if (g == 0) return c < 6 ? 6 * a + c : (c == 6 ? X_TD : -2);
+    if (c >= 6) return -1;
+    return g == 1 ? 6 * j + c : (g == 2 ? 66 + c : 72 + c);
+}
+CERB_D void vis_scatter(Smem &s, int ga, int gb, int ra, int rb, int a, int j, double v) {
+    if (ga == gb && ra > rb) return;
+    const int da = vis_col_dest(ga, ra, a, j), db = vis_col_dest(gb, rb, a, j);
+    if (da == -1 || db == -1) return;                                  // padding columns
+    if (da == -2) { if (db >= 0) s.g[db] += v; return; }               // (r, c): gradient of c; (r, r) is the cost, summed elsewhere
+    if (db == -2) { s.g[da] += v; return; }
+    if (da <= db) s.Hxx[da * NX + db] += v; else s.Hxx[db * NX + da] += v;
+}
 CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const double *x, const double *lam, double *W, double *hh, double *gl,
-                               const double *sl, bool prescale, int tid) {
-    const int nF = P.n_features[w], F = P.maxF;
+                               const double *sl, bool prescale, const int *chunks, int tid) {
+    const int nF = P.n_features[w], F = P.maxF, mo = P.maxObs;
     const double *obs = P.obs + (size_t)w * NOBS_PLANES * P.maxObs;
     const int *stereo = P.obs_stereo + (size_t)w * P.maxObs;
     double cost = 0.0;
     PH_DECL();
     for (int i = tid; i < NX * nF; i += SOLVE_THREADS) W[(i / nF) * F + (i % nF)] = 0.0;
-    for (int c0 = 0; c0 < nF; c0 += FT) {
-        const int fl = tid & (FT - 1), cam = (tid >> 6) & 1;
+    __syncthreads();                                                    // the passes below overwrite / add to rows of W
+    const int wid = tid >> 5, lane = tid & 31;
+    const int jj = tid >> 7, cam = (tid >> 6) & 1, fl = tid & 63;
+    double *T = s.tile;
+    double *jp = s.Ju;                                                  // [8 warps][4 blocks][64]  frame-dependent partial blocks
+    double *pp = (wid < 5) ? s.Ju + 8 * VJ_SZ + VP_SZ * wid : s.tile + VT_SZ + VP_SZ * (wid - 5);     // [6 blocks][64] of this warp
+    // fragment sources of this lane: group g, local column lane / 4 -> physical column (or none)
+    const int c8 = lane >> 2;
+    const double *tq[4];
+    bool tv[4];
+    for (int g = 0; g < 4; g++) { const int pc = g == 0 ? c8 : 8 + 6 * (g - 1) + c8; tv[g] = (g == 0) || c8 < 6; tq[g] = T + (tv[g] ? pc : 0) * VT_LD + (lane & 3); }
+    const int nchunks = chunks[0];
+    for (int ch = 0; ch < nchunks; ch++) {
+        const int c0 = chunks[1 + ch], nc = chunks[2 + ch] - c0;
+        const int a = P.feat_start[(size_t)w * F + c0];
         const int f = c0 + fl;
-        const bool ev = (tid < 2 * FT) && (f < nF);
-        ObsCtx c; c.start = 0; c.nobs = 0; c.off = 0; c.lam = 1.0; c.pix = c.piy = c.vix = c.viy = c.tdi = 0.0;
+        const bool ev = fl < nc;
+        int nobs = 0, off = 0;
+        double lamf = 1.0, pix = 0.0, piy = 0.0, vix = 0.0, viy = 0.0, tdi = 0.0;
         const double slf = (prescale && ev) ? sl[f] : 1.0;
         if (ev) {
-            c.start = P.feat_start[(size_t)w * F + f]; c.nobs = P.feat_nobs[(size_t)w * F + f]; c.off = P.feat_off[(size_t)w * F + f];
-            c.lam = lam[f];
-            c.pix = obs[0 * P.maxObs + c.off]; c.piy = obs[1 * P.maxObs + c.off]; c.vix = obs[2 * P.maxObs + c.off]; c.viy = obs[3 * P.maxObs + c.off];
-            c.tdi = obs[8 * P.maxObs + c.off];
+            nobs = P.feat_nobs[(size_t)w * F + f]; off = P.feat_off[(size_t)w * F + f];
+            lamf = lam[f];
+            pix = obs[0 * mo + off]; piy = obs[1 * mo + off]; vix = obs[2 * mo + off]; viy = obs[3 * mo + off]; tdi = obs[8 * mo + off];
         }
-        if (tid < 2 * FT) s.ti[tid] = ev ? c.start : 127;
-        __syncthreads();
-        if (tid == 0) {   // anchor range of the chunk
-            int lo = 127, hi = -1;
-            for (int k = 0; k < FT; k++) { const int a = s.ti[k]; if (a != 127) { lo = a < lo ? a : lo; hi = a > hi ? a : hi; } }
-            s.ti[128] = lo; s.ti[129] = hi;
-        }
+        for (int k = lane; k < VP_SZ; k += 32) pp[k] = 0.0;
         double h = 0.0, gq = 0.0, wT = 0.0, wI[6], wE0[6], wE1[6];
         for (int k = 0; k < 6; k++) { wI[k] = 0.0; wE0[k] = 0.0; wE1[k] = 0.0; }
-        __syncthreads();
-        const int amin = s.ti[128], amax = s.ti[129];
+        ObsVals ov; ov.px = ov.py = ov.vx = ov.vy = ov.td = 0.0; ov.stereo = 0;
+        { const int j = a + jj; if (ev && j < a + nobs) obs_fetch(obs, stereo, mo, off + (j - a), cam, ov); }
+        const int nvalid = nc - 32 * (wid & 1);                          // valid features among the 32 of this warp
         PH_MARK(20);
-        for (int j = 0; j < NFR; j++) {
-            // --- evaluate the factors of frame j into the tile -------------------------------------------------
-            if (tid < 2 * FT) {
-                double *row0 = s.tile + tid * TILE_LD, *row1 = row0 + 128 * TILE_LD;      // factor tid owns rows tid and tid + 128
-                double r[2]; ProjJac J;
-                double wjv[6] = {0, 0, 0, 0, 0, 0};
-                if (ev && eval_obs(P, s, x, obs, stereo, c, j, cam, r, &J)) {
-                    double cf; const double hw = huber_weight(P.huber, r[0] * r[0] + r[1] * r[1], &cf);
-                    cost += cf;
-                    for (int k = 0; k < 6; k++) {
-                        row0[k] = hw * J.Ji[k]; row1[k] = hw * J.Ji[6 + k];
-                        row0[6 + k] = hw * J.Jj[k]; row1[6 + k] = hw * J.Jj[6 + k];
-                        row0[12 + k] = hw * J.Je0[k]; row1[12 + k] = hw * J.Je0[6 + k];
-                        row0[18 + k] = hw * J.Je1[k]; row1[18 + k] = hw * J.Je1[6 + k];
-                    }
-                    row0[24] = hw * J.Jtd[0]; row1[24] = hw * J.Jtd[1];          // d r / d td
-                    row0[25] = hw * r[0]; row1[25] = hw * r[1];
-                    for (int k = 26; k < 32; k++) { row0[k] = 0.0; row1[k] = 0.0; }
-                    const double l0 = hw * J.Jl[0], l1 = hw * J.Jl[1];
-                    h += l0 * l0 + l1 * l1; gq += l0 * row0[25] + l1 * row1[25];
-                    wT += row0[24] * l0 + row1[24] * l1;
-                    for (int k = 0; k < 6; k++) {
-                        wI[k] += row0[k] * l0 + row1[k] * l1;
-                        wjv[k] = row0[6 + k] * l0 + row1[6 + k] * l1;
-                        wE0[k] += row0[12 + k] * l0 + row1[12 + k] * l1;
-                        wE1[k] += row0[18 + k] * l0 + row1[18 + k] * l1;
-                    }
-                } else {
-                    for (int k = 0; k < 32; k++) { row0[k] = 0.0; row1[k] = 0.0; }
-                }
-                for (int k = 0; k < 6; k++) s.wj[tid * 8 + k] = wjv[k];
+        for (int j0 = a; j0 < NFR; j0 += 2) {
+            const int j = j0 + jj;
+            // --- evaluate this thread's factor into the tile -----------------------------------------------------------
+            bool valid = ev && j < a + nobs;
+            int kind = PROJ_K1;
+            if (valid) {
+                if (j == a) { if (cam == 0 || !ov.stereo) valid = false; kind = PROJ_K3; }
+                else if (cam == 1) { if (!ov.stereo) valid = false; kind = PROJ_K2; }
             }
+            double wjv[6] = {0, 0, 0, 0, 0, 0};
+            double *t0 = T + tid, *t1 = T + 256 + tid;
+            if (valid) {
+                double r[2]; ProjJac J;
+                proj_eval(kind, ldm33(s.Rw + 9 * a), ld3(x + ST_POSE + 7 * a), ldm33(s.Rw + 9 * j), ld3(x + ST_POSE + 7 * j),
+                          ldm33(s.Rex), ld3(x + ST_EX), ldm33(s.Rex + 9), ld3(x + ST_EX + 7), lamf, x[ST_TD], pix, piy, ov.px, ov.py,
+                          vix, viy, ov.vx, ov.vy, tdi, ov.td, P.sqrt_info, r, &J);
+                double cf; const double hw = huber_weight(P.huber, r[0] * r[0] + r[1] * r[1], &cf);
+                cost += cf;
+                const double r0 = hw * r[0], r1 = hw * r[1], l0 = hw * J.Jl[0], l1 = hw * J.Jl[1], d0 = hw * J.Jtd[0], d1 = hw * J.Jtd[1];
+                h += l0 * l0 + l1 * l1; gq += l0 * r0 + l1 * r1; wT += d0 * l0 + d1 * l1;
+                t0[6 * VT_LD] = d0; t1[6 * VT_LD] = d1; t0[7 * VT_LD] = r0; t1[7 * VT_LD] = r1;
+                for (int k = 0; k < 6; k++) {
+                    const double i0 = hw * J.Ji[k], i1 = hw * J.Ji[6 + k], q0 = hw * J.Jj[k], q1 = hw * J.Jj[6 + k];
+                    const double e0 = hw * J.Je0[k], e1 = hw * J.Je0[6 + k], u0 = hw * J.Je1[k], u1 = hw * J.Je1[6 + k];
+                    t0[k * VT_LD] = i0; t1[k * VT_LD] = i1; t0[(8 + k) * VT_LD] = q0; t1[(8 + k) * VT_LD] = q1;
+                    t0[(14 + k) * VT_LD] = e0; t1[(14 + k) * VT_LD] = e1; t0[(20 + k) * VT_LD] = u0; t1[(20 + k) * VT_LD] = u1;
+                    wI[k] += i0 * l0 + i1 * l1; wjv[k] = q0 * l0 + q1 * l1; wE0[k] += e0 * l0 + e1 * l1; wE1[k] += u0 * l0 + u1 * l1;
+                }
+            } else {
+                for (int k = 0; k < VT_COLS; k++) { t0[k * VT_LD] = 0.0; t1[k * VT_LD] = 0.0; }
+            }
+            // W rows of frame j: camera 0 stores, camera 1 adds after the barrier (a K2 factor implies the K1 factor)
+            const bool wrow = valid && j != a;
+            if (wrow && cam == 0) for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] = wjv[k] * (prescale ? s.sc[6 * j + k] * slf : 1.0);
             __syncthreads();
             PH_MARK(21);
-            // --- W rows of frame j: sum of the two cameras -----------------------------------------------------
-            if (tid < FT && ev && j != c.start && j >= c.start && j < c.start + c.nobs)
-                for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] = (s.wj[tid * 8 + k] + s.wj[(tid + FT) * 8 + k]) * (prescale ? s.sc[6 * j + k] * slf : 1.0);
-            // --- J^T J of the tile on the fp64 tensor cores (mma.sync m8n8k4), one pass per anchor frame present.
-            // The tile is a (256 rows) x (32 cols: I 6 | J 6 | E0 6 | E1 6 | r | 0-pad) matrix T; the Gram matrix
-            // T^T T is cut into 8x8 blocks (10 upper ones); warp wid contracts rows [32 wid, 32 wid + 32), the eight
-            // partial results are summed through shared memory and scattered into Hxx / g.
+            if (wrow && cam == 1) for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] += wjv[k] * (prescale ? s.sc[6 * j + k] * slf : 1.0);
+            { const int jn = j + 2; ov.stereo = 0; if (ev && jn < a + nobs) obs_fetch(obs, stereo, mo, off + (jn - a), cam, ov); }     // prefetch the next pass
+            // --- Gram matrix of this warp's 64 rows ------------------------------------------------------------------------
             {
-                const int wid = tid >> 5, lane = tid & 31;
-                double *part = s.tile + 256 * TILE_LD;
-                for (int a = amin; a <= amax && a <= j; a++) {
-                    double acc[10][2];
-                    for (int k = 0; k < 10; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
-                    for (int ks = 0; ks < 8; ks++) {
-                        const int row = 32 * wid + 4 * ks + (lane & 3);
-                        const bool on = (s.ti[row & 127] == a);
-                        const double *q = s.tile + row * TILE_LD + (lane >> 2);
-                        const double v0 = on ? q[0] : 0.0, v1 = on ? q[8] : 0.0, v2 = on ? q[16] : 0.0, v3 = on ? q[24] : 0.0;
-                        CERB_DMMA(acc[0][0], acc[0][1], v0, v0, acc[0][0], acc[0][1]);
-                        CERB_DMMA(acc[1][0], acc[1][1], v0, v1, acc[1][0], acc[1][1]);
-                        CERB_DMMA(acc[2][0], acc[2][1], v0, v2, acc[2][0], acc[2][1]);
-                        CERB_DMMA(acc[3][0], acc[3][1], v0, v3, acc[3][0], acc[3][1]);
-                        CERB_DMMA(acc[4][0], acc[4][1], v1, v1, acc[4][0], acc[4][1]);
-                        CERB_DMMA(acc[5][0], acc[5][1], v1, v2, acc[5][0], acc[5][1]);
-                        CERB_DMMA(acc[6][0], acc[6][1], v1, v3, acc[6][0], acc[6][1]);
-                        CERB_DMMA(acc[7][0], acc[7][1], v2, v2, acc[7][0], acc[7][1]);
-                        CERB_DMMA(acc[8][0], acc[8][1], v2, v3, acc[8][0], acc[8][1]);
-                        CERB_DMMA(acc[9][0], acc[9][1], v3, v3, acc[9][0], acc[9][1]);
-                    }
-                    for (int k = 0; k < 10; k++) {
-                        double *o = part + wid * 640 + k * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
-                        o[0] = acc[k][0]; o[1] = acc[k][1];
-                    }
-                    __syncthreads();
-                    PH_MARK(22);
-                    for (int e = tid; e < 640; e += SOLVE_THREADS) {
-                        const int k = e >> 6, r = (e >> 3) & 7, c = e & 7;
-                        const int mi = k < 4 ? 0 : (k < 7 ? 1 : (k < 9 ? 2 : 3));
-                        const int ni = k < 4 ? k : (k < 7 ? k - 3 : (k < 9 ? k - 5 : 3));
-                        const int la = 8 * mi + r, lb = 8 * ni + c;
-                        if (la > lb || lb > 25 || la == 25) continue;
-                        if (a == j && la < 12) continue;                  // anchor-frame rows (K3) have no pose columns
-                        double accv = 0.0;
-                        for (int wq = 0; wq < 8; wq++) accv += part[wq * 640 + e];
-                        // local column -> x index: I 0..5 | J 6..11 | E0, E1 12..23 | td 24 ; column 25 is the residual
-                        const int ga = la < 6 ? 6 * a + la : (la < 12 ? 6 * j + la - 6 : (la < 24 ? 66 + la - 12 : X_TD));
-                        if (lb == 25) s.g[ga] += accv;
-                        else {
-                            const int gb = lb < 6 ? 6 * a + lb : (lb < 12 ? 6 * j + lb - 6 : (lb < 24 ? 66 + lb - 12 : X_TD));
-                            s.Hxx[ga * NX + gb] += accv;
+                const int jw = j0 + (wid >> 2), camw = (wid >> 1) & 1;
+                const bool k3 = (jw == a);
+                const bool work = jw < NFR && nvalid > 0 && !(k3 && camw == 0);
+                const bool use1 = !k3, use3 = camw == 1;
+                double acc[10][2];
+                for (int k = 0; k < 10; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
+                if (work) {
+                    const int nks = nvalid >= 32 ? 8 : (nvalid + 3) >> 2;
+                    for (int half = 0; half < 2; half++) {
+                        const int rb = 256 * half + 32 * wid;
+                        for (int ks = 0; ks < nks; ks++) {
+                            const int ro = rb + 4 * ks;
+                            const double v0 = tq[0][ro], v2 = tv[2] ? tq[2][ro] : 0.0;
+                            CERB_DMMA(acc[0][0], acc[0][1], v0, v0, acc[0][0], acc[0][1]);
+                            CERB_DMMA(acc[2][0], acc[2][1], v0, v2, acc[2][0], acc[2][1]);
+                            CERB_DMMA(acc[7][0], acc[7][1], v2, v2, acc[7][0], acc[7][1]);
+                            if (use1) {
+                                const double v1 = tv[1] ? tq[1][ro] : 0.0;
+                                CERB_DMMA(acc[1][0], acc[1][1], v0, v1, acc[1][0], acc[1][1]);
+                                CERB_DMMA(acc[4][0], acc[4][1], v1, v1, acc[4][0], acc[4][1]);
+                                CERB_DMMA(acc[5][0], acc[5][1], v1, v2, acc[5][0], acc[5][1]);
+                                if (use3) { const double v3 = tv[3] ? tq[3][ro] : 0.0; CERB_DMMA(acc[6][0], acc[6][1], v1, v3, acc[6][0], acc[6][1]); }
+                            }
+                            if (use3) {
+                                const double v3 = tv[3] ? tq[3][ro] : 0.0;
+                                CERB_DMMA(acc[3][0], acc[3][1], v0, v3, acc[3][0], acc[3][1]);
+                                CERB_DMMA(acc[8][0], acc[8][1], v2, v3, acc[8][0], acc[8][1]);
+                                CERB_DMMA(acc[9][0], acc[9][1], v3, v3, acc[9][0], acc[9][1]);
+                            }
                         }
                     }
-                    __syncthreads();
-                    PH_MARK(23);
+                    const int o = (lane >> 2) * 8 + 2 * (lane & 3);
+                    pp[0 * 64 + o] += acc[0][0]; pp[0 * 64 + o + 1] += acc[0][1];      // (g0, g0)
+                    pp[1 * 64 + o] += acc[2][0]; pp[1 * 64 + o + 1] += acc[2][1];      // (g0, g2)
+                    pp[3 * 64 + o] += acc[7][0]; pp[3 * 64 + o + 1] += acc[7][1];      // (g2, g2)
+                    if (use3) {
+                        pp[2 * 64 + o] += acc[3][0]; pp[2 * 64 + o + 1] += acc[3][1];  // (g0, g3)
+                        pp[4 * 64 + o] += acc[8][0]; pp[4 * 64 + o + 1] += acc[8][1];  // (g2, g3)
+                        pp[5 * 64 + o] += acc[9][0]; pp[5 * 64 + o + 1] += acc[9][1];  // (g3, g3)
+                    }
+                }
+                {
+                    const int o = wid * VJ_SZ + (lane >> 2) * 8 + 2 * (lane & 3);
+                    jp[o] = acc[1][0]; jp[o + 1] = acc[1][1];                           // (g0, g1)
+                    jp[64 + o] = acc[4][0]; jp[64 + o + 1] = acc[4][1];                 // (g1, g1)
+                    jp[128 + o] = acc[5][0]; jp[128 + o + 1] = acc[5][1];               // (g1, g2)
+                    jp[192 + o] = acc[6][0]; jp[192 + o + 1] = acc[6][1];               // (g1, g3)
                 }
             }
             __syncthreads();
-        }
-        // --- per-feature lambda blocks: h, g_lambda, W rows of the anchor pose and the extrinsics --------------
-        if (tid >= FT && tid < 2 * FT) {
-            double *q = s.tile + (tid - FT) * 24;
-            q[0] = h; q[1] = gq; q[20] = wT;
-            for (int k = 0; k < 6; k++) { q[2 + k] = wI[k]; q[8 + k] = wE0[k]; q[14 + k] = wE1[k]; }
+            PH_MARK(22);
+            // --- frame-dependent blocks: sum over the four warps of each frame (fixed order) and scatter ----------------------------
+            for (int e = tid; e < 2 * VJ_SZ; e += SOLVE_THREADS) {
+                const int fj = e >> 8, el = e & 255, blk = el >> 6, ra = (el >> 3) & 7, rb = el & 7;
+                const int jf = j0 + fj;
+                if (jf >= NFR || jf == a) continue;
+                const double *q = jp + (4 * fj) * VJ_SZ + el;
+                const double v = ((q[0] + q[VJ_SZ]) + q[2 * VJ_SZ]) + q[3 * VJ_SZ];
+                vis_scatter(s, blk == 0 ? 0 : 1, blk == 0 ? 1 : blk, ra, rb, a, jf, v);
+            }
+            PH_MARK(23);
         }
         __syncthreads();
-        if (tid < FT && ev) {
-            const double *q = s.tile + tid * 24;
-            hh[f] = (h + q[0]) * slf * slf; gl[f] = (gq + q[1]) * slf;
-            W[(size_t)X_TD * F + f] = (wT + q[20]) * (prescale ? s.sc[X_TD] * slf : 1.0);
+        // --- end of the chunk: frame-independent blocks (sum over the 8 warps) and the per-feature lambda blocks ------------------------
+        {
+            double *ex = T;                                              // [21][256] exchange of the per-thread partial sums
+            ex[0 * 256 + tid] = h; ex[1 * 256 + tid] = gq; ex[2 * 256 + tid] = wT;
+            for (int k = 0; k < 6; k++) { ex[(3 + k) * 256 + tid] = wI[k]; ex[(9 + k) * 256 + tid] = wE0[k]; ex[(15 + k) * 256 + tid] = wE1[k]; }
+        }
+        __syncthreads();
+        for (int e = tid; e < VP_SZ; e += SOLVE_THREADS) {
+            double v = 0.0;
+            for (int wq = 0; wq < 8; wq++) v += ((wq < 5) ? s.Ju + 8 * VJ_SZ + VP_SZ * wq : s.tile + VT_SZ + VP_SZ * (wq - 5))[e];
+            const int blk = e >> 6, ra = (e >> 3) & 7, rb = e & 7;
+            const int ga = blk < 3 ? 0 : (blk < 5 ? 2 : 3), gb = blk == 0 ? 0 : (blk == 1 || blk == 3 ? 2 : 3);
+            vis_scatter(s, ga, gb, ra, rb, a, a, v);
+        }
+        if (tid < 64 && ev) {
+            const double *ex = T;
+            double q[21];
+            for (int k = 0; k < 21; k++) q[k] = ((ex[k * 256 + tid] + ex[k * 256 + 64 + tid]) + ex[k * 256 + 128 + tid]) + ex[k * 256 + 192 + tid];
+            hh[f] = q[0] * slf * slf; gl[f] = q[1] * slf;
+            W[(size_t)X_TD * F + f] = q[2] * (prescale ? s.sc[X_TD] * slf : 1.0);
             for (int k = 0; k < 6; k++) {
-                W[(size_t)(6 * c.start + k) * F + f] = (wI[k] + q[2 + k]) * (prescale ? s.sc[6 * c.start + k] * slf : 1.0);
-                W[(size_t)(66 + k) * F + f] = (wE0[k] + q[8 + k]) * (prescale ? s.sc[66 + k] * slf : 1.0);
-                W[(size_t)(72 + k) * F + f] = (wE1[k] + q[14 + k]) * (prescale ? s.sc[72 + k] * slf : 1.0);
+                W[(size_t)(6 * a + k) * F + f] = q[3 + k] * (prescale ? s.sc[6 * a + k] * slf : 1.0);
+                W[(size_t)(66 + k) * F + f] = q[9 + k] * (prescale ? s.sc[66 + k] * slf : 1.0);
+                W[(size_t)(72 + k) * F + f] = q[15 + k] * (prescale ? s.sc[72 + k] * slf : 1.0);
             }
         }
         __syncthreads();
@@ -525,7 +583,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
     double *ws = P.ws + (size_t)blockIdx.x * P.ws_stride;
     double *W = ws + ws_W(F);
     double *hh = ws + ws_vecs(F), *gl = hh + F, *sl = gl + F, *Dl = sl + F, *ghl = Dl + F, *gnl = ghl + F, *stl = gnl + F, *lamc = stl + F;
-    double *bk = ws + ws_backup(F);
+    int *chunks = reinterpret_cast<int *>(ws + ws_backup(F));          // [0] n, [1..n] chunk starts, [n + 1] nF
     double *sca = s.sca;
     // scalar slots
     enum { S_RADIUS = 0, S_MU, S_REUSE, S_XCOST, S_CCOST, S_ALPHA, S_GNORM2, S_GNNORM2, S_GDOTGN, S_MODEL, S_STEPNORM, S_XNORM, S_DLNORM,
@@ -538,6 +596,17 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
         const bool lb_open = P.optimize_leg_bias && (P.flags[w] & 4) == 0;
         const bool td_open = (P.flags[w] & 2) != 0;
         double *lam = P.lam + (size_t)w * F;
+        if (tid == 0) {      // feature chunks: <= 64 consecutive tracks with the same anchor frame
+            int n = 0, c0 = 0;
+            while (c0 < nF) {
+                chunks[1 + n++] = c0;
+                const int a = P.feat_start[(size_t)w * F + c0];
+                int e = c0 + 1;
+                while (e < nF && e < c0 + 64 && P.feat_start[(size_t)w * F + e] == a) e++;
+                c0 = e;
+            }
+            chunks[1 + n] = nF; chunks[0] = n;
+        }
         for (int k = tid; k < ST_STRIDE; k += SOLVE_THREADS) s.xs[k] = (k < ST_SIZE) ? P.state[(size_t)w * ST_STRIDE + k] : 0.0;
         if (tid == 0) {
             sca[S_RADIUS] = P.radius0; sca[S_MU] = 1e-8; sca[S_REUSE] = 0; sca[S_DONE] = 0; sca[S_TERM] = 1; sca[S_ITER] = 0; sca[S_NSUCC] = 0;
@@ -555,7 +624,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                 load_geometry(s.xs, s, tid);
                 double part[2];
                 PH_MARK(0);
-                part[0] = vision_linearize(P, s, w, s.xs, lam, W, hh, gl, sl, iteration > 0, tid);
+                part[0] = vision_linearize(P, s, w, s.xs, lam, W, hh, gl, sl, iteration > 0, chunks, tid);
                 for (int k = tid; k < HXY_SZ; k += SOLVE_THREADS) s.Hxy[k] = 0.0;     // the tile aliased Hxy
                 for (int k = tid; k < 1859; k += SOLVE_THREADS) s.Ad[k] = 0.0;
                 for (int k = tid; k < 1690; k += SOLVE_THREADS) s.Bo[k] = 0.0;
@@ -674,37 +743,51 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                         const bool act = lane < NYB;
                         const int r = act ? lane : 0;              // idle lanes shadow row 0 and never store
                         double m[NYB];                             // row r of M_{f-1}
+                        _Pragma("unroll")
+                        for (int c = 0; c < NYB; c++) m[c] = 0.0;
+                        _Pragma("unroll 1")                        // keep the block body compact: it is re-used 11 times from the instruction cache
                         for (int f = 0; f < NFR; f++) {
                             double *A = s.Ad + f * 169;
-                            double a[NYB], invd[NYB];
+                            double a[NYB], invd[NYB], myinv = 1.0;
+                            _Pragma("unroll")
                             for (int c = 0; c < NYB; c++) a[c] = A[r * NYB + c];
                             if (f > 0) {
                                 const double *Mp = s.Bo + (f - 1) * 169;        // M[r][c], r: y_f index, c: y_{f-1} index
-                                for (int c = 0; c < NYB; c++) { double t = 0.0; for (int q = 0; q < NYB; q++) t += m[q] * Mp[c * NYB + q]; a[c] -= t; }
+                                _Pragma("unroll")
+                                for (int c = 0; c < NYB; c++) { double t = 0.0; _Pragma("unroll") for (int q = 0; q < NYB; q++) t += m[q] * Mp[c * NYB + q]; a[c] -= t; }
                             }
+                            PH_MARK(34);
+                            _Pragma("unroll")
                             for (int j = 0; j < NYB; j++) {                     // right-looking column sweep
                                 double d = __shfl_sync(0xffffffffu, a[j], j);
                                 if (!(d > 0.0)) { if (lane == 0) sca[S_OK] = 0; d = 1.0; }
                                 const double inv = rsqrt(d);
                                 invd[j] = inv;
+                                if (lane == j) myinv = inv;
                                 const double l = (lane == j) ? d * inv : a[j] * inv;
                                 a[j] = l;
+                                _Pragma("unroll")
                                 for (int k = j + 1; k < NYB; k++) { const double lk = __shfl_sync(0xffffffffu, l, k); a[k] -= l * lk; }
                             }
-                            if (act) { for (int c = 0; c < NYB; c++) if (c <= r) A[r * NYB + c] = a[c]; s.idg[NYB * f + r] = invd[r]; }
+                            PH_MARK(35);
+                            if (act) { _Pragma("unroll") for (int c = 0; c < NYB; c++) if (c <= r) A[r * NYB + c] = a[c]; s.idg[NYB * f + r] = myinv; }
                             __syncwarp();
                             if (f < NFR - 1) {
                                 double *B = s.Bo + f * 169;                     // in: B[k1][k2] = H(y_f[k1], y_{f+1}[k2]); out: M[r][c]
                                 double t[NYB];
+                                _Pragma("unroll")
                                 for (int c = 0; c < NYB; c++) t[c] = B[c * NYB + r];
+                                _Pragma("unroll")
                                 for (int c = 0; c < NYB; c++) {
                                     m[c] = t[c] * invd[c];
+                                    _Pragma("unroll")
                                     for (int c2 = c + 1; c2 < NYB; c2++) t[c2] -= m[c] * A[c2 * NYB + c];
                                 }
                                 __syncwarp();
-                                if (act) for (int c = 0; c < NYB; c++) B[r * NYB + c] = m[c];
+                                if (act) { _Pragma("unroll") for (int c = 0; c < NYB; c++) B[r * NYB + c] = m[c]; }
                                 __syncwarp();
                             }
+                            PH_MARK(36);
                         }
                         PH_MARK(6);
                     } else {
@@ -831,8 +914,10 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                                 const bool act = lane < nb;
                                 const int r = act ? lane : 0;
                                 double a[8];
+                                _Pragma("unroll")
                                 for (int c = 0; c < 8; c++) a[c] = (c < nb && c <= r) ? s.Hxx[(c0 + r) * NX + c0 + c] : 0.0;
                                 double myinv = 1.0;
+                                _Pragma("unroll")
                                 for (int j = 0; j < 8; j++) {
                                     double d = __shfl_sync(0xffffffffu, a[j], j);
                                     if (j < nb && !(d > 0.0)) { if (lane == 0) sca[S_OK] = 0; }
@@ -841,9 +926,11 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                                     if (lane == j) myinv = inv;
                                     const double l = (lane == j) ? d * inv : a[j] * inv;
                                     a[j] = l;
+                                    _Pragma("unroll")
                                     for (int k = j + 1; k < 8; k++) { const double lk = __shfl_sync(0xffffffffu, l, k); a[k] -= l * lk; }
                                 }
                                 if (act) {
+                                    _Pragma("unroll")
                                     for (int c = 0; c < 8; c++) if (c <= r) { s.Hxx[(c0 + r) * NX + c0 + c] = a[c]; Lkk[r * 8 + c] = a[c]; }
                                     Lkk[64 + r] = myinv; s.idx[c0 + r] = myinv;
                                 }
@@ -854,12 +941,17 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                                 const int i = c1 + tid;
                                 double *row = (i < NX) ? s.Hxx + i * NX + c0 : s.yv + c0;
                                 double t[8];
+                                _Pragma("unroll")
                                 for (int c = 0; c < 8; c++) t[c] = (c < nb) ? row[c] : 0.0;
+                                _Pragma("unroll")
                                 for (int c = 0; c < 8; c++) {
-                                    if (c >= nb) break;
-                                    t[c] *= Lkk[64 + c];
-                                    for (int c2 = c + 1; c2 < 8; c2++) if (c2 < nb) t[c2] -= t[c] * Lkk[c2 * 8 + c];
+                                    if (c < nb) {
+                                        t[c] *= Lkk[64 + c];
+                                        _Pragma("unroll")
+                                        for (int c2 = c + 1; c2 < 8; c2++) if (c2 < nb) t[c2] -= t[c] * Lkk[c2 * 8 + c];
+                                    }
                                 }
+                                _Pragma("unroll")
                                 for (int c = 0; c < 8; c++) if (c < nb) row[c] = t[c];
                             }
                             __syncthreads();
@@ -893,26 +985,23 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                         }
                     }
                     PH_MARK(10);
-                    // ---- back substitution L^T y_x = z by warp 0: lane holds y[lane], y[lane + 32], y[lane + 64] in registers --------------
+                    // ---- back substitution L^T y_x = z by warp 0: lane holds y[lane], y[lane + 32], y[lane + 64] in registers;
+                    // branch-free steps (selects), the L entries of the next step are loaded before the current shuffle completes ----
                     if (tid < 32) {
                         double y0 = s.yv[tid], y1 = s.yv[32 + tid], y2 = (64 + tid < NX) ? s.yv[64 + tid] : 0.0;
-                        for (int k = NX - 1; k >= 64; k--) {
-                            const double yk = __shfl_sync(0xffffffffu, y2, k - 64) * s.idx[k];
+                        PH_MARK(30);
+                        _Pragma("unroll 1")
+                        for (int k = NX - 1; k >= 0; k--) {
                             const double *Lk = s.Hxx + k * NX;
-                            if (tid == k - 64) y2 = yk; else if (64 + tid < k) y2 -= Lk[64 + tid] * yk;
-                            y1 -= Lk[32 + tid] * yk; y0 -= Lk[tid] * yk;
+                            const double ik = s.idx[k];
+                            const double l0 = (tid < k) ? Lk[tid] : 0.0, l1 = (32 + tid < k) ? Lk[32 + tid] : 0.0, l2 = (64 + tid < k) ? Lk[64 + tid] : 0.0;
+                            const double src = (k >= 64) ? y2 : (k >= 32 ? y1 : y0);
+                            const double yk = __shfl_sync(0xffffffffu, src, k & 31) * ik;
+                            y0 = (tid == k) ? yk : y0 - l0 * yk;
+                            y1 = (32 + tid == k) ? yk : y1 - l1 * yk;
+                            y2 = (64 + tid == k) ? yk : y2 - l2 * yk;
                         }
-                        for (int k = 63; k >= 32; k--) {
-                            const double yk = __shfl_sync(0xffffffffu, y1, k - 32) * s.idx[k];
-                            const double *Lk = s.Hxx + k * NX;
-                            if (tid == k - 32) y1 = yk; else if (32 + tid < k) y1 -= Lk[32 + tid] * yk;
-                            y0 -= Lk[tid] * yk;
-                        }
-                        for (int k = 31; k >= 0; k--) {
-                            const double yk = __shfl_sync(0xffffffffu, y0, k) * s.idx[k];
-                            const double *Lk = s.Hxx + k * NX;
-                            if (tid == k) y0 = yk; else if (tid < k) y0 -= Lk[tid] * yk;
-                        }
+                        PH_MARK(32);
                         s.yv[tid] = y0; s.yv[32 + tid] = y1; if (64 + tid < NX) s.yv[64 + tid] = y2;
                     }
                     __syncthreads();
