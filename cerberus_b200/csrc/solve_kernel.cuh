@@ -24,7 +24,7 @@ namespace cerb {
 #if defined(CERB_PHASE_TIMING) && !defined(CERB_CUSIM)
 __device__ unsigned long long g_phase_cycles[48];
 #define PH_DECL() long long ph_t = clock64()
-#define PH_MARK_T(id, t) do { if ((threadIdx.x & 31) == 0) { const long long ph_n = clock64(); if (threadIdx.x == (t)) atomicAdd(&g_phase_cycles[id], (unsigned long long)(ph_n - ph_t)); ph_t = ph_n; } } while (0)
+#define PH_MARK_T(id, t) do { if ((threadIdx.x & 31) == 0) { const long long ph_n = clock64(); if (threadIdx.x == (t)) atomicAdd(&g_phase_cycles[id], (unsigned long long)(ph_n - ph_t)); ph_t = ph_n; } __syncwarp(); } while (0)
 #define PH_MARK(id) PH_MARK_T(id, 0)
 #else
 #define PH_DECL()
@@ -195,7 +195,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
     for (int i = tid; i < NX * nF; i += SOLVE_THREADS) W[(i / nF) * F + (i % nF)] = 0.0;
     __syncthreads();                                                    // the passes below overwrite / add to rows of W
     const int wid = tid >> 5, lane = tid & 31;
-    const int jj = tid >> 7, cam = (tid >> 6) & 1, fl = tid & 63;
+    const int cam = tid >> 7, jj = (tid >> 6) & 1, fl = tid & 63;      // tile rows: tid (first residual row) and 256 + tid (second)
     double *T = s.tile;
     double *jp = s.Ju;                                                  // [8 warps][4 blocks][64]  frame-dependent partial blocks
     double *pp = (wid < 5) ? s.Ju + 8 * VJ_SZ + VP_SZ * wid : s.tile + VT_SZ + VP_SZ * (wid - 5);     // [6 blocks][64] of this warp
@@ -223,7 +223,6 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
         for (int k = 0; k < 6; k++) { wI[k] = 0.0; wE0[k] = 0.0; wE1[k] = 0.0; }
         ObsVals ov; ov.px = ov.py = ov.vx = ov.vy = ov.td = 0.0; ov.stereo = 0;
         { const int j = a + jj; if (ev && j < a + nobs) obs_fetch(obs, stereo, mo, off + (j - a), cam, ov); }
-        const int nvalid = nc - 32 * (wid & 1);                          // valid features among the 32 of this warp
         PH_MARK(20);
         for (int j0 = a; j0 < NFR; j0 += 2) {
             const int j = j0 + jj;
@@ -261,50 +260,66 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
             if (wrow && cam == 0) for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] = wjv[k] * (prescale ? s.sc[6 * j + k] * slf : 1.0);
             __syncthreads();
             PH_MARK(21);
-            if (wrow && cam == 1) for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] += wjv[k] * (prescale ? s.sc[6 * j + k] * slf : 1.0);
+            double wprev[6] = {0, 0, 0, 0, 0, 0};                       // loaded here, consumed after the tensor-core loop (L2 latency hidden)
+            if (wrow && cam == 1) for (int k = 0; k < 6; k++) wprev[k] = W[(size_t)(6 * j + k) * F + f];
             { const int jn = j + 2; ov.stereo = 0; if (ev && jn < a + nobs) obs_fetch(obs, stereo, mo, off + (jn - a), cam, ov); }     // prefetch the next pass
-            // --- Gram matrix of this warp's 64 rows ------------------------------------------------------------------------
+            // --- Gram matrix.  Warp (jw = wid / 4, half = (wid / 2) & 1, par = wid & 1) contracts, for BOTH cameras of frame
+            // j0 + jw, the k-steps (4 rows each) of parity `par` of row `half` of the factors: every warp issues the same number
+            // of tensor-core instructions (camera-0 rows need 6 blocks, camera-1 rows 10), operands are fetched one k-step ahead. ---
             {
-                const int jw = j0 + (wid >> 2), camw = (wid >> 1) & 1;
+                const int jw = j0 + (wid >> 2), hw = (wid >> 1) & 1, par = wid & 1;
                 const bool k3 = (jw == a);
-                const bool work = jw < NFR && nvalid > 0 && !(k3 && camw == 0);
-                const bool use1 = !k3, use3 = camw == 1;
+                const int nkt = (nc + 3) >> 2;                                  // k-steps that hold valid features
+                const bool work = jw < NFR && par < nkt;
                 double acc[10][2];
                 for (int k = 0; k < 10; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
                 if (work) {
-                    const int nks = nvalid >= 32 ? 8 : (nvalid + 3) >> 2;
-                    for (int half = 0; half < 2; half++) {
-                        const int rb = 256 * half + 32 * wid;
-                        for (int ks = 0; ks < nks; ks++) {
-                            const int ro = rb + 4 * ks;
-                            const double v0 = tq[0][ro], v2 = tv[2] ? tq[2][ro] : 0.0;
+                    const int rb0 = 256 * hw + 64 * (wid >> 2) + 4 * par;       // camera 0 rows of this unit; camera 1: + 128
+                    if (!k3) {                                                      // camera 0 (K1): groups g0, g1, g2
+                        double v0 = tq[0][rb0], v1 = tv[1] ? tq[1][rb0] : 0.0, v2 = tv[2] ? tq[2][rb0] : 0.0;
+                        for (int ks = par; ks < nkt; ks += 2) {
+                            const int rn = rb0 + 4 * (ks + 2 - par);
+                            const bool more = ks + 2 < nkt;
+                            const double n0 = more ? tq[0][rn] : 0.0, n1 = (more && tv[1]) ? tq[1][rn] : 0.0, n2 = (more && tv[2]) ? tq[2][rn] : 0.0;
+                            CERB_DMMA(acc[0][0], acc[0][1], v0, v0, acc[0][0], acc[0][1]);
+                            CERB_DMMA(acc[1][0], acc[1][1], v0, v1, acc[1][0], acc[1][1]);
+                            CERB_DMMA(acc[2][0], acc[2][1], v0, v2, acc[2][0], acc[2][1]);
+                            CERB_DMMA(acc[4][0], acc[4][1], v1, v1, acc[4][0], acc[4][1]);
+                            CERB_DMMA(acc[5][0], acc[5][1], v1, v2, acc[5][0], acc[5][1]);
+                            CERB_DMMA(acc[7][0], acc[7][1], v2, v2, acc[7][0], acc[7][1]);
+                            v0 = n0; v1 = n1; v2 = n2;
+                        }
+                    }
+                    {                                                               // camera 1 (K2, or K3 in the anchor frame: no g1)
+                        const int rb1 = rb0 + 128;
+                        double v0 = tq[0][rb1], v1 = (!k3 && tv[1]) ? tq[1][rb1] : 0.0, v2 = tv[2] ? tq[2][rb1] : 0.0, v3 = tv[3] ? tq[3][rb1] : 0.0;
+                        for (int ks = par; ks < nkt; ks += 2) {
+                            const int rn = rb1 + 4 * (ks + 2 - par);
+                            const bool more = ks + 2 < nkt;
+                            const double n0 = more ? tq[0][rn] : 0.0, n1 = (more && !k3 && tv[1]) ? tq[1][rn] : 0.0, n2 = (more && tv[2]) ? tq[2][rn] : 0.0, n3 = (more && tv[3]) ? tq[3][rn] : 0.0;
                             CERB_DMMA(acc[0][0], acc[0][1], v0, v0, acc[0][0], acc[0][1]);
                             CERB_DMMA(acc[2][0], acc[2][1], v0, v2, acc[2][0], acc[2][1]);
+                            CERB_DMMA(acc[3][0], acc[3][1], v0, v3, acc[3][0], acc[3][1]);
                             CERB_DMMA(acc[7][0], acc[7][1], v2, v2, acc[7][0], acc[7][1]);
-                            if (use1) {
-                                const double v1 = tv[1] ? tq[1][ro] : 0.0;
+                            CERB_DMMA(acc[8][0], acc[8][1], v2, v3, acc[8][0], acc[8][1]);
+                            CERB_DMMA(acc[9][0], acc[9][1], v3, v3, acc[9][0], acc[9][1]);
+                            if (!k3) {
                                 CERB_DMMA(acc[1][0], acc[1][1], v0, v1, acc[1][0], acc[1][1]);
                                 CERB_DMMA(acc[4][0], acc[4][1], v1, v1, acc[4][0], acc[4][1]);
                                 CERB_DMMA(acc[5][0], acc[5][1], v1, v2, acc[5][0], acc[5][1]);
-                                if (use3) { const double v3 = tv[3] ? tq[3][ro] : 0.0; CERB_DMMA(acc[6][0], acc[6][1], v1, v3, acc[6][0], acc[6][1]); }
+                                CERB_DMMA(acc[6][0], acc[6][1], v1, v3, acc[6][0], acc[6][1]);
                             }
-                            if (use3) {
-                                const double v3 = tv[3] ? tq[3][ro] : 0.0;
-                                CERB_DMMA(acc[3][0], acc[3][1], v0, v3, acc[3][0], acc[3][1]);
-                                CERB_DMMA(acc[8][0], acc[8][1], v2, v3, acc[8][0], acc[8][1]);
-                                CERB_DMMA(acc[9][0], acc[9][1], v3, v3, acc[9][0], acc[9][1]);
-                            }
+                            v0 = n0; v1 = n1; v2 = n2; v3 = n3;
                         }
                     }
+                    PH_MARK(28); PH_MARK_T(30, 128);
                     const int o = (lane >> 2) * 8 + 2 * (lane & 3);
                     pp[0 * 64 + o] += acc[0][0]; pp[0 * 64 + o + 1] += acc[0][1];      // (g0, g0)
                     pp[1 * 64 + o] += acc[2][0]; pp[1 * 64 + o + 1] += acc[2][1];      // (g0, g2)
+                    pp[2 * 64 + o] += acc[3][0]; pp[2 * 64 + o + 1] += acc[3][1];      // (g0, g3)
                     pp[3 * 64 + o] += acc[7][0]; pp[3 * 64 + o + 1] += acc[7][1];      // (g2, g2)
-                    if (use3) {
-                        pp[2 * 64 + o] += acc[3][0]; pp[2 * 64 + o + 1] += acc[3][1];  // (g0, g3)
-                        pp[4 * 64 + o] += acc[8][0]; pp[4 * 64 + o + 1] += acc[8][1];  // (g2, g3)
-                        pp[5 * 64 + o] += acc[9][0]; pp[5 * 64 + o + 1] += acc[9][1];  // (g3, g3)
-                    }
+                    pp[4 * 64 + o] += acc[8][0]; pp[4 * 64 + o + 1] += acc[8][1];      // (g2, g3)
+                    pp[5 * 64 + o] += acc[9][0]; pp[5 * 64 + o + 1] += acc[9][1];      // (g3, g3)
                 }
                 {
                     const int o = wid * VJ_SZ + (lane >> 2) * 8 + 2 * (lane & 3);
@@ -314,6 +329,8 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
                     jp[192 + o] = acc[6][0]; jp[192 + o + 1] = acc[6][1];               // (g1, g3)
                 }
             }
+            if (wrow && cam == 1) for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] = wprev[k] + wjv[k] * (prescale ? s.sc[6 * j + k] * slf : 1.0);
+            PH_MARK(29); PH_MARK_T(31, 128);
             __syncthreads();
             PH_MARK(22);
             // --- frame-dependent blocks: sum over the four warps of each frame (fixed order) and scatter ----------------------------
@@ -321,7 +338,7 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
                 const int fj = e >> 8, el = e & 255, blk = el >> 6, ra = (el >> 3) & 7, rb = el & 7;
                 const int jf = j0 + fj;
                 if (jf >= NFR || jf == a) continue;
-                const double *q = jp + (4 * fj) * VJ_SZ + el;
+                const double *q = jp + (4 * fj) * VJ_SZ + el;             // warps 4 fj .. 4 fj + 3 hold the partial blocks of frame j0 + fj
                 const double v = ((q[0] + q[VJ_SZ]) + q[2 * VJ_SZ]) + q[3 * VJ_SZ];
                 vis_scatter(s, blk == 0 ? 0 : 1, blk == 0 ? 1 : blk, ra, rb, a, jf, v);
             }
@@ -756,7 +773,6 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                                 _Pragma("unroll")
                                 for (int c = 0; c < NYB; c++) { double t = 0.0; _Pragma("unroll") for (int q = 0; q < NYB; q++) t += m[q] * Mp[c * NYB + q]; a[c] -= t; }
                             }
-                            PH_MARK(34);
                             _Pragma("unroll")
                             for (int j = 0; j < NYB; j++) {                     // right-looking column sweep
                                 double d = __shfl_sync(0xffffffffu, a[j], j);
@@ -769,7 +785,6 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                                 _Pragma("unroll")
                                 for (int k = j + 1; k < NYB; k++) { const double lk = __shfl_sync(0xffffffffu, l, k); a[k] -= l * lk; }
                             }
-                            PH_MARK(35);
                             if (act) { _Pragma("unroll") for (int c = 0; c < NYB; c++) if (c <= r) A[r * NYB + c] = a[c]; s.idg[NYB * f + r] = myinv; }
                             __syncwarp();
                             if (f < NFR - 1) {
@@ -787,7 +802,6 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                                 if (act) { _Pragma("unroll") for (int c = 0; c < NYB; c++) B[r * NYB + c] = m[c]; }
                                 __syncwarp();
                             }
-                            PH_MARK(36);
                         }
                         PH_MARK(6);
                     } else {
@@ -989,7 +1003,6 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                     // branch-free steps (selects), the L entries of the next step are loaded before the current shuffle completes ----
                     if (tid < 32) {
                         double y0 = s.yv[tid], y1 = s.yv[32 + tid], y2 = (64 + tid < NX) ? s.yv[64 + tid] : 0.0;
-                        PH_MARK(30);
                         _Pragma("unroll 1")
                         for (int k = NX - 1; k >= 0; k--) {
                             const double *Lk = s.Hxx + k * NX;
@@ -1001,7 +1014,6 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
                             y1 = (32 + tid == k) ? yk : y1 - l1 * yk;
                             y2 = (64 + tid == k) ? yk : y2 - l2 * yk;
                         }
-                        PH_MARK(32);
                         s.yv[tid] = y0; s.yv[32 + tid] = y1; if (64 + tid < NX) s.yv[64 + tid] = y2;
                     }
                     __syncthreads();

@@ -42,9 +42,16 @@ for ln, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
 
 # ---- optional: share of samples per line range of solve_kernel.cuh (rough phase view) ----
 if len(sys.argv) > 4:
-    ranges = [(158, 189, "vis setup"), (190, 223, "vis eval+tile"), (224, 258, "vis DMMA"), (259, 277, "vis reduce"), (278, 303, "vis tail"), (306, 316, "imu lin"), (317, 353, "inertial cost / prior res"),
-              (354, 377, "scatter_H"), (378, 447, "imu whiten+gram"), (448, 490, "prior"), (491, 519, "plus/ambient"), (520, 557, "setup"), (558, 616, "post-lin"), (617, 655, "cauchy"),
-              (656, 720, "hyy chain"), (721, 776, "schur dmma"), (777, 795, "T solve"), (796, 831, "TT^T"), (832, 915, "dense chol"), (916, 942, "backsub"), (943, 964, "y part"), (965, 977, "inv depth"), (978, 1101, "dogleg/accept")]
+    srcl = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "cerberus_b200", "csrc", "solve_kernel.cuh")).read().splitlines()
+    def at(pat):
+        return next(i + 1 for i, l in enumerate(srcl) if pat in l)
+    cuts = [("vision_cost", at("CERB_D double vision_cost")), ("vis setup", at("CERB_D double vision_linearize")), ("vis eval+tile", at("PH_MARK(20)")), ("vis DMMA", at("PH_MARK(21)")),
+            ("vis reduce", at("PH_MARK(22)")), ("vis tail", at("PH_MARK(23)")), ("imu lin", at("CERB_D void imu_lin_all")), ("inertial cost / prior res", at("CERB_D double inertial_cost")),
+            ("scatter_H", at("CERB_D int imu_col_dest")), ("imu whiten+gram", at("CERB_D double inertial_linearize")), ("prior", at("PH_MARK(26)")), ("plus/ambient", at("CERB_D void apply_plus")),
+            ("setup", at("CERB_GLOBAL void")), ("post-lin", at("PH_MARK(0)")), ("cauchy", at("PH_MARK(3)")), ("hyy chain", at("PH_MARK(4)")), ("schur dmma", at("PH_MARK(6)")),
+            ("T solve", at("PH_MARK_T(7")), ("TT^T", at("PH_MARK(8)")), ("dense chol", at("PH_MARK(9)")), ("backsub", at("PH_MARK(10)")), ("y part", at("PH_MARK(11)")),
+            ("inv depth", at("PH_MARK(12)")), ("dogleg/accept", at("PH_MARK(13)")), ("end", len(srcl) + 1)]
+    ranges = [(cuts[i][1], cuts[i + 1][1] - 1, cuts[i][0]) for i in range(len(cuts) - 1)]
     acc = collections.Counter(); bar = collections.Counter()
     for ln, a in agg.items():
         f, n = ln if ln else ("?", 0)
