@@ -12,6 +12,10 @@
 #define CERB_HD __host__ __device__ __forceinline__
 #define CERB_D __device__ __forceinline__
 #define CERB_GLOBAL __global__
+// phase functions of the solve kernel are real calls: each gets its own register allocation (the kernel as one inlined
+// body ran at the 255-register cap with spills in its hottest loops); the kernel parameter block stays addressable in place
+#define CERB_NOINLINE __device__ __noinline__
+#define CERB_GRID_CONSTANT const __grid_constant__
 #define CERB_DYN_SMEM(T, name)                                   \
     extern __shared__ __align__(16) unsigned char name##_raw[]; \
     T *name = reinterpret_cast<T *>(name##_raw)

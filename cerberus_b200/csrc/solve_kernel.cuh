@@ -54,8 +54,9 @@ struct SolveParams {
 // per-CTA global workspace layout (doubles); F = maxF
 CERB_HD long ws_W(int) { return 0; }                                        // [NX][F]
 CERB_HD long ws_vecs(int F) { return (long)NX * F; }                        // 8 vectors of F: hh, gl, sl, Dl, ghl, gnl, stl, lamc
-CERB_HD long ws_backup(int F) { return (long)NX * F + 8L * F; }             // Hxx 6084 | Hxy 11154 | Ad 1859 | Bo 1690
-CERB_HD long ws_size(int F) { return ws_backup(F) + HXX_SZ + HXY_SZ + 1859 + 1690 + 64; }
+CERB_HD long ws_prior(int F) { return (long)NX * F + 8L * F; }              // image of the prior Hessian in the layout of Hxx | Hxy | Ad | Bo
+CERB_HD long ws_chunks(int F) { return ws_prior(F) + HXX_SZ + HXY_SZ + 1859 + 1690; }   // feature chunk table (ints)
+CERB_HD long ws_size(int F) { return ws_chunks(F) + (F + 4) / 2 + 8; }
 
 struct Smem {
     double *Hxx, *Hxy, *Ad, *Bo;            // 78x78, 78x143, 11x13x13, 10x13x13
@@ -108,43 +109,47 @@ CERB_D void load_geometry(const double *x, Smem &s, int tid) {
     __syncthreads();
 }
 
-// Evaluate the (up to) two factors of observation (f, frame j) seen by thread `cam`; returns false if none.
 struct ObsCtx { int start, nobs, off; double lam, pix, piy, vix, viy, tdi; };
-CERB_D bool eval_obs(const SolveParams &P, const Smem &s, const double *x, const double *obs, const int *stereo, const ObsCtx &c, int j, int cam,
-                     double r[2], ProjJac *J) {
-    if (j < c.start || j >= c.start + c.nobs) return false;
-    const int o = c.off + (j - c.start);
-    const int mo = P.maxObs;
-    int kind;
-    if (j == c.start) { if (cam == 0 || !stereo[o]) return false; kind = PROJ_K3; }
-    else if (cam == 0) kind = PROJ_K1;
-    else { if (!stereo[o]) return false; kind = PROJ_K2; }
-    const double pjx = obs[(cam ? 4 : 0) * mo + o], pjy = obs[(cam ? 5 : 1) * mo + o];
-    const double vjx = obs[(cam ? 6 : 2) * mo + o], vjy = obs[(cam ? 7 : 3) * mo + o];
-    const double tdj = obs[8 * mo + o];
-    const int i = c.start;
-    proj_eval(kind, ldm33(s.Rw + 9 * i), ld3(x + ST_POSE + 7 * i), ldm33(s.Rw + 9 * j), ld3(x + ST_POSE + 7 * j),
-              ldm33(s.Rex), ld3(x + ST_EX), ldm33(s.Rex + 9), ld3(x + ST_EX + 7), c.lam, x[ST_TD], c.pix, c.piy, pjx, pjy,
-              c.vix, c.viy, vjx, vjy, c.tdi, tdj, P.sqrt_info, r, J);
-    return true;
-}
 
 // ---- visual part: cost only (candidate evaluation) -------------------------------------------------------
-CERB_D double vision_cost(const SolveParams &P, const Smem &s, int w, const double *x, const double *lam, int tid) {
-    const int nF = P.n_features[w];
+CERB_NOINLINE double vision_cost(const SolveParams &P, int w, const double *x, const double *lam, int tid) {
+    CERB_DYN_SMEM(double, smem_base);
+    Smem s; smem_carve(smem_base, s);
+    // One (feature, camera, track half) per thread and round.  The pass is bound by the L2 latency of the observation loads,
+    // so all loads of an item are issued before its first factor is evaluated.
+    const int nF = P.n_features[w], mo = P.maxObs;
     const double *obs = P.obs + (size_t)w * NOBS_PLANES * P.maxObs;
     const int *stereo = P.obs_stereo + (size_t)w * P.maxObs;
     double cost = 0.0;
-    for (int idx = tid; idx < 2 * nF; idx += SOLVE_THREADS) {
-        const int f = idx >> 1, cam = idx & 1;
+    for (int idx = tid; idx < 4 * nF; idx += SOLVE_THREADS) {
+        const int f = idx >> 2, cam = idx & 1, part = (idx >> 1) & 1;
         ObsCtx c;
         c.start = P.feat_start[(size_t)w * P.maxF + f]; c.nobs = P.feat_nobs[(size_t)w * P.maxF + f]; c.off = P.feat_off[(size_t)w * P.maxF + f];
         c.lam = lam[f];
-        c.pix = obs[0 * P.maxObs + c.off]; c.piy = obs[1 * P.maxObs + c.off]; c.vix = obs[2 * P.maxObs + c.off]; c.viy = obs[3 * P.maxObs + c.off];
-        c.tdi = obs[8 * P.maxObs + c.off];
-        for (int j = c.start; j < c.start + c.nobs; j++) {
+        c.pix = obs[0 * mo + c.off]; c.piy = obs[1 * mo + c.off]; c.vix = obs[2 * mo + c.off]; c.viy = obs[3 * mo + c.off];
+        c.tdi = obs[8 * mo + c.off];
+        const int k0 = part ? 6 : 0, k1 = part ? c.nobs : (c.nobs < 6 ? c.nobs : 6);      // observations [k0, k1) of the track
+        double px[6], py[6], vx[6], vy[6], tj[6]; int st[6];
+        _Pragma("unroll")
+        for (int k = 0; k < 6; k++) {
+            const bool on = k0 + k < k1;
+            const int o = c.off + (on ? k0 + k : 0);
+            px[k] = obs[(cam ? 4 : 0) * mo + o]; py[k] = obs[(cam ? 5 : 1) * mo + o]; vx[k] = obs[(cam ? 6 : 2) * mo + o]; vy[k] = obs[(cam ? 7 : 3) * mo + o];
+            tj[k] = obs[8 * mo + o]; st[k] = stereo[o];
+        }
+        _Pragma("unroll")
+        for (int k = 0; k < 6; k++) {
+            if (k0 + k >= k1) continue;
+            const int j = c.start + k0 + k;
+            int kind;
+            if (k0 + k == 0) { if (cam == 0 || !st[k]) continue; kind = PROJ_K3; }
+            else if (cam == 0) kind = PROJ_K1;
+            else { if (!st[k]) continue; kind = PROJ_K2; }
             double r[2];
-            if (!eval_obs(P, s, x, obs, stereo, c, j, cam, r, nullptr)) continue;
+            const int i = c.start;
+            proj_eval(kind, ldm33(s.Rw + 9 * i), ld3(x + ST_POSE + 7 * i), ldm33(s.Rw + 9 * j), ld3(x + ST_POSE + 7 * j),
+                      ldm33(s.Rex), ld3(x + ST_EX), ldm33(s.Rex + 9), ld3(x + ST_EX + 7), c.lam, x[ST_TD], c.pix, c.piy, px[k], py[k],
+                      c.vix, c.viy, vx[k], vy[k], c.tdi, tj[k], P.sqrt_info, r, nullptr);
             double cf; huber_weight(P.huber, r[0] * r[0] + r[1] * r[1], &cf);
             cost += cf;
         }
@@ -185,8 +190,10 @@ CERB_D void vis_scatter(Smem &s, int ga, int gb, int ra, int rb, int a, int j, d
     if (db == -2) { s.g[da] += v; return; }
     if (da <= db) s.Hxx[da * NX + db] += v; else s.Hxx[db * NX + da] += v;
 }
-CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const double *x, const double *lam, double *W, double *hh, double *gl,
-                               const double *sl, bool prescale, const int *chunks, int tid) {
+CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double *x, const double *lam, double *W, double *hh, double *gl,
+                                      const double *sl, bool prescale, const int *chunks, int tid) {
+    CERB_DYN_SMEM(double, smem_base);
+    Smem s; smem_carve(smem_base, s);
     const int nF = P.n_features[w], F = P.maxF, mo = P.maxObs;
     const double *obs = P.obs + (size_t)w * NOBS_PLANES * P.maxObs;
     const int *stereo = P.obs_stereo + (size_t)w * P.maxObs;
@@ -219,6 +226,21 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
             pix = obs[0 * mo + off]; piy = obs[1 * mo + off]; vix = obs[2 * mo + off]; viy = obs[3 * mo + off]; tdi = obs[8 * mo + off];
         }
         for (int k = lane; k < VP_SZ; k += 32) pp[k] = 0.0;
+        // rotation products shared by all factors of (anchor a, frame j, camera c): A = Rc^T Rj^T, A Ri, T = A Ri ric (27 doubles per
+        // (j, c) in s.lin, which is idle until the inertial pass); slot 20: T3 = ric2^T ric of the anchor-frame stereo factor (K3)
+        if (tid < 2 * (NFR - 1 - a)) {
+            const int jq = a + 1 + (tid >> 1), cq = tid & 1;
+            const m33 Rc = ldm33(cq ? s.Rex + 9 : s.Rex);
+            const m33 A = mulT33(Rc, tr33(ldm33(s.Rw + 9 * jq)));
+            const m33 ARi = mul33(A, ldm33(s.Rw + 9 * a));
+            const m33 Tm = mul33(ARi, ldm33(s.Rex));
+            double *C = s.lin + 27 * tid;
+            for (int k = 0; k < 9; k++) { C[k] = A.m[k]; C[9 + k] = ARi.m[k]; C[18 + k] = Tm.m[k]; }
+        } else if (tid == 32) {
+            const m33 T3 = mul33(tr33(ldm33(s.Rex + 9)), ldm33(s.Rex));
+            for (int k = 0; k < 9; k++) s.lin[540 + k] = T3.m[k];
+        }
+        __syncthreads();
         double h = 0.0, gq = 0.0, wT = 0.0, wI[6], wE0[6], wE1[6];
         for (int k = 0; k < 6; k++) { wI[k] = 0.0; wE0[k] = 0.0; wE1[k] = 0.0; }
         ObsVals ov; ov.px = ov.py = ov.vx = ov.vy = ov.td = 0.0; ov.stereo = 0;
@@ -236,22 +258,74 @@ CERB_D double vision_linearize(const SolveParams &P, Smem &s, int w, const doubl
             double wjv[6] = {0, 0, 0, 0, 0, 0};
             double *t0 = T + tid, *t1 = T + 256 + tid;
             if (valid) {
-                double r[2]; ProjJac J;
-                proj_eval(kind, ldm33(s.Rw + 9 * a), ld3(x + ST_POSE + 7 * a), ldm33(s.Rw + 9 * j), ld3(x + ST_POSE + 7 * j),
-                          ldm33(s.Rex), ld3(x + ST_EX), ldm33(s.Rex + 9), ld3(x + ST_EX + 7), lamf, x[ST_TD], pix, piy, ov.px, ov.py,
-                          vix, viy, ov.vx, ov.vy, tdi, ov.td, P.sqrt_info, r, &J);
-                double cf; const double hw = huber_weight(P.huber, r[0] * r[0] + r[1] * r[1], &cf);
+                // Streamed evaluation (same algebra as proj_eval / the reference, regrouped): with e0, e1 the two Huber-scaled rows
+                // of d(pixel)/d(p_cj) and u_M = [e0; e1] M, every rotation block is a cross product, e.g.
+                // d r / d theta_i = [e0; e1] (-A Ri [p_bi]x) = p_bi x u_ARi.  Blocks go straight to the tile.
+                const d3 tic = ld3(x + ST_EX), tc = kind == PROJ_K1 ? tic : ld3(x + ST_EX + 7);
+                const double *Rcp = kind == PROJ_K1 ? s.Rex : s.Rex + 9;
+                const double tdv = x[ST_TD];
+                const d3 pts_i = mk3(pix, piy, 1.0), vel_i = mk3(vix, viy, 0.0);
+                const d3 pts_i_td = pts_i - (tdv - tdi) * vel_i;
+                const double pjx_td = ov.px - (tdv - ov.td) * ov.vx, pjy_td = ov.py - (tdv - ov.td) * ov.vy;
+                const double inv_l = 1.0 / lamf;
+                const d3 p_ci = inv_l * pts_i_td;
+                const d3 p_bi = mv33(ldm33(s.Rex), p_ci) + tic;
+                d3 p_bj = p_bi;
+                if (kind != PROJ_K3) p_bj = mTv33(ldm33(s.Rw + 9 * j), (mv33(ldm33(s.Rw + 9 * a), p_bi) + ld3(x + ST_POSE + 7 * a)) - ld3(x + ST_POSE + 7 * j));
+                const d3 p_cj = mTv33(ldm33(Rcp), p_bj - tc);
+                const double iz = 1.0 / p_cj.z;
+                double r0 = P.sqrt_info * (p_cj.x * iz - pjx_td), r1 = P.sqrt_info * (p_cj.y * iz - pjy_td);
+                double cf; const double hw = huber_weight(P.huber, r0 * r0 + r1 * r1, &cf);
                 cost += cf;
-                const double r0 = hw * r[0], r1 = hw * r[1], l0 = hw * J.Jl[0], l1 = hw * J.Jl[1], d0 = hw * J.Jtd[0], d1 = hw * J.Jtd[1];
+                r0 *= hw; r1 *= hw;
+                const double q = hw * P.sqrt_info * iz, c0 = -q * p_cj.x * iz, c1 = -q * p_cj.y * iz;
+                const d3 e0 = mk3(q, 0.0, c0), e1 = mk3(0.0, q, c1);
+#define VIS_U(M, u0, u1) const d3 u0 = mk3(q * (M)[0] + c0 * (M)[6], q * (M)[1] + c0 * (M)[7], q * (M)[2] + c0 * (M)[8]), u1 = mk3(q * (M)[3] + c1 * (M)[6], q * (M)[4] + c1 * (M)[7], q * (M)[5] + c1 * (M)[8])
+#define VIS_PUT(col, a0, a1) do { t0[(col) * VT_LD] = (a0); t1[(col) * VT_LD] = (a1); } while (0)
+#define VIS_PUT3(col, v0_, v1_) do { VIS_PUT(col, (v0_).x, (v1_).x); VIS_PUT((col) + 1, (v0_).y, (v1_).y); VIS_PUT((col) + 2, (v0_).z, (v1_).z); } while (0)
+                const double *Tm = kind == PROJ_K3 ? s.lin + 540 : s.lin + 27 * (2 * (j - a - 1) + cam) + 18;
+                VIS_U(Tm, uT0, uT1);
+                const d3 ptl = kind == PROJ_K3 ? pts_i : pts_i_td;              // reference quirk: K3 uses pts_i (projectionOneFrameTwoCamFactor.cpp:119)
+                const double l0 = -inv_l * inv_l * dot3(uT0, ptl), l1 = -inv_l * inv_l * dot3(uT1, ptl);
+                const double d0 = -inv_l * dot3(uT0, vel_i) + hw * P.sqrt_info * ov.vx, d1 = -inv_l * dot3(uT1, vel_i) + hw * P.sqrt_info * ov.vy;
                 h += l0 * l0 + l1 * l1; gq += l0 * r0 + l1 * r1; wT += d0 * l0 + d1 * l1;
-                t0[6 * VT_LD] = d0; t1[6 * VT_LD] = d1; t0[7 * VT_LD] = r0; t1[7 * VT_LD] = r1;
-                for (int k = 0; k < 6; k++) {
-                    const double i0 = hw * J.Ji[k], i1 = hw * J.Ji[6 + k], q0 = hw * J.Jj[k], q1 = hw * J.Jj[6 + k];
-                    const double e0 = hw * J.Je0[k], e1 = hw * J.Je0[6 + k], u0 = hw * J.Je1[k], u1 = hw * J.Je1[6 + k];
-                    t0[k * VT_LD] = i0; t1[k * VT_LD] = i1; t0[(8 + k) * VT_LD] = q0; t1[(8 + k) * VT_LD] = q1;
-                    t0[(14 + k) * VT_LD] = e0; t1[(14 + k) * VT_LD] = e1; t0[(20 + k) * VT_LD] = u0; t1[(20 + k) * VT_LD] = u1;
-                    wI[k] += i0 * l0 + i1 * l1; wjv[k] = q0 * l0 + q1 * l1; wE0[k] += e0 * l0 + e1 * l1; wE1[k] += u0 * l0 + u1 * l1;
+                VIS_PUT(6, d0, d1); VIS_PUT(7, r0, r1);
+                // u_{Rc^T}: rows of Rc^T are the columns of Rc
+                const d3 uC0 = mk3(q * Rcp[0] + c0 * Rcp[2], q * Rcp[3] + c0 * Rcp[5], q * Rcp[6] + c0 * Rcp[8]);
+                const d3 uC1 = mk3(q * Rcp[1] + c1 * Rcp[2], q * Rcp[4] + c1 * Rcp[5], q * Rcp[7] + c1 * Rcp[8]);
+                const d3 er0 = cross3(e0, p_cj), er1 = cross3(e1, p_cj);        // [e0; e1] [p_cj]x
+                const d3 et0 = cross3(p_ci, uT0), et1 = cross3(p_ci, uT1);      // -[e0; e1] T [p_ci]x
+                d3 E0t0, E0t1, E0r0, E0r1, E1t0, E1t1, E1r0, E1r1;
+                if (kind == PROJ_K3) {
+                    for (int k = 0; k < 6; k++) { VIS_PUT(k, 0.0, 0.0); VIS_PUT(8 + k, 0.0, 0.0); }
+                    E0t0 = uC0; E0t1 = uC1; E0r0 = et0; E0r1 = et1; E1t0 = -uC0; E1t1 = -uC1; E1r0 = er0; E1r1 = er1;
+                } else {
+                    const double *C = s.lin + 27 * (2 * (j - a - 1) + cam);
+                    VIS_U(C, uA0, uA1);
+                    VIS_U(C + 9, uR0, uR1);
+                    const d3 ir0 = cross3(p_bi, uR0), ir1 = cross3(p_bi, uR1);  // -[e] A Ri [p_bi]x
+                    const d3 jr0 = cross3(uC0, p_bj), jr1 = cross3(uC1, p_bj);  //  [e] Rc^T [p_bj]x
+                    VIS_PUT3(0, uA0, uA1); VIS_PUT3(3, ir0, ir1);
+                    VIS_PUT3(8, -uA0, -uA1); VIS_PUT3(11, jr0, jr1);
+                    wI[0] += uA0.x * l0 + uA1.x * l1; wI[1] += uA0.y * l0 + uA1.y * l1; wI[2] += uA0.z * l0 + uA1.z * l1;
+                    wI[3] += ir0.x * l0 + ir1.x * l1; wI[4] += ir0.y * l0 + ir1.y * l1; wI[5] += ir0.z * l0 + ir1.z * l1;
+                    wjv[0] = -(uA0.x * l0 + uA1.x * l1); wjv[1] = -(uA0.y * l0 + uA1.y * l1); wjv[2] = -(uA0.z * l0 + uA1.z * l1);
+                    wjv[3] = jr0.x * l0 + jr1.x * l1; wjv[4] = jr0.y * l0 + jr1.y * l1; wjv[5] = jr0.z * l0 + jr1.z * l1;
+                    if (kind == PROJ_K1) {
+                        E0t0 = uR0 - uC0; E0t1 = uR1 - uC1; E0r0 = et0 + er0; E0r1 = et1 + er1;
+                        E1t0 = mk3(0, 0, 0); E1t1 = E1t0; E1r0 = E1t0; E1r1 = E1t0;
+                    } else {
+                        E0t0 = uR0; E0t1 = uR1; E0r0 = et0; E0r1 = et1; E1t0 = -uC0; E1t1 = -uC1; E1r0 = er0; E1r1 = er1;
+                    }
                 }
+                VIS_PUT3(14, E0t0, E0t1); VIS_PUT3(17, E0r0, E0r1); VIS_PUT3(20, E1t0, E1t1); VIS_PUT3(23, E1r0, E1r1);
+                wE0[0] += E0t0.x * l0 + E0t1.x * l1; wE0[1] += E0t0.y * l0 + E0t1.y * l1; wE0[2] += E0t0.z * l0 + E0t1.z * l1;
+                wE0[3] += E0r0.x * l0 + E0r1.x * l1; wE0[4] += E0r0.y * l0 + E0r1.y * l1; wE0[5] += E0r0.z * l0 + E0r1.z * l1;
+                wE1[0] += E1t0.x * l0 + E1t1.x * l1; wE1[1] += E1t0.y * l0 + E1t1.y * l1; wE1[2] += E1t0.z * l0 + E1t1.z * l1;
+                wE1[3] += E1r0.x * l0 + E1r1.x * l1; wE1[4] += E1r0.y * l0 + E1r1.y * l1; wE1[5] += E1r0.z * l0 + E1r1.z * l1;
+#undef VIS_U
+#undef VIS_PUT
+#undef VIS_PUT3
             } else {
                 for (int k = 0; k < VT_COLS; k++) { t0[k * VT_LD] = 0.0; t1[k * VT_LD] = 0.0; }
             }
@@ -388,22 +462,6 @@ CERB_D void imu_lin_all(const SolveParams &P, Smem &s, int w, const double *x, b
     __syncthreads();
 }
 
-// cost only: 0.5 * sum || S r ||^2 over the valid factors + prior
-CERB_D double inertial_cost(const SolveParams &P, Smem &s, int w, const double *x, int tid) {
-    imu_lin_all(P, s, w, x, false, tid);
-    double cost = 0.0;
-    for (int idx = tid; idx < CERB_WINDOW * 31; idx += SOLVE_THREADS) {
-        const int i = idx / 31, r = idx % 31;
-        const double *pre = P.pre + ((size_t)w * CERB_WINDOW + i) * PRE_STRIDE;
-        if (pre[PRE_SUM_DT] > 10.0) continue;
-        const double *ru = s.lin + 96 * i, *S = P.sinfo + ((size_t)w * CERB_WINDOW + i) * 961;
-        double t = 0.0;
-        for (int q = r; q < 31; q++) t += S[r * 31 + q] * ru[q];
-        cost += 0.5 * t * t;
-    }
-    return cost;
-}
-
 // prior residual r = r0 + J0 dx into s.pr; returns this thread's share of 0.5 ||r||^2
 CERB_D double prior_residual(const SolveParams &P, Smem &s, int w, const double *x, int tid) {
     const int *meta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
@@ -415,14 +473,44 @@ CERB_D double prior_residual(const SolveParams &P, Smem &s, int w, const double 
         prior_block_dx(kind, x + prior_block_state_offset(kind, index), x0 + 9 * tid, s.pdx + col);
     }
     __syncthreads();
+    // J0 dx with the column range cut into `parts` slices so that (almost) all threads stream J0 (coalesced over the rows)
+    int parts = SOLVE_THREADS / n; if (parts > 4) parts = 4; if (parts < 1) parts = 1;
+    const int kc = (n + parts - 1) / parts;
+    double *part = s.red;                                               // [parts][PRIOR_LD]
+    for (int e = tid; e < parts * n; e += SOLVE_THREADS) {
+        const int p = e / n, i = e % n;
+        const int k1 = (p + 1) * kc < n ? (p + 1) * kc : n;
+        double t = 0.0;
+        for (int k = p * kc; k < k1; k++) t += J[(size_t)k * n + i] * s.pdx[k];
+        part[p * PRIOR_LD + i] = t;
+    }
+    __syncthreads();
     double cost = 0.0;
     for (int i = tid; i < n; i += SOLVE_THREADS) {
         double t = r0[i];
-        for (int k = 0; k < n; k++) t += J[(size_t)k * n + i] * s.pdx[k];
+        for (int p = 0; p < parts; p++) t += part[p * PRIOR_LD + i];
         s.pr[i] = t; cost += 0.5 * t * t;
     }
     __syncthreads();
     return cost;
+}
+
+// cost only: 0.5 * sum || S r ||^2 over the valid factors + prior
+CERB_NOINLINE double inertial_cost(const SolveParams &P, int w, const double *x, int tid) {
+    CERB_DYN_SMEM(double, smem_base);
+    Smem s; smem_carve(smem_base, s);
+    imu_lin_all(P, s, w, x, false, tid);
+    double cost = 0.0;
+    for (int idx = tid; idx < CERB_WINDOW * 31; idx += SOLVE_THREADS) {
+        const int i = idx / 31, r = idx % 31;
+        const double *pre = P.pre + ((size_t)w * CERB_WINDOW + i) * PRE_STRIDE;
+        if (pre[PRE_SUM_DT] > 10.0) continue;
+        const double *ru = s.lin + 96 * i, *S = P.sinfo + ((size_t)w * CERB_WINDOW + i) * 961;
+        double t = 0.0;
+        for (int q = r; q < 31; q++) t += S[r * 31 + q] * ru[q];
+        cost += 0.5 * t * t;
+    }
+    return cost + prior_residual(P, s, w, x, tid);
 }
 
 // destination of a local IMU-leg tangent column c (0..37) of factor i: x index (>=0) or -(1 + y index)
@@ -448,9 +536,12 @@ CERB_D void scatter_H(Smem &s, int da, int db, double v) {
 // whitened, Jw = S Ju, and the Gram matrix Jw^T Jw (39 x 39: Hessian blocks, gradient column, cost corner) is scattered
 // into Hxx / Hxy / Hyy / g.  Both products are dense contractions (32 x 32 x 40 and 40 x 32 x 40 after padding) and run on
 // the fp64 tensor cores; S of the next factor is prefetched into registers while the current one is processed.
-// Scratch (s.Ju .. s.wj, 4281 doubles): SP [32][36] sqrt_info (zero padded) | JuP [32][44] | JwP [32][44].
-enum { IMU_LDS = 36, IMU_LDJ = 44, IMU_SP = 0, IMU_JU = 32 * 36, IMU_JW = 32 * 36 + 32 * 44 };
-CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const double *x, int tid) {
+// Scratch (s.Ju .. s.wj, 4281 doubles): SP [32][36] sqrt_info (zero padded) | JuP [32][44] | JwP [32][44] | 2 x 128 staged
+// preintegration headers (the constants the Jacobian expansion reads; fetched one factor ahead like S).
+enum { IMU_LDS = 36, IMU_LDJ = 44, IMU_SP = 0, IMU_JU = 32 * 36, IMU_JW = 32 * 36 + 32 * 44, IMU_PRE = 32 * 36 + 2 * 32 * 44 };
+CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const double *x, int tid) {
+    CERB_DYN_SMEM(double, smem_base);
+    Smem s; smem_carve(smem_base, s);
     double cost = 0.0;
     PH_DECL();
     imu_lin_all(P, s, w, x, true, tid);
@@ -458,15 +549,22 @@ CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const dou
     double *SP = s.Ju + IMU_SP, *JuP = s.Ju + IMU_JU, *JwP = s.Ju + IMU_JW;
     const int wid = tid >> 5, lane = tid & 31;
     for (int k = tid; k < IMU_JW; k += SOLVE_THREADS) s.Ju[k] = 0.0;        // SP padding and JuP
-    double sreg[4];
-    {   // prefetch sqrt_info of factor 0 (upper triangular; the lower part is masked when staged)
+    double *preS = s.Ju + IMU_PRE;
+    double sreg[4], preg = 0.0;
+    {   // prefetch sqrt_info of factor 0 (upper triangular; the lower part is masked when staged) and the headers of factors 0, 1
         const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + 0) * 961;
         for (int q = 0; q < 4; q++) { const int k = tid + SOLVE_THREADS * q; sreg[q] = (k < 961) ? S[k] : 0.0; }
+        const double *pre0 = P.pre + ((size_t)w * CERB_WINDOW + 0) * PRE_STRIDE;
+        if (tid < 128) { preS[tid] = pre0[tid]; preg = pre0[PRE_STRIDE + tid]; }
     }
     __syncthreads();
     for (int i = 0; i < CERB_WINDOW; i++) {
-        const double *pre = P.pre + ((size_t)w * CERB_WINDOW + i) * PRE_STRIDE;
+        const double *pre = preS + 128 * (i & 1);                           // staged header of factor i
         const bool skip = pre[PRE_SUM_DT] > 10.0;                          // estimator.cpp:1119 (uniform across the CTA)
+        if (tid < 128 && i + 1 < CERB_WINDOW) {
+            preS[128 * ((i + 1) & 1) + tid] = preg;                         // header of factor i + 1 (its slot was last read before the previous barrier)
+            if (i + 2 < CERB_WINDOW) preg = P.pre[((size_t)w * CERB_WINDOW + i + 2) * PRE_STRIDE + tid];
+        }
         // ---- stage S (padded, lower part masked) and expand Ju ----------------------------------------------------------
         if (!skip) {
             for (int q = 0; q < 4; q++) { const int k = tid + SOLVE_THREADS * q; if (k < 961) { const int r = k / 31, c = k % 31; SP[r * IMU_LDS + c] = (c >= r) ? sreg[q] : 0.0; } }
@@ -477,7 +575,7 @@ CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const dou
             const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + i + 1) * 961;
             for (int q = 0; q < 4; q++) { const int k = tid + SOLVE_THREADS * q; sreg[q] = (k < 961) ? S[k] : 0.0; }
         }
-        if (skip) continue;
+        if (skip) { __syncthreads(); continue; }                           // (the barrier orders the header staging above)
         __syncthreads();
         // ---- Jw = S Ju: 4 x 5 output blocks of 8 x 8; S is upper triangular, so block row mi needs k >= 8 mi only ------------
         for (int t = 0; t < 3; t++) {
@@ -520,41 +618,19 @@ CERB_D double inertial_linearize(const SolveParams &P, Smem &s, int w, const dou
         __syncthreads();
     }
     PH_MARK(26);
-    // ---- prior: r = r0 + J0 dx, g += J0^T r, H += J0^T J0 (precomputed once per solve) -------------------
+    // ---- prior: r = r0 + J0 dx, g += J0^T r.  Its Hessian J0^T J0 is constant and already part of the initial H (prior image).
     const int *meta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
     if (meta[0]) {
         cost += prior_residual(P, s, w, x, tid);
-        const int n = meta[1], nb = meta[2];
-        const double *J = P.prior_J + (size_t)w * PRIOR_LD * PRIOR_LD, *Hp = P.prior_Hp + (size_t)w * PRIOR_LD * PRIOR_LD;
-        // column -> destination map in s.ti[0..n)
-        if (tid < nb) {
-            const int kind = meta[4 + 3 * tid], index = meta[5 + 3 * tid], col = meta[6 + 3 * tid];
-            const int local = (kind == 0 || kind == 3) ? 6 : prior_block_size(kind);
-            for (int k = 0; k < local; k++) {
-                int d;
-                if (kind == 0) d = 6 * index + k;
-                else if (kind == 3) d = 66 + 6 * index + k;
-                else if (kind == 1) d = -(1 + NYB * index + k);
-                else if (kind == 2) d = -(1 + NYB * index + 9 + k);
-                else d = X_TD;
-                s.ti[col + k] = d;
-            }
-        }
-        __syncthreads();
-        for (int c = tid; c < n; c += SOLVE_THREADS) {
-            const int d = s.ti[c];
-            if (d == (1 << 20)) continue;
+        const int n = meta[1];
+        const double *J = P.prior_J + (size_t)w * PRIOR_LD * PRIOR_LD;
+        // one warp per column of J0 (contiguous, coalesced), lanes stride the rows, fixed-order shuffle reduction
+        for (int c = wid; c < n; c += SOLVE_THREADS / 32) {
             double t = 0.0;
-            for (int k = 0; k < n; k++) t += J[(size_t)c * n + k] * s.pr[k];
-            if (d >= 0) s.g[d] += t; else s.g[NX + (-d - 1)] += t;
-        }
-        __syncthreads();
-        for (int idx = tid; idx < n * n; idx += SOLVE_THREADS) {
-            const int a = idx / n, b = idx % n;
-            if (b < a) continue;
-            const int da = s.ti[a], db = s.ti[b];
-            if (da == (1 << 20) || db == (1 << 20)) continue;
-            scatter_H(s, da, db, Hp[a * PRIOR_LD + b]);
+            for (int k = lane; k < n; k += 32) t += J[(size_t)c * n + k] * s.pr[k];
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_sync(0xffffffffu, t, (lane + o) & 31);
+            const int d = s.ti[c];
+            if (lane == 0 && d != (1 << 20)) { if (d >= 0) s.g[d] += t; else s.g[NX + (-d - 1)] += t; }
         }
         __syncthreads();
     }
@@ -592,7 +668,7 @@ CERB_D double ambient_sq(const double *a, const double *b, const double *la, con
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------
-CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolveParams P) {
+CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID_CONSTANT SolveParams P) {
     CERB_DYN_SMEM(double, smem_base);
     Smem s; smem_carve(smem_base, s);
     const int tid = threadIdx.x;
@@ -600,7 +676,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
     double *ws = P.ws + (size_t)blockIdx.x * P.ws_stride;
     double *W = ws + ws_W(F);
     double *hh = ws + ws_vecs(F), *gl = hh + F, *sl = gl + F, *Dl = sl + F, *ghl = Dl + F, *gnl = ghl + F, *stl = gnl + F, *lamc = stl + F;
-    int *chunks = reinterpret_cast<int *>(ws + ws_backup(F));          // [0] n, [1..n] chunk starts, [n + 1] nF
+    int *chunks = reinterpret_cast<int *>(ws + ws_chunks(F));          // [0] n, [1..n] chunk starts, [n + 1] nF
+    double *pimg = ws + ws_prior(F);                                   // prior Hessian image, built once per window
     double *sca = s.sca;
     // scalar slots
     enum { S_RADIUS = 0, S_MU, S_REUSE, S_XCOST, S_CCOST, S_ALPHA, S_GNORM2, S_GNNORM2, S_GDOTGN, S_MODEL, S_STEPNORM, S_XNORM, S_DLNORM,
@@ -624,6 +701,35 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
             }
             chunks[1 + n] = nF; chunks[0] = n;
         }
+        // prior Hessian image (J0^T J0 scattered into the layout of Hxx | Hxy | Ad | Bo): constant during the solve, every
+        // linearisation starts from it instead of from zero.  s.ti keeps the column -> destination map of the prior.
+        const int *pmeta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
+        const bool has_prior = pmeta[0] != 0;
+        if (has_prior) {
+            const int n = pmeta[1], nb = pmeta[2];
+            for (int k = tid; k < HXX_SZ + HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) pimg[k] = 0.0;
+            if (tid < nb) {
+                const int kind = pmeta[4 + 3 * tid], index = pmeta[5 + 3 * tid], col = pmeta[6 + 3 * tid];
+                const int local = (kind == 0 || kind == 3) ? 6 : prior_block_size(kind);
+                for (int k = 0; k < local; k++) {
+                    int d;
+                    if (kind == 0) d = 6 * index + k;
+                    else if (kind == 3) d = 66 + 6 * index + k;
+                    else if (kind == 1) d = -(1 + NYB * index + k);
+                    else if (kind == 2) d = -(1 + NYB * index + 9 + k);
+                    else d = X_TD;
+                    s.ti[col + k] = d;
+                }
+            }
+            __syncthreads();
+            Smem si = s; si.Hxx = pimg; si.Hxy = pimg + HXX_SZ; si.Ad = pimg + HXX_SZ + HXY_SZ; si.Bo = pimg + HXX_SZ + HXY_SZ + 1859;
+            const double *Hp = P.prior_Hp + (size_t)w * PRIOR_LD * PRIOR_LD;
+            for (int idx = tid; idx < n * n; idx += SOLVE_THREADS) {
+                const int a = idx / n, b = idx % n;
+                if (b < a) continue;
+                scatter_H(si, s.ti[a], s.ti[b], Hp[a * PRIOR_LD + b]);
+            }
+        }
         for (int k = tid; k < ST_STRIDE; k += SOLVE_THREADS) s.xs[k] = (k < ST_SIZE) ? P.state[(size_t)w * ST_STRIDE + k] : 0.0;
         if (tid == 0) {
             sca[S_RADIUS] = P.radius0; sca[S_MU] = 1e-8; sca[S_REUSE] = 0; sca[S_DONE] = 0; sca[S_TERM] = 1; sca[S_ITER] = 0; sca[S_NSUCC] = 0;
@@ -636,18 +742,16 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
         while (true) {
             // =============================== linearise at xs ===========================================
             if (need_linearize) {
-                for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = 0.0;
+                for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = has_prior ? pimg[k] : 0.0;
                 for (int k = tid; k < NRP; k += SOLVE_THREADS) s.g[k] = 0.0;
                 load_geometry(s.xs, s, tid);
                 double part[2];
                 PH_MARK(0);
-                part[0] = vision_linearize(P, s, w, s.xs, lam, W, hh, gl, sl, iteration > 0, chunks, tid);
-                for (int k = tid; k < HXY_SZ; k += SOLVE_THREADS) s.Hxy[k] = 0.0;     // the tile aliased Hxy
-                for (int k = tid; k < 1859; k += SOLVE_THREADS) s.Ad[k] = 0.0;
-                for (int k = tid; k < 1690; k += SOLVE_THREADS) s.Bo[k] = 0.0;
+                part[0] = vision_linearize(P, w, s.xs, lam, W, hh, gl, sl, iteration > 0, chunks, tid);
+                for (int k = tid; k < HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) s.Hxy[k] = has_prior ? pimg[HXX_SZ + k] : 0.0;   // Hxy | Ad | Bo (contiguous; the tile aliased them)
                 __syncthreads();
                 PH_MARK(1);
-                part[0] += inertial_linearize(P, s, w, s.xs, tid);
+                part[0] += inertial_linearize(P, w, s.xs, tid);
                 PH_MARK(2);
                 part[1] = ambient_sq(s.xs, nullptr, lam, nullptr, nF, ex_open, lb_open, td_open, tid);
                 double tot[2];
@@ -1133,9 +1237,9 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(SolvePara
             {
                 double part[2];
                 PH_MARK(15);
-                part[0] = vision_cost(P, s, w, s.xc, lamc, tid);
+                part[0] = vision_cost(P, w, s.xc, lamc, tid);
                 PH_MARK(16);
-                part[0] += inertial_cost(P, s, w, s.xc, tid) + prior_residual(P, s, w, s.xc, tid);
+                part[0] += inertial_cost(P, w, s.xc, tid);
                 PH_MARK(17);
                 part[1] = ambient_sq(s.xs, s.xc, lam, lamc, nF, ex_open, lb_open, td_open, tid);
                 double tot[2];

@@ -29,6 +29,8 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
 #define CERB_HD inline
 #define CERB_D inline
 #define CERB_GLOBAL static
+#define CERB_NOINLINE static __attribute__((noinline))
+#define CERB_GRID_CONSTANT const
 #define __shared__ static
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
