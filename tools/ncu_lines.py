@@ -45,9 +45,9 @@ if len(sys.argv) > 4:
     srcl = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "cerberus_b200", "csrc", "solve_kernel.cuh")).read().splitlines()
     def at(pat):
         return next(i + 1 for i, l in enumerate(srcl) if pat in l)
-    cuts = [("vision_cost", at("CERB_D double vision_cost")), ("vis setup", at("CERB_D double vision_linearize")), ("vis eval+tile", at("PH_MARK(20)")), ("vis DMMA", at("PH_MARK(21)")),
-            ("vis reduce", at("PH_MARK(22)")), ("vis tail", at("PH_MARK(23)")), ("imu lin", at("CERB_D void imu_lin_all")), ("inertial cost / prior res", at("CERB_D double inertial_cost")),
-            ("scatter_H", at("CERB_D int imu_col_dest")), ("imu whiten+gram", at("CERB_D double inertial_linearize")), ("prior", at("PH_MARK(26)")), ("plus/ambient", at("CERB_D void apply_plus")),
+    cuts = [("vision_cost", at("double vision_cost(")), ("vis setup", at("double vision_linearize(")), ("vis eval+tile", at("PH_MARK(20)")), ("vis DMMA", at("PH_MARK(21)")),
+            ("vis reduce", at("PH_MARK(22)")), ("vis tail", at("PH_MARK(23)")), ("imu lin", at("CERB_D void imu_lin_all")), ("inertial cost / prior res", at("double inertial_cost(")),
+            ("scatter_H", at("CERB_D int imu_col_dest")), ("imu whiten+gram", at("double inertial_linearize(")), ("prior", at("PH_MARK(26)")), ("plus/ambient", at("CERB_D void apply_plus")),
             ("setup", at("CERB_GLOBAL void")), ("post-lin", at("PH_MARK(0)")), ("cauchy", at("PH_MARK(3)")), ("hyy chain", at("PH_MARK(4)")), ("schur dmma", at("PH_MARK(6)")),
             ("T solve", at("PH_MARK_T(7")), ("TT^T", at("PH_MARK(8)")), ("dense chol", at("PH_MARK(9)")), ("backsub", at("PH_MARK(10)")), ("y part", at("PH_MARK(11)")),
             ("inv depth", at("PH_MARK(12)")), ("dogleg/accept", at("PH_MARK(13)")), ("end", len(srcl) + 1)]
