@@ -194,10 +194,14 @@ CERB_HD void imu_leg_linearize(const double *pre, const double *pose_i, const do
 // 10: the leg-length columns) so that 11 threads can fill one factor concurrently.
 CERB_HD void imu_leg_fill_ju_part(const IMULegLin &L, const double *pre, double *Ju, int ld, int part) {
 #define JU(rr, cc) Ju[(rr) * ld + (cc)]
+    // every value of `pre` (HBM / L2 in the fused solver) is loaded before the first store, so the loads are issued back to back
     const bool imu_only = pre[PRE_IMU_ONLY] != 0.0;
     if (part < 9) {
         const int a = part / 3, b = part % 3;
         const double dt = pre[PRE_SUM_DT];
+        const double dp_dba = pre[PRE_DP_DBA + 3 * a + b], dp_dbg = pre[PRE_DP_DBG + 3 * a + b], dv_dba = pre[PRE_DV_DBA + 3 * a + b], dv_dbg = pre[PRE_DV_DBG + 3 * a + b];
+        double dep_dbg[4];
+        for (int k = 0; k < 4; k++) dep_dbg[k] = pre[PRE_DEP_DBG + 9 * k + 3 * a + b];
         const double rit = L.RiT.m[3 * a + b];
         // pose_i (cols 0..5)
         JU(ILO_P + a, b) = -rit;               JU(ILO_P + a, 3 + b) = L.skP.m[3 * a + b];
@@ -205,12 +209,12 @@ CERB_HD void imu_leg_fill_ju_part(const IMULegLin &L, const double *pre, double 
         JU(ILO_V + a, 3 + b) = L.skV.m[3 * a + b];
         // sb_i (cols 6..14): v, ba, bg
         JU(ILO_P + a, 6 + b) = -rit * dt;
-        JU(ILO_P + a, 9 + b) = -pre[PRE_DP_DBA + 3 * a + b];
-        JU(ILO_P + a, 12 + b) = -pre[PRE_DP_DBG + 3 * a + b];
+        JU(ILO_P + a, 9 + b) = -dp_dba;
+        JU(ILO_P + a, 12 + b) = -dp_dbg;
         JU(ILO_R + a, 12 + b) = L.M2.m[3 * a + b];
         JU(ILO_V + a, 6 + b) = -rit;
-        JU(ILO_V + a, 9 + b) = -pre[PRE_DV_DBA + 3 * a + b];
-        JU(ILO_V + a, 12 + b) = -pre[PRE_DV_DBG + 3 * a + b];
+        JU(ILO_V + a, 9 + b) = -dv_dba;
+        JU(ILO_V + a, 12 + b) = -dv_dbg;
         // pose_j (cols 19..24)
         JU(ILO_P + a, 19 + b) = rit;
         JU(ILO_R + a, 22 + b) = L.M3.m[3 * a + b];
@@ -219,7 +223,7 @@ CERB_HD void imu_leg_fill_ju_part(const IMULegLin &L, const double *pre, double 
         for (int k = 0; k < 4 && !imu_only; k++) {
             JU(ILO_EPS1 + 3 * k + a, b) = -rit;
             JU(ILO_EPS1 + 3 * k + a, 3 + b) = L.skE.m[3 * a + b];
-            JU(ILO_EPS1 + 3 * k + a, 12 + b) = -pre[PRE_DEP_DBG + 9 * k + 3 * a + b];
+            JU(ILO_EPS1 + 3 * k + a, 12 + b) = -dep_dbg[k];
             JU(ILO_EPS1 + 3 * k + a, 19 + b) = rit;
         }
     } else if (part == 9) {
@@ -228,8 +232,10 @@ CERB_HD void imu_leg_fill_ju_part(const IMULegLin &L, const double *pre, double 
             JU(ILO_BA + a, 28 + a) = 1.0;  JU(ILO_BG + a, 31 + a) = 1.0;
         }
     } else if (!imu_only) {
+        double dr[12];
+        for (int k = 0; k < 12; k++) dr[k] = pre[PRE_DEP_DRHO + k];
         for (int k = 0; k < 4; k++) {
-            for (int a = 0; a < 3; a++) JU(ILO_EPS1 + 3 * k + a, 15 + k) = -pre[PRE_DEP_DRHO + 3 * k + a];
+            for (int a = 0; a < 3; a++) JU(ILO_EPS1 + 3 * k + a, 15 + k) = -dr[3 * k + a];
             JU(ILO_RHO1 + k, 15 + k) = -1.0;
             JU(ILO_RHO1 + k, 34 + k) = 1.0;
         }

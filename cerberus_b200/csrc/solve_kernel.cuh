@@ -56,7 +56,8 @@ CERB_HD long ws_W(int) { return 0; }                                        // [
 CERB_HD long ws_vecs(int F) { return (long)NX * F; }                        // 8 vectors of F: hh, gl, sl, Dl, ghl, gnl, stl, lamc
 CERB_HD long ws_prior(int F) { return (long)NX * F + 8L * F; }              // image of the prior Hessian in the layout of Hxx | Hxy | Ad | Bo
 CERB_HD long ws_chunks(int F) { return ws_prior(F) + HXX_SZ + HXY_SZ + 1859 + 1690; }   // feature chunk table (ints)
-CERB_HD long ws_size(int F) { return ws_chunks(F) + (F + 4) / 2 + 8; }
+CERB_HD long ws_imuplan(int F) { return (ws_chunks(F) + (F + 4) / 2 + 8 + 1) & ~1L; }                  // scatter plan of the IMU-leg Gram matrix (ints)
+CERB_HD long ws_size(int F) { return ws_imuplan(F) + 15 * 2 * 32 * 4 / 2 + 8; }                            // even: the plan is read as int4
 
 struct Smem {
     double *Hxx, *Hxy, *Ad, *Bo;            // 78x78, 78x143, 11x13x13, 10x13x13
@@ -111,6 +112,12 @@ CERB_D void load_geometry(const double *x, Smem &s, int tid) {
 
 struct ObsCtx { int start, nobs, off; double lam, pix, piy, vix, viy, tdi; };
 
+struct ObsVals { double px, py, vx, vy, td; int stereo; };
+CERB_D void obs_fetch(const double *obs, const int *stereo, int mo, int o, int cam, ObsVals &v) {
+    v.px = obs[(cam ? 4 : 0) * mo + o]; v.py = obs[(cam ? 5 : 1) * mo + o]; v.vx = obs[(cam ? 6 : 2) * mo + o]; v.vy = obs[(cam ? 7 : 3) * mo + o];
+    v.td = obs[8 * mo + o]; v.stereo = stereo[o];
+}
+
 // ---- visual part: cost only (candidate evaluation) -------------------------------------------------------
 CERB_NOINLINE double vision_cost(const SolveParams &P, int w, const double *x, const double *lam, int tid) {
     CERB_DYN_SMEM(double, smem_base);
@@ -129,29 +136,35 @@ CERB_NOINLINE double vision_cost(const SolveParams &P, int w, const double *x, c
         c.pix = obs[0 * mo + c.off]; c.piy = obs[1 * mo + c.off]; c.vix = obs[2 * mo + c.off]; c.viy = obs[3 * mo + c.off];
         c.tdi = obs[8 * mo + c.off];
         const int k0 = part ? 6 : 0, k1 = part ? c.nobs : (c.nobs < 6 ? c.nobs : 6);      // observations [k0, k1) of the track
-        double px[6], py[6], vx[6], vy[6], tj[6]; int st[6];
-        _Pragma("unroll")
-        for (int k = 0; k < 6; k++) {
-            const bool on = k0 + k < k1;
-            const int o = c.off + (on ? k0 + k : 0);
-            px[k] = obs[(cam ? 4 : 0) * mo + o]; py[k] = obs[(cam ? 5 : 1) * mo + o]; vx[k] = obs[(cam ? 6 : 2) * mo + o]; vy[k] = obs[(cam ? 7 : 3) * mo + o];
-            tj[k] = obs[8 * mo + o]; st[k] = stereo[o];
-        }
-        _Pragma("unroll")
-        for (int k = 0; k < 6; k++) {
-            if (k0 + k >= k1) continue;
-            const int j = c.start + k0 + k;
-            int kind;
-            if (k0 + k == 0) { if (cam == 0 || !st[k]) continue; kind = PROJ_K3; }
-            else if (cam == 0) kind = PROJ_K1;
-            else { if (!st[k]) continue; kind = PROJ_K2; }
-            double r[2];
-            const int i = c.start;
-            proj_eval(kind, ldm33(s.Rw + 9 * i), ld3(x + ST_POSE + 7 * i), ldm33(s.Rw + 9 * j), ld3(x + ST_POSE + 7 * j),
-                      ldm33(s.Rex), ld3(x + ST_EX), ldm33(s.Rex + 9), ld3(x + ST_EX + 7), c.lam, x[ST_TD], c.pix, c.piy, px[k], py[k],
-                      c.vix, c.viy, vx[k], vy[k], c.tdi, tj[k], P.sqrt_info, r, nullptr);
-            double cf; huber_weight(P.huber, r[0] * r[0] + r[1] * r[1], &cf);
-            cost += cf;
+        const double inv_l = 1.0 / c.lam;
+        const int i = c.start;
+        const d3 tic = ld3(x + ST_EX);
+        const double tdv = x[ST_TD];
+        const d3 pts_i_td = mk3(c.pix, c.piy, 1.0) - (tdv - c.tdi) * mk3(c.vix, c.viy, 0.0);
+        const d3 p_bi = mv33(ldm33(s.Rex), inv_l * pts_i_td) + tic;                          // anchor-frame body point: shared by all factors
+        const d3 p_w = mv33(ldm33(s.Rw + 9 * i), p_bi) + ld3(x + ST_POSE + 7 * i);
+        const double *Rcp = cam ? s.Rex + 9 : s.Rex;
+        const d3 tc = cam ? ld3(x + ST_EX + 7) : tic;
+        ObsVals cur, nxt;
+        cur.px = cur.py = cur.vx = cur.vy = cur.td = 0.0; cur.stereo = 0;
+        if (k0 < k1) obs_fetch(obs, stereo, mo, c.off + k0, cam, cur);
+        _Pragma("unroll 1")
+        for (int k = k0; k < k1; k++) {                                   // compact loop body (instruction cache), next observation in flight
+            nxt = cur;
+            if (k + 1 < k1) obs_fetch(obs, stereo, mo, c.off + k + 1, cam, nxt);
+            const bool k3 = (k == 0);
+            const bool on = k3 ? (cam == 1 && cur.stereo) : (cam == 0 || cur.stereo);
+            if (on) {
+                const int j = c.start + k;
+                const d3 p_bj = k3 ? p_bi : mTv33(ldm33(s.Rw + 9 * j), p_w - ld3(x + ST_POSE + 7 * j));
+                const d3 p_cj = mTv33(ldm33(Rcp), p_bj - tc);
+                const double iz = 1.0 / p_cj.z;
+                const double r0 = P.sqrt_info * (p_cj.x * iz - (cur.px - (tdv - cur.td) * cur.vx));
+                const double r1 = P.sqrt_info * (p_cj.y * iz - (cur.py - (tdv - cur.td) * cur.vy));
+                double cf; huber_weight(P.huber, r0 * r0 + r1 * r1, &cf);
+                cost += cf;
+            }
+            cur = nxt;
         }
     }
     return cost;
@@ -171,11 +184,6 @@ CERB_NOINLINE double vision_cost(const SolveParams &P, int w, const double *x, c
 // prescale: write W, hh, gl already multiplied by the Jacobi scales (s.sc for x, sl for the inverse depths), which are
 // fixed after iteration 0 -- saves a read-modify-write pass over W per linearisation.
 enum { VT_LD = 516, VT_COLS = 26, VT_SZ = VT_COLS * VT_LD, VP_SZ = 6 * 64, VJ_SZ = 4 * 64 };
-struct ObsVals { double px, py, vx, vy, td; int stereo; };
-CERB_D void obs_fetch(const double *obs, const int *stereo, int mo, int o, int cam, ObsVals &v) {
-    v.px = obs[(cam ? 4 : 0) * mo + o]; v.py = obs[(cam ? 5 : 1) * mo + o]; v.vx = obs[(cam ? 6 : 2) * mo + o]; v.vy = obs[(cam ? 7 : 3) * mo + o];
-    v.td = obs[8 * mo + o]; v.stereo = stereo[o];
-}
 // destination of local column c (0..7) of group g in the x numbering; -1: padding, -2: the residual column (gradient)
 CERB_D int vis_col_dest(int g, int c, int a, int j) {
     if (g == 0) return c < 6 ? 6 * a + c : (c == 6 ? X_TD : -2);
@@ -222,7 +230,7 @@ CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double 
         const double slf = (prescale && ev) ? sl[f] : 1.0;
         if (ev) {
             nobs = P.feat_nobs[(size_t)w * F + f]; off = P.feat_off[(size_t)w * F + f];
-            lamf = lam[f];
+            lamf = 1.0 / lam[f];                                          // inverse of the inverse depth, used by every factor of the track
             pix = obs[0 * mo + off]; piy = obs[1 * mo + off]; vix = obs[2 * mo + off]; viy = obs[3 * mo + off]; tdi = obs[8 * mo + off];
         }
         for (int k = lane; k < VP_SZ; k += 32) pp[k] = 0.0;
@@ -267,7 +275,7 @@ CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double 
                 const d3 pts_i = mk3(pix, piy, 1.0), vel_i = mk3(vix, viy, 0.0);
                 const d3 pts_i_td = pts_i - (tdv - tdi) * vel_i;
                 const double pjx_td = ov.px - (tdv - ov.td) * ov.vx, pjy_td = ov.py - (tdv - ov.td) * ov.vy;
-                const double inv_l = 1.0 / lamf;
+                const double inv_l = lamf;
                 const d3 p_ci = inv_l * pts_i_td;
                 const d3 p_bi = mv33(ldm33(s.Rex), p_ci) + tic;
                 d3 p_bj = p_bi;
@@ -386,7 +394,7 @@ CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double 
                             v0 = n0; v1 = n1; v2 = n2; v3 = n3;
                         }
                     }
-                    PH_MARK(28); PH_MARK_T(30, 128);
+                    PH_MARK(28);
                     const int o = (lane >> 2) * 8 + 2 * (lane & 3);
                     pp[0 * 64 + o] += acc[0][0]; pp[0 * 64 + o + 1] += acc[0][1];      // (g0, g0)
                     pp[1 * 64 + o] += acc[2][0]; pp[1 * 64 + o + 1] += acc[2][1];      // (g0, g2)
@@ -404,7 +412,7 @@ CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double 
                 }
             }
             if (wrow && cam == 1) for (int k = 0; k < 6; k++) W[(size_t)(6 * j + k) * F + f] = wprev[k] + wjv[k] * (prescale ? s.sc[6 * j + k] * slf : 1.0);
-            PH_MARK(29); PH_MARK_T(31, 128);
+            PH_MARK(29);
             __syncthreads();
             PH_MARK(22);
             // --- frame-dependent blocks: sum over the four warps of each frame (fixed order) and scatter ----------------------------
@@ -521,6 +529,18 @@ CERB_D int imu_col_dest(int i, int c) {
     return -(1 + NYB * (i + 1) + (c - 25));
 }
 // add v to H at (a, b) given destinations in the x / y numbering (a, b come from upper-triangular local order)
+// addresses of H(a, b) (a1: the mirrored entry of a diagonal Hyy block, or null)
+CERB_D void scatter_addr(const Smem &s, int da, int db, double **a0, double **a1) {
+    *a1 = nullptr;
+    if (da >= 0 && db >= 0) { *a0 = (da <= db) ? s.Hxx + da * NX + db : s.Hxx + db * NX + da; return; }
+    if (da >= 0) { *a0 = s.Hxy + da * NY + (-db - 1); return; }
+    if (db >= 0) { *a0 = s.Hxy + db * NY + (-da - 1); return; }
+    const int ya = -da - 1, yb = -db - 1;
+    const int fa = ya / NYB, fb = yb / NYB, ka = ya % NYB, kb = yb % NYB;
+    if (fa == fb) { *a0 = s.Ad + fa * 169 + ka * NYB + kb; if (ka != kb) *a1 = s.Ad + fa * 169 + kb * NYB + ka; }
+    else if (fb == fa + 1) *a0 = s.Bo + fa * 169 + ka * NYB + kb;
+    else *a0 = s.Bo + fb * 169 + kb * NYB + ka;
+}
 CERB_D void scatter_H(Smem &s, int da, int db, double v) {
     if (da >= 0 && db >= 0) { if (da <= db) s.Hxx[da * NX + db] += v; else s.Hxx[db * NX + da] += v; return; }
     if (da >= 0) { s.Hxy[da * NY + (-db - 1)] += v; return; }
@@ -532,13 +552,16 @@ CERB_D void scatter_H(Smem &s, int da, int db, double v) {
     else s.Bo[fb * 169 + kb * NYB + ka] += v;
 }
 
-// IMU-leg factors.  Per factor: Ju (unwhitened 31 x 38 tangent Jacobian + residual column, expanded from IMULegLin) is
-// whitened, Jw = S Ju, and the Gram matrix Jw^T Jw (39 x 39: Hessian blocks, gradient column, cost corner) is scattered
-// into Hxx / Hxy / Hyy / g.  Both products are dense contractions (32 x 32 x 40 and 40 x 32 x 40 after padding) and run on
-// the fp64 tensor cores; S of the next factor is prefetched into registers while the current one is processed.
-// Scratch (s.Ju .. s.wj, 4281 doubles): SP [32][36] sqrt_info (zero padded) | JuP [32][44] | JwP [32][44] | 2 x 128 staged
-// preintegration headers (the constants the Jacobian expansion reads; fetched one factor ahead like S).
-enum { IMU_LDS = 36, IMU_LDJ = 44, IMU_SP = 0, IMU_JU = 32 * 36, IMU_JW = 32 * 36 + 32 * 44, IMU_PRE = 32 * 36 + 2 * 32 * 44 };
+// Inertial linearisation.  Warps 0..2 each run whole IMU-leg factors on their own (warp-synchronous, no block barriers):
+//   Ju (unwhitened 31 x 38 tangent Jacobian + residual column, expanded from IMULegLin) -> Jw = S Ju in place -> Gram matrix
+//   Jw^T Jw (39 x 39: Hessian blocks, gradient column, cost corner) -> scatter into Hxx / Hxy / Hyy / g.
+// Both products are dense contractions (32 x 32 x 40 and 40 x 32 x 40 after padding) on the fp64 tensor cores; the
+// upper-triangular S is fetched from HBM/L2 straight into its A-fragment registers (one factor ahead), Ju / Jw live in a
+// per-warp [32][44] tile.  Factors that share parameter blocks (i, i + 1) are never in flight together: round r handles
+// factors {r, r + 4, r + 8}, rounds are separated by a barrier among the three warps.
+// Warps 3..7 meanwhile evaluate the prior (r = r0 + J0 dx, g_prior = J0^T r into a separate vector that is added at the end;
+// its constant Hessian is already part of the initial H).
+enum { IMU_LDJ = 44, IMU_TILE = 32 * 44, IMU_WARPS = 3, PRIOR_THREADS = SOLVE_THREADS - 32 * IMU_WARPS };
 CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const double *x, int tid) {
     CERB_DYN_SMEM(double, smem_base);
     Smem s; smem_carve(smem_base, s);
@@ -546,94 +569,142 @@ CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const doubl
     PH_DECL();
     imu_lin_all(P, s, w, x, true, tid);
     PH_MARK(25);
-    double *SP = s.Ju + IMU_SP, *JuP = s.Ju + IMU_JU, *JwP = s.Ju + IMU_JW;
     const int wid = tid >> 5, lane = tid & 31;
-    for (int k = tid; k < IMU_JW; k += SOLVE_THREADS) s.Ju[k] = 0.0;        // SP padding and JuP
-    double *preS = s.Ju + IMU_PRE;
-    double sreg[4], preg = 0.0;
-    {   // prefetch sqrt_info of factor 0 (upper triangular; the lower part is masked when staged) and the headers of factors 0, 1
-        const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + 0) * 961;
-        for (int q = 0; q < 4; q++) { const int k = tid + SOLVE_THREADS * q; sreg[q] = (k < 961) ? S[k] : 0.0; }
-        const double *pre0 = P.pre + ((size_t)w * CERB_WINDOW + 0) * PRE_STRIDE;
-        if (tid < 128) { preS[tid] = pre0[tid]; preg = pre0[PRE_STRIDE + tid]; }
+    double *gp = s.gn;                                                  // prior gradient [NRP]; gn | stp | yv are idle during a linearisation
+    double *ppart = s.stp;                                              // [4][PRIOR_LD] partial sums of J0 dx (stp | yv)
+    for (int k = tid; k < NRP; k += SOLVE_THREADS) gp[k] = 0.0;
+    __syncthreads();
+    if (wid < IMU_WARPS) {
+        double *Jt = s.Ju + IMU_TILE * wid;
+        // scatter plan of this lane (built once per launch), kept in registers: x = kind | offset(i = 0) << 2, y = stride | (mirror delta + 256) << 12
+        int plx[30], ply[30];
+        {
+            const int *plan = reinterpret_cast<const int *>(P.ws + (size_t)blockIdx.x * P.ws_stride + ws_imuplan(P.maxF));
+            _Pragma("unroll")
+            for (int q = 0; q < 30; q++) { plx[q] = __ldg(plan + (2 * q) * 32 + lane); ply[q] = __ldg(plan + (2 * q + 1) * 32 + lane); }
+        }
+        double sa[20];
+        auto load_S = [&](int i) {      // A-fragments of the upper-triangular sqrt_info: block row mi needs k-steps ks >= 2 mi
+            const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + i) * 961;
+            int q = 0;
+            _Pragma("unroll")
+            for (int mi = 0; mi < 4; mi++)
+                _Pragma("unroll")
+                for (int ks = 2 * mi; ks < 8; ks++) {
+                    const int r = 8 * mi + (lane >> 2), c = 4 * ks + (lane & 3);
+                    sa[q++] = (r < 31 && c < 31 && c >= r) ? S[r * 31 + c] : 0.0;
+                }
+        };
+        load_S(wid * 4);
+        double sdt[4];                                                    // sum_dt of this warp's factors, fetched up front
+        _Pragma("unroll")
+        for (int rnd = 0; rnd < 4; rnd++) { const int i = rnd + 4 * wid; sdt[rnd] = (i < CERB_WINDOW) ? P.pre[((size_t)w * CERB_WINDOW + i) * PRE_STRIDE + PRE_SUM_DT] : 1e30; }
+        _Pragma("unroll")
+        for (int rnd = 0; rnd < 4; rnd++) {
+            const int i = rnd + 4 * wid;
+            const double *pre = P.pre + ((size_t)w * CERB_WINDOW + (i < CERB_WINDOW ? i : 0)) * PRE_STRIDE;
+            if (i < CERB_WINDOW && !(sdt[rnd] > 10.0)) {                  // estimator.cpp:1119
+                // ---- expand Ju ----------------------------------------------------------------------------------------------
+                for (int k = lane; k < IMU_TILE; k += 32) Jt[k] = 0.0;
+                __syncwarp();
+                if (lane < 11) imu_leg_fill_ju_part(*reinterpret_cast<const IMULegLin *>(s.lin + 96 * i), pre, Jt, IMU_LDJ, lane);
+                if (lane < 31) Jt[lane * IMU_LDJ + 38] = s.lin[96 * i + lane];          // residual column
+                __syncwarp();
+                PH_MARK(32);
+                // ---- Jw = S Ju, one 8-column block at a time, in place --------------------------------------------------------
+                for (int ni = 0; ni < 5; ni++) {
+                    double b[8];
+                    _Pragma("unroll")
+                    for (int ks = 0; ks < 8; ks++) b[ks] = Jt[(4 * ks + (lane & 3)) * IMU_LDJ + 8 * ni + (lane >> 2)];
+                    __syncwarp();
+                    double c[4][2];
+                    int q = 0;
+                    _Pragma("unroll")
+                    for (int mi = 0; mi < 4; mi++) {
+                        c[mi][0] = 0.0; c[mi][1] = 0.0;
+                        _Pragma("unroll")
+                        for (int ks = 2 * mi; ks < 8; ks++) { CERB_DMMA(c[mi][0], c[mi][1], sa[q], b[ks], c[mi][0], c[mi][1]); q++; }
+                    }
+                    _Pragma("unroll")
+                    for (int mi = 0; mi < 4; mi++) { double *o = Jt + (8 * mi + (lane >> 2)) * IMU_LDJ + 8 * ni + 2 * (lane & 3); o[0] = c[mi][0]; o[1] = c[mi][1]; }
+                    __syncwarp();
+                }
+                PH_MARK(33);
+                if (i + 1 < CERB_WINDOW && rnd < 3) load_S(i + 1);         // next round's factor (latency hidden behind the Gram pass)
+                // ---- Gram matrix of Jw (40 x 40, 15 upper blocks, K = 32) -----------------------------------------------------------
+                double acc[15][2];
+                _Pragma("unroll")
+                for (int k = 0; k < 15; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
+                for (int ks = 0; ks < 8; ks++) {
+                    double f[5];
+                    _Pragma("unroll")
+                    for (int n = 0; n < 5; n++) f[n] = Jt[(4 * ks + (lane & 3)) * IMU_LDJ + 8 * n + (lane >> 2)];
+                    int q = 0;
+                    _Pragma("unroll")
+                    for (int mi = 0; mi < 5; mi++)
+                        _Pragma("unroll")
+                        for (int ni = mi; ni < 5; ni++) { CERB_DMMA(acc[q][0], acc[q][1], f[mi], f[ni], acc[q][0], acc[q][1]); q++; }
+                }
+                PH_MARK(34);
+                // scatter through the per-lane plan (built once per launch: every destination is affine in the factor index i)
+                _Pragma("unroll")
+                for (int q = 0; q < 15; q++)
+                    _Pragma("unroll")
+                    for (int e = 0; e < 2; e++) {
+                        const int kind = plx[2 * q + e] & 3, o0 = (plx[2 * q + e] >> 2) + i * (ply[2 * q + e] & 4095);
+                        const double v = acc[q][e];
+                        if (kind == 1) cost += 0.5 * v;
+                        else if (kind >= 2) {
+                            smem_base[o0] += v;
+                            if (kind == 3) smem_base[o0 + (ply[2 * q + e] >> 12) - 256] += v;
+                        }
+                    }
+                PH_MARK(35);
+            } else if (i + 1 < CERB_WINDOW && rnd < 3) load_S(i + 1);
+            CERB_BAR_SYNC(2, 32 * IMU_WARPS);
+            PH_MARK(36);                             // factors of the next round touch the blocks of this one
+        }
+        PH_MARK(30);
+    } else {
+        // ---- prior: r = r0 + J0 dx, g_prior = J0^T r (threads 96..255) ----------------------------------------------------------------
+        const int *meta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
+        if (meta[0]) {
+            const int t5 = tid - 32 * IMU_WARPS, n = meta[1], nb = meta[2];
+            const double *J = P.prior_J + (size_t)w * PRIOR_LD * PRIOR_LD, *r0 = P.prior_r + (size_t)w * PRIOR_LD, *x0 = P.prior_x0 + (size_t)w * 16 * 9;
+            if (t5 < nb) {
+                const int kind = meta[4 + 3 * t5], index = meta[5 + 3 * t5], col = meta[6 + 3 * t5];
+                prior_block_dx(kind, x + prior_block_state_offset(kind, index), x0 + 9 * t5, s.pdx + col);
+            }
+            CERB_BAR_SYNC(3, PRIOR_THREADS);
+            const int kc = (n + 3) / 4;
+            for (int e = t5; e < 4 * n; e += PRIOR_THREADS) {
+                const int p = e / n, i = e % n;
+                const int k1 = (p + 1) * kc < n ? (p + 1) * kc : n;
+                double t = 0.0;
+                for (int k = p * kc; k < k1; k++) t += J[(size_t)k * n + i] * s.pdx[k];
+                ppart[p * PRIOR_LD + i] = t;
+            }
+            CERB_BAR_SYNC(3, PRIOR_THREADS);
+            for (int i = t5; i < n; i += PRIOR_THREADS) {
+                const double t = (((r0[i] + ppart[i]) + ppart[PRIOR_LD + i]) + ppart[2 * PRIOR_LD + i]) + ppart[3 * PRIOR_LD + i];
+                s.pr[i] = t; cost += 0.5 * t * t;
+            }
+            CERB_BAR_SYNC(3, PRIOR_THREADS);
+            // one warp per column of J0 (contiguous, coalesced), lanes stride the rows, fixed-order shuffle reduction
+            for (int c = wid - IMU_WARPS; c < n; c += PRIOR_THREADS / 32) {
+                double t = 0.0;
+                for (int k = lane; k < n; k += 32) t += J[(size_t)c * n + k] * s.pr[k];
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_sync(0xffffffffu, t, (lane + o) & 31);
+                const int d = s.ti[c];
+                if (lane == 0 && d != (1 << 20)) gp[d >= 0 ? d : NX + (-d - 1)] += t;
+            }
+        }
+        PH_MARK_T(31, 96);
     }
     __syncthreads();
-    for (int i = 0; i < CERB_WINDOW; i++) {
-        const double *pre = preS + 128 * (i & 1);                           // staged header of factor i
-        const bool skip = pre[PRE_SUM_DT] > 10.0;                          // estimator.cpp:1119 (uniform across the CTA)
-        if (tid < 128 && i + 1 < CERB_WINDOW) {
-            preS[128 * ((i + 1) & 1) + tid] = preg;                         // header of factor i + 1 (its slot was last read before the previous barrier)
-            if (i + 2 < CERB_WINDOW) preg = P.pre[((size_t)w * CERB_WINDOW + i + 2) * PRE_STRIDE + tid];
-        }
-        // ---- stage S (padded, lower part masked) and expand Ju ----------------------------------------------------------
-        if (!skip) {
-            for (int q = 0; q < 4; q++) { const int k = tid + SOLVE_THREADS * q; if (k < 961) { const int r = k / 31, c = k % 31; SP[r * IMU_LDS + c] = (c >= r) ? sreg[q] : 0.0; } }
-            if (tid < 11) imu_leg_fill_ju_part(*reinterpret_cast<const IMULegLin *>(s.lin + 96 * i), pre, JuP, IMU_LDJ, tid);
-            else if (tid >= 32 && tid < 63) JuP[(tid - 32) * IMU_LDJ + 38] = s.lin[96 * i + (tid - 32)];       // residual column
-        }
-        if (i + 1 < CERB_WINDOW) {
-            const double *S = P.sinfo + ((size_t)w * CERB_WINDOW + i + 1) * 961;
-            for (int q = 0; q < 4; q++) { const int k = tid + SOLVE_THREADS * q; sreg[q] = (k < 961) ? S[k] : 0.0; }
-        }
-        if (skip) { __syncthreads(); continue; }                           // (the barrier orders the header staging above)
-        __syncthreads();
-        // ---- Jw = S Ju: 4 x 5 output blocks of 8 x 8; S is upper triangular, so block row mi needs k >= 8 mi only ------------
-        for (int t = 0; t < 3; t++) {
-            int mi, ni;
-            if (t == 0) { mi = wid & 3; ni = wid >> 2; }
-            else if (t == 1) { mi = 3 - (wid & 3); ni = 2 + (wid >> 2); }
-            else { if (wid >= 4) break; mi = wid; ni = 4; }
-            double a0 = 0.0, a1 = 0.0;
-            for (int ks = 2 * mi; ks < 8; ks++) {
-                const double av = SP[(8 * mi + (lane >> 2)) * IMU_LDS + 4 * ks + (lane & 3)];
-                const double bv = JuP[(4 * ks + (lane & 3)) * IMU_LDJ + 8 * ni + (lane >> 2)];
-                CERB_DMMA(a0, a1, av, bv, a0, a1);
-            }
-            double *o = JwP + (8 * mi + (lane >> 2)) * IMU_LDJ + 8 * ni + 2 * (lane & 3);
-            o[0] = a0; o[1] = a1;
-        }
-        __syncthreads();
-        // ---- Gram matrix of Jw (40 x 40, 15 upper blocks, K = 32) and scatter ---------------------------------------------------
-        for (int b = wid; b < 15; b += 8) {
-            int mi = 0, idx = b;
-            while (idx >= 5 - mi) { idx -= 5 - mi; mi++; }
-            const int ni = mi + idx;
-            double a0 = 0.0, a1 = 0.0;
-            for (int ks = 0; ks < 8; ks++) {
-                const double av = JwP[(4 * ks + (lane & 3)) * IMU_LDJ + 8 * mi + (lane >> 2)];
-                const double bv = JwP[(4 * ks + (lane & 3)) * IMU_LDJ + 8 * ni + (lane >> 2)];
-                CERB_DMMA(a0, a1, av, bv, a0, a1);
-            }
-            const int la = 8 * mi + (lane >> 2);
-            for (int e = 0; e < 2; e++) {
-                const int lb = 8 * ni + 2 * (lane & 3) + e;
-                const double acc = e ? a1 : a0;
-                if (la > lb || lb > 38) continue;
-                if (la == 38) { cost += 0.5 * acc; continue; }
-                const int da = imu_col_dest(i, la);
-                if (lb == 38) { if (da >= 0) s.g[da] += acc; else s.g[NX + (-da - 1)] += acc; continue; }
-                scatter_H(s, da, imu_col_dest(i, lb), acc);
-            }
-        }
-        __syncthreads();
-    }
     PH_MARK(26);
-    // ---- prior: r = r0 + J0 dx, g += J0^T r.  Its Hessian J0^T J0 is constant and already part of the initial H (prior image).
-    const int *meta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
-    if (meta[0]) {
-        cost += prior_residual(P, s, w, x, tid);
-        const int n = meta[1];
-        const double *J = P.prior_J + (size_t)w * PRIOR_LD * PRIOR_LD;
-        // one warp per column of J0 (contiguous, coalesced), lanes stride the rows, fixed-order shuffle reduction
-        for (int c = wid; c < n; c += SOLVE_THREADS / 32) {
-            double t = 0.0;
-            for (int k = lane; k < n; k += 32) t += J[(size_t)c * n + k] * s.pr[k];
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_sync(0xffffffffu, t, (lane + o) & 31);
-            const int d = s.ti[c];
-            if (lane == 0 && d != (1 << 20)) { if (d >= 0) s.g[d] += t; else s.g[NX + (-d - 1)] += t; }
-        }
-        __syncthreads();
-    }
+    for (int k = tid; k < NR; k += SOLVE_THREADS) s.g[k] += gp[k];
+    __syncthreads();
     PH_MARK(27);
     return cost;
 }
@@ -681,9 +752,38 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
     double *sca = s.sca;
     // scalar slots
     enum { S_RADIUS = 0, S_MU, S_REUSE, S_XCOST, S_CCOST, S_ALPHA, S_GNORM2, S_GNNORM2, S_GDOTGN, S_MODEL, S_STEPNORM, S_XNORM, S_DLNORM,
-           S_OK, S_DONE, S_TERM, S_ITER, S_NSUCC, S_INVALID, S_GMAX, S_INIT_COST, S_P, S_Q };
+           S_OK, S_DONE, S_TERM, S_ITER, S_NSUCC, S_INVALID, S_GMAX, S_INIT_COST, S_P, S_Q, S_VHV };
 
     PH_DECL();
+    if (tid < 32) {
+        // Scatter plan of the 40 x 40 IMU-leg Gram matrix (inertial_linearize): lane `tid` holds, for block q = (mi, ni) and
+        // e = 0, 1, the entry (la, lb) = (8 mi + lane / 4, 8 ni + 2 (lane % 4) + e).  Its destination in Hxx / Hxy / Hyy / g is
+        // affine in the factor index i, so the plan stores two packed ints: kind | offset(i = 0) << 2 and stride | (mirror delta + 256) << 12
+        // (in doubles from the start of shared memory); kind 0: nothing, 1: cost corner, 2: one destination, 3: two (diagonal Hyy block).
+        int *plan = reinterpret_cast<int *>(ws + ws_imuplan(F));
+        int q = 0;
+        for (int mi = 0; mi < 5; mi++)
+            for (int ni = mi; ni < 5; ni++, q++)
+                for (int e = 0; e < 2; e++) {
+                    const int la = 8 * mi + (tid >> 2), lb = 8 * ni + 2 * (tid & 3) + e;
+                    int px = 0, py = 0;
+                    if (la <= lb && lb <= 38) {
+                        if (la == 38) px = 1;
+                        else {
+                            double *p0[2], *p1[2];
+                            for (int i = 0; i < 2; i++) {
+                                const int da = imu_col_dest(i, la);
+                                if (lb == 38) { p0[i] = da >= 0 ? s.g + da : s.g + NX + (-da - 1); p1[i] = nullptr; }
+                                else scatter_addr(s, da, imu_col_dest(i, lb), &p0[i], &p1[i]);
+                            }
+                            px = (p1[0] ? 3 : 2) | ((int)(p0[0] - smem_base) << 2);
+                            py = (int)(p0[1] - p0[0]) | (((p1[0] ? (int)(p1[0] - p0[0]) : 0) + 256) << 12);
+                        }
+                    }
+                    plan[(2 * (q * 2 + e)) * 32 + tid] = px; plan[(2 * (q * 2 + e) + 1) * 32 + tid] = py;
+                }
+    }
+    __syncthreads();
     for (int w = blockIdx.x; w < P.n_windows; w += gridDim.x) {
         const int nF = P.n_features[w];
         const bool ex_open = (P.flags[w] & 1) != 0;
@@ -818,42 +918,33 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
 
             // =============================== DoglegStrategy::ComputeStep ===================================
             if (sca[S_REUSE] == 0.0) {
-                // diagonal, gradient / D, Cauchy point
+                // diagonal, gradient / D, scaled gradient v (kept in s.stp: the Cauchy point's v^T H v is finished later, see below)
                 for (int k = tid; k < NR; k += SOLVE_THREADS) {
                     const double d = (k < NX) ? s.Hxx[k * NX + k] : s.Ad[((k - NX) / NYB) * 169 + ((k - NX) % NYB) * (NYB + 1)];
                     const double D = sqrt(fmin(fmax(d, 1e-6), 1e32));
-                    s.D[k] = D; s.gh[k] = s.g[k] / D; s.yv[k] = s.gh[k] / D;      // yv = v = scaled gradient
+                    s.D[k] = D; s.gh[k] = s.g[k] / D; s.stp[k] = s.gh[k] / D;
                 }
                 for (int f = tid; f < nF; f += SOLVE_THREADS) { const double D = sqrt(fmin(fmax(hh[f], 1e-6), 1e32)); Dl[f] = D; ghl[f] = gl[f] / D; stl[f] = ghl[f] / D; }
                 __syncthreads();
-                double part[2] = {0.0, 0.0};     // [0] v^T H v  [1] ||gh||^2
-                for (int k = tid; k < NX * NX; k += SOLVE_THREADS) part[0] += s.yv[k / NX] * s.Hxx[k] * s.yv[k % NX];
-                for (int k = tid; k < NX * NY; k += SOLVE_THREADS) part[0] += 2.0 * s.yv[k / NY] * s.Hxy[k] * s.yv[NX + k % NY];
-                for (int k = tid; k < 1859; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; part[0] += s.yv[NX + NYB * f + a] * s.Ad[k] * s.yv[NX + NYB * f + b]; }
-                for (int k = tid; k < 1690; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; part[0] += 2.0 * s.yv[NX + NYB * f + a] * s.Bo[k] * s.yv[NX + NYB * (f + 1) + b]; }
-                for (int f = tid; f < nF; f += SOLVE_THREADS) {
-                    double wv = 0.0;
-                    for (int a = 0; a < NX; a++) wv += W[(size_t)a * F + f] * s.yv[a];
-                    part[0] += 2.0 * stl[f] * wv + hh[f] * stl[f] * stl[f];
-                    part[1] += ghl[f] * ghl[f];
-                }
+                // ||gh||^2 and the Hyy part of v^T H v (Hyy is about to be factored in place); the Hxx / Hxy / W parts are
+                // computed by warps 1..7 in the shadow of warp 0's chain factorisation
+                double part[2] = {0.0, 0.0};     // [0] v_y^T Hyy v_y  [1] ||gh||^2
+                for (int k = tid; k < 1859; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; part[0] += s.stp[NX + NYB * f + a] * s.Ad[k] * s.stp[NX + NYB * f + b]; }
+                for (int k = tid; k < 1690; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; part[0] += 2.0 * s.stp[NX + NYB * f + a] * s.Bo[k] * s.stp[NX + NYB * (f + 1) + b]; }
+                for (int f = tid; f < nF; f += SOLVE_THREADS) part[1] += ghl[f] * ghl[f];
                 for (int k = tid; k < NR; k += SOLVE_THREADS) part[1] += s.gh[k] * s.gh[k];
                 double tot[2];
                 block_sum<2>(part, s.red, tot, tid);
-                if (tid == 0) { sca[S_GNORM2] = tot[1]; sca[S_ALPHA] = tot[1] / tot[0]; }
-                __syncthreads();
+                if (tid == 0) { sca[S_GNORM2] = tot[1]; sca[S_VHV] = tot[0]; sca[S_OK] = 1; }      // S_OK: a failure below is an invalid step: mu *= 10, re-linearise
                 PH_MARK(4);
 
                 // ---- Gauss-Newton step: (H~ + mu D^2) y = g~, retry with mu *= 10 on failure ----------------
                 {
                     const double mu = sca[S_MU];
-                    if (tid == 0) sca[S_OK] = 1;        // a failure below is handled as an invalid step: mu *= 10, re-linearise
-                    __syncthreads();
-                    // rhs: yv[0..NR) = g~ ; regularise the diagonals
+                    // rhs: yv[0..NR) = g~ ; regularise the diagonal of Hyy (that of Hxx: warps 1..7, after their share of v^T H v)
                     for (int k = tid; k < NR; k += SOLVE_THREADS) {
                         s.yv[k] = s.g[k];
-                        if (k < NX) s.Hxx[k * NX + k] += mu * s.D[k] * s.D[k];
-                        else s.Ad[((k - NX) / NYB) * 169 + ((k - NX) % NYB) * (NYB + 1)] += mu * s.D[k] * s.D[k];
+                        if (k >= NX) s.Ad[((k - NX) / NYB) * 169 + ((k - NX) % NYB) * (NYB + 1)] += mu * s.D[k] * s.D[k];
                     }
                     __syncthreads();
                     if (tid < 32) {
@@ -919,7 +1010,22 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                         const int LDW = 36;
                         double *tw = s.Ju;                         // 80 x 36 tile (aliases Ju .. red, unused during the solve)
                         double *sinv = s.wj;                       // <= CERB features: 1 / sqrt(h + mu D^2)   (wj: 1024 doubles)
-                        for (int f = t2; f < nF; f += n2) sinv[f] = 1.0 / sqrt(hh[f] + mu * Dl[f] * Dl[f]);
+                        {   // Cauchy point: v_x^T Hxx v_x + 2 v_x^T Hxy v_y + lambda terms (H still unregularised / unfactored here)
+                            const double *v = s.stp;
+                            double pv = 0.0;
+                            for (int k = t2; k < NX * NX; k += n2) pv += v[k / NX] * s.Hxx[k] * v[k % NX];
+                            for (int k = t2; k < NX * NY; k += n2) pv += 2.0 * v[k / NY] * s.Hxy[k] * v[NX + k % NY];
+                            for (int f = t2; f < nF; f += n2) {
+                                double wv = 0.0;
+                                for (int a = 0; a < NX; a++) wv += W[(size_t)a * F + f] * v[a];
+                                pv += 2.0 * stl[f] * wv + hh[f] * stl[f] * stl[f];
+                            }
+                            for (int o = 16; o > 0; o >>= 1) pv += __shfl_sync(0xffffffffu, pv, (lane + o) & 31);
+                            if (lane == 0) s.lin[wq] = pv;
+                            CERB_BAR_SYNC(1, n2);
+                            for (int k = t2; k < NX; k += n2) s.Hxx[k * NX + k] += mu * s.D[k] * s.D[k];
+                        }
+                        for (int f = t2; f < nF; f += n2) sinv[f] = rsqrt(hh[f] + mu * Dl[f] * Dl[f]);
                         double acc[8][2];
                         for (int k = 0; k < 8; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
                         int tmi[8], tni[8];
@@ -963,6 +1069,11 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                         PH_MARK_T(7, 32);
                     }
                     __syncthreads();
+                    if (tid == 0) {
+                        double vhv = sca[S_VHV];
+                        for (int k = 0; k < 7; k++) vhv += s.lin[k];
+                        sca[S_ALPHA] = sca[S_GNORM2] / vhv;
+                    }
                     PH_MARK(5);
                     // ---- T = L^-1 Hyx (row a of Hxy in place), and the same for the y part of the rhs (row 78) ----
                     if (tid <= NX) {

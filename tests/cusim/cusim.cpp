@@ -7,7 +7,15 @@ namespace cusim {
 unsigned char *dyn_smem_ptr = nullptr;
 pthread_barrier_t block_barrier;
 pthread_barrier_t *warp_barriers = nullptr;
-pthread_barrier_t named_barrier;
+struct NamedBar { std::mutex m; std::condition_variable cv; int waiting = 0; unsigned gen = 0; };
+static NamedBar named_bars[16];
+void named_sync(int id, int n) {
+    NamedBar &b = named_bars[id & 15];
+    std::unique_lock<std::mutex> lk(b.m);
+    const unsigned g = b.gen;
+    if (++b.waiting == n) { b.waiting = 0; b.gen++; b.cv.notify_all(); }
+    else b.cv.wait(lk, [&] { return b.gen != g; });
+}
 double *warp_scratch = nullptr;
 void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body) {
     blockDim.x = block; gridDim.x = grid;
@@ -20,7 +28,6 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
     std::vector<double> wsc(nwarps * 64);
     warp_scratch = wsc.data();
     pthread_barrier_init(&block_barrier, nullptr, block);
-    pthread_barrier_init(&named_barrier, nullptr, block > 32 ? block - 32 : 1);
     // blocks run one after another (shared / static storage is per block), threads of a block concurrently
     for (unsigned b = 0; b < grid; b++) {
         std::vector<std::thread> th;
@@ -30,7 +37,6 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
         for (auto &x : th) x.join();
     }
     pthread_barrier_destroy(&block_barrier);
-    pthread_barrier_destroy(&named_barrier);
     for (auto &x : wb) pthread_barrier_destroy(&x);
 }
 }  // namespace cusim

@@ -13,9 +13,12 @@
 #include <vector>
 #include <functional>
 #include <pthread.h>
+#include <mutex>
+#include <condition_variable>
 #include <chrono>
 
 struct cusim_dim3 { unsigned x = 1, y = 1, z = 1; };
+struct alignas(16) int4 { int x, y, z, w; };
 extern thread_local cusim_dim3 threadIdx;
 extern thread_local cusim_dim3 blockIdx;
 extern cusim_dim3 blockDim, gridDim;
@@ -38,9 +41,9 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
 #define CERB_LAUNCH(kernel, grid, block, smem, stream, ...) cusim::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
 inline void __syncthreads() { pthread_barrier_wait(&cusim::block_barrier); }
 inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cusim::warp_barriers[threadIdx.x / 32]); }
-// named barrier used by warps 1..7 of the solve kernel (224 threads)
-namespace cusim { extern pthread_barrier_t named_barrier; }
-#define CERB_BAR_SYNC(id, nthreads) pthread_barrier_wait(&cusim::named_barrier)
+// named barriers (bar.sync id, nthreads) among subsets of the warps of a block
+namespace cusim { void named_sync(int id, int nthreads); }
+#define CERB_BAR_SYNC(id, nthreads) cusim::named_sync((id), (nthreads))
 // emulation of mma.sync.m8n8k4.f64 across the 32 threads of a (simulated) warp
 namespace cusim { extern double *warp_scratch; }
 inline void cusim_dmma(double &d0, double &d1, double a, double b, double c0, double c1) {
