@@ -150,13 +150,13 @@ CERB_HD void imu_leg_linearize(const double *pre, const double *pose_i, const do
     const d3 Vi = ld3(sb_i), Bai = ld3(sb_i + 3), Bgi = ld3(sb_i + 6);
     const d3 Vj = ld3(sb_j), Baj = ld3(sb_j + 3), Bgj = ld3(sb_j + 6);
     const d3 g = ld3(G);
-    const double dt = pre[PRE_SUM_DT];
-    const d3 dba = Bai - ld3(pre + PRE_BA), dbg = Bgi - ld3(pre + PRE_BG);
-    const m33 dq_dbg = ldm33(pre + PRE_DQ_DBG);
-    const quat gamma = ldq(pre + PRE_DQ);
+    const double dt = ldro(pre + PRE_SUM_DT);
+    const d3 dba = Bai - ld3ro(pre + PRE_BA), dbg = Bgi - ld3ro(pre + PRE_BG);
+    const m33 dq_dbg = ldm33ro(pre + PRE_DQ_DBG);
+    const quat gamma = mkq(ldro(pre + PRE_DQ), ldro(pre + PRE_DQ + 1), ldro(pre + PRE_DQ + 2), ldro(pre + PRE_DQ + 3));
     const quat cgamma = qmul(gamma, qdelta(mv33(dq_dbg, dbg)));
-    const d3 cdv = ld3(pre + PRE_DV) + mv33(ldm33(pre + PRE_DV_DBA), dba) + mv33(ldm33(pre + PRE_DV_DBG), dbg);
-    const d3 cdp = ld3(pre + PRE_DP) + mv33(ldm33(pre + PRE_DP_DBA), dba) + mv33(ldm33(pre + PRE_DP_DBG), dbg);
+    const d3 cdv = ld3ro(pre + PRE_DV) + mv33(ldm33ro(pre + PRE_DV_DBA), dba) + mv33(ldm33ro(pre + PRE_DV_DBG), dbg);
+    const d3 cdp = ld3ro(pre + PRE_DP) + mv33(ldm33ro(pre + PRE_DP_DBA), dba) + mv33(ldm33ro(pre + PRE_DP_DBG), dbg);
     const quat Qi_inv = qinv(Qi);
     const d3 aP = qrot(Qi_inv, (0.5 * dt * dt) * g + Pj - Pi - dt * Vi);
     const d3 aV = qrot(Qi_inv, dt * g + Vj - Vi);
@@ -167,14 +167,14 @@ CERB_HD void imu_leg_linearize(const double *pre, const double *pose_i, const do
     st3(r + ILO_R, rq);
     st3(r + ILO_V, aV - cdv);
     for (int k = 0; k < 4; k++) {
-        const double drho = lb_i[k] - pre[PRE_RHO + k];
-        const d3 ce = ld3(pre + PRE_DEPS + 3 * k) + mv33(ldm33(pre + PRE_DEP_DBG + 9 * k), dbg) + drho * ld3(pre + PRE_DEP_DRHO + 3 * k);
+        const double drho = lb_i[k] - ldro(pre + PRE_RHO + k);
+        const d3 ce = ld3ro(pre + PRE_DEPS + 3 * k) + mv33(ldm33ro(pre + PRE_DEP_DBG + 9 * k), dbg) + drho * ld3ro(pre + PRE_DEP_DRHO + 3 * k);
         st3(r + ILO_EPS1 + 3 * k, aE - ce);
         r[ILO_RHO1 + k] = lb_j[k] - lb_i[k];
     }
     st3(r + ILO_BA, Baj - Bai);
     st3(r + ILO_BG, Bgj - Bgi);
-    if (pre[PRE_IMU_ONLY] != 0.0) {      // IMUFactor: 15 rows P, R, V, BA, BG only
+    if (ldro(pre + PRE_IMU_ONLY) != 0.0) {      // IMUFactor: 15 rows P, R, V, BA, BG only
         for (int k = ILO_EPS1; k < ILO_BA; k++) r[k] = 0.0;
         for (int k = ILO_RHO1; k < IL_RES; k++) r[k] = 0.0;
     }

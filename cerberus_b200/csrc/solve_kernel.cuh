@@ -104,6 +104,17 @@ CERB_D void block_sum(const double *v, double *red, double *out, int tid) {
     __syncthreads();
 }
 
+// global -> shared copy with the loads of 8 strides issued before the first store (a plain copy loop is compiled as
+// load, store, load, ... because the compiler cannot prove that the two pointers do not alias: one L2 round trip per element)
+CERB_D void copy_g2s(double *dst, const double *src, int n, int tid) {
+    for (int k0 = tid; k0 < n; k0 += 8 * SOLVE_THREADS) {
+        double b[8];
+        _Pragma("unroll")
+        for (int u = 0; u < 8; u++) { const int k = k0 + u * SOLVE_THREADS; b[u] = (k < n) ? src[k] : 0.0; }
+        _Pragma("unroll")
+        for (int u = 0; u < 8; u++) { const int k = k0 + u * SOLVE_THREADS; if (k < n) dst[k] = b[u]; }
+    }
+}
 CERB_D void load_geometry(const double *x, Smem &s, int tid) {
     if (tid < 11) { const m33 R = qtoR(ldq(x + ST_POSE + 7 * tid + 3)); for (int k = 0; k < 9; k++) s.Rw[9 * tid + k] = R.m[k]; }
     else if (tid < 13) { const int e = tid - 11; const m33 R = qtoR(ldq(x + ST_EX + 7 * e + 3)); for (int k = 0; k < 9; k++) s.Rex[9 * e + k] = R.m[k]; }
@@ -646,19 +657,29 @@ CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const doubl
                         for (int ni = mi; ni < 5; ni++) { CERB_DMMA(acc[q][0], acc[q][1], f[mi], f[ni], acc[q][0], acc[q][1]); q++; }
                 }
                 PH_MARK(34);
-                // scatter through the per-lane plan (built once per launch: every destination is affine in the factor index i)
+                // scatter through the per-lane plan (built once per launch: every destination is affine in the factor index i).  The
+                // destinations of a lane (and of different lanes) are distinct, so each half is done as load all / add / store all
+                // instead of 15 dependent read-modify-writes.
                 _Pragma("unroll")
-                for (int q = 0; q < 15; q++)
+                for (int hq = 0; hq < 30; hq += 15) {
+                    double cur[15];
                     _Pragma("unroll")
-                    for (int e = 0; e < 2; e++) {
-                        const int kind = plx[2 * q + e] & 3, o0 = (plx[2 * q + e] >> 2) + i * (ply[2 * q + e] & 4095);
-                        const double v = acc[q][e];
+                    for (int t = 0; t < 15; t++) {
+                        const int px = plx[hq + t];
+                        cur[t] = ((px & 3) >= 2) ? smem_base[(px >> 2) + i * (ply[hq + t] & 4095)] : 0.0;
+                    }
+                    _Pragma("unroll")
+                    for (int t = 0; t < 15; t++) {
+                        const int px = plx[hq + t], py = ply[hq + t], kind = px & 3, o0 = (px >> 2) + i * (py & 4095);
+                        const double v = acc[(hq + t) >> 1][(hq + t) & 1];
                         if (kind == 1) cost += 0.5 * v;
                         else if (kind >= 2) {
-                            smem_base[o0] += v;
-                            if (kind == 3) smem_base[o0 + (ply[2 * q + e] >> 12) - 256] += v;
+                            const double nv = cur[t] + v;
+                            smem_base[o0] = nv;
+                            if (kind == 3) smem_base[o0 + (py >> 12) - 256] = nv;          // mirrored entry of a symmetric diagonal block
                         }
                     }
+                }
                 PH_MARK(35);
             } else if (i + 1 < CERB_WINDOW && rnd < 3) load_S(i + 1);
             CERB_BAR_SYNC(2, 32 * IMU_WARPS);
@@ -842,13 +863,14 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
         while (true) {
             // =============================== linearise at xs ===========================================
             if (need_linearize) {
-                for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = has_prior ? pimg[k] : 0.0;
+                if (has_prior) copy_g2s(s.Hxx, pimg, HXX_SZ, tid); else for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = 0.0;
                 for (int k = tid; k < NRP; k += SOLVE_THREADS) s.g[k] = 0.0;
                 load_geometry(s.xs, s, tid);
                 double part[2];
                 PH_MARK(0);
                 part[0] = vision_linearize(P, w, s.xs, lam, W, hh, gl, sl, iteration > 0, chunks, tid);
-                for (int k = tid; k < HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) s.Hxy[k] = has_prior ? pimg[HXX_SZ + k] : 0.0;   // Hxy | Ad | Bo (contiguous; the tile aliased them)
+                if (has_prior) copy_g2s(s.Hxy, pimg + HXX_SZ, HXY_SZ + 1859 + 1690, tid);                    // Hxy | Ad | Bo (contiguous; the tile aliased them)
+                else for (int k = tid; k < HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) s.Hxy[k] = 0.0;
                 __syncthreads();
                 PH_MARK(1);
                 part[0] += inertial_linearize(P, w, s.xs, tid);
@@ -1036,15 +1058,27 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                             tmi[k] = mi; tni[k] = mi + idx;
                         }
                         CERB_BAR_SYNC(1, n2);
+                        // raw W / g_l values of a tile are fetched into registers one tile ahead (12 per thread: the loads are issued
+                        // together and stay in flight during the tensor-core loop), scaled and stored when the tile buffer is free
+                        double buf[12];
+                        auto fetch = [&](int f0) {
+                            const int nf = (nF - f0) < 32 ? (nF - f0) : 32;
+                            _Pragma("unroll")
+                            for (int u = 0; u < 12; u++) {
+                                const int e = t2 + u * n2, a = e >> 5, f = e & 31;
+                                buf[u] = (e < 80 * 32 && f < nf) ? (a < NX ? W[(size_t)a * F + f0 + f] : (a == NX ? gl[f0 + f] : 0.0)) : 0.0;
+                            }
+                        };
+                        fetch(0);
                         for (int f0 = 0; f0 < nF; f0 += 32) {
                             const int nf = (nF - f0) < 32 ? (nF - f0) : 32;
-                            for (int e = t2; e < 80 * 32; e += n2) {
-                                const int a = e >> 5, f = e & 31;
-                                double v = 0.0;
-                                if (f < nf) { if (a < NX) v = W[(size_t)a * F + f0 + f] * sinv[f0 + f]; else if (a == NX) v = gl[f0 + f] * sinv[f0 + f]; }
-                                tw[a * LDW + f] = v;
+                            _Pragma("unroll")
+                            for (int u = 0; u < 12; u++) {
+                                const int e = t2 + u * n2, a = e >> 5, f = e & 31;
+                                if (e < 80 * 32) tw[a * LDW + f] = (f < nf) ? buf[u] * sinv[f0 + f] : 0.0;
                             }
                             CERB_BAR_SYNC(1, n2);
+                            if (f0 + 32 < nF) fetch(f0 + 32);
                             for (int ks = 0; ks < 8; ks++) {
                                 const int col = 4 * ks + (lane & 3);
                                 for (int k = 0; k < 8; k++) {
@@ -1107,15 +1141,27 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                             while (idx >= 10 - mi) { idx -= 10 - mi; mi++; }
                             tmi[k] = mi; tni[k] = mi + idx;
                         }
+                        // row pointers of this lane's fragments (rows 0..78 of T, row 79 = gy'); operands are fetched one k-step ahead
+                        const double *pa[7], *pb[7];
+                        _Pragma("unroll")
+                        for (int k = 0; k < 7; k++) {
+                            const int ra = 8 * (tmi[k] < 0 ? 0 : tmi[k]) + (lane >> 2), rb = 8 * tni[k] + (lane >> 2);
+                            pa[k] = (ra < NX ? s.Hxy + ra * NY : s.yv + NX) + (lane & 3);
+                            pb[k] = (rb < NX ? s.Hxy + rb * NY : s.yv + NX) + (lane & 3);
+                        }
+                        double av[7], bv[7];
+                        _Pragma("unroll")
+                        for (int k = 0; k < 7; k++) { av[k] = pa[k][0]; bv[k] = pb[k][0]; }
                         for (int q0 = 0; q0 < NY; q0 += 4) {
-                            const int q = q0 + (lane & 3);
-                            for (int k = 0; k < 7; k++) {
-                                if (tmi[k] < 0) continue;
-                                const int ra = 8 * tmi[k] + (lane >> 2), rb = 8 * tni[k] + (lane >> 2);
-                                const double av = (q < NY) ? (ra < NX ? s.Hxy[ra * NY + q] : (ra == NX ? s.yv[NX + q] : 0.0)) : 0.0;
-                                const double bv = (q < NY) ? (rb < NX ? s.Hxy[rb * NY + q] : (rb == NX ? s.yv[NX + q] : 0.0)) : 0.0;
-                                CERB_DMMA(acc[k][0], acc[k][1], av, bv, acc[k][0], acc[k][1]);
-                            }
+                            const int qn = q0 + 4;
+                            const bool more = qn < NY, tail = qn + (lane & 3) >= NY;      // the last k-step holds 3 valid columns (K = 143)
+                            double an[7], bn[7];
+                            _Pragma("unroll")
+                            for (int k = 0; k < 7; k++) { an[k] = (more && !tail) ? pa[k][qn] : 0.0; bn[k] = (more && !tail) ? pb[k][qn] : 0.0; }
+                            _Pragma("unroll")
+                            for (int k = 0; k < 7; k++) CERB_DMMA(acc[k][0], acc[k][1], av[k], bv[k], acc[k][0], acc[k][1]);
+                            _Pragma("unroll")
+                            for (int k = 0; k < 7; k++) { av[k] = an[k]; bv[k] = bn[k]; }
                         }
                         for (int k = 0; k < 7; k++) {
                             if (tmi[k] < 0) continue;

@@ -10,6 +10,15 @@ struct d3 { double x, y, z; };
 struct m33 { double m[9]; };   // row-major
 struct quat { double x, y, z, w; };   // Eigen coeffs order (same as the para_Pose layout, estimator.cpp:852-859)
 
+// read-only global load (ld.global.nc): unlike a plain load it may be hoisted above stores through pointers the compiler
+// cannot disambiguate, so sequences of such loads are issued back to back instead of one L2 round trip at a time
+CERB_HD double ldro(const double *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 CERB_HD d3 mk3(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
 CERB_HD d3 ld3(const double *p) { return mk3(p[0], p[1], p[2]); }
 CERB_HD void st3(double *p, d3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
@@ -24,6 +33,8 @@ CERB_HD double get3(d3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
 CERB_HD m33 ident33() { m33 r; for (int i = 0; i < 9; i++) r.m[i] = 0.0; r.m[0] = r.m[4] = r.m[8] = 1.0; return r; }
 CERB_HD m33 ldm33(const double *p) { m33 r; for (int i = 0; i < 9; i++) r.m[i] = p[i]; return r; }
+CERB_HD d3 ld3ro(const double *p) { return mk3(ldro(p), ldro(p + 1), ldro(p + 2)); }
+CERB_HD m33 ldm33ro(const double *p) { m33 r; for (int i = 0; i < 9; i++) r.m[i] = ldro(p + i); return r; }
 CERB_HD m33 mul33(const m33 &a, const m33 &b) {
     m33 r;
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
