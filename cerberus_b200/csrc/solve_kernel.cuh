@@ -115,6 +115,10 @@ CERB_D void copy_g2s(double *dst, const double *src, int n, int tid) {
         for (int u = 0; u < 8; u++) { const int k = k0 + u * SOLVE_THREADS; if (k < n) dst[k] = b[u]; }
     }
 }
+// the same copy, asynchronous (no registers, no stall): completed by CERB_CP_ASYNC_WAIT() + a barrier
+CERB_D void copy_g2s_async(double *dst, const double *src, int n, int tid) {
+    for (int k = tid; k < n; k += SOLVE_THREADS) CERB_CP_ASYNC8(dst + k, src + k);
+}
 CERB_D void load_geometry(const double *x, Smem &s, int tid) {
     if (tid < 11) { const m33 R = qtoR(ldq(x + ST_POSE + 7 * tid + 3)); for (int k = 0; k < 9; k++) s.Rw[9 * tid + k] = R.m[k]; }
     else if (tid < 13) { const int e = tid - 11; const m33 R = qtoR(ldq(x + ST_EX + 7 * e + 3)); for (int k = 0; k < 9; k++) s.Rex[9 * e + k] = R.m[k]; }
@@ -578,16 +582,17 @@ CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const doubl
     Smem s; smem_carve(smem_base, s);
     double cost = 0.0;
     PH_DECL();
-    imu_lin_all(P, s, w, x, true, tid);
+    imu_lin_all(P, s, w, x, true, tid);                                  // (the asynchronous copy of the Hxy | Hyy image is in flight)
     PH_MARK(25);
     const int wid = tid >> 5, lane = tid & 31;
+    CERB_CP_ASYNC_WAIT();
     double *gp = s.gn;                                                  // prior gradient [NRP]; gn | stp | yv are idle during a linearisation
     double *ppart = s.stp;                                              // [4][PRIOR_LD] partial sums of J0 dx (stp | yv)
     for (int k = tid; k < NRP; k += SOLVE_THREADS) gp[k] = 0.0;
     __syncthreads();
     if (wid < IMU_WARPS) {
         double *Jt = s.Ju + IMU_TILE * wid;
-        // scatter plan of this lane (built once per launch), kept in registers: x = kind | offset(i = 0) << 2, y = stride | (mirror delta + 256) << 12
+        // scatter plan of this lane (built once per launch), kept in registers: x = offset(i = 0), y = stride | (mirror delta + 256) << 12
         int plx[30], ply[30];
         {
             const int *plan = reinterpret_cast<const int *>(P.ws + (size_t)blockIdx.x * P.ws_stride + ws_imuplan(P.maxF));
@@ -660,24 +665,20 @@ CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const doubl
                 // scatter through the per-lane plan (built once per launch: every destination is affine in the factor index i).  The
                 // destinations of a lane (and of different lanes) are distinct, so each half is done as load all / add / store all
                 // instead of 15 dependent read-modify-writes.
+                // Branch-free and decode-free: entries without a destination (padding, lower triangle, the cost corner) point at a
+                // per-lane dummy slot with stride 0; entries without a mirror have delta 0 (second store to the same address).
+                if (lane == 27) cost += 0.5 * acc[14][0];                   // (38, 38): 0.5 ||S r||^2 of this factor
                 _Pragma("unroll")
                 for (int hq = 0; hq < 30; hq += 15) {
                     double cur[15];
                     _Pragma("unroll")
-                    for (int t = 0; t < 15; t++) {
-                        const int px = plx[hq + t];
-                        cur[t] = ((px & 3) >= 2) ? smem_base[(px >> 2) + i * (ply[hq + t] & 4095)] : 0.0;
-                    }
+                    for (int t = 0; t < 15; t++) cur[t] = smem_base[plx[hq + t] + i * (ply[hq + t] & 4095)];
                     _Pragma("unroll")
                     for (int t = 0; t < 15; t++) {
-                        const int px = plx[hq + t], py = ply[hq + t], kind = px & 3, o0 = (px >> 2) + i * (py & 4095);
-                        const double v = acc[(hq + t) >> 1][(hq + t) & 1];
-                        if (kind == 1) cost += 0.5 * v;
-                        else if (kind >= 2) {
-                            const double nv = cur[t] + v;
-                            smem_base[o0] = nv;
-                            if (kind == 3) smem_base[o0 + (py >> 12) - 256] = nv;          // mirrored entry of a symmetric diagonal block
-                        }
+                        const int o = plx[hq + t] + i * (ply[hq + t] & 4095);
+                        const double nv = cur[t] + acc[(hq + t) >> 1][(hq + t) & 1];
+                        smem_base[o] = nv;
+                        smem_base[o + (ply[hq + t] >> 12) - 256] = nv;     // mirrored entry of a symmetric diagonal block (or the same address)
                     }
                 }
                 PH_MARK(35);
@@ -779,27 +780,25 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
     if (tid < 32) {
         // Scatter plan of the 40 x 40 IMU-leg Gram matrix (inertial_linearize): lane `tid` holds, for block q = (mi, ni) and
         // e = 0, 1, the entry (la, lb) = (8 mi + lane / 4, 8 ni + 2 (lane % 4) + e).  Its destination in Hxx / Hxy / Hyy / g is
-        // affine in the factor index i, so the plan stores two packed ints: kind | offset(i = 0) << 2 and stride | (mirror delta + 256) << 12
-        // (in doubles from the start of shared memory); kind 0: nothing, 1: cost corner, 2: one destination, 3: two (diagonal Hyy block).
+        // affine in the factor index i, so the plan stores two ints: offset(i = 0) and stride | (mirror delta + 256) << 12 (in doubles
+        // from the start of shared memory; the mirror is the transposed entry of a diagonal Hyy block).  Entries without a destination
+        // point at a per-lane dummy slot (sca[32 + lane], never read) with stride 0.
         int *plan = reinterpret_cast<int *>(ws + ws_imuplan(F));
         int q = 0;
         for (int mi = 0; mi < 5; mi++)
             for (int ni = mi; ni < 5; ni++, q++)
                 for (int e = 0; e < 2; e++) {
                     const int la = 8 * mi + (tid >> 2), lb = 8 * ni + 2 * (tid & 3) + e;
-                    int px = 0, py = 0;
-                    if (la <= lb && lb <= 38) {
-                        if (la == 38) px = 1;
-                        else {
-                            double *p0[2], *p1[2];
-                            for (int i = 0; i < 2; i++) {
-                                const int da = imu_col_dest(i, la);
-                                if (lb == 38) { p0[i] = da >= 0 ? s.g + da : s.g + NX + (-da - 1); p1[i] = nullptr; }
-                                else scatter_addr(s, da, imu_col_dest(i, lb), &p0[i], &p1[i]);
-                            }
-                            px = (p1[0] ? 3 : 2) | ((int)(p0[0] - smem_base) << 2);
-                            py = (int)(p0[1] - p0[0]) | (((p1[0] ? (int)(p1[0] - p0[0]) : 0) + 256) << 12);
+                    int px = (int)(sca + 32 - smem_base) + tid, py = 256 << 12;      // default: dummy slot of this lane, stride 0, delta 0
+                    if (la <= lb && lb <= 38 && la != 38) {
+                        double *p0[2], *p1[2];
+                        for (int i = 0; i < 2; i++) {
+                            const int da = imu_col_dest(i, la);
+                            if (lb == 38) { p0[i] = da >= 0 ? s.g + da : s.g + NX + (-da - 1); p1[i] = nullptr; }
+                            else scatter_addr(s, da, imu_col_dest(i, lb), &p0[i], &p1[i]);
                         }
+                        px = (int)(p0[0] - smem_base);
+                        py = (int)(p0[1] - p0[0]) | (((p1[0] ? (int)(p1[0] - p0[0]) : 0) + 256) << 12);
                     }
                     plan[(2 * (q * 2 + e)) * 32 + tid] = px; plan[(2 * (q * 2 + e) + 1) * 32 + tid] = py;
                 }
@@ -857,20 +856,24 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
             sca[S_INVALID] = 0; sca[S_DLNORM] = 0;
         }
         __syncthreads();
-        bool need_linearize = true;
+        bool need_linearize = true, hxx_prefetched = false;
         int iteration = 0;
 
         while (true) {
             // =============================== linearise at xs ===========================================
             if (need_linearize) {
-                if (has_prior) copy_g2s(s.Hxx, pimg, HXX_SZ, tid); else for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = 0.0;
+                // start from the prior Hessian image; its Hxx part was prefetched asynchronously when the previous factorisation of
+                // Hxx had been consumed (the copy overlapped with the rest of that iteration), except for the first linearisation
+                if (!has_prior) { for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = 0.0; }
+                else { if (!hxx_prefetched) copy_g2s_async(s.Hxx, pimg, HXX_SZ, tid); CERB_CP_ASYNC_WAIT(); }
+                hxx_prefetched = false;
                 for (int k = tid; k < NRP; k += SOLVE_THREADS) s.g[k] = 0.0;
                 load_geometry(s.xs, s, tid);
                 double part[2];
                 PH_MARK(0);
                 part[0] = vision_linearize(P, w, s.xs, lam, W, hh, gl, sl, iteration > 0, chunks, tid);
-                if (has_prior) copy_g2s(s.Hxy, pimg + HXX_SZ, HXY_SZ + 1859 + 1690, tid);                    // Hxy | Ad | Bo (contiguous; the tile aliased them)
-                else for (int k = tid; k < HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) s.Hxy[k] = 0.0;
+                if (has_prior) copy_g2s_async(s.Hxy, pimg + HXX_SZ, HXY_SZ + 1859 + 1690, tid);              // Hxy | Ad | Bo (contiguous; the tile aliased them);
+                else for (int k = tid; k < HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) s.Hxy[k] = 0.0;         // completed inside inertial_linearize
                 __syncthreads();
                 PH_MARK(1);
                 part[0] += inertial_linearize(P, w, s.xs, tid);
@@ -1278,6 +1281,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                         s.yv[tid] = y0; s.yv[32 + tid] = y1; if (64 + tid < NX) s.yv[64 + tid] = y2;
                     }
                     __syncthreads();
+                    if (has_prior) { copy_g2s_async(s.Hxx, pimg, HXX_SZ, tid); hxx_prefetched = true; }     // the factor of Hxx is dead from here on
                     PH_MARK(11);
                     // ---- y part: u = gy' - T^T y_x, then L^T y_y = u blockwise (warp 0) ------------------------------------
                     for (int q = tid; q < NY; q += SOLVE_THREADS) { double t = 0.0; for (int a = 0; a < NX; a++) t += s.Hxy[a * NY + q] * s.yv[a]; s.yv[NX + q] -= t; }
@@ -1440,6 +1444,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
             PH_MARK(18);
         }
         // ---- write back ---------------------------------------------------------------------------------
+        CERB_CP_ASYNC_WAIT();                                           // drain a prefetch of the prior image that was never consumed
         for (int k = tid; k < ST_SIZE; k += SOLVE_THREADS) P.state[(size_t)w * ST_STRIDE + k] = s.xs[k];
         if (tid == 0) {
             P.rep_i[4 * w + 0] = iteration; P.rep_i[4 * w + 1] = (int)sca[S_NSUCC]; P.rep_i[4 * w + 2] = (int)sca[S_TERM];

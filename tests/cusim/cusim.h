@@ -41,6 +41,8 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
 #define CERB_LAUNCH(kernel, grid, block, smem, stream, ...) cusim::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
 inline void __syncthreads() { pthread_barrier_wait(&cusim::block_barrier); }
 inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cusim::warp_barriers[threadIdx.x / 32]); }
+#define CERB_CP_ASYNC8(dst_smem, src_global) (*(dst_smem) = *(src_global))
+#define CERB_CP_ASYNC_WAIT() ((void)0)
 // named barriers (bar.sync id, nthreads) among subsets of the warps of a block
 namespace cusim { void named_sync(int id, int nthreads); }
 #define CERB_BAR_SYNC(id, nthreads) cusim::named_sync((id), (nthreads))
