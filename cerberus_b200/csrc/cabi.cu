@@ -6,6 +6,7 @@
 #include "../../include/cerberus_b200.h"
 #include "solve_kernel.cuh"
 #include "preint_kernel.cuh"
+#include "feature_kernels.cuh"
 #include <string>
 #include <vector>
 #include <thread>
@@ -43,6 +44,7 @@ struct CerbHandle {
     // pinned staging
     int *h_nfeat = nullptr, *h_fstart = nullptr, *h_fnobs = nullptr, *h_foff = nullptr, *h_flags = nullptr, *h_stereo = nullptr, *h_pmeta = nullptr, *h_repi = nullptr;
     double *h_obs = nullptr, *h_pre = nullptr, *h_pJ = nullptr, *h_pr = nullptr, *h_px0 = nullptr, *h_state = nullptr, *h_lam = nullptr, *h_repd = nullptr, *h_dbg = nullptr;
+    bool solved = false;              // the device states are the solved ones (else: the uploaded initial states)
     std::vector<int> h_perm;          // [B][F] device feature slot -> index in the caller's feature array (tracks are sorted by anchor frame on the device)
     long ws_stride = 0;
     size_t smem_bytes = 0;
@@ -276,7 +278,7 @@ static int upload_range(CerbHandle *h, int w0, int n, cudaStream_t s) {
 #undef H2D
     return CERB_OK;
 }
-static int upload(CerbHandle *h, int n) { int rc = upload_range(h, 0, n, h->stream); h->n = n; return rc; }
+static int upload(CerbHandle *h, int n) { int rc = upload_range(h, 0, n, h->stream); h->n = n; h->solved = false; return rc; }
 
 static SolveParams make_params(CerbHandle *h, int w0, int n, int max_iters, double *dbg, int dbg_window) {
     SolveParams P;
@@ -307,6 +309,7 @@ static int enqueue_solve(CerbHandle *h, int w0, int n, int max_iters, double *db
     CERB_LAUNCH(imu_leg_prepare_kernel, (nfac + 1) / 2, 64, 0, s, nfac, (const double *)(h->d_pre + W0 * 10 * PRE_STRIDE), h->d_sinfo + W0 * 10 * 961);
     CERB_LAUNCH(prior_prepare_kernel, n, 256, 0, s, (const double *)(h->d_pJ + W0 * PRIOR_LD * PRIOR_LD), (const int *)(h->d_pmeta + W0 * PRIOR_META_STRIDE), h->d_pHp + W0 * PRIOR_LD * PRIOR_LD);
     SolveParams P = make_params(h, w0, n, max_iters, dbg, dbg_window);
+    if (max_iters > 0) h->solved = true;
     CERB_LAUNCH(vilo_solve_kernel, std::min(n, h->grid), SOLVE_THREADS, h->smem_bytes, s, P);
     CUDA_TRY(cudaGetLastError());
     return CERB_OK;
@@ -580,6 +583,39 @@ int cerb_a1_kinematics(CerbHandle *h, int32_t n, const double *q, const double *
     CUDA_TRY(cudaStreamSynchronize(s));
     return CERB_OK;
 }
+
+// ---- per-feature steps on the resident batch ------------------------------------------------------------------------
+static int feature_pass(CerbHandle *h, int which, double param, double *out, int32_t *remove) {
+    if (!h || !out) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    if (h->n < 1) return fail(CERB_ERR_BAD_ARGUMENT, "no resident batch");
+    const int n = h->n, F = h->F;
+    cudaStream_t s = h->stream; DevBuf B;
+    double *d_out = B.up(nullptr, (size_t)n * F, s);
+    if (!d_out) return fail(CERB_ERR_CUDA, "device allocation failed");
+    const int threads = 128, blocks = (n * F + threads - 1) / threads;
+    const double *d_st = h->solved ? h->d_state : h->d_state0, *d_lm = h->solved ? h->d_lam : h->d_lam0;
+    if (which == 0)
+        CERB_LAUNCH(outlier_error_kernel, blocks, threads, 0, s, n, F, h->O, (const int *)h->d_nfeat, (const int *)h->d_fstart, (const int *)h->d_fnobs, (const int *)h->d_foff,
+                    (const double *)h->d_obs, (const int *)h->d_stereo, d_st, d_lm, d_out);
+    else
+        CERB_LAUNCH(triangulate_kernel, blocks, threads, 0, s, n, F, h->O, (const int *)h->d_nfeat, (const int *)h->d_fstart, (const int *)h->d_fnobs, (const int *)h->d_foff,
+                    (const double *)h->d_obs, (const int *)h->d_stereo, d_st, d_lm, param, d_out);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> tmp((size_t)n * F);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int w = 0; w < n; w++) {       // device slot -> caller's feature index
+        const int *perm = h->h_perm.data() + (size_t)w * F;
+        for (int k = 0; k < h->h_nfeat[w]; k++) {
+            const double v = tmp[(size_t)w * F + k];
+            out[(size_t)w * F + perm[k]] = v;
+            if (remove) remove[(size_t)w * F + perm[k]] = (v * param > 3.0) ? 1 : 0;
+        }
+    }
+    return CERB_OK;
+}
+int cerb_batch_outlier_errors(CerbHandle *h, double focal_length, double *ave_err, int32_t *remove) { return feature_pass(h, 0, focal_length, ave_err, remove); }
+int cerb_batch_triangulate(CerbHandle *h, double init_depth, double *depth) { return feature_pass(h, 1, init_depth, depth, nullptr); }
 
 // ---- leg-contact preintegration ------------------------------------------------------------------------------------
 static int preintegrate_impl(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n, const CerbPreintJob *jobs, CerbIMULegPreint *out, CerbIMUPreint *out_imu) {

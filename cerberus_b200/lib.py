@@ -57,6 +57,8 @@ class Backend:
         L.cerb_preintegrate_batch.argtypes = [C.c_void_p, C.POINTER(abi.PreintConfig), C.c_int32, C.POINTER(abi.PreintJob), C.POINTER(abi.IMULegPreint)]
         L.cerb_a1_kinematics.argtypes = [C.c_void_p, C.c_int32] + [abi.c_dp] * 8
         L.cerb_double2vector.argtypes = [C.POINTER(abi.WindowState), C.POINTER(abi.WindowState), abi.c_dp, abi.c_dp, abi.c_dp]
+        L.cerb_batch_outlier_errors.argtypes = [C.c_void_p, C.c_double, abi.c_dp, C.POINTER(C.c_int32)]
+        L.cerb_batch_triangulate.argtypes = [C.c_void_p, C.c_double, abi.c_dp]
         L.cerb_double2vector.restype = None
         self.cfg = cfg or abi.default_config()
         self.h = C.c_void_p()
@@ -163,6 +165,20 @@ class Backend:
         Ps, Rs, Vs = np.zeros((11, 3)), np.zeros((11, 3, 3)), np.zeros((11, 3))
         self.lib.cerb_double2vector(C.byref(before_state), C.byref(after_state), _p(Ps), _p(Rs), _p(Vs))
         return Ps, Rs, Vs
+
+    # ---- per-feature steps on the resident batch (after upload / solve) -----------------------------------------------
+    def outlier_errors(self, n, focal_length=460.0):
+        """Estimator::outliersRejection on the resident batch: (ave_err [n][max_features], remove flags)."""
+        F = self.cfg.max_features
+        err = np.full((n, F), np.nan); rem = np.zeros((n, F), dtype=np.int32)
+        self._check(self.lib.cerb_batch_outlier_errors(self.h, focal_length, _p(err), rem.ctypes.data_as(C.POINTER(C.c_int32))))
+        return err, rem
+
+    def triangulate(self, n, init_depth=5.0):
+        """FeatureManager::triangulate on the resident batch: estimated_depth [n][max_features]."""
+        depth = np.full((n, self.cfg.max_features), np.nan)
+        self._check(self.lib.cerb_batch_triangulate(self.h, init_depth, _p(depth)))
+        return depth
 
     # ---- synth backend protocol -----------------------------------------------------------------------------
     def preintegrate(self, pcfg, jobs, n):

@@ -337,6 +337,21 @@ int cerb_a1_kinematics(CerbHandle *h, int32_t n, const double *q, const double *
                        const double *rho_fix, double *fk, double *jac, double *dfk_drho,
                        double *dJ_dq, double *dJ_drho);
 
+/* ---- per-feature steps either side of the solve, on the RESIDENT batch at its current device state
+ * (after cerb_solve_batch / cerb_batch_solve_resident the device holds the solved para_* arrays).
+ * Outputs are [n][max_features] in the caller's feature order; entries >= n_features of a window are left untouched. */
+
+/* Estimator::outliersRejection + reprojectionError (estimator.cpp:1729-1798): mean reprojection error of every feature
+ * over its observations (camera 0 of the other frames, camera 1 of every stereo observation), depth = 1 / para_Feature.
+ * remove (may be NULL) receives the reference's decision ave_err * focal_length > 3 (FOCAL_LENGTH = 460). */
+int cerb_batch_outlier_errors(CerbHandle *h, double focal_length, double *ave_err, int32_t *remove);
+
+/* FeatureManager::triangulate + triangulatePoint (feature_manager.cpp:198-212,302-385): estimated_depth of every feature
+ * whose para_Feature <= 0 (not triangulated yet): two-view SVD triangulation from the left/right cameras of the anchor
+ * frame if that observation is stereo, else from camera 0 of the anchor frame and the next frame; a non-positive result
+ * becomes init_depth (INIT_DEPTH = 5.0, parameters.cpp:250).  Features that already have a depth return 1 / para_Feature. */
+int cerb_batch_triangulate(CerbHandle *h, double init_depth, double *depth);
+
 /* ---- host-side helpers that stay on the CPU in the reference too ---------------------------- */
 /* Gauge re-anchoring of Estimator::double2vector (estimator.cpp:903-957): rotates the solved
  * window by the yaw difference of frame 0 and re-anchors its position.  before/after are the

@@ -553,6 +553,96 @@ void oracle_double2vector(const CerbWindowState *before, const CerbWindowState *
     }
 }
 
+// ---- per-feature steps either side of the solve ------------------------------------------------------
+// Estimator::reprojectionError, estimator.cpp:1729-1739
+static double reprojection_error(const M3 &Ri, V3 Pi, const M3 &rici, V3 tici, const M3 &Rj, V3 Pj, const M3 &ricj, V3 ticj, double depth, V3 uvi, V3 uvj) {
+    V3 pts_w = Ri * (rici * (depth * uvi) + tici) + Pi;
+    V3 pts_cj = transpose(ricj) * (transpose(Rj) * (pts_w - Pj) - ticj);
+    double rx = pts_cj.x / pts_cj.z - uvj.x, ry = pts_cj.y / pts_cj.z - uvj.y;
+    return std::sqrt(rx * rx + ry * ry);
+}
+// Estimator::outliersRejection, estimator.cpp:1741-1798: ave_err[f] for every feature of the window (Rs, Ps, ric, tic from the
+// para_* arrays; depth = estimated_depth = 1 / para_Feature, feature_manager.cpp:189)
+int oracle_outlier_errors(const CerbWindowDesc *d, const CerbWindowState *st, double *ave_err) {
+    auto quat_of = [](const double *p) { return Quat(p[6], p[3], p[4], p[5]); };
+    M3 ric[2] = {toR(quat_of(st->para_Ex_Pose[0])), toR(quat_of(st->para_Ex_Pose[1]))};
+    V3 tic[2] = {V3(st->para_Ex_Pose[0]), V3(st->para_Ex_Pose[1])};
+    for (int f = 0; f < d->n_features; f++) {
+        const CerbFeature &ft = d->features[f];
+        double err = 0; int errCnt = 0;
+        int imu_i = ft.start_frame, imu_j = imu_i - 1;
+        const CerbObservation &o0 = d->obs[ft.obs_offset];
+        V3 pts_i(o0.point[0], o0.point[1], 1.0);
+        double depth = 1.0 / st->para_Feature[f];
+        M3 Ri = toR(quat_of(st->para_Pose[imu_i])); V3 Pi(st->para_Pose[imu_i]);
+        for (int k = 0; k < ft.n_obs; k++) {
+            const CerbObservation &o = d->obs[ft.obs_offset + k];
+            imu_j++;
+            M3 Rj = toR(quat_of(st->para_Pose[imu_j])); V3 Pj(st->para_Pose[imu_j]);
+            if (imu_i != imu_j) { err += reprojection_error(Ri, Pi, ric[0], tic[0], Rj, Pj, ric[0], tic[0], depth, pts_i, V3(o.point[0], o.point[1], 1.0)); errCnt++; }
+            if (o.is_stereo) { err += reprojection_error(Ri, Pi, ric[0], tic[0], Rj, Pj, ric[1], tic[1], depth, pts_i, V3(o.pointRight[0], o.pointRight[1], 1.0)); errCnt++; }
+        }
+        ave_err[f] = err / errCnt;
+    }
+    return 0;
+}
+// Smallest right singular vector of a 4 x 4 matrix (what design_matrix.jacobiSvd(ComputeFullV).matrixV().rightCols<1>() returns up
+// to sign): eigenvector of the smallest eigenvalue of A^T A by cyclic two-sided Jacobi rotations.
+static void null_vector4(const double A[4][4], double v[4]) {
+    double B[4][4], V[4][4];
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { B[i][j] = 0; for (int k = 0; k < 4; k++) B[i][j] += A[k][i] * A[k][j]; V[i][j] = i == j; }
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0; for (int p = 0; p < 4; p++) for (int q = p + 1; q < 4; q++) off += B[p][q] * B[p][q];
+        if (off < 1e-60) break;
+        for (int p = 0; p < 3; p++) for (int q = p + 1; q < 4; q++) {
+            if (B[p][q] == 0.0) continue;
+            double th = (B[q][q] - B[p][p]) / (2 * B[p][q]);
+            double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1)), c = 1 / std::sqrt(t * t + 1), sn = t * c;
+            for (int k = 0; k < 4; k++) { double bp = B[k][p], bq = B[k][q]; B[k][p] = c * bp - sn * bq; B[k][q] = sn * bp + c * bq; }
+            for (int k = 0; k < 4; k++) { double bp = B[p][k], bq = B[q][k]; B[p][k] = c * bp - sn * bq; B[q][k] = sn * bp + c * bq; }
+            for (int k = 0; k < 4; k++) { double vp = V[k][p], vq = V[k][q]; V[k][p] = c * vp - sn * vq; V[k][q] = sn * vp + c * vq; }
+        }
+    }
+    int best = 0; for (int c = 1; c < 4; c++) if (B[c][c] < B[best][best]) best = c;
+    for (int k = 0; k < 4; k++) v[k] = V[k][best];
+}
+// FeatureManager::triangulatePoint, feature_manager.cpp:198-212 (Pose = [R^T | -R^T t], 3 x 4)
+static V3 triangulate_point(const double P0[3][4], const double P1[3][4], double u0x, double u0y, double u1x, double u1y) {
+    double A[4][4], v[4];
+    for (int c = 0; c < 4; c++) { A[0][c] = u0x * P0[2][c] - P0[0][c]; A[1][c] = u0y * P0[2][c] - P0[1][c]; A[2][c] = u1x * P1[2][c] - P1[0][c]; A[3][c] = u1y * P1[2][c] - P1[1][c]; }
+    null_vector4(A, v);
+    return V3(v[0] / v[3], v[1] / v[3], v[2] / v[3]);
+}
+// FeatureManager::triangulate, feature_manager.cpp:302-385: depth[f] for the features with estimated_depth <= 0
+// (para_Feature <= 0); the others return their current 1 / para_Feature.  (:387-428 is unreachable: size() > 1 takes :351.)
+int oracle_triangulate(const CerbWindowDesc *d, const CerbWindowState *st, double init_depth, double *depth) {
+    auto quat_of = [](const double *p) { return Quat(p[6], p[3], p[4], p[5]); };
+    M3 ric[2] = {toR(quat_of(st->para_Ex_Pose[0])), toR(quat_of(st->para_Ex_Pose[1]))};
+    V3 tic[2] = {V3(st->para_Ex_Pose[0]), V3(st->para_Ex_Pose[1])};
+    auto pose34 = [](const M3 &R, V3 t, double P[3][4]) { M3 Rt = transpose(R); V3 m = -(Rt * t); for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) P[r][c] = Rt(r, c); P[r][3] = m[r]; } };
+    for (int f = 0; f < d->n_features; f++) {
+        const double l = st->para_Feature[f];
+        if (l > 0) { depth[f] = 1.0 / l; continue; }
+        const CerbFeature &ft = d->features[f];
+        const CerbObservation &o0 = d->obs[ft.obs_offset];
+        int imu_i = ft.start_frame;
+        M3 Ri = toR(quat_of(st->para_Pose[imu_i])); V3 Pi(st->para_Pose[imu_i]);
+        double left[3][4], right[3][4];
+        pose34(Ri * ric[0], Pi + Ri * tic[0], left);
+        V3 p;
+        if (o0.is_stereo) { pose34(Ri * ric[1], Pi + Ri * tic[1], right); p = triangulate_point(left, right, o0.point[0], o0.point[1], o0.pointRight[0], o0.pointRight[1]); }
+        else if (ft.n_obs > 1) {
+            const CerbObservation &o1 = d->obs[ft.obs_offset + 1];
+            M3 Rj = toR(quat_of(st->para_Pose[imu_i + 1])); V3 Pj(st->para_Pose[imu_i + 1]);
+            pose34(Rj * ric[0], Pj + Rj * tic[0], right);
+            p = triangulate_point(left, right, o0.point[0], o0.point[1], o1.point[0], o1.point[1]);
+        } else { depth[f] = l; continue; }
+        double dz = left[2][0] * p.x + left[2][1] * p.y + left[2][2] * p.z + left[2][3];
+        depth[f] = dz > 0 ? dz : init_depth;
+    }
+    return 0;
+}
+
 int oracle_abi_sizes(int *out, int n) {   // struct-size handshake for the ctypes mirror
     int v[] = {(int)sizeof(CerbSolverConfig), (int)sizeof(CerbIMULegPreint), (int)sizeof(CerbObservation), (int)sizeof(CerbFeature), (int)sizeof(CerbPrior),
                (int)sizeof(CerbWindowDesc), (int)sizeof(CerbWindowState), (int)sizeof(CerbSolveReport), (int)sizeof(CerbIMULegSample), (int)sizeof(CerbPreintConfig), (int)sizeof(CerbPreintJob), (int)sizeof(CerbIMUPreint)};

@@ -126,6 +126,19 @@ class OracleBackend:
         self.lib.oracle_double2vector(C.byref(before_state), C.byref(after_state), _p(Ps), _p(Rs), _p(Vs))
         return Ps, Rs, Vs
 
+    def outlier_errors(self, batch):
+        out = np.full((batch.n, batch.max_features), np.nan)
+        for w in range(batch.n):
+            assert self.lib.oracle_outlier_errors(C.byref(batch.descs[w]), C.byref(batch.states[w]), _p(out[w])) == 0
+        return out
+
+    def triangulate(self, batch, init_depth=5.0):
+        out = np.full((batch.n, batch.max_features), np.nan)
+        self.lib.oracle_triangulate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, abi.c_dp]
+        for w in range(batch.n):
+            assert self.lib.oracle_triangulate(C.byref(batch.descs[w]), C.byref(batch.states[w]), init_depth, _p(out[w])) == 0
+        return out
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # oracle/_ref: the reference's OWN factor sources compiled against the header shims (oracle/shim), `make -C oracle ref`

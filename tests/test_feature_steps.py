@@ -1,0 +1,70 @@
+"""Per-feature steps either side of the solve: Estimator::outliersRejection and FeatureManager::triangulate
+on the resident batch.  CPU tier: the kernels on the CPU simulator vs the oracle restatement (estimator.cpp:1729-1798,
+feature_manager.cpp:198-212,302-385), the oracle's 4x4 null vector vs numpy's LAPACK SVD, and the geometry itself (a noise-free
+track triangulates to its true depth).  GPU tier: the sm_100a kernels vs the oracle."""
+import numpy as np
+import pytest
+from cerberus_b200 import abi, synth
+from oracle_lib import OracleBackend
+from helpers import sim_backend, small_cfg
+
+
+def _batch(backend, realistic, n=3, F=24):
+    batch = synth.generate_batch(n, F, backend, realistic=realistic, window0=77, prior_features=8)
+    return batch
+
+
+def _check_backend(be, oracle, realistic):
+    batch = _batch(be, realistic)
+    nf = [batch.descs[w].n_features for w in range(batch.n)]
+    # (1) outlier errors at the initial states and after the solve
+    be.upload(batch)
+    for phase in range(2):
+        err, rem = be.outlier_errors(batch.n)
+        ref = oracle.outlier_errors(batch)
+        for w in range(batch.n):
+            assert np.abs(err[w, :nf[w]] - ref[w, :nf[w]]).max() < 1e-12 * max(1.0, np.abs(ref[w, :nf[w]]).max())
+            assert (rem[w, :nf[w]] == (ref[w, :nf[w]] * 460.0 > 3)).all()
+        if phase == 0:
+            be.solve_resident(); be.download(batch)           # batch.states now hold the solved states, like the device
+    assert np.nanmax(err) * 460.0 < 3.0                           # solved synthetic windows have no outliers
+    # (2) triangulation: mark every second feature as not triangulated (estimated_depth = -1 -> para_Feature = -1)
+    true_depth = 1.0 / batch.para_Feature.copy()
+    for w in range(batch.n):
+        batch.para_Feature[w, 0:nf[w]:2] = -1.0
+    be.upload(batch)
+    dep = be.triangulate(batch.n)
+    ref = oracle.triangulate(batch)
+    for w in range(batch.n):
+        assert np.abs(dep[w, :nf[w]] - ref[w, :nf[w]]).max() < 1e-8 * np.abs(ref[w, :nf[w]]).max()
+        assert (dep[w, 1:nf[w]:2] == 1.0 / batch.para_Feature[w, 1:nf[w]:2]).all()          # untouched features: current depth
+        # sanity of the geometry: positive depths of the right magnitude (a 0.5-px-noise stereo pair with a ~0.1 m baseline only
+        # constrains depths of 2..15 m to a few tens of percent)
+        assert (dep[w, 0:nf[w]:2] > 0).all() and np.median(np.abs(dep[w, 0:nf[w]:2] / true_depth[w, 0:nf[w]:2] - 1.0)) < 0.6
+
+
+@pytest.mark.parametrize("realistic", [False, True])
+def test_feature_steps_sim(realistic):
+    cfg = small_cfg(max_batch=4, max_features=24, iters=4)
+    _check_backend(sim_backend(cfg), OracleBackend(cfg), realistic)
+
+
+def test_oracle_null_vector_vs_lapack():
+    """The oracle's triangulation on exact two-view geometry: numpy (LAPACK) SVD of the same design matrix gives the same point."""
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        X = np.array([rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(3, 12)])
+        t1 = np.array([0.2, rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05)])
+        P0 = np.hstack([np.eye(3), np.zeros((3, 1))]); P1 = np.hstack([np.eye(3), -t1[:, None]])
+        u0 = X[:2] / X[2]; x1 = X - t1; u1 = x1[:2] / x1[2]
+        A = np.stack([u0[0] * P0[2] - P0[0], u0[1] * P0[2] - P0[1], u1[0] * P1[2] - P1[0], u1[1] * P1[2] - P1[1]])
+        v = np.linalg.svd(A)[2][-1]
+        assert np.abs(v[:3] / v[3] - X).max() < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("realistic", [False, True])
+def test_feature_steps_gpu(realistic):
+    from cerberus_b200 import lib
+    cfg = small_cfg(max_batch=4, max_features=24, iters=4)
+    _check_backend(lib.Backend(cfg), OracleBackend(cfg), realistic)
