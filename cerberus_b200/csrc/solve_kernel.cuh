@@ -882,9 +882,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                 double tot[2];
                 block_sum<2>(part, s.red, tot, tid);
                 if (tid == 0) { sca[S_XCOST] = tot[0]; sca[S_XNORM] = sqrt(tot[1]); if (iteration == 0) sca[S_INIT_COST] = tot[0]; }
-                // symmetrise Hxx (upper -> lower)
-                for (int k = tid; k < NX * NX; k += SOLVE_THREADS) { const int a = k / NX, b = k % NX; if (a > b) s.Hxx[k] = s.Hxx[b * NX + a]; }
-                __syncthreads();
+                // (Hxx holds its upper triangle; it is mirrored and scaled in one row-wise pass below)
                 // gradient max norm over active dims (unscaled), Jacobi scale at iteration 0
                 if (iteration == 0) {
                     for (int k = tid; k < NR; k += SOLVE_THREADS) {
@@ -911,14 +909,17 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                 double gm = 0.0;
                 for (int k = tid; k < NR; k += SOLVE_THREADS) if (s.sc[k] != 0.0) gm = fmax(gm, fabs(s.g[k]));
                 for (int f = tid; f < nF; f += SOLVE_THREADS) gm = fmax(gm, fabs(iteration > 0 ? gl[f] / sl[f] : gl[f]));   // unscaled gradient
-                s.red[tid] = gm;
+                for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_sync(0xffffffffu, gm, (tid + o) & 31));
+                if ((tid & 31) == 0) s.red[tid >> 5] = gm;
                 __syncthreads();
-                for (int st = 128; st > 0; st >>= 1) { if (tid < st) s.red[tid] = fmax(s.red[tid], s.red[tid + st]); __syncthreads(); }
-                if (tid == 0) sca[S_GMAX] = s.red[0];
-                __syncthreads();
-                // apply the Jacobi scaling: H~ = S H S, g~ = S g, w~_f = s_f S_x w_f, h~ = s_f^2 h, gl~ = s_f gl
-                for (int k = tid; k < NX * NX; k += SOLVE_THREADS) s.Hxx[k] *= s.sc[k / NX] * s.sc[k % NX];
-                for (int k = tid; k < NX * NY; k += SOLVE_THREADS) s.Hxy[k] *= s.sc[k / NY] * s.sc[NX + k % NY];
+                if (tid == 0) { double m8 = s.red[0]; for (int k = 1; k < SOLVE_THREADS / 32; k++) m8 = fmax(m8, s.red[k]); sca[S_GMAX] = m8; }
+                // apply the Jacobi scaling: H~ = S H S, g~ = S g, w~_f = s_f S_x w_f, h~ = s_f^2 h, gl~ = s_f gl.  Row-wise (a warp per
+                // row: no index divisions); the Hxx pass also mirrors the upper triangle into the lower one.
+                for (int a = tid >> 5; a < NX; a += SOLVE_THREADS / 32) {
+                    const double sa = s.sc[a];
+                    for (int b = a + (tid & 31); b < NX; b += 32) { const double v = s.Hxx[a * NX + b] * (sa * s.sc[b]); s.Hxx[a * NX + b] = v; s.Hxx[b * NX + a] = v; }
+                    for (int q = tid & 31; q < NY; q += 32) s.Hxy[a * NY + q] *= sa * s.sc[NX + q];
+                }
                 for (int k = tid; k < 1859; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; s.Ad[k] *= s.sc[NX + NYB * f + a] * s.sc[NX + NYB * f + b]; }
                 for (int k = tid; k < 1690; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; s.Bo[k] *= s.sc[NX + NYB * f + a] * s.sc[NX + NYB * (f + 1) + b]; }
                 for (int k = tid; k < NR; k += SOLVE_THREADS) s.g[k] *= s.sc[k];
@@ -1125,7 +1126,12 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                                 const double *M = s.Bo + (f - 1) * 169;
                                 for (int r = 0; r < NYB; r++) { double acc = 0.0; for (int q = 0; q < NYB; q++) acc += M[r * NYB + q] * tp[q]; tc[r] -= acc; }
                             }
-                            for (int r = 0; r < NYB; r++) { double acc = tc[r]; for (int q = 0; q < r; q++) acc -= L[r * NYB + q] * tc[q]; tc[r] = acc * idg[r]; }
+                            _Pragma("unroll")
+                            for (int c = 0; c < NYB; c++) {                 // right-looking: the dependency chain is 13 (multiply, update) steps
+                                tc[c] *= idg[c];
+                                _Pragma("unroll")
+                                for (int r = c + 1; r < NYB; r++) tc[r] -= L[r * NYB + c] * tc[c];
+                            }
                             for (int r = 0; r < NYB; r++) { t[r] = tc[r]; tp[r] = tc[r]; }
                         }
                     }
@@ -1286,21 +1292,32 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                     // ---- y part: u = gy' - T^T y_x, then L^T y_y = u blockwise (warp 0) ------------------------------------
                     for (int q = tid; q < NY; q += SOLVE_THREADS) { double t = 0.0; for (int a = 0; a < NX; a++) t += s.Hxy[a * NY + q] * s.yv[a]; s.yv[NX + q] -= t; }
                     __syncthreads();
-                    if (tid < 32) {
+                    if (tid < 32) {      // lane r holds component r of the current block; one shuffle per substitution step
+                        const int r = tid < NYB ? tid : 0;
+                        double yn[NYB];                                  // solved block f + 1 (all lanes)
+                        _Pragma("unroll")
+                        for (int k = 0; k < NYB; k++) yn[k] = 0.0;
+                        _Pragma("unroll 1")
                         for (int f = NFR - 1; f >= 0; f--) {
-                            double *u = s.yv + NX + NYB * f;
                             const double *L = s.Ad + f * 169;
+                            double u = s.yv[NX + NYB * f + r];
                             if (f < NFR - 1) {
-                                const double *M = s.Bo + f * 169; const double *yn = s.yv + NX + NYB * (f + 1);
-                                if (tid < NYB) { double t = 0.0; for (int r = 0; r < NYB; r++) t += M[r * NYB + tid] * yn[r]; u[tid] -= t; }
-                                __syncwarp();
+                                const double *M = s.Bo + f * 169;
+                                double t = 0.0;
+                                _Pragma("unroll")
+                                for (int k = 0; k < NYB; k++) t += M[k * NYB + r] * yn[k];
+                                u -= t;
                             }
+                            double lc[NYB], ig[NYB];                          // column r of L^T and the inverse pivots: loaded before the chain
+                            _Pragma("unroll")
+                            for (int k = 0; k < NYB; k++) { lc[k] = (tid < k) ? L[k * NYB + r] : 0.0; ig[k] = s.idg[NYB * f + k]; }
+                            _Pragma("unroll")
                             for (int k = NYB - 1; k >= 0; k--) {
-                                if (tid == 0) u[k] *= s.idg[NYB * f + k];
-                                __syncwarp();
-                                if (tid < k) u[tid] -= L[k * NYB + tid] * u[k];
-                                __syncwarp();
+                                const double yk = __shfl_sync(0xffffffffu, u, k) * ig[k];
+                                yn[k] = yk;
+                                u = (tid == k) ? yk : u - lc[k] * yk;
                             }
+                            if (tid < NYB) s.yv[NX + NYB * f + tid] = u;
                         }
                     }
                     __syncthreads();
