@@ -415,8 +415,14 @@ int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, Cerb
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     for (int c = 0; c < nch; c++) {
         const int w0 = bounds[c], cn = bounds[c + 1] - bounds[c];
-        rc = pack_range(h, w0, cn, descs, states); if (rc) return rc;
-        rc = upload_range(h, w0, cn, h->copy_stream); if (rc) return rc;
+        // the first chunk is on the critical path (nothing to overlap with yet): pack and copy it in quarters so that the copy of
+        // one quarter runs while the next one is packed
+        const int nsub = (c == 0 && cn >= 32) ? 4 : 1;
+        for (int q = 0; q < nsub; q++) {
+            const int s0 = w0 + (int)((long)cn * q / nsub), s1 = w0 + (int)((long)cn * (q + 1) / nsub);
+            rc = pack_range(h, s0, s1 - s0, descs, states); if (rc) return rc;
+            rc = upload_range(h, s0, s1 - s0, h->copy_stream); if (rc) return rc;
+        }
         CUDA_TRY(cudaEventRecord(h->ev_copy[c], h->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy[c], 0));
         rc = enqueue_solve(h, w0, cn, h->cfg.max_num_iterations, nullptr, -1); if (rc) return rc;

@@ -972,6 +972,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                         s.yv[k] = s.g[k];
                         if (k >= NX) s.Ad[((k - NX) / NYB) * 169 + ((k - NX) % NYB) * (NYB + 1)] += mu * s.D[k] * s.D[k];
                     }
+                    volatile int *chain_done = s.ti + 130;              // number of Hyy blocks whose factor (L_f, M_f) warp 0 has published
+                    if (tid == 0) *chain_done = 0;
                     __syncthreads();
                     if (tid < 32) {
                         // ---- warp 0: block-bidiagonal Cholesky of Hyy: Ad[f] <- L_f (lower), Bo[f] <- M_f = B_f^T L_f^-T ----
@@ -1023,6 +1025,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                                 if (act) { _Pragma("unroll") for (int c = 0; c < NYB; c++) B[r * NYB + c] = m[c]; }
                                 __syncwarp();
                             }
+                            __threadfence_block();
+                            if (lane == 0) *chain_done = f + 1;              // L_f, M_f and the inverse pivots of block f are in shared memory
                         }
                         PH_MARK(6);
                     } else {
@@ -1105,6 +1109,38 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                             }
                         }
                         PH_MARK_T(7, 32);
+                        // ---- T = L^-1 Hyx (row a of Hxy in place; row 79: the y part of the rhs), rows on threads 32..111: block f
+                        // of the forward substitution starts as soon as warp 0 has published the factor of block f, so that the
+                        // substitution finishes right behind the chain instead of after it ----
+                        if (t2 <= NX) {
+                            double *row = (t2 < NX) ? s.Hxy + t2 * NY : s.yv + NX;
+                            double tp[NYB];
+                            _Pragma("unroll")
+                            for (int k = 0; k < NYB; k++) tp[k] = 0.0;
+                            _Pragma("unroll 1")
+                            for (int f = 0; f < NFR; f++) {
+                                while (*chain_done <= f) { }
+                                __threadfence_block();
+                                const double *L = s.Ad + f * 169, *idg = s.idg + NYB * f;
+                                double *t = row + NYB * f;
+                                double tc[NYB];
+                                _Pragma("unroll")
+                                for (int r = 0; r < NYB; r++) tc[r] = t[r];
+                                if (f > 0) {
+                                    const double *M = s.Bo + (f - 1) * 169;
+                                    _Pragma("unroll")
+                                    for (int r = 0; r < NYB; r++) { double acc = 0.0; _Pragma("unroll") for (int q = 0; q < NYB; q++) acc += M[r * NYB + q] * tp[q]; tc[r] -= acc; }
+                                }
+                                _Pragma("unroll")
+                                for (int c = 0; c < NYB; c++) {             // right-looking: the dependency chain is 13 (multiply, update) steps
+                                    tc[c] *= idg[c];
+                                    _Pragma("unroll")
+                                    for (int r = c + 1; r < NYB; r++) tc[r] -= L[r * NYB + c] * tc[c];
+                                }
+                                _Pragma("unroll")
+                                for (int r = 0; r < NYB; r++) { t[r] = tc[r]; tp[r] = tc[r]; }
+                            }
+                        }
                     }
                     __syncthreads();
                     if (tid == 0) {
@@ -1113,28 +1149,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                         sca[S_ALPHA] = sca[S_GNORM2] / vhv;
                     }
                     PH_MARK(5);
-                    // ---- T = L^-1 Hyx (row a of Hxy in place), and the same for the y part of the rhs (row 78) ----
-                    if (tid <= NX) {
-                        double *row = (tid < NX) ? s.Hxy + tid * NY : s.yv + NX;
-                        double tp[NYB];
-                        for (int f = 0; f < NFR; f++) {
-                            const double *L = s.Ad + f * 169, *idg = s.idg + NYB * f;
-                            double *t = row + NYB * f;
-                            double tc[NYB];
-                            for (int r = 0; r < NYB; r++) tc[r] = t[r];
-                            if (f > 0) {
-                                const double *M = s.Bo + (f - 1) * 169;
-                                for (int r = 0; r < NYB; r++) { double acc = 0.0; for (int q = 0; q < NYB; q++) acc += M[r * NYB + q] * tp[q]; tc[r] -= acc; }
-                            }
-                            _Pragma("unroll")
-                            for (int c = 0; c < NYB; c++) {                 // right-looking: the dependency chain is 13 (multiply, update) steps
-                                tc[c] *= idg[c];
-                                _Pragma("unroll")
-                                for (int r = c + 1; r < NYB; r++) tc[r] -= L[r * NYB + c] * tc[c];
-                            }
-                            for (int r = 0; r < NYB; r++) { t[r] = tc[r]; tp[r] = tc[r]; }
-                        }
-                    }
+                    // (T = L^-1 Hyx was computed by warps 1..3 behind the chain factorisation, see above)
                     __syncthreads();
                     PH_MARK(8);
                     // ---- S' = S - T T^T (lower), rhs'_x = rhs_x - T gy' : Gram matrix of the 79 x 143 matrix [T; gy'^T] on the

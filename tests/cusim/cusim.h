@@ -73,6 +73,8 @@ inline double __shfl_sync(unsigned, double v, int src) {
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline void __threadfence() {}
+#include <atomic>
+inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 // ---- the slice of the CUDA runtime API the C-ABI layer uses ------------------------------------
 typedef int cudaError_t;

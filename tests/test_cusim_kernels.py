@@ -152,3 +152,21 @@ def test_td_open_window_solve():
 
 def saved_td(saved):
     return np.array([[0.004], [-0.003]])
+
+
+def test_empty_and_single_feature_windows():
+    """Edge cases of the track list: a window with no visual factors at all (IMU-leg factors + prior only) and one with a
+    single feature; both must match the oracle."""
+    cfg = small_cfg(max_batch=2, max_features=16, iters=3)
+    o, s = OracleBackend(cfg), sim_backend(cfg)
+    batch = synth.generate_batch(2, 10, o, window0=5, prior_features=6)
+    batch.descs[0].n_features = 0; batch.descs[0].n_obs = 0
+    batch.descs[1].n_features = 1
+    st = batch.state_array(); saved = batch.copy_states()
+    rep_o = o.solve_batch(batch); ref = st.copy(); lam = batch.para_Feature.copy()
+    batch.restore_states(saved)
+    rep_s = s.solve_batch(batch)
+    assert (rep_o["iterations"] == rep_s["iterations"]).all()
+    assert np.abs(rep_o["final_cost"] - rep_s["final_cost"]).max() < 1e-7 * rep_o["final_cost"].max()
+    d = state_diffs(batch.state_array(), ref)
+    assert d["para_Pose"] < 1e-7 and d["para_SpeedBias"] < 1e-6 and np.abs(batch.para_Feature - lam).max() < 1e-7

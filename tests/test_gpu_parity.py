@@ -164,3 +164,15 @@ def test_td_open_windows(gpu, oracle):
     assert (st["para_Td"] != td0).all() and np.abs(st["para_Td"]).max() < 5e-3
     d = state_diffs(st, ref)
     assert d["para_Pose"] < POS_TOL and d["para_SpeedBias"] < 1e-5 and d["para_Ex_Pose"] < POS_TOL, d
+
+
+def test_maximum_feature_count(oracle):
+    """NUM_OF_F = 1000 features per window (parameters.h:24, the reference's static limit): 16 chunks of tracks, 32 Schur tiles."""
+    cfg = abi.default_config()
+    cfg.max_batch, cfg.max_features, cfg.max_obs = 2, 1000, 1000 * 11
+    big = lib.Backend(cfg)
+    batch = synth.generate_batch(2, 1000, big, cfg=cfg, window0=2000, prior_features=16)
+    rep_o, rep_g, ref, lam, st = solve_both(big, OracleBackend(cfg), batch, nthreads=2)
+    assert (rep_o["iterations"] == rep_g["iterations"]).all()
+    d = state_diffs(st, ref)
+    assert d["para_Pose"] < POS_TOL and d["para_SpeedBias"] < 1e-5 and np.abs(batch.para_Feature - lam).max() < 1e-6, d
