@@ -861,7 +861,10 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
 
         while (true) {
             // =============================== linearise at xs ===========================================
-            if (need_linearize) {
+            // Ceres evaluates the Jacobian at every accepted point, but when that point is the last one allowed by max_num_iterations the
+            // evaluation is never used: FinalizeIterationAndCheckIfMinimizerCanContinue tests the iteration limit before the gradient
+            // tolerance, so termination, states and costs are decided already.  That last linearisation is skipped.
+            if (need_linearize && (iteration < P.max_iters || iteration == 0)) {
                 // start from the prior Hessian image; its Hxx part was prefetched asynchronously when the previous factorisation of
                 // Hxx had been consumed (the copy overlapped with the rest of that iteration), except for the first linearisation
                 if (!has_prior) { for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = 0.0; }
@@ -1457,6 +1460,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                         if (rel > 0.75) sca[S_RADIUS] = fmax(sca[S_RADIUS], 3.0 * sca[S_DLNORM]);
                         sca[S_MU] = fmax(1e-8, 2.0 * sca[S_MU] / 10.0);
                         sca[S_REUSE] = 0; sca[S_NSUCC] += 1; sca[S_OK] = 2;     // 2 == accepted marker
+                        sca[S_XCOST] = cand;                                   // x_cost of the new point (re-evaluated by the next linearisation, if any)
                     } else {                              // StepRejected
                         sca[S_RADIUS] *= 0.5; sca[S_REUSE] = 1; sca[S_OK] = 1;
                     }
