@@ -586,8 +586,9 @@ CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const doubl
     PH_MARK(25);
     const int wid = tid >> 5, lane = tid & 31;
     CERB_CP_ASYNC_WAIT();
-    double *gp = s.gn;                                                  // prior gradient [NRP]; gn | stp | yv are idle during a linearisation
-    double *ppart = s.stp;                                              // [4][PRIOR_LD] partial sums of J0 dx (stp | yv)
+    double *gp = s.stp;                                                 // prior gradient [NRP]; stp | yv are idle during a linearisation (gn is not:
+                                                                        // a rejected speculative linearisation is followed by the dogleg re-use path)
+    double *ppart = s.yv;                                               // [2][PRIOR_LD] partial sums of J0 dx
     for (int k = tid; k < NRP; k += SOLVE_THREADS) gp[k] = 0.0;
     __syncthreads();
     if (wid < IMU_WARPS) {
@@ -698,8 +699,8 @@ CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const doubl
                 prior_block_dx(kind, x + prior_block_state_offset(kind, index), x0 + 9 * t5, s.pdx + col);
             }
             CERB_BAR_SYNC(3, PRIOR_THREADS);
-            const int kc = (n + 3) / 4;
-            for (int e = t5; e < 4 * n; e += PRIOR_THREADS) {
+            const int kc = (n + 1) / 2;
+            for (int e = t5; e < 2 * n; e += PRIOR_THREADS) {
                 const int p = e / n, i = e % n;
                 const int k1 = (p + 1) * kc < n ? (p + 1) * kc : n;
                 double t = 0.0;
@@ -708,7 +709,7 @@ CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const doubl
             }
             CERB_BAR_SYNC(3, PRIOR_THREADS);
             for (int i = t5; i < n; i += PRIOR_THREADS) {
-                const double t = (((r0[i] + ppart[i]) + ppart[PRIOR_LD + i]) + ppart[2 * PRIOR_LD + i]) + ppart[3 * PRIOR_LD + i];
+                const double t = (r0[i] + ppart[i]) + ppart[PRIOR_LD + i];
                 s.pr[i] = t; cost += 0.5 * t * t;
             }
             CERB_BAR_SYNC(3, PRIOR_THREADS);
@@ -774,7 +775,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
     double *sca = s.sca;
     // scalar slots
     enum { S_RADIUS = 0, S_MU, S_REUSE, S_XCOST, S_CCOST, S_ALPHA, S_GNORM2, S_GNNORM2, S_GDOTGN, S_MODEL, S_STEPNORM, S_XNORM, S_DLNORM,
-           S_OK, S_DONE, S_TERM, S_ITER, S_NSUCC, S_INVALID, S_GMAX, S_INIT_COST, S_P, S_Q, S_VHV };
+           S_OK, S_DONE, S_TERM, S_ITER, S_NSUCC, S_INVALID, S_GMAX, S_INIT_COST, S_P, S_Q, S_VHV, S_LCOST, S_LNORM, S_LGMAX };
 
     PH_DECL();
     if (tid < 32) {
@@ -856,38 +857,34 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
             sca[S_INVALID] = 0; sca[S_DLNORM] = 0;
         }
         __syncthreads();
-        bool need_linearize = true, hxx_prefetched = false;
+        bool need_linearize = true, hxx_prefetched = false, last_accepted = true;
         int iteration = 0;
 
-        while (true) {
-            // =============================== linearise at xs ===========================================
-            // Ceres evaluates the Jacobian at every accepted point, but when that point is the last one allowed by max_num_iterations the
-            // evaluation is never used: FinalizeIterationAndCheckIfMinimizerCanContinue tests the iteration limit before the gradient
-            // tolerance, so termination, states and costs are decided already.  That last linearisation is skipped.
-            if (need_linearize && (iteration < P.max_iters || iteration == 0)) {
+        // ---- linearisation at (xl, laml): H, g (Jacobi scaled), W, hh, gl; results S_LCOST (cost), S_LNORM (||x||), S_LGMAX (max |g|) --------
+        auto linearize = [&](const double *xl, const double *laml, bool first) {
                 // start from the prior Hessian image; its Hxx part was prefetched asynchronously when the previous factorisation of
                 // Hxx had been consumed (the copy overlapped with the rest of that iteration), except for the first linearisation
                 if (!has_prior) { for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = 0.0; }
                 else { if (!hxx_prefetched) copy_g2s_async(s.Hxx, pimg, HXX_SZ, tid); CERB_CP_ASYNC_WAIT(); }
                 hxx_prefetched = false;
                 for (int k = tid; k < NRP; k += SOLVE_THREADS) s.g[k] = 0.0;
-                load_geometry(s.xs, s, tid);
+                load_geometry(xl, s, tid);
                 double part[2];
                 PH_MARK(0);
-                part[0] = vision_linearize(P, w, s.xs, lam, W, hh, gl, sl, iteration > 0, chunks, tid);
+                part[0] = vision_linearize(P, w, xl, laml, W, hh, gl, sl, !first, chunks, tid);
                 if (has_prior) copy_g2s_async(s.Hxy, pimg + HXX_SZ, HXY_SZ + 1859 + 1690, tid);              // Hxy | Ad | Bo (contiguous; the tile aliased them);
                 else for (int k = tid; k < HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) s.Hxy[k] = 0.0;         // completed inside inertial_linearize
                 __syncthreads();
                 PH_MARK(1);
-                part[0] += inertial_linearize(P, w, s.xs, tid);
+                part[0] += inertial_linearize(P, w, xl, tid);
                 PH_MARK(2);
-                part[1] = ambient_sq(s.xs, nullptr, lam, nullptr, nF, ex_open, lb_open, td_open, tid);
+                part[1] = ambient_sq(xl, nullptr, laml, nullptr, nF, ex_open, lb_open, td_open, tid);
                 double tot[2];
                 block_sum<2>(part, s.red, tot, tid);
-                if (tid == 0) { sca[S_XCOST] = tot[0]; sca[S_XNORM] = sqrt(tot[1]); if (iteration == 0) sca[S_INIT_COST] = tot[0]; }
+                if (tid == 0) { sca[S_LCOST] = tot[0]; sca[S_LNORM] = sqrt(tot[1]); }
                 // (Hxx holds its upper triangle; it is mirrored and scaled in one row-wise pass below)
-                // gradient max norm over active dims (unscaled), Jacobi scale at iteration 0
-                if (iteration == 0) {
+                // gradient max norm over active dims (unscaled), Jacobi scale at the first linearisation
+                if (first) {
                     for (int k = tid; k < NR; k += SOLVE_THREADS) {
                         double d;
                         bool active = true;
@@ -898,7 +895,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                     for (int f = tid; f < nF; f += SOLVE_THREADS) sl[f] = 1.0 / (1.0 + sqrt(hh[f]));
                 }
                 __syncthreads();
-                if (P.dbg && w == P.dbg_window && iteration == 0) {      // parity probe, ABI order
+                if (P.dbg && w == P.dbg_window && first) {      // parity probe, ABI order
                     for (int k = tid; k < NR; k += SOLVE_THREADS) {
                         int dst; double d;
                         if (k < NX) { dst = k < X_TD ? k : 221; d = s.Hxx[k * NX + k]; }      // ABI order: td after the leg biases
@@ -907,15 +904,15 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                         P.dbg[1 + dst] = act ? s.g[k] : 0.0; P.dbg[1 + NR + F + dst] = act ? d : 0.0;
                     }
                     for (int f = tid; f < nF; f += SOLVE_THREADS) { P.dbg[1 + NR + f] = gl[f]; P.dbg[1 + NR + F + NR + f] = hh[f]; }
-                    if (tid == 0) P.dbg[0] = sca[S_XCOST];
+                    if (tid == 0) P.dbg[0] = sca[S_LCOST];
                 }
                 double gm = 0.0;
                 for (int k = tid; k < NR; k += SOLVE_THREADS) if (s.sc[k] != 0.0) gm = fmax(gm, fabs(s.g[k]));
-                for (int f = tid; f < nF; f += SOLVE_THREADS) gm = fmax(gm, fabs(iteration > 0 ? gl[f] / sl[f] : gl[f]));   // unscaled gradient
+                for (int f = tid; f < nF; f += SOLVE_THREADS) gm = fmax(gm, fabs(!first ? gl[f] / sl[f] : gl[f]));   // unscaled gradient
                 for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_sync(0xffffffffu, gm, (tid + o) & 31));
                 if ((tid & 31) == 0) s.red[tid >> 5] = gm;
                 __syncthreads();
-                if (tid == 0) { double m8 = s.red[0]; for (int k = 1; k < SOLVE_THREADS / 32; k++) m8 = fmax(m8, s.red[k]); sca[S_GMAX] = m8; }
+                if (tid == 0) { double m8 = s.red[0]; for (int k = 1; k < SOLVE_THREADS / 32; k++) m8 = fmax(m8, s.red[k]); sca[S_LGMAX] = m8; }
                 // apply the Jacobi scaling: H~ = S H S, g~ = S g, w~_f = s_f S_x w_f, h~ = s_f^2 h, gl~ = s_f gl.  Row-wise (a warp per
                 // row: no index divisions); the Hxx pass also mirrors the upper triangle into the lower one.
                 for (int a = tid >> 5; a < NX; a += SOLVE_THREADS / 32) {
@@ -926,10 +923,20 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                 for (int k = tid; k < 1859; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; s.Ad[k] *= s.sc[NX + NYB * f + a] * s.sc[NX + NYB * f + b]; }
                 for (int k = tid; k < 1690; k += SOLVE_THREADS) { const int f = k / 169, a = (k % 169) / NYB, b = k % NYB; s.Bo[k] *= s.sc[NX + NYB * f + a] * s.sc[NX + NYB * (f + 1) + b]; }
                 for (int k = tid; k < NR; k += SOLVE_THREADS) s.g[k] *= s.sc[k];
-                if (iteration == 0) {      // later linearisations write W, hh, gl pre-scaled
+                if (first) {      // later linearisations write W, hh, gl pre-scaled
                     for (int k = tid; k < NX * nF; k += SOLVE_THREADS) { const int a = k / nF, f = k % nF; W[(size_t)a * F + f] *= s.sc[a] * sl[f]; }
                     for (int f = tid; f < nF; f += SOLVE_THREADS) { hh[f] *= sl[f] * sl[f]; gl[f] *= sl[f]; }
                 }
+                __syncthreads();
+        };
+        while (true) {
+            // =============================== linearise at xs ===========================================
+            // Ceres evaluates the Jacobian at every accepted point, but when that point is the last one allowed by max_num_iterations the
+            // evaluation is never used: FinalizeIterationAndCheckIfMinimizerCanContinue tests the iteration limit before the gradient
+            // tolerance, so termination, states and costs are decided already.  That last linearisation is skipped.
+            if (need_linearize && (iteration < P.max_iters || iteration == 0)) {
+                linearize(s.xs, lam, iteration == 0);
+                if (tid == 0) { sca[S_XCOST] = sca[S_LCOST]; sca[S_XNORM] = sca[S_LNORM]; sca[S_GMAX] = sca[S_LGMAX]; if (iteration == 0) sca[S_INIT_COST] = sca[S_LCOST]; }
                 __syncthreads();
                 need_linearize = false;
                 PH_MARK(3);
@@ -1429,19 +1436,27 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
             // =============================== candidate point and its cost ===================================
             PH_MARK(14);
             apply_plus(s, s.stp, lam, stl, lamc, nF, ex_open, td_open, tid);
-            load_geometry(s.xc, s, tid);
+            // Speculative linearisation: if the previous step of this window was accepted, the candidate is linearised right away --
+            // its cost is the candidate cost, and when the step is accepted (the common case) the linearisation of the next iteration
+            // is already there, so the separate cost-only pass is saved.  A rejected step leaves H / g / W at the candidate, which is
+            // harmless: the re-use path of the dogleg needs none of them.  Not done for the last allowed iteration (never needed).
+            const bool speculate = last_accepted && iteration < P.max_iters;
             {
                 double part[2];
                 PH_MARK(15);
-                part[0] = vision_cost(P, w, s.xc, lamc, tid);
-                PH_MARK(16);
-                part[0] += inertial_cost(P, w, s.xc, tid);
+                if (speculate) { linearize(s.xc, lamc, false); part[0] = 0.0; }
+                else {
+                    load_geometry(s.xc, s, tid);
+                    part[0] = vision_cost(P, w, s.xc, lamc, tid);
+                    PH_MARK(16);
+                    part[0] += inertial_cost(P, w, s.xc, tid);
+                }
                 PH_MARK(17);
                 part[1] = ambient_sq(s.xs, s.xc, lam, lamc, nF, ex_open, lb_open, td_open, tid);
                 double tot[2];
                 block_sum<2>(part, s.red, tot, tid);
                 if (tid == 0) {
-                    double cc = tot[0];
+                    double cc = speculate ? sca[S_LCOST] : tot[0];
                     if (!(cc == cc) || fabs(cc) > 1e300) cc = 1.7976931348623157e308;
                     sca[S_CCOST] = cc; sca[S_STEPNORM] = sqrt(tot[1]);
                 }
@@ -1473,10 +1488,11 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
             if (accepted) {
                 for (int k = tid; k < ST_STRIDE; k += SOLVE_THREADS) s.xs[k] = s.xc[k];
                 for (int f = tid; f < nF; f += SOLVE_THREADS) lam[f] = lamc[f];
-                if (tid == 0) sca[S_OK] = 1;
+                if (tid == 0) { sca[S_OK] = 1; if (speculate) { sca[S_XNORM] = sca[S_LNORM]; sca[S_GMAX] = sca[S_LGMAX]; } }
                 __syncthreads();
-                need_linearize = true;
+                need_linearize = !speculate;                     // a speculative linearisation is the linearisation at the new point
             }
+            last_accepted = accepted;
             PH_MARK(18);
         }
         // ---- write back ---------------------------------------------------------------------------------

@@ -170,3 +170,30 @@ def test_empty_and_single_feature_windows():
     assert np.abs(rep_o["final_cost"] - rep_s["final_cost"]).max() < 1e-7 * rep_o["final_cost"].max()
     d = state_diffs(batch.state_array(), ref)
     assert d["para_Pose"] < 1e-7 and d["para_SpeedBias"] < 1e-6 and np.abs(batch.para_Feature - lam).max() < 1e-7
+
+
+def _rejected_steps_case(backend_factory):
+    """Windows whose trust region rejects steps (min_relative_decrease raised to 0.97 for both sides): exercises the dogleg re-use
+    path after a rejected step -- in particular after a rejected SPECULATIVE linearisation of the candidate -- against the oracle."""
+    cfg = small_cfg(max_batch=6, max_features=16, iters=12)
+    cfg.min_relative_decrease = 0.97
+    o, s = OracleBackend(cfg), backend_factory(cfg)
+    batch = synth.generate_batch(6, 12, o, window0=900, prior_features=6)
+    st = batch.state_array()
+    rng = np.random.default_rng(3)
+    for w in range(6):
+        st["para_Pose"][w, :, :3] += rng.normal(0, 0.1 + 0.1 * w, (11, 3))
+        batch.para_Feature[w] *= np.exp(rng.normal(0, 0.5, batch.para_Feature.shape[1]))
+    saved = batch.copy_states()
+    rep_o = o.solve_batch(batch); ref = st.copy(); lam = batch.para_Feature.copy()
+    batch.restore_states(saved)
+    rep_s = s.solve_batch(batch)
+    assert (rep_o["num_successful_steps"] < rep_o["iterations"]).any()          # the case does contain rejected steps
+    assert (rep_o["iterations"] == rep_s["iterations"]).all() and (rep_o["num_successful_steps"] == rep_s["num_successful_steps"]).all()
+    assert np.abs(rep_o["final_cost"] - rep_s["final_cost"]).max() < 1e-7 * rep_o["final_cost"].max()
+    d = state_diffs(batch.state_array(), ref)
+    assert d["para_Pose"] < 1e-6 and d["para_SpeedBias"] < 1e-6 and np.abs(batch.para_Feature - lam).max() < 1e-6, d
+
+
+def test_rejected_steps_match_oracle():
+    _rejected_steps_case(sim_backend)

@@ -176,3 +176,8 @@ def test_maximum_feature_count(oracle):
     assert (rep_o["iterations"] == rep_g["iterations"]).all()
     d = state_diffs(st, ref)
     assert d["para_Pose"] < POS_TOL and d["para_SpeedBias"] < 1e-5 and np.abs(batch.para_Feature - lam).max() < 1e-6, d
+
+
+def test_rejected_steps_match_oracle_gpu():
+    from test_cusim_kernels import _rejected_steps_case
+    _rejected_steps_case(lambda cfg: lib.Backend(cfg))
