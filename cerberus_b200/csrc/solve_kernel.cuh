@@ -1129,7 +1129,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                             for (int k = 0; k < NYB; k++) tp[k] = 0.0;
                             _Pragma("unroll 1")
                             for (int f = 0; f < NFR; f++) {
-                                while (*chain_done <= f) { }
+                                while (*chain_done <= f) { CERB_SPIN_PAUSE(); }
                                 __threadfence_block();
                                 const double *L = s.Ad + f * 169, *idg = s.idg + NYB * f;
                                 double *t = row + NYB * f;

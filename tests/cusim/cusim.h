@@ -43,6 +43,7 @@ inline void __syncthreads() { pthread_barrier_wait(&cusim::block_barrier); }
 inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cusim::warp_barriers[threadIdx.x / 32]); }
 #define CERB_CP_ASYNC8(dst_smem, src_global) (*(dst_smem) = *(src_global))
 #define CERB_CP_ASYNC_WAIT() ((void)0)
+#define CERB_SPIN_PAUSE() std::this_thread::yield()
 // named barriers (bar.sync id, nthreads) among subsets of the warps of a block
 namespace cusim { void named_sync(int id, int nthreads); }
 #define CERB_BAR_SYNC(id, nthreads) cusim::named_sync((id), (nthreads))

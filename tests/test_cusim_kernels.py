@@ -172,16 +172,16 @@ def test_empty_and_single_feature_windows():
     assert d["para_Pose"] < 1e-7 and d["para_SpeedBias"] < 1e-6 and np.abs(batch.para_Feature - lam).max() < 1e-7
 
 
-def _rejected_steps_case(backend_factory):
+def _rejected_steps_case(backend_factory, nw=6, iters=12):
     """Windows whose trust region rejects steps (min_relative_decrease raised to 0.97 for both sides): exercises the dogleg re-use
     path after a rejected step -- in particular after a rejected SPECULATIVE linearisation of the candidate -- against the oracle."""
-    cfg = small_cfg(max_batch=6, max_features=16, iters=12)
+    cfg = small_cfg(max_batch=6, max_features=16, iters=iters)
     cfg.min_relative_decrease = 0.97
     o, s = OracleBackend(cfg), backend_factory(cfg)
-    batch = synth.generate_batch(6, 12, o, window0=900, prior_features=6)
+    batch = synth.generate_batch(nw, 12, o, window0=900 + (6 - nw), prior_features=6)
     st = batch.state_array()
     rng = np.random.default_rng(3)
-    for w in range(6):
+    for w in range(nw):
         st["para_Pose"][w, :, :3] += rng.normal(0, 0.1 + 0.1 * w, (11, 3))
         batch.para_Feature[w] *= np.exp(rng.normal(0, 0.5, batch.para_Feature.shape[1]))
     saved = batch.copy_states()
@@ -196,4 +196,4 @@ def _rejected_steps_case(backend_factory):
 
 
 def test_rejected_steps_match_oracle():
-    _rejected_steps_case(sim_backend)
+    _rejected_steps_case(sim_backend, nw=3, iters=9)          # (the GPU tier runs the 6-window / 12-iteration case)

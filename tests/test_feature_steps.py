@@ -9,7 +9,7 @@ from oracle_lib import OracleBackend
 from helpers import sim_backend, small_cfg
 
 
-def _batch(backend, realistic, n=3, F=24):
+def _batch(backend, realistic, n=2, F=24):
     batch = synth.generate_batch(n, F, backend, realistic=realistic, window0=77, prior_features=8)
     return batch
 
@@ -45,7 +45,7 @@ def _check_backend(be, oracle, realistic):
 
 @pytest.mark.parametrize("realistic", [False, True])
 def test_feature_steps_sim(realistic):
-    cfg = small_cfg(max_batch=4, max_features=24, iters=4)
+    cfg = small_cfg(max_batch=4, max_features=24, iters=3)
     _check_backend(sim_backend(cfg), OracleBackend(cfg), realistic)
 
 
