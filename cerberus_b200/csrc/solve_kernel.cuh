@@ -761,6 +761,60 @@ CERB_D double ambient_sq(const double *a, const double *b, const double *la, con
     return t;
 }
 
+// ---- S' = S - T T^T for one warp (see the call site).  The 55 upper 8 x 8 blocks of the 80 x 80 Gram matrix of [T; gy'^T] are dealt to
+// the 8 warps as rectangles of the block grid, so that a warp's 6-7 blocks share 4-7 fragment rows: 40 fragment loads per k-step
+// and CTA instead of 110 (the row stride of T, 143 doubles, makes every fragment load a 4-way bank conflict, and the loop was bound
+// by exactly that).  TT_ROWS: distinct block rows of warp W; TT_A / TT_B: the two block rows of each of its blocks (indices into
+// TT_ROWS); everything is compile-time so that the fragments stay in registers.
+template <int W> struct TTPlan;
+#define CERB_TT_PLAN(W, NR_, NB_, ...) template <> struct TTPlan<W> { static constexpr int nr = NR_, nb = NB_; static CERB_HD int tab(int i) { constexpr int t[] = {__VA_ARGS__}; return t[i]; } };
+//            rows (padded to 7)           block -> first row index      block -> second row index
+CERB_TT_PLAN(0, 4, 7, 0, 1, 2, 3, 0, 0, 0,   0, 0, 1, 0, 1, 0, 1,   0, 1, 1, 2, 2, 3, 3)
+CERB_TT_PLAN(1, 4, 7, 2, 3, 4, 5, 0, 0, 0,   0, 0, 1, 0, 1, 0, 1,   0, 1, 1, 2, 2, 3, 3)
+CERB_TT_PLAN(2, 4, 7, 4, 5, 6, 7, 0, 0, 0,   0, 0, 1, 0, 1, 0, 1,   0, 1, 1, 2, 2, 3, 3)
+CERB_TT_PLAN(3, 4, 7, 6, 7, 8, 9, 0, 0, 0,   0, 0, 1, 0, 1, 0, 1,   0, 1, 1, 2, 2, 3, 3)
+CERB_TT_PLAN(4, 6, 7, 8, 9, 0, 1, 4, 5, 0,   0, 0, 1, 2, 3, 2, 3,   0, 1, 1, 4, 4, 5, 5)
+CERB_TT_PLAN(5, 6, 7, 0, 1, 6, 7, 8, 9, 0,   0, 0, 0, 0, 1, 1, 1,   2, 3, 4, 5, 2, 3, 4)
+CERB_TT_PLAN(6, 7, 7, 1, 9, 2, 6, 7, 8, 3,   0, 2, 2, 2, 2, 6, 6,   1, 3, 4, 5, 1, 3, 4)
+CERB_TT_PLAN(7, 5, 6, 3, 4, 5, 8, 9, 0, 0,   0, 0, 1, 1, 2, 2, 0,   3, 4, 3, 4, 3, 4, 0)
+template <int W> CERB_D void ttt_warp(Smem &s, int lane) {
+    typedef TTPlan<W> PL;
+    const double *pr[7];
+    _Pragma("unroll")
+    for (int u = 0; u < 7; u++) {
+        const int r = 8 * PL::tab(u < PL::nr ? u : 0) + (lane >> 2);
+        pr[u] = (r < NX ? s.Hxy + r * NY : s.yv + NX) + (lane & 3);      // rows 0..78 of T, row 79 = gy'
+    }
+    double acc[7][2], fv[7];
+    _Pragma("unroll")
+    for (int k = 0; k < 7; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
+    _Pragma("unroll")
+    for (int u = 0; u < 7; u++) fv[u] = (u < PL::nr) ? pr[u][0] : 0.0;
+    for (int q0 = 0; q0 < NY; q0 += 4) {
+        const int qn = q0 + 4;
+        const bool take = qn < NY && qn + (lane & 3) < NY;                   // the last k-step holds 3 valid columns (K = 143)
+        double fn[7];
+        _Pragma("unroll")
+        for (int u = 0; u < 7; u++) fn[u] = (u < PL::nr && take) ? pr[u][qn] : 0.0;
+        _Pragma("unroll")
+        for (int k = 0; k < 7; k++) if (k < PL::nb) CERB_DMMA(acc[k][0], acc[k][1], fv[PL::tab(7 + k)], fv[PL::tab(14 + k)], acc[k][0], acc[k][1]);
+        _Pragma("unroll")
+        for (int u = 0; u < 7; u++) fv[u] = fn[u];
+    }
+    _Pragma("unroll")
+    for (int k = 0; k < 7; k++) {
+        if (k >= PL::nb) continue;
+        const int ba = PL::tab(PL::tab(7 + k)), bb = PL::tab(PL::tab(14 + k));        // block rows (ba <= bb)
+        const int a = 8 * ba + (lane >> 2);
+        for (int e = 0; e < 2; e++) {
+            const int b = 8 * bb + 2 * (lane & 3) + e;
+            if (a > b || a >= NX || b > NX) continue;
+            if (b == NX) s.yv[a] -= acc[k][e];
+            else s.Hxx[b * NX + a] -= acc[k][e];
+        }
+    }
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------------------
 CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID_CONSTANT SolveParams P) {
     CERB_DYN_SMEM(double, smem_base);
@@ -1163,50 +1217,16 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                     __syncthreads();
                     PH_MARK(8);
                     // ---- S' = S - T T^T (lower), rhs'_x = rhs_x - T gy' : Gram matrix of the 79 x 143 matrix [T; gy'^T] on the
-                    // fp64 tensor cores, 55 upper 8x8 blocks dealt round-robin to the 8 warps, K = 143 padded to 144 ----------
-                    {
-                        const int wq = tid >> 5, lane = tid & 31;
-                        double acc[7][2];
-                        int tmi[7], tni[7];
-                        for (int k = 0; k < 7; k++) {
-                            acc[k][0] = 0.0; acc[k][1] = 0.0;
-                            int idx = wq + 8 * k, mi = 0;
-                            if (idx >= 55) { tmi[k] = -1; tni[k] = 0; continue; }
-                            while (idx >= 10 - mi) { idx -= 10 - mi; mi++; }
-                            tmi[k] = mi; tni[k] = mi + idx;
-                        }
-                        // row pointers of this lane's fragments (rows 0..78 of T, row 79 = gy'); operands are fetched one k-step ahead
-                        const double *pa[7], *pb[7];
-                        _Pragma("unroll")
-                        for (int k = 0; k < 7; k++) {
-                            const int ra = 8 * (tmi[k] < 0 ? 0 : tmi[k]) + (lane >> 2), rb = 8 * tni[k] + (lane >> 2);
-                            pa[k] = (ra < NX ? s.Hxy + ra * NY : s.yv + NX) + (lane & 3);
-                            pb[k] = (rb < NX ? s.Hxy + rb * NY : s.yv + NX) + (lane & 3);
-                        }
-                        double av[7], bv[7];
-                        _Pragma("unroll")
-                        for (int k = 0; k < 7; k++) { av[k] = pa[k][0]; bv[k] = pb[k][0]; }
-                        for (int q0 = 0; q0 < NY; q0 += 4) {
-                            const int qn = q0 + 4;
-                            const bool more = qn < NY, tail = qn + (lane & 3) >= NY;      // the last k-step holds 3 valid columns (K = 143)
-                            double an[7], bn[7];
-                            _Pragma("unroll")
-                            for (int k = 0; k < 7; k++) { an[k] = (more && !tail) ? pa[k][qn] : 0.0; bn[k] = (more && !tail) ? pb[k][qn] : 0.0; }
-                            _Pragma("unroll")
-                            for (int k = 0; k < 7; k++) CERB_DMMA(acc[k][0], acc[k][1], av[k], bv[k], acc[k][0], acc[k][1]);
-                            _Pragma("unroll")
-                            for (int k = 0; k < 7; k++) { av[k] = an[k]; bv[k] = bn[k]; }
-                        }
-                        for (int k = 0; k < 7; k++) {
-                            if (tmi[k] < 0) continue;
-                            const int a = 8 * tmi[k] + (lane >> 2);
-                            for (int e = 0; e < 2; e++) {
-                                const int b = 8 * tni[k] + 2 * (lane & 3) + e;
-                                if (a > b || a >= NX || b > NX) continue;
-                                if (b == NX) s.yv[a] -= acc[k][e];
-                                else s.Hxx[b * NX + a] -= acc[k][e];
-                            }
-                        }
+                    // fp64 tensor cores, K = 143 padded to 144; block rectangles per warp, see ttt_warp ----------
+                    switch (tid >> 5) {
+                        case 0: ttt_warp<0>(s, tid & 31); break;
+                        case 1: ttt_warp<1>(s, tid & 31); break;
+                        case 2: ttt_warp<2>(s, tid & 31); break;
+                        case 3: ttt_warp<3>(s, tid & 31); break;
+                        case 4: ttt_warp<4>(s, tid & 31); break;
+                        case 5: ttt_warp<5>(s, tid & 31); break;
+                        case 6: ttt_warp<6>(s, tid & 31); break;
+                        default: ttt_warp<7>(s, tid & 31); break;
                     }
                     __syncthreads();
                     PH_MARK(9);
