@@ -13,6 +13,8 @@
 #include <cstring>
 #include <cstdio>
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 using namespace cerb;
 
@@ -412,6 +414,9 @@ int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, Cerb
         bounds[nch] = n;
     }
     h->n = n;
+    const bool trace = std::getenv("CERB_TRACE") != nullptr;            // host timeline of the pipeline on stderr (diagnostics)
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now(); double t_pack = 0.0, t_enq = 0.0;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     for (int c = 0; c < nch; c++) {
         const int w0 = bounds[c], cn = bounds[c + 1] - bounds[c];
@@ -420,15 +425,21 @@ int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, Cerb
         const int nsub = (c == 0 && cn >= 32) ? 4 : 1;
         for (int q = 0; q < nsub; q++) {
             const int s0 = w0 + (int)((long)cn * q / nsub), s1 = w0 + (int)((long)cn * (q + 1) / nsub);
+            const double ta = now();
             rc = pack_range(h, s0, s1 - s0, descs, states); if (rc) return rc;
+            const double tb = now();
             rc = upload_range(h, s0, s1 - s0, h->copy_stream); if (rc) return rc;
+            t_pack += tb - ta; t_enq += now() - tb;
         }
         CUDA_TRY(cudaEventRecord(h->ev_copy[c], h->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy[c], 0));
         rc = enqueue_solve(h, w0, cn, h->cfg.max_num_iterations, nullptr, -1); if (rc) return rc;
     }
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->ev_pending = true; h->last_launches = 3 * nch;
-    return download(h, states, reports);
+    const double t_issued = now();
+    rc = download(h, states, reports);
+    if (trace) std::fprintf(stderr, "[cerb_solve_batch] n=%d chunks=%d pack %.2f ms, enqueue copies %.2f ms, all issued at %.2f ms, done at %.2f ms\n", n, nch, t_pack, t_enq, t_issued - t_begin, now() - t_begin);
+    return rc;
 }
 int cerb_solve_window(CerbHandle *h, const CerbWindowDesc *desc, CerbWindowState *state, CerbSolveReport *report) {
     return cerb_solve_batch(h, 1, desc, state, report);
