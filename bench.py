@@ -121,10 +121,29 @@ def run_reference(args, rank, world):
                          "sample": f"{CPU_SAMPLE} windows per step, one window per thread, each solve single-threaded like the reference (estimator.cpp:1224)"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything except the ONE JSON line goes to stderr: libraries (NCCL prints its version banner to stdout under torchrun) write
+    to file descriptor 1 directly, so fd 1 is pointed at stderr and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -257,7 +276,7 @@ def main():
                                         "sample": f"the first {ns} windows of the batch, one window per thread, each solve single-threaded like the reference (estimator.cpp:1224); {dt:.2f} s wall"}
             except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
