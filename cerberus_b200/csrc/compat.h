@@ -28,6 +28,8 @@
 #define CERB_CP_ASYNC_WAIT() asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory")
 // body of a spin-wait on a shared-memory flag (a short sleep keeps the polling warps out of the producer's issue slots)
 #define CERB_SPIN_PAUSE() __nanosleep(20)
+// non-blocking arrival at a named barrier (producer / consumer hand-over: one side arrives, the other side syncs)
+#define CERB_BAR_ARRIVE(id, nthreads) asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory")
 // fp64 tensor-core MMA, D(8x8) = A(8x4, row) * B(4x8, col) + C.  Fragment layout (PTX ISA, m8n8k4 .f64):
 //   a = A[lane / 4][lane % 4], b = B[lane % 4][lane / 4], c/d{0,1} = C[lane / 4][2 * (lane % 4) + {0,1}]
 #define CERB_DMMA(d0, d1, a, b, c0, c1) \

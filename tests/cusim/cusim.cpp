@@ -9,6 +9,11 @@ pthread_barrier_t block_barrier;
 pthread_barrier_t *warp_barriers = nullptr;
 struct NamedBar { std::mutex m; std::condition_variable cv; int waiting = 0; unsigned gen = 0; };
 static NamedBar named_bars[16];
+void named_arrive(int id, int n) {
+    NamedBar &b = named_bars[id & 15];
+    std::unique_lock<std::mutex> lk(b.m);
+    if (++b.waiting == n) { b.waiting = 0; b.gen++; b.cv.notify_all(); }
+}
 void named_sync(int id, int n) {
     NamedBar &b = named_bars[id & 15];
     std::unique_lock<std::mutex> lk(b.m);

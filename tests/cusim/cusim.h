@@ -45,7 +45,8 @@ inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cusim::wa
 #define CERB_CP_ASYNC_WAIT() ((void)0)
 #define CERB_SPIN_PAUSE() std::this_thread::yield()
 // named barriers (bar.sync id, nthreads) among subsets of the warps of a block
-namespace cusim { void named_sync(int id, int nthreads); }
+namespace cusim { void named_sync(int id, int nthreads); void named_arrive(int id, int nthreads); }
+#define CERB_BAR_ARRIVE(id, nthreads) cusim::named_arrive((id), (nthreads))
 #define CERB_BAR_SYNC(id, nthreads) cusim::named_sync((id), (nthreads))
 // emulation of mma.sync.m8n8k4.f64 across the 32 threads of a (simulated) warp
 namespace cusim { extern double *warp_scratch; }
