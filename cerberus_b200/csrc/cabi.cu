@@ -103,6 +103,7 @@ int cerb_create(const CerbSolverConfig *cfg, CerbHandle **out) {
     h->smem_bytes = (size_t)SMEM_DOUBLES * sizeof(double);
     if (h->smem_bytes > prop.sharedMemPerBlockOptin) { delete h; return fail(CERB_ERR_CUDA, "solve kernel needs more shared memory than the device offers"); }
     CUDA_TRY(cudaFuncSetAttribute(vilo_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(prior_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PRIOR_TROWS * PRIOR_TLD * sizeof(double))));
     CUDA_TRY(cudaStreamCreate(&h->stream));
     CUDA_TRY(cudaStreamCreate(&h->copy_stream));
     for (int k = 0; k < 8; k++) CUDA_TRY(cudaEventCreate(&h->ev_copy[k]));
@@ -309,7 +310,7 @@ static int enqueue_solve(CerbHandle *h, int w0, int n, int max_iters, double *db
     CUDA_TRY(cudaMemcpyAsync(h->d_lam + W0 * h->F, h->d_lam0 + W0 * h->F, (size_t)n * h->F * sizeof(double), cudaMemcpyDeviceToDevice, s));
     const int nfac = n * 10;
     CERB_LAUNCH(imu_leg_prepare_kernel, (nfac + 1) / 2, 64, 0, s, nfac, (const double *)(h->d_pre + W0 * 10 * PRE_STRIDE), h->d_sinfo + W0 * 10 * 961);
-    CERB_LAUNCH(prior_prepare_kernel, n, 256, 0, s, (const double *)(h->d_pJ + W0 * PRIOR_LD * PRIOR_LD), (const int *)(h->d_pmeta + W0 * PRIOR_META_STRIDE), h->d_pHp + W0 * PRIOR_LD * PRIOR_LD);
+    CERB_LAUNCH(prior_prepare_kernel, n, 256, (size_t)PRIOR_TROWS * PRIOR_TLD * sizeof(double), s, (const double *)(h->d_pJ + W0 * PRIOR_LD * PRIOR_LD), (const int *)(h->d_pmeta + W0 * PRIOR_META_STRIDE), h->d_pHp + W0 * PRIOR_LD * PRIOR_LD);
     SolveParams P = make_params(h, w0, n, max_iters, dbg, dbg_window);
     if (max_iters > 0) h->solved = true;
     CERB_LAUNCH(vilo_solve_kernel, std::min(n, h->grid), SOLVE_THREADS, h->smem_bytes, s, P);
@@ -409,7 +410,9 @@ int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, Cerb
     if (n <= 2 * wave) { bounds[1] = n; nch = 1; }
     else {
         int pos = wave; bounds[++nch] = pos;
-        const int rest = n - pos, per = ((rest + 5) / 6 + wave - 1) / wave * wave;      // <= 6 more chunks, whole waves each
+        // <= 3 more chunks of whole waves: large copies run at ~2x the PCIe rate of wave-sized ones, and with two waves per chunk the
+        // solve of a chunk (2 x 3.3 ms) still covers the pack + copy of the next one
+        const int rest = n - pos, per = ((rest + 2) / 3 + wave - 1) / wave * wave;
         while (pos < n && nch < 7) { pos = std::min(n, pos + per); bounds[++nch] = pos; }
         bounds[nch] = n;
     }

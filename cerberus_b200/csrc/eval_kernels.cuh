@@ -60,14 +60,14 @@ CERB_D void warp_sqrt_info(const double *cov, double *info, double *sm, int lane
     __syncwarp();
     // LU with partial pivoting (right-looking), lanes = rows for the update
     for (int k = 0; k < N; k++) {
-        if (lane == 0) {
-            int p = k; double best = fabs(A[k * LD + k]);
-            for (int i = k + 1; i < N; i++) { double v = fabs(A[i * LD + k]); if (v > best) { best = v; p = i; } }
-            piv[40] = (double)p;
-            if (best == 0.0) *ok_flag = 0;
+        // partial pivoting: first row of maximal |A[i][k]|, i >= k (same choice as a serial scan), by a warp arg-max
+        double bv = (lane >= k && lane < N) ? fabs(A[lane * LD + k]) : -1.0, bi = (double)lane;
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_sync(0xffffffffu, bv, (lane + o) & 31), oi = __shfl_sync(0xffffffffu, bi, (lane + o) & 31);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        __syncwarp();
-        const int p = (int)piv[40];
+        if (lane == 0 && bv == 0.0) *ok_flag = 0;
+        const int p = (int)bi;
         if (p != k) {
             if (lane < N) { double t = A[k * LD + lane]; A[k * LD + lane] = A[p * LD + lane]; A[p * LD + lane] = t; }
             if (lane == 0) { double t = piv[k]; piv[k] = piv[p]; piv[p] = t; }
@@ -97,11 +97,14 @@ CERB_D void warp_sqrt_info(const double *cov, double *info, double *sm, int lane
     __syncwarp();
     // Cholesky of the lower triangle of X (left-looking), L overwrites the lower triangle
     for (int j = 0; j < N; j++) {
-        if (lane == 0) {
-            double s = X[j * LD + j];
-            for (int k = 0; k < j; k++) s -= X[j * LD + k] * X[j * LD + k];
-            if (!(s > 0.0)) { *ok_flag = 0; s = 1.0; }
-            X[j * LD + j] = sqrt(s);
+        {   // diagonal: X[j][j] - sum_k L[j][k]^2 with the products spread over the lanes (fixed-order shuffle reduction)
+            double part = (lane < j) ? X[j * LD + lane] * X[j * LD + lane] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_sync(0xffffffffu, part, (lane + o) & 31);
+            if (lane == 0) {
+                double s = X[j * LD + j] - part;
+                if (!(s > 0.0)) { *ok_flag = 0; s = 1.0; }
+                X[j * LD + j] = sqrt(s);
+            }
         }
         __syncwarp();
         if (lane > j && lane < N) {
@@ -168,19 +171,41 @@ CERB_GLOBAL void imu_leg_eval_kernel(int n, const double *pre_all, const double 
 // meta[0] = valid, meta[1] = n, meta[2] = num_blocks, meta[4+3b..] = (kind, index, col), x0 [16][7].
 enum { PRIOR_META_STRIDE = 64, PRIOR_LD = 96 };
 
-// Hp (row-major [n][n], leading dim PRIOR_LD) = J0^T J0.  grid = n_windows, block = 256.
+// Hp (row-major [n][n], leading dim PRIOR_LD) = J0^T J0.
+// J0 (n x n, column-major) is staged once into shared memory as tile[k][a] (row stride PRIOR_TLD, zero padded to multiples of 8),
+// then the upper 8 x 8 blocks of the Gram matrix are contracted on the fp64 tensor cores and mirrored on the way out.
+// grid = n_windows, block = 256, dynamic shared memory = PRIOR_TROWS * PRIOR_TLD doubles.
+enum { PRIOR_TLD = 108, PRIOR_TROWS = 96 };                  // 108 = 12 (mod 16): conflict-free fragment loads
 CERB_GLOBAL void prior_prepare_kernel(const double *J_all, const int *meta_all, double *Hp_all) {
-    const int w = blockIdx.x;
+    CERB_DYN_SMEM(double, tile);
+    const int w = blockIdx.x, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int *meta = meta_all + (size_t)w * PRIOR_META_STRIDE;
     const int n = meta[0] ? meta[1] : 0;
+    if (n == 0) return;
     const double *J = J_all + (size_t)w * PRIOR_LD * PRIOR_LD;
     double *Hp = Hp_all + (size_t)w * PRIOR_LD * PRIOR_LD;
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-        const int a = idx / n, b = idx % n;
-        if (b < a) continue;
-        double s = 0.0;
-        for (int k = 0; k < n; k++) s += J[(size_t)a * n + k] * J[(size_t)b * n + k];
-        Hp[a * PRIOR_LD + b] = s; Hp[b * PRIOR_LD + a] = s;
+    const int nb = (n + 7) >> 3, np = 8 * nb;                 // blocks per side, padded size
+    for (int e = tid; e < np * PRIOR_TLD; e += blockDim.x) tile[e] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < n * n; e += blockDim.x) { const int a = e / n, k = e % n; tile[k * PRIOR_TLD + a] = J[e]; }      // J[a * n + k]: column a, row k
+    __syncthreads();
+    const int nblk = nb * (nb + 1) / 2;
+    for (int b = wid; b < nblk; b += (int)(blockDim.x >> 5)) {
+        int mi = 0, idx = b;
+        while (idx >= nb - mi) { idx -= nb - mi; mi++; }
+        const int ni = mi + idx;
+        double a0 = 0.0, a1 = 0.0;
+        for (int ks = 0; ks < 2 * nb; ks++) {
+            const double av = tile[(4 * ks + (lane & 3)) * PRIOR_TLD + 8 * mi + (lane >> 2)];
+            const double bv = tile[(4 * ks + (lane & 3)) * PRIOR_TLD + 8 * ni + (lane >> 2)];
+            CERB_DMMA(a0, a1, av, bv, a0, a1);
+        }
+        const int ra = 8 * mi + (lane >> 2);
+        for (int e = 0; e < 2; e++) {
+            const int rb = 8 * ni + 2 * (lane & 3) + e;
+            const double v = e ? a1 : a0;
+            if (ra < n && rb < n && ra <= rb) { Hp[ra * PRIOR_LD + rb] = v; Hp[rb * PRIOR_LD + ra] = v; }
+        }
     }
 }
 
