@@ -213,6 +213,22 @@ CERB_D void vis_scatter(Smem &s, int ga, int gb, int ra, int rb, int a, int j, d
     if (db == -2) { s.g[da] += v; return; }
     if (da <= db) s.Hxx[da * NX + db] += v; else s.Hxx[db * NX + da] += v;
 }
+// Destination of entry el = (blk, ra, rb) of the frame-dependent blocks (g0,g1), (g1,g1), (g1,g2), (g1,g3) as an affine function of the
+// anchor a and the frame j: offset = base + ca * a + cj * j doubles from the start of shared memory (base < 0: no destination).
+CERB_D void vis_jplan(const Smem &s, const double *smem_base, int el, int *base, int *ca, int *cj) {
+    const int blk = el >> 6, ra = (el >> 3) & 7, rb = el & 7;
+    const int hxx = (int)(s.Hxx - smem_base), g = (int)(s.g - smem_base);
+    *base = -1; *ca = 0; *cj = 0;
+    if (rb >= 6) return;                                                // padding columns of g1 / g2 / g3
+    if (blk == 0) {                                                     // rows: pose_a (0..5), td (6), residual (7); columns: pose_j
+        if (ra < 6) { *base = hxx + ra * NX + rb; *ca = 6 * NX; *cj = 6; }
+        else if (ra == 6) { *base = hxx + rb * NX + X_TD; *cj = 6 * NX; }          // H(pose_j, td), stored in the upper triangle
+        else { *base = g + rb; *cj = 6; }                                           // gradient of pose_j
+    } else {
+        if (ra >= 6 || (blk == 1 && ra > rb)) return;
+        *base = hxx + ra * NX + (blk == 1 ? rb : (blk == 2 ? 66 + rb : 72 + rb)); *cj = 6 * NX + (blk == 1 ? 6 : 0);
+    }
+}
 CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double *x, const double *lam, double *W, double *hh, double *gl,
                                       const double *sl, bool prescale, const int *chunks, int tid) {
     CERB_DYN_SMEM(double, smem_base);
@@ -234,6 +250,8 @@ CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double 
     const double *tq[4];
     bool tv[4];
     for (int g = 0; g < 4; g++) { const int pc = g == 0 ? c8 : 8 + 6 * (g - 1) + c8; tv[g] = (g == 0) || c8 < 6; tq[g] = T + (tv[g] ? pc : 0) * VT_LD + (lane & 3); }
+    int jbase, jca, jcj;                                                // scatter plan of this thread's entry of the frame-dependent blocks
+    vis_jplan(s, smem_base, tid, &jbase, &jca, &jcj);
     const int nchunks = chunks[0];
     for (int ch = 0; ch < nchunks; ch++) {
         const int c0 = chunks[1 + ch], nc = chunks[2 + ch] - c0;
@@ -431,13 +449,15 @@ CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double 
             __syncthreads();
             PH_MARK(22);
             // --- frame-dependent blocks: sum over the four warps of each frame (fixed order) and scatter ----------------------------
-            for (int e = tid; e < 2 * VJ_SZ; e += SOLVE_THREADS) {
-                const int fj = e >> 8, el = e & 255, blk = el >> 6, ra = (el >> 3) & 7, rb = el & 7;
-                const int jf = j0 + fj;
-                if (jf >= NFR || jf == a) continue;
-                const double *q = jp + (4 * fj) * VJ_SZ + el;             // warps 4 fj .. 4 fj + 3 hold the partial blocks of frame j0 + fj
-                const double v = ((q[0] + q[VJ_SZ]) + q[2 * VJ_SZ]) + q[3 * VJ_SZ];
-                vis_scatter(s, blk == 0 ? 0 : 1, blk == 0 ? 1 : blk, ra, rb, a, jf, v);
+            // (thread tid owns entry el = tid of both frames; its destination is affine in (a, j): vis_jplan)
+            if (jbase >= 0) {
+                _Pragma("unroll")
+                for (int fj = 0; fj < 2; fj++) {
+                    const int jf = j0 + fj;
+                    if (jf >= NFR || jf == a) continue;
+                    const double *q = jp + (4 * fj) * VJ_SZ + tid;        // warps 4 fj .. 4 fj + 3 hold the partial blocks of frame j0 + fj
+                    smem_base[jbase + jca * a + jcj * jf] += ((q[0] + q[VJ_SZ]) + q[2 * VJ_SZ]) + q[3 * VJ_SZ];
+                }
             }
             PH_MARK(23);
         }
