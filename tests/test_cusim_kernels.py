@@ -197,3 +197,22 @@ def _rejected_steps_case(backend_factory, nw=6, iters=12):
 
 def test_rejected_steps_match_oracle():
     _rejected_steps_case(sim_backend, nw=3, iters=9)          # (the GPU tier runs the 6-window / 12-iteration case)
+
+
+def test_skipped_imu_factor():
+    """estimator.cpp:1119: an IMU-leg factor whose sum_dt exceeds 10 s is not added; the frames it would couple are then tied
+    together by the visual factors and the prior only."""
+    cfg = small_cfg(max_batch=2, max_features=16, iters=3)
+    o, s = OracleBackend(cfg), sim_backend(cfg)
+    batch = synth.generate_batch(2, 12, o, window0=31, prior_features=6)
+    batch.preint[0][3]["sum_dt"] = 10.5          # window 0: factor 3 skipped
+    batch.preint[1][0]["sum_dt"] = 12.0          # window 1: factors 0 and 9 skipped
+    batch.preint[1][9]["sum_dt"] = 11.0
+    st = batch.state_array(); saved = batch.copy_states()
+    rep_o = o.solve_batch(batch); ref = st.copy(); lam = batch.para_Feature.copy()
+    batch.restore_states(saved)
+    rep_s = s.solve_batch(batch)
+    assert (rep_o["iterations"] == rep_s["iterations"]).all()
+    assert np.abs(rep_o["final_cost"] - rep_s["final_cost"]).max() < 1e-7 * rep_o["final_cost"].max()
+    d = state_diffs(batch.state_array(), ref)
+    assert d["para_Pose"] < 1e-7 and d["para_SpeedBias"] < 1e-5 and np.abs(batch.para_Feature - lam).max() < 1e-7, d
