@@ -1089,8 +1089,13 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                                 if (lane == j) myinv = inv;
                                 const double l = (lane == j) ? d * inv : a[j] * inv;
                                 a[j] = l;
+                                // column j of L to all lanes through a double-buffered shared-memory line (1 store + 12 broadcast loads
+                                // instead of 12 two-instruction shuffles: the sweep is bound by the instruction issue of this one warp)
+                                double *colb = s.sca + 32 + 16 * (j & 1);
+                                if (act) colb[lane] = l;
+                                __syncwarp();
                                 _Pragma("unroll")
-                                for (int k = j + 1; k < NYB; k++) { const double lk = __shfl_sync(0xffffffffu, l, k); a[k] -= l * lk; }
+                                for (int k = j + 1; k < NYB; k++) a[k] -= l * colb[k];
                             }
                             if (act) { _Pragma("unroll") for (int c = 0; c < NYB; c++) if (c <= r) A[r * NYB + c] = a[c]; s.idg[NYB * f + r] = myinv; }
                             __syncwarp();
@@ -1250,41 +1255,65 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                     }
                     __syncthreads();
                     PH_MARK(9);
-                    // ---- dense Cholesky of the 79 x 79 lower triangle, rhs carried as row 79 (z = L^-1 rhs), blocked by panels of 8:
-                    // (a) warp 0 factors the diagonal block in registers (pivots / column entries exchanged by shuffles),
-                    // (b) one thread per row below solves its 8 panel entries against L_kk, (c) the trailing lower triangle
-                    // is updated block by block on the fp64 tensor cores (A_ij -= L_ik L_jk^T, K = 8).
+                    // ---- dense Cholesky of the 79 x 79 lower triangle, rhs carried as row 79 (z = L^-1 rhs), blocked by panels of 8,
+                    // with look-ahead: (a) warp 0 factors a diagonal block in registers (pivots / column entries exchanged by shuffles),
+                    // (b) one thread per row below solves its 8 panel entries against L_kk, (c) the trailing lower triangle is updated
+                    // block by block on the fp64 tensor cores (A_ij -= L_ik L_jk^T, K = 8) -- warp 0 takes only the block that becomes
+                    // the next diagonal block and factors it right away, while warps 1..7 update the rest.  Two barriers per panel; the
+                    // serial column sweeps of the diagonal blocks (the critical path) overlap with the trailing updates.
                     {
                         const int wq = tid >> 5, lane = tid & 31;
-                        double *Lkk = s.red;                           // 8 x 8 factored diagonal block (+ its inverse diagonal at [64..72))
-                        for (int c0 = 0; c0 < NX; c0 += 8) {
-                            const int nb = (NX - c0) < 8 ? (NX - c0) : 8, c1 = c0 + nb;
-                            if (wq == 0) {
-                                const bool act = lane < nb;
-                                const int r = act ? lane : 0;
-                                double a[8];
+                        auto factor_diag = [&](int c0, int nb, double *Lkk) {      // warp 0: L_kk of the nb x nb block at (c0, c0); Lkk[64..72) = 1 / diag
+                            const bool act = lane < nb;
+                            const int r = act ? lane : 0;
+                            double a[8];
+                            _Pragma("unroll")
+                            for (int c = 0; c < 8; c++) a[c] = (c < nb && c <= r) ? s.Hxx[(c0 + r) * NX + c0 + c] : 0.0;
+                            double myinv = 1.0;
+                            _Pragma("unroll")
+                            for (int j = 0; j < 8; j++) {
+                                double d = __shfl_sync(0xffffffffu, a[j], j);
+                                if (j < nb && !(d > 0.0)) { if (lane == 0) sca[S_OK] = 0; }
+                                if (!(d > 0.0)) d = 1.0;
+                                const double inv = rsqrt(d);
+                                if (lane == j) myinv = inv;
+                                const double l = (lane == j) ? d * inv : a[j] * inv;
+                                a[j] = l;
                                 _Pragma("unroll")
-                                for (int c = 0; c < 8; c++) a[c] = (c < nb && c <= r) ? s.Hxx[(c0 + r) * NX + c0 + c] : 0.0;
-                                double myinv = 1.0;
-                                _Pragma("unroll")
-                                for (int j = 0; j < 8; j++) {
-                                    double d = __shfl_sync(0xffffffffu, a[j], j);
-                                    if (j < nb && !(d > 0.0)) { if (lane == 0) sca[S_OK] = 0; }
-                                    if (!(d > 0.0)) d = 1.0;
-                                    const double inv = rsqrt(d);
-                                    if (lane == j) myinv = inv;
-                                    const double l = (lane == j) ? d * inv : a[j] * inv;
-                                    a[j] = l;
-                                    _Pragma("unroll")
-                                    for (int k = j + 1; k < 8; k++) { const double lk = __shfl_sync(0xffffffffu, l, k); a[k] -= l * lk; }
-                                }
-                                if (act) {
-                                    _Pragma("unroll")
-                                    for (int c = 0; c < 8; c++) if (c <= r) { s.Hxx[(c0 + r) * NX + c0 + c] = a[c]; Lkk[r * 8 + c] = a[c]; }
-                                    Lkk[64 + r] = myinv; s.idx[c0 + r] = myinv;
-                                }
+                                for (int k = j + 1; k < 8; k++) { const double lk = __shfl_sync(0xffffffffu, l, k); a[k] -= l * lk; }
                             }
-                            __syncthreads();
+                            if (act) {
+                                _Pragma("unroll")
+                                for (int c = 0; c < 8; c++) if (c <= r) { s.Hxx[(c0 + r) * NX + c0 + c] = a[c]; Lkk[r * 8 + c] = a[c]; }
+                                Lkk[64 + r] = myinv; s.idx[c0 + r] = myinv;
+                            }
+                        };
+                        auto trailing_block = [&](int c0, int b0, int b) {          // block b = (bi, bj), bj <= bi, of the rows / columns from 8 b0 on
+                            int bi = 0, idx = b;
+                            while (idx > bi) { idx -= bi + 1; bi++; }
+                            const int ri = 8 * (b0 + bi) + (lane >> 2), rj = 8 * (b0 + idx) + (lane >> 2);
+                            double a0 = 0.0, a1 = 0.0;
+                            for (int ks = 0; ks < 2; ks++) {
+                                const int cc = c0 + 4 * ks + (lane & 3);
+                                const double av = (ri < NX) ? s.Hxx[ri * NX + cc] : (ri == NX ? s.yv[cc] : 0.0);
+                                const double bv = (rj < NX) ? s.Hxx[rj * NX + cc] : 0.0;
+                                CERB_DMMA(a0, a1, av, bv, a0, a1);
+                            }
+                            const int cj = 8 * (b0 + idx) + 2 * (lane & 3);
+                            if (ri < NX) {
+                                if (cj <= ri && cj < NX) s.Hxx[ri * NX + cj] -= a0;
+                                if (cj + 1 <= ri && cj + 1 < NX) s.Hxx[ri * NX + cj + 1] -= a1;
+                            } else if (ri == NX) {
+                                if (cj < NX) s.yv[cj] -= a0;
+                                if (cj + 1 < NX) s.yv[cj + 1] -= a1;
+                            }
+                        };
+                        if (wq == 0) factor_diag(0, 8, s.red);
+                        __syncthreads();
+                        int pk = 0;
+                        for (int c0 = 0; c0 < NX; c0 += 8, pk ^= 1) {
+                            const int nb = (NX - c0) < 8 ? (NX - c0) : 8, c1 = c0 + nb;
+                            const double *Lkk = s.red + 80 * pk;            // factored diagonal block of this panel (+ inverse diagonal at [64..72))
                             // (b) rows c1 .. NX (row NX = rhs, kept in yv)
                             if (tid <= NX - c1) {
                                 const int i = c1 + tid;
@@ -1305,29 +1334,16 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                             }
                             __syncthreads();
                             if (c1 >= NX) break;
-                            // (c) trailing update; 8 x 8 blocks (bi >= bj) of rows / columns c1 .. NX, row NX = rhs
+                            // (c) trailing update of rows / columns c1 .. NX (row NX = rhs) + look-ahead factorisation of the next diagonal block
                             {
                                 const int b0 = c1 >> 3, nbt = 10 - b0;               // block rows b0 .. 9
                                 const int nblk = nbt * (nbt + 1) / 2;
-                                for (int b = wq; b < nblk; b += 8) {
-                                    int bi = 0, idx = b;
-                                    while (idx > bi) { idx -= bi + 1; bi++; }          // b -> (bi, bj) with bj <= bi (relative)
-                                    const int ri = 8 * (b0 + bi) + (lane >> 2), rj = 8 * (b0 + idx) + (lane >> 2);
-                                    double a0 = 0.0, a1 = 0.0;
-                                    for (int ks = 0; ks < 2; ks++) {
-                                        const int cc = c0 + 4 * ks + (lane & 3);
-                                        const double av = (ri < NX) ? s.Hxx[ri * NX + cc] : (ri == NX ? s.yv[cc] : 0.0);
-                                        const double bv = (rj < NX) ? s.Hxx[rj * NX + cc] : 0.0;
-                                        CERB_DMMA(a0, a1, av, bv, a0, a1);
-                                    }
-                                    const int cj = 8 * (b0 + idx) + 2 * (lane & 3);
-                                    if (ri < NX) {
-                                        if (cj <= ri && cj < NX) s.Hxx[ri * NX + cj] -= a0;
-                                        if (cj + 1 <= ri && cj + 1 < NX) s.Hxx[ri * NX + cj + 1] -= a1;
-                                    } else if (ri == NX) {
-                                        if (cj < NX) s.yv[cj] -= a0;
-                                        if (cj + 1 < NX) s.yv[cj + 1] -= a1;
-                                    }
+                                if (wq == 0) {
+                                    trailing_block(c0, b0, 0);
+                                    __syncwarp();
+                                    factor_diag(c1, (NX - c1) < 8 ? (NX - c1) : 8, s.red + 80 * (pk ^ 1));
+                                } else {
+                                    for (int b = wq; b < nblk; b += 7) trailing_block(c0, b0, b);
                                 }
                             }
                             __syncthreads();
