@@ -252,10 +252,11 @@ CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double 
     for (int g = 0; g < 4; g++) { const int pc = g == 0 ? c8 : 8 + 6 * (g - 1) + c8; tv[g] = (g == 0) || c8 < 6; tq[g] = T + (tv[g] ? pc : 0) * VT_LD + (lane & 3); }
     int jbase, jca, jcj;                                                // scatter plan of this thread's entry of the frame-dependent blocks
     vis_jplan(s, smem_base, tid, &jbase, &jca, &jcj);
-    const int nchunks = chunks[0];
+    const int nchunks = s.ti[96];
     for (int ch = 0; ch < nchunks; ch++) {
-        const int c0 = chunks[1 + ch], nc = chunks[2 + ch] - c0;
-        const int a = P.feat_start[(size_t)w * F + c0];
+        int c0, nc, a;                                                  // chunk table: shared-memory cache (no dependent L2 round trips), else global
+        if (ch < 15) { c0 = s.ti[97 + 2 * ch]; nc = s.ti[98 + 2 * ch] >> 8; a = s.ti[98 + 2 * ch] & 255; }
+        else { c0 = chunks[1 + ch]; nc = chunks[2 + ch] - c0; a = P.feat_start[(size_t)w * F + c0]; }
         const int f = c0 + fl;
         const bool ev = fl < nc;
         int nobs = 0, off = 0;
@@ -266,6 +267,9 @@ CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double 
             lamf = 1.0 / lam[f];                                          // inverse of the inverse depth, used by every factor of the track
             pix = obs[0 * mo + off]; piy = obs[1 * mo + off]; vix = obs[2 * mo + off]; viy = obs[3 * mo + off]; tdi = obs[8 * mo + off];
         }
+        // first observation of this thread, issued with the loads above (the shared-memory stores below would otherwise order it after them)
+        ObsVals ov; ov.px = ov.py = ov.vx = ov.vy = ov.td = 0.0; ov.stereo = 0;
+        { const int j = a + jj; if (ev && j < a + nobs) obs_fetch(obs, stereo, mo, off + (j - a), cam, ov); }
         for (int k = lane; k < VP_SZ; k += 32) pp[k] = 0.0;
         // rotation products shared by all factors of (anchor a, frame j, camera c): A = Rc^T Rj^T, A Ri, T = A Ri ric (27 doubles per
         // (j, c) in s.lin, which is idle until the inertial pass); slot 20: T3 = ric2^T ric of the anchor-frame stereo factor (K3)
@@ -284,8 +288,6 @@ CERB_NOINLINE double vision_linearize(const SolveParams &P, int w, const double 
         __syncthreads();
         double h = 0.0, gq = 0.0, wT = 0.0, wI[6], wE0[6], wE1[6];
         for (int k = 0; k < 6; k++) { wI[k] = 0.0; wE0[k] = 0.0; wE1[k] = 0.0; }
-        ObsVals ov; ov.px = ov.py = ov.vx = ov.vy = ov.td = 0.0; ov.stereo = 0;
-        { const int j = a + jj; if (ev && j < a + nobs) obs_fetch(obs, stereo, mo, off + (j - a), cam, ov); }
         PH_MARK(20);
         for (int j0 = a; j0 < NFR; j0 += 2) {
             const int j = j0 + jj;
@@ -888,13 +890,14 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
         if (tid == 0) {      // feature chunks: <= 64 consecutive tracks with the same anchor frame
             int n = 0, c0 = 0;
             while (c0 < nF) {
-                chunks[1 + n++] = c0;
+                chunks[1 + n] = c0;
                 const int a = P.feat_start[(size_t)w * F + c0];
                 int e = c0 + 1;
                 while (e < nF && e < c0 + 64 && P.feat_start[(size_t)w * F + e] == a) e++;
-                c0 = e;
+                if (n < 15) { s.ti[97 + 2 * n] = c0; s.ti[98 + 2 * n] = ((e - c0) << 8) | a; }      // the first 15 chunks are also cached in shared memory
+                n++; c0 = e;
             }
-            chunks[1 + n] = nF; chunks[0] = n;
+            chunks[1 + n] = nF; chunks[0] = n; s.ti[96] = n;
         }
         // prior Hessian image (J0^T J0 scattered into the layout of Hxx | Hxy | Ad | Bo): constant during the solve, every
         // linearisation starts from it instead of from zero.  s.ti keeps the column -> destination map of the prior.
