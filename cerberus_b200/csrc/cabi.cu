@@ -636,6 +636,30 @@ static int feature_pass(CerbHandle *h, int which, double param, double *out, int
 }
 int cerb_batch_outlier_errors(CerbHandle *h, double focal_length, double *ave_err, int32_t *remove) { return feature_pass(h, 0, focal_length, ave_err, remove); }
 int cerb_batch_triangulate(CerbHandle *h, double init_depth, double *depth) { return feature_pass(h, 1, init_depth, depth, nullptr); }
+int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_frame, double *depth, int32_t *keep) {
+    if (!h || !new_start_frame || !depth || !keep) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    if (h->n < 1) return fail(CERB_ERR_BAD_ARGUMENT, "no resident batch");
+    const int n = h->n, F = h->F;
+    const size_t N = (size_t)n * F;
+    cudaStream_t s = h->stream; DevBuf B;
+    double *d_out = B.up(nullptr, 3 * N, s);
+    if (!d_out) return fail(CERB_ERR_CUDA, "device allocation failed");
+    const double *d_st = h->solved ? h->d_state : h->d_state0, *d_lm = h->solved ? h->d_lam : h->d_lam0;
+    CERB_LAUNCH(shift_depth_kernel, (int)((N + 127) / 128), 128, 0, s, n, F, h->O, (const int *)h->d_nfeat, (const int *)h->d_fstart, (const int *)h->d_fnobs, (const int *)h->d_foff,
+                (const double *)h->d_obs, d_st, d_lm, init_depth, d_out);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> tmp(3 * N);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int w = 0; w < n; w++) {
+        const int *perm = h->h_perm.data() + (size_t)w * F;
+        for (int k = 0; k < h->h_nfeat[w]; k++) {
+            const size_t src = (size_t)w * F + k, dst = (size_t)w * F + perm[k];
+            new_start_frame[dst] = (int32_t)tmp[src]; depth[dst] = tmp[N + src]; keep[dst] = (int32_t)tmp[2 * N + src];
+        }
+    }
+    return CERB_OK;
+}
 
 // ---- leg-contact preintegration ------------------------------------------------------------------------------------
 static int preintegrate_impl(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n, const CerbPreintJob *jobs, CerbIMULegPreint *out, CerbIMUPreint *out_imu) {

@@ -2,6 +2,7 @@
 // windows: one thread per (window, feature), streaming the observation planes (HBM / L2 bound, 0.5 KB per feature).
 //   outlier_error_kernel   Estimator::outliersRejection + reprojectionError   src/estimator/estimator.cpp:1729-1798
 //   triangulate_kernel     FeatureManager::triangulate + triangulatePoint      src/featureTracker/feature_manager.cpp:198-212,302-385
+//   shift_depth_kernel     FeatureManager::removeBackShiftDepth (MARGIN_OLD slide)  src/featureTracker/feature_manager.cpp:450-488, estimator.cpp:1660-1677
 #pragma once
 #include "eval_kernels.cuh"
 
@@ -116,6 +117,34 @@ CERB_GLOBAL void triangulate_kernel(int n_windows, int maxF, int maxObs, const i
         } else out = l;                                                           // left untouched by the reference
     }
     depth[(size_t)w * maxF + f] = out;
+}
+
+// Depth bookkeeping of slideWindowOld(): the oldest frame leaves the window.  Tracks anchored later just move one frame down
+// (start_frame - 1, depth unchanged); tracks anchored at frame 0 lose their first observation, are erased if fewer than 2 remain
+// (keep = 0), else their depth is re-expressed in camera 0 of the new anchor (old frame 1): dep_j = (R1^T (R0 (uv_i depth) + P0 - P1)).z
+// with R0 = Rs[0] ric0, P0 = Ps[0] + Rs[0] tic0, R1 = Rs[1] ric0, P1 = Ps[1] + Rs[1] tic0; dep_j <= 0 becomes init_depth.
+// out [3][n_windows * maxF]: new start_frame, new estimated_depth, keep flag.
+CERB_GLOBAL void shift_depth_kernel(int n_windows, int maxF, int maxObs, const int *n_features, const int *feat_start, const int *feat_nobs,
+                                    const int *feat_off, const double *obs, const double *state, const double *lam, double init_depth, double *out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = idx / maxF, f = idx % maxF;
+    if (w >= n_windows || f >= n_features[w]) return;
+    const size_t N = (size_t)n_windows * maxF, k = (size_t)w * maxF + f;
+    const int start = feat_start[k], nobs = feat_nobs[k], off = feat_off[k];
+    const double depth = 1.0 / lam[k];
+    if (start != 0) { out[k] = (double)(start - 1); out[N + k] = depth; out[2 * N + k] = 1.0; return; }
+    out[k] = 0.0;
+    if (nobs - 1 < 2) { out[N + k] = depth; out[2 * N + k] = 0.0; return; }
+    const double *x = state + (size_t)w * ST_STRIDE;
+    const double *ob = obs + (size_t)w * 9 * maxObs;
+    const m33 Rs0 = qtoR(ldq(x + ST_POSE + 3)), Rs1 = qtoR(ldq(x + ST_POSE + 7 + 3)), ric0 = qtoR(ldq(x + ST_EX + 3));
+    const d3 Ps0 = ld3(x + ST_POSE), Ps1 = ld3(x + ST_POSE + 7), tic0 = ld3(x + ST_EX);
+    const m33 R0 = mul33(Rs0, ric0), R1 = mul33(Rs1, ric0);
+    const d3 P0 = Ps0 + mv33(Rs0, tic0), P1 = Ps1 + mv33(Rs1, tic0);
+    const d3 pts_i = depth * mk3(ob[0 * maxObs + off], ob[1 * maxObs + off], 1.0);
+    const d3 pts_j = mTv33(R1, (mv33(R0, pts_i) + P0) - P1);
+    out[N + k] = pts_j.z > 0.0 ? pts_j.z : init_depth;
+    out[2 * N + k] = 1.0;
 }
 
 }  // namespace cerb

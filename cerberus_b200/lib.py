@@ -59,6 +59,7 @@ class Backend:
         L.cerb_double2vector.argtypes = [C.POINTER(abi.WindowState), C.POINTER(abi.WindowState), abi.c_dp, abi.c_dp, abi.c_dp]
         L.cerb_batch_outlier_errors.argtypes = [C.c_void_p, C.c_double, abi.c_dp, C.POINTER(C.c_int32)]
         L.cerb_batch_triangulate.argtypes = [C.c_void_p, C.c_double, abi.c_dp]
+        L.cerb_batch_shift_depth.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_int32), abi.c_dp, C.POINTER(C.c_int32)]
         L.cerb_double2vector.restype = None
         self.cfg = cfg or abi.default_config()
         self.h = C.c_void_p()
@@ -173,6 +174,13 @@ class Backend:
         err = np.full((n, F), np.nan); rem = np.zeros((n, F), dtype=np.int32)
         self._check(self.lib.cerb_batch_outlier_errors(self.h, focal_length, _p(err), rem.ctypes.data_as(C.POINTER(C.c_int32))))
         return err, rem
+
+    def shift_depth(self, n, init_depth=5.0):
+        """FeatureManager::removeBackShiftDepth on the resident batch: (new start_frame, new depth, keep flag), each [n][max_features]."""
+        F = self.cfg.max_features
+        start = np.full((n, F), -1, dtype=np.int32); depth = np.full((n, F), np.nan); keep = np.full((n, F), -1, dtype=np.int32)
+        self._check(self.lib.cerb_batch_shift_depth(self.h, init_depth, start.ctypes.data_as(C.POINTER(C.c_int32)), _p(depth), keep.ctypes.data_as(C.POINTER(C.c_int32))))
+        return start, depth, keep
 
     def triangulate(self, n, init_depth=5.0):
         """FeatureManager::triangulate on the resident batch: estimated_depth [n][max_features]."""

@@ -352,6 +352,12 @@ int cerb_batch_outlier_errors(CerbHandle *h, double focal_length, double *ave_er
  * becomes init_depth (INIT_DEPTH = 5.0, parameters.cpp:250).  Features that already have a depth return 1 / para_Feature. */
 int cerb_batch_triangulate(CerbHandle *h, double init_depth, double *depth);
 
+/* FeatureManager::removeBackShiftDepth as called by Estimator::slideWindowOld (feature_manager.cpp:450-488, estimator.cpp:1660-1677)
+ * when the oldest frame is marginalized: for every feature of the resident batch at its current state, the start_frame after the
+ * slide, the estimated_depth after the slide (tracks anchored at frame 0 are re-anchored at the old frame 1; a non-positive depth
+ * becomes init_depth) and keep = 0 for the tracks the reference erases (anchored at frame 0 with fewer than 2 remaining observations). */
+int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_frame, double *depth, int32_t *keep);
+
 /* ---- host-side helpers that stay on the CPU in the reference too ---------------------------- */
 /* Gauge re-anchoring of Estimator::double2vector (estimator.cpp:903-957): rotates the solved
  * window by the yaw difference of frame 0 and re-anchors its position.  before/after are the

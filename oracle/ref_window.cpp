@@ -643,6 +643,31 @@ int oracle_triangulate(const CerbWindowDesc *d, const CerbWindowState *st, doubl
     return 0;
 }
 
+// FeatureManager::removeBackShiftDepth via Estimator::slideWindowOld, feature_manager.cpp:450-488 + estimator.cpp:1660-1677
+int oracle_shift_depth(const CerbWindowDesc *d, const CerbWindowState *st, double init_depth, int *new_start, double *depth, int *keep) {
+    auto quat_of = [](const double *p) { return Quat(p[6], p[3], p[4], p[5]); };
+    M3 ric0 = toR(quat_of(st->para_Ex_Pose[0])); V3 tic0(st->para_Ex_Pose[0]);
+    M3 back_R0 = toR(quat_of(st->para_Pose[0])), Rs0 = toR(quat_of(st->para_Pose[1]));      // Rs[0] after the slide is the old frame 1
+    V3 back_P0(st->para_Pose[0]), Ps0(st->para_Pose[1]);
+    M3 R0 = back_R0 * ric0, R1 = Rs0 * ric0;
+    V3 P0 = back_P0 + back_R0 * tic0, P1 = Ps0 + Rs0 * tic0;
+    for (int f = 0; f < d->n_features; f++) {
+        const CerbFeature &ft = d->features[f];
+        double est = 1.0 / st->para_Feature[f];
+        keep[f] = 1; depth[f] = est;
+        if (ft.start_frame != 0) { new_start[f] = ft.start_frame - 1; continue; }
+        new_start[f] = 0;
+        if (ft.n_obs - 1 < 2) { keep[f] = 0; continue; }
+        const CerbObservation &o0 = d->obs[ft.obs_offset];
+        V3 uv_i(o0.point[0], o0.point[1], 1.0);
+        V3 pts_i = uv_i * est;
+        V3 w_pts_i = R0 * pts_i + P0;
+        V3 pts_j = transpose(R1) * (w_pts_i - P1);
+        depth[f] = pts_j.z > 0 ? pts_j.z : init_depth;
+    }
+    return 0;
+}
+
 int oracle_abi_sizes(int *out, int n) {   // struct-size handshake for the ctypes mirror
     int v[] = {(int)sizeof(CerbSolverConfig), (int)sizeof(CerbIMULegPreint), (int)sizeof(CerbObservation), (int)sizeof(CerbFeature), (int)sizeof(CerbPrior),
                (int)sizeof(CerbWindowDesc), (int)sizeof(CerbWindowState), (int)sizeof(CerbSolveReport), (int)sizeof(CerbIMULegSample), (int)sizeof(CerbPreintConfig), (int)sizeof(CerbPreintJob), (int)sizeof(CerbIMUPreint)};

@@ -132,6 +132,15 @@ class OracleBackend:
             assert self.lib.oracle_outlier_errors(C.byref(batch.descs[w]), C.byref(batch.states[w]), _p(out[w])) == 0
         return out
 
+    def shift_depth(self, batch, init_depth=5.0):
+        n, F = batch.n, batch.max_features
+        start = np.full((n, F), -1, dtype=np.int32); depth = np.full((n, F), np.nan); keep = np.full((n, F), -1, dtype=np.int32)
+        self.lib.oracle_shift_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_int32), abi.c_dp, C.POINTER(C.c_int32)]
+        for w in range(n):
+            assert self.lib.oracle_shift_depth(C.byref(batch.descs[w]), C.byref(batch.states[w]), init_depth, start[w].ctypes.data_as(C.POINTER(C.c_int32)),
+                                               _p(depth[w]), keep[w].ctypes.data_as(C.POINTER(C.c_int32))) == 0
+        return start, depth, keep
+
     def triangulate(self, batch, init_depth=5.0):
         out = np.full((batch.n, batch.max_features), np.nan)
         self.lib.oracle_triangulate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, abi.c_dp]

@@ -11,6 +11,9 @@ from helpers import sim_backend, small_cfg
 
 def _batch(backend, realistic, n=2, F=24):
     batch = synth.generate_batch(n, F, backend, realistic=realistic, window0=77, prior_features=8)
+    for w in range(n):                                           # one two-frame track anchored at frame 0 per window: removeBackShiftDepth erases it
+        f = next(f for f in range(batch.descs[w].n_features) if batch.descs[w].features[f].start_frame == 0)
+        batch.descs[w].features[f].n_obs = 2
     return batch
 
 
@@ -28,11 +31,22 @@ def _check_backend(be, oracle, realistic):
         if phase == 0:
             be.solve_resident(); be.download(batch)           # batch.states now hold the solved states, like the device
     assert np.nanmax(err) * 460.0 < 3.0                           # solved synthetic windows have no outliers
+    # (1b) depth bookkeeping of slideWindowOld at the solved states
+    st_o, dep_o, keep_o = oracle.shift_depth(batch)
+    st_g, dep_g, keep_g = be.shift_depth(batch.n)
+    for w in range(batch.n):
+        assert (st_g[w, :nf[w]] == st_o[w, :nf[w]]).all() and (keep_g[w, :nf[w]] == keep_o[w, :nf[w]]).all()
+        assert np.abs(dep_g[w, :nf[w]] - dep_o[w, :nf[w]]).max() < 1e-12 * np.abs(dep_o[w, :nf[w]]).max()
+        assert (dep_g[w, :nf[w]] > 0).all() and (keep_o[w, :nf[w]] == 0).sum() == 1 and (st_o[w, :nf[w]] >= 0).all()
     # (2) triangulation: mark every second feature as not triangulated (estimated_depth = -1 -> para_Feature = -1)
     true_depth = 1.0 / batch.para_Feature.copy()
     for w in range(batch.n):
         batch.para_Feature[w, 0:nf[w]:2] = -1.0
     be.upload(batch)
+    st_o, dep_o, keep_o = oracle.shift_depth(batch, 7.5); st_g, dep_g, keep_g = be.shift_depth(batch.n, 7.5)    # negative depths -> INIT_DEPTH
+    for w in range(batch.n):
+        assert (dep_g[w, :nf[w]] == dep_o[w, :nf[w]]).all() or np.abs(dep_g[w, :nf[w]] - dep_o[w, :nf[w]]).max() < 1e-12 * 20
+    assert realistic or (dep_o == 7.5).any()
     dep = be.triangulate(batch.n)
     ref = oracle.triangulate(batch)
     for w in range(batch.n):
