@@ -7,6 +7,7 @@
 #include "solve_kernel.cuh"
 #include "preint_kernel.cuh"
 #include "feature_kernels.cuh"
+#include "marg_kernels.cuh"
 #include <string>
 #include <vector>
 #include <thread>
@@ -636,6 +637,25 @@ static int feature_pass(CerbHandle *h, int which, double param, double *out, int
 }
 int cerb_batch_outlier_errors(CerbHandle *h, double focal_length, double *ave_err, int32_t *remove) { return feature_pass(h, 0, focal_length, ave_err, remove); }
 int cerb_batch_triangulate(CerbHandle *h, double init_depth, double *depth) { return feature_pass(h, 1, init_depth, depth, nullptr); }
+int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t n, const double *A, const double *b, double eps,
+                           double *linearized_jacobians, double *linearized_residuals, int32_t *sweeps) {
+    if (!h || !A || !b || !linearized_jacobians || !linearized_residuals) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    if (n_windows < 1 || m < 1 || n < 1 || m > 4096 || n > CERB_MAX_PRIOR_DIM) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_marginalize_schur: bad sizes");
+    const size_t pos = (size_t)m + n, N = n_windows;
+    const int grid = std::min<int>(n_windows, 2 * h->sm_count);
+    cudaStream_t s = h->stream; DevBuf B;
+    double *dA = B.up(A, N * pos * pos, s), *db = B.up(b, N * pos, s), *dws = B.up(nullptr, (size_t)grid * marg_ws_doubles(m, n), s);
+    double *dJ = B.up(nullptr, N * n * n, s), *dr = B.up(nullptr, N * n, s), *dsw = B.up(nullptr, N, s);     // dsw: 2 ints per window
+    if (!dA || !db || !dws || !dJ || !dr || !dsw) return fail(CERB_ERR_CUDA, "device allocation failed");
+    CERB_LAUNCH(marg_schur_kernel, grid, MARG_THREADS, marg_smem_bytes(m, n), s, (int)n_windows, (int)m, (int)n, (const double *)dA, (const double *)db, eps, dws, dJ, dr, (int *)dsw);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(linearized_jacobians, dJ, N * n * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(linearized_residuals, dr, N * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (sweeps) CUDA_TRY(cudaMemcpyAsync(sweeps, dsw, N * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return CERB_OK;
+}
+
 int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_frame, double *depth, int32_t *keep) {
     if (!h || !new_start_frame || !depth || !keep) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
     if (h->n < 1) return fail(CERB_ERR_BAD_ARGUMENT, "no resident batch");

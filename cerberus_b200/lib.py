@@ -59,6 +59,7 @@ class Backend:
         L.cerb_double2vector.argtypes = [C.POINTER(abi.WindowState), C.POINTER(abi.WindowState), abi.c_dp, abi.c_dp, abi.c_dp]
         L.cerb_batch_outlier_errors.argtypes = [C.c_void_p, C.c_double, abi.c_dp, C.POINTER(C.c_int32)]
         L.cerb_batch_triangulate.argtypes = [C.c_void_p, C.c_double, abi.c_dp]
+        L.cerb_marginalize_schur.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, abi.c_dp, abi.c_dp, C.c_double, abi.c_dp, abi.c_dp, C.POINTER(C.c_int32)]
         L.cerb_batch_shift_depth.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_int32), abi.c_dp, C.POINTER(C.c_int32)]
         L.cerb_double2vector.restype = None
         self.cfg = cfg or abi.default_config()
@@ -193,6 +194,16 @@ class Backend:
         out = np.zeros(n, dtype=abi.preint_dtype)
         self._check(self.lib.cerb_preintegrate_batch(self.h, C.byref(pcfg), n, jobs, out.ctypes.data_as(C.POINTER(abi.IMULegPreint))))
         return out
+
+    def marginalize_schur(self, A, b, m, eps=1e-8, return_sweeps=False):
+        """MarginalizationInfo::marginalize() after the A / b assembly (marginalization_factor.cpp:281-305) for a stack of windows:
+        A [B, pos, pos], b [B, pos], dropped coordinates first -> (linearized_jacobians [B, n, n] row k = sqrt(S_k) v_k^T, linearized_residuals [B, n])."""
+        A = np.ascontiguousarray(A, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+        B, pos = b.shape; n = pos - m
+        J = np.zeros((B, n * n)); r = np.zeros((B, n)); sw = np.zeros((B, 2), dtype=np.int32)
+        self._check(self.lib.cerb_marginalize_schur(self.h, B, m, n, _p(A), _p(b), eps, _p(J), _p(r), sw.ctypes.data_as(C.POINTER(C.c_int32))))
+        J = J.reshape(B, n, n).transpose(0, 2, 1)          # column-major on the wire
+        return (J, r, sw) if return_sweeps else (J, r)
 
     def marginalize(self, cfg, src, dst, margin_old=True):
         from . import marginalization

@@ -2,10 +2,12 @@
 src/factor/marginalization_factor.cpp:12-333), host glue over the device factor evaluators.
 
 The factor Jacobians at the solved state (ResidualBlockInfo::Evaluate) come from the sm_100a "kernel per
-factor family" entry points (cerb_eval_projection / cerb_eval_imu_leg / cerb_eval_prior); the loss
-corrector, the A = J^T J assembly, the eps = 1e-8 clamped eigen-Schur complement and the factoring of the
-result into (linearized_jacobians, linearized_residuals) follow marginalization_factor.cpp:46-77,183-305
-in numpy.  Moving this glue onto the device is the "next #1" row of SURVEY.md section 8(f).
+factor family" entry points (cerb_eval_projection / cerb_eval_imu_leg / cerb_eval_prior); the eps = 1e-8
+clamped eigen-Schur complement and the factoring of the result into (linearized_jacobians,
+linearized_residuals) (marginalization_factor.cpp:281-305) run on the device too (cerb_marginalize_schur,
+csrc/marg_kernels.cuh).  What is left in numpy here is the bookkeeping in between: the loss corrector and the
+A = J^T J, b = J^T r assembly (marginalization_factor.cpp:46-77,150-181) -- moving that onto the device (the solve
+kernel's linearisation restricted to the factors that touch frame 0) is the rest of the "next #1" row of SURVEY.md 8(f).
 
 Block order inside the new prior is fixed (the reference's order is that of an unordered_map keyed by
 pointer value, i.e. arbitrary): dropped = [pose0, speedbias0, legbias0, lambdas...], kept = [pose k ...,
@@ -95,7 +97,7 @@ def marginalize_batch(backend, cfg, src, dst, margin_old=True):
 
     if margin_old and _uniform_structure(src) and not any(src.descs[w].prior.valid for w in range(B)) and imu is not None \
             and (src.preint[:, 0]["sum_dt"] < 10.0).all() and all(k in evals for k in (0, 1, 2)):
-        _marginalize_uniform(cfg, src, dst, st, evals, imu)
+        _marginalize_uniform(backend, cfg, src, dst, st, evals, imu)
         return
 
     for w in range(B):
@@ -192,19 +194,9 @@ def marginalize_batch(backend, cfg, src, dst, margin_old=True):
             ro += r.shape[0]
         A = Jbig.T @ Jbig
         b = Jbig.T @ rbig
-        # marginalization_factor.cpp:278-305
-        Amm = 0.5 * (A[:m, :m] + A[:m, :m].T)
-        ev, V = np.linalg.eigh(Amm)
-        inv = np.where(ev > EPS, 1.0 / np.where(ev > EPS, ev, 1.0), 0.0)
-        Amm_inv = (V * inv) @ V.T
-        Arm = A[m:, :m]
-        Ar = A[m:, m:] - Arm @ Amm_inv @ A[:m, m:]
-        br = b[m:] - Arm @ Amm_inv @ b[:m]
-        ev2, V2 = np.linalg.eigh(0.5 * (Ar + Ar.T))
-        S = np.where(ev2 > EPS, ev2, 0.0)
-        S_inv = np.where(ev2 > EPS, 1.0 / np.where(ev2 > EPS, ev2, 1.0), 0.0)
-        lin_J = np.sqrt(S)[:, None] * V2.T
-        lin_r = np.sqrt(S_inv) * (V2.T @ br)
+        # marginalization_factor.cpp:281-305 on the device (csrc/marg_kernels.cuh)
+        lin_J, lin_r = backend.marginalize_schur(A[None], b[None], m, EPS)
+        lin_J, lin_r = lin_J[0], lin_r[0]
         # getParameterBlocks + addr_shift (estimator.cpp:1357-1372 / :1413-1447)
         pr = dst.descs[w].prior
         x0s, metas = [], []
@@ -250,7 +242,7 @@ def _uniform_structure(src):
     return bool((src.obs[:, :no]["is_stereo"] == src.obs[0, :no]["is_stereo"]).all())
 
 
-def _marginalize_uniform(cfg, src, dst, st, evals, imu, chunk=64):
+def _marginalize_uniform(backend, cfg, src, dst, st, evals, imu, chunk=64):
     """Vectorised MARGIN_OLD for batches whose windows all share one factor-graph structure and carry no prior."""
     B = src.n
     nf = src.descs[0].n_features
@@ -314,18 +306,7 @@ def _marginalize_uniform(cfg, src, dst, st, evals, imu, chunk=64):
         r[:, ro:ro + 31] = imu[0][c0:c1]
         A = np.einsum("bri,brj->bij", J, J, optimize=True)
         bv = np.einsum("bri,br->bi", J, r)
-        Amm = 0.5 * (A[:, :m, :m] + np.swapaxes(A[:, :m, :m], 1, 2))
-        ev, V = np.linalg.eigh(Amm)
-        inv = np.where(ev > EPS, 1.0 / np.where(ev > EPS, ev, 1.0), 0.0)
-        Amm_inv = (V * inv[:, None, :]) @ np.swapaxes(V, 1, 2)
-        Arm = A[:, m:, :m]
-        Ar = A[:, m:, m:] - Arm @ Amm_inv @ A[:, :m, m:]
-        br = bv[:, m:] - (Arm @ Amm_inv @ bv[:, :m, None])[..., 0]
-        ev2, V2 = np.linalg.eigh(0.5 * (Ar + np.swapaxes(Ar, 1, 2)))
-        S = np.where(ev2 > EPS, ev2, 0.0)
-        S_inv = np.where(ev2 > EPS, 1.0 / np.where(ev2 > EPS, ev2, 1.0), 0.0)
-        lin_J = np.sqrt(S)[:, :, None] * np.swapaxes(V2, 1, 2)
-        lin_r = np.sqrt(S_inv) * (np.swapaxes(V2, 1, 2) @ br[..., None])[..., 0]
+        lin_J, lin_r = backend.marginalize_schur(A, bv, m, EPS)      # marginalization_factor.cpp:281-305 on the device
         for i in range(nb):
             w = c0 + i
             pr = dst.descs[w].prior

@@ -358,6 +358,15 @@ int cerb_batch_triangulate(CerbHandle *h, double init_depth, double *depth);
  * becomes init_depth) and keep = 0 for the tracks the reference erases (anchored at frame 0 with fewer than 2 remaining observations). */
 int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_frame, double *depth, int32_t *keep);
 
+/* The dense tail of MarginalizationInfo::marginalize() (marginalization_factor.cpp:281-305), batched: for every window the
+ * (m + n) x (m + n) Hessian A = sum J^T J (row-major, the m dropped coordinates first -- the reference's idx order) and b = sum J^T r
+ * as ThreadsConstructA (:150-181) leaves them; out: linearized_jacobians [n_windows][n * n] column-major (CerbPrior layout) and
+ * linearized_residuals [n_windows][n].  Amm is symmetrised, eigen-decomposed and pseudo-inverted with eigenvalues <= eps dropped
+ * (eps = 1e-8 in the reference), the Schur complement is eigen-decomposed from its lower triangle, S / S_inv clamped the same way.
+ * sweeps (optional, [n_windows][2]): Jacobi sweeps of the two eigen-decompositions, a convergence diagnostic. */
+int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t n, const double *A, const double *b, double eps,
+                           double *linearized_jacobians, double *linearized_residuals, int32_t *sweeps);
+
 /* ---- host-side helpers that stay on the CPU in the reference too ---------------------------- */
 /* Gauge re-anchoring of Estimator::double2vector (estimator.cpp:903-957): rotates the solved
  * window by the yaw difference of frame 0 and re-anchors its position.  before/after are the

@@ -188,6 +188,37 @@ struct RBInfo {
     }
 };
 
+// marginalization_factor.cpp:281-305: eigen pseudo-inverse of Amm, Schur complement, factoring into (linearized_jacobians, linearized_residuals)
+static void marg_schur(const Mat &A, const std::vector<double> &b, int m, int n, double eps, Mat &linearized_jacobians, std::vector<double> &linearized_residuals) {
+    Mat Amm(m, m);
+    for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Amm(i, j) = 0.5 * (A(i, j) + A(j, i));
+    std::vector<double> ev; Mat V;
+    sym_eig_jacobi(Amm, ev, V);
+    Mat Amm_inv(m, m);
+    for (int k = 0; k < m; k++) { if (!(ev[k] > eps)) continue; double inv = 1.0 / ev[k];
+        for (int i = 0; i < m; i++) { double vi = V(i, k) * inv; for (int j = 0; j < m; j++) Amm_inv(i, j) += vi * V(j, k); } }
+    // A = Arr - Arm * Amm_inv * Amr ; b = brr - Arm * Amm_inv * bmm
+    Mat Arm(n, m), Amr(m, n);
+    for (int i = 0; i < n; i++) for (int j = 0; j < m; j++) { Arm(i, j) = A(m + i, j); Amr(j, i) = A(j, m + i); }
+    Mat T = matmul(Arm, Amm_inv);
+    Mat TA = matmul(T, Amr);
+    Mat Ar(n, n); std::vector<double> br(n);
+    for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) Ar(i, j) = A(m + i, m + j) - TA(i, j);
+        double s = b[m + i]; for (int j = 0; j < m; j++) s -= T(i, j) * b[j]; br[i] = s; }
+    std::vector<double> ev2; Mat V2;
+    Mat Asym(n, n); for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Asym(i, j) = Ar(i, j);   // SelfAdjointEigenSolver reads the lower triangle
+    for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) Asym(i, j) = Asym(j, i);
+    sym_eig_jacobi(Asym, ev2, V2);
+    linearized_jacobians = Mat(n, n); linearized_residuals.assign(n, 0.0);
+    for (int k = 0; k < n; k++) {
+        double S = ev2[k] > eps ? ev2[k] : 0.0, Sinv = ev2[k] > eps ? 1.0 / ev2[k] : 0.0;
+        double ss = std::sqrt(S), sis = std::sqrt(Sinv);
+        double vb = 0; for (int i = 0; i < n; i++) vb += V2(i, k) * br[i];
+        for (int j = 0; j < n; j++) linearized_jacobians(k, j) = ss * V2(j, k);
+        linearized_residuals[k] = sis * vb;
+    }
+}
+
 struct MargInfo {
     std::vector<RBInfo> factors;
     std::vector<double *> order;                         // insertion order of parameter blocks (replaces unordered_map order)
@@ -232,33 +263,7 @@ struct MargInfo {
                 for (int a = 0; a < size_i; a++) { double s = 0; for (int r = 0; r < nr; r++) s += f.jacobians[i][r * gi + a] * f.residuals[r]; b[idx_i + a] += s; }
             }
         }
-        Mat Amm(m, m);
-        for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Amm(i, j) = 0.5 * (A(i, j) + A(j, i));
-        std::vector<double> ev; Mat V;
-        sym_eig_jacobi(Amm, ev, V);
-        Mat Amm_inv(m, m);
-        for (int k = 0; k < m; k++) { if (!(ev[k] > eps)) continue; double inv = 1.0 / ev[k];
-            for (int i = 0; i < m; i++) { double vi = V(i, k) * inv; for (int j = 0; j < m; j++) Amm_inv(i, j) += vi * V(j, k); } }
-        // A = Arr - Arm * Amm_inv * Amr ; b = brr - Arm * Amm_inv * bmm
-        Mat Arm(n, m), Amr(m, n);
-        for (int i = 0; i < n; i++) for (int j = 0; j < m; j++) { Arm(i, j) = A(m + i, j); Amr(j, i) = A(j, m + i); }
-        Mat T = matmul(Arm, Amm_inv);
-        Mat TA = matmul(T, Amr);
-        Mat Ar(n, n); std::vector<double> br(n);
-        for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) Ar(i, j) = A(m + i, m + j) - TA(i, j);
-            double s = b[m + i]; for (int j = 0; j < m; j++) s -= T(i, j) * b[j]; br[i] = s; }
-        std::vector<double> ev2; Mat V2;
-        Mat Asym(n, n); for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Asym(i, j) = Ar(i, j);   // SelfAdjointEigenSolver reads the lower triangle
-        for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) Asym(i, j) = Asym(j, i);
-        sym_eig_jacobi(Asym, ev2, V2);
-        linearized_jacobians = Mat(n, n); linearized_residuals.assign(n, 0.0);
-        for (int k = 0; k < n; k++) {
-            double S = ev2[k] > eps ? ev2[k] : 0.0, Sinv = ev2[k] > eps ? 1.0 / ev2[k] : 0.0;
-            double ss = std::sqrt(S), sis = std::sqrt(Sinv);
-            double vb = 0; for (int i = 0; i < n; i++) vb += V2(i, k) * br[i];
-            for (int j = 0; j < n; j++) linearized_jacobians(k, j) = ss * V2(j, k);
-            linearized_residuals[k] = sis * vb;
-        }
+        marg_schur(A, b, m, n, eps, linearized_jacobians, linearized_residuals);
     }
 };
 
@@ -665,6 +670,15 @@ int oracle_shift_depth(const CerbWindowDesc *d, const CerbWindowState *st, doubl
         V3 pts_j = transpose(R1) * (w_pts_i - P1);
         depth[f] = pts_j.z > 0 ? pts_j.z : init_depth;
     }
+    return 0;
+}
+
+int oracle_marginalize_schur(int m, int n, const double *A_rowmajor, const double *b_in, double eps, double *lin_J_colmajor, double *lin_r) {
+    int pos = m + n;
+    Mat A(pos, pos); std::vector<double> b(b_in, b_in + pos), r; Mat J;
+    for (int i = 0; i < pos; i++) for (int j = 0; j < pos; j++) A(i, j) = A_rowmajor[(size_t)i * pos + j];
+    marg_schur(A, b, m, n, eps, J, r);
+    for (int k = 0; k < n; k++) { for (int j = 0; j < n; j++) lin_J_colmajor[k + (size_t)j * n] = J(k, j); lin_r[k] = r[k]; }
     return 0;
 }
 

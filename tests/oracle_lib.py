@@ -132,6 +132,15 @@ class OracleBackend:
             assert self.lib.oracle_outlier_errors(C.byref(batch.descs[w]), C.byref(batch.states[w]), _p(out[w])) == 0
         return out
 
+    def marginalize_schur(self, A, b, m, eps=1e-8):
+        A = np.ascontiguousarray(A, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+        B, pos = b.shape; n = pos - m
+        J = np.zeros((B, n * n)); r = np.zeros((B, n))
+        self.lib.oracle_marginalize_schur.argtypes = [C.c_int, C.c_int, abi.c_dp, abi.c_dp, C.c_double, abi.c_dp, abi.c_dp]
+        for w in range(B):
+            assert self.lib.oracle_marginalize_schur(m, n, _p(A[w]), _p(b[w]), eps, _p(J[w]), _p(r[w])) == 0
+        return J.reshape(B, n, n).transpose(0, 2, 1), r
+
     def shift_depth(self, batch, init_depth=5.0):
         n, F = batch.n, batch.max_features
         start = np.full((n, F), -1, dtype=np.int32); depth = np.full((n, F), np.nan); keep = np.full((n, F), -1, dtype=np.int32)

@@ -22,7 +22,7 @@ def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for s in ("cerb_create", "cerb_destroy", "cerb_solve_window", "cerb_solve_batch", "cerb_batch_upload", "cerb_batch_solve_resident",
               "cerb_batch_download", "cerb_eval_projection", "cerb_eval_imu_leg", "cerb_eval_prior", "cerb_preintegrate_batch",
-              "cerb_a1_kinematics", "cerb_double2vector", "cerb_last_error", "cerb_batch_outlier_errors", "cerb_batch_triangulate", "cerb_batch_shift_depth"):
+              "cerb_a1_kinematics", "cerb_double2vector", "cerb_last_error", "cerb_batch_outlier_errors", "cerb_batch_triangulate", "cerb_batch_shift_depth", "cerb_marginalize_schur"):
         assert s in syms
 
 
