@@ -155,3 +155,25 @@ def test_imu_only_kernels_vs_reference_in_simulator(ref):
     pre, params = imu_setup(3)
     r0, j0, s0 = ref.eval_imu(pre, params); r1, j1, s1 = sb.eval_imu(pre, params)
     assert np.abs(s0 - s1).max() < 1e-9 * np.abs(s0).max() and np.abs(r0 - r1).max() < 1e-9 * np.abs(r0).max() and np.abs(j0 - j1).max() < 1e-9 * np.abs(j0).max()
+
+
+@pytest.mark.parametrize("margin_old", [True, False])
+def test_marginalization_with_prior_vs_reference(ref, margin_old):
+    """Windows that already carry a prior: MARGIN_OLD folds the old MarginalizationFactor in (estimator.cpp:1253-1270),
+    MARGIN_SECOND_NEW (estimator.cpp:1377-1455) drops para_Pose[WINDOW_SIZE - 1] from it and keeps the rest; reference classes
+    vs oracle restatement vs the product glue (device evaluators + cerb_marginalize_schur in the simulator)."""
+    from helpers import prior_canonical, sim_backend, small_cfg
+    cfg = small_cfg()
+    mk = lambda: synth.generate_batch(2, 10, ob, with_prior=True, window0=47)
+    src = mk()
+    assert all(src.descs[w].prior.valid for w in range(2))
+    a, b, c = mk(), mk(), mk()
+    ref.marginalize(cfg, src, a, margin_old); ob.marginalize(cfg, src, b, margin_old); sim_backend(cfg).marginalize(cfg, src, c, margin_old)
+    for w in range(2):
+        A0, b0, x0 = prior_canonical(a, w)
+        assert A0.shape[0] == (86 if margin_old else 80)
+        for other in (b, c):
+            A1, b1, x1 = prior_canonical(other, w)
+            assert A0.shape == A1.shape and set(x0) == set(x1)
+            assert np.abs(A0 - A1).max() < 1e-5 * np.abs(A0).max() and np.abs(b0 - b1).max() < 1e-4 * np.abs(b0).max()
+            assert all(np.abs(x0[k][:7] - x1[k][:7]).max() == 0 for k in x0)
