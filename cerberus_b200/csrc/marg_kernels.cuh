@@ -27,7 +27,7 @@ CERB_HD size_t marg_ws_doubles(int m, int n) {
 }
 CERB_HD size_t marg_smem_bytes(int m, int n) {           // (c, s) per concurrent rotation + the sweep flag
     const int k = m > n ? m : n;
-    return (size_t)(k + 1) * sizeof(double) + 16;
+    return (size_t)(k + 1) * sizeof(double) + 16;      // flag[2] behind the (c, s) pairs
 }
 
 // pair t (0 .. kp / 2 - 1) of round r (0 .. kp - 2) of a round-robin tournament over kp (even) players, p < q
@@ -39,32 +39,39 @@ CERB_D void jacobi_pair(int t, int r, int kp, int &p, int &q) {
     p = a < b ? a : b; q = a < b ? b : a;
 }
 
+// rotation angles of round r from the upper triangle of M as it stands; (c, s) -> cs, a non-trivial rotation raises *flag
+CERB_D void jacobi_angles(const double *M, int k, int kp, int r, double *cs, int *flag) {
+    for (int t = threadIdx.x; t < kp / 2; t += blockDim.x) {
+        int p, q; jacobi_pair(t, r, kp, p, q);
+        double c = 1.0, s = 0.0;
+        if (q < k) {
+            const double apq = M[p + (size_t)q * k], app = M[p + (size_t)p * k], aqq = M[q + (size_t)q * k];
+            if (apq != 0.0 && fabs(apq) > 1e-15 * sqrt(fabs(app * aqq))) {
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                c = 1.0 / sqrt(tt * tt + 1.0); s = tt * c;
+                if (s != 0.0) *flag = 1;
+            }
+        }
+        cs[2 * t] = c; cs[2 * t + 1] = s;
+    }
+}
+
 // Eigen-decomposition of the symmetric k x k matrix M (column-major, leading dimension k): on return the eigenvalues are on the
 // diagonal of M and the eigenvectors are the columns of V.  Called by all threads of the CTA; returns the number of sweeps.
+// Three CTA barriers per round: column pass | row pass | re-symmetrisation together with the angles of the next round (both only
+// read the upper triangle the row pass left).  flag[sweep & 1] collects "some rotation was non-trivial" for that sweep.
 CERB_D int jacobi_eig(double *M, double *V, int k, double *cs, int *flag) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
-    const int kp = k + (k & 1), half = kp / 2;
+    const int kp = k + (k & 1), half = kp / 2, rounds = kp - 1;
     for (int i = tid; i < k * k; i += nt) V[i] = (i / k == i % k) ? 1.0 : 0.0;
+    if (tid == 0) { flag[0] = 0; flag[1] = 0; }
+    __syncthreads();
+    jacobi_angles(M, k, kp, 0, cs, flag);
+    __syncthreads();
     int sweeps = 0;
     for (; sweeps < MARG_MAX_SWEEPS; sweeps++) {
-        if (tid == 0) *flag = 0;
-        __syncthreads();
-        for (int r = 0; r < kp - 1; r++) {
-            for (int t = tid; t < half; t += nt) {            // rotation angles from the entries as they are at the start of the round
-                int p, q; jacobi_pair(t, r, kp, p, q);
-                double c = 1.0, s = 0.0;
-                if (q < k) {
-                    const double apq = M[p + (size_t)q * k], app = M[p + (size_t)p * k], aqq = M[q + (size_t)q * k];
-                    if (apq != 0.0 && fabs(apq) > 1e-15 * sqrt(fabs(app * aqq))) {
-                        const double theta = (aqq - app) / (2.0 * apq);
-                        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                        c = 1.0 / sqrt(tt * tt + 1.0); s = tt * c;
-                        if (s != 0.0) *flag = 1;
-                    }
-                }
-                cs[2 * t] = c; cs[2 * t + 1] = s;
-            }
-            __syncthreads();
+        for (int r = 0; r < rounds; r++) {
             for (int t = wid; t < half; t += nwarp) {         // columns p, q of M and V
                 const double c = cs[2 * t], s = cs[2 * t + 1];
                 if (s == 0.0) continue;
@@ -86,15 +93,17 @@ CERB_D int jacobi_eig(double *M, double *V, int k, double *cs, int *flag) {
                     M[p + (size_t)j * k] = c * a - s * b; M[q + (size_t)j * k] = s * a + c * b;
                 }
             }
+            // every thread has read last sweep's verdict by now (it did so before this sweep's first column pass)
+            if (r == 0 && tid == 0) flag[(sweeps + 1) & 1] = 0;
             __syncthreads();
             // keep M exactly symmetric: the column and the row pass round differently, and an asymmetric residue of eps |M| is enough to
             // keep the null space of a rank-deficient Schur complement rotating for ever (the angles are taken from the upper triangle)
             for (int e = tid; e < k * k; e += nt) { const int i = e % k, j = e / k; if (i > j) M[e] = M[j + (size_t)i * k]; }
+            if (r + 1 < rounds) jacobi_angles(M, k, kp, r + 1, cs, flag + (sweeps & 1));
+            else jacobi_angles(M, k, kp, 0, cs, flag + ((sweeps + 1) & 1));
             __syncthreads();
         }
-        const int any = *flag;
-        __syncthreads();
-        if (!any) break;
+        if (!flag[sweeps & 1]) break;
     }
     return sweeps;
 }
