@@ -346,6 +346,7 @@ def generate_batch(n, n_features, backend, cfg=None, pcfg=None, window0=0, reali
         pfeats = make_features(F0, 0, 11, "prior")
         fill_batch(pb, pfeats, 0, pre_all[:, 0:10])
         backend.marginalize(cfg, pb, batch, margin_old=True)
+        batch.prior_window = pb        # the previous window (frames -1..9), for tests that chain solve -> marginalize -> solve
     if return_truth:
         tr_out = SynthTruth()
         tr_out.R, tr_out.p, tr_out.v = R_f[:, 1:], p_f[:, 1:], v_f[:, 1:]

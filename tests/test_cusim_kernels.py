@@ -216,3 +216,46 @@ def test_skipped_imu_factor():
     assert np.abs(rep_o["final_cost"] - rep_s["final_cost"]).max() < 1e-7 * rep_o["final_cost"].max()
     d = state_diffs(batch.state_array(), ref)
     assert d["para_Pose"] < 1e-7 and d["para_SpeedBias"] < 1e-5 and np.abs(batch.para_Feature - lam).max() < 1e-7, d
+
+
+def _chained_windows_case(make_backend, nw=2, F=12, F0=8, iters=3, nthreads=4):
+    """optimization() twice in a row, the way processImage() chains it: solve the previous window (frames -1..9), marginalize its oldest
+    frame at the SOLVED states (estimator.cpp:1247-1376), solve the next window against that prior.  Same chain on the oracle."""
+    cfg = small_cfg(max_batch=max(nw, 4), max_features=max(F, F0, 8), iters=iters)
+    o, be = OracleBackend(cfg), make_backend(cfg)
+    import ctypes as C
+    out = []
+    for X in (o, be):
+        batch = synth.generate_batch(nw, F, o, prior_features=F0, window0=91)
+        pb = batch.prior_window
+        rep_prev = (X.solve_batch(pb, nthreads=nthreads) if X is o else X.solve_batch(pb)).copy()
+        X.marginalize(cfg, pb, batch, margin_old=True)
+        before = (abi.WindowState * nw)()
+        C.memmove(before, batch.states, C.sizeof(before))
+        rep = (X.solve_batch(batch, nthreads=nthreads) if X is o else X.solve_batch(batch)).copy()
+        # what the estimator publishes: the states after the yaw / position re-anchoring of double2vector (estimator.cpp:868-1005)
+        anchored = [be.double2vector(before[w], batch.states[w]) for w in range(nw)]
+        out.append((batch, rep_prev, rep, anchored))
+    (b0, rp0, r0, a0), (b1, rp1, r1, a1) = out
+    assert (rp0["iterations"] == rp1["iterations"]).all() and (r0["iterations"] == r1["iterations"]).all()
+    assert (r0["num_successful_steps"] == r1["num_successful_steps"]).all()
+    for w in range(nw):
+        A0, g0, x0 = prior_canonical(b0, w); A1, g1, x1 = prior_canonical(b1, w)
+        assert np.abs(A0 - A1).max() < 1e-5 * np.abs(A0).max() and np.abs(g0 - g1).max() < 1e-4 * max(1.0, np.abs(g0).max())
+        assert all(np.abs(x0[k][:7] - x1[k][:7]).max() < 1e-7 for k in x0)              # linearisation point = solved previous window
+    # The eps-clamped eigen factoring of a gauge-deficient Hessian (|A| ~ 1e14 from near features; the eigenvalues that should be 0 are
+    # rounding noise of either sign, far above eps = 1e-8) leaves implementation-dependent noise along the gauge directions of the
+    # prior, which the next solve turns into a common drift of the raw poses: ~1e-5 m between the two Jacobi-based implementations
+    # compared here, ~4e-3 m against a LAPACK / tridiagonal-QR eigen-solver (measured; Eigen's solver in the reference is of that
+    # kind).  double2vector's yaw / position re-anchoring removes most of it.  Tolerances: the 1e-4 m bar of the path on the raw poses,
+    # 1e-5 on what the estimator publishes.
+    d = state_diffs(b1.state_array(), b0.state_array())
+    assert d["para_Pose"] < 1e-4 and d["para_SpeedBias"] < 1e-4 and d["para_Ex_Pose"] < 1e-5, d
+    for w in range(nw):
+        for x, y in zip(a0[w], a1[w]):
+            assert np.abs(np.asarray(x) - np.asarray(y)).max() < 1e-5
+    assert np.abs(r0["final_cost"] - r1["final_cost"]).max() < 1e-4 * r0["final_cost"].max()
+
+
+def test_chained_windows_match_oracle():
+    _chained_windows_case(lambda cfg: sim_backend(cfg))

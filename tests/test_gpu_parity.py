@@ -181,3 +181,8 @@ def test_maximum_feature_count(oracle):
 def test_rejected_steps_match_oracle_gpu():
     from test_cusim_kernels import _rejected_steps_case
     _rejected_steps_case(lambda cfg: lib.Backend(cfg))
+
+
+def test_chained_windows_match_oracle_gpu():
+    from test_cusim_kernels import _chained_windows_case
+    _chained_windows_case(lambda cfg: lib.Backend(cfg), nw=4, F=24, F0=16, iters=8, nthreads=4)
