@@ -218,7 +218,7 @@ def test_skipped_imu_factor():
     assert d["para_Pose"] < 1e-7 and d["para_SpeedBias"] < 1e-5 and np.abs(batch.para_Feature - lam).max() < 1e-7, d
 
 
-def _chained_windows_case(make_backend, nw=2, F=12, F0=8, iters=3, nthreads=4):
+def _chained_windows_case(make_backend, nw=1, F=12, F0=8, iters=3, nthreads=4):
     """optimization() twice in a row, the way processImage() chains it: solve the previous window (frames -1..9), marginalize its oldest
     frame at the SOLVED states (estimator.cpp:1247-1376), solve the next window against that prior.  Same chain on the oracle."""
     cfg = small_cfg(max_batch=max(nw, 4), max_features=max(F, F0, 8), iters=iters)
