@@ -64,6 +64,12 @@ def test_marg_schur_sim(m, n, rank):
     _check(sim_backend(cfg), OracleBackend(cfg), np.random.default_rng(m * 100 + n), 3, m, n, rank)
 
 
+def test_marg_schur_more_windows_than_ctas_sim():
+    """the per-CTA workspace is reused window after window (grid = min(windows, 2 x SMs))"""
+    cfg = abi.default_config(); cfg.max_batch, cfg.max_features, cfg.max_obs = 2, 8, 8 * 11
+    _check(sim_backend(cfg), OracleBackend(cfg), np.random.default_rng(5), 40, 3, 5, n_oracle=40)
+
+
 def test_marg_schur_bad_arguments_sim():
     cfg = abi.default_config(); cfg.max_batch, cfg.max_features, cfg.max_obs = 2, 8, 8 * 11
     be = sim_backend(cfg)
