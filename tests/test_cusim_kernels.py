@@ -259,3 +259,19 @@ def _chained_windows_case(make_backend, nw=1, F=12, F0=8, iters=3, nthreads=4):
 
 def test_chained_windows_match_oracle():
     _chained_windows_case(lambda cfg: sim_backend(cfg))
+
+
+def test_host_buffer_pipeline_chunks():
+    """cerb_solve_batch packs / copies / solves in chunks of whole waves (here: 9 windows on a 4-CTA grid -> chunks of 4, 4, 1, three
+    launches each); windows with identical inputs must come back bit-identical whichever chunk carried them.  (Host-buffer path == resident path at 1024 windows is asserted on the GPU tier.)"""
+    cfg = small_cfg(max_batch=16, max_features=8, iters=1)
+    s = sim_backend(cfg)
+    base = synth.generate_batch(3, 4, ob, with_prior=False, window0=140)
+    big = synth.tile_batch(base, 9)
+    rep = s.solve_batch(big)
+    assert s.last_solve_stats()[1] == 3 * 3
+    pose = big.state_array()["para_Pose"]
+    assert not (pose[:3] == base.state_array()["para_Pose"]).all()                  # the solve moved the states
+    for k in range(3, 9):
+        assert (pose[k] == pose[k % 3]).all() and (big.para_Feature[k] == big.para_Feature[k % 3]).all()
+    assert (rep["final_cost"][3:6] == rep["final_cost"][0:3]).all() and (rep["status"] == 0).all()
