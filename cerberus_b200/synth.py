@@ -376,3 +376,138 @@ def tile_batch(batch, n):
         d.prior.linearized_jacobians = big.prior_J[w].ctypes.data_as(abi.c_dp)
         d.prior.linearized_residuals = big.prior_r[w].ctypes.data_as(abi.c_dp)
     return big
+
+
+# ----------------------------------------------------------------------------- sequences (replay harness)
+class SynthSequence:
+    """Raw sensor streams of `n` independent synthetic robots over `n_frames` camera frames (what the reference's frontend hands to
+    Estimator::inputIMU / inputLeg / inputFeature): per inter-frame interval 33 IMU + leg samples, per frame the tracked features
+    (id -> normalised point / pixel velocity per camera).  See generate_sequence()."""
+    pass
+
+
+def generate_sequence(n, n_frames, tracked=60, seed0=7000, stereo_prob=0.9, outlier_fraction=0.0, min_len=2, max_len=14):
+    """n robots, n_frames frames (>= 12).  Features: every frame spawns enough new landmarks to keep ~`tracked` alive; a landmark is seen
+    for L in [min_len, max_len] consecutive frames (tracks shorter than 4 never enter the solve, like in the reference), in the left
+    camera always and in the right one with probability stereo_prob per observation.
+    Returns a SynthSequence with
+      samples [n, n_frames - 1, 33] sample_dtype, first [n, n_frames] (acc, gyr, phi, dphi, c at the frame instants: the integrators' ctor args),
+      images: list over frames of list over robots of dict(ids, pts0 [k,7], has1 [k], pts1 [k,7]) with the reference's 7-vector (x, y, z=1, u, v, vx, vy),
+      truth R/p/v [n, n_frames, ...], initial guesses p_g, R_g, v_g of every frame, ric_g / tic_g, ba, bg, lc_true."""
+    pcfg = abi.default_preint_config()
+    B, NF, S = n, n_frames, SAMPLES_PER_FRAME
+    T = (NF - 1) * S + 1
+    dt = FRAME_DT / S
+    t = np.arange(T) * dt
+    rngs = [np.random.Generator(np.random.PCG64(seed0 + w)) for w in range(B)]
+
+    def draw(fn):
+        return np.stack([fn(r) for r in rngs])
+
+    par = {
+        "yaw0": draw(lambda r: r.uniform(-np.pi, np.pi, 1)), "wz": draw(lambda r: r.uniform(-0.3, 0.3, 1)),
+        "ph_r": draw(lambda r: r.uniform(0, 2 * np.pi, 1)), "ph_p": draw(lambda r: r.uniform(0, 2 * np.pi, 1)),
+        "ph_z": draw(lambda r: r.uniform(0, 2 * np.pi, 1)),
+        "x0": draw(lambda r: r.uniform(-5, 5, 1)), "y0": draw(lambda r: r.uniform(-5, 5, 1)), "z0": draw(lambda r: r.uniform(0.25, 0.35, 1)),
+    }
+    tr = _trajectory(par, t)
+    ba = draw(lambda r: r.normal(0, 0.05, 3))
+    bg = draw(lambda r: r.normal(0, 0.005, 3))
+    gvec = np.array([0.0, 0.0, G_NORM])
+    RT = np.swapaxes(tr["R"], -1, -2)
+    acc = np.einsum("btij,btj->bti", RT, tr["a"] + gvec) + ba[:, None, :] + draw(lambda r: r.normal(0, 0.1, (T, 3)))
+    gyr = tr["w"] + bg[:, None, :] + draw(lambda r: r.normal(0, 0.01, (T, 3)))
+    fix = np.array([[pcfg.rho_fix[l][k] for k in range(4)] for l in range(4)])
+    lc_true = LC_NOMINAL + draw(lambda r: r.normal(0, 0.005, 4))
+    phase0 = draw(lambda r: r.uniform(0, 0.5, 1))
+    gait = (np.floor((t[None, :] + phase0) / 0.25).astype(int) % 2)
+    contact = np.stack([gait == 0, gait == 1, gait == 1, gait == 0], axis=-1).astype(float)
+    phi = np.zeros((B, T, 4, 3)); dphi = np.zeros((B, T, 4, 3))
+    phi[:, 0] = PHI_NOMINAL + draw(lambda r: r.normal(0, 0.05, (4, 3)))
+    v_body = np.einsum("btij,btj->bti", RT, tr["v"])
+
+    def joint_rate(ph, k):
+        f = a1_fk(ph, lc_true, fix); J = a1_jac(ph, lc_true, fix)
+        rhs = v_body[:, k, None, :] + np.cross(tr["w"][:, k, None, :], f)
+        st = -np.linalg.solve(J, rhs[..., None])[..., 0]
+        sw = 4.0 * (PHI_NOMINAL - ph)
+        c = contact[:, k, :, None]
+        return c * st + (1 - c) * sw
+
+    for k in range(T - 1):
+        k1 = joint_rate(phi[:, k], k); dphi[:, k] = k1
+        mid = phi[:, k] + 0.5 * dt * k1
+        phi[:, k + 1] = phi[:, k] + dt * 0.5 * (joint_rate(mid, k) + joint_rate(mid, k + 1))
+    dphi[:, T - 1] = joint_rate(phi[:, T - 1], T - 1)
+    phi_m = phi + draw(lambda r: r.normal(0, 1e-4, (T, 4, 3)))
+    dphi_m = dphi + draw(lambda r: r.normal(0, 0.02, (T, 4, 3)))
+
+    seq = SynthSequence()
+    seq.n, seq.n_frames, seq.dt = B, NF, dt
+    fidx = np.arange(NF) * S
+    seq.R, seq.p, seq.v = tr["R"][:, fidx], tr["p"][:, fidx], tr["v"][:, fidx]
+    seq.ba, seq.bg, seq.lc_true = ba, bg, lc_true
+    seq.R_g = seq.R @ so3_exp(draw(lambda r: r.normal(0, 0.01, (NF, 3))))
+    seq.p_g = seq.p + draw(lambda r: r.normal(0, 0.02, (NF, 3)))
+    seq.v_g = seq.v + draw(lambda r: r.normal(0, 0.05, (NF, 3)))
+    seq.ric_g = RIC @ so3_exp(draw(lambda r: r.normal(0, 0.005, (2, 3))))
+    seq.tic_g = TIC + draw(lambda r: r.normal(0, 0.005, (2, 3)))
+    samples = np.zeros((B, NF - 1, S), dtype=abi.sample_dtype)
+    first = np.zeros((B, NF), dtype=abi.sample_dtype)
+    for i in range(NF - 1):
+        ks = i * S + 1 + np.arange(S)
+        samples["dt"][:, i] = dt
+        samples["acc"][:, i] = acc[:, ks]; samples["gyr"][:, i] = gyr[:, ks]
+        samples["phi"][:, i] = phi_m[:, ks].reshape(B, S, 12); samples["dphi"][:, i] = dphi_m[:, ks].reshape(B, S, 12)
+        samples["c"][:, i] = contact[:, ks]
+    first["acc"], first["gyr"] = acc[:, fidx], gyr[:, fidx]
+    first["phi"], first["dphi"], first["c"] = phi_m[:, fidx].reshape(B, NF, 12), dphi_m[:, fidx].reshape(B, NF, 12), contact[:, fidx]
+    seq.samples, seq.first = samples, first
+
+    # ---- landmarks: per robot, per frame new tracks ---------------------------------------------------------------------------
+    images = [[None] * B for _ in range(NF)]
+    for w in range(B):
+        r = rngs[w]
+        tracks = []                                    # (id, start, L, p_world)
+        alive_until = []
+        next_id = 0
+        for k in range(NF):
+            alive = sum(1 for e in alive_until if e > k)
+            need = tracked - alive
+            for _ in range(max(need, 0)):
+                L = int(r.integers(min_len, max_len + 1))
+                depth = r.uniform(2, 15); nx = r.uniform(-0.6, 0.6); ny = r.uniform(-0.45, 0.45)
+                pc = np.array([nx * depth, ny * depth, depth])
+                pw = seq.R[w, k] @ (RIC @ pc + TIC[0]) + seq.p[w, k]
+                tracks.append((next_id, k, L, pw)); alive_until.append(k + L); next_id += 1
+        per_frame = [[] for _ in range(NF)]
+        prev_uv = {}
+        for (fid, s0, L, pw) in tracks:
+            for k in range(s0, min(s0 + L, NF)):
+                pb = seq.R[w, k].T @ (pw - seq.p[w, k])
+                uv = np.zeros((2, 2)); ok = True
+                for cam in range(2):
+                    pcam = RIC.T @ (pb - TIC[cam])
+                    if pcam[2] < 0.3: ok = False
+                    uv[cam] = pcam[:2] / pcam[2]
+                if not ok or abs(uv[0, 0]) > 1.2 or abs(uv[0, 1]) > 0.9:
+                    break                                                   # the track ends when the point leaves the view
+                uv += r.normal(0, 0.5 / 460.0, (2, 2))
+                if outlier_fraction > 0 and r.uniform() < outlier_fraction: uv += r.normal(0, 20.0 / 460.0, (2, 2))
+                has1 = r.uniform() < stereo_prob
+                pu = prev_uv.get(fid)
+                vel = (uv - pu) / FRAME_DT if pu is not None else np.zeros((2, 2))
+                prev_uv[fid] = uv
+                per_frame[k].append((fid, uv, vel, has1))
+        for k in range(NF):
+            lst = per_frame[k]
+            m = len(lst)
+            ids = np.array([e[0] for e in lst], dtype=np.int64)
+            pts0, pts1 = np.zeros((m, 7)), np.zeros((m, 7))
+            has1 = np.array([e[3] for e in lst], dtype=bool)
+            for q, (fid, uv, vel, h1) in enumerate(lst):
+                pts0[q] = (uv[0, 0], uv[0, 1], 1.0, 460.0 * uv[0, 0] + 320, 460.0 * uv[0, 1] + 240, vel[0, 0], vel[0, 1])
+                pts1[q] = (uv[1, 0], uv[1, 1], 1.0, 460.0 * uv[1, 0] + 320, 460.0 * uv[1, 1] + 240, vel[1, 0], vel[1, 1])
+            images[k][w] = dict(ids=ids, pts0=pts0, has1=has1, pts1=pts1)
+    seq.images = images
+    return seq

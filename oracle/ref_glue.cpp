@@ -19,6 +19,8 @@
 #include "factor/marginalization_factor.h"
 #include "factor/pose_local_parameterization.h"
 #include "legKinematics/A1Kinematics.h"
+#include "featureTracker/feature_manager.h"
+#include "utils/utility.h"
 #include <cstring>
 
 // ---- globals of src/utils/parameters.cpp that the compiled objects reference --------------------------------
@@ -26,6 +28,8 @@ double ACC_N, ACC_N_Z, ACC_W, GYR_N, GYR_W;
 Eigen::Vector3d G{0.0, 0.0, 9.805};
 int CONTACT_SENSOR_TYPE;
 double PHI_N, DPHI_N, RHO_C_N, RHO_NC_N;
+double INIT_DEPTH = 5.0, MIN_PARALLAX = 10.0 / 460.0;      // parameters.cpp:250 (INIT_DEPTH), yaml keyframe_parallax / FOCAL_LENGTH
+int NUM_OF_CAM = 2, STEREO = 1;
 double V_N_MIN_XY, V_N_MIN_Z, V_N_MIN, V_N_MAX, V_N_FORCE_THRES_RATIO, V_N_TERM1_STEEP, V_N_TERM2_VAR_RESCALE, V_N_TERM3_DISTANCE_RESCALE;
 
 namespace {
@@ -355,6 +359,127 @@ int ref_preintegrate_imu(int n, const CerbPreintJob *jobs, CerbIMUPreint *out) {
         for (int t = 0; t < 3; t++) { q.delta_p[t] = pre.delta_p(t); q.delta_v[t] = pre.delta_v(t); q.linearized_ba[t] = pre.linearized_ba(t); q.linearized_bg[t] = pre.linearized_bg(t); }
         q.delta_q[0] = pre.delta_q.x(); q.delta_q[1] = pre.delta_q.y(); q.delta_q[2] = pre.delta_q.z(); q.delta_q[3] = pre.delta_q.w();
         std::memcpy(q.jacobian, pre.jacobian.data(), sizeof(q.jacobian)); std::memcpy(q.covariance, pre.covariance.data(), sizeof(q.covariance));
+    }
+    return 0;
+}
+
+// ---- rows a2 / n3: the host-side steps either side of the solve, on the reference's own code --------------------------------------
+void ref_set_eigen_mode(int mode) { Eigen::shim_eig_mode() = mode; }    // 0: tridiagonal QR (Eigen's algorithm), 1: cyclic Jacobi
+
+// Estimator::double2vector, estimator.cpp:903-957 (USE_IMU branch), re-issued statement by statement on Utility::R2ypr / ypr2R
+// (utils/utility.h:85-125, compiled from the reference) and the quaternion -> rotation conversions of the Eigen shim.
+// `before` holds the para_* arrays written by vector2double() (Rs[0] = its quaternion as a matrix, Ps[0] = its position).
+void ref_double2vector(const CerbWindowState *before, const CerbWindowState *after, double *Ps_out, double *Rs_out, double *Vs_out) {
+    using namespace Eigen;
+    const double (*para_Pose)[7] = after->para_Pose; const double (*para_SpeedBias)[9] = after->para_SpeedBias;
+    Matrix3d Rs0 = Quaterniond(before->para_Pose[0][6], before->para_Pose[0][3], before->para_Pose[0][4], before->para_Pose[0][5]).toRotationMatrix();
+    Vector3d origin_R0 = Utility::R2ypr(Rs0);
+    Vector3d origin_P0(before->para_Pose[0][0], before->para_Pose[0][1], before->para_Pose[0][2]);
+    Vector3d origin_R00 = Utility::R2ypr(Quaterniond(para_Pose[0][6], para_Pose[0][3], para_Pose[0][4], para_Pose[0][5]).toRotationMatrix());
+    double y_diff = origin_R0.x() - origin_R00.x();
+    Matrix3d rot_diff = Utility::ypr2R(Vector3d(y_diff, 0, 0));
+    if (abs(abs(origin_R0.y()) - 90) < 1.0 || abs(abs(origin_R00.y()) - 90) < 1.0)
+        rot_diff = Rs0 * Quaterniond(para_Pose[0][6], para_Pose[0][3], para_Pose[0][4], para_Pose[0][5]).toRotationMatrix().transpose();
+    for (int i = 0; i <= WINDOW_SIZE; i++) {
+        Matrix3d R = rot_diff * Quaterniond(para_Pose[i][6], para_Pose[i][3], para_Pose[i][4], para_Pose[i][5]).normalized().toRotationMatrix();
+        Vector3d P = rot_diff * Vector3d(para_Pose[i][0] - para_Pose[0][0], para_Pose[i][1] - para_Pose[0][1], para_Pose[i][2] - para_Pose[0][2]) + origin_P0;
+        Vector3d V = rot_diff * Vector3d(para_SpeedBias[i][0], para_SpeedBias[i][1], para_SpeedBias[i][2]);
+        for (int k = 0; k < 3; k++) { Ps_out[3 * i + k] = P(k); Vs_out[3 * i + k] = V(k); for (int c = 0; c < 3; c++) Rs_out[9 * i + 3 * k + c] = R(k, c); }
+    }
+}
+
+namespace {
+// FeatureManager of the reference filled from the ABI descriptors (feature_id = index in the caller's array) + Rs / Ps / ric / tic
+struct RefWindow {
+    Eigen::Matrix3d Rs[WINDOW_SIZE + 1], ric[2]; Eigen::Vector3d Ps[WINDOW_SIZE + 1], tic[2];
+    FeatureManager fm;
+    RefWindow(const CerbWindowDesc *d, const CerbWindowState *st, bool depth_from_state) : fm(Rs) {
+        for (int i = 0; i <= WINDOW_SIZE; i++) {
+            Rs[i] = Eigen::Quaterniond(st->para_Pose[i][6], st->para_Pose[i][3], st->para_Pose[i][4], st->para_Pose[i][5]).normalized().toRotationMatrix();
+            Ps[i] = Eigen::Vector3d(st->para_Pose[i][0], st->para_Pose[i][1], st->para_Pose[i][2]);
+        }
+        for (int c = 0; c < 2; c++) {
+            ric[c] = Eigen::Quaterniond(st->para_Ex_Pose[c][6], st->para_Ex_Pose[c][3], st->para_Ex_Pose[c][4], st->para_Ex_Pose[c][5]).normalized().toRotationMatrix();
+            tic[c] = Eigen::Vector3d(st->para_Ex_Pose[c][0], st->para_Ex_Pose[c][1], st->para_Ex_Pose[c][2]);
+        }
+        fm.setRic(ric);
+        for (int f = 0; f < d->n_features; f++) {
+            const CerbFeature &ft = d->features[f];
+            fm.feature.push_back(FeaturePerId(f, ft.start_frame));
+            for (int k = 0; k < ft.n_obs; k++) {
+                const CerbObservation &o = d->obs[ft.obs_offset + k];
+                Eigen::Matrix<double, 7, 1> p; p << o.point[0], o.point[1], 1.0, 0.0, 0.0, o.velocity[0], o.velocity[1];
+                FeaturePerFrame fpf(p, o.cur_td);
+                if (o.is_stereo) { Eigen::Matrix<double, 7, 1> q; q << o.pointRight[0], o.pointRight[1], 1.0, 0.0, 0.0, o.velocityRight[0], o.velocityRight[1]; fpf.rightObservation(q); }
+                fm.feature.back().feature_per_frame.push_back(fpf);
+            }
+            if (depth_from_state) fm.feature.back().estimated_depth = 1.0 / st->para_Feature[f];        // FeatureManager::setDepth, feature_manager.cpp:142-160
+        }
+    }
+};
+// Estimator::reprojectionError, estimator.cpp:1729-1739 (a member of Estimator, which cannot be compiled here: statements re-issued)
+double reprojectionError(Eigen::Matrix3d &Ri, Eigen::Vector3d &Pi, Eigen::Matrix3d &rici, Eigen::Vector3d &tici, Eigen::Matrix3d &Rj, Eigen::Vector3d &Pj,
+                         Eigen::Matrix3d &ricj, Eigen::Vector3d &ticj, double depth, Eigen::Vector3d &uvi, Eigen::Vector3d &uvj) {
+    Eigen::Vector3d pts_w = Ri * (rici * (depth * uvi) + tici) + Pi;
+    Eigen::Vector3d pts_cj = ricj.transpose() * (Rj.transpose() * (pts_w - Pj) - ticj);
+    Eigen::Vector2d residual = (pts_cj / pts_cj.z()).head<2>() - uvj.head<2>();
+    double rx = residual.x(), ry = residual.y();
+    return sqrt(rx * rx + ry * ry);
+}
+}  // namespace
+
+// FeatureManager::triangulate (feature_manager.cpp:302-431) of the reference on the window: features with para_Feature <= 0 start
+// untriangulated (estimated_depth = -1, FeaturePerId ctor), the others keep 1 / para_Feature.
+int ref_triangulate(const CerbWindowDesc *d, const CerbWindowState *st, double init_depth, double *depth) {
+    INIT_DEPTH = init_depth; STEREO = 1;
+    RefWindow W(d, st, false);
+    { int f = 0; for (auto &it : W.fm.feature) { if (st->para_Feature[f] > 0.0) it.estimated_depth = 1.0 / st->para_Feature[f]; f++; } }
+    W.fm.triangulate(WINDOW_SIZE, W.Ps, W.Rs, W.tic, W.ric);
+    for (auto &it : W.fm.feature) depth[it.feature_id] = it.estimated_depth;
+    return 0;
+}
+
+// Estimator::slideWindowOld + FeatureManager::removeBackShiftDepth (estimator.cpp:1660-1677, feature_manager.cpp:450-488): back_R0 / back_P0
+// are the marginalized frame 0, Rs[0] / Ps[0] after the slide are the old frame 1.
+int ref_shift_depth(const CerbWindowDesc *d, const CerbWindowState *st, double init_depth, int *new_start, double *depth, int *keep) {
+    INIT_DEPTH = init_depth;
+    RefWindow W(d, st, true);
+    Eigen::Matrix3d back_R0 = W.Rs[0]; Eigen::Vector3d back_P0 = W.Ps[0];
+    Eigen::Matrix3d R0, R1; Eigen::Vector3d P0, P1;
+    R0 = back_R0 * W.ric[0];
+    R1 = W.Rs[1] * W.ric[0];
+    P0 = back_P0 + back_R0 * W.tic[0];
+    P1 = W.Ps[1] + W.Rs[1] * W.tic[0];
+    for (int f = 0; f < d->n_features; f++) keep[f] = 0;
+    W.fm.removeBackShiftDepth(R0, P0, R1, P1);
+    for (auto &it : W.fm.feature) { keep[it.feature_id] = 1; new_start[it.feature_id] = it.start_frame; depth[it.feature_id] = it.estimated_depth; }
+    return 0;
+}
+
+// Estimator::outliersRejection, estimator.cpp:1741-1798, statements re-issued on the reference's FeatureManager list; ave_err per feature
+int ref_outlier_errors(const CerbWindowDesc *d, const CerbWindowState *st, double *ave_err_out) {
+    STEREO = 1;
+    RefWindow W(d, st, true);
+    Eigen::Matrix3d *Rs = W.Rs, *ric = W.ric; Eigen::Vector3d *Ps = W.Ps, *tic = W.tic;
+    for (auto &it_per_id : W.fm.feature) {
+        double err = 0; int errCnt = 0;
+        it_per_id.used_num = it_per_id.feature_per_frame.size();
+        if (it_per_id.used_num < 4) continue;
+        int imu_i = it_per_id.start_frame, imu_j = imu_i - 1;
+        Eigen::Vector3d pts_i = it_per_id.feature_per_frame[0].point;
+        double depth = it_per_id.estimated_depth;
+        for (auto &it_per_frame : it_per_id.feature_per_frame) {
+            imu_j++;
+            if (imu_i != imu_j) {
+                Eigen::Vector3d pts_j = it_per_frame.point;
+                err += reprojectionError(Rs[imu_i], Ps[imu_i], ric[0], tic[0], Rs[imu_j], Ps[imu_j], ric[0], tic[0], depth, pts_i, pts_j); errCnt++;
+            }
+            if (STEREO && it_per_frame.is_stereo) {
+                Eigen::Vector3d pts_j_right = it_per_frame.pointRight;
+                err += reprojectionError(Rs[imu_i], Ps[imu_i], ric[0], tic[0], Rs[imu_j], Ps[imu_j], ric[1], tic[1], depth, pts_i, pts_j_right); errCnt++;
+            }
+        }
+        ave_err_out[it_per_id.feature_id] = err / errCnt;
     }
     return 0;
 }

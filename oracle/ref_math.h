@@ -8,6 +8,7 @@
 //   Utility::{deltaQ, skewSymmetric, Qleft, Qright, R2ypr, ypr2R}   src/utils/utility.h:28-125
 // PARITY UNPINNED: the reference ships no golden vectors for this path.
 #pragma once
+#include "sym_eig_qr.h"
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -264,6 +265,19 @@ inline void sym_eig_jacobi(const Mat &Ain, std::vector<double> &evals, Mat &V) {
     }
     evals.resize(n);
     for (int i = 0; i < n; i++) evals[i] = A(i, i);
+}
+
+// Eigen::SelfAdjointEigenSolver as the reference uses it (marginalization_factor.cpp:281,297): Householder tridiagonalisation + implicit QR,
+// eigenvalues ascending (oracle/sym_eig_qr.h restates Eigen 3.3.x's algorithm).  eig_mode() == 1 switches to the cyclic Jacobi solver above
+// (what the device kernels use), kept so that the sensitivity of the marginalization prior to the eigen-solver can be measured.
+inline int &eig_mode() { static int mode = 0; return mode; }
+inline void sym_eig(const Mat &A, std::vector<double> &evals, Mat &V) {
+    if (eig_mode() == 1) { sym_eig_jacobi(A, evals, V); return; }
+    const int n = A.r;
+    evals.resize(n); std::vector<double> Q((size_t)n * n);
+    symeig::tridiag_qr(n, A.d.data(), n, 1, evals.data(), Q.data());          // row-major A: (i, j) at i * n + j
+    V = Mat(n, n);
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V(i, j) = Q[(size_t)j * n + i];
 }
 
 }  // namespace oracle

@@ -193,7 +193,7 @@ static void marg_schur(const Mat &A, const std::vector<double> &b, int m, int n,
     Mat Amm(m, m);
     for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Amm(i, j) = 0.5 * (A(i, j) + A(j, i));
     std::vector<double> ev; Mat V;
-    sym_eig_jacobi(Amm, ev, V);
+    sym_eig(Amm, ev, V);
     Mat Amm_inv(m, m);
     for (int k = 0; k < m; k++) { if (!(ev[k] > eps)) continue; double inv = 1.0 / ev[k];
         for (int i = 0; i < m; i++) { double vi = V(i, k) * inv; for (int j = 0; j < m; j++) Amm_inv(i, j) += vi * V(j, k); } }
@@ -208,7 +208,7 @@ static void marg_schur(const Mat &A, const std::vector<double> &b, int m, int n,
     std::vector<double> ev2; Mat V2;
     Mat Asym(n, n); for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Asym(i, j) = Ar(i, j);   // SelfAdjointEigenSolver reads the lower triangle
     for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) Asym(i, j) = Asym(j, i);
-    sym_eig_jacobi(Asym, ev2, V2);
+    sym_eig(Asym, ev2, V2);
     linearized_jacobians = Mat(n, n); linearized_residuals.assign(n, 0.0);
     for (int k = 0; k < n; k++) {
         double S = ev2[k] > eps ? ev2[k] : 0.0, Sinv = ev2[k] > eps ? 1.0 / ev2[k] : 0.0;
@@ -681,6 +681,8 @@ int oracle_marginalize_schur(int m, int n, const double *A_rowmajor, const doubl
     for (int k = 0; k < n; k++) { for (int j = 0; j < n; j++) lin_J_colmajor[k + (size_t)j * n] = J(k, j); lin_r[k] = r[k]; }
     return 0;
 }
+
+void oracle_set_eig_mode(int mode) { eig_mode() = mode; }   // 0: tridiagonal QR (the reference's Eigen solver, default), 1: cyclic Jacobi
 
 int oracle_abi_sizes(int *out, int n) {   // struct-size handshake for the ctypes mirror
     int v[] = {(int)sizeof(CerbSolverConfig), (int)sizeof(CerbIMULegPreint), (int)sizeof(CerbObservation), (int)sizeof(CerbFeature), (int)sizeof(CerbPrior),

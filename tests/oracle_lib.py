@@ -49,12 +49,18 @@ class OracleBackend:
         return out
 
     def marginalize(self, cfg, src, dst, margin_old=True):
+        """margin_old: one flag for the batch, or one per window (True / 1: MARGIN_OLD, False / 0: MARGIN_SECOND_NEW)."""
+        flags = np.broadcast_to(np.asarray(margin_old, dtype=bool), (src.n,))
         for w in range(src.n):
             pr = dst.descs[w].prior
             J, r = dst.prior_J[w], dst.prior_r[w]
-            rc = self.lib.oracle_marginalize(C.byref(cfg), C.byref(src.descs[w]), C.byref(src.states[w]), 1 if margin_old else 0,
+            rc = self.lib.oracle_marginalize(C.byref(cfg), C.byref(src.descs[w]), C.byref(src.states[w]), 1 if flags[w] else 0,
                                              C.byref(pr), _p(J), _p(r))
             assert rc == 0
+
+    def set_eig_mode(self, mode):
+        """0: tridiagonal QR (the reference's Eigen::SelfAdjointEigenSolver; default), 1: cyclic Jacobi."""
+        self.lib.oracle_set_eig_mode(int(mode))
 
     def solve_batch(self, batch, nthreads=1, cfg=None):
         cfg = cfg or self.cfg
@@ -230,10 +236,48 @@ class RefBackend:
 
 def _ref_marginalize(self, cfg, src, dst, margin_old=True):
     """RefBackend.marginalize: the reference's own MarginalizationInfo / ResidualBlockInfo classes."""
+    flags = np.broadcast_to(np.asarray(margin_old, dtype=bool), (src.n,))
     for w in range(src.n):
         pr = dst.descs[w].prior
-        rc = self.lib.ref_marginalize(C.byref(src.descs[w]), C.byref(src.states[w]), 1 if margin_old else 0, C.byref(pr), _p(dst.prior_J[w]), _p(dst.prior_r[w]))
+        rc = self.lib.ref_marginalize(C.byref(src.descs[w]), C.byref(src.states[w]), 1 if flags[w] else 0, C.byref(pr), _p(dst.prior_J[w]), _p(dst.prior_r[w]))
         assert rc == 0
+
+
+def _ref_double2vector(self, before_state, after_state):
+    Ps, Rs, Vs = np.zeros((11, 3)), np.zeros((11, 3, 3)), np.zeros((11, 3))
+    self.lib.ref_double2vector(C.byref(before_state), C.byref(after_state), _p(Ps), _p(Rs), _p(Vs))
+    return Ps, Rs, Vs
+
+
+def _ref_triangulate(self, batch, init_depth=5.0):
+    out = np.full((batch.n, batch.max_features), np.nan)
+    self.lib.ref_triangulate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, abi.c_dp]
+    for w in range(batch.n):
+        assert self.lib.ref_triangulate(C.byref(batch.descs[w]), C.byref(batch.states[w]), init_depth, _p(out[w])) == 0
+    return out
+
+
+def _ref_outlier_errors(self, batch):
+    out = np.full((batch.n, batch.max_features), np.nan)
+    for w in range(batch.n):
+        assert self.lib.ref_outlier_errors(C.byref(batch.descs[w]), C.byref(batch.states[w]), _p(out[w])) == 0
+    return out
+
+
+def _ref_shift_depth(self, batch, init_depth=5.0):
+    n, F = batch.n, batch.max_features
+    start = np.full((n, F), -1, dtype=np.int32); depth = np.full((n, F), np.nan); keep = np.full((n, F), -1, dtype=np.int32)
+    self.lib.ref_shift_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_int32), abi.c_dp, C.POINTER(C.c_int32)]
+    for w in range(n):
+        assert self.lib.ref_shift_depth(C.byref(batch.descs[w]), C.byref(batch.states[w]), init_depth, start[w].ctypes.data_as(C.POINTER(C.c_int32)),
+                                        _p(depth[w]), keep[w].ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    return start, depth, keep
+
+
+RefBackend.double2vector = _ref_double2vector
+RefBackend.triangulate = _ref_triangulate
+RefBackend.outlier_errors = _ref_outlier_errors
+RefBackend.shift_depth = _ref_shift_depth
 
 
 RefBackend.marginalize = _ref_marginalize
@@ -256,3 +300,27 @@ def _ref_preintegrate_imu(self, pcfg, jobs, n):
 
 RefBackend.eval_imu = _ref_eval_imu
 RefBackend.preintegrate_imu = _ref_preintegrate_imu
+
+
+class OracleOps:
+    """Backend adapter of cerberus_b200.estimator.ReplayDriver on the CPU oracle (the reference arm of the replay comparison)."""
+
+    def __init__(self, cfg, nthreads=8, eig_mode=0, marg=None, feat=None):
+        self.o, self.cfg, self.nthreads, self.eig_mode = OracleBackend(cfg), cfg, nthreads, eig_mode
+        self.marg = marg          # optional RefBackend: the reference's own MarginalizationInfo classes for the marginalization step
+        self.feat = feat          # optional RefBackend: the reference's own FeatureManager for triangulation / depth shift / outlier errors
+
+    def preintegrate(self, pcfg, jobs, n): return self.o.preintegrate(pcfg, jobs, n)
+    def solve(self, batch): return self.o.solve_batch(batch, nthreads=self.nthreads)
+    def double2vector(self, before, after): return self.o.double2vector(before, after)
+    def triangulate(self, batch): return (self.feat or self.o).triangulate(batch)
+    def outlier_errors(self, batch): return (self.feat or self.o).outlier_errors(batch)
+    def shift_depth(self, batch): return (self.feat or self.o).shift_depth(batch)
+
+    def marginalize(self, src, dst, flags):
+        if self.marg is not None:
+            self.marg.lib.ref_set_eigen_mode(int(self.eig_mode))
+            self.marg.marginalize(self.cfg, src, dst, margin_old=(np.asarray(flags) == 0))
+        else:
+            self.o.set_eig_mode(self.eig_mode)
+            self.o.marginalize(self.cfg, src, dst, margin_old=(np.asarray(flags) == 0))
