@@ -43,15 +43,22 @@ struct CerbHandle {
     // device buffers
     int *d_nfeat = nullptr, *d_fstart = nullptr, *d_fnobs = nullptr, *d_foff = nullptr, *d_flags = nullptr, *d_stereo = nullptr, *d_pmeta = nullptr, *d_repi = nullptr;
     double *d_obs = nullptr, *d_pre = nullptr, *d_sinfo = nullptr, *d_pJ = nullptr, *d_pr = nullptr, *d_px0 = nullptr, *d_pHp = nullptr;
-    double *d_state = nullptr, *d_state0 = nullptr, *d_lam = nullptr, *d_lam0 = nullptr, *d_repd = nullptr, *d_ws = nullptr, *d_dbg = nullptr, *d_G = nullptr;
+    double *d_state = nullptr, *d_state0 = nullptr, *d_lam = nullptr, *d_lam0 = nullptr, *d_repd = nullptr, *d_ws = nullptr, *d_dbg = nullptr, *d_G = nullptr, *d_probe_repd = nullptr;
+    int *d_probe_repi = nullptr;
     // pinned staging
     int *h_nfeat = nullptr, *h_fstart = nullptr, *h_fnobs = nullptr, *h_foff = nullptr, *h_flags = nullptr, *h_stereo = nullptr, *h_pmeta = nullptr, *h_repi = nullptr;
     double *h_obs = nullptr, *h_pre = nullptr, *h_pJ = nullptr, *h_pr = nullptr, *h_px0 = nullptr, *h_state = nullptr, *h_lam = nullptr, *h_repd = nullptr, *h_dbg = nullptr;
+    int test_fail_factorizations = 0; double test_initial_mu = 0.0;   // fault injection of the parity tests (environment, read by cerb_create)
     bool solved = false;              // the device states are the solved ones (else: the uploaded initial states)
     std::vector<int> h_perm;          // [B][F] device feature slot -> index in the caller's feature array (tracks are sorted by anchor frame on the device)
     long ws_stride = 0;
     size_t smem_bytes = 0;
 };
+
+static int create_impl(CerbHandle *h, const CerbSolverConfig *cfg, const cudaDeviceProp &prop);
+// every entry point re-selects the handle's device: the host application (or torch) may have changed the current device, and two
+// handles on different GPUs may be driven from one thread
+#define CERB_DEVICE(h) do { if (h) { cudaError_t e_ = cudaSetDevice((h)->cfg.device); if (e_ != cudaSuccess) return fail(CERB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e_)); } } while (0)
 
 extern "C" {
 
@@ -98,11 +105,24 @@ int cerb_create(const CerbSolverConfig *cfg, CerbHandle **out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
     CerbHandle *h = new CerbHandle();
+    const int rc = create_impl(h, cfg, prop);
+    if (rc != CERB_OK) { const std::string keep = g_err; cerb_destroy(h); g_err = keep; return rc; }      // no leak of streams / buffers on a failed create
+    *out = h;
+    return CERB_OK;
+}
+
+}  // extern "C"
+
+static int create_impl(CerbHandle *h, const CerbSolverConfig *cfg, const cudaDeviceProp &prop) {
     h->cfg = *cfg; h->sm_count = prop.multiProcessorCount;
+    // Test hooks of the Ceres LINEAR_SOLVER_FAILURE path (tests/test_solver_failure.py); unset in production.  A factorisation of
+    // J^T J + 1e-8 D^2 practically never fails in fp64, so the in-step mu retry of DoglegStrategy can only be exercised by injection.
+    if (const char *e = std::getenv("CERB_TEST_FAIL_FACTORIZATIONS")) h->test_fail_factorizations = std::atoi(e);
+    if (const char *e = std::getenv("CERB_TEST_INITIAL_MU")) h->test_initial_mu = std::atof(e);
     h->B = cfg->max_batch; h->F = cfg->max_features; h->O = cfg->max_obs;
     h->grid = std::min(h->B, h->sm_count);
     h->smem_bytes = (size_t)SMEM_DOUBLES * sizeof(double);
-    if (h->smem_bytes > prop.sharedMemPerBlockOptin) { delete h; return fail(CERB_ERR_CUDA, "solve kernel needs more shared memory than the device offers"); }
+    if (h->smem_bytes > prop.sharedMemPerBlockOptin) return fail(CERB_ERR_CUDA, "solve kernel needs more shared memory than the device offers");
     CUDA_TRY(cudaFuncSetAttribute(vilo_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     CUDA_TRY(cudaFuncSetAttribute(prior_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PRIOR_TROWS * PRIOR_TLD * sizeof(double))));
     CUDA_TRY(cudaStreamCreate(&h->stream));
@@ -117,6 +137,7 @@ int cerb_create(const CerbSolverConfig *cfg, CerbHandle **out) {
     CUDA_TRY(dmalloc(&h->d_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(dmalloc(&h->d_pr, B * PRIOR_LD)); CUDA_TRY(dmalloc(&h->d_px0, B * 16 * 9)); CUDA_TRY(dmalloc(&h->d_pHp, B * PRIOR_LD * PRIOR_LD));
     CUDA_TRY(dmalloc(&h->d_state, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_state0, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_lam, B * F)); CUDA_TRY(dmalloc(&h->d_lam0, B * F));
     CUDA_TRY(dmalloc(&h->d_repd, B * 2)); CUDA_TRY(dmalloc(&h->d_ws, (size_t)h->grid * h->ws_stride)); CUDA_TRY(dmalloc(&h->d_dbg, 2 * (NR + F) + 8)); CUDA_TRY(dmalloc(&h->d_G, 4));
+    CUDA_TRY(dmalloc(&h->d_probe_repi, 4)); CUDA_TRY(dmalloc(&h->d_probe_repd, 2));
     CUDA_TRY(hmalloc(&h->h_nfeat, B)); CUDA_TRY(hmalloc(&h->h_fstart, B * F)); CUDA_TRY(hmalloc(&h->h_fnobs, B * F)); CUDA_TRY(hmalloc(&h->h_foff, B * F));
     CUDA_TRY(hmalloc(&h->h_flags, B)); CUDA_TRY(hmalloc(&h->h_stereo, B * O)); CUDA_TRY(hmalloc(&h->h_pmeta, B * PRIOR_META_STRIDE)); CUDA_TRY(hmalloc(&h->h_repi, B * 4));
     CUDA_TRY(hmalloc(&h->h_obs, B * NOBS_PLANES * O)); CUDA_TRY(hmalloc(&h->h_pre, B * 10 * PRE_STRIDE));
@@ -124,15 +145,17 @@ int cerb_create(const CerbSolverConfig *cfg, CerbHandle **out) {
     h->h_perm.assign(B * F, 0);
     CUDA_TRY(hmalloc(&h->h_state, B * ST_STRIDE)); CUDA_TRY(hmalloc(&h->h_lam, B * F)); CUDA_TRY(hmalloc(&h->h_repd, B * 2)); CUDA_TRY(hmalloc(&h->h_dbg, 2 * (NR + F) + 8));
     CUDA_TRY(cudaMemcpy(h->d_G, cfg->g, 3 * sizeof(double), cudaMemcpyHostToDevice));
-    *out = h;
     return CERB_OK;
 }
 
+extern "C" {
+
 void cerb_destroy(CerbHandle *h) {
     if (!h) return;
-    cudaStreamSynchronize(h->stream);
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     void *dev[] = {h->d_nfeat, h->d_fstart, h->d_fnobs, h->d_foff, h->d_flags, h->d_stereo, h->d_pmeta, h->d_repi, h->d_obs, h->d_pre, h->d_sinfo, h->d_pJ, h->d_pr,
-                   h->d_px0, h->d_pHp, h->d_state, h->d_state0, h->d_lam, h->d_lam0, h->d_repd, h->d_ws, h->d_dbg, h->d_G};
+                   h->d_px0, h->d_pHp, h->d_state, h->d_state0, h->d_lam, h->d_lam0, h->d_repd, h->d_ws, h->d_dbg, h->d_G, h->d_probe_repi, h->d_probe_repd};
     for (void *p : dev) if (p) cudaFree(p);
     void *hst[] = {h->h_nfeat, h->h_fstart, h->h_fnobs, h->h_foff, h->h_flags, h->h_stereo, h->h_pmeta, h->h_repi, h->h_obs, h->h_pre, h->h_pJ, h->h_pr, h->h_px0,
                    h->h_state, h->h_lam, h->h_repd, h->h_dbg};
@@ -189,7 +212,9 @@ static int pack_prior(const CerbPrior &pr, int *meta, double *J, double *r, doub
     if (pr.n < 1 || pr.n > CERB_MAX_PRIOR_DIM || pr.num_blocks < 1 || pr.num_blocks > CERB_MAX_PRIOR_BLOCKS || !pr.linearized_jacobians || !pr.linearized_residuals)
         return fail(CERB_ERR_BAD_ARGUMENT, "prior: bad n / num_blocks / null matrices");
     meta[0] = 1; meta[1] = pr.n; meta[2] = pr.num_blocks;
+    bool covered[CERB_MAX_PRIOR_DIM] = {false};          // the kept blocks must tile [0, n) exactly once (the solver's column -> destination map is built from them)
     for (int b = 0; b < pr.num_blocks; b++) {
+        for (int c = 0; c < b; c++) if (pr.block_kind[c] == pr.block_kind[b] && pr.block_index[c] == pr.block_index[b]) return fail(CERB_ERR_BAD_ARGUMENT, "prior: duplicate parameter block");
         const int kind = pr.block_kind[b], index = pr.block_index[b];
         if (kind < 0 || kind > 4 || index < 0 || index > 10 || ((kind == CERB_BLOCK_EX_POSE) && index > 1)) return fail(CERB_ERR_BAD_ARGUMENT, "prior: bad block");
         // the solver keeps Hyy block tridiagonal: a prior may only keep the speed/leg bias of frame 0 (what
@@ -198,8 +223,10 @@ static int pack_prior(const CerbPrior &pr, int *meta, double *J, double *r, doub
         meta[4 + 3 * b] = kind; meta[5 + 3 * b] = index; meta[6 + 3 * b] = pr.block_col[b];
         const int size = prior_block_size(kind), local = size == 7 ? 6 : size;
         if (pr.block_col[b] < 0 || pr.block_col[b] + local > pr.n) return fail(CERB_ERR_BAD_ARGUMENT, "prior: block column out of range");
+        for (int k = 0; k < local; k++) { if (covered[pr.block_col[b] + k]) return fail(CERB_ERR_BAD_ARGUMENT, "prior: overlapping block columns"); covered[pr.block_col[b] + k] = true; }
         for (int k = 0; k < 9; k++) x0[9 * b + k] = pr.block_x0[b][k];
     }
+    for (int k = 0; k < pr.n; k++) if (!covered[k]) return fail(CERB_ERR_BAD_ARGUMENT, "prior: the kept blocks do not cover all n columns");
     std::memcpy(J, pr.linearized_jacobians, sizeof(double) * pr.n * pr.n);
     std::memcpy(r, pr.linearized_residuals, sizeof(double) * pr.n);
     return CERB_OK;
@@ -300,19 +327,23 @@ static SolveParams make_params(CerbHandle *h, int w0, int n, int max_iters, doub
     P.prior_meta = h->d_pmeta + W0 * PRIOR_META_STRIDE;
     P.state = h->d_state + W0 * ST_STRIDE; P.lam = h->d_lam + W0 * F; P.rep_i = h->d_repi + W0 * 4; P.rep_d = h->d_repd + W0 * 2; P.ws = h->d_ws; P.ws_stride = h->ws_stride;
     P.dbg = dbg; P.dbg_window = dbg_window;
+    P.test_fail_factorizations = h->test_fail_factorizations; P.test_initial_mu = h->test_initial_mu;
     return P;
 }
 
 // restore the initial states of windows [w0, w0 + n), prepare (sqrt_info, prior Gram matrix) and solve; asynchronous on the stream
-static int enqueue_solve(CerbHandle *h, int w0, int n, int max_iters, double *dbg, int dbg_window) {
+static int enqueue_solve(CerbHandle *h, int w0, int n, int max_iters, double *dbg, int dbg_window, bool restore = true, bool probe = false) {
     cudaStream_t s = h->stream;
     const size_t W0 = (size_t)w0;
-    CUDA_TRY(cudaMemcpyAsync(h->d_state + W0 * ST_STRIDE, h->d_state0 + W0 * ST_STRIDE, (size_t)n * ST_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->d_lam + W0 * h->F, h->d_lam0 + W0 * h->F, (size_t)n * h->F * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (restore) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_state + W0 * ST_STRIDE, h->d_state0 + W0 * ST_STRIDE, (size_t)n * ST_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(h->d_lam + W0 * h->F, h->d_lam0 + W0 * h->F, (size_t)n * h->F * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
     const int nfac = n * 10;
     CERB_LAUNCH(imu_leg_prepare_kernel, (nfac + 1) / 2, 64, 0, s, nfac, (const double *)(h->d_pre + W0 * 10 * PRE_STRIDE), h->d_sinfo + W0 * 10 * 961);
     CERB_LAUNCH(prior_prepare_kernel, n, 256, (size_t)PRIOR_TROWS * PRIOR_TLD * sizeof(double), s, (const double *)(h->d_pJ + W0 * PRIOR_LD * PRIOR_LD), (const int *)(h->d_pmeta + W0 * PRIOR_META_STRIDE), h->d_pHp + W0 * PRIOR_LD * PRIOR_LD);
     SolveParams P = make_params(h, w0, n, max_iters, dbg, dbg_window);
+    if (probe) { P.rep_i = h->d_probe_repi; P.rep_d = h->d_probe_repd; }       // a probe leaves the reports of the batch alone
     if (max_iters > 0) h->solved = true;
     CERB_LAUNCH(vilo_solve_kernel, std::min(n, h->grid), SOLVE_THREADS, h->smem_bytes, s, P);
     CUDA_TRY(cudaGetLastError());
@@ -373,6 +404,7 @@ extern "C" {
 
 int cerb_batch_upload(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, const CerbWindowState *states) {
     if (!h || !descs || !states) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    CERB_DEVICE(h);
     if (n < 1 || n > h->B) return fail(CERB_ERR_BAD_ARGUMENT, "batch size over capacity");
     CUDA_TRY(cudaStreamSynchronize(h->stream));          // staging buffers may still be in flight
     int rc = pack_all(h, n, descs, states); if (rc) return rc;
@@ -380,20 +412,24 @@ int cerb_batch_upload(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, con
 }
 int cerb_batch_solve_resident(CerbHandle *h) {
     if (!h) return fail(CERB_ERR_BAD_ARGUMENT, "null handle");
+    CERB_DEVICE(h);
     int rc = collect_time(h); if (rc) return rc;
     return launch_solve(h, h->cfg.max_num_iterations, nullptr, -1, true);
 }
 int cerb_batch_download(CerbHandle *h, CerbWindowState *states, CerbSolveReport *reports) {
     if (!h) return fail(CERB_ERR_BAD_ARGUMENT, "null handle");
+    CERB_DEVICE(h);
     return download(h, states, reports);
 }
 int cerb_sync(CerbHandle *h) {
     if (!h) return fail(CERB_ERR_BAD_ARGUMENT, "null handle");
+    CERB_DEVICE(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return collect_time(h);
 }
 int cerb_last_solve_stats(CerbHandle *h, double *kernel_ms, int32_t *kernel_launches) {
     if (!h) return fail(CERB_ERR_BAD_ARGUMENT, "null handle");
+    CERB_DEVICE(h);
     int rc = collect_time(h); if (rc) return rc;
     if (kernel_ms) *kernel_ms = h->last_ms;
     if (kernel_launches) *kernel_launches = h->last_launches;
@@ -401,6 +437,7 @@ int cerb_last_solve_stats(CerbHandle *h, double *kernel_ms, int32_t *kernel_laun
 }
 int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, CerbWindowState *states, CerbSolveReport *reports) {
     if (!h || !descs || !states) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    CERB_DEVICE(h);
     if (n < 1 || n > h->B) return fail(CERB_ERR_BAD_ARGUMENT, "batch size over capacity");
     CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
     int rc = collect_time(h); if (rc) return rc;
@@ -451,11 +488,14 @@ int cerb_solve_window(CerbHandle *h, const CerbWindowDesc *desc, CerbWindowState
 
 int cerb_debug_linearize(CerbHandle *h, int32_t w, double *cost, double *gradient, double *jtj_diag, int32_t n_alloc) {
     if (!h || w < 0 || w >= h->n) return fail(CERB_ERR_BAD_ARGUMENT, "bad window index");
+    CERB_DEVICE(h);
     const int nf = h->h_nfeat[w], F = h->F;
     if (n_alloc < NR + nf) return fail(CERB_ERR_BAD_ARGUMENT, "n_alloc too small");
     const size_t cnt = 2 * (size_t)(NR + F) + 8;
     CUDA_TRY(cudaMemsetAsync(h->d_dbg, 0, cnt * sizeof(double), h->stream));
-    int rc = launch_solve(h, 0, h->d_dbg, w, false); if (rc) return rc;
+    // Read-only with respect to the resident batch: only window w is linearised, at the solved states if the batch has been solved
+    // (else at the uploaded initial states, which are first copied into place), with the reports going to scratch.
+    int rc = enqueue_solve(h, w, 1, 0, h->d_dbg, 0, !h->solved, true); if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(h->h_dbg, h->d_dbg, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (cost) *cost = h->h_dbg[0];
@@ -494,6 +534,7 @@ int cerb_eval_projection(CerbHandle *h, int32_t kind, int32_t n, const double *p
                          const double *inv_dep, const double *td, const double *pts_i, const double *pts_j, const double *vel_i, const double *vel_j,
                          const double *td_i, const double *td_j, double *residuals, double *jacobians) {
     if (!h || n < 1 || kind < 0 || kind > 2 || !ex0 || !inv_dep || !td || !pts_i || !pts_j || !vel_i || !vel_j || !td_i || !td_j) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_projection: bad argument");
+    CERB_DEVICE(h);
     if (kind != CERB_PROJ_ONE_FRAME_TWO_CAM && (!pose_i || !pose_j)) return fail(CERB_ERR_BAD_ARGUMENT, "poses required");
     if (kind != CERB_PROJ_TWO_FRAME_ONE_CAM && !ex1) return fail(CERB_ERR_BAD_ARGUMENT, "ex1 required");
     cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
@@ -516,6 +557,7 @@ int cerb_eval_projection(CerbHandle *h, int32_t kind, int32_t n, const double *p
 
 int cerb_eval_imu_leg(CerbHandle *h, int32_t n, const CerbIMULegPreint *preint, const double *params, double *residuals, double *jacobians, double *sqrt_info) {
     if (!h || n < 1 || !preint || !params) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_imu_leg: bad argument");
+    CERB_DEVICE(h);
     cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
     std::vector<double> packed(N * PRE_STRIDE, 0.0);
     for (int k = 0; k < n; k++) pack_preint(preint[k], packed.data() + (size_t)k * PRE_STRIDE);
@@ -534,6 +576,7 @@ int cerb_eval_imu_leg(CerbHandle *h, int32_t n, const CerbIMULegPreint *preint, 
 
 int cerb_eval_imu(CerbHandle *h, int32_t n, const CerbIMUPreint *preint, const double *params, double *residuals, double *jacobians, double *sqrt_info) {
     if (!h || n < 1 || !preint || !params) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_imu: bad argument");
+    CERB_DEVICE(h);
     cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
     std::vector<double> packed(N * PRE_STRIDE), p40(N * 40, 0.0);
     for (int k = 0; k < n; k++) {
@@ -568,6 +611,7 @@ int cerb_eval_imu(CerbHandle *h, int32_t n, const CerbIMUPreint *preint, const d
 
 int cerb_eval_prior(CerbHandle *h, const CerbPrior *prior, const CerbWindowState *state, double *residuals, double *jacobians) {
     if (!h || !prior || !state || !prior->valid || !residuals) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_prior: bad argument");
+    CERB_DEVICE(h);
     std::vector<int> meta(PRIOR_META_STRIDE); std::vector<double> J(PRIOR_LD * PRIOR_LD, 0.0), r(PRIOR_LD, 0.0), x0(16 * 9, 0.0), st(ST_STRIDE, 0.0);
     int rc = pack_prior(*prior, meta.data(), J.data(), r.data(), x0.data()); if (rc) return rc;
     std::memcpy(st.data() + ST_POSE, state->para_Pose, sizeof(state->para_Pose)); std::memcpy(st.data() + ST_SB, state->para_SpeedBias, sizeof(state->para_SpeedBias));
@@ -590,6 +634,7 @@ int cerb_eval_prior(CerbHandle *h, const CerbPrior *prior, const CerbWindowState
 int cerb_a1_kinematics(CerbHandle *h, int32_t n, const double *q, const double *rho_opt, const double *rho_fix, double *fk, double *jac, double *dfk_drho,
                        double *dJ_dq, double *dJ_drho) {
     if (!h || n < 1 || !q || !rho_opt || !rho_fix) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_a1_kinematics: bad argument");
+    CERB_DEVICE(h);
     cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
     double *dq = B.up(q, 3 * N, s), *dro = B.up(rho_opt, N, s), *drf = B.up(rho_fix, 4 * N, s);
     double *dfk = fk ? B.up(nullptr, 3 * N, s) : nullptr, *dj = jac ? B.up(nullptr, 9 * N, s) : nullptr, *ddf = dfk_drho ? B.up(nullptr, 3 * N, s) : nullptr;
@@ -608,6 +653,7 @@ int cerb_a1_kinematics(CerbHandle *h, int32_t n, const double *q, const double *
 // ---- per-feature steps on the resident batch ------------------------------------------------------------------------
 static int feature_pass(CerbHandle *h, int which, double param, double *out, int32_t *remove) {
     if (!h || !out) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    CERB_DEVICE(h);
     if (h->n < 1) return fail(CERB_ERR_BAD_ARGUMENT, "no resident batch");
     const int n = h->n, F = h->F;
     cudaStream_t s = h->stream; DevBuf B;
@@ -640,6 +686,7 @@ int cerb_batch_triangulate(CerbHandle *h, double init_depth, double *depth) { re
 int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t n, const double *A, const double *b, double eps,
                            double *linearized_jacobians, double *linearized_residuals, int32_t *sweeps) {
     if (!h || !A || !b || !linearized_jacobians || !linearized_residuals) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    CERB_DEVICE(h);
     if (n_windows < 1 || m < 1 || n < 1 || m > 4096 || n > CERB_MAX_PRIOR_DIM) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_marginalize_schur: bad sizes");
     const size_t pos = (size_t)m + n, N = n_windows;
     int grid = std::min<int>(n_windows, 2 * h->sm_count);
@@ -659,6 +706,7 @@ int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t 
 
 int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_frame, double *depth, int32_t *keep) {
     if (!h || !new_start_frame || !depth || !keep) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    CERB_DEVICE(h);
     if (h->n < 1) return fail(CERB_ERR_BAD_ARGUMENT, "no resident batch");
     const int n = h->n, F = h->F;
     const size_t N = (size_t)n * F;
@@ -685,6 +733,7 @@ int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_
 // ---- leg-contact preintegration ------------------------------------------------------------------------------------
 static int preintegrate_impl(CerbHandle *h, const CerbPreintConfig *cfg, int32_t n, const CerbPreintJob *jobs, CerbIMULegPreint *out, CerbIMUPreint *out_imu) {
     if (!h || !cfg || n < 1 || !jobs || (!out && !out_imu)) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_preintegrate: bad argument");
+    CERB_DEVICE(h);
     PreintParams P;
     P.imu_only = out_imu ? 1 : 0;
     P.acc_n = cfg->acc_n; P.acc_n_z = cfg->acc_n_z; P.gyr_n = cfg->gyr_n; P.acc_w = cfg->acc_w; P.gyr_w = cfg->gyr_w; P.phi_n = cfg->phi_n; P.dphi_n = cfg->dphi_n;

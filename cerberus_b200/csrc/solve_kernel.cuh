@@ -49,6 +49,9 @@ struct SolveParams {
     double *ws;                                                             // [grid][ws_stride] per-CTA workspace
     long ws_stride;
     double *dbg; int dbg_window;                                            // optional probe (cost, gradient, diag)
+    double test_initial_mu;                                                 // parity tests only (env CERB_TEST_INITIAL_MU): DoglegStrategy::mu_ at the start (0: Ceres' 1e-8)
+    int test_fail_factorizations;                                           // parity tests only (env CERB_TEST_FAIL_FACTORIZATIONS): report the first k
+                                                                            // Gauss-Newton solves of every window as failed (LINEAR_SOLVER_FAILURE path)
 };
 
 // per-CTA global workspace layout (doubles); F = maxF
@@ -930,12 +933,12 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
         }
         for (int k = tid; k < ST_STRIDE; k += SOLVE_THREADS) s.xs[k] = (k < ST_SIZE) ? P.state[(size_t)w * ST_STRIDE + k] : 0.0;
         if (tid == 0) {
-            sca[S_RADIUS] = P.radius0; sca[S_MU] = 1e-8; sca[S_REUSE] = 0; sca[S_DONE] = 0; sca[S_TERM] = 1; sca[S_ITER] = 0; sca[S_NSUCC] = 0;
+            sca[S_RADIUS] = P.radius0; sca[S_MU] = P.test_initial_mu > 0.0 ? P.test_initial_mu : 1e-8; sca[S_REUSE] = 0; sca[S_DONE] = 0; sca[S_TERM] = 1; sca[S_ITER] = 0; sca[S_NSUCC] = 0;
             sca[S_INVALID] = 0; sca[S_DLNORM] = 0;
         }
         __syncthreads();
         bool need_linearize = true, hxx_prefetched = false, last_accepted = true;
-        int iteration = 0;
+        int iteration = 0, gn_attempts = 0;
 
         // ---- linearisation at (xl, laml): H, g (Jacobi scaled), W, hh, gl; results S_LCOST (cost), S_LNORM (||x||), S_LGMAX (max |g|) --------
         auto linearize = [&](const double *xl, const double *laml, bool first) {
@@ -1031,6 +1034,17 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
 
             // =============================== DoglegStrategy::ComputeStep ===================================
             if (sca[S_REUSE] == 0.0) {
+              // DoglegStrategy::ComputeGaussNewtonStep retries INSIDE one ComputeStep (`while (mu_ < max_mu_)`, Ceres 1.14 dogleg_strategy.cc):
+              // a failed factorisation / non-finite step multiplies mu by 10 and solves again at the same point -- no iteration and no invalid
+              // step is consumed; only when mu reaches max_mu (1.0) does the strategy report LINEAR_SOLVER_FAILURE.  The factorisation here is
+              // in place, so a retry first rebuilds H / g at the same point.
+              for (;;) {
+                if (!(sca[S_MU] < 1.0)) {                 // while (mu_ < max_mu_) not entered: LINEAR_SOLVER_FAILURE without a solve
+                    __syncthreads();
+                    if (tid == 0) { sca[S_OK] = 0; sca[S_REUSE] = 1; }
+                    __syncthreads();
+                    break;
+                }
                 // diagonal, gradient / D, scaled gradient v (kept in s.stp: the Cauchy point's v^T H v is finished later, see below)
                 for (int k = tid; k < NR; k += SOLVE_THREADS) {
                     const double d = (k < NX) ? s.Hxx[k * NX + k] : s.Ad[((k - NX) / NYB) * 169 + ((k - NX) % NYB) * (NYB + 1)];
@@ -1417,6 +1431,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                     }
                     for (int k = tid; k < NR; k += SOLVE_THREADS) if (!(fabs(s.yv[k]) < 1e300)) bad = 1.0;
                     if (bad != 0.0) sca[S_OK] = 0;          // benign race: every writer stores 0
+                    if (gn_attempts < P.test_fail_factorizations) sca[S_OK] = 0;      // fault injection of the parity tests (0 in production)
+                    gn_attempts++;
                     __syncthreads();
                     PH_MARK(13);
                 }
@@ -1432,6 +1448,13 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                 }
                 if (tid == 0) sca[S_REUSE] = 1;
                 __syncthreads();
+                if (sca[S_OK] != 0.0) break;              // the Gauss-Newton step is there
+                __syncthreads();
+                if (tid == 0) sca[S_MU] *= 10.0;           // mu_ *= mu_increase_factor_; continue;
+                __syncthreads();
+                if (!(sca[S_MU] < 1.0)) break;            // LINEAR_SOLVER_FAILURE (S_OK == 0)
+                linearize(s.xs, lam, false);               // the failed in-place factorisation overwrote H: rebuild it at the same point
+              }
             }
             // =============================== step validity =================================================
             if (sca[S_OK] == 0.0) {       // LINEAR_SOLVER_FAILURE -> HandleInvalidStep
@@ -1439,7 +1462,6 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                     sca[S_INVALID] += 1;
                     if (sca[S_INVALID] >= 5) { sca[S_DONE] = 1; sca[S_TERM] = 2; }
                     sca[S_MU] *= 10.0; sca[S_REUSE] = 0;      // StepIsInvalid
-                    if (sca[S_MU] >= 1.0) sca[S_MU] = 1.0 - 1e-12;   // keep retrying like Ceres does at max_mu
                 }
                 __syncthreads();
                 if (sca[S_DONE] != 0.0) break;
@@ -1477,7 +1499,6 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                     sca[S_INVALID] += 1;
                     if (sca[S_INVALID] >= 5) { sca[S_DONE] = 1; sca[S_TERM] = 2; }
                     sca[S_MU] *= 10.0; sca[S_REUSE] = 0;
-                    if (sca[S_MU] >= 1.0) sca[S_MU] = 1.0 - 1e-12;
                 }
                 __syncthreads();
                 if (sca[S_DONE] != 0.0) break;

@@ -252,6 +252,7 @@ struct Dogleg {
     double increase_threshold = 0.75, decrease_threshold = 0.25;
     double dogleg_step_norm = 0, alpha = 0;
     bool reuse = false;
+    int gn_attempts = 0, test_fail_factorizations = 0;      // CERB_TEST_FAIL_FACTORIZATIONS (environment): report the first k linear solves as LINEAR_SOLVER_FAILURE
     std::vector<double> diagonal, gradient, gauss_newton_step;
 
     // returns 0 SUCCESS, 1 FAILURE
@@ -275,7 +276,9 @@ struct Dogleg {
         bool ok = false;
         while (mu < max_mu) {
             std::vector<double> lm(n); for (int i = 0; i < n; i++) lm[i] = diagonal[i] * std::sqrt(mu);
-            if (schur_solve(G, jac, residuals, lm.data(), gauss_newton_step.data())) { ok = true; break; }
+            bool solved = schur_solve(G, jac, residuals, lm.data(), gauss_newton_step.data());
+            if (gn_attempts++ < test_fail_factorizations) solved = false;         // fault injection (tests/test_solver_failure.py)
+            if (solved) { ok = true; break; }
             mu *= mu_increase_factor;
         }
         if (!ok) return 1;
@@ -338,6 +341,8 @@ void Solve(const SolverOptions &opt, Problem &problem, SolverSummary &summary) {
     for (int idx : G.active) { const Problem::PB &b = problem.pbs[idx]; for (int k = 0; k < b.size; k++) x[b.xoff + k] = b.data[k]; }
     double x_norm = vnorm(x), x_cost = 0, candidate_cost = 0, model_cost_change = 0;
     Dogleg strategy; strategy.radius = opt.initial_trust_region_radius; strategy.max_radius = opt.max_trust_region_radius;
+    if (const char *e = getenv("CERB_TEST_FAIL_FACTORIZATIONS")) strategy.test_fail_factorizations = atoi(e);     // same hooks as the product library
+    if (const char *e = getenv("CERB_TEST_INITIAL_MU")) strategy.mu = atof(e);
     int iteration = 0, num_consecutive_invalid_steps = 0;
     bool step_is_successful = false;
     double gradient_max_norm = 0;
