@@ -501,6 +501,35 @@ class ReplayDriver:
         return P, R
 
 
+class DeviceOps:
+    """Backend adapter of ReplayDriver over one CerbHandle (cerberus_b200.lib.Backend): every numerical step of the frame loop is a call
+    through the C ABI.  The handle's feature capacity must cover the triangulation batch (2 x the solve batch)."""
+
+    def __init__(self, backend, cfg):
+        self.be, self.cfg = backend, cfg
+
+    def preintegrate(self, pcfg, jobs, n): return self.be.preintegrate(pcfg, jobs, n)
+    def solve(self, batch): return self.be.solve_batch(batch)
+    def double2vector(self, before, after): return self.be.double2vector(before, after)
+
+    def triangulate(self, batch):
+        self.be.upload(batch)
+        return self.be.triangulate(batch.n, INIT_DEPTH)[:, :batch.max_features]
+
+    def outlier_errors(self, batch):
+        self.be.upload(batch)                           # the states were re-anchored by double2vector after the solve
+        return self.be.outlier_errors(batch.n, FOCAL_LENGTH)[0][:, :batch.max_features]
+
+    def shift_depth(self, batch):
+        self.be.upload(batch)
+        a, b, c = self.be.shift_depth(batch.n, INIT_DEPTH)
+        F = batch.max_features
+        return a[:, :F], b[:, :F], c[:, :F]
+
+    def marginalize(self, src, dst, flags):
+        self.be.marginalize(self.cfg, src, dst, margin_old=(np.asarray(flags) == MARGIN_OLD))
+
+
 def write_csv(path, est, pcfg):
     """The result file of the reference's main loop (src/main.cpp:153-197): time [ns], robot-body position / velocity (IMU pose moved
     by R_br p_br), six Kalman-filter columns and three mocap columns (not produced here: 0), rho1..rho4 of the newest frame."""

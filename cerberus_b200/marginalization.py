@@ -48,10 +48,14 @@ def marginalize_batch(backend, cfg, src, dst, margin_old=True):
     B = src.n
     st = src.state_array()
     delta = cfg.huber_delta
+    flags = np.broadcast_to(np.asarray(margin_old, dtype=bool), (B,))        # one flag for the batch or one per window (True: MARGIN_OLD)
+    any_old = bool(flags.any())
     # ---- gather the projection factors anchored at frame 0 over the whole batch (MARGIN_OLD only) -------------
     per_kind = {0: [], 1: [], 2: []}
-    if margin_old:
+    if any_old:
         for w in range(B):
+            if not flags[w]:
+                continue
             d = src.descs[w]
             nf = d.n_features
             ft = src.features[w][:nf]
@@ -88,20 +92,21 @@ def marginalize_batch(backend, cfg, src, dst, margin_old=True):
         evals[kind] = (ws, fidx, kk, res, jac)
     # ---- IMU-leg factor between frames 0 and 1 ------------------------------------------------------------------
     imu = None
-    if margin_old:
+    if any_old:
         params = np.concatenate([st["para_Pose"][:, 0], st["para_SpeedBias"][:, 0], st["para_LegBias"][:, 0],
                                  st["para_Pose"][:, 1], st["para_SpeedBias"][:, 1], st["para_LegBias"][:, 1]], axis=1)
         pre0 = np.ascontiguousarray(src.preint[:, 0])
         r_imu, j_imu, _ = backend.eval_imu_leg(pre0, params)
         imu = (r_imu, j_imu.reshape(B, -1))
 
-    if margin_old and _uniform_structure(src) and not any(src.descs[w].prior.valid for w in range(B)) and imu is not None \
+    if flags.all() and _uniform_structure(src) and not any(src.descs[w].prior.valid for w in range(B)) and imu is not None \
             and (src.preint[:, 0]["sum_dt"] < 10.0).all() and all(k in evals for k in (0, 1, 2)):
         _marginalize_uniform(backend, cfg, src, dst, st, evals, imu)
         return
 
     for w in range(B):
         d = src.descs[w]
+        margin_old = bool(flags[w])
         rows_J, rows_r = [], []       # list of (residual vector, [(block key, jac [nr, local])])
         blocks_seen = []              # insertion order of (kind, index) / ('f', feature)
 
