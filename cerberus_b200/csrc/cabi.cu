@@ -8,6 +8,7 @@
 #include "preint_kernel.cuh"
 #include "feature_kernels.cuh"
 #include "marg_kernels.cuh"
+#include "pack_kernels.cuh"
 #include <string>
 #include <vector>
 #include <thread>
@@ -16,6 +17,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <cstdint>
+#include <utility>
 
 using namespace cerb;
 
@@ -37,22 +40,31 @@ struct CerbHandle {
     cudaEvent_t ev_copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_pending = false;
-    double last_ms = 0; int last_launches = 0;
+    double last_ms = 0; int last_launches = 0, last_dma_ops = 0; size_t last_staged_bytes = 0;
     int B = 0, F = 0, O = 0;          // capacities
     int n = 0;                        // windows currently resident
-    // device buffers
-    int *d_nfeat = nullptr, *d_fstart = nullptr, *d_fnobs = nullptr, *d_foff = nullptr, *d_flags = nullptr, *d_stereo = nullptr, *d_pmeta = nullptr, *d_repi = nullptr;
+    // device: the caller's descriptors as they are (filled by DMA) ...
+    CerbWindowDesc *d_rdesc = nullptr; CerbFeature *d_rfeat = nullptr; CerbObservation *d_robs = nullptr; CerbWindowState *d_rstate = nullptr;
+    double *d_rpre = nullptr, *d_rlam = nullptr;
+    // ... and the solver's layout (written by pack_kernel)
+    int *d_nfeat = nullptr, *d_fstart = nullptr, *d_fnobs = nullptr, *d_foff = nullptr, *d_flags = nullptr, *d_stereo = nullptr, *d_pmeta = nullptr, *d_repi = nullptr, *d_perm = nullptr;
     double *d_obs = nullptr, *d_pre = nullptr, *d_sinfo = nullptr, *d_pJ = nullptr, *d_pr = nullptr, *d_px0 = nullptr, *d_pHp = nullptr;
     double *d_state = nullptr, *d_state0 = nullptr, *d_lam = nullptr, *d_lam0 = nullptr, *d_repd = nullptr, *d_ws = nullptr, *d_dbg = nullptr, *d_G = nullptr, *d_probe_repd = nullptr;
     int *d_probe_repi = nullptr;
-    // pinned staging
-    int *h_nfeat = nullptr, *h_fstart = nullptr, *h_fnobs = nullptr, *h_foff = nullptr, *h_flags = nullptr, *h_stereo = nullptr, *h_pmeta = nullptr, *h_repi = nullptr;
-    double *h_obs = nullptr, *h_pre = nullptr, *h_pJ = nullptr, *h_pr = nullptr, *h_px0 = nullptr, *h_state = nullptr, *h_lam = nullptr, *h_repd = nullptr, *h_dbg = nullptr;
+    double *d_olam = nullptr, *d_ostate = nullptr; CerbSolveReport *d_orep = nullptr;      // results in the caller's layout (unpack_kernel)
+    // pinned staging (used for sources that are not in registered memory, and for the results)
+    CerbWindowDesc *h_rdesc = nullptr; CerbFeature *h_rfeat = nullptr; CerbObservation *h_robs = nullptr; CerbWindowState *h_rstate = nullptr;
+    double *h_rpre = nullptr, *h_rlam = nullptr, *h_pJ = nullptr, *h_pr = nullptr, *h_state = nullptr, *h_lam = nullptr, *h_dbg = nullptr;
+    CerbSolveReport *h_orep = nullptr;
+    std::vector<std::pair<uintptr_t, size_t>> regs;   // host ranges registered with cerb_register_host_buffer: DMA straight out of them
+    std::vector<int> nfeat;           // [B] n_features of the resident windows
     int test_fail_factorizations = 0; double test_initial_mu = 0.0;   // fault injection of the parity tests (environment, read by cerb_create)
     bool solved = false;              // the device states are the solved ones (else: the uploaded initial states)
-    std::vector<int> h_perm;          // [B][F] device feature slot -> index in the caller's feature array (tracks are sorted by anchor frame on the device)
+    std::vector<int> h_perm; bool perm_valid = false;     // [B][F] device feature slot -> index in the caller's feature array (fetched on demand)
     long ws_stride = 0;
     size_t smem_bytes = 0;
+    // scratch arena of the evaluator / feature / preintegration entry points: grows to the high-water mark, then no more cudaMalloc per call
+    std::vector<std::pair<char *, size_t>> arena; size_t arena_chunk = 0, arena_used = 0;
 };
 
 static int create_impl(CerbHandle *h, const CerbSolverConfig *cfg, const cudaDeviceProp &prop);
@@ -131,6 +143,9 @@ static int create_impl(CerbHandle *h, const CerbSolverConfig *cfg, const cudaDev
     CUDA_TRY(cudaEventCreate(&h->ev0)); CUDA_TRY(cudaEventCreate(&h->ev1));
     const size_t B = h->B, F = h->F, O = h->O;
     h->ws_stride = ws_size(h->F);
+    CUDA_TRY(dmalloc(&h->d_rdesc, B)); CUDA_TRY(dmalloc(&h->d_rfeat, B * F)); CUDA_TRY(dmalloc(&h->d_robs, B * O)); CUDA_TRY(dmalloc(&h->d_rstate, B));
+    CUDA_TRY(dmalloc(&h->d_rpre, B * 10 * RAW_PRE_STRIDE)); CUDA_TRY(dmalloc(&h->d_rlam, B * F)); CUDA_TRY(dmalloc(&h->d_perm, B * F));
+    CUDA_TRY(dmalloc(&h->d_olam, B * F)); CUDA_TRY(dmalloc(&h->d_ostate, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_orep, B));
     CUDA_TRY(dmalloc(&h->d_nfeat, B)); CUDA_TRY(dmalloc(&h->d_fstart, B * F)); CUDA_TRY(dmalloc(&h->d_fnobs, B * F)); CUDA_TRY(dmalloc(&h->d_foff, B * F));
     CUDA_TRY(dmalloc(&h->d_flags, B)); CUDA_TRY(dmalloc(&h->d_stereo, B * O)); CUDA_TRY(dmalloc(&h->d_pmeta, B * PRIOR_META_STRIDE)); CUDA_TRY(dmalloc(&h->d_repi, B * 4));
     CUDA_TRY(dmalloc(&h->d_obs, B * NOBS_PLANES * O)); CUDA_TRY(dmalloc(&h->d_pre, B * 10 * PRE_STRIDE)); CUDA_TRY(dmalloc(&h->d_sinfo, B * 10 * 961));
@@ -138,12 +153,11 @@ static int create_impl(CerbHandle *h, const CerbSolverConfig *cfg, const cudaDev
     CUDA_TRY(dmalloc(&h->d_state, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_state0, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_lam, B * F)); CUDA_TRY(dmalloc(&h->d_lam0, B * F));
     CUDA_TRY(dmalloc(&h->d_repd, B * 2)); CUDA_TRY(dmalloc(&h->d_ws, (size_t)h->grid * h->ws_stride)); CUDA_TRY(dmalloc(&h->d_dbg, 2 * (NR + F) + 8)); CUDA_TRY(dmalloc(&h->d_G, 4));
     CUDA_TRY(dmalloc(&h->d_probe_repi, 4)); CUDA_TRY(dmalloc(&h->d_probe_repd, 2));
-    CUDA_TRY(hmalloc(&h->h_nfeat, B)); CUDA_TRY(hmalloc(&h->h_fstart, B * F)); CUDA_TRY(hmalloc(&h->h_fnobs, B * F)); CUDA_TRY(hmalloc(&h->h_foff, B * F));
-    CUDA_TRY(hmalloc(&h->h_flags, B)); CUDA_TRY(hmalloc(&h->h_stereo, B * O)); CUDA_TRY(hmalloc(&h->h_pmeta, B * PRIOR_META_STRIDE)); CUDA_TRY(hmalloc(&h->h_repi, B * 4));
-    CUDA_TRY(hmalloc(&h->h_obs, B * NOBS_PLANES * O)); CUDA_TRY(hmalloc(&h->h_pre, B * 10 * PRE_STRIDE));
-    CUDA_TRY(hmalloc(&h->h_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_pr, B * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_px0, B * 16 * 9));
-    h->h_perm.assign(B * F, 0);
-    CUDA_TRY(hmalloc(&h->h_state, B * ST_STRIDE)); CUDA_TRY(hmalloc(&h->h_lam, B * F)); CUDA_TRY(hmalloc(&h->h_repd, B * 2)); CUDA_TRY(hmalloc(&h->h_dbg, 2 * (NR + F) + 8));
+    CUDA_TRY(hmalloc(&h->h_rdesc, B)); CUDA_TRY(hmalloc(&h->h_rfeat, B * F)); CUDA_TRY(hmalloc(&h->h_robs, B * O)); CUDA_TRY(hmalloc(&h->h_rstate, B));
+    CUDA_TRY(hmalloc(&h->h_rpre, B * 10 * RAW_PRE_STRIDE)); CUDA_TRY(hmalloc(&h->h_rlam, B * F));
+    CUDA_TRY(hmalloc(&h->h_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_pr, B * PRIOR_LD));
+    CUDA_TRY(hmalloc(&h->h_state, B * ST_STRIDE)); CUDA_TRY(hmalloc(&h->h_lam, B * F)); CUDA_TRY(hmalloc(&h->h_orep, B)); CUDA_TRY(hmalloc(&h->h_dbg, 2 * (NR + F) + 8));
+    h->nfeat.assign(B, 0);
     CUDA_TRY(cudaMemcpy(h->d_G, cfg->g, 3 * sizeof(double), cudaMemcpyHostToDevice));
     return CERB_OK;
 }
@@ -154,11 +168,13 @@ void cerb_destroy(CerbHandle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void *dev[] = {h->d_nfeat, h->d_fstart, h->d_fnobs, h->d_foff, h->d_flags, h->d_stereo, h->d_pmeta, h->d_repi, h->d_obs, h->d_pre, h->d_sinfo, h->d_pJ, h->d_pr,
+    void *dev[] = {h->d_rdesc, h->d_rfeat, h->d_robs, h->d_rstate, h->d_rpre, h->d_rlam, h->d_perm, h->d_olam, h->d_ostate, h->d_orep,
+                   h->d_nfeat, h->d_fstart, h->d_fnobs, h->d_foff, h->d_flags, h->d_stereo, h->d_pmeta, h->d_repi, h->d_obs, h->d_pre, h->d_sinfo, h->d_pJ, h->d_pr,
                    h->d_px0, h->d_pHp, h->d_state, h->d_state0, h->d_lam, h->d_lam0, h->d_repd, h->d_ws, h->d_dbg, h->d_G, h->d_probe_repi, h->d_probe_repd};
     for (void *p : dev) if (p) cudaFree(p);
-    void *hst[] = {h->h_nfeat, h->h_fstart, h->h_fnobs, h->h_foff, h->h_flags, h->h_stereo, h->h_pmeta, h->h_repi, h->h_obs, h->h_pre, h->h_pJ, h->h_pr, h->h_px0,
-                   h->h_state, h->h_lam, h->h_repd, h->h_dbg};
+    for (auto &c : h->arena) cudaFree(c.first);
+    for (auto &r : h->regs) cudaHostUnregister((void *)r.first);
+    void *hst[] = {h->h_rdesc, h->h_rfeat, h->h_robs, h->h_rstate, h->h_rpre, h->h_rlam, h->h_pJ, h->h_pr, h->h_state, h->h_lam, h->h_orep, h->h_dbg};
     for (void *p : hst) if (p) cudaFreeHost(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -170,48 +186,61 @@ void cerb_destroy(CerbHandle *h) {
 
 }  // extern "C"
 
-// ---- host packing ---------------------------------------------------------------------------------------------
-static void pack_preint(const CerbIMULegPreint &p, double *o) {
-    o[PRE_SUM_DT] = p.sum_dt; o[PRE_IMU_ONLY] = 0.0;
-    for (int k = 0; k < 3; k++) { o[PRE_DP + k] = p.delta_p[k]; o[PRE_DV + k] = p.delta_v[k]; o[PRE_BA + k] = p.linearized_ba[k]; o[PRE_BG + k] = p.linearized_bg[k]; }
-    for (int k = 0; k < 4; k++) { o[PRE_DQ + k] = p.delta_q[k]; o[PRE_RHO + k] = p.linearized_rho[k]; }
-    for (int k = 0; k < 12; k++) o[PRE_DEPS + k] = p.delta_epsilon[k];
-    auto J = [&](int r, int c) { return p.jacobian[c * 31 + r]; };   // column-major source
-    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
-        o[PRE_DP_DBA + 3 * a + b] = J(ILO_P + a, ILO_BA + b); o[PRE_DP_DBG + 3 * a + b] = J(ILO_P + a, ILO_BG + b);
-        o[PRE_DQ_DBG + 3 * a + b] = J(ILO_R + a, ILO_BG + b);
-        o[PRE_DV_DBA + 3 * a + b] = J(ILO_V + a, ILO_BA + b); o[PRE_DV_DBG + 3 * a + b] = J(ILO_V + a, ILO_BG + b);
-        for (int k = 0; k < 4; k++) o[PRE_DEP_DBG + 9 * k + 3 * a + b] = J(ILO_EPS1 + 3 * k + a, ILO_BG + b);
-    }
-    for (int k = 0; k < 4; k++) for (int a = 0; a < 3; a++) o[PRE_DEP_DRHO + 3 * k + a] = J(ILO_EPS1 + 3 * k + a, ILO_RHO1 + k);
-    for (int r = 0; r < 31; r++) for (int c = 0; c < 31; c++) o[PRE_INFO + r * 31 + c] = p.covariance[c * 31 + r];
+// ---- host side of an upload: validation + DMA of the caller's arrays as they are ---------------------------------------
+// The descriptors are reference-shaped AoS; csrc/pack_kernels.cuh turns them into the solver's HBM layout on the device.  What the host
+// does per window is (1) validate the descriptor (the device trusts it), (2) get the bytes across PCIe: straight out of the caller's
+// buffers when they lie in memory registered with cerb_register_host_buffer (zero CPU copies; uniformly strided per-window arrays go
+// as ONE 2-D copy per array and chunk), else through pinned staging filled with plain memcpy on a few threads.
+struct StageJob { void *dst; const void *src; size_t bytes; };
+struct DmaOp { void *dst; size_t dpitch; const void *src; size_t spitch, width, height; };
+struct UploadPlan { std::vector<StageJob> stage; std::vector<DmaOp> dma; };
+
+static bool in_registered(const CerbHandle *h, const void *p, size_t bytes) {
+    const uintptr_t a = (uintptr_t)p;
+    for (const auto &r : h->regs) if (a >= r.first && a + bytes <= r.first + r.second) return true;
+    return false;
 }
 
-// IntegrationBase result (USE_LEG == 0) embedded in the 31-row IMU-leg layout: rows / columns P, R, V, BA, BG map to their
-// ILStateOrder slots, the EPS / RHO diagonal of the covariance is the identity (block diagonal => sqrt_info restricted to
-// the 15 kept rows equals LLT(cov15^-1).matrixL()^T) and PRE_IMU_ONLY makes the device drop the EPS / RHO residual rows.
-static const int kImuTo31[15] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 21, 22, 23, 24, 25, 26};
-static void pack_imu_preint(const CerbIMUPreint &p, double *o) {
-    for (int k = 0; k < PRE_STRIDE; k++) o[k] = 0.0;
-    o[PRE_SUM_DT] = p.sum_dt; o[PRE_IMU_ONLY] = 1.0;
-    for (int k = 0; k < 3; k++) { o[PRE_DP + k] = p.delta_p[k]; o[PRE_DV + k] = p.delta_v[k]; o[PRE_BA + k] = p.linearized_ba[k]; o[PRE_BG + k] = p.linearized_bg[k]; }
-    for (int k = 0; k < 4; k++) o[PRE_DQ + k] = p.delta_q[k];
-    auto J = [&](int r, int c) { return p.jacobian[c * 15 + r]; };
-    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
-        o[PRE_DP_DBA + 3 * a + b] = J(0 + a, 9 + b); o[PRE_DP_DBG + 3 * a + b] = J(0 + a, 12 + b);
-        o[PRE_DQ_DBG + 3 * a + b] = J(3 + a, 12 + b);
-        o[PRE_DV_DBA + 3 * a + b] = J(6 + a, 9 + b); o[PRE_DV_DBG + 3 * a + b] = J(6 + a, 12 + b);
+// One logical array of windows [w0, w0 + cn): window w holds `rows` rows of width_of(w) bytes, row r at src_of(w) + r * spitch;
+// device row (w - w0) * rows + r at dst + that * dpitch (stage: the pinned mirror of dst).
+template <class SrcOf, class WidthOf>
+static void plan_rows(const CerbHandle *h, UploadPlan &pl, int w0, int cn, char *dst, char *stage, size_t dpitch, int rows, size_t spitch, SrcOf src_of, WidthOf width_of) {
+    size_t maxw = 0; bool all_reg = true, uniform = true; int nact = 0;
+    ptrdiff_t delta = 0;
+    for (int i = 0; i < cn; i++) {
+        const size_t wd = width_of(w0 + i);
+        if (wd == 0) { uniform = false; continue; }
+        nact++;
+        maxw = std::max(maxw, wd);
+        const char *p = (const char *)src_of(w0 + i);
+        if (!in_registered(h, p, (rows - 1) * spitch + wd)) all_reg = false;
+        if (i > 0 && width_of(w0 + i - 1) != 0) {
+            const ptrdiff_t dl = p - (const char *)src_of(w0 + i - 1);
+            if (i == 1) delta = dl; else if (dl != delta) uniform = false;
+        }
     }
-    for (int r = 0; r < 31; r++) o[PRE_INFO + r * 31 + r] = 1.0;
-    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) o[PRE_INFO + kImuTo31[r] * 31 + kImuTo31[c]] = p.covariance[c * 15 + r];
+    if (nact == 0) return;
+    if (all_reg) {
+        const char *p0 = (const char *)src_of(w0);
+        if (uniform && cn > 1 && nact == cn && delta > 0) {
+            if (rows == 1 && (size_t)delta >= maxw && in_registered(h, p0, (size_t)delta * (cn - 1) + maxw)) { pl.dma.push_back({dst, dpitch, p0, (size_t)delta, maxw, (size_t)cn}); return; }
+            if (rows > 1 && (size_t)delta == rows * spitch && in_registered(h, p0, (size_t)delta * cn - spitch + maxw)) { pl.dma.push_back({dst, dpitch, p0, spitch, maxw, (size_t)rows * cn}); return; }
+        }
+        for (int i = 0; i < cn; i++) { const size_t wd = width_of(w0 + i); if (wd) pl.dma.push_back({dst + (size_t)i * rows * dpitch, dpitch, src_of(w0 + i), rows > 1 ? spitch : wd, wd, (size_t)rows}); }
+        return;
+    }
+    for (int i = 0; i < cn; i++) {
+        const size_t wd = width_of(w0 + i); if (!wd) continue;
+        const char *p = (const char *)src_of(w0 + i);
+        for (int r = 0; r < rows; r++) pl.stage.push_back({stage + ((size_t)i * rows + r) * dpitch, p + (size_t)r * spitch, wd});
+    }
+    pl.dma.push_back({dst, dpitch, stage, dpitch, maxw, (size_t)rows * cn});
 }
 
-static int pack_prior(const CerbPrior &pr, int *meta, double *J, double *r, double *x0) {
-    std::memset(meta, 0, PRIOR_META_STRIDE * sizeof(int));
+static int validate_prior(const CerbPrior &pr) {
     if (!pr.valid) return CERB_OK;
     if (pr.n < 1 || pr.n > CERB_MAX_PRIOR_DIM || pr.num_blocks < 1 || pr.num_blocks > CERB_MAX_PRIOR_BLOCKS || !pr.linearized_jacobians || !pr.linearized_residuals)
         return fail(CERB_ERR_BAD_ARGUMENT, "prior: bad n / num_blocks / null matrices");
-    meta[0] = 1; meta[1] = pr.n; meta[2] = pr.num_blocks;
     bool covered[CERB_MAX_PRIOR_DIM] = {false};          // the kept blocks must tile [0, n) exactly once (the solver's column -> destination map is built from them)
     for (int b = 0; b < pr.num_blocks; b++) {
         for (int c = 0; c < b; c++) if (pr.block_kind[c] == pr.block_kind[b] && pr.block_index[c] == pr.block_index[b]) return fail(CERB_ERR_BAD_ARGUMENT, "prior: duplicate parameter block");
@@ -220,96 +249,110 @@ static int pack_prior(const CerbPrior &pr, int *meta, double *J, double *r, doub
         // the solver keeps Hyy block tridiagonal: a prior may only keep the speed/leg bias of frame 0 (what
         // MARGIN_OLD / MARGIN_SECOND_NEW produce, estimator.cpp:1253-1401)
         if ((kind == CERB_BLOCK_SPEEDBIAS || kind == CERB_BLOCK_LEGBIAS) && index != 0) return fail(CERB_ERR_BAD_ARGUMENT, "prior keeps a speed/leg bias block of a frame other than 0");
-        meta[4 + 3 * b] = kind; meta[5 + 3 * b] = index; meta[6 + 3 * b] = pr.block_col[b];
         const int size = prior_block_size(kind), local = size == 7 ? 6 : size;
         if (pr.block_col[b] < 0 || pr.block_col[b] + local > pr.n) return fail(CERB_ERR_BAD_ARGUMENT, "prior: block column out of range");
         for (int k = 0; k < local; k++) { if (covered[pr.block_col[b] + k]) return fail(CERB_ERR_BAD_ARGUMENT, "prior: overlapping block columns"); covered[pr.block_col[b] + k] = true; }
-        for (int k = 0; k < 9; k++) x0[9 * b + k] = pr.block_x0[b][k];
     }
     for (int k = 0; k < pr.n; k++) if (!covered[k]) return fail(CERB_ERR_BAD_ARGUMENT, "prior: the kept blocks do not cover all n columns");
-    std::memcpy(J, pr.linearized_jacobians, sizeof(double) * pr.n * pr.n);
-    std::memcpy(r, pr.linearized_residuals, sizeof(double) * pr.n);
     return CERB_OK;
 }
 
-static int pack_window(CerbHandle *h, int w, const CerbWindowDesc &d, const CerbWindowState &st) {
-    const int F = h->F, O = h->O;
-    if (d.n_features < 0 || d.n_features > F) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_features over capacity");
-    if (d.n_obs < 0 || d.n_obs > O) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_obs over capacity");
+static int validate_window(const CerbHandle *h, const CerbWindowDesc &d, const CerbWindowState &st) {
+    if (d.n_features < 0 || d.n_features > h->F) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_features over capacity");
+    if (d.n_obs < 0 || d.n_obs > h->O) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_obs over capacity");
     if ((d.n_features && (!d.features || !d.obs || !st.para_Feature)) || (!d.preint && !d.imu_preint)) return fail(CERB_ERR_BAD_ARGUMENT, "window: null pointer");
-    h->h_nfeat[w] = d.n_features;
-    h->h_flags[w] = (d.extrinsic_open ? 1 : 0) | (d.td_open ? 2 : 0) | (d.preint ? 0 : 4);      // bit2: USE_LEG == 0, no leg-bias blocks
-    // Device order: tracks sorted by anchor frame (stable counting sort), so that the solver's feature chunks share one anchor.
-    // The reference's f_manager.feature list is already in first-seen order (feature_manager.cpp:60-92); arbitrary orders are accepted.
-    int cnt[CERB_NUM_FRAMES + 1] = {0};
     for (int f = 0; f < d.n_features; f++) {
         const CerbFeature &ft = d.features[f];
         if (ft.start_frame < 0 || ft.n_obs < 1 || ft.start_frame + ft.n_obs > CERB_NUM_FRAMES || ft.obs_offset < 0 || ft.obs_offset + ft.n_obs > d.n_obs)
             return fail(CERB_ERR_BAD_ARGUMENT, "window: malformed feature track");
-        cnt[ft.start_frame + 1]++;
     }
-    for (int a = 0; a < CERB_NUM_FRAMES; a++) cnt[a + 1] += cnt[a];
-    int *perm = h->h_perm.data() + (size_t)w * F;
-    for (int f = 0; f < d.n_features; f++) perm[cnt[d.features[f].start_frame]++] = f;
-    for (int k = 0; k < d.n_features; k++) {
-        const CerbFeature &ft = d.features[perm[k]];
-        h->h_fstart[(size_t)w * F + k] = ft.start_frame; h->h_fnobs[(size_t)w * F + k] = ft.n_obs; h->h_foff[(size_t)w * F + k] = ft.obs_offset;
-        h->h_lam[(size_t)w * F + k] = st.para_Feature[perm[k]];
-    }
-    double *ob = h->h_obs + (size_t)w * NOBS_PLANES * O;
-    int *sto = h->h_stereo + (size_t)w * O;
-    for (int o = 0; o < d.n_obs; o++) {
-        const CerbObservation &q = d.obs[o];
-        ob[0 * O + o] = q.point[0]; ob[1 * O + o] = q.point[1]; ob[2 * O + o] = q.velocity[0]; ob[3 * O + o] = q.velocity[1];
-        ob[4 * O + o] = q.pointRight[0]; ob[5 * O + o] = q.pointRight[1]; ob[6 * O + o] = q.velocityRight[0]; ob[7 * O + o] = q.velocityRight[1];
-        ob[8 * O + o] = q.cur_td; sto[o] = q.is_stereo;
-    }
-    for (int i = 0; i < CERB_WINDOW_SIZE; i++) {
-        if (d.preint) pack_preint(d.preint[i], h->h_pre + ((size_t)w * 10 + i) * PRE_STRIDE);
-        else pack_imu_preint(d.imu_preint[i], h->h_pre + ((size_t)w * 10 + i) * PRE_STRIDE);
-    }
-    int rc = pack_prior(d.prior, h->h_pmeta + (size_t)w * PRIOR_META_STRIDE, h->h_pJ + (size_t)w * PRIOR_LD * PRIOR_LD, h->h_pr + (size_t)w * PRIOR_LD, h->h_px0 + (size_t)w * 16 * 9);
-    if (rc) return rc;
-    double *s = h->h_state + (size_t)w * ST_STRIDE;
-    std::memcpy(s + ST_POSE, st.para_Pose, sizeof(st.para_Pose));
-    std::memcpy(s + ST_SB, st.para_SpeedBias, sizeof(st.para_SpeedBias));
-    std::memcpy(s + ST_LB, st.para_LegBias, sizeof(st.para_LegBias));
-    std::memcpy(s + ST_EX, st.para_Ex_Pose, sizeof(st.para_Ex_Pose));
-    s[ST_TD] = st.para_Td[0];
-    return CERB_OK;
+    return validate_prior(d.prior);
 }
 
-static int pack_range(CerbHandle *h, int w0, int n, const CerbWindowDesc *descs, const CerbWindowState *states) {
+static void run_stage_jobs(const std::vector<StageJob> &jobs) {
+    if (jobs.empty()) return;
+    size_t total = 0; for (const auto &j : jobs) total += j.bytes;
     unsigned hw = std::thread::hardware_concurrency();
     int nth = (int)std::min<unsigned>(hw ? hw : 1, 16u);
-    if (n < 8) nth = 1;
-    std::vector<int> rcs(nth, 0); std::vector<std::string> errs(nth);
-    auto work = [&](int t) {
-        for (int w = w0 + t; w < w0 + n; w += nth) { int rc = pack_window(h, w, descs[w], states[w]); if (rc) { rcs[t] = rc; errs[t] = g_err; return; } }
-    };
+    if (total < (4u << 20)) nth = 1;
+    auto work = [&](int t) { for (size_t k = t; k < jobs.size(); k += nth) std::memcpy(jobs[k].dst, jobs[k].src, jobs[k].bytes); };
     std::vector<std::thread> th;
     for (int t = 1; t < nth; t++) th.emplace_back(work, t);
     work(0);
     for (auto &t : th) t.join();
-    for (int t = 0; t < nth; t++) if (rcs[t]) return fail(rcs[t], errs[t]);
-    return CERB_OK;
 }
 
-static int pack_all(CerbHandle *h, int n, const CerbWindowDesc *descs, const CerbWindowState *states) { return pack_range(h, 0, n, descs, states); }
-
-// H2D of windows [w0, w0 + n) from the pinned staging buffers on stream s
-static int upload_range(CerbHandle *h, int w0, int n, cudaStream_t s) {
+// validate windows [w0, w0 + cn), move their raw descriptors to the device on stream s (staging only what is not registered)
+static int upload_raw(CerbHandle *h, int w0, int cn, const CerbWindowDesc *descs, const CerbWindowState *states, cudaStream_t s, double *t_stage_ms) {
+    for (int w = w0; w < w0 + cn; w++) { int rc = validate_window(h, descs[w], states[w]); if (rc) return rc; h->nfeat[w] = descs[w].n_features; }
+    UploadPlan pl;
     const size_t F = h->F, O = h->O, W0 = (size_t)w0;
-#define H2D(dst, src, per) CUDA_TRY(cudaMemcpyAsync((dst) + W0 * (per), (src) + W0 * (per), (size_t)n * (per) * sizeof(*(src)), cudaMemcpyHostToDevice, s))
-    H2D(h->d_nfeat, h->h_nfeat, 1); H2D(h->d_fstart, h->h_fstart, F); H2D(h->d_fnobs, h->h_fnobs, F); H2D(h->d_foff, h->h_foff, F);
-    H2D(h->d_flags, h->h_flags, 1); H2D(h->d_stereo, h->h_stereo, O); H2D(h->d_pmeta, h->h_pmeta, (size_t)PRIOR_META_STRIDE);
-    H2D(h->d_obs, h->h_obs, NOBS_PLANES * O); H2D(h->d_pre, h->h_pre, (size_t)10 * PRE_STRIDE);
-    H2D(h->d_pJ, h->h_pJ, (size_t)PRIOR_LD * PRIOR_LD); H2D(h->d_pr, h->h_pr, (size_t)PRIOR_LD); H2D(h->d_px0, h->h_px0, (size_t)16 * 9);
-    H2D(h->d_state0, h->h_state, (size_t)ST_STRIDE); H2D(h->d_lam0, h->h_lam, F);
-#undef H2D
+    auto dv = [&](void *base, size_t per) { return (char *)base + W0 * per; };
+    plan_rows(h, pl, w0, cn, dv(h->d_rdesc, sizeof(CerbWindowDesc)), dv(h->h_rdesc, sizeof(CerbWindowDesc)), sizeof(CerbWindowDesc), 1, 0,
+              [&](int w) { return (const void *)&descs[w]; }, [&](int) { return sizeof(CerbWindowDesc); });
+    plan_rows(h, pl, w0, cn, dv(h->d_rstate, sizeof(CerbWindowState)), dv(h->h_rstate, sizeof(CerbWindowState)), sizeof(CerbWindowState), 1, 0,
+              [&](int w) { return (const void *)&states[w]; }, [&](int) { return sizeof(CerbWindowState); });
+    plan_rows(h, pl, w0, cn, dv(h->d_rfeat, F * sizeof(CerbFeature)), dv(h->h_rfeat, F * sizeof(CerbFeature)), F * sizeof(CerbFeature), 1, 0,
+              [&](int w) { return (const void *)descs[w].features; }, [&](int w) { return (size_t)descs[w].n_features * sizeof(CerbFeature); });
+    plan_rows(h, pl, w0, cn, dv(h->d_robs, O * sizeof(CerbObservation)), dv(h->h_robs, O * sizeof(CerbObservation)), O * sizeof(CerbObservation), 1, 0,
+              [&](int w) { return (const void *)descs[w].obs; }, [&](int w) { return (size_t)descs[w].n_obs * sizeof(CerbObservation); });
+    plan_rows(h, pl, w0, cn, dv(h->d_rlam, F * 8), dv(h->h_rlam, F * 8), F * 8, 1, 0,
+              [&](int w) { return (const void *)states[w].para_Feature; }, [&](int w) { return (size_t)descs[w].n_features * 8; });
+    // preintegration results: the members IMULegFactor::Evaluate reads -- head (33 doubles) and, contiguous in the struct, jacobian columns 21..30 + covariance
+    const size_t pre_pitch = (size_t)RAW_PRE_STRIDE * 8, tail_off = (size_t)(RAW_PRE_HEAD + RAW_PRE_JCOL0 * 31) * 8, tail_w = sizeof(CerbIMULegPreint) - tail_off;
+    static_assert(sizeof(CerbIMULegPreint) == (33 + 2 * 961) * 8, "CerbIMULegPreint layout");
+    static_assert(sizeof(CerbIMUPreint) == 467 * 8 && sizeof(CerbIMUPreint) <= RAW_PRE_STRIDE * 8, "CerbIMUPreint layout");
+    plan_rows(h, pl, w0, cn, dv(h->d_rpre, 10 * pre_pitch), dv(h->h_rpre, 10 * pre_pitch), pre_pitch, CERB_WINDOW_SIZE, sizeof(CerbIMULegPreint),
+              [&](int w) { return (const void *)descs[w].preint; }, [&](int w) { return descs[w].preint ? (size_t)RAW_PRE_HEAD * 8 : (size_t)0; });
+    plan_rows(h, pl, w0, cn, dv(h->d_rpre, 10 * pre_pitch) + RAW_PRE_HEAD * 8, dv(h->h_rpre, 10 * pre_pitch) + RAW_PRE_HEAD * 8, pre_pitch, CERB_WINDOW_SIZE, sizeof(CerbIMULegPreint),
+              [&](int w) { return (const void *)((const char *)descs[w].preint + tail_off); }, [&](int w) { return descs[w].preint ? tail_w : (size_t)0; });
+    plan_rows(h, pl, w0, cn, dv(h->d_rpre, 10 * pre_pitch), dv(h->h_rpre, 10 * pre_pitch), pre_pitch, CERB_WINDOW_SIZE, sizeof(CerbIMUPreint),
+              [&](int w) { return (const void *)descs[w].imu_preint; }, [&](int w) { return descs[w].preint ? (size_t)0 : sizeof(CerbIMUPreint); });
+    const size_t pj_pitch = (size_t)PRIOR_LD * PRIOR_LD * 8;
+    plan_rows(h, pl, w0, cn, dv(h->d_pJ, pj_pitch), dv(h->h_pJ, pj_pitch), pj_pitch, 1, 0,
+              [&](int w) { return (const void *)descs[w].prior.linearized_jacobians; }, [&](int w) { return descs[w].prior.valid ? (size_t)descs[w].prior.n * descs[w].prior.n * 8 : (size_t)0; });
+    plan_rows(h, pl, w0, cn, dv(h->d_pr, PRIOR_LD * 8), dv(h->h_pr, PRIOR_LD * 8), (size_t)PRIOR_LD * 8, 1, 0,
+              [&](int w) { return (const void *)descs[w].prior.linearized_residuals; }, [&](int w) { return descs[w].prior.valid ? (size_t)descs[w].prior.n * 8 : (size_t)0; });
+    const auto t0 = std::chrono::steady_clock::now();
+    run_stage_jobs(pl.stage);
+    if (t_stage_ms) *t_stage_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (const DmaOp &op : pl.dma) {
+        if (op.height == 1) CUDA_TRY(cudaMemcpyAsync(op.dst, op.src, op.width, cudaMemcpyHostToDevice, s));
+        else CUDA_TRY(cudaMemcpy2DAsync(op.dst, op.dpitch, op.src, op.spitch, op.width, op.height, cudaMemcpyHostToDevice, s));
+    }
+    h->last_dma_ops += (int)pl.dma.size(); h->last_staged_bytes += [&] { size_t t = 0; for (const auto &j : pl.stage) t += j.bytes; return t; }();
     return CERB_OK;
 }
-static int upload(CerbHandle *h, int n) { int rc = upload_range(h, 0, n, h->stream); h->n = n; h->solved = false; return rc; }
+
+// device pack of windows [w0, w0 + cn) (after their raw descriptors have arrived) on stream s
+static int enqueue_pack(CerbHandle *h, int w0, int cn, cudaStream_t s) {
+    PackParams P;
+    const size_t W0 = (size_t)w0, F = h->F, O = h->O;
+    P.n = cn; P.maxF = h->F; P.maxObs = h->O;
+    P.rdesc = h->d_rdesc + W0; P.rfeat = h->d_rfeat + W0 * F; P.robs = h->d_robs + W0 * O; P.rpre = h->d_rpre + W0 * 10 * RAW_PRE_STRIDE; P.rstate = h->d_rstate + W0; P.rlam = h->d_rlam + W0 * F;
+    P.n_features = h->d_nfeat + W0; P.feat_start = h->d_fstart + W0 * F; P.feat_nobs = h->d_fnobs + W0 * F; P.feat_off = h->d_foff + W0 * F; P.flags = h->d_flags + W0;
+    P.obs_stereo = h->d_stereo + W0 * O; P.prior_meta = h->d_pmeta + W0 * PRIOR_META_STRIDE; P.perm = h->d_perm + W0 * F;
+    P.obs = h->d_obs + W0 * NOBS_PLANES * O; P.pre = h->d_pre + W0 * 10 * PRE_STRIDE; P.prior_x0 = h->d_px0 + W0 * 16 * 9; P.state0 = h->d_state0 + W0 * ST_STRIDE; P.lam0 = h->d_lam0 + W0 * F;
+    CERB_LAUNCH(pack_kernel, std::min(cn, 8 * h->sm_count), PACK_THREADS, 0, s, P);
+    CUDA_TRY(cudaGetLastError());
+    return CERB_OK;
+}
+static int upload(CerbHandle *h, int n, const CerbWindowDesc *descs, const CerbWindowState *states) {
+    h->last_dma_ops = 0; h->last_staged_bytes = 0;
+    int rc = upload_raw(h, 0, n, descs, states, h->stream, nullptr); if (rc) return rc;
+    rc = enqueue_pack(h, 0, n, h->stream); if (rc) return rc;
+    h->n = n; h->solved = false; h->perm_valid = false;
+    return CERB_OK;
+}
+// device slot -> caller's feature index of the resident batch (computed by the pack kernel; fetched on demand by the probes / feature passes)
+static int ensure_perm(CerbHandle *h) {
+    if (h->perm_valid) return CERB_OK;
+    h->h_perm.resize((size_t)h->B * h->F);
+    CUDA_TRY(cudaMemcpyAsync(h->h_perm.data(), h->d_perm, (size_t)h->n * h->F * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->perm_valid = true;
+    return CERB_OK;
+}
 
 static SolveParams make_params(CerbHandle *h, int w0, int n, int max_iters, double *dbg, int dbg_window) {
     SolveParams P;
@@ -370,31 +413,25 @@ static int collect_time(CerbHandle *h) {
 static int download(CerbHandle *h, CerbWindowState *states, CerbSolveReport *reports) {
     const int n = h->n; const size_t F = h->F;
     cudaStream_t s = h->stream;
-    CUDA_TRY(cudaMemcpyAsync(h->h_state, h->d_state, (size_t)n * ST_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(h->h_lam, h->d_lam, n * F * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(h->h_repi, h->d_repi, (size_t)n * 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(h->h_repd, h->d_repd, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    UnpackParams U;
+    U.n = n; U.maxF = h->F; U.n_features = h->d_nfeat; U.perm = h->d_perm; U.rep_i = h->d_repi; U.rep_d = h->d_repd;
+    U.lam = h->solved ? h->d_lam : h->d_lam0; U.state = h->solved ? h->d_state : h->d_state0;
+    U.olam = h->d_olam; U.orep = h->d_orep; U.ostate = h->d_ostate;
+    CERB_LAUNCH(unpack_kernel, std::min(n, 8 * h->sm_count), PACK_THREADS, 0, s, U);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h->h_state, h->d_ostate, (size_t)n * ST_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_lam, h->d_olam, n * F * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_orep, h->d_orep, (size_t)n * sizeof(CerbSolveReport), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     int rc = collect_time(h); if (rc) return rc;
     int status = CERB_OK;
     for (int w = 0; w < n; w++) {
         if (states) {
-            CerbWindowState &st = states[w];
-            const double *q = h->h_state + (size_t)w * ST_STRIDE;
-            std::memcpy(st.para_Pose, q + ST_POSE, sizeof(st.para_Pose));
-            std::memcpy(st.para_SpeedBias, q + ST_SB, sizeof(st.para_SpeedBias));
-            std::memcpy(st.para_LegBias, q + ST_LB, sizeof(st.para_LegBias));
-            std::memcpy(st.para_Ex_Pose, q + ST_EX, sizeof(st.para_Ex_Pose));
-            st.para_Td[0] = q[ST_TD];
-            const int nf = h->h_nfeat[w];
-            if (st.para_Feature) { const int *perm = h->h_perm.data() + (size_t)w * F; for (int k = 0; k < nf; k++) st.para_Feature[perm[k]] = h->h_lam[(size_t)w * F + k]; }
+            std::memcpy(&states[w], h->h_state + (size_t)w * ST_STRIDE, ST_SIZE * sizeof(double));        // para_Pose .. para_Td: contiguous, same order
+            if (states[w].para_Feature && h->nfeat[w]) std::memcpy(states[w].para_Feature, h->h_lam + (size_t)w * F, (size_t)h->nfeat[w] * sizeof(double));
         }
-        if (reports) {
-            CerbSolveReport &r = reports[w];
-            r.iterations = h->h_repi[4 * w]; r.num_successful_steps = h->h_repi[4 * w + 1]; r.termination = h->h_repi[4 * w + 2]; r.status = h->h_repi[4 * w + 3];
-            r.initial_cost = h->h_repd[2 * w]; r.final_cost = h->h_repd[2 * w + 1];
-        }
-        if (h->h_repi[4 * w + 3] != 0) status = CERB_ERR_NON_FINITE;
+        if (reports) reports[w] = h->h_orep[w];
+        if (h->h_orep[w].status != 0) status = CERB_ERR_NON_FINITE;
     }
     if (status) return fail(status, "at least one window produced a non-finite cost (see reports[].status)");
     return CERB_OK;
@@ -402,13 +439,31 @@ static int download(CerbHandle *h, CerbWindowState *states, CerbSolveReport *rep
 
 extern "C" {
 
+int cerb_register_host_buffer(CerbHandle *h, void *ptr, size_t bytes) {
+    if (!h || !ptr || !bytes) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_register_host_buffer: null argument");
+    CERB_DEVICE(h);
+    CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    h->regs.emplace_back((uintptr_t)ptr, bytes);
+    return CERB_OK;
+}
+int cerb_unregister_host_buffer(CerbHandle *h, void *ptr) {
+    if (!h || !ptr) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_unregister_host_buffer: null argument");
+    CERB_DEVICE(h);
+    for (size_t k = 0; k < h->regs.size(); k++) if (h->regs[k].first == (uintptr_t)ptr) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+        CUDA_TRY(cudaHostUnregister(ptr));
+        h->regs.erase(h->regs.begin() + k);
+        return CERB_OK;
+    }
+    return fail(CERB_ERR_BAD_ARGUMENT, "cerb_unregister_host_buffer: not registered with this handle");
+}
+
 int cerb_batch_upload(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, const CerbWindowState *states) {
     if (!h || !descs || !states) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
     CERB_DEVICE(h);
     if (n < 1 || n > h->B) return fail(CERB_ERR_BAD_ARGUMENT, "batch size over capacity");
     CUDA_TRY(cudaStreamSynchronize(h->stream));          // staging buffers may still be in flight
-    int rc = pack_all(h, n, descs, states); if (rc) return rc;
-    return upload(h, n);
+    return upload(h, n, descs, states);
 }
 int cerb_batch_solve_resident(CerbHandle *h) {
     if (!h) return fail(CERB_ERR_BAD_ARGUMENT, "null handle");
@@ -435,51 +490,48 @@ int cerb_last_solve_stats(CerbHandle *h, double *kernel_ms, int32_t *kernel_laun
     if (kernel_launches) *kernel_launches = h->last_launches;
     return CERB_OK;
 }
+int cerb_last_upload_stats(CerbHandle *h, int32_t *dma_ops, int64_t *staged_bytes) {
+    if (!h) return fail(CERB_ERR_BAD_ARGUMENT, "null handle");
+    if (dma_ops) *dma_ops = h->last_dma_ops;
+    if (staged_bytes) *staged_bytes = (int64_t)h->last_staged_bytes;
+    return CERB_OK;
+}
 int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, CerbWindowState *states, CerbSolveReport *reports) {
     if (!h || !descs || !states) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
     CERB_DEVICE(h);
     if (n < 1 || n > h->B) return fail(CERB_ERR_BAD_ARGUMENT, "batch size over capacity");
     CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
     int rc = collect_time(h); if (rc) return rc;
-    // Pipeline in chunks that are whole waves of the persistent grid (first chunk one wave so the GPU starts early): the
-    // host packs chunk c + 1 and the copy stream moves it while the compute stream solves chunk c.
+    // Pipeline in chunks that are whole waves of the persistent grid (first chunk one wave so the GPU starts early): the copy stream
+    // moves chunk c + 1 (and the host stages it, if its buffers are not registered) while the compute stream packs and solves chunk c.
     const int wave = h->grid;
     int bounds[9], nch = 0; bounds[0] = 0;
     if (n <= 2 * wave) { bounds[1] = n; nch = 1; }
     else {
         int pos = wave; bounds[++nch] = pos;
-        // <= 3 more chunks of whole waves: large copies run at ~2x the PCIe rate of wave-sized ones, and with two waves per chunk the
-        // solve of a chunk (2 x 3.3 ms) still covers the pack + copy of the next one
         const int rest = n - pos, per = ((rest + 2) / 3 + wave - 1) / wave * wave;
         while (pos < n && nch < 7) { pos = std::min(n, pos + per); bounds[++nch] = pos; }
         bounds[nch] = n;
     }
-    h->n = n;
+    h->n = n; h->perm_valid = false;
+    h->last_dma_ops = 0; h->last_staged_bytes = 0;
     const bool trace = std::getenv("CERB_TRACE") != nullptr;            // host timeline of the pipeline on stderr (diagnostics)
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_begin = now(); double t_pack = 0.0, t_enq = 0.0;
+    const double t_begin = now(); double t_stage = 0.0;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     for (int c = 0; c < nch; c++) {
         const int w0 = bounds[c], cn = bounds[c + 1] - bounds[c];
-        // the first chunk is on the critical path (nothing to overlap with yet): pack and copy it in quarters so that the copy of
-        // one quarter runs while the next one is packed
-        const int nsub = (c == 0 && cn >= 32) ? 4 : 1;
-        for (int q = 0; q < nsub; q++) {
-            const int s0 = w0 + (int)((long)cn * q / nsub), s1 = w0 + (int)((long)cn * (q + 1) / nsub);
-            const double ta = now();
-            rc = pack_range(h, s0, s1 - s0, descs, states); if (rc) return rc;
-            const double tb = now();
-            rc = upload_range(h, s0, s1 - s0, h->copy_stream); if (rc) return rc;
-            t_pack += tb - ta; t_enq += now() - tb;
-        }
+        rc = upload_raw(h, w0, cn, descs, states, h->copy_stream, &t_stage); if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_copy[c], h->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy[c], 0));
+        rc = enqueue_pack(h, w0, cn, h->stream); if (rc) return rc;
         rc = enqueue_solve(h, w0, cn, h->cfg.max_num_iterations, nullptr, -1); if (rc) return rc;
     }
-    CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->ev_pending = true; h->last_launches = 3 * nch;
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->ev_pending = true; h->last_launches = 4 * nch + 1;      // + the unpack kernel of the download
     const double t_issued = now();
     rc = download(h, states, reports);
-    if (trace) std::fprintf(stderr, "[cerb_solve_batch] n=%d chunks=%d pack %.2f ms, enqueue copies %.2f ms, all issued at %.2f ms, done at %.2f ms\n", n, nch, t_pack, t_enq, t_issued - t_begin, now() - t_begin);
+    if (trace) std::fprintf(stderr, "[cerb_solve_batch] n=%d chunks=%d dma ops %d, staged %.1f MB in %.2f ms, all issued at %.2f ms, done at %.2f ms\n", n, nch, h->last_dma_ops,
+                            h->last_staged_bytes / 1e6, t_stage, t_issued - t_begin, now() - t_begin);
     return rc;
 }
 int cerb_solve_window(CerbHandle *h, const CerbWindowDesc *desc, CerbWindowState *state, CerbSolveReport *report) {
@@ -489,13 +541,14 @@ int cerb_solve_window(CerbHandle *h, const CerbWindowDesc *desc, CerbWindowState
 int cerb_debug_linearize(CerbHandle *h, int32_t w, double *cost, double *gradient, double *jtj_diag, int32_t n_alloc) {
     if (!h || w < 0 || w >= h->n) return fail(CERB_ERR_BAD_ARGUMENT, "bad window index");
     CERB_DEVICE(h);
-    const int nf = h->h_nfeat[w], F = h->F;
+    const int nf = h->nfeat[w], F = h->F;
     if (n_alloc < NR + nf) return fail(CERB_ERR_BAD_ARGUMENT, "n_alloc too small");
+    int rc = ensure_perm(h); if (rc) return rc;
     const size_t cnt = 2 * (size_t)(NR + F) + 8;
     CUDA_TRY(cudaMemsetAsync(h->d_dbg, 0, cnt * sizeof(double), h->stream));
     // Read-only with respect to the resident batch: only window w is linearised, at the solved states if the batch has been solved
     // (else at the uploaded initial states, which are first copied into place), with the reports going to scratch.
-    int rc = enqueue_solve(h, w, 1, 0, h->d_dbg, 0, !h->solved, true); if (rc) return rc;
+    rc = enqueue_solve(h, w, 1, 0, h->d_dbg, 0, !h->solved, true); if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(h->h_dbg, h->d_dbg, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (cost) *cost = h->h_dbg[0];
@@ -519,16 +572,58 @@ extern "C" int cerb_prof_phase_cycles(unsigned long long *out48) {
 #endif
 
 // ---- factor-family evaluators ----------------------------------------------------------------------------------
-struct DevBuf {   // RAII scratch
-    std::vector<void *> ptrs;
-    ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
+struct DevBuf {   // bump allocator over the handle's scratch arena (reset per entry point; chunks are kept, so steady state does no cudaMalloc)
+    CerbHandle *h;
+    explicit DevBuf(CerbHandle *h_) : h(h_) { h->arena_chunk = 0; h->arena_used = 0; }
+    void *raw(size_t bytes) {
+        bytes = (std::max<size_t>(bytes, 8) + 255) & ~(size_t)255;
+        while (h->arena_chunk < h->arena.size() && h->arena_used + bytes > h->arena[h->arena_chunk].second) { h->arena_chunk++; h->arena_used = 0; }
+        if (h->arena_chunk == h->arena.size()) {
+            const size_t sz = std::max<size_t>(bytes, (size_t)16 << 20);
+            char *p = nullptr; if (cudaMalloc((void **)&p, sz) != cudaSuccess) return nullptr;
+            h->arena.emplace_back(p, sz); h->arena_used = 0;
+        }
+        void *r = h->arena[h->arena_chunk].first + h->arena_used; h->arena_used += bytes;
+        return r;
+    }
     double *up(const double *src, size_t n, cudaStream_t s) {
-        double *d = nullptr; if (cudaMalloc((void **)&d, std::max<size_t>(n, 1) * sizeof(double)) != cudaSuccess) return nullptr;
-        ptrs.push_back(d);
+        double *d = (double *)raw(n * sizeof(double)); if (!d) return nullptr;
         if (src) cudaMemcpyAsync(d, src, n * sizeof(double), cudaMemcpyHostToDevice, s);
         return d;
     }
+    int *upi(const int *src, size_t n, cudaStream_t s) {
+        int *d = (int *)raw(n * sizeof(int)); if (!d) return nullptr;
+        if (src) cudaMemcpyAsync(d, src, n * sizeof(int), cudaMemcpyHostToDevice, s);
+        return d;
+    }
 };
+
+// host views of the device pack functions (one source of truth for the record layout): used by the evaluator entry points
+static void pack_preint(const CerbIMULegPreint &p, double *o) {
+    const double *sdb = reinterpret_cast<const double *>(&p);
+    std::vector<double> raw(RAW_PRE_STRIDE);
+    for (int k = 0; k < RAW_PRE_STRIDE; k++) raw[k] = k < RAW_PRE_HEAD ? sdb[k] : sdb[k + RAW_PRE_JCOL0 * 31];
+    for (int k = 0; k < PRE_STRIDE; k++) o[k] = pack_pre_leg(raw.data(), k);
+}
+static void pack_imu_preint(const CerbIMUPreint &p, double *o) {
+    const double *raw = reinterpret_cast<const double *>(&p);
+    for (int k = 0; k < PRE_STRIDE; k++) o[k] = pack_pre_imu(raw, k);
+}
+static const int kImuTo31[15] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 21, 22, 23, 24, 25, 26};
+static int pack_prior(const CerbPrior &pr, int *meta, double *J, double *r, double *x0) {
+    std::memset(meta, 0, PRIOR_META_STRIDE * sizeof(int));
+    if (!pr.valid) return CERB_OK;
+    int rc = validate_prior(pr); if (rc) return rc;
+    meta[0] = 1; meta[1] = pr.n; meta[2] = pr.num_blocks;
+    for (int b = 0; b < pr.num_blocks; b++) {
+        meta[4 + 3 * b] = pr.block_kind[b]; meta[5 + 3 * b] = pr.block_index[b]; meta[6 + 3 * b] = pr.block_col[b];
+        for (int k = 0; k < 9; k++) x0[9 * b + k] = pr.block_x0[b][k];
+    }
+    std::memcpy(J, pr.linearized_jacobians, sizeof(double) * pr.n * pr.n);
+    std::memcpy(r, pr.linearized_residuals, sizeof(double) * pr.n);
+    return CERB_OK;
+}
+
 
 int cerb_eval_projection(CerbHandle *h, int32_t kind, int32_t n, const double *pose_i, const double *pose_j, const double *ex0, const double *ex1,
                          const double *inv_dep, const double *td, const double *pts_i, const double *pts_j, const double *vel_i, const double *vel_j,
@@ -537,7 +632,7 @@ int cerb_eval_projection(CerbHandle *h, int32_t kind, int32_t n, const double *p
     CERB_DEVICE(h);
     if (kind != CERB_PROJ_ONE_FRAME_TWO_CAM && (!pose_i || !pose_j)) return fail(CERB_ERR_BAD_ARGUMENT, "poses required");
     if (kind != CERB_PROJ_TWO_FRAME_ONE_CAM && !ex1) return fail(CERB_ERR_BAD_ARGUMENT, "ex1 required");
-    cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
+    cudaStream_t s = h->stream; DevBuf B(h); const size_t N = n;
     const int JS = kind == 0 ? 46 : (kind == 1 ? 60 : 32);
     double *dpi = pose_i ? B.up(pose_i, 7 * N, s) : nullptr, *dpj = pose_j ? B.up(pose_j, 7 * N, s) : nullptr;
     double *de0 = B.up(ex0, 7 * N, s), *de1 = ex1 ? B.up(ex1, 7 * N, s) : nullptr;
@@ -558,7 +653,7 @@ int cerb_eval_projection(CerbHandle *h, int32_t kind, int32_t n, const double *p
 int cerb_eval_imu_leg(CerbHandle *h, int32_t n, const CerbIMULegPreint *preint, const double *params, double *residuals, double *jacobians, double *sqrt_info) {
     if (!h || n < 1 || !preint || !params) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_imu_leg: bad argument");
     CERB_DEVICE(h);
-    cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
+    cudaStream_t s = h->stream; DevBuf B(h); const size_t N = n;
     std::vector<double> packed(N * PRE_STRIDE, 0.0);
     for (int k = 0; k < n; k++) pack_preint(preint[k], packed.data() + (size_t)k * PRE_STRIDE);
     double *dpre = B.up(packed.data(), N * PRE_STRIDE, s), *dsi = B.up(nullptr, N * 961, s), *dpar = B.up(params, 40 * N, s);
@@ -577,7 +672,7 @@ int cerb_eval_imu_leg(CerbHandle *h, int32_t n, const CerbIMULegPreint *preint, 
 int cerb_eval_imu(CerbHandle *h, int32_t n, const CerbIMUPreint *preint, const double *params, double *residuals, double *jacobians, double *sqrt_info) {
     if (!h || n < 1 || !preint || !params) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_eval_imu: bad argument");
     CERB_DEVICE(h);
-    cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
+    cudaStream_t s = h->stream; DevBuf B(h); const size_t N = n;
     std::vector<double> packed(N * PRE_STRIDE), p40(N * 40, 0.0);
     for (int k = 0; k < n; k++) {
         pack_imu_preint(preint[k], packed.data() + (size_t)k * PRE_STRIDE);
@@ -618,11 +713,11 @@ int cerb_eval_prior(CerbHandle *h, const CerbPrior *prior, const CerbWindowState
     std::memcpy(st.data() + ST_LB, state->para_LegBias, sizeof(state->para_LegBias)); std::memcpy(st.data() + ST_EX, state->para_Ex_Pose, sizeof(state->para_Ex_Pose));
     st[ST_TD] = state->para_Td[0];
     size_t jtot = 0; for (int b = 0; b < prior->num_blocks; b++) jtot += (size_t)prior->n * prior_block_size(prior->block_kind[b]);
-    cudaStream_t s = h->stream; DevBuf B;
+    cudaStream_t s = h->stream; DevBuf B(h);
     double *dJ = B.up(J.data(), J.size(), s), *dr0 = B.up(r.data(), r.size(), s), *dx0 = B.up(x0.data(), x0.size(), s), *dst = B.up(st.data(), st.size(), s);
     double *dres = B.up(nullptr, PRIOR_LD, s), *djac = jacobians ? B.up(nullptr, jtot, s) : nullptr;
-    int *dmeta = nullptr; CUDA_TRY(cudaMalloc((void **)&dmeta, PRIOR_META_STRIDE * sizeof(int))); B.ptrs.push_back(dmeta);
-    CUDA_TRY(cudaMemcpyAsync(dmeta, meta.data(), PRIOR_META_STRIDE * sizeof(int), cudaMemcpyHostToDevice, s));
+    int *dmeta = B.upi(meta.data(), PRIOR_META_STRIDE, s);
+    if (!dJ || !dr0 || !dx0 || !dst || !dres || !dmeta || (jacobians && !djac)) return fail(CERB_ERR_CUDA, "device allocation failed");
     CERB_LAUNCH(prior_eval_kernel, 1, 128, 0, s, (const double *)dJ, (const double *)dr0, (const int *)dmeta, (const double *)dx0, (const double *)dst, dres, djac);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(residuals, dres, prior->n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -635,7 +730,7 @@ int cerb_a1_kinematics(CerbHandle *h, int32_t n, const double *q, const double *
                        double *dJ_dq, double *dJ_drho) {
     if (!h || n < 1 || !q || !rho_opt || !rho_fix) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_a1_kinematics: bad argument");
     CERB_DEVICE(h);
-    cudaStream_t s = h->stream; DevBuf B; const size_t N = n;
+    cudaStream_t s = h->stream; DevBuf B(h); const size_t N = n;
     double *dq = B.up(q, 3 * N, s), *dro = B.up(rho_opt, N, s), *drf = B.up(rho_fix, 4 * N, s);
     double *dfk = fk ? B.up(nullptr, 3 * N, s) : nullptr, *dj = jac ? B.up(nullptr, 9 * N, s) : nullptr, *ddf = dfk_drho ? B.up(nullptr, 3 * N, s) : nullptr;
     double *djq = dJ_dq ? B.up(nullptr, 27 * N, s) : nullptr, *djr = dJ_drho ? B.up(nullptr, 9 * N, s) : nullptr;
@@ -656,9 +751,9 @@ static int feature_pass(CerbHandle *h, int which, double param, double *out, int
     CERB_DEVICE(h);
     if (h->n < 1) return fail(CERB_ERR_BAD_ARGUMENT, "no resident batch");
     const int n = h->n, F = h->F;
-    cudaStream_t s = h->stream; DevBuf B;
-    double *d_out = B.up(nullptr, (size_t)n * F, s);
-    if (!d_out) return fail(CERB_ERR_CUDA, "device allocation failed");
+    cudaStream_t s = h->stream; DevBuf B(h);
+    double *d_out = B.up(nullptr, (size_t)n * F, s), *d_perm_out = B.up(nullptr, (size_t)n * F, s);
+    if (!d_out || !d_perm_out) return fail(CERB_ERR_CUDA, "device allocation failed");
     const int threads = 128, blocks = (n * F + threads - 1) / threads;
     const double *d_st = h->solved ? h->d_state : h->d_state0, *d_lm = h->solved ? h->d_lam : h->d_lam0;
     if (which == 0)
@@ -667,18 +762,17 @@ static int feature_pass(CerbHandle *h, int which, double param, double *out, int
     else
         CERB_LAUNCH(triangulate_kernel, blocks, threads, 0, s, n, F, h->O, (const int *)h->d_nfeat, (const int *)h->d_fstart, (const int *)h->d_fnobs, (const int *)h->d_foff,
                     (const double *)h->d_obs, (const int *)h->d_stereo, d_st, d_lm, param, d_out);
+    CERB_LAUNCH(unpermute_kernel, blocks, threads, 0, s, n, F, 1, (const int *)h->d_nfeat, (const int *)h->d_perm, (const double *)d_out, d_perm_out);      // device slot -> caller's feature index
     CUDA_TRY(cudaGetLastError());
     std::vector<double> tmp((size_t)n * F);
-    CUDA_TRY(cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), d_perm_out, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    for (int w = 0; w < n; w++) {       // device slot -> caller's feature index
-        const int *perm = h->h_perm.data() + (size_t)w * F;
-        for (int k = 0; k < h->h_nfeat[w]; k++) {
-            const double v = tmp[(size_t)w * F + k];
-            out[(size_t)w * F + perm[k]] = v;
-            if (remove) remove[(size_t)w * F + perm[k]] = (v * param > 3.0) ? 1 : 0;
+    for (int w = 0; w < n; w++)
+        for (int f = 0; f < h->nfeat[w]; f++) {
+            const double v = tmp[(size_t)w * F + f];
+            out[(size_t)w * F + f] = v;
+            if (remove) remove[(size_t)w * F + f] = (v * param > 3.0) ? 1 : 0;
         }
-    }
     return CERB_OK;
 }
 int cerb_batch_outlier_errors(CerbHandle *h, double focal_length, double *ave_err, int32_t *remove) { return feature_pass(h, 0, focal_length, ave_err, remove); }
@@ -691,11 +785,11 @@ int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t 
     const size_t pos = (size_t)m + n, N = n_windows;
     int grid = std::min<int>(n_windows, 2 * h->sm_count);
     grid = (int)std::max<size_t>(1, std::min<size_t>(grid, ((size_t)4 << 30) / (marg_ws_doubles(m, n) * sizeof(double))));      // <= 4 GB of per-CTA workspace
-    cudaStream_t s = h->stream; DevBuf B;
+    cudaStream_t s = h->stream; DevBuf B(h);
     double *dA = B.up(A, N * pos * pos, s), *db = B.up(b, N * pos, s), *dws = B.up(nullptr, (size_t)grid * marg_ws_doubles(m, n), s);
     double *dJ = B.up(nullptr, N * n * n, s), *dr = B.up(nullptr, N * n, s), *dsw = B.up(nullptr, N, s);     // dsw: 2 ints per window
     if (!dA || !db || !dws || !dJ || !dr || !dsw) return fail(CERB_ERR_CUDA, "device allocation failed");
-    CERB_LAUNCH(marg_schur_kernel, grid, MARG_THREADS, marg_smem_bytes(m, n), s, (int)n_windows, (int)m, (int)n, (const double *)dA, (const double *)db, eps, dws, dJ, dr, (int *)dsw);
+    CERB_LAUNCH(marg_schur_kernel, grid, MARG_THREADS, marg_smem_bytes(m, n), s, (int)n_windows, (int)m, (int)n, (const int *)nullptr, (const double *)dA, 0L, (const double *)db, 0L, eps, dws, dJ, 0L, dr, 0L, (int *)dsw);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(linearized_jacobians, dJ, N * n * n * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(linearized_residuals, dr, N * n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -710,23 +804,22 @@ int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_
     if (h->n < 1) return fail(CERB_ERR_BAD_ARGUMENT, "no resident batch");
     const int n = h->n, F = h->F;
     const size_t N = (size_t)n * F;
-    cudaStream_t s = h->stream; DevBuf B;
-    double *d_out = B.up(nullptr, 3 * N, s);
-    if (!d_out) return fail(CERB_ERR_CUDA, "device allocation failed");
+    cudaStream_t s = h->stream; DevBuf B(h);
+    double *d_out = B.up(nullptr, 3 * N, s), *d_perm_out = B.up(nullptr, 3 * N, s);
+    if (!d_out || !d_perm_out) return fail(CERB_ERR_CUDA, "device allocation failed");
     const double *d_st = h->solved ? h->d_state : h->d_state0, *d_lm = h->solved ? h->d_lam : h->d_lam0;
     CERB_LAUNCH(shift_depth_kernel, (int)((N + 127) / 128), 128, 0, s, n, F, h->O, (const int *)h->d_nfeat, (const int *)h->d_fstart, (const int *)h->d_fnobs, (const int *)h->d_foff,
                 (const double *)h->d_obs, d_st, d_lm, init_depth, d_out);
+    CERB_LAUNCH(unpermute_kernel, (int)((N + 127) / 128), 128, 0, s, n, F, 3, (const int *)h->d_nfeat, (const int *)h->d_perm, (const double *)d_out, d_perm_out);
     CUDA_TRY(cudaGetLastError());
     std::vector<double> tmp(3 * N);
-    CUDA_TRY(cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), d_perm_out, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    for (int w = 0; w < n; w++) {
-        const int *perm = h->h_perm.data() + (size_t)w * F;
-        for (int k = 0; k < h->h_nfeat[w]; k++) {
-            const size_t src = (size_t)w * F + k, dst = (size_t)w * F + perm[k];
-            new_start_frame[dst] = (int32_t)tmp[src]; depth[dst] = tmp[N + src]; keep[dst] = (int32_t)tmp[2 * N + src];
+    for (int w = 0; w < n; w++)
+        for (int f = 0; f < h->nfeat[w]; f++) {
+            const size_t q = (size_t)w * F + f;
+            new_start_frame[q] = (int32_t)tmp[q]; depth[q] = tmp[N + q]; keep[q] = (int32_t)tmp[2 * N + q];
         }
-    }
     return CERB_OK;
 }
 
@@ -761,11 +854,10 @@ static int preintegrate_impl(CerbHandle *h, const CerbPreintConfig *cfg, int32_t
         }
         off += q.n_samples;
     }
-    cudaStream_t s = h->stream; DevBuf B;
+    cudaStream_t s = h->stream; DevBuf B(h);
     double *dj = B.up(hj.data(), hj.size(), s), *ds = B.up(hs.data(), hs.size(), s), *dout = B.up(nullptr, (size_t)n * PRE_STRIDE, s), *dfull = B.up(nullptr, (size_t)n * 1922, s);
-    int *di = nullptr; CUDA_TRY(cudaMalloc((void **)&di, hi.size() * sizeof(int))); B.ptrs.push_back(di);
-    if (!dj || !ds || !dout || !dfull) return fail(CERB_ERR_CUDA, "device allocation failed");
-    CUDA_TRY(cudaMemcpyAsync(di, hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    int *di = B.upi(hi.data(), hi.size(), s);
+    if (!dj || !ds || !dout || !dfull || !di) return fail(CERB_ERR_CUDA, "device allocation failed");
     CERB_LAUNCH(preintegrate_kernel, n, 128, 0, s, P, (int)n, (const double *)dj, (const int *)di, (const double *)ds, dout, dfull);
     CUDA_TRY(cudaGetLastError());
     std::vector<double> ho((size_t)n * PRE_STRIDE), hf((size_t)n * 1922);

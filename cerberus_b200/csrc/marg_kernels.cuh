@@ -110,16 +110,21 @@ CERB_D int jacobi_eig(double *M, double *V, int k, double *cs, int *flag) {
 
 // A [n_windows][(m + n)^2] row-major (dropped block first), b [n_windows][m + n]; lin_J [n_windows][n * n] column-major,
 // lin_r [n_windows][n]; ws [gridDim.x][marg_ws_doubles(m, n)]; sweeps [n_windows][2] (diagnostics, may be null)
-CERB_GLOBAL void marg_schur_kernel(int n_windows, int m, int n, const double *A_all, const double *b_all, double eps, double *ws_all,
-                                   double *lin_J, double *lin_r, int *sweeps) {
+// dims (optional): per-window sizes [n_windows][4] = m, n, status (only status == 1 windows are processed), -; then mmax / nmax bound them
+// and A / b / lin_J / lin_r are strided by A_stride / b_stride / J_stride / r_stride doubles per window (0: tight, from m and n)
+CERB_GLOBAL void marg_schur_kernel(int n_windows, int mmax, int nmax, const int *dims, const double *A_all, long A_stride, const double *b_all, long b_stride, double eps,
+                                   double *ws_all, double *lin_J, long J_stride, double *lin_r, long r_stride, int *sweeps) {
     CERB_DYN_SMEM(double, sm);
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int pos = m + n, nc = n + 1, kmax = m > n ? m : n;
+    const int kmax = mmax > nmax ? mmax : nmax;
     double *cs = sm; int *flag = reinterpret_cast<int *>(sm + kmax + 1);
-    double *M1 = ws_all + (size_t)blockIdx.x * marg_ws_doubles(m, n), *V1 = M1 + (size_t)m * m, *Y = V1 + (size_t)m * m, *X = Y + (size_t)m * nc;
-    double *T2 = X + (size_t)m * nc, *M2 = T2 + (size_t)n * n, *V2 = M2 + (size_t)n * n, *br = V2 + (size_t)n * n;
     for (int w = blockIdx.x; w < n_windows; w += gridDim.x) {
-        const double *A = A_all + (size_t)w * pos * pos, *b = b_all + (size_t)w * pos;
+        const int m = dims ? dims[4 * w] : mmax, n = dims ? dims[4 * w + 1] : nmax;
+        if (dims && dims[4 * w + 2] != 1) continue;
+        const int pos = m + n, nc = n + 1;
+        double *M1 = ws_all + (size_t)blockIdx.x * marg_ws_doubles(mmax, nmax), *V1 = M1 + (size_t)m * m, *Y = V1 + (size_t)m * m, *X = Y + (size_t)m * nc;
+        double *T2 = X + (size_t)m * nc, *M2 = T2 + (size_t)n * n, *V2 = M2 + (size_t)n * n, *br = V2 + (size_t)n * n;
+        const double *A = A_all + (size_t)w * (A_stride ? A_stride : (long)pos * pos), *b = b_all + (size_t)w * (b_stride ? b_stride : (long)pos);
         for (int e = tid; e < m * m; e += nt) { const int i = e % m, j = e / m; M1[e] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); }
         __syncthreads();
         const int sw1 = jacobi_eig(M1, V1, m, cs, flag);
@@ -158,7 +163,7 @@ CERB_GLOBAL void marg_schur_kernel(int n_windows, int m, int n, const double *A_
         for (int e = tid; e < n * n; e += nt) { const int i = e % n, j = e / n; M2[e] = i >= j ? T2[i + (size_t)j * n] : T2[j + (size_t)i * n]; }
         __syncthreads();
         const int sw2 = jacobi_eig(M2, V2, n, cs, flag);
-        double *Jo = lin_J + (size_t)w * n * n, *ro = lin_r + (size_t)w * n;
+        double *Jo = lin_J + (size_t)w * (J_stride ? J_stride : (long)n * n), *ro = lin_r + (size_t)w * (r_stride ? r_stride : (long)n);
         for (int e = tid; e < n * n; e += nt) {
             const int kk = e % n, j = e / n;
             const double lam = M2[kk + (size_t)kk * n];

@@ -638,6 +638,7 @@ CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const doubl
                 }
         };
         load_S(wid * 4);
+        const int imu_mask = s.ti[131];                                   // 0: all factors (solve); marginalization: 1 only factor 0, 2 none
         double sdt[4];                                                    // sum_dt of this warp's factors, fetched up front
         _Pragma("unroll")
         for (int rnd = 0; rnd < 4; rnd++) { const int i = rnd + 4 * wid; sdt[rnd] = (i < CERB_WINDOW) ? P.pre[((size_t)w * CERB_WINDOW + i) * PRE_STRIDE + PRE_SUM_DT] : 1e30; }
@@ -645,7 +646,7 @@ CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const doubl
         for (int rnd = 0; rnd < 4; rnd++) {
             const int i = rnd + 4 * wid;
             const double *pre = P.pre + ((size_t)w * CERB_WINDOW + (i < CERB_WINDOW ? i : 0)) * PRE_STRIDE;
-            if (i < CERB_WINDOW && !(sdt[rnd] > 10.0)) {                  // estimator.cpp:1119
+            if (i < CERB_WINDOW && !(sdt[rnd] > 10.0) && (imu_mask == 0 || (imu_mask == 1 && i == 0))) {      // estimator.cpp:1119
                 // ---- expand Ju ----------------------------------------------------------------------------------------------
                 for (int k = lane; k < IMU_TILE; k += 32) Jt[k] = 0.0;
                 __syncwarp();
@@ -840,6 +841,39 @@ template <int W> CERB_D void ttt_warp(Smem &s, int lane) {
     }
 }
 
+// prior Hessian image (J0^T J0 scattered into the layout of Hxx | Hxy | Ad | Bo) in global memory + the column -> destination map of
+// the prior in s.ti[0..n); returns whether the window has a prior
+CERB_D bool build_prior_image(const SolveParams &P, Smem &s, int w, double *pimg, int tid) {
+    const int *pmeta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
+    const bool has_prior = pmeta[0] != 0;
+    if (has_prior) {
+        const int n = pmeta[1], nb = pmeta[2];
+        for (int k = tid; k < HXX_SZ + HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) pimg[k] = 0.0;
+        if (tid < nb) {
+            const int kind = pmeta[4 + 3 * tid], index = pmeta[5 + 3 * tid], col = pmeta[6 + 3 * tid];
+            const int local = (kind == 0 || kind == 3) ? 6 : prior_block_size(kind);
+            for (int k = 0; k < local; k++) {
+                int d;
+                if (kind == 0) d = 6 * index + k;
+                else if (kind == 3) d = 66 + 6 * index + k;
+                else if (kind == 1) d = -(1 + NYB * index + k);
+                else if (kind == 2) d = -(1 + NYB * index + 9 + k);
+                else d = X_TD;
+                s.ti[col + k] = d;
+            }
+        }
+        __syncthreads();
+        Smem si = s; si.Hxx = pimg; si.Hxy = pimg + HXX_SZ; si.Ad = pimg + HXX_SZ + HXY_SZ; si.Bo = pimg + HXX_SZ + HXY_SZ + 1859;
+        const double *Hp = P.prior_Hp + (size_t)w * PRIOR_LD * PRIOR_LD;
+        for (int idx = tid; idx < n * n; idx += SOLVE_THREADS) {
+            const int a = idx / n, b = idx % n;
+            if (b < a) continue;
+            scatter_H(si, s.ti[a], s.ti[b], Hp[a * PRIOR_LD + b]);
+        }
+    }
+    return has_prior;
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------------------
 CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID_CONSTANT SolveParams P) {
     CERB_DYN_SMEM(double, smem_base);
@@ -904,33 +938,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
         }
         // prior Hessian image (J0^T J0 scattered into the layout of Hxx | Hxy | Ad | Bo): constant during the solve, every
         // linearisation starts from it instead of from zero.  s.ti keeps the column -> destination map of the prior.
-        const int *pmeta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
-        const bool has_prior = pmeta[0] != 0;
-        if (has_prior) {
-            const int n = pmeta[1], nb = pmeta[2];
-            for (int k = tid; k < HXX_SZ + HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) pimg[k] = 0.0;
-            if (tid < nb) {
-                const int kind = pmeta[4 + 3 * tid], index = pmeta[5 + 3 * tid], col = pmeta[6 + 3 * tid];
-                const int local = (kind == 0 || kind == 3) ? 6 : prior_block_size(kind);
-                for (int k = 0; k < local; k++) {
-                    int d;
-                    if (kind == 0) d = 6 * index + k;
-                    else if (kind == 3) d = 66 + 6 * index + k;
-                    else if (kind == 1) d = -(1 + NYB * index + k);
-                    else if (kind == 2) d = -(1 + NYB * index + 9 + k);
-                    else d = X_TD;
-                    s.ti[col + k] = d;
-                }
-            }
-            __syncthreads();
-            Smem si = s; si.Hxx = pimg; si.Hxy = pimg + HXX_SZ; si.Ad = pimg + HXX_SZ + HXY_SZ; si.Bo = pimg + HXX_SZ + HXY_SZ + 1859;
-            const double *Hp = P.prior_Hp + (size_t)w * PRIOR_LD * PRIOR_LD;
-            for (int idx = tid; idx < n * n; idx += SOLVE_THREADS) {
-                const int a = idx / n, b = idx % n;
-                if (b < a) continue;
-                scatter_H(si, s.ti[a], s.ti[b], Hp[a * PRIOR_LD + b]);
-            }
-        }
+        const bool has_prior = build_prior_image(P, s, w, pimg, tid);
+        if (tid == 0) s.ti[131] = 0;                                    // all IMU-leg factors (the marginalization kernel restricts them)
         for (int k = tid; k < ST_STRIDE; k += SOLVE_THREADS) s.xs[k] = (k < ST_SIZE) ? P.state[(size_t)w * ST_STRIDE + k] : 0.0;
         if (tid == 0) {
             sca[S_RADIUS] = P.radius0; sca[S_MU] = P.test_initial_mu > 0.0 ? P.test_initial_mu : 1e-8; sca[S_REUSE] = 0; sca[S_DONE] = 0; sca[S_TERM] = 1; sca[S_ITER] = 0; sca[S_NSUCC] = 0;
@@ -1582,6 +1591,187 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
             P.rep_i[4 * w + 0] = iteration; P.rep_i[4 * w + 1] = (int)sca[S_NSUCC]; P.rep_i[4 * w + 2] = (int)sca[S_TERM];
             P.rep_i[4 * w + 3] = (sca[S_XCOST] == sca[S_XCOST] && fabs(sca[S_XCOST]) < 1e300) ? 0 : 4;
             P.rep_d[2 * w + 0] = sca[S_INIT_COST]; P.rep_d[2 * w + 1] = sca[S_XCOST];
+        }
+        __syncthreads();
+    }
+}
+
+
+// ---- marginalization: A = sum J^T J, b = sum J^T r over the factors that touch the dropped blocks ----------------------------------
+// MarginalizationInfo::{addResidualBlockInfo, preMarginalize, marginalize} up to ThreadsConstructA (marginalization_factor.cpp:98-279)
+// for the factor set Estimator::optimization() hands it (estimator.cpp:1247-1376 MARGIN_OLD: the old prior, the IMU-leg factor 0 -> 1
+// unless sum_dt > 10, every projection factor of the tracks anchored at frame 0 with the Huber corrector of ResidualBlockInfo::Evaluate;
+// :1377-1455 MARGIN_SECOND_NEW: the old prior only).  The linearisation is the solve kernel's own (vision_linearize restricted to the
+// anchor-0 chunks, inertial_linearize restricted to factor 0, the prior image): H and g in the solver's x | y | lambda partition are then
+// scattered into the reference's [dropped | kept] order:
+//   dropped: pose0, speedbias0, legbias0 (those that occur), the inverse depths of the anchor-0 tracks in the caller's order
+//            (MARGIN_SECOND_NEW: para_Pose[WINDOW_SIZE - 1] of the old prior)
+//   kept   : poses ascending, speed bias, leg bias, ex0, ex1, td (those that occur)
+// The eps-clamped eigen Schur complement then runs in marg_schur_kernel on A / b in place (no host round trip).
+struct MargParams {
+    const int *flags;                // [n] 0: MARGIN_OLD, 1: MARGIN_SECOND_NEW
+    const double *state, *lam;       // [n][ST_STRIDE], [n][maxF] (device feature order): the states the reference calls vector2double() on
+    double *A, *b;                   // [n][posmax * posmax] row-major (leading dimension pos of the window), [n][posmax]
+    int posmax;
+    int *dims;                       // [n][4]: m, n, status (1: prior produced, 0: none (m == 0), 2: old prior carried over unchanged), number of kept blocks
+    int *blocks;                     // [n][16][3]: kind, index AFTER the address shift of the slide, column, of every kept block
+};
+enum { MARG_OLD = 0, MARG_SECOND_NEW = 1 };
+
+CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) marg_assemble_kernel(CERB_GRID_CONSTANT SolveParams P, CERB_GRID_CONSTANT MargParams M) {
+    CERB_DYN_SMEM(double, smem_base);
+    Smem s; smem_carve(smem_base, s);
+    const int tid = threadIdx.x, F = P.maxF;
+    double *ws = P.ws + (size_t)blockIdx.x * P.ws_stride;
+    double *W = ws + ws_W(F);
+    double *hh = ws + ws_vecs(F), *gl = hh + F, *sl = gl + F;
+    int *chunks = reinterpret_cast<int *>(ws + ws_chunks(F));
+    double *pimg = ws + ws_prior(F);
+    int *colx = reinterpret_cast<int *>(s.idg);           // [79] column of x index a in A (-1: block absent), then [26] of the y indices of frames 0 / 1
+                                                          // (idg | idx: 224 doubles that only the Gauss-Newton step of the solver uses)
+    int *coly = colx + 80;
+    int *misc = coly + 32;                                // [0] n0, [1] m, [2] n, [3] status, [4] stereo seen, [5] longest anchor-0 track
+    if (tid < 32) {                                       // scatter plan of the IMU-leg Gram matrix (same as in vilo_solve_kernel)
+        int *plan = reinterpret_cast<int *>(ws + ws_imuplan(F));
+        int q = 0;
+        for (int mi = 0; mi < 5; mi++)
+            for (int ni = mi; ni < 5; ni++, q++)
+                for (int e = 0; e < 2; e++) {
+                    const int la = 8 * mi + (tid >> 2), lb = 8 * ni + 2 * (tid & 3) + e;
+                    int px = (int)(s.sca + 32 - smem_base) + tid, py = 256 << 12;
+                    if (la <= lb && lb <= 38 && la != 38) {
+                        double *p0[2], *p1[2];
+                        for (int i = 0; i < 2; i++) {
+                            const int da = imu_col_dest(i, la);
+                            if (lb == 38) { p0[i] = da >= 0 ? s.g + da : s.g + NX + (-da - 1); p1[i] = nullptr; }
+                            else scatter_addr(s, da, imu_col_dest(i, lb), &p0[i], &p1[i]);
+                        }
+                        px = (int)(p0[0] - smem_base);
+                        py = (int)(p0[1] - p0[0]) | (((p1[0] ? (int)(p1[0] - p0[0]) : 0) + 256) << 12);
+                    }
+                    plan[(2 * (q * 2 + e)) * 32 + tid] = px; plan[(2 * (q * 2 + e) + 1) * 32 + tid] = py;
+                }
+    }
+    __syncthreads();
+    for (int w = blockIdx.x; w < P.n_windows; w += gridDim.x) {
+        const int nF = P.n_features[w], flag = M.flags[w];
+        const double *lam = M.lam + (size_t)w * F;
+        const int *pmeta = P.prior_meta + (size_t)w * PRIOR_META_STRIDE;
+        const int *fstart = P.feat_start + (size_t)w * F, *fnobs = P.feat_nobs + (size_t)w * F, *foff = P.feat_off + (size_t)w * F;
+        const int *stereo = P.obs_stereo + (size_t)w * P.maxObs;
+        // ---- tracks anchored at frame 0 (the device order is sorted by anchor: they are the first n0 slots, in the caller's order) ----
+        if (tid == 0) {
+            int n0 = 0;
+            if (flag == MARG_OLD) while (n0 < nF && fstart[n0] == 0) n0++;
+            int n = 0, c0 = 0;
+            while (c0 < n0) {
+                const int e = (c0 + 64 < n0) ? c0 + 64 : n0;
+                chunks[1 + n] = c0;
+                if (n < 15) { s.ti[97 + 2 * n] = c0; s.ti[98 + 2 * n] = ((e - c0) << 8) | 0; }
+                n++; c0 = e;
+            }
+            chunks[1 + n] = n0; chunks[0] = n; s.ti[96] = n;
+            s.ti[131] = flag == MARG_OLD ? 1 : 2;
+            misc[0] = n0; misc[4] = 0; misc[5] = 0;
+        }
+        const bool has_prior = build_prior_image(P, s, w, pimg, tid);
+        for (int k = tid; k < ST_STRIDE; k += SOLVE_THREADS) s.xs[k] = (k < ST_SIZE) ? M.state[(size_t)w * ST_STRIDE + k] : 0.0;
+        __syncthreads();
+        const int n0 = misc[0];
+        {   // which of ex1 / pose_j occur among the visual factors: any stereo observation, the longest anchor-0 track
+            int st = 0, len = 0;
+            for (int f = tid; f < n0; f += SOLVE_THREADS) { const int nb = fnobs[f]; len = nb > len ? nb : len; for (int k = 0; k < nb; k++) st |= (stereo[foff[f] + k] != 0); }
+            s.red[tid] = (double)(len | (st << 8));
+            __syncthreads();
+            if (tid == 0) { int l = 0, q = 0; for (int k = 0; k < SOLVE_THREADS; k++) { const int v = (int)s.red[k]; l = (v & 255) > l ? (v & 255) : l; q |= v >> 8; } misc[4] = q; misc[5] = l; }
+            __syncthreads();
+        }
+        // ---- linearise: prior image | visual factors of the anchor-0 tracks | IMU-leg factor 0 | prior gradient ---------------------
+        if (!has_prior) { for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = 0.0; }
+        else copy_g2s(s.Hxx, pimg, HXX_SZ, tid);
+        for (int k = tid; k < NRP; k += SOLVE_THREADS) s.g[k] = 0.0;
+        load_geometry(s.xs, s, tid);
+        if (n0 > 0) vision_linearize(P, w, s.xs, lam, W, hh, gl, sl, false, chunks, tid);
+        __syncthreads();
+        if (has_prior) copy_g2s(s.Hxy, pimg + HXX_SZ, HXY_SZ + 1859 + 1690, tid);
+        else for (int k = tid; k < HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) s.Hxy[k] = 0.0;
+        __syncthreads();
+        inertial_linearize(P, w, s.xs, tid);
+        // ---- block presence and the [dropped | kept] column map ---------------------------------------------------------------
+        if (tid == 0) {
+            bool pose[NFR] = {false}, sb[2] = {false, false}, lb[2] = {false, false}, ex[2] = {false, false}, td = false;
+            if (has_prior) for (int b = 0; b < pmeta[2]; b++) {
+                const int kind = pmeta[4 + 3 * b], index = pmeta[5 + 3 * b];
+                if (kind == 0) pose[index] = true; else if (kind == 1) sb[index ? 1 : 0] = true; else if (kind == 2) lb[index ? 1 : 0] = true;
+                else if (kind == 3) ex[index] = true; else td = true;
+            }
+            const bool noleg = (P.flags[w] & 4) != 0;
+            if (flag == MARG_OLD) {
+                if (!(P.pre[(size_t)w * CERB_WINDOW * PRE_STRIDE + PRE_SUM_DT] > 10.0)) { pose[0] = pose[1] = true; sb[0] = sb[1] = true; if (!noleg) lb[0] = lb[1] = true; }
+                if (n0 > 0) { pose[0] = true; ex[0] = true; td = true; if (misc[4]) ex[1] = true; for (int j = 1; j < misc[5] && j < NFR; j++) pose[j] = true; }
+            }
+            for (int k = 0; k < 80 + 32; k++) colx[k] = -1;
+            int m = 0, n = 0, status = 1, nblk = 0;
+            int *blk = M.blocks + (size_t)w * 48;
+            if (flag == MARG_OLD) {
+                if (pose[0]) { for (int k = 0; k < 6; k++) colx[k] = m + k; m += 6; }
+                if (sb[0]) { for (int k = 0; k < 9; k++) coly[k] = m + k; m += 9; }
+                if (lb[0]) { for (int k = 0; k < 4; k++) coly[9 + k] = m + k; m += 4; }
+                m += n0;                                                   // lambda k -> column (m - n0) + k
+                if (m == 0) status = 0;                                    // MarginalizationInfo::valid = false (marginalization_factor.cpp:205-210)
+                for (int j = 1; j < NFR; j++) if (pose[j]) { for (int k = 0; k < 6; k++) colx[6 * j + k] = m + n + k; blk[3 * nblk] = 0; blk[3 * nblk + 1] = j - 1; blk[3 * nblk + 2] = n; nblk++; n += 6; }
+                if (sb[1]) { for (int k = 0; k < 9; k++) coly[13 + k] = m + n + k; blk[3 * nblk] = 1; blk[3 * nblk + 1] = 0; blk[3 * nblk + 2] = n; nblk++; n += 9; }
+                if (lb[1]) { for (int k = 0; k < 4; k++) coly[13 + 9 + k] = m + n + k; blk[3 * nblk] = 2; blk[3 * nblk + 1] = 0; blk[3 * nblk + 2] = n; nblk++; n += 4; }
+            } else {
+                if (!has_prior || !pose[CERB_WINDOW - 1]) status = 2;       // prior carried over unchanged (estimator.cpp:1380-1381)
+                else {
+                    for (int k = 0; k < 6; k++) colx[6 * (CERB_WINDOW - 1) + k] = k;
+                    m = 6;
+                    for (int j = 0; j < NFR; j++) if (pose[j] && j != CERB_WINDOW - 1) {
+                        for (int k = 0; k < 6; k++) colx[6 * j + k] = m + n + k;
+                        blk[3 * nblk] = 0; blk[3 * nblk + 1] = (j == CERB_WINDOW) ? j - 1 : j; blk[3 * nblk + 2] = n; nblk++; n += 6;
+                    }
+                    if (sb[0]) { for (int k = 0; k < 9; k++) coly[k] = m + n + k; blk[3 * nblk] = 1; blk[3 * nblk + 1] = 0; blk[3 * nblk + 2] = n; nblk++; n += 9; }
+                    if (lb[0]) { for (int k = 0; k < 4; k++) coly[9 + k] = m + n + k; blk[3 * nblk] = 2; blk[3 * nblk + 1] = 0; blk[3 * nblk + 2] = n; nblk++; n += 4; }
+                }
+            }
+            if (status == 1) {
+                for (int e = 0; e < 2; e++) if (ex[e]) { for (int k = 0; k < 6; k++) colx[66 + 6 * e + k] = m + n + k; blk[3 * nblk] = 3; blk[3 * nblk + 1] = e; blk[3 * nblk + 2] = n; nblk++; n += 6; }
+                if (td) { colx[X_TD] = m + n; blk[3 * nblk] = 4; blk[3 * nblk + 1] = 0; blk[3 * nblk + 2] = n; nblk++; n += 1; }
+            }
+            misc[1] = m; misc[2] = n; misc[3] = status;
+            int *dm = M.dims + 4 * w; dm[0] = m; dm[1] = n; dm[2] = status; dm[3] = nblk;
+        }
+        __syncthreads();
+        if (misc[3] == 1) {
+            const int m = misc[1], n = misc[2], pos = m + n, l0 = m - n0;      // l0: column of lambda 0 (MARGIN_OLD)
+            double *A = M.A + (size_t)w * M.posmax * M.posmax, *b = M.b + (size_t)w * M.posmax;
+            for (int e = tid; e < pos * pos; e += SOLVE_THREADS) A[e] = 0.0;
+            __syncthreads();
+            for (int e = tid; e < NX * NX; e += SOLVE_THREADS) {             // x - x (Hxx holds its upper triangle)
+                const int a = e / NX, c = e % NX; if (c < a) continue;
+                const int ca = colx[a], cc = colx[c]; if (ca < 0 || cc < 0) continue;
+                const double v = s.Hxx[a * NX + c];
+                A[(size_t)ca * pos + cc] = v; A[(size_t)cc * pos + ca] = v;
+            }
+            for (int e = tid; e < NX * 26; e += SOLVE_THREADS) {             // x - y (frames 0, 1)
+                const int a = e / 26, q = e % 26, ca = colx[a], cq = coly[q]; if (ca < 0 || cq < 0) continue;
+                const double v = s.Hxy[a * NY + q];
+                A[(size_t)ca * pos + cq] = v; A[(size_t)cq * pos + ca] = v;
+            }
+            for (int e = tid; e < 26 * 26; e += SOLVE_THREADS) {             // y - y
+                const int q = e / 26, r = e % 26, cq = coly[q], cr = coly[r]; if (cq < 0 || cr < 0) continue;
+                const int fq = q / NYB, fr = r / NYB, kq = q % NYB, kr = r % NYB;
+                A[(size_t)cq * pos + cr] = fq == fr ? s.Ad[fq * 169 + kq * NYB + kr] : (fq < fr ? s.Bo[kq * NYB + kr] : s.Bo[kr * NYB + kq]);
+            }
+            for (int e = tid; e < NX * n0; e += SOLVE_THREADS) {             // x - lambda
+                const int a = e / n0, k = e % n0, ca = colx[a]; if (ca < 0) continue;
+                const double v = W[(size_t)a * F + k];
+                A[(size_t)ca * pos + l0 + k] = v; A[(size_t)(l0 + k) * pos + ca] = v;
+            }
+            for (int k = tid; k < n0; k += SOLVE_THREADS) { A[(size_t)(l0 + k) * pos + l0 + k] = hh[k]; b[l0 + k] = gl[k]; }
+            for (int a = tid; a < NX; a += SOLVE_THREADS) if (colx[a] >= 0) b[colx[a]] = s.g[a];
+            for (int q = tid; q < 26; q += SOLVE_THREADS) if (coly[q] >= 0) b[coly[q]] = s.g[NX + q];
         }
         __syncthreads();
     }

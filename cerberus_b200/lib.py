@@ -61,6 +61,9 @@ class Backend:
         L.cerb_batch_triangulate.argtypes = [C.c_void_p, C.c_double, abi.c_dp]
         L.cerb_marginalize_schur.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, abi.c_dp, abi.c_dp, C.c_double, abi.c_dp, abi.c_dp, C.POINTER(C.c_int32)]
         L.cerb_batch_shift_depth.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_int32), abi.c_dp, C.POINTER(C.c_int32)]
+        L.cerb_register_host_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.cerb_unregister_host_buffer.argtypes = [C.c_void_p, C.c_void_p]
+        L.cerb_last_upload_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         L.cerb_double2vector.restype = None
         self.cfg = cfg or abi.default_config()
         self.h = C.c_void_p()
@@ -104,6 +107,24 @@ class Backend:
         self._check(self.lib.cerb_batch_download(self.h, batch.states, batch.reports), allow=(abi.ERR_NON_FINITE,))
         return batch.report_array().copy()
 
+    def register_batch(self, batch):
+        """cerb_register_host_buffer on every array of a WindowBatch: later solve_batch / upload calls DMA straight out of them."""
+        bufs = [batch.features, batch.obs, batch.preint, batch.prior_J, batch.prior_r, batch.para_Feature]
+        if batch.imu_preint is not None: bufs.append(batch.imu_preint)
+        regs = [(a.ctypes.data, a.nbytes) for a in bufs] + [(C.addressof(batch.states), C.sizeof(batch.states)), (C.addressof(batch.descs), C.sizeof(batch.descs))]
+        for ptr, nbytes in regs:
+            self._check(self.lib.cerb_register_host_buffer(self.h, C.c_void_p(ptr), nbytes))
+        return [p for p, _ in regs]
+
+    def unregister(self, ptrs):
+        for p in ptrs:
+            self._check(self.lib.cerb_unregister_host_buffer(self.h, C.c_void_p(p)))
+
+    def last_upload_stats(self):
+        ops, staged = C.c_int32(), C.c_int64()
+        self._check(self.lib.cerb_last_upload_stats(self.h, C.byref(ops), C.byref(staged)))
+        return ops.value, staged.value
+
     def sync(self):
         self._check(self.lib.cerb_sync(self.h))
 
@@ -113,7 +134,7 @@ class Backend:
         return ms.value, nl.value
 
     def debug_linearize(self, batch, w):
-        """cost, gradient, diag(J^T J) of resident window w at its initial state (ABI tangent order)."""
+        """cost, gradient, diag(J^T J) of resident window w at its current state (solved states after a solve, else the uploaded ones; ABI tangent order)."""
         nf = batch.descs[w].n_features
         g, d = np.zeros(abi.NUM_REDUCED + nf), np.zeros(abi.NUM_REDUCED + nf)
         cost = C.c_double()

@@ -31,6 +31,7 @@
 #define CERBERUS_B200_H
 
 #include <stdint.h>
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -269,11 +270,20 @@ int cerb_batch_upload(CerbHandle *h, int32_t n, const CerbWindowDesc *descs,
 int cerb_batch_solve_resident(CerbHandle *h);
 int cerb_batch_download(CerbHandle *h, CerbWindowState *states, CerbSolveReport *reports);
 int cerb_sync(CerbHandle *h);
+/* Zero-copy uploads.  The descriptors travel to the device as they are (the AoS -> HBM-layout transpose runs on the device); when a
+ * source array lies in memory registered here, cerb_solve_batch / cerb_batch_upload DMA straight out of it (per array ONE 2-D copy per
+ * pipeline chunk if the per-window arrays are uniformly strided, like members of one allocation), otherwise it is first copied into the
+ * handle's pinned staging by a few host threads.  Register the long-lived buffers of the estimator once (page-locks them:
+ * cudaHostRegister); unregister before freeing them.  Registration is an optimisation only: results are identical either way. */
+int cerb_register_host_buffer(CerbHandle *h, void *ptr, size_t bytes);
+int cerb_unregister_host_buffer(CerbHandle *h, void *ptr);
+/* Diagnostics of the last cerb_solve_batch / cerb_batch_upload: DMA operations issued, bytes that went through staging memcpy. */
+int cerb_last_upload_stats(CerbHandle *h, int32_t *dma_ops, int64_t *staged_bytes);
 /* CUDA-event milliseconds of the last completed solve launch sequence on the handle's stream and
  * the number of kernels it launched. */
 int cerb_last_solve_stats(CerbHandle *h, double *kernel_ms, int32_t *kernel_launches);
-/* Debug/parity probe: linearisation of window `w` of the resident batch at its CURRENT state,
- * exactly what the first solver iteration sees: cost, gradient (tangent space, order
+/* Debug/parity probe: linearisation of window `w` of the resident batch at its CURRENT state (the solved states after a solve, else
+ * the uploaded initial ones), exactly what a first solver iteration there sees; read-only with respect to the batch and its reports: cost, gradient (tangent space, order
  * [pose0..10 (66) | ex0, ex1 (12) | speedbias0..10 (99) | legbias0..10 (44) | td (1) | features]),
  * the Schur-reduced 221x221 system is not exposed, only the gradient and diag(J^T J). */
 int cerb_debug_linearize(CerbHandle *h, int32_t w, double *cost, double *gradient, double *jtj_diag,

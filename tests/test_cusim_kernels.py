@@ -285,9 +285,39 @@ def test_host_buffer_pipeline_chunks():
     base = synth.generate_batch(3, 4, ob, with_prior=False, window0=140)
     big = synth.tile_batch(base, 9)
     rep = s.solve_batch(big)
-    assert s.last_solve_stats()[1] == 3 * 3
+    assert s.last_solve_stats()[1] == 4 * 3 + 1      # per chunk: pack, two prepare kernels, solve; + the unpack kernel of the download
     pose = big.state_array()["para_Pose"]
     assert not (pose[:3] == base.state_array()["para_Pose"]).all()                  # the solve moved the states
     for k in range(3, 9):
         assert (pose[k] == pose[k % 3]).all() and (big.para_Feature[k] == big.para_Feature[k % 3]).all()
     assert (rep["final_cost"][3:6] == rep["final_cost"][0:3]).all() and (rep["status"] == 0).all()
+
+
+def test_registered_host_buffers_take_the_zero_copy_path():
+    """cerb_register_host_buffer: arrays inside registered memory are DMA'd straight out of the caller's buffers (ONE 2-D copy per array and
+    pipeline chunk when the per-window arrays are uniformly strided), the others go through pinned staging.  Results are bit-identical."""
+    cfg = small_cfg(max_batch=16, max_features=8, iters=2)
+    s = sim_backend(cfg)
+    base = synth.generate_batch(3, 6, ob, window0=150, prior_features=4)
+    big = synth.tile_batch(base, 9)
+    saved = big.copy_states()
+    rep_a = s.solve_batch(big); out_a = np.frombuffer(big.states, dtype=np.uint8).copy(); lam_a = big.para_Feature.copy()
+    ops_a, staged_a = s.last_upload_stats()
+    assert staged_a > 0
+    big.restore_states(saved)
+    regs = s.register_batch(big)
+    rep_b = s.solve_batch(big)
+    ops_b, staged_b = s.last_upload_stats()
+    assert staged_b == 0 and ops_b <= 3 * 10            # 3 chunks x (descs, states, features, obs, para_Feature, preint head + tail, prior J, prior r)
+    assert (np.frombuffer(big.states, dtype=np.uint8) == out_a).all() and (big.para_Feature == lam_a).all() and (rep_a["final_cost"] == rep_b["final_cost"]).all()
+    # irregular batch: one window without features, one without a prior -> per-window copies for those arrays, same results as staged
+    big.restore_states(saved)
+    big.descs[1].n_features = 0; big.descs[1].n_obs = 0; big.descs[4].prior.valid = 0
+    rep_c = s.solve_batch(big); out_c = np.frombuffer(big.states, dtype=np.uint8).copy()
+    assert s.last_upload_stats()[1] == 0
+    s.unregister(regs)
+    big.restore_states(saved)
+    rep_d = s.solve_batch(big)
+    assert s.last_upload_stats()[1] > 0
+    assert (np.frombuffer(big.states, dtype=np.uint8) == out_c).all() and (rep_c["final_cost"] == rep_d["final_cost"]).all()
+    assert (rep_c["final_cost"][[0, 2, 3]] == rep_a["final_cost"][[0, 2, 3]]).all() and rep_c["final_cost"][1] != rep_a["final_cost"][1]
