@@ -57,7 +57,7 @@ struct CerbHandle {
     double *h_rpre = nullptr, *h_rlam = nullptr, *h_pJ = nullptr, *h_pr = nullptr, *h_state = nullptr, *h_lam = nullptr, *h_dbg = nullptr;
     CerbSolveReport *h_orep = nullptr;
     std::vector<std::pair<uintptr_t, size_t>> regs;   // host ranges registered with cerb_register_host_buffer: DMA straight out of them
-    std::vector<int> nfeat;           // [B] n_features of the resident windows
+    std::vector<int> nfeat, n0;       // [B] n_features / number of tracks anchored at frame 0 of the resident windows
     int test_fail_factorizations = 0; double test_initial_mu = 0.0;   // fault injection of the parity tests (environment, read by cerb_create)
     bool solved = false;              // the device states are the solved ones (else: the uploaded initial states)
     std::vector<int> h_perm; bool perm_valid = false;     // [B][F] device feature slot -> index in the caller's feature array (fetched on demand)
@@ -157,7 +157,7 @@ static int create_impl(CerbHandle *h, const CerbSolverConfig *cfg, const cudaDev
     CUDA_TRY(hmalloc(&h->h_rpre, B * 10 * RAW_PRE_STRIDE)); CUDA_TRY(hmalloc(&h->h_rlam, B * F));
     CUDA_TRY(hmalloc(&h->h_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(hmalloc(&h->h_pr, B * PRIOR_LD));
     CUDA_TRY(hmalloc(&h->h_state, B * ST_STRIDE)); CUDA_TRY(hmalloc(&h->h_lam, B * F)); CUDA_TRY(hmalloc(&h->h_orep, B)); CUDA_TRY(hmalloc(&h->h_dbg, 2 * (NR + F) + 8));
-    h->nfeat.assign(B, 0);
+    h->nfeat.assign(B, 0); h->n0.assign(B, 0);
     CUDA_TRY(cudaMemcpy(h->d_G, cfg->g, 3 * sizeof(double), cudaMemcpyHostToDevice));
     return CERB_OK;
 }
@@ -257,15 +257,18 @@ static int validate_prior(const CerbPrior &pr) {
     return CERB_OK;
 }
 
-static int validate_window(const CerbHandle *h, const CerbWindowDesc &d, const CerbWindowState &st) {
+static int validate_window(const CerbHandle *h, const CerbWindowDesc &d, const CerbWindowState &st, int *n_anchor0) {
     if (d.n_features < 0 || d.n_features > h->F) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_features over capacity");
     if (d.n_obs < 0 || d.n_obs > h->O) return fail(CERB_ERR_BAD_ARGUMENT, "window: n_obs over capacity");
     if ((d.n_features && (!d.features || !d.obs || !st.para_Feature)) || (!d.preint && !d.imu_preint)) return fail(CERB_ERR_BAD_ARGUMENT, "window: null pointer");
+    int n0 = 0;
     for (int f = 0; f < d.n_features; f++) {
         const CerbFeature &ft = d.features[f];
         if (ft.start_frame < 0 || ft.n_obs < 1 || ft.start_frame + ft.n_obs > CERB_NUM_FRAMES || ft.obs_offset < 0 || ft.obs_offset + ft.n_obs > d.n_obs)
             return fail(CERB_ERR_BAD_ARGUMENT, "window: malformed feature track");
+        n0 += ft.start_frame == 0;
     }
+    if (n_anchor0) *n_anchor0 = n0;
     return validate_prior(d.prior);
 }
 
@@ -284,7 +287,7 @@ static void run_stage_jobs(const std::vector<StageJob> &jobs) {
 
 // validate windows [w0, w0 + cn), move their raw descriptors to the device on stream s (staging only what is not registered)
 static int upload_raw(CerbHandle *h, int w0, int cn, const CerbWindowDesc *descs, const CerbWindowState *states, cudaStream_t s, double *t_stage_ms) {
-    for (int w = w0; w < w0 + cn; w++) { int rc = validate_window(h, descs[w], states[w]); if (rc) return rc; h->nfeat[w] = descs[w].n_features; }
+    for (int w = w0; w < w0 + cn; w++) { int rc = validate_window(h, descs[w], states[w], &h->n0[w]); if (rc) return rc; h->nfeat[w] = descs[w].n_features; }
     UploadPlan pl;
     const size_t F = h->F, O = h->O, W0 = (size_t)w0;
     auto dv = [&](void *base, size_t per) { return (char *)base + W0 * per; };
@@ -783,8 +786,9 @@ int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t 
     CERB_DEVICE(h);
     if (n_windows < 1 || m < 1 || n < 1 || m > 4096 || n > CERB_MAX_PRIOR_DIM) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_marginalize_schur: bad sizes");
     const size_t pos = (size_t)m + n, N = n_windows;
-    int grid = std::min<int>(n_windows, 2 * h->sm_count);
+    int grid = std::min<int>(n_windows, (marg_smem_bytes(m, n) > 110 * 1024 ? 1 : 2) * h->sm_count);
     grid = (int)std::max<size_t>(1, std::min<size_t>(grid, ((size_t)4 << 30) / (marg_ws_doubles(m, n) * sizeof(double))));      // <= 4 GB of per-CTA workspace
+    CUDA_TRY(cudaFuncSetAttribute(marg_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem_bytes(m, n)));
     cudaStream_t s = h->stream; DevBuf B(h);
     double *dA = B.up(A, N * pos * pos, s), *db = B.up(b, N * pos, s), *dws = B.up(nullptr, (size_t)grid * marg_ws_doubles(m, n), s);
     double *dJ = B.up(nullptr, N * n * n, s), *dr = B.up(nullptr, N * n, s), *dsw = B.up(nullptr, N, s);     // dsw: 2 ints per window
@@ -795,6 +799,124 @@ int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t 
     CUDA_TRY(cudaMemcpyAsync(linearized_residuals, dr, N * n * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (sweeps) CUDA_TRY(cudaMemcpyAsync(sweeps, dsw, N * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    return CERB_OK;
+}
+
+// ---- marginalization of the resident batch ----------------------------------------------------------------------------------
+CERB_GLOBAL void permute_lam_kernel(int n, int F, const int *n_features, const int *perm, const double *lam_caller, double *lam_dev) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n * F) return;
+    const int w = (int)(idx / F), k = (int)(idx % F);
+    if (k < n_features[w]) lam_dev[idx] = lam_caller[(size_t)w * F + perm[idx]];
+}
+
+int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindowState *states, CerbPrior *priors, int32_t *sweeps) {
+    if (!h || !flags || !priors) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_batch_marginalize: null argument");
+    CERB_DEVICE(h);
+    const int n = h->n, F = h->F;
+    if (n < 1) return fail(CERB_ERR_BAD_ARGUMENT, "no resident batch");
+    for (int w = 0; w < n; w++) {
+        if (flags[w] != 0 && flags[w] != 1) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_batch_marginalize: flag must be 0 (MARGIN_OLD) or 1 (MARGIN_SECOND_NEW)");
+        if (!priors[w].linearized_jacobians || !priors[w].linearized_residuals) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_batch_marginalize: priors[w] needs storage for linearized_jacobians / linearized_residuals");
+    }
+    cudaStream_t s = h->stream; DevBuf B(h);
+    int mmax = 19, nmax = CERB_MAX_PRIOR_DIM;
+    for (int w = 0; w < n; w++) if (flags[w] == 0) mmax = std::max(mmax, 19 + h->n0[w]);
+    const int posmax = mmax + nmax;
+    // states to linearise at: the caller's (after double2vector + vector2double), or the resident ones
+    std::vector<double> hst((size_t)n * ST_STRIDE, 0.0);
+    const double *d_st, *d_lm;
+    if (states) {
+        std::vector<double> hl((size_t)n * F, 0.0);
+        for (int w = 0; w < n; w++) {
+            std::memcpy(hst.data() + (size_t)w * ST_STRIDE, &states[w], ST_SIZE * sizeof(double));
+            if (h->nfeat[w]) { if (!states[w].para_Feature) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_batch_marginalize: null para_Feature"); std::memcpy(hl.data() + (size_t)w * F, states[w].para_Feature, (size_t)h->nfeat[w] * 8); }
+        }
+        double *ds = B.up(hst.data(), hst.size(), s), *dlc = B.up(hl.data(), hl.size(), s), *dl = B.up(nullptr, (size_t)n * F, s);
+        if (!ds || !dlc || !dl) return fail(CERB_ERR_CUDA, "device allocation failed");
+        CERB_LAUNCH(permute_lam_kernel, (int)(((size_t)n * F + 127) / 128), 128, 0, s, n, F, (const int *)h->d_nfeat, (const int *)h->d_perm, (const double *)dlc, dl);
+        CUDA_TRY(cudaStreamSynchronize(s));               // hl / hst are read by the asynchronous copies
+        d_st = ds; d_lm = dl;
+    } else {
+        d_st = h->solved ? h->d_state : h->d_state0; d_lm = h->solved ? h->d_lam : h->d_lam0;
+        CUDA_TRY(cudaMemcpyAsync(hst.data(), d_st, hst.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    std::vector<int> hflags(flags, flags + n);
+    int *dflags = B.upi(hflags.data(), n, s), *ddims = B.upi(nullptr, (size_t)n * 4, s), *dblocks = B.upi(nullptr, (size_t)n * 64, s), *dsw = B.upi(nullptr, (size_t)n * 2, s);
+    double *dJ = B.up(nullptr, (size_t)n * PRIOR_LD * PRIOR_LD, s), *dr = B.up(nullptr, (size_t)n * PRIOR_LD, s);
+    // A / b of a sub-batch and the per-CTA workspace of the eigen-solver: bounded device memory whatever the batch size
+    const size_t a_bytes = (size_t)posmax * posmax * 8, budget = (size_t)3 << 30;
+    const int per = (int)std::max<size_t>(1, std::min<size_t>(n, budget / a_bytes));
+    double *dA = B.up(nullptr, (size_t)per * posmax * posmax, s), *db = B.up(nullptr, (size_t)per * posmax, s);
+    int sgrid = std::min(per, (marg_smem_bytes(mmax, nmax) > 110 * 1024 ? 1 : 2) * h->sm_count);
+    CUDA_TRY(cudaFuncSetAttribute(marg_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem_bytes(mmax, nmax)));
+    sgrid = (int)std::max<size_t>(1, std::min<size_t>(sgrid, ((size_t)2 << 30) / (marg_ws_doubles(mmax, nmax) * sizeof(double))));
+    double *dws = B.up(nullptr, (size_t)sgrid * marg_ws_doubles(mmax, nmax), s);
+    if (!dflags || !ddims || !dblocks || !dsw || !dJ || !dr || !dA || !db || !dws) return fail(CERB_ERR_CUDA, "device allocation failed");
+    CUDA_TRY(cudaMemsetAsync(dsw, 0, (size_t)n * 2 * sizeof(int), s));
+    CUDA_TRY(cudaFuncSetAttribute(marg_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    for (int w0 = 0; w0 < n; w0 += per) {
+        const int cn = std::min(per, n - w0);
+        // sqrt_info of the IMU-leg factors and the Gram matrix of the old prior (a solve leaves them behind; a bare upload does not)
+        const int nfac = cn * 10;
+        CERB_LAUNCH(imu_leg_prepare_kernel, (nfac + 1) / 2, 64, 0, s, nfac, (const double *)(h->d_pre + (size_t)w0 * 10 * PRE_STRIDE), h->d_sinfo + (size_t)w0 * 10 * 961);
+        CERB_LAUNCH(prior_prepare_kernel, cn, 256, (size_t)PRIOR_TROWS * PRIOR_TLD * sizeof(double), s, (const double *)(h->d_pJ + (size_t)w0 * PRIOR_LD * PRIOR_LD), (const int *)(h->d_pmeta + (size_t)w0 * PRIOR_META_STRIDE), h->d_pHp + (size_t)w0 * PRIOR_LD * PRIOR_LD);
+        SolveParams P = make_params(h, w0, cn, 0, nullptr, -1);
+        MargParams M;
+        M.flags = dflags + w0; M.state = d_st + (size_t)w0 * ST_STRIDE; M.lam = d_lm + (size_t)w0 * F; M.A = dA; M.b = db; M.posmax = posmax;
+        M.dims = ddims + (size_t)w0 * 4; M.blocks = dblocks + (size_t)w0 * 64;
+        CERB_LAUNCH(marg_assemble_kernel, std::min(cn, h->grid), SOLVE_THREADS, h->smem_bytes, s, P, M);
+        CERB_LAUNCH(marg_schur_kernel, std::min(cn, sgrid), MARG_THREADS, marg_smem_bytes(mmax, nmax), s, cn, mmax, nmax, (const int *)(ddims + (size_t)w0 * 4), (const double *)dA, (long)posmax * posmax,
+                    (const double *)db, (long)posmax, 1e-8, dws, dJ + (size_t)w0 * PRIOR_LD * PRIOR_LD, (long)PRIOR_LD * PRIOR_LD, dr + (size_t)w0 * PRIOR_LD, (long)PRIOR_LD, dsw + (size_t)w0 * 2);
+        CUDA_TRY(cudaGetLastError());
+    }
+    std::vector<int> hdims((size_t)n * 4), hblocks((size_t)n * 64), hsw((size_t)n * 2);
+    std::vector<double> hJ((size_t)n * PRIOR_LD * PRIOR_LD), hr((size_t)n * PRIOR_LD);
+    CUDA_TRY(cudaMemcpyAsync(hdims.data(), ddims, hdims.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hblocks.data(), dblocks, hblocks.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hsw.data(), dsw, hsw.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hJ.data(), dJ, hJ.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hr.data(), dr, hr.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    // a prior that is carried over unchanged comes back from the device copy of the old one
+    std::vector<int> hmeta((size_t)n * PRIOR_META_STRIDE); std::vector<double> hx0((size_t)n * 16 * 9);
+    CUDA_TRY(cudaMemcpyAsync(hmeta.data(), h->d_pmeta, hmeta.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hx0.data(), h->d_px0, hx0.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<double> oldJ, oldr;
+    for (int w = 0; w < n; w++) {
+        CerbPrior &pr = priors[w];
+        double *Jout = const_cast<double *>(pr.linearized_jacobians), *rout = const_cast<double *>(pr.linearized_residuals);
+        const int status = hdims[4 * w + 2];
+        if (sweeps) { sweeps[2 * w] = hsw[2 * w]; sweeps[2 * w + 1] = hsw[2 * w + 1]; }
+        pr.valid = 0; pr.n = 0; pr.num_blocks = 0;
+        if (status == 0) continue;
+        if (status == 2) {                       // MARGIN_SECOND_NEW without para_Pose[WINDOW_SIZE - 1] in the old prior: unchanged (estimator.cpp:1380-1381)
+            const int *meta = hmeta.data() + (size_t)w * PRIOR_META_STRIDE;
+            if (!meta[0]) continue;
+            pr.valid = 1; pr.n = meta[1]; pr.num_blocks = meta[2];
+            for (int b = 0; b < pr.num_blocks; b++) {
+                pr.block_kind[b] = meta[4 + 3 * b]; pr.block_index[b] = meta[5 + 3 * b]; pr.block_col[b] = meta[6 + 3 * b];
+                for (int k = 0; k < 9; k++) pr.block_x0[b][k] = hx0[(size_t)w * 144 + 9 * b + k];
+            }
+            oldJ.resize((size_t)pr.n * pr.n); oldr.resize(pr.n);
+            CUDA_TRY(cudaMemcpy(oldJ.data(), h->d_pJ + (size_t)w * PRIOR_LD * PRIOR_LD, oldJ.size() * 8, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(oldr.data(), h->d_pr + (size_t)w * PRIOR_LD, oldr.size() * 8, cudaMemcpyDeviceToHost));
+            std::memcpy(Jout, oldJ.data(), oldJ.size() * 8); std::memcpy(rout, oldr.data(), oldr.size() * 8);
+            continue;
+        }
+        const int nn = hdims[4 * w + 1], nb = hdims[4 * w + 3];
+        pr.valid = 1; pr.n = nn; pr.num_blocks = nb;
+        const double *st = hst.data() + (size_t)w * ST_STRIDE;
+        for (int b = 0; b < nb; b++) {
+            const int *q = hblocks.data() + (size_t)w * 64 + 4 * b;
+            pr.block_kind[b] = q[0]; pr.block_index[b] = q[1]; pr.block_col[b] = q[2];
+            const int size = prior_block_size(q[0]);
+            const double *x = st + prior_block_state_offset(q[0], q[3]);          // keep_block_data: the state the factors were linearised at
+            for (int k = 0; k < 9; k++) pr.block_x0[b][k] = k < size ? x[k] : 0.0;
+        }
+        std::memcpy(Jout, hJ.data() + (size_t)w * PRIOR_LD * PRIOR_LD, (size_t)nn * nn * 8);
+        std::memcpy(rout, hr.data() + (size_t)w * PRIOR_LD, (size_t)nn * 8);
+    }
     return CERB_OK;
 }
 

@@ -5,8 +5,8 @@
 //     SelfAdjointEigenSolver(A) (lower triangle);  S = lambda > eps ? lambda : 0;  S_inv = lambda > eps ? 1 / lambda : 0
 //     linearized_jacobians = diag(sqrt S) V^T;  linearized_residuals = diag(sqrt S_inv) V^T b
 // The eigen-solver is a parallel two-sided Jacobi iteration (round-robin pair ordering: kp / 2 disjoint rotations per round,
-// column phase, row phase, re-symmetrisation), in fp64, on matrices that live in L2 (m = 19 + tracks anchored at frame 0 -> 169 x 169 for
-// the 150-feature configuration, 86 x 86 for the kept block).  Rotation formulas as in the CPU restatement
+// column phase, row phase, re-symmetrisation), in fp64, on matrices that live in SHARED memory (m = 19 + tracks anchored at frame 0 -> 169 x 169
+// for the 150-feature configuration = 223 KB, 86 x 86 for the kept block; larger m falls back to the L2-resident workspace).  Rotation formulas as in the CPU restatement
 // (oracle/ref_math.h sym_eig_jacobi), different pair order; the rows of linearized_jacobians come out in the order the
 // eigenvalues sit on the diagonal (J^T J and J^T r, the only things MarginalizationFactor uses, do not depend on it).
 #pragma once
@@ -21,13 +21,27 @@ constexpr int MARG_THREADS = 256;
 #endif
 constexpr int MARG_MAX_SWEEPS = 60;
 
-// per-CTA workspace in doubles: M1, V1 (m x m) | Y, X (m x (n + 1)) | T2, M2, V2 (n x n) | br (n)
-CERB_HD size_t marg_ws_doubles(int m, int n) {
-    return 2 * (size_t)m * m + 2 * (size_t)m * (n + 1) + 3 * (size_t)n * n + (size_t)n;
+// Memory plan of one CTA (ld = k | 1: odd leading dimensions keep the row pass free of shared-memory bank conflicts):
+//   phase 1  M1 (m x m) in SHARED memory when it fits (m <= 169: the 150-feature configuration), else in the global workspace;
+//            T = V1^T [Amr | bm] (m x (n + 1)) in the global workspace (L2): the rotations are applied to its rows as they are applied to the
+//            rows of M1, so V1 itself is never formed:  Arm Amm_inv [Amr | bm] = T^T diag(lambda > eps ? 1 / lambda : 0) T
+//   phase 2  T staged in shared memory for the contraction, M2 and V2 (n x n, n <= 96) in shared memory
+constexpr size_t MARG_SMEM_MAX = 232448 - 1024;        // 227 KB opt-in limit of sm_100 minus static shared memory head-room
+CERB_HD int marg_ld(int k) { return k | 1; }
+CERB_HD size_t marg_fixed_doubles(int m, int n) { const int k = m > n ? m : n; return 2 * (size_t)(k + 2) + 4; }        // (c, s) pairs | 1 / lambda | flags
+CERB_HD bool marg_m1_in_smem(int m, int n) { return (marg_fixed_doubles(m, n) + (size_t)marg_ld(m) * marg_ld(m)) * sizeof(double) <= MARG_SMEM_MAX; }
+// T staged in shared memory next to M2; V2 then goes over the dead T if T is at least as large, else behind M2
+CERB_HD size_t marg_t_body(int m, int n) { const size_t t = (size_t)marg_ld(m) * (n + 1), q = (size_t)marg_ld(n) * marg_ld(n); return t + q + (t < q ? q : 0); }
+CERB_HD bool marg_t_in_smem(int m, int n) { return (marg_fixed_doubles(m, n) + marg_t_body(m, n)) * sizeof(double) <= MARG_SMEM_MAX; }
+CERB_HD size_t marg_smem_bytes(int m, int n) {
+    size_t body = 2 * (size_t)marg_ld(n) * marg_ld(n);
+    if (marg_m1_in_smem(m, n)) body = body > (size_t)marg_ld(m) * marg_ld(m) ? body : (size_t)marg_ld(m) * marg_ld(m);
+    if (marg_t_in_smem(m, n)) { const size_t t = marg_t_body(m, n); body = body > t ? body : t; }
+    return (marg_fixed_doubles(m, n) + body) * sizeof(double);
 }
-CERB_HD size_t marg_smem_bytes(int m, int n) {           // (c, s) per concurrent rotation + the sweep flag
-    const int k = m > n ? m : n;
-    return (size_t)(k + 1) * sizeof(double) + 16;      // flag[2] behind the (c, s) pairs
+// per-CTA global workspace in doubles: T | M1 (only when it does not fit in shared memory) | br
+CERB_HD size_t marg_ws_doubles(int m, int n) {
+    return (size_t)marg_ld(m) * (n + 1) + (marg_m1_in_smem(m, n) ? 0 : (size_t)marg_ld(m) * marg_ld(m)) + (size_t)n + 8;
 }
 
 // pair t (0 .. kp / 2 - 1) of round r (0 .. kp - 2) of a round-robin tournament over kp (even) players, p < q
@@ -40,12 +54,12 @@ CERB_D void jacobi_pair(int t, int r, int kp, int &p, int &q) {
 }
 
 // rotation angles of round r from the upper triangle of M as it stands; (c, s) -> cs, a non-trivial rotation raises *flag
-CERB_D void jacobi_angles(const double *M, int k, int kp, int r, double *cs, int *flag) {
+CERB_D void jacobi_angles(const double *M, int ld, int k, int kp, int r, double *cs, int *flag) {
     for (int t = threadIdx.x; t < kp / 2; t += blockDim.x) {
         int p, q; jacobi_pair(t, r, kp, p, q);
         double c = 1.0, s = 0.0;
         if (q < k) {
-            const double apq = M[p + (size_t)q * k], app = M[p + (size_t)p * k], aqq = M[q + (size_t)q * k];
+            const double apq = M[p + (size_t)q * ld], app = M[p + (size_t)p * ld], aqq = M[q + (size_t)q * ld];
             if (apq != 0.0 && fabs(apq) > 1e-15 * sqrt(fabs(app * aqq))) {
                 const double theta = (aqq - app) / (2.0 * apq);
                 const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
@@ -57,40 +71,45 @@ CERB_D void jacobi_angles(const double *M, int k, int kp, int r, double *cs, int
     }
 }
 
-// Eigen-decomposition of the symmetric k x k matrix M (column-major, leading dimension k): on return the eigenvalues are on the
-// diagonal of M and the eigenvectors are the columns of V.  Called by all threads of the CTA; returns the number of sweeps.
-// Three CTA barriers per round: column pass | row pass | re-symmetrisation together with the angles of the next round (both only
-// read the upper triangle the row pass left).  flag[sweep & 1] collects "some rotation was non-trivial" for that sweep.
-CERB_D int jacobi_eig(double *M, double *V, int k, double *cs, int *flag) {
+// Eigen-decomposition of the symmetric k x k matrix M (column-major, leading dimension ld): on return the eigenvalues are on the
+// diagonal of M.  V (optional, k x k, leading dimension ldv, set to the identity here): the eigenvectors as columns.  T (optional,
+// k x nct, leading dimension ldt): replaced by V^T T (its rows are rotated like the rows of M).  Called by all threads of the CTA;
+// returns the number of sweeps.  Three CTA barriers per round: column pass | row pass | re-symmetrisation together with the angles of the
+// next round (both only read the upper triangle the row pass left).  flag[sweep & 1] collects "some rotation was non-trivial".
+CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, int ldt, int nct, double *cs, int *flag) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
     const int kp = k + (k & 1), half = kp / 2, rounds = kp - 1;
-    for (int i = tid; i < k * k; i += nt) V[i] = (i / k == i % k) ? 1.0 : 0.0;
+    if (V) for (int e = tid; e < k * k; e += nt) { const int i = e % k, j = e / k; V[i + (size_t)j * ldv] = (i == j) ? 1.0 : 0.0; }
     if (tid == 0) { flag[0] = 0; flag[1] = 0; }
     __syncthreads();
-    jacobi_angles(M, k, kp, 0, cs, flag);
+    jacobi_angles(M, ld, k, kp, 0, cs, flag);
     __syncthreads();
     int sweeps = 0;
     for (; sweeps < MARG_MAX_SWEEPS; sweeps++) {
         for (int r = 0; r < rounds; r++) {
-            for (int t = wid; t < half; t += nwarp) {         // columns p, q of M and V
+            for (int t = wid; t < half; t += nwarp) {         // columns p, q of M (and V)
                 const double c = cs[2 * t], s = cs[2 * t + 1];
                 if (s == 0.0) continue;
                 int p, q; jacobi_pair(t, r, kp, p, q);
-                double *mp = M + (size_t)p * k, *mq = M + (size_t)q * k, *vp = V + (size_t)p * k, *vq = V + (size_t)q * k;
-                for (int i = lane; i < k; i += 32) {
-                    const double a = mp[i], b = mq[i], e = vp[i], f = vq[i];
-                    mp[i] = c * a - s * b; mq[i] = s * a + c * b;
-                    vp[i] = c * e - s * f; vq[i] = s * e + c * f;
+                double *mp = M + (size_t)p * ld, *mq = M + (size_t)q * ld;
+                for (int i = lane; i < k; i += 32) { const double a = mp[i], b = mq[i]; mp[i] = c * a - s * b; mq[i] = s * a + c * b; }
+                if (V) {
+                    double *vp = V + (size_t)p * ldv, *vq = V + (size_t)q * ldv;
+                    for (int i = lane; i < k; i += 32) { const double e = vp[i], f = vq[i]; vp[i] = c * e - s * f; vq[i] = s * e + c * f; }
                 }
             }
             __syncthreads();
-            for (int t = wid; t < half; t += nwarp) {         // rows p, q of M
+            for (int t = wid; t < half; t += nwarp) {         // rows p, q of M (and T)
                 const double c = cs[2 * t], s = cs[2 * t + 1];
                 if (s == 0.0) continue;
                 int p, q; jacobi_pair(t, r, kp, p, q);
                 for (int j = lane; j < k; j += 32) {
-                    const double a = M[p + (size_t)j * k], b = M[q + (size_t)j * k];
-                    M[p + (size_t)j * k] = c * a - s * b; M[q + (size_t)j * k] = s * a + c * b;
+                    const double a = M[p + (size_t)j * ld], b = M[q + (size_t)j * ld];
+                    M[p + (size_t)j * ld] = c * a - s * b; M[q + (size_t)j * ld] = s * a + c * b;
+                }
+                if (T) for (int j = lane; j < nct; j += 32) {
+                    const double a = T[p + (size_t)j * ldt], b = T[q + (size_t)j * ldt];
+                    T[p + (size_t)j * ldt] = c * a - s * b; T[q + (size_t)j * ldt] = s * a + c * b;
                 }
             }
             // every thread has read last sweep's verdict by now (it did so before this sweep's first column pass)
@@ -98,9 +117,9 @@ CERB_D int jacobi_eig(double *M, double *V, int k, double *cs, int *flag) {
             __syncthreads();
             // keep M exactly symmetric: the column and the row pass round differently, and an asymmetric residue of eps |M| is enough to
             // keep the null space of a rank-deficient Schur complement rotating for ever (the angles are taken from the upper triangle)
-            for (int e = tid; e < k * k; e += nt) { const int i = e % k, j = e / k; if (i > j) M[e] = M[j + (size_t)i * k]; }
-            if (r + 1 < rounds) jacobi_angles(M, k, kp, r + 1, cs, flag + (sweeps & 1));
-            else jacobi_angles(M, k, kp, 0, cs, flag + ((sweeps + 1) & 1));
+            for (int e = tid; e < k * k; e += nt) { const int i = e % k, j = e / k; if (i > j) M[i + (size_t)j * ld] = M[j + (size_t)i * ld]; }
+            if (r + 1 < rounds) jacobi_angles(M, ld, k, kp, r + 1, cs, flag + (sweeps & 1));
+            else jacobi_angles(M, ld, k, kp, 0, cs, flag + ((sweeps + 1) & 1));
             __syncthreads();
         }
         if (!flag[sweeps & 1]) break;
@@ -117,62 +136,50 @@ CERB_GLOBAL void marg_schur_kernel(int n_windows, int mmax, int nmax, const int 
     CERB_DYN_SMEM(double, sm);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int kmax = mmax > nmax ? mmax : nmax;
-    double *cs = sm; int *flag = reinterpret_cast<int *>(sm + kmax + 1);
+    double *cs = sm, *inv = sm + (kmax + 2); int *flag = reinterpret_cast<int *>(sm + 2 * (kmax + 2));
+    double *body = sm + marg_fixed_doubles(mmax, nmax);
+    const bool m1_smem = marg_m1_in_smem(mmax, nmax), t_smem = marg_t_in_smem(mmax, nmax);
+    double *wsp = ws_all + (size_t)blockIdx.x * marg_ws_doubles(mmax, nmax);
+    double *Tg = wsp, *M1g = Tg + (size_t)marg_ld(mmax) * (nmax + 1), *br = M1g + (m1_smem ? 0 : (size_t)marg_ld(mmax) * marg_ld(mmax));
     for (int w = blockIdx.x; w < n_windows; w += gridDim.x) {
         const int m = dims ? dims[4 * w] : mmax, n = dims ? dims[4 * w + 1] : nmax;
         if (dims && dims[4 * w + 2] != 1) continue;
-        const int pos = m + n, nc = n + 1;
-        double *M1 = ws_all + (size_t)blockIdx.x * marg_ws_doubles(mmax, nmax), *V1 = M1 + (size_t)m * m, *Y = V1 + (size_t)m * m, *X = Y + (size_t)m * nc;
-        double *T2 = X + (size_t)m * nc, *M2 = T2 + (size_t)n * n, *V2 = M2 + (size_t)n * n, *br = V2 + (size_t)n * n;
+        const int pos = m + n, nc = n + 1, ld1 = marg_ld(m), ld2 = marg_ld(n), ldt = marg_ld(m);
         const double *A = A_all + (size_t)w * (A_stride ? A_stride : (long)pos * pos), *b = b_all + (size_t)w * (b_stride ? b_stride : (long)pos);
-        for (int e = tid; e < m * m; e += nt) { const int i = e % m, j = e / m; M1[e] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); }
+        // ---- phase 1: Amm = 0.5 (Amm + Amm^T) = V1 diag(lambda) V1^T;  T = V1^T [Amr | bm] --------------------------------------
+        double *M1 = m1_smem ? body : M1g;
+        for (int e = tid; e < m * m; e += nt) { const int i = e % m, j = e / m; M1[i + (size_t)j * ld1] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); }
+        for (int e = tid; e < m * nc; e += nt) { const int c = e % nc, i = e / nc; Tg[i + (size_t)c * ldt] = c < n ? A[(size_t)i * pos + m + c] : b[i]; }
         __syncthreads();
-        const int sw1 = jacobi_eig(M1, V1, m, cs, flag);
-        // Y = diag(inv) V1^T [Amr | bm]
-        for (int e = tid; e < m * nc; e += nt) {
-            const int c = e % nc, kk = e / nc;
-            const double lam = M1[kk + (size_t)kk * m];
-            double acc = 0.0;
-            if (lam > eps) {
-                const double *v = V1 + (size_t)kk * m;
-                if (c < n) for (int i = 0; i < m; i++) acc += v[i] * A[(size_t)i * pos + m + c];
-                else for (int i = 0; i < m; i++) acc += v[i] * b[i];
-                acc *= 1.0 / lam;
-            }
-            Y[kk + (size_t)c * m] = acc;
-        }
+        const int sw1 = jacobi_eig(M1, ld1, m, nullptr, 0, Tg, ldt, nc, cs, flag);
+        for (int i = tid; i < m; i += nt) { const double lam = M1[i + (size_t)i * ld1]; inv[i] = lam > eps ? 1.0 / lam : 0.0; }
         __syncthreads();
-        // X = V1 Y = Amm_inv [Amr | bm]
-        for (int e = tid; e < m * nc; e += nt) {
-            const int i = e % m, c = e / m;
-            const double *y = Y + (size_t)c * m;
-            double acc = 0.0;
-            for (int kk = 0; kk < m; kk++) acc += V1[i + (size_t)kk * m] * y[kk];
-            X[i + (size_t)c * m] = acc;
-        }
-        __syncthreads();
-        // [Ar | br] = [Arr | brr] - Arm X
+        // ---- [Ar | br] = [Arr | brr] - T^T diag(inv) T (lower triangle; SelfAdjointEigenSolver reads the lower triangle) ---------------
+        double *Ts = t_smem ? body : Tg, *M2 = t_smem ? body + (size_t)ldt * nc : body;
+        if (t_smem) { for (int e = tid; e < m * nc; e += nt) { const int i = e % m, c = e / m; Ts[i + (size_t)c * ldt] = Tg[i + (size_t)c * ldt]; } __syncthreads(); }
         for (int e = tid; e < n * nc; e += nt) {
-            const int c = e % nc, r = e / nc;
-            const double *arow = A + (size_t)(m + r) * pos, *x = X + (size_t)c * m;
+            const int r = e % n, c = e / n;
+            if (c < n && c > r) continue;
+            const double *tr = Ts + (size_t)r * ldt, *tc = Ts + (size_t)c * ldt;
             double acc = 0.0;
-            for (int i = 0; i < m; i++) acc += arow[i] * x[i];
-            if (c < n) T2[r + (size_t)c * n] = arow[m + c] - acc; else br[r] = b[m + r] - acc;
+            for (int i = 0; i < m; i++) acc += tr[i] * inv[i] * tc[i];
+            if (c < n) { const double v = A[(size_t)(m + r) * pos + m + c] - acc; M2[r + (size_t)c * ld2] = v; M2[c + (size_t)r * ld2] = v; }
+            else br[r] = b[m + r] - acc;
         }
         __syncthreads();
-        for (int e = tid; e < n * n; e += nt) { const int i = e % n, j = e / n; M2[e] = i >= j ? T2[i + (size_t)j * n] : T2[j + (size_t)i * n]; }
-        __syncthreads();
-        const int sw2 = jacobi_eig(M2, V2, n, cs, flag);
+        // ---- phase 2: A = V2 diag(lambda) V2^T;  linearized_jacobians = sqrt(S) V2^T, linearized_residuals = sqrt(S_inv) V2^T b ----------
+        double *V2 = (t_smem && (size_t)ldt * nc >= (size_t)ld2 * ld2) ? body : M2 + (size_t)ld2 * ld2;      // over the dead T if it is large enough, else behind M2
+        const int sw2 = jacobi_eig(M2, ld2, n, V2, ld2, nullptr, 0, 0, cs, flag);
         double *Jo = lin_J + (size_t)w * (J_stride ? J_stride : (long)n * n), *ro = lin_r + (size_t)w * (r_stride ? r_stride : (long)n);
         for (int e = tid; e < n * n; e += nt) {
             const int kk = e % n, j = e / n;
-            const double lam = M2[kk + (size_t)kk * n];
-            Jo[e] = lam > eps ? sqrt(lam) * V2[j + (size_t)kk * n] : 0.0;
+            const double lam = M2[kk + (size_t)kk * ld2];
+            Jo[e] = lam > eps ? sqrt(lam) * V2[j + (size_t)kk * ld2] : 0.0;
         }
         for (int kk = tid; kk < n; kk += nt) {
-            const double lam = M2[kk + (size_t)kk * n];
+            const double lam = M2[kk + (size_t)kk * ld2];
             double acc = 0.0;
-            if (lam > eps) { const double *v = V2 + (size_t)kk * n; for (int i = 0; i < n; i++) acc += v[i] * br[i]; acc *= sqrt(1.0 / lam); }
+            if (lam > eps) { const double *v = V2 + (size_t)kk * ld2; for (int i = 0; i < n; i++) acc += v[i] * br[i]; acc *= sqrt(1.0 / lam); }
             ro[kk] = acc;
         }
         if (sweeps && tid == 0) { sweeps[2 * w] = sw1; sweeps[2 * w + 1] = sw2; }

@@ -1614,7 +1614,7 @@ struct MargParams {
     double *A, *b;                   // [n][posmax * posmax] row-major (leading dimension pos of the window), [n][posmax]
     int posmax;
     int *dims;                       // [n][4]: m, n, status (1: prior produced, 0: none (m == 0), 2: old prior carried over unchanged), number of kept blocks
-    int *blocks;                     // [n][16][3]: kind, index AFTER the address shift of the slide, column, of every kept block
+    int *blocks;                     // [n][16][4]: kind, index AFTER the address shift of the slide, column, index in the window being marginalized, of every kept block
 };
 enum { MARG_OLD = 0, MARG_SECOND_NEW = 1 };
 
@@ -1712,16 +1712,17 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) marg_assemble_kernel(CERB_G
             }
             for (int k = 0; k < 80 + 32; k++) colx[k] = -1;
             int m = 0, n = 0, status = 1, nblk = 0;
-            int *blk = M.blocks + (size_t)w * 48;
+            int *blk = M.blocks + (size_t)w * 64;
+#define MARG_BLK(kind_, shifted_, src_) do { blk[4 * nblk] = (kind_); blk[4 * nblk + 1] = (shifted_); blk[4 * nblk + 2] = n; blk[4 * nblk + 3] = (src_); nblk++; } while (0)
             if (flag == MARG_OLD) {
                 if (pose[0]) { for (int k = 0; k < 6; k++) colx[k] = m + k; m += 6; }
                 if (sb[0]) { for (int k = 0; k < 9; k++) coly[k] = m + k; m += 9; }
                 if (lb[0]) { for (int k = 0; k < 4; k++) coly[9 + k] = m + k; m += 4; }
                 m += n0;                                                   // lambda k -> column (m - n0) + k
                 if (m == 0) status = 0;                                    // MarginalizationInfo::valid = false (marginalization_factor.cpp:205-210)
-                for (int j = 1; j < NFR; j++) if (pose[j]) { for (int k = 0; k < 6; k++) colx[6 * j + k] = m + n + k; blk[3 * nblk] = 0; blk[3 * nblk + 1] = j - 1; blk[3 * nblk + 2] = n; nblk++; n += 6; }
-                if (sb[1]) { for (int k = 0; k < 9; k++) coly[13 + k] = m + n + k; blk[3 * nblk] = 1; blk[3 * nblk + 1] = 0; blk[3 * nblk + 2] = n; nblk++; n += 9; }
-                if (lb[1]) { for (int k = 0; k < 4; k++) coly[13 + 9 + k] = m + n + k; blk[3 * nblk] = 2; blk[3 * nblk + 1] = 0; blk[3 * nblk + 2] = n; nblk++; n += 4; }
+                for (int j = 1; j < NFR; j++) if (pose[j]) { for (int k = 0; k < 6; k++) colx[6 * j + k] = m + n + k; MARG_BLK(0, j - 1, j); n += 6; }
+                if (sb[1]) { for (int k = 0; k < 9; k++) coly[13 + k] = m + n + k; MARG_BLK(1, 0, 1); n += 9; }
+                if (lb[1]) { for (int k = 0; k < 4; k++) coly[13 + 9 + k] = m + n + k; MARG_BLK(2, 0, 1); n += 4; }
             } else {
                 if (!has_prior || !pose[CERB_WINDOW - 1]) status = 2;       // prior carried over unchanged (estimator.cpp:1380-1381)
                 else {
@@ -1729,16 +1730,17 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) marg_assemble_kernel(CERB_G
                     m = 6;
                     for (int j = 0; j < NFR; j++) if (pose[j] && j != CERB_WINDOW - 1) {
                         for (int k = 0; k < 6; k++) colx[6 * j + k] = m + n + k;
-                        blk[3 * nblk] = 0; blk[3 * nblk + 1] = (j == CERB_WINDOW) ? j - 1 : j; blk[3 * nblk + 2] = n; nblk++; n += 6;
+                        MARG_BLK(0, (j == CERB_WINDOW) ? j - 1 : j, j); n += 6;
                     }
-                    if (sb[0]) { for (int k = 0; k < 9; k++) coly[k] = m + n + k; blk[3 * nblk] = 1; blk[3 * nblk + 1] = 0; blk[3 * nblk + 2] = n; nblk++; n += 9; }
-                    if (lb[0]) { for (int k = 0; k < 4; k++) coly[9 + k] = m + n + k; blk[3 * nblk] = 2; blk[3 * nblk + 1] = 0; blk[3 * nblk + 2] = n; nblk++; n += 4; }
+                    if (sb[0]) { for (int k = 0; k < 9; k++) coly[k] = m + n + k; MARG_BLK(1, 0, 0); n += 9; }
+                    if (lb[0]) { for (int k = 0; k < 4; k++) coly[9 + k] = m + n + k; MARG_BLK(2, 0, 0); n += 4; }
                 }
             }
             if (status == 1) {
-                for (int e = 0; e < 2; e++) if (ex[e]) { for (int k = 0; k < 6; k++) colx[66 + 6 * e + k] = m + n + k; blk[3 * nblk] = 3; blk[3 * nblk + 1] = e; blk[3 * nblk + 2] = n; nblk++; n += 6; }
-                if (td) { colx[X_TD] = m + n; blk[3 * nblk] = 4; blk[3 * nblk + 1] = 0; blk[3 * nblk + 2] = n; nblk++; n += 1; }
+                for (int e = 0; e < 2; e++) if (ex[e]) { for (int k = 0; k < 6; k++) colx[66 + 6 * e + k] = m + n + k; MARG_BLK(3, e, e); n += 6; }
+                if (td) { colx[X_TD] = m + n; MARG_BLK(4, 0, 0); n += 1; }
             }
+#undef MARG_BLK
             misc[1] = m; misc[2] = n; misc[3] = status;
             int *dm = M.dims + 4 * w; dm[0] = m; dm[1] = n; dm[2] = status; dm[3] = nblk;
         }

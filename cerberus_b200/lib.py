@@ -64,6 +64,7 @@ class Backend:
         L.cerb_register_host_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.cerb_unregister_host_buffer.argtypes = [C.c_void_p, C.c_void_p]
         L.cerb_last_upload_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+        L.cerb_batch_marginalize.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(abi.WindowState), C.POINTER(abi.Prior), C.POINTER(C.c_int32)]
         L.cerb_double2vector.restype = None
         self.cfg = cfg or abi.default_config()
         self.h = C.c_void_p()
@@ -226,6 +227,14 @@ class Backend:
         J = J.reshape(B, n, n).transpose(0, 2, 1)          # column-major on the wire
         return (J, r, sw) if return_sweeps else (J, r)
 
+    def batch_marginalize(self, flags, states, priors):
+        """cerb_batch_marginalize on the resident batch: flags [n] int32 (0 MARGIN_OLD, 1 MARGIN_SECOND_NEW), states: ctypes array of WindowState
+        (or None: the solved states on the device), priors: ctypes array of Prior with their matrix / vector pointers set.  Returns the Jacobi sweeps [n, 2]."""
+        n = len(priors)
+        sw = np.zeros((n, 2), dtype=np.int32)
+        self._check(self.lib.cerb_batch_marginalize(self.h, flags.ctypes.data_as(C.POINTER(C.c_int32)), states, priors, sw.ctypes.data_as(C.POINTER(C.c_int32))))
+        return sw
+
     def marginalize(self, cfg, src, dst, margin_old=True):
         from . import marginalization
-        marginalization.marginalize_batch(self, cfg, src, dst, margin_old)
+        return marginalization.marginalize_batch(self, cfg, src, dst, margin_old)

@@ -377,6 +377,22 @@ int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_
 int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t n, const double *A, const double *b, double eps,
                            double *linearized_jacobians, double *linearized_residuals, int32_t *sweeps);
 
+/* The marginalization half of Estimator::optimization() (estimator.cpp:1247-1456; MarginalizationInfo::{addResidualBlockInfo, preMarginalize,
+ * marginalize}, marginalization_factor.cpp:98-333) for every window of the RESIDENT batch (the descriptors of the last cerb_solve_batch /
+ * cerb_batch_upload: tracks, preintegrations, old prior), entirely on the device: the factors that touch the dropped blocks are linearised
+ * by the solver's own passes (same Huber corrector as ResidualBlockInfo::Evaluate), A = sum J^T J, b = sum J^T r assembled in the
+ * reference's [dropped | kept] order and reduced by the eps = 1e-8 clamped eigen Schur complement (see cerb_marginalize_schur).
+ *   flags  [n]  0: MARGIN_OLD (drop para_Pose[0], para_SpeedBias[0], para_LegBias[0] and the features anchored at frame 0),
+ *               1: MARGIN_SECOND_NEW (drop para_Pose[WINDOW_SIZE - 1] from the old prior; without it the prior is carried over)
+ *   states [n]  the para_* arrays to linearise at -- what vector2double() writes after double2vector() (estimator.cpp:1251 / :1384),
+ *               para_Feature in the caller's feature order; NULL: the solved states as they sit on the device
+ *   priors [n]  out.  On entry linearized_jacobians / linearized_residuals must point at storage for CERB_MAX_PRIOR_DIM^2 / CERB_MAX_PRIOR_DIM
+ *               doubles (written: n x n column-major, n); valid / n / blocks / block_x0 are filled with the block indices already shifted
+ *               to the next window (addr_shift, estimator.cpp:1357-1372 / :1413-1447), ready to be passed as CerbWindowDesc.prior.
+ *   sweeps (optional) [n][2]  Jacobi sweeps of the two eigen-decompositions.
+ * Kept-block order: poses ascending, speed bias, leg bias, ex0, ex1, td (the reference's order is that of an unordered_map keyed by pointer). */
+int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindowState *states, CerbPrior *priors, int32_t *sweeps);
+
 /* ---- host-side helpers that stay on the CPU in the reference too ---------------------------- */
 /* Gauge re-anchoring of Estimator::double2vector (estimator.cpp:903-957): rotates the solved
  * window by the yaw difference of frame 0 and re-anchors its position.  before/after are the

@@ -55,9 +55,16 @@ def main():
     A = np.swapaxes(J, 1, 2) @ J; b = (np.swapaxes(J, 1, 2) @ rng.standard_normal((nwm, 3 * pos, 1)))[..., 0]
     t = wall(lambda: be.marginalize_schur(A, b, m), reps=2)
     print(f"marginalize_schur ({nwm} windows, m={m}, n={n}): {t * 1e3:.2f} ms wall = {t / nwm * 1e6:.1f} us / window")
-    if hasattr(be, "marginalize_resident"):
-        t = wall(lambda: be.marginalize_resident(), reps=2)
-        print(f"marginalize_resident ({NW} windows): {t * 1e3:.2f} ms wall = {t / NW * 1e6:.1f} us / window")
+    # the whole marginalization step on the resident batch (assembly by the solver's linearisation passes + eigen Schur complement), host buffers out
+    flags = np.zeros(NW, dtype=np.int32)
+    J = np.zeros((NW, abi.MAX_PRIOR_DIM * abi.MAX_PRIOR_DIM)); r = np.zeros((NW, abi.MAX_PRIOR_DIM))
+    priors = (abi.Prior * NW)()
+    for w in range(NW):
+        priors[w].linearized_jacobians = J[w].ctypes.data_as(abi.c_dp); priors[w].linearized_residuals = r[w].ctypes.data_as(abi.c_dp)
+    sw = be.batch_marginalize(flags, None, priors)
+    t = wall(lambda: be.batch_marginalize(flags, None, priors), reps=2)
+    print(f"batch_marginalize ({NW} windows x {F} features anchored at frame 0: m = {19 + F}, n = {priors[0].n}; MARGIN_OLD at the solved states): {t * 1e3:.2f} ms wall = {t / NW * 1e6:.1f} us / window, "
+          f"Jacobi sweeps {sw[:, 0].mean():.1f} / {sw[:, 1].mean():.1f}")
 
 
 if __name__ == "__main__":
