@@ -26,6 +26,22 @@
 // registers and without stalling the issuing thread; CERB_CP_ASYNC_WAIT() makes this thread's copies complete
 #define CERB_CP_ASYNC8(dst_smem, src_global) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src_global) : "memory")
 #define CERB_CP_ASYNC_WAIT() asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory")
+// 1-D bulk copy global -> shared through the TMA unit (cp.async.bulk, SASS UBLKCP): ONE thread issues the whole region, completion is
+// signalled on an mbarrier in shared memory (transaction bytes), every consumer waits on the barrier's phase parity.  Addresses and size
+// must be multiples of 16 bytes.  The issuing thread fences the async proxy first (the destination was last touched by generic accesses).
+#define CERB_SMEM_U32(p) ((unsigned)__cvta_generic_to_shared(p))
+#define CERB_MBAR_INIT(bar) do { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(CERB_SMEM_U32(bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); } while (0)
+#define CERB_BULK_G2S(dst_smem, src_global, bytes, bar) do {                                                                                        \
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                                                                 \
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(CERB_SMEM_U32(bar)), "r"((unsigned)(bytes)) : "memory");         \
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"                                      \
+                     ::"r"(CERB_SMEM_U32(dst_smem)), "l"(src_global), "r"((unsigned)(bytes)), "r"(CERB_SMEM_U32(bar)) : "memory");                   \
+    } while (0)
+#define CERB_MBAR_WAIT(bar, parity) do {                                                                                                             \
+        unsigned done_ = 0;                                                                                                                          \
+        while (!done_) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"                 \
+                                    : "=r"(done_) : "r"(CERB_SMEM_U32(bar)), "r"((unsigned)(parity)) : "memory");                                    \
+    } while (0)
 // body of a spin-wait on a shared-memory flag (a short sleep keeps the polling warps out of the producer's issue slots)
 #define CERB_SPIN_PAUSE() __nanosleep(20)
 // non-blocking arrival at a named barrier (producer / consumer hand-over: one side arrives, the other side syncs)

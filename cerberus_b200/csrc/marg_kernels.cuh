@@ -17,7 +17,7 @@ namespace cerb {
 #if defined(CERB_CUSIM)
 constexpr int MARG_THREADS = 64;      // the CPU simulator pays ~ one futex wake-up per thread and barrier; two warps still exercise every path
 #else
-constexpr int MARG_THREADS = 256;
+constexpr int MARG_THREADS = 512;      // 64 registers per thread, one CTA per SM (shared memory): more loads in flight for the L2-resident T pass
 #endif
 constexpr int MARG_MAX_SWEEPS = 60;
 
@@ -30,8 +30,8 @@ constexpr size_t MARG_SMEM_MAX = 232448 - 1024;        // 227 KB opt-in limit of
 CERB_HD int marg_ld(int k) { return k | 1; }
 CERB_HD size_t marg_fixed_doubles(int m, int n) { const int k = m > n ? m : n; return 2 * (size_t)(k + 2) + 4; }        // (c, s) pairs | 1 / lambda | flags
 CERB_HD bool marg_m1_in_smem(int m, int n) { return (marg_fixed_doubles(m, n) + (size_t)marg_ld(m) * marg_ld(m)) * sizeof(double) <= MARG_SMEM_MAX; }
-// T staged in shared memory next to M2; V2 then goes over the dead T if T is at least as large, else behind M2
-CERB_HD size_t marg_t_body(int m, int n) { const size_t t = (size_t)marg_ld(m) * (n + 1), q = (size_t)marg_ld(n) * marg_ld(n); return t + q + (t < q ? q : 0); }
+// phase 2 with T staged in shared memory: [M2 | X], X = T during the contraction, V2 afterwards (whatever the m of the window)
+CERB_HD size_t marg_t_body(int m, int n) { const size_t t = (size_t)m * (n + 1), q = (size_t)marg_ld(n) * marg_ld(n); return q + (t > q ? t : q); }
 CERB_HD bool marg_t_in_smem(int m, int n) { return (marg_fixed_doubles(m, n) + marg_t_body(m, n)) * sizeof(double) <= MARG_SMEM_MAX; }
 CERB_HD size_t marg_smem_bytes(int m, int n) {
     size_t body = 2 * (size_t)marg_ld(n) * marg_ld(n);
@@ -41,7 +41,7 @@ CERB_HD size_t marg_smem_bytes(int m, int n) {
 }
 // per-CTA global workspace in doubles: T | M1 (only when it does not fit in shared memory) | br
 CERB_HD size_t marg_ws_doubles(int m, int n) {
-    return (size_t)marg_ld(m) * (n + 1) + (marg_m1_in_smem(m, n) ? 0 : (size_t)marg_ld(m) * marg_ld(m)) + (size_t)n + 8;
+    return (size_t)m * (n + 1) + 1 + (marg_m1_in_smem(m, n) ? 0 : (size_t)marg_ld(m) * marg_ld(m)) + (size_t)n + 8;
 }
 
 // pair t (0 .. kp / 2 - 1) of round r (0 .. kp - 2) of a round-robin tournament over kp (even) players, p < q
@@ -73,7 +73,7 @@ CERB_D void jacobi_angles(const double *M, int ld, int k, int kp, int r, double 
 
 // Eigen-decomposition of the symmetric k x k matrix M (column-major, leading dimension ld): on return the eigenvalues are on the
 // diagonal of M.  V (optional, k x k, leading dimension ldv, set to the identity here): the eigenvectors as columns.  T (optional,
-// k x nct, leading dimension ldt): replaced by V^T T (its rows are rotated like the rows of M).  Called by all threads of the CTA;
+// k x nct ROW-major, leading dimension ldt): replaced by V^T T (its rows are rotated like the rows of M).  Called by all threads of the CTA;
 // returns the number of sweeps.  Three CTA barriers per round: column pass | row pass | re-symmetrisation together with the angles of the
 // next round (both only read the upper triangle the row pass left).  flag[sweep & 1] collects "some rotation was non-trivial".
 CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, int ldt, int nct, double *cs, int *flag) {
@@ -107,9 +107,25 @@ CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, i
                     const double a = M[p + (size_t)j * ld], b = M[q + (size_t)j * ld];
                     M[p + (size_t)j * ld] = c * a - s * b; M[q + (size_t)j * ld] = s * a + c * b;
                 }
-                if (T) for (int j = lane; j < nct; j += 32) {
-                    const double a = T[p + (size_t)j * ldt], b = T[q + (size_t)j * ldt];
-                    T[p + (size_t)j * ldt] = c * a - s * b; T[q + (size_t)j * ldt] = s * a + c * b;
+            }
+            // rows p, q of T (row-major in global memory / L2): a flat loop over (pair, column) so that consecutive threads touch consecutive
+            // addresses, four elements per thread in flight (the pass is bound by L2 latency, not by arithmetic)
+            if (T) {
+                const int total = half * nct;
+                for (int e0 = tid; e0 < total; e0 += 4 * nt) {
+                    double a[4], b[4], cc[4], ss[4]; size_t ip[4], iq[4];
+                    _Pragma("unroll")
+                    for (int u = 0; u < 4; u++) {
+                        const int e = e0 + u * nt;
+                        ss[u] = 0.0; cc[u] = 1.0; a[u] = 0.0; b[u] = 0.0; ip[u] = 0; iq[u] = 0;
+                        if (e < total) {
+                            const int t = e / nct, j = e - t * nct;
+                            cc[u] = cs[2 * t]; ss[u] = cs[2 * t + 1];
+                            if (ss[u] != 0.0) { int p, q; jacobi_pair(t, r, kp, p, q); ip[u] = (size_t)p * ldt + j; iq[u] = (size_t)q * ldt + j; a[u] = T[ip[u]]; b[u] = T[iq[u]]; }
+                        }
+                    }
+                    _Pragma("unroll")
+                    for (int u = 0; u < 4; u++) if (ss[u] != 0.0) { T[ip[u]] = cc[u] * a[u] - ss[u] * b[u]; T[iq[u]] = ss[u] * a[u] + cc[u] * b[u]; }
                 }
             }
             // every thread has read last sweep's verdict by now (it did so before this sweep's first column pass)
@@ -140,35 +156,35 @@ CERB_GLOBAL void marg_schur_kernel(int n_windows, int mmax, int nmax, const int 
     double *body = sm + marg_fixed_doubles(mmax, nmax);
     const bool m1_smem = marg_m1_in_smem(mmax, nmax), t_smem = marg_t_in_smem(mmax, nmax);
     double *wsp = ws_all + (size_t)blockIdx.x * marg_ws_doubles(mmax, nmax);
-    double *Tg = wsp, *M1g = Tg + (size_t)marg_ld(mmax) * (nmax + 1), *br = M1g + (m1_smem ? 0 : (size_t)marg_ld(mmax) * marg_ld(mmax));
+    double *Tg = wsp, *M1g = Tg + (size_t)mmax * (nmax + 1) + 1, *br = M1g + (m1_smem ? 0 : (size_t)marg_ld(mmax) * marg_ld(mmax));
     for (int w = blockIdx.x; w < n_windows; w += gridDim.x) {
         const int m = dims ? dims[4 * w] : mmax, n = dims ? dims[4 * w + 1] : nmax;
         if (dims && dims[4 * w + 2] != 1) continue;
-        const int pos = m + n, nc = n + 1, ld1 = marg_ld(m), ld2 = marg_ld(n), ldt = marg_ld(m);
+        const int pos = m + n, nc = n + 1, ld1 = marg_ld(m), ld2 = marg_ld(n), ldt = nc;       // T: m rows of nc doubles
         const double *A = A_all + (size_t)w * (A_stride ? A_stride : (long)pos * pos), *b = b_all + (size_t)w * (b_stride ? b_stride : (long)pos);
         // ---- phase 1: Amm = 0.5 (Amm + Amm^T) = V1 diag(lambda) V1^T;  T = V1^T [Amr | bm] --------------------------------------
         double *M1 = m1_smem ? body : M1g;
         for (int e = tid; e < m * m; e += nt) { const int i = e % m, j = e / m; M1[i + (size_t)j * ld1] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); }
-        for (int e = tid; e < m * nc; e += nt) { const int c = e % nc, i = e / nc; Tg[i + (size_t)c * ldt] = c < n ? A[(size_t)i * pos + m + c] : b[i]; }
+        for (int e = tid; e < m * nc; e += nt) { const int c = e % nc, i = e / nc; Tg[(size_t)i * ldt + c] = c < n ? A[(size_t)i * pos + m + c] : b[i]; }
         __syncthreads();
         const int sw1 = jacobi_eig(M1, ld1, m, nullptr, 0, Tg, ldt, nc, cs, flag);
         for (int i = tid; i < m; i += nt) { const double lam = M1[i + (size_t)i * ld1]; inv[i] = lam > eps ? 1.0 / lam : 0.0; }
         __syncthreads();
         // ---- [Ar | br] = [Arr | brr] - T^T diag(inv) T (lower triangle; SelfAdjointEigenSolver reads the lower triangle) ---------------
-        double *Ts = t_smem ? body : Tg, *M2 = t_smem ? body + (size_t)ldt * nc : body;
-        if (t_smem) { for (int e = tid; e < m * nc; e += nt) { const int i = e % m, c = e / m; Ts[i + (size_t)c * ldt] = Tg[i + (size_t)c * ldt]; } __syncthreads(); }
+        const size_t tsz = (size_t)m * nc;
+        double *M2 = body, *Ts = t_smem ? body + (size_t)ld2 * ld2 : Tg;
+        if (t_smem) { for (int e = tid; e < (int)tsz; e += nt) Ts[e] = Tg[e]; __syncthreads(); }
         for (int e = tid; e < n * nc; e += nt) {
             const int r = e % n, c = e / n;
             if (c < n && c > r) continue;
-            const double *tr = Ts + (size_t)r * ldt, *tc = Ts + (size_t)c * ldt;
             double acc = 0.0;
-            for (int i = 0; i < m; i++) acc += tr[i] * inv[i] * tc[i];
+            for (int i = 0; i < m; i++) acc += Ts[(size_t)i * ldt + r] * inv[i] * Ts[(size_t)i * ldt + c];
             if (c < n) { const double v = A[(size_t)(m + r) * pos + m + c] - acc; M2[r + (size_t)c * ld2] = v; M2[c + (size_t)r * ld2] = v; }
             else br[r] = b[m + r] - acc;
         }
         __syncthreads();
         // ---- phase 2: A = V2 diag(lambda) V2^T;  linearized_jacobians = sqrt(S) V2^T, linearized_residuals = sqrt(S_inv) V2^T b ----------
-        double *V2 = (t_smem && (size_t)ldt * nc >= (size_t)ld2 * ld2) ? body : M2 + (size_t)ld2 * ld2;      // over the dead T if it is large enough, else behind M2
+        double *V2 = M2 + (size_t)ld2 * ld2;                                               // over the dead staged T
         const int sw2 = jacobi_eig(M2, ld2, n, V2, ld2, nullptr, 0, 0, cs, flag);
         double *Jo = lin_J + (size_t)w * (J_stride ? J_stride : (long)n * n), *ro = lin_r + (size_t)w * (r_stride ? r_stride : (long)n);
         for (int e = tid; e < n * n; e += nt) {

@@ -33,6 +33,10 @@ __device__ unsigned long long g_phase_cycles[48];
 #endif
 
 enum { CERB_WINDOW = 10, NX = 79, NYB = 13, NFR = 11, NY = 143, NR = 222, NRP = 224, HXX_SZ = 79 * 79, HXY_SZ = 79 * 143, X_TD = 78, SOLVE_THREADS = 256, FT = 64, TILE_LD = 33, NOBS_PLANES = 9 };
+// prior Hessian image in global memory: [Hxx (6241) | pad (1) | Hxy | Ad | Bo]: both parts start on 16-byte boundaries and have sizes that are
+// multiples of 16 bytes, so that each is ONE bulk copy (TMA 1-D, cp.async.bulk); shared memory has the same pad after Hxx (+ two mbarriers)
+enum { PIMG_HXY = HXX_SZ + 1, PIMG_REST = HXY_SZ + 1859 + 1690, PIMG_SZ = PIMG_HXY + PIMG_REST, SMEM_HXX_PAD = 3 };
+static_assert((PIMG_HXY * 8) % 16 == 0 && (PIMG_REST * 8) % 16 == 0 && ((HXX_SZ + SMEM_HXX_PAD) * 8) % 16 == 0, "bulk-copy alignment of the prior image");
 
 struct SolveParams {
     int n_windows, maxF, maxObs, max_iters, optimize_leg_bias;
@@ -58,7 +62,7 @@ struct SolveParams {
 CERB_HD long ws_W(int) { return 0; }                                        // [NX][F]
 CERB_HD long ws_vecs(int F) { return (long)NX * F; }                        // 8 vectors of F: hh, gl, sl, Dl, ghl, gnl, stl, lamc
 CERB_HD long ws_prior(int F) { return (long)NX * F + 8L * F; }              // image of the prior Hessian in the layout of Hxx | Hxy | Ad | Bo
-CERB_HD long ws_chunks(int F) { return ws_prior(F) + HXX_SZ + HXY_SZ + 1859 + 1690; }   // feature chunk table (ints)
+CERB_HD long ws_chunks(int F) { return ws_prior(F) + PIMG_SZ; }                          // feature chunk table (ints)
 CERB_HD long ws_imuplan(int F) { return (ws_chunks(F) + (F + 4) / 2 + 8 + 1) & ~1L; }                  // scatter plan of the IMU-leg Gram matrix (ints)
 CERB_HD long ws_size(int F) { return ws_imuplan(F) + 15 * 2 * 32 * 4 / 2 + 8; }                            // even: the plan is read as int4
 
@@ -76,13 +80,14 @@ struct Smem {
     double *idg;                            // 143 (+pad): 1 / diag(L) of the block-bidiagonal factor of Hyy
     double *idx;                            // 79 (+pad): 1 / diag(L) of the dense factor of the reduced camera system
     int *ti;                                // 128 ints: anchor per tile factor ; + misc ints
+    unsigned long long *mbar;               // two mbarriers (bulk copies of the prior image: [0] Hxx part, [1] Hxy | Ad | Bo part)
     double *tile;                           // alias of Hxy (+ Ad, Bo): 256 x TILE_LD tile + 8 x 640 partial Gram tiles
 };
-enum { SMEM_DOUBLES = HXX_SZ + HXY_SZ + 1859 + 1690 + 7 * NRP + 2 * ST_STRIDE + 99 + 18 + 3 + 31 * 39 + 960 + 192 + 8 * 256 + 128 * 8 + 64 + 66 + 144 + 80 };
+enum { SMEM_DOUBLES = HXX_SZ + SMEM_HXX_PAD + HXY_SZ + 1859 + 1690 + 7 * NRP + 2 * ST_STRIDE + 99 + 18 + 3 + 31 * 39 + 960 + 192 + 8 * 256 + 128 * 8 + 64 + 66 + 144 + 80 };
 
 CERB_D void smem_carve(double *base, Smem &s) {
     double *p = base;
-    s.Hxx = p; p += HXX_SZ; s.Hxy = p; p += HXY_SZ; s.Ad = p; p += 1859; s.Bo = p; p += 1690;
+    s.Hxx = p; p += HXX_SZ; s.mbar = reinterpret_cast<unsigned long long *>(p + 1); p += SMEM_HXX_PAD; s.Hxy = p; p += HXY_SZ; s.Ad = p; p += 1859; s.Bo = p; p += 1690;
     s.g = p; p += NRP; s.sc = p; p += NRP; s.D = p; p += NRP; s.gh = p; p += NRP; s.gn = p; p += NRP; s.stp = p; p += NRP; s.yv = p; p += NRP;
     s.xs = p; p += ST_STRIDE; s.xc = p; p += ST_STRIDE;
     s.Rw = p; p += 99; s.Rex = p; p += 18; p += 3;
@@ -848,7 +853,7 @@ CERB_D bool build_prior_image(const SolveParams &P, Smem &s, int w, double *pimg
     const bool has_prior = pmeta[0] != 0;
     if (has_prior) {
         const int n = pmeta[1], nb = pmeta[2];
-        for (int k = tid; k < HXX_SZ + HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) pimg[k] = 0.0;
+        for (int k = tid; k < PIMG_SZ; k += SOLVE_THREADS) pimg[k] = 0.0;
         if (tid < nb) {
             const int kind = pmeta[4 + 3 * tid], index = pmeta[5 + 3 * tid], col = pmeta[6 + 3 * tid];
             const int local = (kind == 0 || kind == 3) ? 6 : prior_block_size(kind);
@@ -863,7 +868,7 @@ CERB_D bool build_prior_image(const SolveParams &P, Smem &s, int w, double *pimg
             }
         }
         __syncthreads();
-        Smem si = s; si.Hxx = pimg; si.Hxy = pimg + HXX_SZ; si.Ad = pimg + HXX_SZ + HXY_SZ; si.Bo = pimg + HXX_SZ + HXY_SZ + 1859;
+        Smem si = s; si.Hxx = pimg; si.Hxy = pimg + PIMG_HXY; si.Ad = pimg + PIMG_HXY + HXY_SZ; si.Bo = pimg + PIMG_HXY + HXY_SZ + 1859;
         const double *Hp = P.prior_Hp + (size_t)w * PRIOR_LD * PRIOR_LD;
         for (int idx = tid; idx < n * n; idx += SOLVE_THREADS) {
             const int a = idx / n, b = idx % n;
@@ -891,6 +896,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
            S_OK, S_DONE, S_TERM, S_ITER, S_NSUCC, S_INVALID, S_GMAX, S_INIT_COST, S_P, S_Q, S_VHV, S_LCOST, S_LNORM, S_LGMAX };
 
     PH_DECL();
+    unsigned par0 = 0, par1 = 0;                                          // phase parities of the two bulk-copy mbarriers (uniform over the CTA)
+    if (tid == 0) { CERB_MBAR_INIT(&s.mbar[0]); CERB_MBAR_INIT(&s.mbar[1]); }
     if (tid < 32) {
         // Scatter plan of the 40 x 40 IMU-leg Gram matrix (inertial_linearize): lane `tid` holds, for block q = (mi, ni) and
         // e = 0, 1, the entry (la, lb) = (8 mi + lane / 4, 8 ni + 2 (lane % 4) + e).  Its destination in Hxx / Hxy / Hyy / g is
@@ -946,6 +953,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
             sca[S_INVALID] = 0; sca[S_DLNORM] = 0;
         }
         __syncthreads();
+        const bool bulk_ok = (reinterpret_cast<uintptr_t>(pimg) & 15) == 0;          // TMA bulk copies need 16-byte aligned sources (max_features even)
         bool need_linearize = true, hxx_prefetched = false, last_accepted = true;
         int iteration = 0, gn_attempts = 0;
 
@@ -954,15 +962,21 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                 // start from the prior Hessian image; its Hxx part was prefetched asynchronously when the previous factorisation of
                 // Hxx had been consumed (the copy overlapped with the rest of that iteration), except for the first linearisation
                 if (!has_prior) { for (int k = tid; k < HXX_SZ; k += SOLVE_THREADS) s.Hxx[k] = 0.0; }
-                else { if (!hxx_prefetched) copy_g2s_async(s.Hxx, pimg, HXX_SZ, tid); CERB_CP_ASYNC_WAIT(); }
+                else if (bulk_ok) {
+                    if (!hxx_prefetched) { __syncthreads(); if (tid == 0) CERB_BULK_G2S(s.Hxx, pimg, PIMG_HXY * 8, &s.mbar[0]); }
+                    CERB_MBAR_WAIT(&s.mbar[0], par0); par0 ^= 1;
+                } else { if (!hxx_prefetched) copy_g2s_async(s.Hxx, pimg, HXX_SZ, tid); CERB_CP_ASYNC_WAIT(); }
                 hxx_prefetched = false;
                 for (int k = tid; k < NRP; k += SOLVE_THREADS) s.g[k] = 0.0;
                 load_geometry(xl, s, tid);
                 double part[2];
                 PH_MARK(0);
                 part[0] = vision_linearize(P, w, xl, laml, W, hh, gl, sl, !first, chunks, tid);
-                if (has_prior) copy_g2s_async(s.Hxy, pimg + HXX_SZ, HXY_SZ + 1859 + 1690, tid);              // Hxy | Ad | Bo (contiguous; the tile aliased them);
-                else for (int k = tid; k < HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) s.Hxy[k] = 0.0;         // completed inside inertial_linearize
+                if (has_prior && bulk_ok) {                                                                  // Hxy | Ad | Bo (contiguous; the tile aliased them):
+                    if (tid == 0) CERB_BULK_G2S(s.Hxy, pimg + PIMG_HXY, PIMG_REST * 8, &s.mbar[1]);            // one bulk copy (vision_linearize ended with a barrier)
+                    CERB_MBAR_WAIT(&s.mbar[1], par1); par1 ^= 1;
+                } else if (has_prior) copy_g2s_async(s.Hxy, pimg + PIMG_HXY, PIMG_REST, tid);                 // completed inside inertial_linearize
+                else for (int k = tid; k < PIMG_REST; k += SOLVE_THREADS) s.Hxy[k] = 0.0;
                 __syncthreads();
                 PH_MARK(1);
                 part[0] += inertial_linearize(P, w, xl, tid);
@@ -1394,7 +1408,11 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                         s.yv[tid] = y0; s.yv[32 + tid] = y1; if (64 + tid < NX) s.yv[64 + tid] = y2;
                     }
                     __syncthreads();
-                    if (has_prior) { copy_g2s_async(s.Hxx, pimg, HXX_SZ, tid); hxx_prefetched = true; }     // the factor of Hxx is dead from here on
+                    if (has_prior) {                                                                         // the factor of Hxx is dead from here on
+                        if (bulk_ok) { if (tid == 0) CERB_BULK_G2S(s.Hxx, pimg, PIMG_HXY * 8, &s.mbar[0]); }
+                        else copy_g2s_async(s.Hxx, pimg, HXX_SZ, tid);
+                        hxx_prefetched = true;
+                    }
                     PH_MARK(11);
                     // ---- y part: u = gy' - T^T y_x, then L^T y_y = u blockwise (warp 0) ------------------------------------
                     for (int q = tid; q < NY; q += SOLVE_THREADS) { double t = 0.0; for (int a = 0; a < NX; a++) t += s.Hxy[a * NY + q] * s.yv[a]; s.yv[NX + q] -= t; }
@@ -1585,7 +1603,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
             PH_MARK(18);
         }
         // ---- write back ---------------------------------------------------------------------------------
-        CERB_CP_ASYNC_WAIT();                                           // drain a prefetch of the prior image that was never consumed
+        if (bulk_ok && hxx_prefetched) { CERB_MBAR_WAIT(&s.mbar[0], par0); par0 ^= 1; }   // drain a prefetch of the prior image that was never consumed
+        CERB_CP_ASYNC_WAIT();
         for (int k = tid; k < ST_SIZE; k += SOLVE_THREADS) P.state[(size_t)w * ST_STRIDE + k] = s.xs[k];
         if (tid == 0) {
             P.rep_i[4 * w + 0] = iteration; P.rep_i[4 * w + 1] = (int)sca[S_NSUCC]; P.rep_i[4 * w + 2] = (int)sca[S_TERM];
@@ -1693,7 +1712,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) marg_assemble_kernel(CERB_G
         load_geometry(s.xs, s, tid);
         if (n0 > 0) vision_linearize(P, w, s.xs, lam, W, hh, gl, sl, false, chunks, tid);
         __syncthreads();
-        if (has_prior) copy_g2s(s.Hxy, pimg + HXX_SZ, HXY_SZ + 1859 + 1690, tid);
+        if (has_prior) copy_g2s(s.Hxy, pimg + PIMG_HXY, PIMG_REST, tid);
         else for (int k = tid; k < HXY_SZ + 1859 + 1690; k += SOLVE_THREADS) s.Hxy[k] = 0.0;
         __syncthreads();
         inertial_linearize(P, w, s.xs, tid);

@@ -44,6 +44,10 @@ inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cusim::wa
 #define CERB_CP_ASYNC8(dst_smem, src_global) (*(dst_smem) = *(src_global))
 #define CERB_CP_ASYNC_WAIT() ((void)0)
 #define CERB_SPIN_PAUSE() std::this_thread::yield()
+// TMA bulk copy + mbarrier: the issuing thread copies at once, the (uniformly executed) wait is a block barrier
+#define CERB_MBAR_INIT(bar) ((void)0)
+#define CERB_BULK_G2S(dst_smem, src_global, bytes, bar) std::memcpy((dst_smem), (src_global), (bytes))
+#define CERB_MBAR_WAIT(bar, parity) __syncthreads()
 // named barriers (bar.sync id, nthreads) among subsets of the warps of a block
 namespace cusim { void named_sync(int id, int nthreads); void named_arrive(int id, int nthreads); }
 #define CERB_BAR_ARRIVE(id, nthreads) cusim::named_arrive((id), (nthreads))
