@@ -105,11 +105,12 @@ def run_reference(args, rank, world):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from cerberus_b200 import abi, synth
     from oracle_lib import OracleBackend
+    NW, F = args.windows, args.features
     cfg = abi.default_config()
+    cfg.max_batch, cfg.max_features, cfg.max_obs = NW, ((F + 7) // 8) * 8 + 8, (((F + 7) // 8) * 8 + 8) * abi.NUM_FRAMES
     ob = OracleBackend(cfg)
     cores = usable_cpus()
-    NW, F = args.windows, args.features
-    base = synth.generate_batch(min(NW, CPU_SAMPLE), F, ob, prior_features=PRIOR_FEATURES)
+    base = synth.generate_batch(min(NW, CPU_SAMPLE if F <= 200 else 32), F, ob, cfg=cfg, prior_features=PRIOR_FEATURES)
     batch = synth.tile_batch(base, NW) if NW > base.n else base       # the preintegration set-up of 1024 windows on the CPU would take minutes; the solve does not care
     saved = batch.copy_states()
     nthreads = min(cores, NW)
@@ -163,6 +164,7 @@ def main():
     ap.add_argument("--windows", type=int, default=WINDOWS_PER_GPU)
     ap.add_argument("--features", type=int, default=FEATURES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic windows to generate (tiled up to --windows); 0: all distinct up to 200 features, else 64")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,7 +191,11 @@ def main():
     cfg.max_batch, cfg.max_features, cfg.max_obs = NW, ((F + 7) // 8) * 8 + 8, (((F + 7) // 8) * 8 + 8) * abi.NUM_FRAMES
     gpu = lib.Backend(cfg)                                     # no CPU fallback: raises without CUDA
     t_setup = time.perf_counter()
-    batch = synth.generate_batch(NW, F, gpu, cfg=cfg, window0=rank * NW, prior_features=PRIOR_FEATURES)
+    distinct = args.distinct or (NW if F <= 200 else min(NW, 64))
+    if distinct >= NW:
+        batch = synth.generate_batch(NW, F, gpu, cfg=cfg, window0=rank * NW, prior_features=PRIOR_FEATURES)
+    else:       # stress sizes: the numpy set-up of thousands of 2000-feature windows would dominate the run; the solver does not care
+        batch = synth.tile_batch(synth.generate_batch(distinct, F, gpu, cfg=cfg, window0=rank * NW, prior_features=PRIOR_FEATURES), NW)
     saved = batch.copy_states()
     t_setup = time.perf_counter() - t_setup
 

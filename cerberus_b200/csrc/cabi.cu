@@ -108,7 +108,7 @@ void cerb_default_preint_config(CerbPreintConfig *p) {
 
 int cerb_create(const CerbSolverConfig *cfg, CerbHandle **out) {
     if (!cfg || !out) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_create: null argument");
-    if (cfg->max_batch < 1 || cfg->max_features < 1 || cfg->max_features > CERB_NUM_OF_F || cfg->max_obs < 1)
+    if (cfg->max_batch < 1 || cfg->max_features < 1 || cfg->max_features > CERB_MAX_FEATURES || cfg->max_obs < 1)
         return fail(CERB_ERR_BAD_ARGUMENT, "cerb_create: bad capacities");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device)

@@ -28,7 +28,7 @@ constexpr int MARG_MAX_SWEEPS = 60;
 //   phase 2  T staged in shared memory for the contraction, M2 and V2 (n x n, n <= 96) in shared memory
 constexpr size_t MARG_SMEM_MAX = 232448 - 1024;        // 227 KB opt-in limit of sm_100 minus static shared memory head-room
 CERB_HD int marg_ld(int k) { return k | 1; }
-CERB_HD size_t marg_fixed_doubles(int m, int n) { const int k = m > n ? m : n; return 2 * (size_t)(k + 2) + 4; }        // (c, s) pairs | 1 / lambda | flags
+CERB_HD size_t marg_fixed_doubles(int m, int n) { const int k = m > n ? m : n; return 2 * (size_t)(k + 2) + 4 + (size_t)(k + 2) / 2 + 2; }   // (c, s) pairs | 1 / lambda | flags | pair table
 CERB_HD bool marg_m1_in_smem(int m, int n) { return (marg_fixed_doubles(m, n) + (size_t)marg_ld(m) * marg_ld(m)) * sizeof(double) <= MARG_SMEM_MAX; }
 // phase 2 with T staged in shared memory: [M2 | X], X = T during the contraction, V2 afterwards (whatever the m of the window)
 CERB_HD size_t marg_t_body(int m, int n) { const size_t t = (size_t)m * (n + 1), q = (size_t)marg_ld(n) * marg_ld(n); return q + (t > q ? t : q); }
@@ -53,8 +53,9 @@ CERB_D void jacobi_pair(int t, int r, int kp, int &p, int &q) {
     p = a < b ? a : b; q = a < b ? b : a;
 }
 
-// rotation angles of round r from the upper triangle of M as it stands; (c, s) -> cs, a non-trivial rotation raises *flag
-CERB_D void jacobi_angles(const double *M, int ld, int k, int kp, int r, double *cs, int *flag) {
+// rotation angles of round r from the upper triangle of M as it stands; (c, s) -> cs, the pair -> pq (p | q << 16; the passes of the
+// round read it instead of redoing the modulo arithmetic), a non-trivial rotation raises *flag
+CERB_D void jacobi_angles(const double *M, int ld, int k, int kp, int r, double *cs, int *pq, int *flag) {
     for (int t = threadIdx.x; t < kp / 2; t += blockDim.x) {
         int p, q; jacobi_pair(t, r, kp, p, q);
         double c = 1.0, s = 0.0;
@@ -67,22 +68,24 @@ CERB_D void jacobi_angles(const double *M, int ld, int k, int kp, int r, double 
                 if (s != 0.0) *flag = 1;
             }
         }
-        cs[2 * t] = c; cs[2 * t + 1] = s;
+        cs[2 * t] = c; cs[2 * t + 1] = s; pq[t] = p | (q << 16);
     }
 }
 
 // Eigen-decomposition of the symmetric k x k matrix M (column-major, leading dimension ld): on return the eigenvalues are on the
 // diagonal of M.  V (optional, k x k, leading dimension ldv, set to the identity here): the eigenvectors as columns.  T (optional,
-// k x nct ROW-major, leading dimension ldt): replaced by V^T T (its rows are rotated like the rows of M).  Called by all threads of the CTA;
-// returns the number of sweeps.  Three CTA barriers per round: column pass | row pass | re-symmetrisation together with the angles of the
-// next round (both only read the upper triangle the row pass left).  flag[sweep & 1] collects "some rotation was non-trivial".
-CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, int ldt, int nct, double *cs, int *flag) {
+// k x nct ROW-major, leading dimension ldt, nct <= 128): replaced by V^T T (its rows are rotated like the rows of M).  Called by all
+// threads of the CTA; returns the number of sweeps.  Three CTA barriers per round: column pass | row pass | re-symmetrisation together
+// with the angles of the next round (both only read the upper triangle the row pass left).  flag[sweep & 1] collects "some rotation was
+// non-trivial".  T lives in global memory (L2): a warp loads the two rows of its pair (coalesced) BEFORE it does its share of the row
+// pass on the shared-memory matrix and rotates / stores them afterwards, so the L2 round trip hides behind the row pass.
+CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, int ldt, int nct, double *cs, int *pq, int *flag) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
     const int kp = k + (k & 1), half = kp / 2, rounds = kp - 1;
-    if (V) for (int e = tid; e < k * k; e += nt) { const int i = e % k, j = e / k; V[i + (size_t)j * ldv] = (i == j) ? 1.0 : 0.0; }
+    if (V) for (int j = wid; j < k; j += nwarp) for (int i = lane; i < k; i += 32) V[i + (size_t)j * ldv] = (i == j) ? 1.0 : 0.0;
     if (tid == 0) { flag[0] = 0; flag[1] = 0; }
     __syncthreads();
-    jacobi_angles(M, ld, k, kp, 0, cs, flag);
+    jacobi_angles(M, ld, k, kp, 0, cs, pq, flag);
     __syncthreads();
     int sweeps = 0;
     for (; sweeps < MARG_MAX_SWEEPS; sweeps++) {
@@ -90,7 +93,7 @@ CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, i
             for (int t = wid; t < half; t += nwarp) {         // columns p, q of M (and V)
                 const double c = cs[2 * t], s = cs[2 * t + 1];
                 if (s == 0.0) continue;
-                int p, q; jacobi_pair(t, r, kp, p, q);
+                const int p = pq[t] & 0xffff, q = pq[t] >> 16;
                 double *mp = M + (size_t)p * ld, *mq = M + (size_t)q * ld;
                 for (int i = lane; i < k; i += 32) { const double a = mp[i], b = mq[i]; mp[i] = c * a - s * b; mq[i] = s * a + c * b; }
                 if (V) {
@@ -99,33 +102,33 @@ CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, i
                 }
             }
             __syncthreads();
-            for (int t = wid; t < half; t += nwarp) {         // rows p, q of M (and T)
-                const double c = cs[2 * t], s = cs[2 * t + 1];
-                if (s == 0.0) continue;
-                int p, q; jacobi_pair(t, r, kp, p, q);
-                for (int j = lane; j < k; j += 32) {
-                    const double a = M[p + (size_t)j * ld], b = M[q + (size_t)j * ld];
-                    M[p + (size_t)j * ld] = c * a - s * b; M[q + (size_t)j * ld] = s * a + c * b;
-                }
-            }
-            // rows p, q of T (row-major in global memory / L2): a flat loop over (pair, column) so that consecutive threads touch consecutive
-            // addresses, four elements per thread in flight (the pass is bound by L2 latency, not by arithmetic)
-            if (T) {
-                const int total = half * nct;
-                for (int e0 = tid; e0 < total; e0 += 4 * nt) {
-                    double a[4], b[4], cc[4], ss[4]; size_t ip[4], iq[4];
-                    _Pragma("unroll")
-                    for (int u = 0; u < 4; u++) {
-                        const int e = e0 + u * nt;
-                        ss[u] = 0.0; cc[u] = 1.0; a[u] = 0.0; b[u] = 0.0; ip[u] = 0; iq[u] = 0;
-                        if (e < total) {
-                            const int t = e / nct, j = e - t * nct;
-                            cc[u] = cs[2 * t]; ss[u] = cs[2 * t + 1];
-                            if (ss[u] != 0.0) { int p, q; jacobi_pair(t, r, kp, p, q); ip[u] = (size_t)p * ldt + j; iq[u] = (size_t)q * ldt + j; a[u] = T[ip[u]]; b[u] = T[iq[u]]; }
-                        }
+            for (int t0 = wid; t0 < half; t0 += 2 * nwarp) {      // rows p, q of M (and T): two pairs per warp iteration
+                double ta[2][4], tb[2][4];
+                _Pragma("unroll")
+                for (int u = 0; u < 2; u++) {                     // T rows first: the loads stay in flight during the row pass below
+                    const int t = t0 + u * nwarp;
+                    if (T && t < half && cs[2 * t + 1] != 0.0) {
+                        const double *tp = T + (size_t)(pq[t] & 0xffff) * ldt, *tq = T + (size_t)(pq[t] >> 16) * ldt;
+                        _Pragma("unroll")
+                        for (int v = 0; v < 4; v++) { const int j = lane + 32 * v; ta[u][v] = j < nct ? tp[j] : 0.0; tb[u][v] = j < nct ? tq[j] : 0.0; }
                     }
-                    _Pragma("unroll")
-                    for (int u = 0; u < 4; u++) if (ss[u] != 0.0) { T[ip[u]] = cc[u] * a[u] - ss[u] * b[u]; T[iq[u]] = ss[u] * a[u] + cc[u] * b[u]; }
+                }
+                _Pragma("unroll")
+                for (int u = 0; u < 2; u++) {
+                    const int t = t0 + u * nwarp;
+                    if (t >= half) continue;
+                    const double c = cs[2 * t], s = cs[2 * t + 1];
+                    if (s == 0.0) continue;
+                    const int p = pq[t] & 0xffff, q = pq[t] >> 16;
+                    for (int j = lane; j < k; j += 32) {
+                        const double a = M[p + (size_t)j * ld], b = M[q + (size_t)j * ld];
+                        M[p + (size_t)j * ld] = c * a - s * b; M[q + (size_t)j * ld] = s * a + c * b;
+                    }
+                    if (T) {
+                        double *tp = T + (size_t)p * ldt, *tq = T + (size_t)q * ldt;
+                        _Pragma("unroll")
+                        for (int v = 0; v < 4; v++) { const int j = lane + 32 * v; if (j < nct) { tp[j] = c * ta[u][v] - s * tb[u][v]; tq[j] = s * ta[u][v] + c * tb[u][v]; } }
+                    }
                 }
             }
             // every thread has read last sweep's verdict by now (it did so before this sweep's first column pass)
@@ -133,9 +136,9 @@ CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, i
             __syncthreads();
             // keep M exactly symmetric: the column and the row pass round differently, and an asymmetric residue of eps |M| is enough to
             // keep the null space of a rank-deficient Schur complement rotating for ever (the angles are taken from the upper triangle)
-            for (int e = tid; e < k * k; e += nt) { const int i = e % k, j = e / k; if (i > j) M[i + (size_t)j * ld] = M[j + (size_t)i * ld]; }
-            if (r + 1 < rounds) jacobi_angles(M, ld, k, kp, r + 1, cs, flag + (sweeps & 1));
-            else jacobi_angles(M, ld, k, kp, 0, cs, flag + ((sweeps + 1) & 1));
+            for (int j = wid; j < k; j += nwarp) for (int i = j + 1 + lane; i < k; i += 32) M[i + (size_t)j * ld] = M[j + (size_t)i * ld];
+            if (r + 1 < rounds) jacobi_angles(M, ld, k, kp, r + 1, cs, pq, flag + (sweeps & 1));
+            else jacobi_angles(M, ld, k, kp, 0, cs, pq, flag + ((sweeps + 1) & 1));
             __syncthreads();
         }
         if (!flag[sweeps & 1]) break;
@@ -152,7 +155,7 @@ CERB_GLOBAL void marg_schur_kernel(int n_windows, int mmax, int nmax, const int 
     CERB_DYN_SMEM(double, sm);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int kmax = mmax > nmax ? mmax : nmax;
-    double *cs = sm, *inv = sm + (kmax + 2); int *flag = reinterpret_cast<int *>(sm + 2 * (kmax + 2));
+    double *cs = sm, *inv = sm + (kmax + 2); int *flag = reinterpret_cast<int *>(sm + 2 * (kmax + 2)), *pq = flag + 8;
     double *body = sm + marg_fixed_doubles(mmax, nmax);
     const bool m1_smem = marg_m1_in_smem(mmax, nmax), t_smem = marg_t_in_smem(mmax, nmax);
     double *wsp = ws_all + (size_t)blockIdx.x * marg_ws_doubles(mmax, nmax);
@@ -167,7 +170,7 @@ CERB_GLOBAL void marg_schur_kernel(int n_windows, int mmax, int nmax, const int 
         for (int e = tid; e < m * m; e += nt) { const int i = e % m, j = e / m; M1[i + (size_t)j * ld1] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); }
         for (int e = tid; e < m * nc; e += nt) { const int c = e % nc, i = e / nc; Tg[(size_t)i * ldt + c] = c < n ? A[(size_t)i * pos + m + c] : b[i]; }
         __syncthreads();
-        const int sw1 = jacobi_eig(M1, ld1, m, nullptr, 0, Tg, ldt, nc, cs, flag);
+        const int sw1 = jacobi_eig(M1, ld1, m, nullptr, 0, Tg, ldt, nc, cs, pq, flag);
         for (int i = tid; i < m; i += nt) { const double lam = M1[i + (size_t)i * ld1]; inv[i] = lam > eps ? 1.0 / lam : 0.0; }
         __syncthreads();
         // ---- [Ar | br] = [Arr | brr] - T^T diag(inv) T (lower triangle; SelfAdjointEigenSolver reads the lower triangle) ---------------
@@ -185,7 +188,7 @@ CERB_GLOBAL void marg_schur_kernel(int n_windows, int mmax, int nmax, const int 
         __syncthreads();
         // ---- phase 2: A = V2 diag(lambda) V2^T;  linearized_jacobians = sqrt(S) V2^T, linearized_residuals = sqrt(S_inv) V2^T b ----------
         double *V2 = M2 + (size_t)ld2 * ld2;                                               // over the dead staged T
-        const int sw2 = jacobi_eig(M2, ld2, n, V2, ld2, nullptr, 0, 0, cs, flag);
+        const int sw2 = jacobi_eig(M2, ld2, n, V2, ld2, nullptr, 0, 0, cs, pq, flag);
         double *Jo = lin_J + (size_t)w * (J_stride ? J_stride : (long)n * n), *ro = lin_r + (size_t)w * (r_stride ? r_stride : (long)n);
         for (int e = tid; e < n * n; e += nt) {
             const int kk = e % n, j = e / n;

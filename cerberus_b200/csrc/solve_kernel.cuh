@@ -60,8 +60,8 @@ struct SolveParams {
 
 // per-CTA global workspace layout (doubles); F = maxF
 CERB_HD long ws_W(int) { return 0; }                                        // [NX][F]
-CERB_HD long ws_vecs(int F) { return (long)NX * F; }                        // 8 vectors of F: hh, gl, sl, Dl, ghl, gnl, stl, lamc
-CERB_HD long ws_prior(int F) { return (long)NX * F + 8L * F; }              // image of the prior Hessian in the layout of Hxx | Hxy | Ad | Bo
+CERB_HD long ws_vecs(int F) { return (long)NX * F; }                        // 9 vectors of F: hh, gl, sl, Dl, ghl, gnl, stl, lamc, sinv (windows with > 1024 features)
+CERB_HD long ws_prior(int F) { return (long)NX * F + 9L * F; }              // image of the prior Hessian in the layout of Hxx | Hxy | Ad | Bo
 CERB_HD long ws_chunks(int F) { return ws_prior(F) + PIMG_SZ; }                          // feature chunk table (ints)
 CERB_HD long ws_imuplan(int F) { return (ws_chunks(F) + (F + 4) / 2 + 8 + 1) & ~1L; }                  // scatter plan of the IMU-leg Gram matrix (ints)
 CERB_HD long ws_size(int F) { return ws_imuplan(F) + 15 * 2 * 32 * 4 / 2 + 8; }                            // even: the plan is read as int4
@@ -1168,7 +1168,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                         const int wq = (tid >> 5) - 1, lane = tid & 31;
                         const int LDW = 36;
                         double *tw = s.Ju;                         // 80 x 36 tile (aliases Ju .. red, unused during the solve)
-                        double *sinv = s.wj;                       // <= CERB features: 1 / sqrt(h + mu D^2)   (wj: 1024 doubles)
+                        double *sinv = nF <= 1024 ? s.wj : lamc + F;   // 1 / sqrt(h + mu D^2): shared memory (wj: 1024 doubles) up to the reference's NUM_OF_F,
+                                                                       // the ninth workspace vector for the larger synthetic stress windows
                         {   // Cauchy point: v_x^T Hxx v_x + 2 v_x^T Hxy v_y + lambda terms (H still unregularised / unfactored here)
                             const double *v = s.stp;
                             double pv = 0.0;

@@ -41,6 +41,8 @@ extern "C" {
 #define CERB_WINDOW_SIZE 10        /* WINDOW_SIZE */
 #define CERB_NUM_FRAMES 11         /* WINDOW_SIZE + 1 states */
 #define CERB_NUM_OF_F 1000         /* NUM_OF_F: para_Feature capacity of the reference */
+#define CERB_MAX_FEATURES 2048     /* capacity limit of this library: the synthetic stress configuration (BASELINE.json configs[4]: 2000
+                                      features per window) deliberately exceeds the reference's static limit (parameters.h:24) */
 #define CERB_SIZE_POSE 7
 #define CERB_SIZE_SPEEDBIAS 9
 #define CERB_SIZE_LEG_BIAS 4
@@ -90,7 +92,7 @@ enum {
 typedef struct CerbSolverConfig {
     int32_t device;               /* CUDA device ordinal */
     int32_t max_batch;            /* capacity: windows per batch call */
-    int32_t max_features;         /* capacity: features per window (<= CERB_NUM_OF_F) */
+    int32_t max_features;         /* capacity: features per window (<= CERB_MAX_FEATURES; the reference stops at CERB_NUM_OF_F) */
     int32_t max_obs;              /* capacity: observations per window (sum of track lengths) */
     int32_t max_num_iterations;   /* NUM_ITERATIONS (yaml max_num_iterations, 12) */
     int32_t optimize_leg_bias;    /* OPTIMIZE_LEG_BIAS; 0 => para_LegBias constant (estimator.cpp:1074) */

@@ -231,3 +231,25 @@ def test_feature_steps_gpu_vs_reference_feature_manager(realistic):
     assert ref_lib() is not None
     cfg = small_cfg(max_batch=4, max_features=24, iters=4)
     _check_backend(lib.Backend(cfg), RefBackend(), realistic)
+
+
+@pytest.mark.gpu
+def test_stress_feature_count_gpu():
+    """BASELINE.json configs[4]: 10-frame x 2000-feature windows (dense Schur: 32 chunks of tracks, 63 Schur tiles, the inverse-depth scales in the
+    global workspace instead of shared memory).  Exceeds the reference's static NUM_OF_F = 1000 (parameters.h:24) on purpose; parity vs the oracle."""
+    cfg = abi.default_config()
+    cfg.max_batch, cfg.max_features, cfg.max_obs = 2, 2000, 2000 * 11
+    big = lib.Backend(cfg)
+    o = OracleBackend(cfg)
+    batch = synth.generate_batch(2, 2000, big, cfg=cfg, window0=4000, prior_features=16)
+    st = batch.state_array(); saved = batch.copy_states()
+    rep_o = o.solve_batch(batch, nthreads=2); ref = st.copy(); lam = batch.para_Feature.copy()
+    batch.restore_states(saved)
+    rep_g = big.solve_batch(batch)
+    assert (rep_o["iterations"] == rep_g["iterations"]).all() and (rep_o["num_successful_steps"] == rep_g["num_successful_steps"]).all()
+    d = state_diffs(batch.state_array(), ref)
+    assert d["para_Pose"] < 1e-6 and d["para_SpeedBias"] < 1e-5 and np.abs(batch.para_Feature - lam).max() < 1e-6, d
+    # over the capacity limit of the library
+    cfg2 = abi.default_config(); cfg2.max_batch, cfg2.max_features, cfg2.max_obs = 1, 2049, 2049 * 11
+    with pytest.raises(lib.CerbError):
+        lib.Backend(cfg2)
