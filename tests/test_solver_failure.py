@@ -15,7 +15,7 @@ from oracle_lib import OracleBackend
 from helpers import sim_backend, small_cfg, state_diffs
 
 
-def _run(make_backend, env, nw=2, F=12, iters=8):
+def _run(make_backend, env, nw=1, F=10, iters=6):
     old = {k: os.environ.get(k) for k in ("CERB_TEST_FAIL_FACTORIZATIONS", "CERB_TEST_INITIAL_MU")}
     os.environ.update(env)
     try:
@@ -34,7 +34,6 @@ def _run(make_backend, env, nw=2, F=12, iters=8):
 
 
 def _check_retry_inside_the_step(make_backend):
-    base_o, base_b, *_ = _run(make_backend, {})
     rep_o, rep_b, ref, got, lam_o, lam_b, _ = _run(make_backend, {"CERB_TEST_FAIL_FACTORIZATIONS": "3"})
     # three failed solves: mu 1e-8 -> 1e-5 inside the first ComputeStep; no iteration / invalid step consumed on either arm
     assert (rep_o["iterations"] == rep_b["iterations"]).all() and (rep_o["num_successful_steps"] == rep_b["num_successful_steps"]).all()
