@@ -98,6 +98,28 @@ def usable_cpus():
     return n
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads (and so the first-touch placement of its page-locked batch buffers) to the NUMA node its GPU hangs off,
+    so that the H2D DMA of the end-to-end path does not cross the socket interconnect.  Best effort: returns a note for `details`."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=10).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"): bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-"); cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return f"numa node {node}: none of its cpus in the affinity mask"
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node} ({len(allowed)} cpus)"
+    except Exception as e:      # no sysfs / no permission: run unpinned
+        return f"unpinned ({type(e).__name__})"
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of Estimator::optimization() on all host cores, the same 1024-window batch per step as the GPU arm."""
     if rank != 0:
@@ -185,6 +207,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist_mod.init_process_group("nccl", device_id=device)
         dist = dist_mod
+    numa_note = bind_to_gpu_numa_node(local_rank)
     NW, F = args.windows, args.features
     cfg = abi.default_config()
     cfg.device = local_rank
@@ -271,6 +294,7 @@ def main():
             "details": {"wall_ms_per_step_resident": 1e3 * wall_resident / args.steps, "setup_s": t_setup, "mean_iterations": float(np.mean(rep["iterations"])),
                         "e2e_ms_per_step": 1e3 * e2e_s / args.steps, "e2e_dma_ops_per_step": int(dma_ops), "e2e_staged_bytes_per_step": int(staged_bytes),
                         "e2e_device_ms_last_step": e2e_ms, "e2e_kernel_launches_per_step": int(e2e_launches),
+                        "host_affinity": numa_note,
                         "e2e_host_buffers": "page-locked once with cerb_register_host_buffer; descriptors DMA'd as they are, AoS -> HBM layout on the device"},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),

@@ -78,3 +78,15 @@ def test_bad_descriptors_are_rejected():
     batch.features[0][2]["n_obs"] = 40
     with pytest.raises(lib.CerbError):
         sb.solve_batch(batch)
+
+
+def test_integration_stub_compiles_against_the_header_and_reference_headers():
+    """tools/integration_stub.cpp (the reference-side binding of INTEGRATION.md) type-checks as C++14 against include/cerberus_b200.h, the
+    reference's own headers where they lie and the Eigen / ROS / OpenCV shims of oracle/shim; the header alone also compiles as plain C."""
+    hdr_c = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "cerberus_b200.h")], capture_output=True, text=True)
+    assert hdr_c.returncode == 0, hdr_c.stderr
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("/root/reference absent (GPU box)")
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "shim"),
+                        "-I/root/reference/src", os.path.join(ROOT, "tools", "integration_stub.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
