@@ -281,7 +281,9 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_traffic.json"))).get("dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_traffic.json")))
+            if tj.get("windows") == NW and tj.get("features") == F:       # the ncu capture is of the default workload only
+                traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
         kernel_s = ev_ms * 1e-3 / args.steps
@@ -302,7 +304,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "note": "vilo_solve_kernel; algorithmic bytes = (114160 + 816 F) per solve x windows per launch; peak = " + peak_src +
                                  "; the kernel is fp64-latency bound, not HBM bound (arithmetic intensity ~420 flop/B, SURVEY.md 8(d))",
-                         "fp64_gflops_algorithmic": 0.1 * value},
+                         "fp64_gflops_algorithmic": 0.1 * (F / 150.0) * value},      # ~0.1 Gflop per 150-feature solve, dominated by the visual factors (proportional to F)
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -453,7 +453,7 @@ int oracle_marginalize(const CerbSolverConfig *cfg, const CerbWindowDesc *desc, 
     st.para_Feature = feat.data();
     FactorGlobals fg; fg.G = V3(cfg->g); fg.visual_sqrt_info = cfg->visual_sqrt_info;
     MargInfo mi;
-    MargInfoLite last; std::vector<LegPreintState> pre;
+    MargInfoLite last; std::vector<LegPreintState> pre; std::vector<ImuPreintState> ipre;
     std::memset(out, 0, sizeof(*out));
     if (margin_old) {
         if (desc->prior.valid) {
@@ -466,12 +466,22 @@ int oracle_marginalize(const CerbSolverConfig *cfg, const CerbWindowDesc *desc, 
             }
             mi.add(std::move(f));
         }
-        pre.push_back(to_state(desc->preint[0]));
-        if (pre[0].sum_dt < 10.0) {
-            RBInfo f; f.cost = std::make_shared<IMULegFactor>(&pre[0], fg); f.huber = false;
-            f.params = {st.para_Pose[0], st.para_SpeedBias[0], st.para_LegBias[0], st.para_Pose[1], st.para_SpeedBias[1], st.para_LegBias[1]};
-            f.drop_set = {0, 1, 2};
-            mi.add(std::move(f));
+        if (desc->preint) {                                          // USE_LEG: estimator.cpp:1271-1285
+            pre.push_back(to_state(desc->preint[0]));
+            if (pre[0].sum_dt < 10.0) {
+                RBInfo f; f.cost = std::make_shared<IMULegFactor>(&pre[0], fg); f.huber = false;
+                f.params = {st.para_Pose[0], st.para_SpeedBias[0], st.para_LegBias[0], st.para_Pose[1], st.para_SpeedBias[1], st.para_LegBias[1]};
+                f.drop_set = {0, 1, 2};
+                mi.add(std::move(f));
+            }
+        } else {                                                     // USE_IMU only: IMUFactor <15,7,9,7,9>, drop pose0 / speedbias0 (estimator.cpp:1287-1297)
+            ipre.push_back(to_imu_state(desc->imu_preint[0]));
+            if (ipre[0].sum_dt < 10.0) {
+                RBInfo f; f.cost = std::make_shared<IMUFactor>(&ipre[0], fg); f.huber = false;
+                f.params = {st.para_Pose[0], st.para_SpeedBias[0], st.para_Pose[1], st.para_SpeedBias[1]};
+                f.drop_set = {0, 1};
+                mi.add(std::move(f));
+            }
         }
         for (int fi = 0; fi < desc->n_features; fi++) {
             const CerbFeature &ft = desc->features[fi];

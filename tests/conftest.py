@@ -9,3 +9,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_xdist_auto_num_workers(config):
+    """`-n auto` (pytest.ini): parallel workers only for the CPU tier; the GPU tier stays in one process (one handle owns the device and its pinned staging)."""
+    expr = getattr(config.option, "markexpr", "") or ""
+    if "not gpu" in expr:
+        return min(4, max(1, (os.cpu_count() or 2) // 2))
+    return 0

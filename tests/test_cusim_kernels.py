@@ -155,10 +155,14 @@ def saved_td(saved):
 
 
 def test_empty_and_single_feature_windows():
+    _empty_and_single_feature_case(sim_backend)
+
+
+def _empty_and_single_feature_case(make_backend, iters=3):
     """Edge cases of the track list: a window with no visual factors at all (IMU-leg factors + prior only) and one with a
     single feature; both must match the oracle."""
-    cfg = small_cfg(max_batch=2, max_features=16, iters=3)
-    o, s = OracleBackend(cfg), sim_backend(cfg)
+    cfg = small_cfg(max_batch=2, max_features=16, iters=iters)
+    o, s = OracleBackend(cfg), make_backend(cfg)
     batch = synth.generate_batch(2, 10, o, window0=5, prior_features=6)
     batch.descs[0].n_features = 0; batch.descs[0].n_obs = 0
     batch.descs[1].n_features = 1
@@ -294,12 +298,16 @@ def test_host_buffer_pipeline_chunks():
 
 
 def test_registered_host_buffers_take_the_zero_copy_path():
+    _registered_buffers_case(sim_backend, 16, 9, 3)
+
+
+def _registered_buffers_case(make_backend, max_batch, n, max_chunks, iters=1):
     """cerb_register_host_buffer: arrays inside registered memory are DMA'd straight out of the caller's buffers (ONE 2-D copy per array and
     pipeline chunk when the per-window arrays are uniformly strided), the others go through pinned staging.  Results are bit-identical."""
-    cfg = small_cfg(max_batch=16, max_features=8, iters=1)
-    s = sim_backend(cfg)
+    cfg = small_cfg(max_batch=max_batch, max_features=8, iters=iters)
+    s = make_backend(cfg)
     base = synth.generate_batch(3, 4, ob, window0=150, prior_features=4)
-    big = synth.tile_batch(base, 9)
+    big = synth.tile_batch(base, n)
     saved = big.copy_states()
     rep_a = s.solve_batch(big); out_a = np.frombuffer(big.states, dtype=np.uint8).copy(); lam_a = big.para_Feature.copy()
     ops_a, staged_a = s.last_upload_stats()
@@ -308,7 +316,7 @@ def test_registered_host_buffers_take_the_zero_copy_path():
     regs = s.register_batch(big)
     rep_b = s.solve_batch(big)
     ops_b, staged_b = s.last_upload_stats()
-    assert staged_b == 0 and ops_b <= 3 * 10            # 3 chunks x (descs, states, features, obs, para_Feature, preint head + tail, prior J, prior r)
+    assert staged_b == 0 and ops_b <= max_chunks * 10   # per chunk: descs, states, features, obs, para_Feature, preint head + tail, prior J, prior r
     assert (np.frombuffer(big.states, dtype=np.uint8) == out_a).all() and (big.para_Feature == lam_a).all() and (rep_a["final_cost"] == rep_b["final_cost"]).all()
     # irregular batch: one window without features, one without a prior -> per-window copies for those arrays, same results as staged
     big.restore_states(saved)
@@ -317,3 +325,21 @@ def test_registered_host_buffers_take_the_zero_copy_path():
     assert s.last_upload_stats()[1] == 0
     s.unregister(regs)
     assert (rep_c["final_cost"][[0, 2, 3]] == rep_a["final_cost"][[0, 2, 3]]).all() and rep_c["final_cost"][1] != rep_a["final_cost"][1]
+
+
+def test_marginalization_of_imu_only_windows():
+    _imu_only_marginalization_case(sim_backend)
+
+
+def _imu_only_marginalization_case(make_backend):
+    """USE_LEG == 0 (estimator.cpp:1287-1297): the frame 0 -> 1 factor is IMUFactor <15,7,9,7,9>, there are no leg-bias blocks; the device
+    path (IMU factor embedded in the 31-row kernels) against the oracle's MarginalizationInfo restatement with the plain IMUFactor."""
+    cfg = small_cfg()
+    s = make_backend(cfg)
+    src = synth.generate_batch(2, 10, ob, use_leg=False, window0=61)
+    a, b = synth.generate_batch(2, 10, ob, use_leg=False, window0=61), synth.generate_batch(2, 10, ob, use_leg=False, window0=61)
+    ob.marginalize(cfg, src, a); s.marginalize(cfg, src, b)
+    for w in range(2):
+        A0, b0, x0 = prior_canonical(a, w); A1, b1, x1 = prior_canonical(b, w)
+        assert A0.shape == A1.shape and set(x0) == set(x1) and not any(k[0] == abi.BLOCK_LEGBIAS for k in x1)
+        assert np.abs(A0 - A1).max() < 1e-5 * np.abs(A0).max() and np.abs(b0 - b1).max() < 1e-4 * np.abs(b0).max()

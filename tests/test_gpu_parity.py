@@ -186,3 +186,47 @@ def test_rejected_steps_match_oracle_gpu():
 def test_chained_windows_match_oracle_gpu():
     from test_cusim_kernels import _chained_windows_case
     _chained_windows_case(lambda cfg: lib.Backend(cfg), nw=4, F=24, F0=16, iters=8, nthreads=4)
+
+
+def test_edge_windows_gpu():
+    """A window without visual factors, a window with a single feature (12 iterations on the sm_100a build)."""
+    from test_cusim_kernels import _empty_and_single_feature_case
+    _empty_and_single_feature_case(lambda cfg: lib.Backend(cfg), iters=12)
+
+
+def test_registered_host_buffers_gpu():
+    """Zero-copy path with REAL page-locked memory (cudaHostRegister) and merged 2-D DMA: bit-identical to the staged path, nothing staged;
+    444 windows on a 148-CTA grid -> 4 pipeline chunks."""
+    from test_cusim_kernels import _registered_buffers_case
+    _registered_buffers_case(lambda cfg: lib.Backend(cfg), 512, 444, 4, iters=2)
+
+
+def test_marginalization_of_imu_only_windows_gpu():
+    from test_cusim_kernels import _imu_only_marginalization_case
+    _imu_only_marginalization_case(lambda cfg: lib.Backend(cfg))
+
+
+def test_marginalize_at_resident_solved_states(gpu, oracle):
+    """cerb_batch_marginalize with states = NULL: MARGIN_OLD at the solved states as they sit on the device == the oracle's marginalization at the
+    downloaded solved states."""
+    cfg = abi.default_config()
+    batch = synth.generate_batch(3, 40, gpu, window0=700, prior_features=12)
+    gpu.solve_batch(batch)                                   # batch.states now hold the solved states, like the device
+    J = np.zeros((3, abi.MAX_PRIOR_DIM * abi.MAX_PRIOR_DIM)); r = np.zeros((3, abi.MAX_PRIOR_DIM))
+    priors = (abi.Prior * 3)()
+    for w in range(3):
+        priors[w].linearized_jacobians = J[w].ctypes.data_as(abi.c_dp); priors[w].linearized_residuals = r[w].ctypes.data_as(abi.c_dp)
+    sw = gpu.batch_marginalize(np.zeros(3, dtype=np.int32), None, priors)
+    assert (sw > 0).all() and (sw < 40).all()
+    ref = synth.generate_batch(3, 40, gpu, window0=700, prior_features=12)
+    oracle.marginalize(cfg, batch, ref)
+    for w in range(3):
+        A0, b0, x0 = prior_canonical(ref, w)
+        n = priors[w].n
+        Jm = J[w][:n * n].reshape(n, n).T
+        A, g = Jm.T @ Jm, Jm.T @ r[w][:n]
+        loc = {0: 6, 1: 9, 2: 4, 3: 6, 4: 1}
+        keys = sorted((priors[w].block_kind[i], priors[w].block_index[i], priors[w].block_col[i]) for i in range(priors[w].num_blocks))
+        perm = [c + t for (k, i, c) in keys for t in range(loc[k])]
+        assert A0.shape == (n, n)
+        assert np.abs(A[np.ix_(perm, perm)] - A0).max() < 1e-5 * np.abs(A0).max() and np.abs(g[perm] - b0).max() < 1e-4 * max(1.0, np.abs(b0).max())

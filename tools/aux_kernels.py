@@ -47,6 +47,14 @@ def main():
     t = wall(lambda: be.outlier_errors(NW)); print(f"outlier_errors ({NW} x {F}): {t * 1e3:.2f} ms wall")
     t = wall(lambda: be.triangulate(NW)); print(f"triangulate    ({NW} x {F}): {t * 1e3:.2f} ms wall")
     t = wall(lambda: be.shift_depth(NW)); print(f"shift_depth    ({NW} x {F}): {t * 1e3:.2f} ms wall")
+    # per-frame use (BASELINE.json configs[2]: one window per camera frame): latency of the drop-in call for ONE window, host buffers in / out
+    one = synth.tile_batch(small, 1)
+    saved1 = one.copy_states()
+    def solve_one():
+        one.restore_states(saved1); be.solve_batch(one)
+    t = wall(solve_one, reps=5); ms, _ = be.last_solve_stats()
+    print(f"cerb_solve_window (1 window x {F} features, 12 iterations, host buffers in / out): {t * 1e3:.2f} ms wall, {ms:.2f} ms on the device")
+    be.upload(big); be.solve_resident(); be.sync()
     rng = np.random.default_rng(0)
     m, n = 19 + F, 86
     pos = m + n

@@ -54,3 +54,32 @@ shutil.copy(os.path.join(G, "bench_final.json"), os.path.join(Pf, f"bench_{tag}.
 shutil.copy(os.path.join(G, "bench_reference.json"), os.path.join(Pf, f"bench_{tag}_reference.json"))
 d = json.load(open(os.path.join(G, "bench_final.json")))
 print("bench", round(d["value"]), "e2e", round(d["e2e"]["value"]), "cpu", d.get("cpu_baseline"))
+
+# ---- round 2: marg_schur_kernel capture, auxiliary kernels, end-to-end trace, replay -------------------------------------------
+mrep = os.path.join(G, "marg_schur_final.ncu-rep")
+if os.path.exists(mrep):
+    a = raw(mrep)
+    with open(os.path.join(Pf, f"marg_schur_kernel_{tag}.txt"), "w") as f:
+        f.write(f"# ncu --set full summary, marg_schur_kernel, 1024 windows (m = 169, n = 86, MARGIN_OLD of the solved 150-feature windows), B200 ({tag})\n"
+                f"# command: ncu --set full --clock-control none --import-source on -k regex:marg_schur -s 1 -c 1 python tools/aux_kernels.py 1024 150\n\n")
+        for k in WANT:
+            if k in a: f.write(f"{k:92s} {a[k][0]} {a[k][1]}\n")
+aux = os.path.join(G, "aux_launches_final.csv")
+if os.path.exists(aux):
+    rows = [r for r in csv.reader(open(aux)) if len(r) > 10]
+    H = rows[0]; ik, im, iv, iid = H.index('Kernel Name'), H.index('Metric Name'), H.index('Metric Value'), H.index('ID')
+    d = collections.OrderedDict()
+    for r in rows[1:]:
+        d.setdefault((r[iid], r[ik].split('(')[0]), {})[r[im]] = float(r[iv].replace(',', ''))
+    with open(os.path.join(Pf, f"aux_kernels_{tag}.csv"), "w") as f:
+        f.write(f"# kernels outside the timed solve step at benchmark scale (python tools/aux_kernels.py 1024 150 under ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum), {tag}\n"
+                "# measured copy peak of this pool: 6566 GB/s (MEASURED_PEAKS.json)\nid,kernel,duration_us,dram_MB,dram_GBps,frac_of_hbm_peak\n")
+        for (i, k), m in d.items():
+            t = m.get('gpu__time_duration.sum', 0.0); b = m.get('dram__bytes_read.sum', 0.0) + m.get('dram__bytes_write.sum', 0.0)
+            f.write(f"{i},{k},{t / 1e3:.1f},{b / 1e6:.2f},{(b / t if t else 0):.1f},{(b / t / 6566.1 if t else 0):.4f}\n")
+for src, dst in (("aux_wall_final.txt", f"aux_wall_{tag}.txt"), ("marg_bench_final.txt", f"marg_bench_{tag}.txt"), ("replay_gpu.txt", f"replay_gpu_{tag}.txt")):
+    if os.path.exists(os.path.join(G, src)): shutil.copy(os.path.join(G, src), os.path.join(Pf, dst))
+err = os.path.join(G, "bench_final.err")
+if os.path.exists(err):
+    lines = [l for l in open(err) if "cerb_solve_batch" in l]
+    open(os.path.join(Pf, f"e2e_trace_{tag}.txt"), "w").write("# CERB_TRACE=1 python bench.py: host timeline of every cerb_solve_batch call of the end-to-end leg (registered host buffers)\n" + "".join(lines))
