@@ -41,12 +41,12 @@ for r in rows[hi + 1:]:
     try: v = float(r[vi].replace(',', ''))
     except ValueError: continue
     v *= {'nsecond': 1e-3, 'ns': 1e-3, 'usecond': 1.0, 'us': 1.0, 'msecond': 1e3, 'ms': 1e3}.get(r[ui], 1.0)
-    n = r[ki].split('(')[0]; tot[n] += v; cnt[n] += 1
+    n = r[ki].split('(')[0].split('::')[-1]; tot[n] += v; cnt[n] += 1
 T = sum(tot.values())
 with open(os.path.join(Pf, f"launches_{tag}_summary.csv"), "w") as f:
     f.write(f"# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` ({tag}, B200); gpu__time_duration.sum per kernel,\n# cold-cache / serialised: compare SHARES, not absolutes.  preintegrate / *_eval kernels belong to the synthetic-data set-up.\nkernel,launches,total_us,share\n")
     for k, v in tot.most_common(): f.write(f"{k},{cnt[k]},{v:.1f},{v / T:.4f}\n")
-step = {k: v for k, v in tot.items() if k in ("vilo_solve_kernel", "prior_prepare_kernel", "imu_leg_prepare_kernel")}
+step = {k: v for k, v in tot.items() if k in ("vilo_solve_kernel", "prior_prepare_kernel", "imu_leg_prepare_kernel", "pack_kernel", "unpack_kernel")}
 print({k: round(v / sum(step.values()), 4) for k, v in step.items()})
 shutil.copy(os.path.join(G, "launches_final.csv"), os.path.join(Pf, f"launches_{tag}.csv"))
 shutil.copy(os.path.join(G, "phase_final.txt"), os.path.join(Pf, f"phase_breakdown_{tag}.txt"))
