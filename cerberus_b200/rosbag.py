@@ -274,3 +274,39 @@ def load_sequence(path, imu_topic=IMU_TOPIC, leg_topic=LEG_TOPIC, feature_topic=
         o["dt"] = t - out[n - 1]["t"] if n else 0.0
         n += 1
     return frames, out[:n]
+
+
+class BagSequence:
+    """What ReplayDriver.seed / run read of a sequence (see synth.SynthSequence), rebuilt from a bag's streams for ONE robot."""
+    pass
+
+
+def sequence_from_bag(frames, samples, init, time_slop=1e-4):
+    """frames / samples: the outputs of load_sequence; init: dict(p_g [F,3], R_g [F,3,3], v_g [F,3], tic_g [2,3], ric_g [2,3,3]) -- the states the
+    window is seeded with (the reference gets them from its initialisation, which is out of scope here).  Samples are cut into inter-frame
+    intervals by the camera stamps: interval k = samples with stamp in (t_k, t_k+1]; first[k] = the sample at t_k (processIMULeg's acc_0 / gyr_0 ...)."""
+    nF = len(frames)
+    seq = BagSequence()
+    seq.n, seq.n_frames = 1, nF
+    ft = np.array([f["t"] for f in frames]); st = samples["t"]
+    names = abi.sample_dtype.names
+    def strip(a):
+        out = np.zeros(len(a), dtype=abi.sample_dtype)
+        for n in names: out[n] = a[n]
+        return out
+    first = np.zeros((1, nF), dtype=abi.sample_dtype); per = []
+    for k in range(nF):
+        i0 = int(np.argmin(np.abs(st - ft[k])))
+        if abs(st[i0] - ft[k]) > time_slop: raise ValueError(f"no IMU / leg sample at camera stamp {ft[k]:.6f}")
+        first[0, k] = strip(samples[i0:i0 + 1])[0]
+        if k + 1 < nF:
+            sel = (st > ft[k] + time_slop) & (st <= ft[k + 1] + time_slop)
+            per.append(strip(samples[sel]))
+    S = max(len(p) for p in per)
+    if any(len(p) != S for p in per): seq.samples = [per]                      # ragged intervals: list indexing [w][k]
+    else: seq.samples = np.stack(per)[None]
+    seq.first = first
+    seq.images = [[{"ids": f["ids"], "pts0": f["pts0"], "has1": f["has1"], "pts1": f["pts1"]}] for f in frames]
+    seq.p_g, seq.R_g, seq.v_g = init["p_g"][None], init["R_g"][None], init["v_g"][None]
+    seq.tic_g, seq.ric_g = init["tic_g"][None], init["ric_g"][None]
+    return seq

@@ -62,3 +62,31 @@ def test_bz2_chunk_and_raw_mode(tmp_path):
     assert topic == "/imu" and abs(t - 12.5) < 1e-9 and m["header"]["seq"] == 7 and (m["linear_acceleration"] == [1.0, 2.0, 3.0]).all() and (m["angular_velocity"] == [0.1, 0.2, 0.3]).all()
     (topic, t, (typ, rawmsg)), = list(rosbag.read_bag(p2, decode=False))
     assert typ == "sensor_msgs/Imu" and rawmsg == body
+
+
+def test_replay_from_a_bag_matches_replay_from_the_sequence(tmp_path):
+    """bag -> load_sequence -> sequence_from_bag -> ReplayDriver (oracle arm) == the same replay fed from the synthetic sequence directly (with
+    the float32 rounding of the feature tracker's PointCloud message applied to it too: the reference receives its features as float32)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from cerberus_b200 import estimator
+    from oracle_lib import OracleOps
+    seq = synth.generate_sequence(1, 14, tracked=16, max_len=12, min_len=3)
+    path = str(tmp_path / "replay.bag")
+    rosbag.write_bag(path, rosbag.sequence_to_messages(seq, 0))
+    frames, smp = rosbag.load_sequence(path)
+    bseq = rosbag.sequence_from_bag(frames, smp, dict(p_g=seq.p_g[0], R_g=seq.R_g[0], v_g=seq.v_g[0], tic_g=seq.tic_g[0], ric_g=seq.ric_g[0]))
+    assert bseq.samples.shape == seq.samples.shape
+    cfg = abi.default_config(); cfg.max_batch, cfg.max_features, cfg.max_obs, cfg.max_num_iterations = 1, 128, 128 * 11, 6
+    pcfg = abi.default_preint_config()
+    for img in seq.images:                     # the same float32 rounding on the direct arm: a 1e-8 input difference grows ~20 x per chained frame
+        img[0]["pts0"] = img[0]["pts0"].astype(np.float32).astype(np.float64); img[0]["pts1"] = img[0]["pts1"].astype(np.float32).astype(np.float64)
+    seq.samples["dt"] = bseq.samples["dt"]      # stamps are stored with nanosecond resolution: dt = stamp differences, like main.cpp:284-300 forms it
+    a = estimator.ReplayDriver(OracleOps(cfg), cfg, pcfg, 1, max_features=64).run(seq)
+    b = estimator.ReplayDriver(OracleOps(cfg), cfg, pcfg, 1, max_features=64).run(bseq)
+    Pa, Ra = a.poses(); Pb, Rb = b.poses()
+    assert Pa.shape == Pb.shape and Pa.shape[1] == 4
+    assert np.abs(Pa - Pb).max() < 1e-9 and np.abs(Ra - Rb).max() < 1e-9, (np.abs(Pa - Pb).max(), np.abs(Ra - Rb).max())
+    csv = str(tmp_path / "vilo.csv")
+    estimator.write_csv(csv, b.est[0], pcfg)
+    assert len(open(csv).read().strip().split("\n")) == 4

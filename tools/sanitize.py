@@ -1,0 +1,29 @@
+"""Small end-to-end run of every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
+
+    compute-sanitizer --tool memcheck  python tools/sanitize.py
+    compute-sanitizer --tool racecheck python tools/sanitize.py     (shared-memory hazards: mbarrier-guarded bulk copies, named barriers)
+
+6 windows x 20 features (two pipeline waves on a grid capped at 4 CTAs would need > 8 windows; the chunked path is covered by tests), prior,
+2 iterations; host-buffer solve (pack / prepare / solve / unpack), per-feature passes, marginalization (both modes), preintegration, evaluators."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from cerberus_b200 import abi, synth, lib
+
+cfg = abi.default_config(); cfg.max_batch, cfg.max_features, cfg.max_obs, cfg.max_num_iterations = 8, 24, 24 * 11, int(os.environ.get("ITERS", "2"))
+be = lib.Backend(cfg)
+batch = synth.generate_batch(6, 20, be, cfg=cfg, prior_features=8, window0=5)       # preintegrate_kernel, evaluators, marg kernels (the prior)
+regs = be.register_batch(batch)
+rep = be.solve_batch(batch)
+be.unregister(regs)
+print("solve", rep["iterations"], rep["final_cost"][:2])
+err, rem = be.outlier_errors(batch.n); dep = be.triangulate(batch.n); sh = be.shift_depth(batch.n)
+flags = np.array([0, 1, 0, 1, 0, 0], dtype=np.int32)
+J = np.zeros((6, abi.MAX_PRIOR_DIM ** 2)); r = np.zeros((6, abi.MAX_PRIOR_DIM)); priors = (abi.Prior * 6)()
+for w in range(6):
+    priors[w].linearized_jacobians = J[w].ctypes.data_as(abi.c_dp); priors[w].linearized_residuals = r[w].ctypes.data_as(abi.c_dp)
+sw = be.batch_marginalize(flags, None, priors)
+print("marginalize", [priors[w].n for w in range(6)], sw.ravel())
+cost, g, d = be.debug_linearize(batch, 1)
+print("probe", cost)
