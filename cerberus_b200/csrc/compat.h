@@ -42,6 +42,10 @@
         while (!done_) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"                 \
                                     : "=r"(done_) : "r"(CERB_SMEM_U32(bar)), "r"((unsigned)(parity)) : "memory");                                    \
     } while (0)
+// producer / consumer hand-over through a shared-memory flag: release store by the producer (after a __syncwarp that orders the other
+// lanes' writes before it), acquire load in the consumer's spin loop
+#define CERB_ST_RELEASE_S32(p, v) asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(CERB_SMEM_U32(p)), "r"((int)(v)) : "memory")
+#define CERB_LD_ACQUIRE_S32(p) ({ int v_; asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v_) : "r"(CERB_SMEM_U32(p)) : "memory"); v_; })
 // body of a spin-wait on a shared-memory flag (a short sleep keeps the polling warps out of the producer's issue slots)
 #define CERB_SPIN_PAUSE() __nanosleep(20)
 // non-blocking arrival at a named barrier (producer / consumer hand-over: one side arrives, the other side syncs)

@@ -629,6 +629,10 @@ CERB_NOINLINE double inertial_linearize(const SolveParams &P, int w, const doubl
             const int *plan = reinterpret_cast<const int *>(P.ws + (size_t)blockIdx.x * P.ws_stride + ws_imuplan(P.maxF));
             _Pragma("unroll")
             for (int q = 0; q < 30; q++) { plx[q] = __ldg(plan + (2 * q) * 32 + lane); ply[q] = __ldg(plan + (2 * q + 1) * 32 + lane); }
+            // entries without a destination share a dummy slot per lane in the plan: give every IMU warp its own (no write-write hazard between warps)
+            const int dummy = (int)(s.idg - smem_base) + lane;
+            _Pragma("unroll")
+            for (int q = 0; q < 30; q++) if (plx[q] == dummy && (ply[q] & 4095) == 0) plx[q] += 32 * wid;
         }
         double sa[20];
         auto load_S = [&](int i) {      // A-fragments of the upper-triangular sqrt_info: block row mi needs k-steps ks >= 2 mi
@@ -903,14 +907,14 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
         // e = 0, 1, the entry (la, lb) = (8 mi + lane / 4, 8 ni + 2 (lane % 4) + e).  Its destination in Hxx / Hxy / Hyy / g is
         // affine in the factor index i, so the plan stores two ints: offset(i = 0) and stride | (mirror delta + 256) << 12 (in doubles
         // from the start of shared memory; the mirror is the transposed entry of a diagonal Hyy block).  Entries without a destination
-        // point at a per-lane dummy slot (sca[32 + lane], never read) with stride 0.
+        // point at a per-lane dummy slot (idg[32 warp + lane], never read) with stride 0.
         int *plan = reinterpret_cast<int *>(ws + ws_imuplan(F));
         int q = 0;
         for (int mi = 0; mi < 5; mi++)
             for (int ni = mi; ni < 5; ni++, q++)
                 for (int e = 0; e < 2; e++) {
                     const int la = 8 * mi + (tid >> 2), lb = 8 * ni + 2 * (tid & 3) + e;
-                    int px = (int)(sca + 32 - smem_base) + tid, py = 256 << 12;      // default: dummy slot of this lane, stride 0, delta 0
+                    int px = (int)(s.idg - smem_base) + tid, py = 256 << 12;         // default: dummy slot of this lane (idg is idle during a linearisation; each IMU warp adds 32 x its index), stride 0, delta 0
                     if (la <= lb && lb <= 38 && la != 38) {
                         double *p0[2], *p1[2];
                         for (int i = 0; i < 2; i++) {
@@ -1096,7 +1100,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                         s.yv[k] = s.g[k];
                         if (k >= NX) s.Ad[((k - NX) / NYB) * 169 + ((k - NX) % NYB) * (NYB + 1)] += mu * s.D[k] * s.D[k];
                     }
-                    volatile int *chain_done = s.ti + 130;              // number of Hyy blocks whose factor (L_f, M_f) warp 0 has published
+                    int *chain_done = s.ti + 130;              // number of Hyy blocks whose factor (L_f, M_f) warp 0 has published
                     if (tid == 0) *chain_done = 0;
                     __syncthreads();
                     if (tid < 32) {
@@ -1154,8 +1158,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                                 if (act) { _Pragma("unroll") for (int c = 0; c < NYB; c++) B[r * NYB + c] = m[c]; }
                                 __syncwarp();
                             }
-                            __threadfence_block();
-                            if (lane == 0) *chain_done = f + 1;              // L_f, M_f and the inverse pivots of block f are in shared memory
+                            __threadfence_block(); __syncwarp();
+                            if (lane == 0) CERB_ST_RELEASE_S32(chain_done, f + 1);   // L_f, M_f and the inverse pivots of block f are in shared memory
                         }
                         PH_MARK(6);
                     } else {
@@ -1249,7 +1253,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
                             for (int k = 0; k < NYB; k++) tp[k] = 0.0;
                             _Pragma("unroll 1")
                             for (int f = 0; f < NFR; f++) {
-                                while (*chain_done <= f) { CERB_SPIN_PAUSE(); }
+                                while (CERB_LD_ACQUIRE_S32(chain_done) <= f) { CERB_SPIN_PAUSE(); }
                                 __threadfence_block();
                                 const double *L = s.Ad + f * 169, *idg = s.idg + NYB * f;
                                 double *t = row + NYB * f;
@@ -1647,8 +1651,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) marg_assemble_kernel(CERB_G
     double *hh = ws + ws_vecs(F), *gl = hh + F, *sl = gl + F;
     int *chunks = reinterpret_cast<int *>(ws + ws_chunks(F));
     double *pimg = ws + ws_prior(F);
-    int *colx = reinterpret_cast<int *>(s.idg);           // [79] column of x index a in A (-1: block absent), then [26] of the y indices of frames 0 / 1
-                                                          // (idg | idx: 224 doubles that only the Gauss-Newton step of the solver uses)
+    int *colx = reinterpret_cast<int *>(s.idx);           // [79] column of x index a in A (-1: block absent), then [26] of the y indices of frames 0 / 1
+                                                          // (idx: 80 doubles that only the Gauss-Newton step of the solver uses; idg holds the dummy slots of the IMU scatter)
     int *coly = colx + 80;
     int *misc = coly + 32;                                // [0] n0, [1] m, [2] n, [3] status, [4] stereo seen, [5] longest anchor-0 track
     if (tid < 32) {                                       // scatter plan of the IMU-leg Gram matrix (same as in vilo_solve_kernel)
@@ -1658,7 +1662,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) marg_assemble_kernel(CERB_G
             for (int ni = mi; ni < 5; ni++, q++)
                 for (int e = 0; e < 2; e++) {
                     const int la = 8 * mi + (tid >> 2), lb = 8 * ni + 2 * (tid & 3) + e;
-                    int px = (int)(s.sca + 32 - smem_base) + tid, py = 256 << 12;
+                    int px = (int)(s.idg - smem_base) + tid, py = 256 << 12;
                     if (la <= lb && lb <= 38 && la != 38) {
                         double *p0[2], *p1[2];
                         for (int i = 0; i < 2; i++) {

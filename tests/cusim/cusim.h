@@ -45,6 +45,8 @@ inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cusim::wa
 #define CERB_CP_ASYNC_WAIT() ((void)0)
 #define CERB_SPIN_PAUSE() std::this_thread::yield()
 // TMA bulk copy + mbarrier: the issuing thread copies at once, the (uniformly executed) wait is a block barrier
+#define CERB_ST_RELEASE_S32(p, v) __atomic_store_n((int *)(p), (int)(v), __ATOMIC_RELEASE)
+#define CERB_LD_ACQUIRE_S32(p) __atomic_load_n((const int *)(p), __ATOMIC_ACQUIRE)
 #define CERB_MBAR_INIT(bar) ((void)0)
 #define CERB_BULK_G2S(dst_smem, src_global, bytes, bar) std::memcpy((dst_smem), (src_global), (bytes))
 #define CERB_MBAR_WAIT(bar, parity) __syncthreads()
