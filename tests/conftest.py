@@ -17,3 +17,9 @@ def pytest_xdist_auto_num_workers(config):
     if "not gpu" in expr:
         return min(4, max(1, (os.cpu_count() or 2) // 2))
     return 0
+
+
+def pytest_addoption(parser, pluginmanager):
+    """pytest.ini passes `-n auto`; without pytest-xdist (or with `-p no:xdist`) accept and ignore it, so that the suite still runs (serially)."""
+    if not pluginmanager.hasplugin("xdist"):
+        parser.getgroup("xdist-fallback")._addoption("-n", "--numprocesses", dest="numprocesses_ignored", default=None, help="ignored: pytest-xdist is not active")
