@@ -11,6 +11,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.hookimpl(optionalhook=True)
 def pytest_xdist_auto_num_workers(config):
     """`-n auto` (pytest.ini): parallel workers only for the CPU tier; the GPU tier stays in one process (one handle owns the device and its pinned staging)."""
     expr = getattr(config.option, "markexpr", "") or ""
