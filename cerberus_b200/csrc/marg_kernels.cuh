@@ -60,7 +60,7 @@ CERB_D void jacobi_angles(const double *M, int ld, int k, int kp, int r, double 
         int p, q; jacobi_pair(t, r, kp, p, q);
         double c = 1.0, s = 0.0;
         if (q < k) {
-            const double apq = M[p + (size_t)q * ld], app = M[p + (size_t)p * ld], aqq = M[q + (size_t)q * ld];
+            const double apq = M[p + q * ld], app = M[p + p * ld], aqq = M[q + q * ld];
             if (apq != 0.0 && fabs(apq) > 1e-15 * sqrt(fabs(app * aqq))) {
                 const double theta = (aqq - app) / (2.0 * apq);
                 const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
@@ -82,7 +82,7 @@ CERB_D void jacobi_angles(const double *M, int ld, int k, int kp, int r, double 
 CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, int ldt, int nct, double *cs, int *pq, int *flag) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
     const int kp = k + (k & 1), half = kp / 2, rounds = kp - 1;
-    if (V) for (int j = wid; j < k; j += nwarp) for (int i = lane; i < k; i += 32) V[i + (size_t)j * ldv] = (i == j) ? 1.0 : 0.0;
+    if (V) for (int j = wid; j < k; j += nwarp) for (int i = lane; i < k; i += 32) V[i + j * ldv] = (i == j) ? 1.0 : 0.0;
     if (tid == 0) { flag[0] = 0; flag[1] = 0; }
     __syncthreads();
     jacobi_angles(M, ld, k, kp, 0, cs, pq, flag);
@@ -94,10 +94,10 @@ CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, i
                 const double c = cs[2 * t], s = cs[2 * t + 1];
                 if (s == 0.0) continue;
                 const int p = pq[t] & 0xffff, q = pq[t] >> 16;
-                double *mp = M + (size_t)p * ld, *mq = M + (size_t)q * ld;
+                double *mp = M + p * ld, *mq = M + q * ld;
                 for (int i = lane; i < k; i += 32) { const double a = mp[i], b = mq[i]; mp[i] = c * a - s * b; mq[i] = s * a + c * b; }
                 if (V) {
-                    double *vp = V + (size_t)p * ldv, *vq = V + (size_t)q * ldv;
+                    double *vp = V + p * ldv, *vq = V + q * ldv;
                     for (int i = lane; i < k; i += 32) { const double e = vp[i], f = vq[i]; vp[i] = c * e - s * f; vq[i] = s * e + c * f; }
                 }
             }
@@ -108,7 +108,7 @@ CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, i
                 for (int u = 0; u < 2; u++) {                     // T rows first: the loads stay in flight during the row pass below
                     const int t = t0 + u * nwarp;
                     if (T && t < half && cs[2 * t + 1] != 0.0) {
-                        const double *tp = T + (size_t)(pq[t] & 0xffff) * ldt, *tq = T + (size_t)(pq[t] >> 16) * ldt;
+                        const double *tp = T + (pq[t] & 0xffff) * ldt, *tq = T + (pq[t] >> 16) * ldt;
                         _Pragma("unroll")
                         for (int v = 0; v < 4; v++) { const int j = lane + 32 * v; ta[u][v] = j < nct ? tp[j] : 0.0; tb[u][v] = j < nct ? tq[j] : 0.0; }
                     }
@@ -121,11 +121,11 @@ CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, i
                     if (s == 0.0) continue;
                     const int p = pq[t] & 0xffff, q = pq[t] >> 16;
                     for (int j = lane; j < k; j += 32) {
-                        const double a = M[p + (size_t)j * ld], b = M[q + (size_t)j * ld];
-                        M[p + (size_t)j * ld] = c * a - s * b; M[q + (size_t)j * ld] = s * a + c * b;
+                        const double a = M[p + j * ld], b = M[q + j * ld];
+                        M[p + j * ld] = c * a - s * b; M[q + j * ld] = s * a + c * b;
                     }
                     if (T) {
-                        double *tp = T + (size_t)p * ldt, *tq = T + (size_t)q * ldt;
+                        double *tp = T + p * ldt, *tq = T + q * ldt;
                         _Pragma("unroll")
                         for (int v = 0; v < 4; v++) { const int j = lane + 32 * v; if (j < nct) { tp[j] = c * ta[u][v] - s * tb[u][v]; tq[j] = s * ta[u][v] + c * tb[u][v]; } }
                     }
@@ -136,7 +136,7 @@ CERB_D int jacobi_eig(double *M, int ld, int k, double *V, int ldv, double *T, i
             __syncthreads();
             // keep M exactly symmetric: the column and the row pass round differently, and an asymmetric residue of eps |M| is enough to
             // keep the null space of a rank-deficient Schur complement rotating for ever (the angles are taken from the upper triangle)
-            for (int j = wid; j < k; j += nwarp) for (int i = j + 1 + lane; i < k; i += 32) M[i + (size_t)j * ld] = M[j + (size_t)i * ld];
+            for (int j = wid; j < k; j += nwarp) for (int i = j + 1 + lane; i < k; i += 32) M[i + j * ld] = M[j + i * ld];
             if (r + 1 < rounds) jacobi_angles(M, ld, k, kp, r + 1, cs, pq, flag + (sweeps & 1));
             else jacobi_angles(M, ld, k, kp, 0, cs, pq, flag + ((sweeps + 1) & 1));
             __syncthreads();
@@ -167,10 +167,12 @@ CERB_GLOBAL void marg_schur_kernel(int n_windows, int mmax, int nmax, const int 
         const double *A = A_all + (size_t)w * (A_stride ? A_stride : (long)pos * pos), *b = b_all + (size_t)w * (b_stride ? b_stride : (long)pos);
         // ---- phase 1: Amm = 0.5 (Amm + Amm^T) = V1 diag(lambda) V1^T;  T = V1^T [Amr | bm] --------------------------------------
         double *M1 = m1_smem ? body : M1g;
-        for (int e = tid; e < m * m; e += nt) { const int i = e % m, j = e / m; M1[i + (size_t)j * ld1] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]); }
+        for (int j = tid / 32; j < m; j += nt / 32) for (int i = tid & 31; i < m; i += 32) M1[i + j * ld1] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]);
         for (int e = tid; e < m * nc; e += nt) { const int c = e % nc, i = e / nc; Tg[(size_t)i * ldt + c] = c < n ? A[(size_t)i * pos + m + c] : b[i]; }
         __syncthreads();
-        const int sw1 = jacobi_eig(M1, ld1, m, nullptr, 0, Tg, ldt, nc, cs, pq, flag);
+        // two instantiations: with the matrix in shared memory the compiler sees the address space (LDS / STS with 32-bit addresses instead of
+        // generic 64-bit loads: the passes are instruction-bound)
+        const int sw1 = m1_smem ? jacobi_eig(body, ld1, m, nullptr, 0, Tg, ldt, nc, cs, pq, flag) : jacobi_eig(M1g, ld1, m, nullptr, 0, Tg, ldt, nc, cs, pq, flag);
         for (int i = tid; i < m; i += nt) { const double lam = M1[i + (size_t)i * ld1]; inv[i] = lam > eps ? 1.0 / lam : 0.0; }
         __syncthreads();
         // ---- [Ar | br] = [Arr | brr] - T^T diag(inv) T (lower triangle; SelfAdjointEigenSolver reads the lower triangle) ---------------

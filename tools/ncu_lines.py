@@ -3,11 +3,12 @@ usage: python tools/ncu_lines.py <ncu_sass.csv> <lib.so> [top]
 Joins instruction order with `nvdisasm -g` line info of the same library build (instruction i of the kernel in both)."""
 import csv, re, subprocess, sys, tempfile, os, collections
 csv_path, lib, top = sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40
+kernel = next((a[7:] for a in sys.argv[4:] if a.startswith("kernel=")), "vilo_solve_kernel")      # e.g. kernel=marg_schur_kernel
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
-start = next(i for i, l in enumerate(dis) if ".text._ZN4cerb17vilo_solve_kernel" in l)
+start = next(i for i, l in enumerate(dis) if l.startswith("//--------------------- .text._ZN4cerb") and kernel in l)
 lines, cur = [], None
 for l in dis[start + 1:]:
     if l.startswith("//--------------------- .text"): break
