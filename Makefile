@@ -2,7 +2,7 @@
 NVCC ?= nvcc
 CXX ?= g++
 CSRC = cerberus_b200/csrc
-HDRS = $(wildcard $(CSRC)/*.cuh) $(CSRC)/compat.h include/cerberus_b200.h
+HDRS = $(wildcard $(CSRC)/*.cuh) $(CSRC)/*.inl $(CSRC)/compat.h include/cerberus_b200.h
 
 .PHONY: all lib oracle sim prof clean
 all: lib oracle sim

@@ -236,3 +236,8 @@ class WindowBatch:
         self.para_Feature[...] = feat
         for w in range(self.n):
             self.states[w].para_Feature = self.para_Feature[w].ctypes.data_as(c_dp)
+
+
+class Image(C.Structure):
+    """CerbImage: one camera frame of one robot (the feature tracker's output, main.cpp:200-233)."""
+    _fields_ = [("n", C.c_int32), ("reserved", C.c_int32), ("ids", C.POINTER(C.c_int64)), ("pts0", c_dp), ("has1", C.POINTER(C.c_uint8)), ("pts1", c_dp)]

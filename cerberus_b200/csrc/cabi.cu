@@ -1062,3 +1062,5 @@ void cerb_double2vector(const CerbWindowState *before, const CerbWindowState *af
 }
 
 }  // extern "C"
+
+#include "replay_host.inl"

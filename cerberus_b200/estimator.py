@@ -530,6 +530,98 @@ class DeviceOps:
         self.be.marginalize(self.cfg, src, dst, margin_old=(np.asarray(flags) == MARGIN_OLD))
 
 
+class NativeReplay:
+    """The same lock-step replay with the host side in C++ inside the library (csrc/replay_host.inl, cerb_replay_*): one call per camera frame
+    for all robots.  Same inputs and outputs as ReplayDriver(DeviceOps(...)); tests/test_replay.py compares the two."""
+
+    def __init__(self, backend, pcfg, n, max_features=160, estimate_extrinsic=1, estimate_td=0):
+        L = backend.lib
+        L.cerb_replay_create.argtypes = [C.c_void_p, C.POINTER(abi.PreintConfig), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.cerb_replay_destroy.argtypes = [C.c_void_p]; L.cerb_replay_destroy.restype = None
+        L.cerb_replay_set_extrinsics.argtypes = [C.c_void_p, C.c_int32, abi.c_dp, abi.c_dp]
+        L.cerb_replay_seed_frame.argtypes = [C.c_void_p, C.c_int32, C.c_int32, abi.c_dp, abi.c_dp, abi.c_dp, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(abi.Image), C.c_double]
+        L.cerb_replay_step.argtypes = [C.c_void_p, C.POINTER(abi.Image), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_double, C.POINTER(abi.SolveReport)]
+        L.cerb_replay_path.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), abi.c_dp, C.c_int32]
+        L.cerb_replay_feature_ids.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]
+        L.cerb_replay_timing.argtypes = [C.c_void_p, abi.c_dp, abi.c_dp]
+        self.be, self.n = backend, n
+        self.r = C.c_void_p()
+        backend._check(L.cerb_replay_create(backend.h, C.byref(pcfg), n, max_features, estimate_extrinsic, estimate_td, C.byref(self.r)))
+        self.reports = []
+
+    def close(self):
+        if self.r:
+            self.be.lib.cerb_replay_destroy(self.r); self.r = C.c_void_p()
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+    @staticmethod
+    def _image(img, keep):
+        ids = np.ascontiguousarray(img["ids"], dtype=np.int64); p0 = np.ascontiguousarray(img["pts0"], dtype=np.float64)
+        h1 = np.ascontiguousarray(img["has1"], dtype=np.uint8); p1 = np.ascontiguousarray(img["pts1"], dtype=np.float64)
+        keep.extend([ids, p0, h1, p1])
+        im = abi.Image(); im.n = len(ids)
+        im.ids = ids.ctypes.data_as(C.POINTER(C.c_int64)); im.pts0 = p0.ctypes.data_as(abi.c_dp); im.has1 = h1.ctypes.data_as(C.POINTER(C.c_uint8)); im.pts1 = p1.ctypes.data_as(abi.c_dp)
+        return im
+
+    def seed(self, seq):
+        L, _p = self.be.lib, lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(abi.c_dp)
+        for w in range(self.n):
+            tic, ric = np.ascontiguousarray(seq.tic_g[w]), np.ascontiguousarray(seq.ric_g[w])
+            self.be._check(L.cerb_replay_set_extrinsics(self.r, w, _p(tic), _p(ric)))
+            for k in range(WINDOW_SIZE + 1):
+                keep = []
+                first = np.ascontiguousarray(seq.first[w, 0 if k == 0 else k - 1: (1 if k == 0 else k)])
+                smp = np.ascontiguousarray(seq.samples[w][k - 1]) if k > 0 else first[:0]
+                im = self._image(seq.images[k][w], keep) if k < WINDOW_SIZE else None
+                P, R, V = np.ascontiguousarray(seq.p_g[w, k]), np.ascontiguousarray(seq.R_g[w, k]), np.ascontiguousarray(seq.v_g[w, k])
+                self.be._check(L.cerb_replay_seed_frame(self.r, w, k, _p(P), _p(R), _p(V), first.ctypes.data, smp.ctypes.data if len(smp) else None, len(smp),
+                                                        C.byref(im) if im is not None else None, float(k)))
+
+    def step(self, images, firsts, samples, header):
+        keep = []
+        ims = (abi.Image * self.n)(*[self._image(images[w], keep) for w in range(self.n)])
+        fr = np.ascontiguousarray(np.stack([np.asarray(firsts[w]).reshape(()) for w in range(self.n)]))
+        smp = [np.ascontiguousarray(samples[w]) for w in range(self.n)]
+        ptrs = (C.c_void_p * self.n)(*[s.ctypes.data if len(s) else None for s in smp])
+        ns = (C.c_int32 * self.n)(*[len(s) for s in smp])
+        rep = (abi.SolveReport * self.n)()
+        self.be._check(self.be.lib.cerb_replay_step(self.r, ims, fr.ctypes.data, ptrs, ns, float(header), rep))
+        self.reports.append(np.frombuffer(rep, dtype=abi.report_dtype, count=self.n).copy())
+
+    def run(self, seq, n_steps=None):
+        self.seed(seq)
+        last = seq.n_frames if n_steps is None else min(seq.n_frames, WINDOW_SIZE + n_steps)
+        for k in range(WINDOW_SIZE, last):
+            firsts = [seq.first[w, k - 1] for w in range(self.n)]
+            smp = [seq.samples[w][k - 1][:0] if k == WINDOW_SIZE else seq.samples[w][k - 1] for w in range(self.n)]
+            self.step([seq.images[k][w] for w in range(self.n)], firsts, smp, float(k))
+        return self
+
+    def path(self, w):
+        n = C.c_int32()
+        self.be._check(self.be.lib.cerb_replay_path(self.r, w, C.byref(n), None, 0))
+        out = np.zeros((n.value, 20))
+        self.be._check(self.be.lib.cerb_replay_path(self.r, w, C.byref(n), out.ctypes.data_as(abi.c_dp), n.value))
+        return out
+
+    def poses(self):
+        rows = np.stack([self.path(w) for w in range(self.n)])
+        return rows[:, :, 1:4], rows[:, :, 4:13].reshape(self.n, -1, 3, 3)
+
+    def feature_ids(self, w):
+        n = C.c_int32(); ids = np.zeros(4096, dtype=np.int32)
+        self.be._check(self.be.lib.cerb_replay_feature_ids(self.r, w, C.byref(n), ids.ctypes.data_as(C.POINTER(C.c_int32)), ids.size))
+        return ids[:n.value].tolist()
+
+    def timing(self):
+        dev = np.zeros(6); host = C.c_double()
+        self.be._check(self.be.lib.cerb_replay_timing(self.r, dev.ctypes.data_as(abi.c_dp), C.cast(C.byref(host), abi.c_dp)))
+        return dict(zip(("preintegrate", "triangulate", "solve", "marginalize", "outliers", "shift"), dev.tolist()), host=host.value)
+
+
 def write_csv(path, est, pcfg):
     """The result file of the reference's main loop (src/main.cpp:153-197): time [ns], robot-body position / velocity (IMU pose moved
     by R_br p_br), six Kalman-filter columns and three mocap columns (not produced here: 0), rho1..rho4 of the newest frame."""

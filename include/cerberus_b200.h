@@ -395,6 +395,41 @@ int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t 
  * Kept-block order: poses ascending, speed bias, leg bias, ex0, ex1, td (the reference's order is that of an unordered_map keyed by pointer). */
 int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindowState *states, CerbPrior *priors, int32_t *sweeps);
 
+/* ---- sequence replay: the reference's steady-state frame loop for B robots in lock step, host side in C++ inside this library -----------------
+ * (csrc/replay_host.inl mirrors Estimator::processIMULeg / processImage (NON_LINEAR) / optimization / slideWindow and FeatureManager,
+ * estimator.cpp:590-846,1054-1677, feature_manager.cpp; every numerical step is one of the batched entry points above).  The reference's
+ * initialisation (estimator.cpp:700-797) is out of scope: the window is seeded frame by frame at given states. */
+typedef struct CerbReplay CerbReplay;
+/* one camera frame of one robot as the feature tracker delivers it (main.cpp:200-233): per feature the 7-vector x, y, z = 1, u, v, vx, vy of
+ * camera 0 and, where has1, of camera 1 */
+typedef struct CerbImage {
+    int32_t n;
+    int32_t reserved;
+    const int64_t *ids;        /* [n] feature ids */
+    const double *pts0;        /* [n][7] */
+    const uint8_t *has1;       /* [n] */
+    const double *pts1;        /* [n][7] */
+} CerbImage;
+/* h must have max_batch >= n_robots and max_features >= 2 * max_features of the replay (the triangulation batch holds every track). */
+int cerb_replay_create(CerbHandle *h, const CerbPreintConfig *pcfg, int32_t n_robots, int32_t max_features, int32_t estimate_extrinsic,
+                       int32_t estimate_td, CerbReplay **out);
+void cerb_replay_destroy(CerbReplay *r);
+int cerb_replay_set_extrinsics(CerbReplay *r, int32_t robot, const double *tic /* [2][3] */, const double *ric /* [2][9] row-major */);
+/* Seed frame k = 0 .. WINDOW_SIZE of a robot: states P, R (row-major), V; `first` = the IMU / leg sample at the previous frame instant (at
+ * frame 0: at frame 0), `samples` = the interval k-1 -> k (ignored for k = 0); image = the tracked features of frame k (NULL for k = WINDOW_SIZE:
+ * that frame's image arrives with the first cerb_replay_step, whose interval is then empty). */
+int cerb_replay_seed_frame(CerbReplay *r, int32_t robot, int32_t k, const double *P, const double *R, const double *V, const CerbIMULegSample *first,
+                           const CerbIMULegSample *samples, int32_t n_samples, const CerbImage *image, double header);
+/* processMeasurements for one camera frame of every robot: images [n_robots], firsts [n_robots] (sample at the previous frame instant),
+ * samples [n_robots] pointers / n_samples [n_robots] (the new interval), header = the frame's stamp; reports (optional) [n_robots]. */
+int cerb_replay_step(CerbReplay *r, const CerbImage *images, const CerbIMULegSample *firsts, const CerbIMULegSample *const *samples,
+                     const int32_t *n_samples, double header, CerbSolveReport *reports);
+/* Published states of the newest frame after every processed image: rows of 20 doubles = header, P(3), R(9, row-major), V(3), rho(4). */
+int cerb_replay_path(CerbReplay *r, int32_t robot, int32_t *n_rows, double *out, int32_t max_rows);
+int cerb_replay_feature_ids(CerbReplay *r, int32_t robot, int32_t *n, int32_t *ids, int32_t max_ids);
+/* seconds spent in: preintegrate, triangulate, solve, marginalize, outliers, shift (device + ABI) and in host bookkeeping */
+int cerb_replay_timing(CerbReplay *r, double *device6, double *host);
+
 /* ---- host-side helpers that stay on the CPU in the reference too ---------------------------- */
 /* Gauge re-anchoring of Estimator::double2vector (estimator.cpp:903-957): rotates the solved
  * window by the yaw difference of frame 0 and re-anchors its position.  before/after are the

@@ -87,3 +87,70 @@ def test_replay_50_frames_gpu():
     Po, _ = arms[1].poses()
     err_o = np.linalg.norm(Po - seq.p[:, 10:10 + Po.shape[1]], axis=-1)
     assert np.abs(err - err_o).max() < 2e-3 and err.max() < 0.5
+
+
+def test_native_replay_matches_python_mirror_sim():
+    """The C++ host mirror inside the library (csrc/replay_host.inl, cerb_replay_*) against the Python mirror, same backend (CPU simulator), same sequence:
+    identical bookkeeping (feature lists, iteration counts), published poses equal up to the rounding of a few host-side 3 x 3 products."""
+    n, F = 1, 24
+    cfg = abi.default_config(); cfg.max_batch = n; cfg.max_features = 2 * F; cfg.max_obs = 2 * F * 11; cfg.max_num_iterations = 2
+    pcfg = abi.default_preint_config()
+    seq = synth.generate_sequence(n, 14, tracked=14, max_len=12, min_len=3)
+    py = estimator.ReplayDriver(estimator.DeviceOps(sim_backend(cfg), cfg), cfg, pcfg, n, max_features=F).run(seq)
+    nat = estimator.NativeReplay(sim_backend(cfg), pcfg, n, max_features=F).run(seq)
+    P1, R1 = py.poses(); P2, R2 = nat.poses()
+    assert P1.shape == P2.shape == (1, 4, 3)
+    assert np.abs(P1 - P2).max() < 1e-6 and np.abs(R1 - R2).max() < 1e-6 and np.abs(P1[:, :2] - P2[:, :2]).max() < 1e-12
+    assert [f.feature_id for f in py.est[0].f_manager.feature] == nat.feature_ids(0)
+    for a, b in zip(py.reports, nat.reports):
+        assert (a["iterations"] == b["iterations"]).all() and np.abs(a["final_cost"] - b["final_cost"]).max() < 1e-3 * a["final_cost"].max()
+    t = nat.timing()
+    assert t["host"] < 0.5 and t["solve"] > 0
+
+
+@pytest.mark.gpu
+def test_native_replay_gpu():
+    """C++ host mirror on the B200: (1) 4 robots x 52 frames against the Python mirror over the same library and against the oracle arm;
+    (2) 256 robots x 20 frames: the batched replay the Python mirror cannot keep up with (8 ms of bookkeeping per robot and frame)."""
+    n, n_frames, F = 4, 62, 160
+    cfg = abi.default_config(); cfg.max_batch = n; cfg.max_features = 2 * F; cfg.max_obs = 2 * F * 11
+    pcfg = abi.default_preint_config()
+    seq = synth.generate_sequence(n, n_frames, tracked=90, max_len=14, min_len=3)
+    t0 = time.perf_counter()
+    nat = estimator.NativeReplay(lib.Backend(cfg), pcfg, n, max_features=F).run(seq)
+    t_nat = time.perf_counter() - t0
+    py = estimator.ReplayDriver(estimator.DeviceOps(lib.Backend(cfg), cfg), cfg, pcfg, n, max_features=F).run(seq)
+    ora = estimator.ReplayDriver(OracleOps(cfg, eig_mode=1), cfg, pcfg, n, max_features=F).run(seq)
+    Pn, Rn = nat.poses(); Pp, Rp = py.poses(); Po, Ro = ora.poses()
+    d_py = np.abs(Pn - Pp).max(axis=(0, 2)); d_or = np.abs(Pn - Po).max(axis=(0, 2))
+    assert Pn.shape[1] == n_frames - 10
+    assert d_py[:3].max() < 1e-6 and d_py.max() < 2e-3, d_py            # same library underneath: only host rounding differs, then the chain's sensitivity
+    assert d_or[:3].max() < 1e-5 and d_or.max() < 2e-3, d_or
+    for w in range(n):
+        assert [f.feature_id for f in py.est[w].f_manager.feature] == nat.feature_ids(w) or d_py.max() > 1e-6   # identical bookkeeping unless an outlier test flipped on a chain difference
+    T = nat.timing()
+    # (2) many robots
+    nb, fb = 256, 30
+    cfg2 = abi.default_config(); cfg2.max_batch = nb; cfg2.max_features = 2 * F; cfg2.max_obs = 2 * F * 11
+    seq2 = synth.generate_sequence(8, fb, tracked=90, max_len=14, min_len=3)
+    class Tiled:      # 256 robots replaying 8 distinct synthetic sequences
+        pass
+    big = Tiled(); big.n, big.n_frames = nb, fb
+    idx = np.arange(nb) % 8
+    for name in ("tic_g", "ric_g", "p_g", "R_g", "v_g", "first", "samples"):
+        setattr(big, name, getattr(seq2, name)[idx])
+    big.images = [[seq2.images[k][w % 8] for w in range(nb)] for k in range(fb)]
+    t0 = time.perf_counter()
+    many = estimator.NativeReplay(lib.Backend(cfg2), pcfg, nb, max_features=F).run(big)
+    t_many = time.perf_counter() - t0
+    Tm = many.timing()
+    Pm, _ = many.poses()
+    assert np.abs(Pm[8:16] - Pm[0:8]).max() == 0.0                      # identical robots -> bit-identical trajectories
+    lines = [f"native replay (C++ host mirror, cerb_replay_*): {n} robots x {n_frames - 10} frames: {t_nat:.2f} s wall = {n * (n_frames - 10) / t_nat:.0f} robot-frames/s "
+             f"(device + ABI: solve {T['solve']:.2f} s, marginalize {T['marginalize']:.2f} s, preintegrate {T['preintegrate']:.2f} s, other {T['triangulate'] + T['outliers'] + T['shift']:.2f} s; host bookkeeping {T['host']:.3f} s)",
+             f"  max |published position delta| vs the Python mirror over the same library {d_py.max():.2e} m (first 3 frames {d_py[:3].max():.1e}), vs the oracle arm {d_or.max():.2e} m",
+             f"native replay, {nb} robots x {fb - 10} frames: {t_many:.2f} s wall = {nb * (fb - 10) / t_many:.0f} robot-frames/s "
+             f"(solve {Tm['solve']:.2f} s, marginalize {Tm['marginalize']:.2f} s, preintegrate {Tm['preintegrate']:.2f} s, other {Tm['triangulate'] + Tm['outliers'] + Tm['shift']:.2f} s; host bookkeeping {Tm['host']:.2f} s; Python glue around the ABI {t_many - sum(Tm.values()):.2f} s)"]
+    os.makedirs("gpurun_out", exist_ok=True)
+    open("gpurun_out/replay_native_gpu.txt", "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
