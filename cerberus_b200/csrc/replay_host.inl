@@ -199,6 +199,20 @@ struct CerbReplay {
 };
 
 namespace cerbhost {
+// the robots are independent: per-robot bookkeeping runs on a few host threads (fn returns a status; the first failure wins)
+template <class Fn> static int parallel_robots(int n, Fn fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nth = (int)std::min<unsigned>(hw ? hw : 1, 16u);
+    if (n < 16) nth = 1;
+    std::vector<int> rcs(nth, CERB_OK); std::vector<std::string> errs(nth);
+    auto work = [&](int t) { for (int w = t; w < n; w += nth) { const int rc = fn(w); if (rc) { rcs[t] = rc; errs[t] = g_err; return; } } };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nth; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int t = 0; t < nth; t++) if (rcs[t]) return fail(rcs[t], errs[t]);
+    return CERB_OK;
+}
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // CerbWindowDesc / CerbWindowState of robot w: the factor enumeration of estimator.cpp:1114-1216 (features with used_num >= min_used in list order)
@@ -312,49 +326,53 @@ int cerb_replay_step(CerbReplay *rp, const CerbImage *images, const CerbIMULegSa
     const int n = rp->n, F = rp->F;
     int rc;
     double th = now_s(), t0;
-    for (int w = 0; w < n; w++) {
+    parallel_robots(n, [&](int w) {
         Robot &e = rp->robots[w];
         e.process_interval(firsts[w], samples[w], n_samples[w]);
         e.Headers[e.frame_count] = header;
         e.marginalization_flag = e.addFeatureCheckParallax(e.frame_count, images[w], e.td) ? 0 : 1;
-    }
+        return (int)CERB_OK;
+    });
     rp->t_host += now_s() - th;
     rc = preintegrate_dirty(rp); if (rc) return rc;
     // ---- f_manager.triangulate (estimator.cpp:803)
     th = now_s();
-    for (int w = 0; w < n; w++) {
-        rc = fill_window(rp, w, 1, true); if (rc) return rc;
+    rc = parallel_robots(n, [&](int w) {
+        const int r2 = fill_window(rp, w, 1, true); if (r2) return r2;
         double *lam = rp->lam_all.data() + (size_t)w * 2 * F; int k = 0;
         for (auto &it : rp->robots[w].feature) lam[k++] = it.estimated_depth > 0 ? 1.0 / it.estimated_depth : -1.0;
-    }
+        return (int)CERB_OK;
+    });
+    if (rc) return rc;
     rp->t_host += now_s() - th; t0 = now_s();
     std::vector<double> depth((size_t)n * rp->h->F, 0.0);
     rc = cerb_batch_upload(rp->h, n, rp->descs_all.data(), rp->states_all.data()); if (rc) return rc;
     rc = cerb_batch_triangulate(rp->h, kInitDepth, depth.data()); if (rc) return rc;
     rp->t_device[1] += now_s() - t0; th = now_s();
-    for (int w = 0; w < n; w++) { int k = 0; for (auto &it : rp->robots[w].feature) { if (!(it.estimated_depth > 0)) it.estimated_depth = depth[(size_t)w * rp->h->F + k]; k++; } }
-    // ---- optimization(): solve
-    for (int w = 0; w < n; w++) { rc = fill_window(rp, w, 4, false); if (rc) return rc; }
+    rc = parallel_robots(n, [&](int w) {
+        int k = 0; for (auto &it : rp->robots[w].feature) { if (!(it.estimated_depth > 0)) it.estimated_depth = depth[(size_t)w * rp->h->F + k]; k++; }
+        return fill_window(rp, w, 4, false);           // ---- optimization(): solve
+    });
+    if (rc) return rc;
     std::memcpy(rp->before.data(), rp->states.data(), sizeof(CerbWindowState) * n);
     rp->t_host += now_s() - th; t0 = now_s();
     std::vector<CerbSolveReport> rep(n);
     rc = cerb_solve_batch(rp->h, n, rp->descs.data(), rp->states.data(), rep.data()); if (rc && rc != CERB_ERR_NON_FINITE) return rc;
     rp->t_device[2] += now_s() - t0; th = now_s();
     if (reports) std::memcpy(reports, rep.data(), sizeof(CerbSolveReport) * n);
-    for (int w = 0; w < n; w++) {
+    // ---- optimization(): marginalization at the re-anchored states (vector2double again, estimator.cpp:1251 / :1384); the batch is still resident
+    std::vector<int32_t> flags(n);
+    parallel_robots(n, [&](int w) {
         double P[NFRM * 3], R[NFRM * 9], V[NFRM * 3];
         cerb_double2vector(&rp->before[w], &rp->states[w], P, R, V);
         rp->robots[w].double2vector_rest(rp->states[w], rp->states[w].para_Feature, P, R, V);
-    }
-    // ---- optimization(): marginalization at the re-anchored states (vector2double again, estimator.cpp:1251 / :1384); the batch is still resident
-    std::vector<int32_t> flags(n);
-    for (int w = 0; w < n; w++) {
         Robot &e = rp->robots[w];
         double *keep = rp->states[w].para_Feature;
         e.vector2double(rp->states[w]); rp->states[w].para_Feature = keep; e.depthVector(keep);
         flags[w] = e.marginalization_flag;
         rp->next_priors[w].linearized_jacobians = rp->nJ.data() + (size_t)w * CERB_MAX_PRIOR_DIM * CERB_MAX_PRIOR_DIM; rp->next_priors[w].linearized_residuals = rp->nr.data() + (size_t)w * CERB_MAX_PRIOR_DIM;
-    }
+        return (int)CERB_OK;
+    });
     rp->t_host += now_s() - th; t0 = now_s();
     rc = cerb_batch_marginalize(rp->h, flags.data(), rp->states.data(), rp->next_priors.data(), nullptr); if (rc) return rc;
     rp->t_device[3] += now_s() - t0; th = now_s();
@@ -371,31 +389,32 @@ int cerb_replay_step(CerbReplay *rp, const CerbImage *images, const CerbIMULegSa
     rc = cerb_batch_upload(rp->h, n, rp->descs.data(), rp->states.data()); if (rc) return rc;
     rc = cerb_batch_outlier_errors(rp->h, kFocal, err.data(), nullptr); if (rc) return rc;
     rp->t_device[4] += now_s() - t0; th = now_s();
-    for (int w = 0; w < n; w++) {
+    rc = parallel_robots(n, [&](int w) {
         Robot &e = rp->robots[w]; const int *idw = rp->ids.data() + (size_t)w * F;
         std::map<int, bool> bad; bool any = false;
         for (int k = 0; k < rp->nids[w]; k++) if (err[(size_t)w * rp->h->F + k] * kFocal > 3) { bad[idw[k]] = true; any = true; }
         if (any) e.feature.remove_if([&](const Feature &f) { return bad.count(f.id) != 0; });
-    }
-    // ---- slideWindow (+ removeBackShiftDepth on the device for the robots that marginalize the oldest frame)
-    for (int w = 0; w < n; w++) {
-        rc = fill_window(rp, w, 1, true); if (rc) return rc;
+        // ---- slideWindow (+ removeBackShiftDepth on the device for the robots that marginalize the oldest frame)
+        const int r2 = fill_window(rp, w, 1, true); if (r2) return r2;
         double *lam = rp->lam_all.data() + (size_t)w * 2 * F; int k = 0;
-        for (auto &it : rp->robots[w].feature) lam[k++] = 1.0 / it.estimated_depth;
-    }
+        for (auto &it : e.feature) lam[k++] = 1.0 / it.estimated_depth;
+        return (int)CERB_OK;
+    });
+    if (rc) return rc;
     rp->t_host += now_s() - th; t0 = now_s();
     std::vector<int32_t> nstart((size_t)n * rp->h->F), keepf((size_t)n * rp->h->F); std::vector<double> sdepth((size_t)n * rp->h->F, 0.0);
     rc = cerb_batch_upload(rp->h, n, rp->descs_all.data(), rp->states_all.data()); if (rc) return rc;
     rc = cerb_batch_shift_depth(rp->h, kInitDepth, nstart.data(), sdepth.data(), keepf.data()); if (rc) return rc;
     rp->t_device[5] += now_s() - t0; th = now_s();
-    for (int w = 0; w < n; w++) {
+    parallel_robots(n, [&](int w) {
         Robot &e = rp->robots[w]; const int *idw = rp->ids_all.data() + (size_t)w * 2 * F;
         std::map<int, double> nd; for (int k = 0; k < rp->nids_all[w]; k++) nd[idw[k]] = sdepth[(size_t)w * rp->h->F + k];
         e.slide_window(nd);
         e.removeFailures();
         e.path.push_back(header); for (int k = 0; k < 3; k++) e.path.push_back(e.Ps[W][k]); for (int k = 0; k < 9; k++) e.path.push_back(e.Rs[W][k]);
         for (int k = 0; k < 3; k++) e.path.push_back(e.Vs[W][k]); for (int k = 0; k < 4; k++) e.path.push_back(e.Rho[W][k]);
-    }
+        return (int)CERB_OK;
+    });
     rp->t_host += now_s() - th;
     return CERB_OK;
 }
