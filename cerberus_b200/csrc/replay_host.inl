@@ -54,6 +54,7 @@ struct Robot {
     bool has_prior = false; CerbPrior prior; std::vector<double> pJ, pr;
     bool openEx = false; int estimate_extrinsic = 1, estimate_td = 0;
     std::vector<double> path;              // per processed image: header, P(3), R(9), V(3), rho(4) of the newest frame
+    std::vector<int> flag_hist;            // marginalization_flag of every processed image
     int last_track_num = 0, new_feature_num = 0, long_track_num = 0;
 
     Robot() {
@@ -331,6 +332,7 @@ int cerb_replay_step(CerbReplay *rp, const CerbImage *images, const CerbIMULegSa
         e.process_interval(firsts[w], samples[w], n_samples[w]);
         e.Headers[e.frame_count] = header;
         e.marginalization_flag = e.addFeatureCheckParallax(e.frame_count, images[w], e.td) ? 0 : 1;
+        e.flag_hist.push_back(e.marginalization_flag);
         return (int)CERB_OK;
     });
     rp->t_host += now_s() - th;
@@ -424,6 +426,13 @@ int cerb_replay_path(CerbReplay *rp, int32_t robot, int32_t *n_rows, double *out
     const std::vector<double> &p = rp->robots[robot].path;
     *n_rows = (int32_t)(p.size() / 20);
     if (out) { const size_t rows = std::min<size_t>(*n_rows, max_rows > 0 ? max_rows : 0); std::memcpy(out, p.data(), rows * 20 * sizeof(double)); }
+    return CERB_OK;
+}
+int cerb_replay_flags(CerbReplay *rp, int32_t robot, int32_t *n, int32_t *flags, int32_t max_flags) {
+    if (!rp || robot < 0 || robot >= rp->n || !n) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_replay_flags: bad argument");
+    const std::vector<int> &f = rp->robots[robot].flag_hist;
+    *n = (int32_t)f.size();
+    if (flags) for (int k = 0; k < *n && k < max_flags; k++) flags[k] = f[k];
     return CERB_OK;
 }
 int cerb_replay_timing(CerbReplay *rp, double *device6, double *host) {

@@ -370,6 +370,7 @@ class ReplayDriver:
         self.batch_all = abi.WindowBatch(n, 2 * max_features)        # triangulation sees every track, also those with < 4 observations
         self.batch_next = abi.WindowBatch(n, 1, 1)                   # receives the priors of the next window
         self.reports = []
+        self.flags = []                                              # marginalization flag of every robot at every processed frame
         self.timing = dict(preintegrate=0.0, triangulate=0.0, solve=0.0, marginalize=0.0, outliers=0.0, shift=0.0, host=0.0)
 
     def seed(self, seq):
@@ -451,6 +452,7 @@ class ReplayDriver:
         for w, e in enumerate(self.est):
             e.vector2double(self.batch.states[w], self.batch.para_Feature[w])
         flags = np.array([e.marginalization_flag for e in self.est], dtype=np.int32)
+        self.flags.append(flags.copy())
         T["host"] += time.perf_counter() - t0
         t0 = time.perf_counter()
         self.ops.marginalize(self.batch, self.batch_next, flags)
@@ -615,6 +617,12 @@ class NativeReplay:
         n = C.c_int32(); ids = np.zeros(4096, dtype=np.int32)
         self.be._check(self.be.lib.cerb_replay_feature_ids(self.r, w, C.byref(n), ids.ctypes.data_as(C.POINTER(C.c_int32)), ids.size))
         return ids[:n.value].tolist()
+
+    def flag_history(self, w):
+        n = C.c_int32(); out = np.zeros(4096, dtype=np.int32)
+        self.be.lib.cerb_replay_flags.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]
+        self.be._check(self.be.lib.cerb_replay_flags(self.r, w, C.byref(n), out.ctypes.data_as(C.POINTER(C.c_int32)), out.size))
+        return out[:n.value]
 
     def timing(self):
         dev = np.zeros(6); host = C.c_double()

@@ -144,7 +144,7 @@ def _trajectory(par, t):
     wz = par["wz"]
     small = np.abs(wz) < 1e-6
     wz_s = np.where(small, 1.0, wz)
-    sp = 0.5
+    sp = par.get("sp", 0.5)                      # forward speed [m/s] (0.5)
     x = np.where(small, sp * np.cos(par["yaw0"]) * t, sp * (np.sin(yaw) - np.sin(par["yaw0"])) / wz_s)
     y = np.where(small, sp * np.sin(par["yaw0"]) * t, -sp * (np.cos(yaw) - np.cos(par["yaw0"])) / wz_s)
     wb = 4 * np.pi
@@ -386,7 +386,7 @@ class SynthSequence:
     pass
 
 
-def generate_sequence(n, n_frames, tracked=60, seed0=7000, stereo_prob=0.9, outlier_fraction=0.0, min_len=2, max_len=14):
+def generate_sequence(n, n_frames, tracked=60, seed0=7000, stereo_prob=0.9, outlier_fraction=0.0, min_len=2, max_len=14, speed=0.5, yaw_rate=0.3):
     """n robots, n_frames frames (>= 12).  Features: every frame spawns enough new landmarks to keep ~`tracked` alive; a landmark is seen
     for L in [min_len, max_len] consecutive frames (tracks shorter than 4 never enter the solve, like in the reference), in the left
     camera always and in the right one with probability stereo_prob per observation.
@@ -405,7 +405,7 @@ def generate_sequence(n, n_frames, tracked=60, seed0=7000, stereo_prob=0.9, outl
         return np.stack([fn(r) for r in rngs])
 
     par = {
-        "yaw0": draw(lambda r: r.uniform(-np.pi, np.pi, 1)), "wz": draw(lambda r: r.uniform(-0.3, 0.3, 1)),
+        "yaw0": draw(lambda r: r.uniform(-np.pi, np.pi, 1)), "wz": draw(lambda r: r.uniform(-yaw_rate, yaw_rate, 1)), "sp": speed,
         "ph_r": draw(lambda r: r.uniform(0, 2 * np.pi, 1)), "ph_p": draw(lambda r: r.uniform(0, 2 * np.pi, 1)),
         "ph_z": draw(lambda r: r.uniform(0, 2 * np.pi, 1)),
         "x0": draw(lambda r: r.uniform(-5, 5, 1)), "y0": draw(lambda r: r.uniform(-5, 5, 1)), "z0": draw(lambda r: r.uniform(0.25, 0.35, 1)),

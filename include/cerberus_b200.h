@@ -427,6 +427,8 @@ int cerb_replay_step(CerbReplay *r, const CerbImage *images, const CerbIMULegSam
 /* Published states of the newest frame after every processed image: rows of 20 doubles = header, P(3), R(9, row-major), V(3), rho(4). */
 int cerb_replay_path(CerbReplay *r, int32_t robot, int32_t *n_rows, double *out, int32_t max_rows);
 int cerb_replay_feature_ids(CerbReplay *r, int32_t robot, int32_t *n, int32_t *ids, int32_t max_ids);
+/* marginalization_flag (0 MARGIN_OLD, 1 MARGIN_SECOND_NEW) the keyframe test chose at every processed image */
+int cerb_replay_flags(CerbReplay *r, int32_t robot, int32_t *n, int32_t *flags, int32_t max_flags);
 /* seconds spent in: preintegrate, triangulate, solve, marginalize, outliers, shift (device + ABI) and in host bookkeeping */
 int cerb_replay_timing(CerbReplay *r, double *device6, double *host);
 

@@ -129,6 +129,20 @@ def test_native_replay_gpu():
     for w in range(n):
         assert [f.feature_id for f in py.est[w].f_manager.feature] == nat.feature_ids(w) or d_py.max() > 1e-6   # identical bookkeeping unless an outlier test flipped on a chain difference
     T = nat.timing()
+    # (1b) slow robots: the keyframe test (addFeatureCheckParallax) says "not a keyframe" on most frames -> MARGIN_SECOND_NEW, removeFront,
+    # the sample buffers of two intervals merged (slideWindowNew, estimator.cpp:1576-1616), the prior without para_Pose[WINDOW_SIZE - 1]
+    slow = synth.generate_sequence(2, 40, tracked=90, max_len=30, min_len=6, speed=0.01, yaw_rate=0.01, seed0=7100)
+    nat_s = estimator.NativeReplay(lib.Backend(cfg), pcfg, 2, max_features=F).run(slow)
+    py_s = estimator.ReplayDriver(estimator.DeviceOps(lib.Backend(cfg), cfg), cfg, pcfg, 2, max_features=F).run(slow)
+    ora_s = estimator.ReplayDriver(OracleOps(cfg, eig_mode=1), cfg, pcfg, 2, max_features=F).run(slow)
+    fl_py = np.array(py_s.flags).T; fl_or = np.array(ora_s.flags).T
+    n_second_new = int((fl_py == 1).sum())
+    assert n_second_new >= 10 and (fl_py == 0).sum() >= 2, fl_py                     # both marginalization modes occur
+    for w in range(2):
+        assert (nat_s.flag_history(w) == fl_py[w]).all() and (fl_or[w] == fl_py[w]).all()
+    Ps_n, _ = nat_s.poses(); Ps_p, _ = py_s.poses(); Ps_o, _ = ora_s.poses()
+    ds_py = np.abs(Ps_n - Ps_p).max(axis=(0, 2)); ds_or = np.abs(Ps_p - Ps_o).max(axis=(0, 2))
+    assert ds_py[:3].max() < 1e-6 and ds_py.max() < 2e-3 and ds_or[:3].max() < 1e-5 and ds_or.max() < 2e-3, (ds_py, ds_or)
     # (2) many robots
     nb, fb = 256, 30
     cfg2 = abi.default_config(); cfg2.max_batch = nb; cfg2.max_features = 2 * F; cfg2.max_obs = 2 * F * 11
@@ -149,6 +163,7 @@ def test_native_replay_gpu():
     lines = [f"native replay (C++ host mirror, cerb_replay_*): {n} robots x {n_frames - 10} frames: {t_nat:.2f} s wall = {n * (n_frames - 10) / t_nat:.0f} robot-frames/s "
              f"(device + ABI: solve {T['solve']:.2f} s, marginalize {T['marginalize']:.2f} s, preintegrate {T['preintegrate']:.2f} s, other {T['triangulate'] + T['outliers'] + T['shift']:.2f} s; host bookkeeping {T['host']:.3f} s)",
              f"  max |published position delta| vs the Python mirror over the same library {d_py.max():.2e} m (first 3 frames {d_py[:3].max():.1e}), vs the oracle arm {d_or.max():.2e} m",
+             f"slow robots (2 x 30 frames, {n_second_new} of 60 frames MARGIN_SECOND_NEW): native vs Python mirror {ds_py.max():.2e} m, Python mirror on the device vs oracle arm {ds_or.max():.2e} m, identical keyframe decisions on all three arms",
              f"native replay, {nb} robots x {fb - 10} frames: {t_many:.2f} s wall = {nb * (fb - 10) / t_many:.0f} robot-frames/s "
              f"(solve {Tm['solve']:.2f} s, marginalize {Tm['marginalize']:.2f} s, preintegrate {Tm['preintegrate']:.2f} s, other {Tm['triangulate'] + Tm['outliers'] + Tm['shift']:.2f} s; host bookkeeping {Tm['host']:.2f} s; Python glue around the ABI {t_many - sum(Tm.values()):.2f} s)"]
     os.makedirs("gpurun_out", exist_ok=True)
