@@ -161,12 +161,14 @@ static int create_impl(CerbHandle *h, const CerbSolverConfig *cfg, const cudaDev
     CUDA_TRY(cudaMemcpy(h->d_G, cfg->g, 3 * sizeof(double), cudaMemcpyHostToDevice));
 #if !defined(CERB_CUSIM)
     // The per-CTA workspace (W, the prior Hessian image: ~290 KB x 148 CTAs) is re-read every iteration while ~300 KB of inputs per window
-    // stream through once per linearisation: pin the workspace in L2 (persisting access-policy window on the compute stream) so that the
-    // streaming reads stop evicting it -- round 1 measured 7.8 x the algorithmic DRAM traffic from exactly these capacity misses.
+    // stream through once per linearisation; a persisting access-policy window on the compute stream keeps the workspace in L2.  Measured
+    // on the B200 (profiles/README.md): DRAM traffic of the solve 7.8 x -> 6.3 x the algorithmic bytes, but the step gets 1.7 % SLOWER
+    // (23.08 ms vs 22.70 ms per 1024 windows, alternating runs on one box): DRAM is at < 1 % utilisation, the carve-out only takes L2 away
+    // from the inputs.  Hence opt-in (CERB_L2_PERSIST=1), off by default.
     {
         const size_t ws_bytes = (size_t)h->grid * h->ws_stride * sizeof(double);
         const size_t want = std::min<size_t>(ws_bytes, (size_t)prop.persistingL2CacheMaxSize);
-        if (want > 0 && std::getenv("CERB_NO_L2_PERSIST") == nullptr) {
+        if (want > 0 && std::getenv("CERB_L2_PERSIST") != nullptr) {
             if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
                 cudaStreamAttrValue av;
                 std::memset(&av, 0, sizeof(av));
