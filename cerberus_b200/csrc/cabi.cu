@@ -397,6 +397,7 @@ static SolveParams make_params(CerbHandle *h, int w0, int n, int max_iters, doub
     P.state = h->d_state + W0 * ST_STRIDE; P.lam = h->d_lam + W0 * F; P.rep_i = h->d_repi + W0 * 4; P.rep_d = h->d_repd + W0 * 2; P.ws = h->d_ws; P.ws_stride = h->ws_stride;
     P.dbg = dbg; P.dbg_window = dbg_window;
     P.test_fail_factorizations = h->test_fail_factorizations; P.test_initial_mu = h->test_initial_mu;
+    P.no_bulk_copy = std::getenv("CERB_NO_TMA") != nullptr;
     return P;
 }
 

@@ -54,6 +54,7 @@ struct SolveParams {
     long ws_stride;
     double *dbg; int dbg_window;                                            // optional probe (cost, gradient, diag)
     double test_initial_mu;                                                 // parity tests only (env CERB_TEST_INITIAL_MU): DoglegStrategy::mu_ at the start (0: Ceres' 1e-8)
+    int no_bulk_copy;                                                       // diagnostics (env CERB_NO_TMA): prior image by per-element cp.async instead of TMA bulk copies
     int test_fail_factorizations;                                           // parity tests only (env CERB_TEST_FAIL_FACTORIZATIONS): report the first k
                                                                             // Gauss-Newton solves of every window as failed (LINEAR_SOLVER_FAILURE path)
 };
@@ -957,7 +958,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID
             sca[S_INVALID] = 0; sca[S_DLNORM] = 0;
         }
         __syncthreads();
-        const bool bulk_ok = (reinterpret_cast<uintptr_t>(pimg) & 15) == 0;          // TMA bulk copies need 16-byte aligned sources (max_features even)
+        const bool bulk_ok = (reinterpret_cast<uintptr_t>(pimg) & 15) == 0 && !P.no_bulk_copy;          // TMA bulk copies need 16-byte aligned sources (max_features even)
         bool need_linearize = true, hxx_prefetched = false, last_accepted = true;
         int iteration = 0, gn_attempts = 0;
 
