@@ -895,12 +895,12 @@ int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindow
         CUDA_TRY(cudaGetLastError());
     }
     std::vector<int> hdims((size_t)n * 4), hblocks((size_t)n * 64), hsw((size_t)n * 2);
-    std::vector<double> hJ((size_t)n * PRIOR_LD * PRIOR_LD), hr((size_t)n * PRIOR_LD);
+    double *hJ = h->h_pJ, *hr = h->h_pr;       // the pinned staging of the prior upload is idle here: D2H at PCIe rate instead of through pageable memory
     CUDA_TRY(cudaMemcpyAsync(hdims.data(), ddims, hdims.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(hblocks.data(), dblocks, hblocks.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(hsw.data(), dsw, hsw.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(hJ.data(), dJ, hJ.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(hr.data(), dr, hr.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hJ, dJ, (size_t)n * PRIOR_LD * PRIOR_LD * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hr, dr, (size_t)n * PRIOR_LD * sizeof(double), cudaMemcpyDeviceToHost, s));
     // a prior that is carried over unchanged comes back from the device copy of the old one
     std::vector<int> hmeta((size_t)n * PRIOR_META_STRIDE); std::vector<double> hx0((size_t)n * 16 * 9);
     CUDA_TRY(cudaMemcpyAsync(hmeta.data(), h->d_pmeta, hmeta.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -938,8 +938,8 @@ int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindow
             const double *x = st + prior_block_state_offset(q[0], q[3]);          // keep_block_data: the state the factors were linearised at
             for (int k = 0; k < 9; k++) pr.block_x0[b][k] = k < size ? x[k] : 0.0;
         }
-        std::memcpy(Jout, hJ.data() + (size_t)w * PRIOR_LD * PRIOR_LD, (size_t)nn * nn * 8);
-        std::memcpy(rout, hr.data() + (size_t)w * PRIOR_LD, (size_t)nn * 8);
+        std::memcpy(Jout, hJ + (size_t)w * PRIOR_LD * PRIOR_LD, (size_t)nn * nn * 8);
+        std::memcpy(rout, hr + (size_t)w * PRIOR_LD, (size_t)nn * 8);
     }
     return CERB_OK;
 }
