@@ -230,3 +230,66 @@ def test_marginalize_at_resident_solved_states(gpu, oracle):
         perm = [c + t for (k, i, c) in keys for t in range(loc[k])]
         assert A0.shape == (n, n)
         assert np.abs(A[np.ix_(perm, perm)] - A0).max() < 1e-5 * np.abs(A0).max() and np.abs(g[perm] - b0).max() < 1e-4 * max(1.0, np.abs(b0).max())
+
+
+def _shuffle_features(batch, rng):
+    """Same windows, tracks handed over in a random order (the library sorts them by anchor frame on the device and returns everything in the
+    caller's order).  Returns the permutation per window."""
+    perms = []
+    for w in range(batch.n):
+        nf = batch.descs[w].n_features
+        p = rng.permutation(nf)
+        batch.features[w][:nf] = batch.features[w][:nf][p].copy()          # obs_offset travels with the track: the observations stay where they are
+        batch.para_Feature[w][:nf] = batch.para_Feature[w][:nf][p].copy()
+        perms.append(p)
+    return perms
+
+
+def test_full_size_feature_order_invariance(gpu):
+    """Size-independent property at BASELINE.json configs[1] scale (1024 x 150): the result does not depend on the order in which the caller lists the
+    tracks (device-side anchor sort, chunking, un-permutation of inverse depths / outlier errors), beyond the rounding of a different summation order."""
+    base = synth.generate_batch(16, 150, gpu, realistic=True, prior_features=16, window0=2600)
+    a = synth.tile_batch(base, 1024); b = synth.tile_batch(base, 1024)
+    perms = _shuffle_features(b, np.random.default_rng(7))
+    rep_a = gpu.solve_batch(a); err_a, _ = gpu.outlier_errors(1024)
+    rep_b = gpu.solve_batch(b); err_b, _ = gpu.outlier_errors(1024)
+    assert (rep_a["iterations"] == rep_b["iterations"]).all() and (rep_a["status"] == 0).all()
+    assert np.abs(rep_a["final_cost"] - rep_b["final_cost"]).max() < 1e-7 * rep_a["final_cost"].max()
+    d = state_diffs(a.state_array(), b.state_array())
+    assert d["para_Pose"] < 1e-7 and d["para_SpeedBias"] < 1e-6 and d["para_Ex_Pose"] < 1e-7, d
+    for w in range(0, 1024, 37):
+        nf = a.descs[w].n_features; p = perms[w]
+        assert np.abs(b.para_Feature[w][:nf] - a.para_Feature[w][:nf][p]).max() < 1e-7
+        assert np.abs(err_b[w, :nf] - err_a[w, :nf][p]).max() < 1e-9
+
+
+def test_gauge_covariance_of_the_solve(gpu):
+    """Physics property of the whole path: without a prior the cost is invariant under a rotation about gravity + translation of the world frame, so
+    solving the transformed window gives the transformed solution (the solver itself has no gauge fix: estimator.cpp:1084 pins nothing with USE_IMU)."""
+    n = 8
+    a = synth.generate_batch(n, 80, gpu, with_prior=False, window0=2700)
+    b = synth.generate_batch(n, 80, gpu, with_prior=False, window0=2700)
+    yaw, t = 0.83, np.array([3.0, -7.0, 0.4])
+    Rz = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1.0]])
+    qz = np.array([0, 0, np.sin(yaw / 2), np.cos(yaw / 2)])                        # (x, y, z, w)
+    def qmul(p, q):      # Hamilton product, (x, y, z, w)
+        px, py, pz, pw = p; qx, qy, qz_, qw = q
+        return np.array([pw * qx + px * qw + py * qz_ - pz * qy, pw * qy - px * qz_ + py * qw + pz * qx, pw * qz_ + px * qy - py * qx + pz * qw, pw * qw - px * qx - py * qy - pz * qz_])
+    def transform(st):
+        for w in range(n):
+            for i in range(11):
+                st["para_Pose"][w, i, :3] = Rz @ st["para_Pose"][w, i, :3] + t
+                st["para_Pose"][w, i, 3:7] = qmul(qz, st["para_Pose"][w, i, 3:7])
+                st["para_SpeedBias"][w, i, :3] = Rz @ st["para_SpeedBias"][w, i, :3]
+    transform(b.state_array())
+    rep_a = gpu.solve_batch(a); rep_b = gpu.solve_batch(b)
+    assert np.abs(rep_a["initial_cost"] - rep_b["initial_cost"]).max() < 1e-9 * rep_a["initial_cost"].max()
+    assert (rep_a["iterations"] == rep_b["iterations"]).all()
+    assert np.abs(rep_a["final_cost"] - rep_b["final_cost"]).max() < 1e-6 * rep_a["final_cost"].max()
+    sa = a.state_array().copy(); transform(sa); sb = b.state_array()
+    # the gauge itself is free (4 null directions): compare what is observable -- relative poses to frame 0, velocities, biases, depths
+    for w in range(n):
+        for i in range(1, 11):
+            assert np.abs((sa["para_Pose"][w, i, :3] - sa["para_Pose"][w, 0, :3]) - (sb["para_Pose"][w, i, :3] - sb["para_Pose"][w, 0, :3])).max() < 2e-4
+    assert np.abs(sa["para_SpeedBias"][:, :, 3:] - sb["para_SpeedBias"][:, :, 3:]).max() < 1e-4 and np.abs(sa["para_LegBias"] - sb["para_LegBias"]).max() < 1e-6
+    assert np.abs(a.para_Feature - b.para_Feature).max() < 1e-4
