@@ -804,20 +804,28 @@ static int feature_pass(CerbHandle *h, int which, double param, double *out, int
 }
 int cerb_batch_outlier_errors(CerbHandle *h, double focal_length, double *ave_err, int32_t *remove) { return feature_pass(h, 0, focal_length, ave_err, remove); }
 int cerb_batch_triangulate(CerbHandle *h, double init_depth, double *depth) { return feature_pass(h, 1, init_depth, depth, nullptr); }
+// test hook: CERB_TEST_MARG_SMEM=<bytes> shrinks the shared-memory budget of the eigen-solver's memory plan (split / global layouts on small matrices)
+static size_t marg_smem_limit() {
+    const char *e = std::getenv("CERB_TEST_MARG_SMEM");
+    if (!e) return MARG_SMEM_MAX;
+    const long v = std::atol(e);
+    return (v >= 4096 && (size_t)v <= MARG_SMEM_MAX) ? (size_t)v : MARG_SMEM_MAX;
+}
 int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t n, const double *A, const double *b, double eps,
                            double *linearized_jacobians, double *linearized_residuals, int32_t *sweeps) {
     if (!h || !A || !b || !linearized_jacobians || !linearized_residuals) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
     CERB_DEVICE(h);
     if (n_windows < 1 || m < 1 || n < 1 || m > 4096 || n > CERB_MAX_PRIOR_DIM) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_marginalize_schur: bad sizes");
     const size_t pos = (size_t)m + n, N = n_windows;
-    int grid = std::min<int>(n_windows, (marg_smem_bytes(m, n) > 110 * 1024 ? 1 : 2) * h->sm_count);
-    grid = (int)std::max<size_t>(1, std::min<size_t>(grid, ((size_t)4 << 30) / (marg_ws_doubles(m, n) * sizeof(double))));      // <= 4 GB of per-CTA workspace
-    CUDA_TRY(cudaFuncSetAttribute(marg_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem_bytes(m, n)));
+    const size_t lim = marg_smem_limit();
+    int grid = std::min<int>(n_windows, marg_ctas_per_sm(m, n, lim) * h->sm_count);
+    grid = (int)std::max<size_t>(1, std::min<size_t>(grid, ((size_t)4 << 30) / (marg_ws_doubles(m, n, lim) * sizeof(double))));      // <= 4 GB of per-CTA workspace
+    CUDA_TRY(cudaFuncSetAttribute(marg_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem_bytes(m, n, lim)));
     cudaStream_t s = h->stream; DevBuf B(h);
-    double *dA = B.up(A, N * pos * pos, s), *db = B.up(b, N * pos, s), *dws = B.up(nullptr, (size_t)grid * marg_ws_doubles(m, n), s);
+    double *dA = B.up(A, N * pos * pos, s), *db = B.up(b, N * pos, s), *dws = B.up(nullptr, (size_t)grid * marg_ws_doubles(m, n, lim), s);
     double *dJ = B.up(nullptr, N * n * n, s), *dr = B.up(nullptr, N * n, s), *dsw = B.up(nullptr, N, s);     // dsw: 2 ints per window
     if (!dA || !db || !dws || !dJ || !dr || !dsw) return fail(CERB_ERR_CUDA, "device allocation failed");
-    CERB_LAUNCH(marg_schur_kernel, grid, MARG_THREADS, marg_smem_bytes(m, n), s, (int)n_windows, (int)m, (int)n, (const int *)nullptr, (const double *)dA, 0L, (const double *)db, 0L, eps, dws, dJ, 0L, dr, 0L, (int *)dsw);
+    CERB_LAUNCH(marg_schur_kernel, grid, marg_threads(m, n, lim), marg_smem_bytes(m, n, lim), s, (int)n_windows, (int)m, (int)n, (const int *)nullptr, (const double *)dA, 0L, (const double *)db, 0L, eps, dws, dJ, 0L, dr, 0L, (int *)dsw, (int)lim);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(linearized_jacobians, dJ, N * n * n * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(linearized_residuals, dr, N * n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -844,9 +852,10 @@ int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindow
         if (!priors[w].linearized_jacobians || !priors[w].linearized_residuals) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_batch_marginalize: priors[w] needs storage for linearized_jacobians / linearized_residuals");
     }
     cudaStream_t s = h->stream; DevBuf B(h);
-    int mmax = 19, nmax = CERB_MAX_PRIOR_DIM;
+    int mmax = 19;
+    const int nmax = MARG_N_STRUCT;            // what a window can keep (the kernel skips a window that claims more); the prior arrays keep the stride CERB_MAX_PRIOR_DIM
     for (int w = 0; w < n; w++) if (flags[w] == 0) mmax = std::max(mmax, 19 + h->n0[w]);
-    const int posmax = mmax + nmax;
+    const int posmax = mmax + CERB_MAX_PRIOR_DIM;
     // states to linearise at: the caller's (after double2vector + vector2double), or the resident ones
     std::vector<double> hst((size_t)n * ST_STRIDE, 0.0);
     const double *d_st, *d_lm;
@@ -872,10 +881,11 @@ int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindow
     const size_t a_bytes = (size_t)posmax * posmax * 8, budget = (size_t)3 << 30;
     const int per = (int)std::max<size_t>(1, std::min<size_t>(n, budget / a_bytes));
     double *dA = B.up(nullptr, (size_t)per * posmax * posmax, s), *db = B.up(nullptr, (size_t)per * posmax, s);
-    int sgrid = std::min(per, (marg_smem_bytes(mmax, nmax) > 110 * 1024 ? 1 : 2) * h->sm_count);
-    CUDA_TRY(cudaFuncSetAttribute(marg_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem_bytes(mmax, nmax)));
-    sgrid = (int)std::max<size_t>(1, std::min<size_t>(sgrid, ((size_t)2 << 30) / (marg_ws_doubles(mmax, nmax) * sizeof(double))));
-    double *dws = B.up(nullptr, (size_t)sgrid * marg_ws_doubles(mmax, nmax), s);
+    const size_t lim = marg_smem_limit();
+    int sgrid = std::min(per, marg_ctas_per_sm(mmax, nmax, lim) * h->sm_count);
+    CUDA_TRY(cudaFuncSetAttribute(marg_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)marg_smem_bytes(mmax, nmax, lim)));
+    sgrid = (int)std::max<size_t>(1, std::min<size_t>(sgrid, ((size_t)2 << 30) / (marg_ws_doubles(mmax, nmax, lim) * sizeof(double))));
+    double *dws = B.up(nullptr, (size_t)sgrid * marg_ws_doubles(mmax, nmax, lim), s);
     if (!dflags || !ddims || !dblocks || !dsw || !dJ || !dr || !dA || !db || !dws) return fail(CERB_ERR_CUDA, "device allocation failed");
     CUDA_TRY(cudaMemsetAsync(dsw, 0, (size_t)n * 2 * sizeof(int), s));
     CUDA_TRY(cudaFuncSetAttribute(marg_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -890,8 +900,8 @@ int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindow
         M.flags = dflags + w0; M.state = d_st + (size_t)w0 * ST_STRIDE; M.lam = d_lm + (size_t)w0 * F; M.A = dA; M.b = db; M.posmax = posmax;
         M.dims = ddims + (size_t)w0 * 4; M.blocks = dblocks + (size_t)w0 * 64;
         CERB_LAUNCH(marg_assemble_kernel, std::min(cn, h->grid), SOLVE_THREADS, h->smem_bytes, s, P, M);
-        CERB_LAUNCH(marg_schur_kernel, std::min(cn, sgrid), MARG_THREADS, marg_smem_bytes(mmax, nmax), s, cn, mmax, nmax, (const int *)(ddims + (size_t)w0 * 4), (const double *)dA, (long)posmax * posmax,
-                    (const double *)db, (long)posmax, 1e-8, dws, dJ + (size_t)w0 * PRIOR_LD * PRIOR_LD, (long)PRIOR_LD * PRIOR_LD, dr + (size_t)w0 * PRIOR_LD, (long)PRIOR_LD, dsw + (size_t)w0 * 2);
+        CERB_LAUNCH(marg_schur_kernel, std::min(cn, sgrid), marg_threads(mmax, nmax, lim), marg_smem_bytes(mmax, nmax, lim), s, cn, mmax, nmax, (const int *)(ddims + (size_t)w0 * 4), (const double *)dA, (long)posmax * posmax,
+                    (const double *)db, (long)posmax, 1e-8, dws, dJ + (size_t)w0 * PRIOR_LD * PRIOR_LD, (long)PRIOR_LD * PRIOR_LD, dr + (size_t)w0 * PRIOR_LD, (long)PRIOR_LD, dsw + (size_t)w0 * 2, (int)lim);
         CUDA_TRY(cudaGetLastError());
     }
     std::vector<int> hdims((size_t)n * 4), hblocks((size_t)n * 64), hsw((size_t)n * 2);

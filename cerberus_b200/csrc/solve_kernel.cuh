@@ -33,6 +33,9 @@ __device__ unsigned long long g_phase_cycles[48];
 #endif
 
 enum { CERB_WINDOW = 10, NX = 79, NYB = 13, NFR = 11, NY = 143, NR = 222, NRP = 224, HXX_SZ = 79 * 79, HXY_SZ = 79 * 143, X_TD = 78, SOLVE_THREADS = 256, FT = 64, TILE_LD = 33, NOBS_PLANES = 9 };
+#ifndef CERB_SOLVE_MIN_BLOCKS
+#define CERB_SOLVE_MIN_BLOCKS 1
+#endif
 // prior Hessian image in global memory: [Hxx (6241) | pad (1) | Hxy | Ad | Bo]: both parts start on 16-byte boundaries and have sizes that are
 // multiples of 16 bytes, so that each is ONE bulk copy (TMA 1-D, cp.async.bulk); shared memory has the same pad after Hxx (+ two mbarriers)
 enum { PIMG_HXY = HXX_SZ + 1, PIMG_REST = HXY_SZ + 1859 + 1690, PIMG_SZ = PIMG_HXY + PIMG_REST, SMEM_HXX_PAD = 3 };
@@ -885,7 +888,7 @@ CERB_D bool build_prior_image(const SolveParams &P, Smem &s, int w, double *pimg
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------
-CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, 1) vilo_solve_kernel(CERB_GRID_CONSTANT SolveParams P) {
+CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, CERB_SOLVE_MIN_BLOCKS) vilo_solve_kernel(CERB_GRID_CONSTANT SolveParams P) {
     CERB_DYN_SMEM(double, smem_base);
     Smem s; smem_carve(smem_base, s);
     const int tid = threadIdx.x;

@@ -64,6 +64,16 @@ def test_marg_schur_sim(m, n, rank):
     _check(sim_backend(cfg), OracleBackend(cfg), np.random.default_rng(m * 100 + n), 3, m, n, rank)
 
 
+@pytest.mark.parametrize("limit,m,n,rank", [(8192, 30, 20, None), (8192, 31, 20, 40), (4096, 30, 20, None), (4096, 33, 12, 40)])
+def test_marg_schur_memory_plans_sim(monkeypatch, limit, m, n, rank):
+    """the layouts a large dropped block falls into, forced on small matrices by shrinking the shared-memory budget of the plan (test hook):
+    8192 B -> M1 in shared memory, T split between shared memory and the global workspace (what m = 169 gets on the device);
+    4096 B -> M1 and T in the global workspace (m > ~235)"""
+    monkeypatch.setenv("CERB_TEST_MARG_SMEM", str(limit))
+    cfg = abi.default_config(); cfg.max_batch, cfg.max_features, cfg.max_obs = 2, 8, 8 * 11
+    _check(sim_backend(cfg), OracleBackend(cfg), np.random.default_rng(limit + m), 3, m, n, rank)
+
+
 def test_marg_schur_more_windows_than_ctas_sim():
     """the per-CTA workspace is reused window after window (grid = min(windows, 2 x SMs))"""
     cfg = abi.default_config(); cfg.max_batch, cfg.max_features, cfg.max_obs = 2, 8, 8 * 11
@@ -79,7 +89,7 @@ def test_marg_schur_bad_arguments_sim():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,m,n,rank", [(32, 169, 86, None), (8, 6, 80, None), (4, 40, 86, 60)])
+@pytest.mark.parametrize("B,m,n,rank", [(32, 169, 86, None), (8, 6, 80, None), (4, 40, 86, 60), (300, 35, 86, None), (3, 260, 86, None)])
 def test_marg_schur_gpu(B, m, n, rank):
     """MARGIN_OLD at the 150-feature size (m = 19 + 150), MARGIN_SECOND_NEW (m = 6) and a rank-deficient problem"""
     cfg = abi.default_config(); cfg.max_batch, cfg.max_features, cfg.max_obs = 2, 8, 8 * 11

@@ -17,11 +17,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--windows", type=int, default=256)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--only", type=int, default=-1, help="index of the single size to run (profiling)")
     a = ap.parse_args()
     cfg = abi.default_config(); cfg.max_batch, cfg.max_features, cfg.max_obs = 2, 8, 88
     be = lib.Backend(cfg)
     rng = np.random.default_rng(0)
-    for m, n in ((6, 80), (19 + 16, 86), (19 + 50, 86), (19 + 150, 86)):
+    sizes = ((6, 80), (19 + 16, 86), (19 + 50, 86), (19 + 150, 86))
+    for m, n in (sizes if a.only < 0 else sizes[a.only:a.only + 1]):
         pos = m + n
         J = rng.standard_normal((a.windows, 3 * pos, pos)); J[:, :, :m] *= np.exp(rng.uniform(-2, 2, (a.windows, 1, m)))
         A = np.swapaxes(J, 1, 2) @ J; b = (np.swapaxes(J, 1, 2) @ rng.standard_normal((a.windows, 3 * pos, 1)))[..., 0]
