@@ -77,7 +77,8 @@ if os.path.exists(aux):
         for (i, k), m in d.items():
             t = m.get('gpu__time_duration.sum', 0.0); b = m.get('dram__bytes_read.sum', 0.0) + m.get('dram__bytes_write.sum', 0.0)
             f.write(f"{i},{k},{t / 1e3:.1f},{b / 1e6:.2f},{(b / t if t else 0):.1f},{(b / t / 6566.1 if t else 0):.4f}\n")
-for src, dst in (("aux_wall_final.txt", f"aux_wall_{tag}.txt"), ("marg_bench_final.txt", f"marg_bench_{tag}.txt"), ("replay_gpu.txt", f"replay_gpu_{tag}.txt")):
+for src, dst in (("aux_wall_final.txt", f"aux_wall_{tag}.txt"), ("marg_bench_final.txt", f"marg_bench_{tag}.txt"), ("replay_gpu.txt", f"replay_gpu_{tag}.txt"),
+                 ("marg_phase_final.txt", f"marg_phase_{tag}.txt"), ("marg_kernel_times_final.txt", f"marg_kernel_times_{tag}.txt"), ("replay_native_gpu.txt", f"replay_native_gpu_{tag}.txt")):
     if os.path.exists(os.path.join(G, src)): shutil.copy(os.path.join(G, src), os.path.join(Pf, dst))
 err = os.path.join(G, "bench_final.err")
 if os.path.exists(err):
