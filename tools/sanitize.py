@@ -27,3 +27,15 @@ sw = be.batch_marginalize(flags, None, priors)
 print("marginalize", [priors[w].n for w in range(6)], sw.ravel())
 cost, g, d = be.debug_linearize(batch, 1)
 print("probe", cost)
+# the eigen-Schur kernel in its other memory plans: T split between shared memory and the L2 workspace (m = 169, one CTA of 512 threads per SM),
+# everything in the workspace (forced on a small matrix through the plan's test hook)
+rng = np.random.default_rng(3)
+for m, n, hook in ((169, 86, None), (30, 20, "4096")):
+    if hook: os.environ["CERB_TEST_MARG_SMEM"] = hook
+    pos = m + n
+    Jf = rng.standard_normal((2, 2 * pos, pos)); A = np.swapaxes(Jf, 1, 2) @ Jf; b = (np.swapaxes(Jf, 1, 2) @ rng.standard_normal((2, 2 * pos, 1)))[..., 0]
+    Jo, ro, sw2 = be.marginalize_schur(A, b, m, return_sweeps=True)
+    H = np.swapaxes(Jo, 1, 2) @ Jo
+    Ai = np.linalg.inv(A[:, :m, :m]); Hr = A[:, m:, m:] - A[:, m:, :m] @ Ai @ A[:, :m, m:]
+    print("marginalize_schur", m, n, hook, sw2.ravel(), float(np.abs(H - Hr).max() / np.abs(Hr).max()))
+    os.environ.pop("CERB_TEST_MARG_SMEM", None)
