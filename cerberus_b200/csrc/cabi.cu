@@ -815,7 +815,7 @@ int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t 
                            double *linearized_jacobians, double *linearized_residuals, int32_t *sweeps) {
     if (!h || !A || !b || !linearized_jacobians || !linearized_residuals) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
     CERB_DEVICE(h);
-    if (n_windows < 1 || m < 1 || n < 1 || m > 4096 || n > CERB_MAX_PRIOR_DIM) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_marginalize_schur: bad sizes");
+    if (n_windows < 1 || m < 1 || n < 1 || m > 19 + CERB_MAX_FEATURES || n > CERB_MAX_PRIOR_DIM) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_marginalize_schur: bad sizes");      // m: what a window can drop (also keeps the kernel's multiply-high divisions exact)
     const size_t pos = (size_t)m + n, N = n_windows;
     const size_t lim = marg_smem_limit();
     int grid = std::min<int>(n_windows, marg_ctas_per_sm(m, n, lim) * h->sm_count);

@@ -375,7 +375,8 @@ int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_
  * as ThreadsConstructA (:150-181) leaves them; out: linearized_jacobians [n_windows][n * n] column-major (CerbPrior layout) and
  * linearized_residuals [n_windows][n].  Amm is symmetrised, eigen-decomposed and pseudo-inverted with eigenvalues <= eps dropped
  * (eps = 1e-8 in the reference), the Schur complement is eigen-decomposed from its lower triangle, S / S_inv clamped the same way.
- * sweeps (optional, [n_windows][2]): Jacobi sweeps of the two eigen-decompositions, a convergence diagnostic. */
+ * sweeps (optional, [n_windows][2]): Jacobi sweeps of the two eigen-decompositions, a convergence diagnostic.
+ * 1 <= m <= 19 + CERB_MAX_FEATURES, 1 <= n <= CERB_MAX_PRIOR_DIM. */
 int cerb_marginalize_schur(CerbHandle *h, int32_t n_windows, int32_t m, int32_t n, const double *A, const double *b, double eps,
                            double *linearized_jacobians, double *linearized_residuals, int32_t *sweeps);
 
