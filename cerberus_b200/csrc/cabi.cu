@@ -954,6 +954,27 @@ int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindow
     return CERB_OK;
 }
 
+int cerb_batch_update_states(CerbHandle *h, int32_t n, const CerbWindowState *states) {
+    if (!h || !states) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
+    CERB_DEVICE(h);
+    if (h->n < 1 || n != h->n) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_batch_update_states: n must be the size of the resident batch");
+    const int F = h->F;
+    cudaStream_t s = h->stream; DevBuf B(h);
+    std::vector<double> hst((size_t)n * ST_STRIDE, 0.0), hl((size_t)n * F, 0.0);
+    for (int w = 0; w < n; w++) {
+        std::memcpy(hst.data() + (size_t)w * ST_STRIDE, &states[w], ST_SIZE * sizeof(double));
+        if (h->nfeat[w]) { if (!states[w].para_Feature) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_batch_update_states: null para_Feature"); std::memcpy(hl.data() + (size_t)w * F, states[w].para_Feature, (size_t)h->nfeat[w] * 8); }
+    }
+    double *ds = B.up(hst.data(), hst.size(), s), *dlc = B.up(hl.data(), hl.size(), s);
+    if (!ds || !dlc) return fail(CERB_ERR_CUDA, "device allocation failed");
+    CUDA_TRY(cudaMemcpyAsync(h->d_state0, ds, hst.size() * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CERB_LAUNCH(permute_lam_kernel, (int)(((size_t)n * F + 127) / 128), 128, 0, s, n, F, (const int *)h->d_nfeat, (const int *)h->d_perm, (const double *)dlc, h->d_lam0);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s));               // hst / hl are read by the asynchronous copies
+    h->solved = false;                                 // the per-feature passes and a resident solve start from these states
+    return CERB_OK;
+}
+
 int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_frame, double *depth, int32_t *keep) {
     if (!h || !new_start_frame || !depth || !keep) return fail(CERB_ERR_BAD_ARGUMENT, "null argument");
     CERB_DEVICE(h);

@@ -388,7 +388,7 @@ int cerb_replay_step(CerbReplay *rp, const CerbImage *images, const CerbIMULegSa
     // ---- outliersRejection + removeOutlier (:812-814) at the re-anchored states
     rp->t_host += now_s() - th; t0 = now_s();
     std::vector<double> err((size_t)n * rp->h->F, 0.0);
-    rc = cerb_batch_upload(rp->h, n, rp->descs.data(), rp->states.data()); if (rc) return rc;
+    rc = cerb_batch_update_states(rp->h, n, rp->states.data()); if (rc) return rc;       // same windows as the solve, moved by double2vector: only the states travel
     rc = cerb_batch_outlier_errors(rp->h, kFocal, err.data(), nullptr); if (rc) return rc;
     rp->t_device[4] += now_s() - t0; th = now_s();
     rc = parallel_robots(n, [&](int w) {

@@ -44,6 +44,7 @@ class Backend:
         L.cerb_solve_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.WindowDesc), C.POINTER(abi.WindowState), C.POINTER(abi.SolveReport)]
         L.cerb_solve_window.argtypes = [C.c_void_p, C.POINTER(abi.WindowDesc), C.POINTER(abi.WindowState), C.POINTER(abi.SolveReport)]
         L.cerb_batch_upload.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.WindowDesc), C.POINTER(abi.WindowState)]
+        L.cerb_batch_update_states.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.WindowState)]
         L.cerb_batch_solve_resident.argtypes = [C.c_void_p]
         L.cerb_batch_download.argtypes = [C.c_void_p, C.POINTER(abi.WindowState), C.POINTER(abi.SolveReport)]
         L.cerb_sync.argtypes = [C.c_void_p]
@@ -100,6 +101,10 @@ class Backend:
 
     def upload(self, batch):
         self._check(self.lib.cerb_batch_upload(self.h, batch.n, batch.descs, batch.states))
+
+    def update_states(self, batch):
+        """cerb_batch_update_states: new para_* of the resident windows (same tracks, same order), nothing else travels"""
+        self._check(self.lib.cerb_batch_update_states(self.h, batch.n, batch.states))
 
     def solve_resident(self):
         self._check(self.lib.cerb_batch_solve_resident(self.h))

@@ -370,6 +370,11 @@ int cerb_batch_triangulate(CerbHandle *h, double init_depth, double *depth);
  * becomes init_depth) and keep = 0 for the tracks the reference erases (anchored at frame 0 with fewer than 2 remaining observations). */
 int cerb_batch_shift_depth(CerbHandle *h, double init_depth, int32_t *new_start_frame, double *depth, int32_t *keep);
 
+/* Replace the states of the RESIDENT batch (n = its size; same windows, same tracks, same order -- only para_* change): what the estimator
+ * does between optimization() and outliersRejection() (double2vector() moves the window, estimator.cpp:1241 / :815) without shipping the tracks,
+ * preintegrations and priors again.  The per-feature passes and cerb_batch_solve_resident then start from these states. */
+int cerb_batch_update_states(CerbHandle *h, int32_t n, const CerbWindowState *states);
+
 /* The dense tail of MarginalizationInfo::marginalize() (marginalization_factor.cpp:281-305), batched: for every window the
  * (m + n) x (m + n) Hessian A = sum J^T J (row-major, the m dropped coordinates first -- the reference's idx order) and b = sum J^T r
  * as ThreadsConstructA (:150-181) leaves them; out: linearized_jacobians [n_windows][n * n] column-major (CerbPrior layout) and

@@ -33,6 +33,18 @@ def _check_backend(be, oracle, realistic):
         if phase == 0:
             be.solve_resident(); be.download(batch)           # batch.states now hold the solved states, like the device
     assert np.nanmax(err) * 460.0 < 3.0                           # solved synthetic windows have no outliers
+    # (1a) cerb_batch_update_states: the window moved (double2vector + vector2double), only the states travel; same as a full upload of the moved window
+    rng = np.random.default_rng(3)
+    st = batch.state_array()
+    st["para_Pose"][:, :, :3] += rng.normal(0, 0.01, st["para_Pose"][:, :, :3].shape)
+    for w in range(batch.n): batch.para_Feature[w, :nf[w]] *= 1.0 + rng.normal(0, 0.01, nf[w])
+    be.update_states(batch); err_u, rem_u = be.outlier_errors(batch.n)
+    be.upload(batch); err_f, rem_f = be.outlier_errors(batch.n)
+    ref = oracle.outlier_errors(batch)
+    for w in range(batch.n):
+        ok = np.isfinite(ref[w, :nf[w]])
+        assert (err_u[w, :nf[w]] == err_f[w, :nf[w]]).all() and (rem_u[w] == rem_f[w]).all()
+        assert np.abs(err_u[w, :nf[w]][ok] - ref[w, :nf[w]][ok]).max() < 1e-12 * max(1.0, np.abs(ref[w, :nf[w]][ok]).max())
     # (1b) depth bookkeeping of slideWindowOld at the solved states
     st_o, dep_o, keep_o = oracle.shift_depth(batch)
     st_g, dep_g, keep_g = be.shift_depth(batch.n)
