@@ -60,7 +60,7 @@ mrep = os.path.join(G, "marg_schur_final.ncu-rep")
 if os.path.exists(mrep):
     a = raw(mrep)
     with open(os.path.join(Pf, f"marg_schur_kernel_{tag}.txt"), "w") as f:
-        f.write(f"# ncu --set full summary, marg_schur_kernel, 1024 windows (m = 169, n = 86, MARGIN_OLD of the solved 150-feature windows), B200 ({tag})\n"
+        f.write(f"# ncu --set full summary, marg_schur_kernel, 296 windows of the 150-feature size (m = 169, n = 86; the cerb_marginalize_schur launch of tools/aux_kernels.py), B200 ({tag})\n"
                 f"# command: ncu --set full --clock-control none --import-source on -k regex:marg_schur -s 1 -c 1 python tools/aux_kernels.py 1024 150\n\n")
         for k in WANT:
             if k in a: f.write(f"{k:92s} {a[k][0]} {a[k][1]}\n")
