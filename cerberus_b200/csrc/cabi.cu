@@ -917,6 +917,7 @@ int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindow
     CUDA_TRY(cudaMemcpyAsync(hx0.data(), h->d_px0, hx0.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     std::vector<double> oldJ, oldr;
+    for (int w = 0; w < n; w++) if (hdims[4 * w + 2] == 1 && (hdims[4 * w] > mmax || hdims[4 * w + 1] > nmax)) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_batch_marginalize: a window exceeds the structural size of the kept / dropped blocks");
     for (int w = 0; w < n; w++) {
         CerbPrior &pr = priors[w];
         double *Jout = const_cast<double *>(pr.linearized_jacobians), *rout = const_cast<double *>(pr.linearized_residuals);
