@@ -1193,6 +1193,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, CERB_SOLVE_MIN_BLOCKS) vilo_so
                             CERB_BAR_SYNC(1, n2);
                             for (int k = t2; k < NX; k += n2) s.Hxx[k * NX + k] += mu * s.D[k] * s.D[k];
                         }
+                        PH_MARK_T(19, 32);
                         for (int f = t2; f < nF; f += n2) sinv[f] = rsqrt(hh[f] + mu * Dl[f] * Dl[f]);
                         double acc[8][2];
                         for (int k = 0; k < 8; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
@@ -1216,6 +1217,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, CERB_SOLVE_MIN_BLOCKS) vilo_so
                             }
                         };
                         fetch(0);
+                        PH_MARK_T(37, 32);
                         for (int f0 = 0; f0 < nF; f0 += 32) {
                             const int nf = (nF - f0) < 32 ? (nF - f0) : 32;
                             _Pragma("unroll")
@@ -1224,6 +1226,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, CERB_SOLVE_MIN_BLOCKS) vilo_so
                                 if (e < 80 * 32) tw[a * LDW + f] = (f < nf) ? buf[u] * sinv[f0 + f] : 0.0;
                             }
                             CERB_BAR_SYNC(1, n2);
+                            PH_MARK_T(38, 32);
                             if (f0 + 32 < nF) fetch(f0 + 32);
                             for (int ks = 0; ks < 8; ks++) {
                                 const int col = 4 * ks + (lane & 3);
@@ -1235,6 +1238,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, CERB_SOLVE_MIN_BLOCKS) vilo_so
                                 }
                             }
                             CERB_BAR_SYNC(1, n2);
+                            PH_MARK_T(39, 32);
                         }
                         for (int k = 0; k < 8; k++) {
                             if (tmi[k] < 0) continue;

@@ -14,6 +14,7 @@ NAMES = {0: "zero+geometry", 1: "vision_linearize (total)", 2: "inertial_lineari
          14: "gn norms + dogleg scalars + step", 15: "apply_plus + geometry", 16: "vision_cost", 17: "inertial_cost + prior", 18: "accept / copy",
          20: "  vis: chunk setup", 21: "  vis: eval + tile write", 22: "  vis: DMMA Gram + partial store", 23: "  vis: reduce + scatter", 24: "  vis: per-feature tail",
          28: "    dmma loop (warp 0 view)", 29: "    partial stores + W (warp 0)", 30: "  imu: warps 0-2 (factor rounds, tail)", 32: "    imu warp 0: zero + expand Ju", 33: "    imu warp 0: whiten", 34: "    imu warp 0: S prefetch + Gram", 35: "    imu warp 0: scatter", 36: "    imu warp 0: round barrier", 31: "  imu: warps 3-7 (prior)",
+         19: "  schur (warp 1): rhs + Cauchy v^T H v", 37: "  schur (warp 1): sinv + block table + first fetch", 38: "  schur (warp 1): tile scale/store + barrier (all tiles)", 39: "  schur (warp 1): DMMA loop + barrier (all tiles)",
          25: "  imu: linearize (10 threads)", 26: "  imu: whiten + Gram x10", 27: "  imu: prior"}
 cfg = abi.default_config(); cfg.max_batch = NW; cfg.max_features = 160; cfg.max_obs = 160 * 11
 gb = lib.Backend(cfg, lib_path=os.path.join(ROOT, "tools", "libcerberus_b200_prof.so"))
