@@ -45,6 +45,14 @@ def _check_backend(be, oracle, realistic):
         ok = np.isfinite(ref[w, :nf[w]])
         assert (err_u[w, :nf[w]] == err_f[w, :nf[w]]).all() and (rem_u[w] == rem_f[w]).all()
         assert np.abs(err_u[w, :nf[w]][ok] - ref[w, :nf[w]][ok]).max() < 1e-12 * max(1.0, np.abs(ref[w, :nf[w]][ok]).max())
+    # (1a') a resident solve after the update starts from the shipped states: same result as solving the moved window from host buffers
+    import copy
+    moved = synth.tile_batch(batch, batch.n)                        # deep copy (descriptors + states)
+    be.update_states(batch); be.solve_resident(); rep_r = be.download(batch)
+    rep_h = be.solve_batch(moved)
+    assert (rep_r["iterations"] == rep_h["iterations"]).all() and np.abs(rep_r["final_cost"] - rep_h["final_cost"]).max() < 1e-9 * np.abs(rep_h["final_cost"]).max()
+    assert np.abs(batch.state_array()["para_Pose"] - moved.state_array()["para_Pose"]).max() < 1e-10
+    be.upload(batch)                                                 # the solved states again, for the passes below
     # (1b) depth bookkeeping of slideWindowOld at the solved states
     st_o, dep_o, keep_o = oracle.shift_depth(batch)
     st_g, dep_g, keep_g = be.shift_depth(batch.n)
