@@ -36,8 +36,11 @@ template <typename T> static cudaError_t hmalloc(T **p, size_t n) { return cudaM
 struct CerbHandle {
     CerbSolverConfig cfg;
     int sm_count = 0, grid = 0;
+    enum { MAX_CHUNKS = 32, LANES = 4 };
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t lane[LANES] = {};       // compute lanes of the chunked pipeline: lane[0] == stream; each has its own slice of d_ws
+    cudaEvent_t ev_lane[LANES] = {};
+    cudaEvent_t ev_copy[MAX_CHUNKS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_pending = false;
     double last_ms = 0; int last_launches = 0, last_dma_ops = 0; size_t last_staged_bytes = 0;
@@ -139,7 +142,10 @@ static int create_impl(CerbHandle *h, const CerbSolverConfig *cfg, const cudaDev
     CUDA_TRY(cudaFuncSetAttribute(prior_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PRIOR_TROWS * PRIOR_TLD * sizeof(double))));
     CUDA_TRY(cudaStreamCreate(&h->stream));
     CUDA_TRY(cudaStreamCreate(&h->copy_stream));
-    for (int k = 0; k < 8; k++) CUDA_TRY(cudaEventCreate(&h->ev_copy[k]));
+    h->lane[0] = h->stream;
+    for (int k = 1; k < CerbHandle::LANES; k++) CUDA_TRY(cudaStreamCreate(&h->lane[k]));
+    for (int k = 0; k < CerbHandle::LANES; k++) CUDA_TRY(cudaEventCreate(&h->ev_lane[k]));
+    for (int k = 0; k < CerbHandle::MAX_CHUNKS; k++) CUDA_TRY(cudaEventCreate(&h->ev_copy[k]));
     CUDA_TRY(cudaEventCreate(&h->ev0)); CUDA_TRY(cudaEventCreate(&h->ev1));
     const size_t B = h->B, F = h->F, O = h->O;
     h->ws_stride = ws_size(h->F);
@@ -151,7 +157,7 @@ static int create_impl(CerbHandle *h, const CerbSolverConfig *cfg, const cudaDev
     CUDA_TRY(dmalloc(&h->d_obs, B * NOBS_PLANES * O)); CUDA_TRY(dmalloc(&h->d_pre, B * 10 * PRE_STRIDE)); CUDA_TRY(dmalloc(&h->d_sinfo, B * 10 * 961));
     CUDA_TRY(dmalloc(&h->d_pJ, B * PRIOR_LD * PRIOR_LD)); CUDA_TRY(dmalloc(&h->d_pr, B * PRIOR_LD)); CUDA_TRY(dmalloc(&h->d_px0, B * 16 * 9)); CUDA_TRY(dmalloc(&h->d_pHp, B * PRIOR_LD * PRIOR_LD));
     CUDA_TRY(dmalloc(&h->d_state, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_state0, B * ST_STRIDE)); CUDA_TRY(dmalloc(&h->d_lam, B * F)); CUDA_TRY(dmalloc(&h->d_lam0, B * F));
-    CUDA_TRY(dmalloc(&h->d_repd, B * 2)); CUDA_TRY(dmalloc(&h->d_ws, (size_t)h->grid * h->ws_stride)); CUDA_TRY(dmalloc(&h->d_dbg, 2 * (NR + F) + 8)); CUDA_TRY(dmalloc(&h->d_G, 4));
+    CUDA_TRY(dmalloc(&h->d_repd, B * 2)); CUDA_TRY(dmalloc(&h->d_ws, (size_t)CerbHandle::LANES * h->grid * h->ws_stride)); CUDA_TRY(dmalloc(&h->d_dbg, 2 * (NR + F) + 8)); CUDA_TRY(dmalloc(&h->d_G, 4));
     CUDA_TRY(dmalloc(&h->d_probe_repi, 4)); CUDA_TRY(dmalloc(&h->d_probe_repd, 2));
     CUDA_TRY(hmalloc(&h->h_rdesc, B)); CUDA_TRY(hmalloc(&h->h_rfeat, B * F)); CUDA_TRY(hmalloc(&h->h_robs, B * O)); CUDA_TRY(hmalloc(&h->h_rstate, B));
     CUDA_TRY(hmalloc(&h->h_rpre, B * 10 * RAW_PRE_STRIDE)); CUDA_TRY(hmalloc(&h->h_rlam, B * F));
@@ -201,7 +207,9 @@ void cerb_destroy(CerbHandle *h) {
     for (void *p : hst) if (p) cudaFreeHost(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    for (int k = 0; k < 8; k++) if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]);
+    for (int k = 0; k < CerbHandle::MAX_CHUNKS; k++) if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]);
+    for (int k = 0; k < CerbHandle::LANES; k++) if (h->ev_lane[k]) cudaEventDestroy(h->ev_lane[k]);
+    for (int k = 1; k < CerbHandle::LANES; k++) if (h->lane[k]) cudaStreamDestroy(h->lane[k]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -402,8 +410,8 @@ static SolveParams make_params(CerbHandle *h, int w0, int n, int max_iters, doub
 }
 
 // restore the initial states of windows [w0, w0 + n), prepare (sqrt_info, prior Gram matrix) and solve; asynchronous on the stream
-static int enqueue_solve(CerbHandle *h, int w0, int n, int max_iters, double *dbg, int dbg_window, bool restore = true, bool probe = false) {
-    cudaStream_t s = h->stream;
+static int enqueue_solve(CerbHandle *h, int w0, int n, int max_iters, double *dbg, int dbg_window, bool restore = true, bool probe = false, int lane = 0) {
+    cudaStream_t s = h->lane[lane];
     const size_t W0 = (size_t)w0;
     if (restore) {
         CUDA_TRY(cudaMemcpyAsync(h->d_state + W0 * ST_STRIDE, h->d_state0 + W0 * ST_STRIDE, (size_t)n * ST_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -413,6 +421,7 @@ static int enqueue_solve(CerbHandle *h, int w0, int n, int max_iters, double *db
     CERB_LAUNCH(imu_leg_prepare_kernel, (nfac + 1) / 2, 64, 0, s, nfac, (const double *)(h->d_pre + W0 * 10 * PRE_STRIDE), h->d_sinfo + W0 * 10 * 961);
     CERB_LAUNCH(prior_prepare_kernel, n, 256, (size_t)PRIOR_TROWS * PRIOR_TLD * sizeof(double), s, (const double *)(h->d_pJ + W0 * PRIOR_LD * PRIOR_LD), (const int *)(h->d_pmeta + W0 * PRIOR_META_STRIDE), h->d_pHp + W0 * PRIOR_LD * PRIOR_LD);
     SolveParams P = make_params(h, w0, n, max_iters, dbg, dbg_window);
+    P.ws = h->d_ws + (size_t)lane * h->grid * h->ws_stride;                      // kernels of different lanes run concurrently: one workspace slice each
     if (probe) { P.rep_i = h->d_probe_repi; P.rep_d = h->d_probe_repd; }       // a probe leaves the reports of the batch alone
     if (max_iters > 0) h->solved = true;
     CERB_LAUNCH(vilo_solve_kernel, std::min(n, h->grid), SOLVE_THREADS, h->smem_bytes, s, P);
@@ -528,17 +537,32 @@ int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, Cerb
     CERB_DEVICE(h);
     if (n < 1 || n > h->B) return fail(CERB_ERR_BAD_ARGUMENT, "batch size over capacity");
     CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+    for (int l = 1; l < CerbHandle::LANES; l++) CUDA_TRY(cudaStreamSynchronize(h->lane[l]));       // only busy after a call that failed half way
     int rc = collect_time(h); if (rc) return rc;
-    // Pipeline in chunks that are whole waves of the persistent grid (first chunk one wave so the GPU starts early): the copy stream
-    // moves chunk c + 1 (and the host stages it, if its buffers are not registered) while the compute stream packs and solves chunk c.
-    const int wave = h->grid;
-    int bounds[9], nch = 0; bounds[0] = 0;
-    if (n <= 2 * wave) { bounds[1] = n; nch = 1; }
+    // Pipeline in chunks: the copy stream moves chunk c + 1 (and the host stages it, if its buffers are not registered) while the compute lanes pack
+    // and solve the chunks that have arrived.  Three lanes (streams) take the chunks round-robin and their kernels run concurrently, so a chunk's CTAs
+    // fill the SMs as earlier windows retire -- no wave alignment, whatever the batch size is relative to the SM count.  Chunk sizes ramp up (64, 64,
+    // 128, 256, 256, ...): the GPU starts after the first 64 windows (19 MB at F = 150) are across, and every later chunk arrives before the SMs run dry
+    // while the number of launches / DMA operations stays small (measured: sixteen equal chunks of 64 lose more to their prepare kernels than they gain).
+    const int MAXC = CerbHandle::MAX_CHUNKS;
+    int NL = 3, first = 64;
+    if (const char *e = std::getenv("CERB_PIPE_LANES")) NL = std::min((int)CerbHandle::LANES, std::max(1, std::atoi(e)));       // tuning knobs of the measurement in DESIGN.md 2.4
+    if (const char *e = std::getenv("CERB_PIPE_FIRST")) first = std::max(16, std::atoi(e));
+    int bounds[CerbHandle::MAX_CHUNKS + 1], nch = 0; bounds[0] = 0;
+    if (const char *e = std::getenv("CERB_TEST_CHUNK")) {              // test hook: the multi-chunk / multi-lane path on a handful of windows
+        const int per = std::max(std::max(1, std::atoi(e)), (n + MAXC - 1) / MAXC);
+        for (int pos = 0; pos < n; ) { pos = std::min(n, pos + per); bounds[++nch] = pos; }
+    } else if (n <= 96) { bounds[1] = n; nch = 1; }
     else {
-        int pos = wave; bounds[++nch] = pos;
-        const int rest = n - pos, per = ((rest + 2) / 3 + wave - 1) / wave * wave;
-        while (pos < n && nch < 7) { pos = std::min(n, pos + per); bounds[++nch] = pos; }
-        bounds[nch] = n;
+        int cap = 256;
+        if ((n + cap - 1) / cap > MAXC - 8) cap = (((n + MAXC - 9) / (MAXC - 8)) + 63) / 64 * 64;
+        int pos = 0, sz = first, k = 0;
+        while (pos < n) {
+            int take = std::min(sz, n - pos);
+            if (n - pos - take < 32 || nch == MAXC - 1) take = n - pos;  // no crumbs; never more than MAXC chunks
+            pos += take; bounds[++nch] = pos;
+            if (++k >= 2) sz = std::min(cap, 2 * sz);
+        }
     }
     h->n = n; h->perm_valid = false;
     h->last_dma_ops = 0; h->last_staged_bytes = 0;
@@ -546,14 +570,16 @@ int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, Cerb
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now(); double t_stage = 0.0;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    for (int l = 1; l < NL; l++) CUDA_TRY(cudaStreamWaitEvent(h->lane[l], h->ev0, 0));
     for (int c = 0; c < nch; c++) {
-        const int w0 = bounds[c], cn = bounds[c + 1] - bounds[c];
+        const int w0 = bounds[c], cn = bounds[c + 1] - bounds[c], l = c % NL;
         rc = upload_raw(h, w0, cn, descs, states, h->copy_stream, &t_stage); if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_copy[c], h->copy_stream));
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy[c], 0));
-        rc = enqueue_pack(h, w0, cn, h->stream); if (rc) return rc;
-        rc = enqueue_solve(h, w0, cn, h->cfg.max_num_iterations, nullptr, -1); if (rc) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(h->lane[l], h->ev_copy[c], 0));
+        rc = enqueue_pack(h, w0, cn, h->lane[l]); if (rc) return rc;
+        rc = enqueue_solve(h, w0, cn, h->cfg.max_num_iterations, nullptr, -1, true, false, l); if (rc) return rc;
     }
+    for (int l = 1; l < NL; l++) { CUDA_TRY(cudaEventRecord(h->ev_lane[l], h->lane[l])); CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_lane[l], 0)); }
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->ev_pending = true; h->last_launches = 4 * nch + 1;      // + the unpack kernel of the download
     const double t_issued = now();
     rc = download(h, states, reports);

@@ -281,9 +281,11 @@ def test_chained_windows_match_oracle():
     _chained_windows_case(lambda cfg: sim_backend(cfg))
 
 
-def test_host_buffer_pipeline_chunks():
-    """cerb_solve_batch packs / copies / solves in chunks of whole waves (here: 9 windows on a 4-CTA grid -> chunks of 4, 4, 1, three
-    launches each); windows with identical inputs must come back bit-identical whichever chunk carried them.  (Host-buffer path == resident path at 1024 windows is asserted on the GPU tier.)"""
+def test_host_buffer_pipeline_chunks(monkeypatch):
+    """cerb_solve_batch packs / copies / solves in chunks on three compute lanes (here, through the test hook: 9 windows in chunks of 4, 4, 1, one lane
+    each, four launches per chunk); windows with identical inputs must come back bit-identical whichever chunk / lane / workspace slice carried them.
+    (Host-buffer path == resident path at 1024 windows is asserted on the GPU tier.)"""
+    monkeypatch.setenv("CERB_TEST_CHUNK", "4")
     cfg = small_cfg(max_batch=16, max_features=8, iters=1)
     s = sim_backend(cfg)
     base = synth.generate_batch(3, 4, ob, with_prior=False, window0=140)
