@@ -4,11 +4,11 @@
 //     A   = Arr - Arm Amm_inv Amr;  b = brr - Arm Amm_inv bmm
 //     SelfAdjointEigenSolver(A) (lower triangle);  S = lambda > eps ? lambda : 0;  S_inv = lambda > eps ? 1 / lambda : 0
 //     linearized_jacobians = diag(sqrt S) V^T;  linearized_residuals = diag(sqrt S_inv) V^T b
-// The eigen-solver is a parallel two-sided Jacobi iteration (round-robin pair ordering: kp / 2 disjoint rotations per round,
-// column phase, row phase, re-symmetrisation), in fp64, on matrices that live in SHARED memory (m = 19 + tracks anchored at frame 0 -> 169 x 169
-// for the 150-feature configuration = 223 KB, 86 x 86 for the kept block; larger m falls back to the L2-resident workspace).  Rotation formulas as in the CPU restatement
-// (oracle/ref_math.h sym_eig_jacobi), different pair order; the rows of linearized_jacobians come out in the order the
-// eigenvalues sit on the diagonal (J^T J and J^T r, the only things MarginalizationFactor uses, do not depend on it).
+// The eigen-solver is a parallel two-sided Jacobi iteration (round-robin pair ordering: kp / 2 disjoint rotations per round, applied to both
+// sides in one pass over 2 x 2 blocks), in fp64, on PACKED symmetric matrices that live in SHARED memory (m = 19 + tracks anchored at frame 0 ->
+// 169 x 169 for the 150-feature configuration = 112 KB, 86 x 86 for the kept block; m > ~235 falls back to the L2-resident workspace).  Rotation
+// formulas as in the CPU restatement (oracle/ref_math.h sym_eig_jacobi), different pair order; the rows of linearized_jacobians come out in the
+// order the eigenvalues sit on the diagonal (J^T J and J^T r, the only things MarginalizationFactor uses, do not depend on it).
 #pragma once
 #include "compat.h"
 
