@@ -854,6 +854,56 @@ template <int W> CERB_D void ttt_warp(Smem &s, int lane) {
     }
 }
 
+// ---- inverse-depth elimination S -= W' W'^T on the tensor cores: the 55 upper 8 x 8 blocks of the 80 x 80 Gram matrix of a staged 80 x 32 tile,
+// dealt to the seven warps 1..7 as row strips (8 blocks each, 7 for the last) so that a warp needs at most nine 8-row fragments per k-step.
+// Everything is compile-time (like TTPlan): the fragments of a k-step sit in DISTINCT registers and the DMMAs issue back to back -- with a
+// run-time block table ptxas re-used one register pair for the operands of all blocks and every DMMA waited for its own two LDS (~119 cycles
+// per DMMA instead of 16 - 32, measured with the phase timers).
+template <int W> struct SCPlan;
+#define CERB_SC_PLAN(W, NR_, NB_, ...) template <> struct SCPlan<W> { static constexpr int nr = NR_, nb = NB_; static CERB_HD int tab(int i) { constexpr int t[] = {__VA_ARGS__}; return t[i]; } };
+//            block rows (padded to 9)          block -> first row index     block -> second row index
+CERB_SC_PLAN(0, 8, 8, 0, 1, 2, 3, 4, 5, 6, 7, 0,   0, 0, 0, 0, 0, 0, 0, 0,   0, 1, 2, 3, 4, 5, 6, 7)      // (0,0) .. (0,7)
+CERB_SC_PLAN(1, 9, 8, 0, 8, 9, 1, 2, 3, 4, 5, 6,   0, 0, 3, 3, 3, 3, 3, 3,   1, 2, 3, 4, 5, 6, 7, 8)      // (0,8) (0,9) (1,1) .. (1,6)
+CERB_SC_PLAN(2, 9, 8, 1, 7, 8, 9, 2, 3, 4, 5, 6,   0, 0, 0, 4, 4, 4, 4, 4,   1, 2, 3, 4, 5, 6, 7, 8)      // (1,7) .. (1,9) (2,2) .. (2,6)
+CERB_SC_PLAN(3, 8, 8, 2, 7, 8, 9, 3, 4, 5, 6, 0,   0, 0, 0, 4, 4, 4, 4, 4,   1, 2, 3, 4, 5, 6, 7, 1)      // (2,7) .. (2,9) (3,3) .. (3,7)
+CERB_SC_PLAN(4, 7, 8, 3, 8, 9, 4, 5, 6, 7, 0, 0,   0, 0, 3, 3, 3, 3, 3, 3,   1, 2, 3, 4, 5, 6, 1, 2)      // (3,8) (3,9) (4,4) .. (4,9)
+CERB_SC_PLAN(5, 5, 8, 5, 6, 7, 8, 9, 0, 0, 0, 0,   0, 0, 0, 0, 0, 1, 1, 1,   0, 1, 2, 3, 4, 1, 2, 3)      // (5,5) .. (5,9) (6,6) .. (6,8)
+CERB_SC_PLAN(6, 4, 7, 6, 7, 8, 9, 0, 0, 0, 0, 0,   0, 1, 1, 1, 2, 2, 3, 0,   3, 1, 2, 3, 2, 3, 3, 0)      // (6,9) (7,7) .. (7,9) (8,8) (8,9) (9,9)
+enum { SC_LDW = 36 };
+template <int W> CERB_D void schur_tile(const double *tw, double (&acc)[8][2], int lane) {
+    typedef SCPlan<W> PL;
+    const double *pr[9];
+    _Pragma("unroll")
+    for (int u = 0; u < 9; u++) pr[u] = tw + (8 * PL::tab(u < PL::nr ? u : 0) + (lane >> 2)) * SC_LDW + (lane & 3);
+    double fv[9];
+    _Pragma("unroll")
+    for (int u = 0; u < 9; u++) fv[u] = (u < PL::nr) ? pr[u][0] : 0.0;
+    _Pragma("unroll")
+    for (int ks = 0; ks < 8; ks++) {
+        double fn[9];
+        _Pragma("unroll")
+        for (int u = 0; u < 9; u++) fn[u] = (u < PL::nr && ks < 7) ? pr[u][4 * (ks + 1)] : 0.0;      // operands one k-step ahead
+        _Pragma("unroll")
+        for (int k = 0; k < 8; k++) if (k < PL::nb) CERB_DMMA(acc[k][0], acc[k][1], fv[PL::tab(9 + k)], fv[PL::tab(17 + k)], acc[k][0], acc[k][1]);
+        _Pragma("unroll")
+        for (int u = 0; u < 9; u++) fv[u] = fn[u];
+    }
+}
+template <int W> CERB_D void schur_scatter(Smem &s, const double (&acc)[8][2], int lane) {
+    typedef SCPlan<W> PL;
+    _Pragma("unroll")
+    for (int k = 0; k < 8; k++) {
+        if (k >= PL::nb) continue;
+        const int a = 8 * PL::tab(PL::tab(9 + k)) + (lane >> 2);
+        for (int e = 0; e < 2; e++) {
+            const int b = 8 * PL::tab(PL::tab(17 + k)) + 2 * (lane & 3) + e;
+            if (a > b || a >= NX || b > NX) continue;
+            if (b == NX) s.yv[a] -= acc[k][e];            // rhs_x
+            else { s.Hxx[b * NX + a] -= acc[k][e]; if (a != b) s.Hxx[a * NX + b] -= acc[k][e]; }
+        }
+    }
+}
+
 // prior Hessian image (J0^T J0 scattered into the layout of Hxx | Hxy | Ad | Bo) in global memory + the column -> destination map of
 // the prior in s.ti[0..n); returns whether the window has a prior
 CERB_D bool build_prior_image(const SolveParams &P, Smem &s, int w, double *pimg, int tid) {
@@ -1174,7 +1224,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, CERB_SOLVE_MIN_BLOCKS) vilo_so
                         // The 55 upper 8x8 blocks of the 80x80 Gram matrix are dealt round-robin to the 7 warps.
                         const int t2 = tid - 32, n2 = SOLVE_THREADS - 32;
                         const int wq = (tid >> 5) - 1, lane = tid & 31;
-                        const int LDW = 36;
+                        const int LDW = SC_LDW;
                         double *tw = s.Ju;                         // 80 x 36 tile (aliases Ju .. red, unused during the solve)
                         double *sinv = nF <= 1024 ? s.wj : lamc + F;   // 1 / sqrt(h + mu D^2): shared memory (wj: 1024 doubles) up to the reference's NUM_OF_F,
                                                                        // the ninth workspace vector for the larger synthetic stress windows
@@ -1196,14 +1246,8 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, CERB_SOLVE_MIN_BLOCKS) vilo_so
                         PH_MARK_T(19, 32);
                         for (int f = t2; f < nF; f += n2) sinv[f] = rsqrt(hh[f] + mu * Dl[f] * Dl[f]);
                         double acc[8][2];
+                        _Pragma("unroll")
                         for (int k = 0; k < 8; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
-                        int tmi[8], tni[8];
-                        for (int k = 0; k < 8; k++) {
-                            int idx = wq + 7 * k, mi = 0;
-                            if (idx >= 55) { tmi[k] = -1; tni[k] = 0; continue; }
-                            while (idx >= 10 - mi) { idx -= 10 - mi; mi++; }
-                            tmi[k] = mi; tni[k] = mi + idx;
-                        }
                         CERB_BAR_SYNC(1, n2);
                         // raw W / g_l values of a tile are fetched into registers one tile ahead (12 per thread: the loads are issued
                         // together and stay in flight during the tensor-core loop), scaled and stored when the tile buffer is free
@@ -1228,27 +1272,26 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, CERB_SOLVE_MIN_BLOCKS) vilo_so
                             CERB_BAR_SYNC(1, n2);
                             PH_MARK_T(38, 32);
                             if (f0 + 32 < nF) fetch(f0 + 32);
-                            for (int ks = 0; ks < 8; ks++) {
-                                const int col = 4 * ks + (lane & 3);
-                                for (int k = 0; k < 8; k++) {
-                                    if (tmi[k] < 0) continue;              // warp-uniform
-                                    const double av = tw[(8 * tmi[k] + (lane >> 2)) * LDW + col];
-                                    const double bv = tw[(8 * tni[k] + (lane >> 2)) * LDW + col];
-                                    CERB_DMMA(acc[k][0], acc[k][1], av, bv, acc[k][0], acc[k][1]);
-                                }
+                            switch (wq) {                                  // warp-uniform; block plan per warp: SCPlan
+                                case 0: schur_tile<0>(tw, acc, lane); break;
+                                case 1: schur_tile<1>(tw, acc, lane); break;
+                                case 2: schur_tile<2>(tw, acc, lane); break;
+                                case 3: schur_tile<3>(tw, acc, lane); break;
+                                case 4: schur_tile<4>(tw, acc, lane); break;
+                                case 5: schur_tile<5>(tw, acc, lane); break;
+                                default: schur_tile<6>(tw, acc, lane); break;
                             }
                             CERB_BAR_SYNC(1, n2);
                             PH_MARK_T(39, 32);
                         }
-                        for (int k = 0; k < 8; k++) {
-                            if (tmi[k] < 0) continue;
-                            const int a = 8 * tmi[k] + (lane >> 2);
-                            for (int e = 0; e < 2; e++) {
-                                const int b = 8 * tni[k] + 2 * (lane & 3) + e;
-                                if (a > b || a >= NX || b > NX) continue;
-                                if (b == NX) s.yv[a] -= acc[k][e];            // rhs_x
-                                else { s.Hxx[b * NX + a] -= acc[k][e]; if (a != b) s.Hxx[a * NX + b] -= acc[k][e]; }
-                            }
+                        switch (wq) {
+                            case 0: schur_scatter<0>(s, acc, lane); break;
+                            case 1: schur_scatter<1>(s, acc, lane); break;
+                            case 2: schur_scatter<2>(s, acc, lane); break;
+                            case 3: schur_scatter<3>(s, acc, lane); break;
+                            case 4: schur_scatter<4>(s, acc, lane); break;
+                            case 5: schur_scatter<5>(s, acc, lane); break;
+                            default: schur_scatter<6>(s, acc, lane); break;
                         }
                         PH_MARK_T(7, 32);
                         // ---- T = L^-1 Hyx (row a of Hxy in place; row 79: the y part of the rhs), rows on threads 32..111: block f
