@@ -1221,7 +1221,7 @@ CERB_GLOBAL void __launch_bounds__(SOLVE_THREADS, CERB_SOLVE_MIN_BLOCKS) vilo_so
                         //   S = Hxx - W' W'^T,  rhs_x -= W' (w g_l),  W'[a][f] = W[a][f] / sqrt(h_f + mu D_f^2)
                         // W' is staged through shared memory 32 features at a time as an 80-row tile whose row 78 carries
                         // g_l / sqrt(h + mu D^2) (so that column 78 of the Gram matrix is the rhs update) and row 79 is zero.
-                        // The 55 upper 8x8 blocks of the 80x80 Gram matrix are dealt round-robin to the 7 warps.
+                        // The 55 upper 8x8 blocks of the 80x80 Gram matrix go to the 7 warps as row strips (SCPlan, compile-time).
                         const int t2 = tid - 32, n2 = SOLVE_THREADS - 32;
                         const int wq = (tid >> 5) - 1, lane = tid & 31;
                         const int LDW = SC_LDW;
