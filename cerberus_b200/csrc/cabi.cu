@@ -943,6 +943,7 @@ int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindow
     CUDA_TRY(cudaMemcpyAsync(hx0.data(), h->d_px0, hx0.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     std::vector<double> oldJ, oldr;
+    std::vector<StageJob> out_jobs; out_jobs.reserve(n);
     for (int w = 0; w < n; w++) if (hdims[4 * w + 2] == 1 && (hdims[4 * w] > mmax || hdims[4 * w + 1] > nmax)) return fail(CERB_ERR_BAD_ARGUMENT, "cerb_batch_marginalize: a window exceeds the structural size of the kept / dropped blocks");
     for (int w = 0; w < n; w++) {
         CerbPrior &pr = priors[w];
@@ -975,9 +976,10 @@ int cerb_batch_marginalize(CerbHandle *h, const int32_t *flags, const CerbWindow
             const double *x = st + prior_block_state_offset(q[0], q[3]);          // keep_block_data: the state the factors were linearised at
             for (int k = 0; k < 9; k++) pr.block_x0[b][k] = k < size ? x[k] : 0.0;
         }
-        std::memcpy(Jout, hJ + (size_t)w * PRIOR_LD * PRIOR_LD, (size_t)nn * nn * 8);
+        out_jobs.push_back({Jout, hJ + (size_t)w * PRIOR_LD * PRIOR_LD, (size_t)nn * nn * 8});       // 59 KB per window: copied by a few threads below
         std::memcpy(rout, hr + (size_t)w * PRIOR_LD, (size_t)nn * 8);
     }
+    run_stage_jobs(out_jobs);
     return CERB_OK;
 }
 
