@@ -547,19 +547,19 @@ int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, Cerb
     const int MAXC = CerbHandle::MAX_CHUNKS;
     int NL = 3, first = 64;
     if (const char *e = std::getenv("CERB_PIPE_LANES")) NL = std::min((int)CerbHandle::LANES, std::max(1, std::atoi(e)));       // tuning knobs of the measurement in DESIGN.md 2.4
-    if (const char *e = std::getenv("CERB_PIPE_FIRST")) first = std::max(16, std::atoi(e));
+    if (const char *e = std::getenv("CERB_PIPE_FIRST")) first = std::max(1, std::atoi(e));
     int bounds[CerbHandle::MAX_CHUNKS + 1], nch = 0; bounds[0] = 0;
     if (const char *e = std::getenv("CERB_TEST_CHUNK")) {              // test hook: the multi-chunk / multi-lane path on a handful of windows
         const int per = std::max(std::max(1, std::atoi(e)), (n + MAXC - 1) / MAXC);
         for (int pos = 0; pos < n; ) { pos = std::min(n, pos + per); bounds[++nch] = pos; }
-    } else if (n <= 96) { bounds[1] = n; nch = 1; }
+    } else if (n <= first + first / 2) { bounds[1] = n; nch = 1; }
     else {
-        int cap = 256;
-        if ((n + cap - 1) / cap > MAXC - 8) cap = (((n + MAXC - 9) / (MAXC - 8)) + 63) / 64 * 64;
+        int cap = 4 * first;
+        if ((n + cap - 1) / cap > MAXC - 8) cap = (((n + MAXC - 9) / (MAXC - 8)) + first - 1) / first * first;
         int pos = 0, sz = first, k = 0;
         while (pos < n) {
             int take = std::min(sz, n - pos);
-            if (n - pos - take < 32 || nch == MAXC - 1) take = n - pos;  // no crumbs; never more than MAXC chunks
+            if (n - pos - take < first / 2 || nch == MAXC - 1) take = n - pos;  // no crumbs; never more than MAXC chunks
             pos += take; bounds[++nch] = pos;
             if (++k >= 2) sz = std::min(cap, 2 * sz);
         }

@@ -299,6 +299,25 @@ def test_host_buffer_pipeline_chunks(monkeypatch):
     assert (rep["final_cost"][3:6] == rep["final_cost"][0:3]).all() and (rep["status"] == 0).all()
 
 
+def test_host_buffer_pipeline_ramp(monkeypatch):
+    """the shipped chunk schedule (first, first, 2 first, 4 first, ...; here first = 2 through the tuning knob: 9 windows -> 2, 2, 4, 1 on three lanes,
+    lane 0 carries two chunks) against the single-chunk solve of the same batch: bit-identical states and reports"""
+    cfg = small_cfg(max_batch=16, max_features=8, iters=1)
+    s = sim_backend(cfg)
+    base = synth.generate_batch(3, 4, ob, window0=145, prior_features=4)
+    one = synth.tile_batch(base, 9); ramp = synth.tile_batch(base, 9)
+    rep_one = s.solve_batch(one)
+    assert s.last_solve_stats()[1] == 4 * 1 + 1
+    monkeypatch.setenv("CERB_PIPE_FIRST", "2")
+    rep_ramp = s.solve_batch(ramp)
+    assert s.last_solve_stats()[1] == 4 * 4 + 1
+    sa, sb = one.state_array(), ramp.state_array()
+    for name in ("para_Pose", "para_SpeedBias", "para_LegBias", "para_Ex_Pose", "para_Td"):
+        assert (sa[name] == sb[name]).all(), name
+    assert (one.para_Feature == ramp.para_Feature).all()
+    assert (rep_one["final_cost"] == rep_ramp["final_cost"]).all() and (rep_one["iterations"] == rep_ramp["iterations"]).all()
+
+
 def test_registered_host_buffers_take_the_zero_copy_path():
     _registered_buffers_case(sim_backend, 16, 9, 3)
 
