@@ -196,9 +196,9 @@ def test_edge_windows_gpu():
 
 def test_registered_host_buffers_gpu():
     """Zero-copy path with REAL page-locked memory (cudaHostRegister) and merged 2-D DMA: bit-identical to the staged path, nothing staged;
-    444 windows -> 7 pipeline chunks of 64 on three compute lanes."""
+    444 windows -> 4 pipeline chunks (64, 64, 128, 188) on three compute lanes."""
     from test_cusim_kernels import _registered_buffers_case
-    _registered_buffers_case(lambda cfg: lib.Backend(cfg), 512, 444, 7, iters=2)
+    _registered_buffers_case(lambda cfg: lib.Backend(cfg), 512, 444, 4, iters=2)
 
 
 def test_marginalization_of_imu_only_windows_gpu():
