@@ -90,3 +90,28 @@ def test_integration_stub_compiles_against_the_header_and_reference_headers():
     r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "shim"),
                         "-I/root/reference/src", os.path.join(ROOT, "tools", "integration_stub.cpp")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_update_states_and_schur_argument_checks():
+    """cerb_batch_update_states needs a resident batch of exactly n windows; cerb_marginalize_schur bounds m by what a window can drop"""
+    import numpy as np
+    from cerberus_b200 import synth
+    from oracle_lib import OracleBackend
+    from helpers import small_cfg
+    cfg = small_cfg()
+    sb = sim_backend(cfg)
+    batch = synth.generate_batch(2, 6, OracleBackend(cfg), with_prior=False)
+    with pytest.raises(lib.CerbError) as e:
+        sb.update_states(batch)                          # nothing resident yet
+    assert e.value.code == abi.ERR_BAD_ARGUMENT
+    sb.upload(batch)
+    one = synth.tile_batch(batch, 1)
+    with pytest.raises(lib.CerbError) as e:
+        sb.update_states(one)                            # wrong window count
+    assert e.value.code == abi.ERR_BAD_ARGUMENT
+    sb.update_states(batch)
+    A = np.eye(8)[None]; b = np.zeros((1, 8))
+    with pytest.raises(lib.CerbError):
+        sb.marginalize_schur(np.eye(2100 + 4)[None], np.zeros((1, 2104)), 2100)       # m > 19 + CERB_MAX_FEATURES
+    J, r = sb.marginalize_schur(A, b, 3)
+    assert J.shape == (1, 5, 5)
