@@ -571,13 +571,15 @@ int cerb_solve_batch(CerbHandle *h, int32_t n, const CerbWindowDesc *descs, Cerb
     const double t_begin = now(); double t_stage = 0.0;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     for (int l = 1; l < NL; l++) CUDA_TRY(cudaStreamWaitEvent(h->lane[l], h->ev0, 0));
+    // a descriptor rejected in a later chunk: drain what the earlier chunks have in flight before the caller sees the error (its buffers may go away)
+    auto drain = [&](int code) { for (int l = 0; l < NL; l++) cudaStreamSynchronize(h->lane[l]); cudaStreamSynchronize(h->copy_stream); return code; };
     for (int c = 0; c < nch; c++) {
         const int w0 = bounds[c], cn = bounds[c + 1] - bounds[c], l = c % NL;
-        rc = upload_raw(h, w0, cn, descs, states, h->copy_stream, &t_stage); if (rc) return rc;
+        rc = upload_raw(h, w0, cn, descs, states, h->copy_stream, &t_stage); if (rc) return drain(rc);
         CUDA_TRY(cudaEventRecord(h->ev_copy[c], h->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(h->lane[l], h->ev_copy[c], 0));
-        rc = enqueue_pack(h, w0, cn, h->lane[l]); if (rc) return rc;
-        rc = enqueue_solve(h, w0, cn, h->cfg.max_num_iterations, nullptr, -1, true, false, l); if (rc) return rc;
+        rc = enqueue_pack(h, w0, cn, h->lane[l]); if (rc) return drain(rc);
+        rc = enqueue_solve(h, w0, cn, h->cfg.max_num_iterations, nullptr, -1, true, false, l); if (rc) return drain(rc);
     }
     for (int l = 1; l < NL; l++) { CUDA_TRY(cudaEventRecord(h->ev_lane[l], h->lane[l])); CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_lane[l], 0)); }
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream)); h->ev_pending = true; h->last_launches = 4 * nch + 1;      // + the unpack kernel of the download

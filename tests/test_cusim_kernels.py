@@ -318,6 +318,24 @@ def test_host_buffer_pipeline_ramp(monkeypatch):
     assert (rep_one["final_cost"] == rep_ramp["final_cost"]).all() and (rep_one["iterations"] == rep_ramp["iterations"]).all()
 
 
+def test_bad_descriptor_in_a_later_chunk(monkeypatch):
+    """a malformed window in the third chunk: the call fails with CERB_ERR_BAD_ARGUMENT after draining the chunks already in flight, and the handle
+    stays usable"""
+    from cerberus_b200 import lib as _lib
+    monkeypatch.setenv("CERB_TEST_CHUNK", "2")
+    cfg = small_cfg(max_batch=16, max_features=8, iters=1)
+    s = sim_backend(cfg)
+    base = synth.generate_batch(3, 4, ob, with_prior=False, window0=160)
+    big = synth.tile_batch(base, 6)
+    big.descs[5].n_features = cfg.max_features + 1
+    with pytest.raises(_lib.CerbError) as e:
+        s.solve_batch(big)
+    assert e.value.code == abi.ERR_BAD_ARGUMENT
+    big.descs[5].n_features = base.descs[2].n_features
+    rep = s.solve_batch(big)
+    assert (rep["status"] == 0).all() and (rep["final_cost"][3:] == rep["final_cost"][:3]).all()
+
+
 def test_registered_host_buffers_take_the_zero_copy_path():
     _registered_buffers_case(sim_backend, 16, 9, 3)
 
